@@ -1,0 +1,182 @@
+"""Oracle: one SQP(-RTI) iteration of the sdf-nmpc OCP, batched numpy float64.
+
+TEST INFRASTRUCTURE - see ``oracle/__init__.py``.  **Parity unpinned** for the
+acados semantics (third-party, source not in the reference tree): the choices
+below restate SURVEY.md section 8a-5 [from memory of acados 0.3.1] and define what
+"the reference QP" means for this repository:
+
+  1. stage cost 1/2||y-yref||^2_W, its Gauss-Newton Hessian/gradient and the slack
+     penalties are scaled by the stage length Ts_k; terminal scaling 1
+     (``ocp.py:54-61,85-92``; acados cost "scaling").
+  2. Levenberg-Marquardt: + Ts_k*lm*I on the (nu+nx) stage block, + lm*I at N
+     (``ocp.py:119-120``).
+  3. QP variables per stage [du; dx]; dx_0 = x0 - xbar_0 (``ocp.py:160-161,169``).
+  4. nonlinear rows h (hfov, vfov, sdf - order ``gen_model.py:42,68``) at nodes
+     1..N-1 and N; none at node 0 (switch ``h_at_node0``).
+  5. soft rows: lh <= h + s_l, h - s_u <= uh, s >= 0, penalty z's + 1/2 s'Zs
+     (``base_model.py:142-168``; ``default.yaml:49-50``).
+  6. ERK4, one step per interval, exact sensitivities of the discrete map.
+  7. full step, no globalisation; status = QP status.
+The QP is condensed to the N*nu inputs (``FULL_CONDENSING_HPIPM``, ``ocp.py:113``)
+and solved by ``oracle.qp.solve_dense``.
+"""
+import numpy as np
+
+from . import model_att as M
+from . import qp as QP
+from . import sdf as SDF
+
+
+def default_cfg():
+    c = dict(M.DEFAULT)
+    c.update(N=20, T=1.5, lm=10.0, lbu=np.array([0.0, -1, -1, -1]), ubu=np.array([1.0, 1, 1, 1]),
+             slack_df=(200.0, 50.0), slack_fov=(20.0, 0.0), size_xy=0.22, bound_margin=0.15,
+             h_at_node0=False, qp_tol=1e-8, qp_iter_max=100)
+    c['dt'] = np.full(c['N'], c['T'] / c['N'])
+    return c
+
+
+def h_bounds(cfg, max_df):
+    """(lh, uh) for [hfov, vfov, sdf]  (cost_const_helpers.py:67-75, gen_model.py:35)."""
+    hl, vl = cfg['hfov'] * cfg['fov_ratio'], cfg['vfov'] * cfg['fov_ratio']
+    return (np.array([-hl, -vl, cfg['size_xy'] + cfg['bound_margin']]), np.array([hl, vl, max_df + 0.2]))
+
+
+def slack_weights(cfg):
+    """(z [3], Z [3]) in h order (ocp.py:85-92)."""
+    return (np.array([cfg['slack_fov'][0], cfg['slack_fov'][0], cfg['slack_df'][0]]),
+            np.array([cfg['slack_fov'][1], cfg['slack_fov'][1], cfg['slack_df'][1]]))
+
+
+def init_traj(x0, cfg):
+    """ocp.py:144-149: x_k = x0, u_k = u_hover."""
+    B, N = x0.shape[0], cfg['N']
+    xb = np.repeat(x0[:, None, :], N + 1, 1).copy()
+    ub = np.zeros((B, N, 4))
+    ub[:, :, 0] = cfg['g'] / cfg['gamma']
+    return xb, ub
+
+
+def eval_h(net, xk, prob, cfg):
+    """h [B,3] and dh/dp [B,3,3] at one node."""
+    flag = prob['flag']
+    hf, Jf = M.h_fov(xk, prob['W_p_Co'], prob['W_R_Co'], flag, cfg)
+    c0 = M.sdf_query(xk, prob['W_p_Co'], prob['W_R_Co'])
+    # the network runs in float32 behind a double interface (L4CasADi)
+    d, gs = SDF.value_and_grad(net, c0.astype(np.float32), prob['latent'], dtype=prob.get('sdf_dtype', np.float32))
+    d, gs = d.astype(np.float64), gs.astype(np.float64)
+    h3 = flag * d + (1.0 - flag) * net['max_df']
+    J3 = flag[:, None] * np.einsum('bc,bpc->bp', gs, prob['W_R_Co'])
+    return np.concatenate([hf, h3[:, None]], 1), np.concatenate([Jf, J3[:, None, :]], 1)
+
+
+def linearize(net, xb, ub, prob, cfg):
+    """All stage quantities of the OCP-QP at (xb, ub)."""
+    B, N = xb.shape[0], cfg['N']
+    dt = cfg['dt']
+    A = np.zeros((B, N, 10, 10)); Bm = np.zeros((B, N, 10, 4)); b = np.zeros((B, N, 10))
+    H = np.zeros((B, N, 14, 14)); g = np.zeros((B, N, 14))
+    C = np.zeros((B, N + 1, 3, 10)); hbar = np.zeros((B, N + 1, 3))
+    for k in range(N):
+        xn, A[:, k], Bm[:, k] = M.rk4_sens(xb[:, k], ub[:, k], dt[k], cfg)
+        b[:, k] = xn - xb[:, k + 1]
+        y, J = M.y_fun(xb[:, k], ub[:, k], prob['qd'][:, k], cfg)
+        Wk = prob['W'][:, k]
+        H[:, k] = dt[k] * (np.einsum('byi,by,byj->bij', J, Wk, J) + cfg['lm'] * np.eye(14)[None])
+        g[:, k] = dt[k] * np.einsum('byi,by->bi', J, Wk * (y - prob['yref'][:, k]))
+    yN, JN = M.y_fun(xb[:, N], np.zeros((B, 4)), prob['qd'][:, N], cfg)
+    yN, JN = yN[:, :4], JN[:, :4, 4:]
+    HN = np.einsum('byi,by,byj->bij', JN, prob['WN'], JN) + cfg['lm'] * np.eye(10)[None]
+    gN = np.einsum('byi,by->bi', JN, prob['WN'] * (yN - prob['yrefN']))
+    k0 = 0 if cfg['h_at_node0'] else 1
+    for k in range(k0, N + 1):
+        hbar[:, k], Jp = eval_h(net, xb[:, k], prob, cfg)
+        C[:, k, :, 0:3] = Jp
+    return dict(A=A, B=Bm, b=b, H=H, g=g, HN=HN, gN=gN, C=C, hbar=hbar, k0=k0)
+
+
+def condense(lin, xb, ub, prob, cfg, max_df):
+    """Dense QP in U = (du_0..du_{N-1}) with the row list used for active-set comparison:
+    rows = [u lower (N*4), u upper (N*4), h lower (nodes k0..N, 3 each), h upper (same)]."""
+    B, N = xb.shape[0], cfg['N']
+    nv = 4 * N
+    Gam = np.zeros((B, N + 1, 10, nv)); gam = np.zeros((B, N + 1, 10))
+    gam[:, 0] = prob['x0'] - xb[:, 0]
+    for k in range(N):
+        Gam[:, k + 1] = lin['A'][:, k] @ Gam[:, k]
+        Gam[:, k + 1, :, 4 * k:4 * k + 4] += lin['B'][:, k]
+        gam[:, k + 1] = np.einsum('bij,bj->bi', lin['A'][:, k], gam[:, k]) + lin['b'][:, k]
+    P = np.zeros((B, nv, nv)); q = np.zeros((B, nv))
+    for k in range(N):
+        T = np.zeros((B, 14, nv)); T[:, np.arange(4), 4 * k + np.arange(4)] = 1.0; T[:, 4:] = Gam[:, k]
+        t = np.concatenate([np.zeros((B, 4)), gam[:, k]], 1)
+        HT = lin['H'][:, k] @ T
+        P += np.swapaxes(T, 1, 2) @ HT
+        q += np.einsum('bin,bi->bn', T, np.einsum('bij,bj->bi', lin['H'][:, k], t) + lin['g'][:, k])
+    TN = Gam[:, N]
+    P += np.swapaxes(TN, 1, 2) @ lin['HN'] @ TN
+    q += np.einsum('bin,bi->bn', TN, np.einsum('bij,bj->bi', lin['HN'], gam[:, N]) + lin['gN'])
+    P = 0.5 * (P + np.swapaxes(P, 1, 2))
+    lh, uh = h_bounds(cfg, max_df)
+    zl, Zl = slack_weights(cfg)
+    k0 = lin['k0']
+    nk = N + 1 - k0
+    I = np.broadcast_to(np.eye(nv), (B, nv, nv))
+    ubar = ub.reshape(B, nv)
+    rows_G = [I, -I]
+    rows_d = [np.tile(cfg['lbu'], N)[None] - ubar, -(np.tile(cfg['ubu'], N)[None] - ubar)]
+    CG = np.einsum('bkrx,bkxn->bkrn', lin['C'][:, k0:], Gam[:, k0:]).reshape(B, nk * 3, nv)
+    Cg = np.einsum('bkrx,bkx->bkr', lin['C'][:, k0:], gam[:, k0:]).reshape(B, nk * 3)
+    hb = lin['hbar'][:, k0:].reshape(B, nk * 3)
+    rows_G += [CG, -CG]
+    rows_d += [np.tile(lh, nk)[None] - hb - Cg, -(np.tile(uh, nk)[None] - hb - Cg)]
+    G = np.concatenate(rows_G, 1); d = np.concatenate(rows_d, 1)
+    soft = np.concatenate([np.zeros(2 * nv, bool), np.ones(2 * nk * 3, bool)])
+    # slack penalties of stage rows (nodes k0..N-1) are scaled by Ts_k, terminal rows by 1
+    sc = np.concatenate([np.repeat(cfg['dt'][k0:N], 3), np.ones(3)])
+    zz = np.concatenate([np.zeros(2 * nv), np.tile(zl, nk) * sc, np.tile(zl, nk) * sc])
+    ZZ = np.concatenate([np.zeros(2 * nv), np.tile(Zl, nk) * sc, np.tile(Zl, nk) * sc])
+    return dict(P=P, q=q, G=G, d=d, soft=soft, z=zz, Z=ZZ, Gam=Gam, gam=gam, nk=nk)
+
+
+def rti_step(net, xb, ub, prob, cfg):
+    """One SQP-RTI iteration (preparation + feedback).  Returns new (xb, ub) and diagnostics."""
+    B, N = xb.shape[0], cfg['N']
+    lin = linearize(net, xb, ub, prob, cfg)
+    cq = condense(lin, xb, ub, prob, cfg, net['max_df'])
+    sol = QP.solve_dense(cq['P'], cq['q'], cq['G'], cq['d'], cq['soft'], cq['z'], cq['Z'],
+                         tol=cfg['qp_tol'], max_iter=cfg['qp_iter_max'])
+    U = sol['v']
+    dx = np.einsum('bkxn,bn->bkx', cq['Gam'], U) + cq['gam']
+    xn = xb + dx
+    un = ub + U.reshape(B, N, 4)
+    nv, nk = 4 * N, cq['nk']
+    lam = sol['lam']
+    out = dict(u0=un[:, 0].copy(), status=sol['status'], qp_iters=sol['iters'],
+               lam_lbu=lam[:, :nv].reshape(B, N, 4), lam_ubu=lam[:, nv:2 * nv].reshape(B, N, 4),
+               lam_lh=lam[:, 2 * nv:2 * nv + 3 * nk].reshape(B, nk, 3), lam_uh=lam[:, 2 * nv + 3 * nk:].reshape(B, nk, 3),
+               slack_l=sol['s'][:, 2 * nv:2 * nv + 3 * nk].reshape(B, nk, 3), slack_u=sol['s'][:, 2 * nv + 3 * nk:].reshape(B, nk, 3),
+               du=U.reshape(B, N, 4), dx=dx, lin=lin, qp=cq)
+    return xn, un, out
+
+
+def active_set(out, thr=1e-6):
+    """Boolean masks of active rows: multiplier > thr*max(1, max multiplier)."""
+    allm = np.concatenate([out[k].reshape(out[k].shape[0], -1) for k in ('lam_lbu', 'lam_ubu', 'lam_lh', 'lam_uh')], 1)
+    ref = thr * np.maximum(1.0, allm.max(1))
+    return {k: out[k] > ref.reshape((-1,) + (1,) * (out[k].ndim - 1)) for k in ('lam_lbu', 'lam_ubu', 'lam_lh', 'lam_uh')}
+
+
+def closed_loop(net, prob, cfg, steps, plant_dt=None, move_ref=True):
+    """RK4 plant = same model; SQP-RTI once per control step, warm start = previous solution (shift 0)."""
+    x = prob['x0'].copy()
+    xb, ub = init_traj(x, cfg)
+    plant_dt = cfg['dt'][0] if plant_dt is None else plant_dt
+    hist = []
+    p = dict(prob)
+    for _ in range(steps):
+        p['x0'] = x
+        xb, ub, out = rti_step(net, xb, ub, p, cfg)
+        hist.append(dict(x=x.copy(), u0=out['u0'].copy(), status=out['status'].copy()))
+        x = M.rk4(x, out['u0'], plant_dt, cfg)
+    return x, xb, ub, hist

@@ -1,0 +1,94 @@
+// Stage-wise linearisation of the sdf-nmpc OCP around the current SQP iterate.
+//
+// One call handles ONE tangent direction `dir` (column of [du; dx]) of ONE shooting
+// node of ONE instance: it propagates a dual number through the ERK4 step, the NLS
+// outputs and the FoV rows and writes column `dir` of [B|A], J and C.  This is the
+// role of acados' per-node calls to the CasADi-generated expl_vde_forw,
+// cost_y_fun_jac_ut_xt and constr_h_fun_jac_uxt_zt (sdf_nmpc/ocp.py:106-120).
+#pragma once
+#include "model_att.cuh"
+
+namespace sdfnmpc {
+
+struct LinIn {           // device pointers, whole batch
+    const double* xbar;  // [B][N+1][NX]
+    const double* ubar;  // [B][N][NU]
+    const double* yref;  // [B][N][NY]
+    const double* yrefN; // [B][NYN]
+    const double* qd;    // [B][N+1][4]
+    const double* pose;  // [B][12]
+    const double* flag;  // [B]
+    const double* dt;    // [N]
+};
+
+struct LinOut {
+    double* AB;    // [B][N][NX][NW]   columns ordered [u; x]
+    double* bdyn;  // [B][N][NX]       phi(xbar_k, ubar_k) - xbar_{k+1}
+    double* J;     // [B][N+1][NY][NW]
+    double* yres;  // [B][N+1][NY]     y - yref (terminal rows >= NYN are zero)
+    double* C;     // [B][N+1][NH][NW] rows 0,1 = FoV; row 2 (sdf) is filled by the QP prologue
+    double* hval;  // [B][N+1][NH]
+    float* qpts;   // [B][N+1][3]      SDF query points Co_p_B (float32, as L4CasADi casts)
+};
+
+SDF_HD void linearize_dir(const ModelConst& mc, int N, const LinIn& in, const LinOut& out, int b, int k, int dir) {
+    constexpr int NX = ATT_NX, NU = ATT_NU, NW = ATT_NW, NY = ATT_NY, NH = ATT_NH;
+    const double* x = in.xbar + ((size_t)b * (N + 1) + k) * NX;
+    Dual xd[NX], ud[NU];
+    for (int i = 0; i < NX; ++i) xd[i] = Dual(x[i], (dir - NU) == i ? 1.0 : 0.0);
+    if (k < N) {
+        const double* u = in.ubar + ((size_t)b * N + k) * NU;
+        for (int j = 0; j < NU; ++j) ud[j] = Dual(u[j], dir == j ? 1.0 : 0.0);
+    } else {
+        for (int j = 0; j < NU; ++j) ud[j] = Dual(0.0, 0.0);
+    }
+    const size_t node = (size_t)b * (N + 1) + k;
+    if (k < N) {
+        Dual xn[NX];
+        rk4_step(mc, xd, ud, in.dt[k], xn);
+        double* AB = out.AB + ((size_t)b * N + k) * NX * NW;
+        for (int i = 0; i < NX; ++i) AB[i * NW + dir] = xn[i].d;
+        if (dir == 0) {
+            const double* x1 = x + NX;
+            double* bd = out.bdyn + ((size_t)b * N + k) * NX;
+            for (int i = 0; i < NX; ++i) bd[i] = xn[i].v - x1[i];
+        }
+    }
+    {
+        Dual y[NY];
+        y_att(mc, xd, ud, in.qd + node * 4, y);
+        double* J = out.J + node * NY * NW;
+        for (int r = 0; r < NY; ++r) J[r * NW + dir] = y[r].d;
+        if (dir == 0) {
+            double* yr = out.yres + node * NY;
+            if (k < N) {
+                const double* ref = in.yref + ((size_t)b * N + k) * NY;
+                for (int r = 0; r < NY; ++r) yr[r] = y[r].v - ref[r];
+            } else {
+                const double* ref = in.yrefN + (size_t)b * ATT_NYN;
+                for (int r = 0; r < NY; ++r) yr[r] = r < ATT_NYN ? y[r].v - ref[r] : 0.0;
+            }
+        }
+    }
+    {
+        const double* pose = in.pose + (size_t)b * 12;
+        Dual h[2];
+        hfov_att(mc, pose, in.flag[b], xd, h);
+        double* C = out.C + node * NH * NW;
+        C[0 * NW + dir] = h[0].d;
+        C[1 * NW + dir] = h[1].d;
+        C[2 * NW + dir] = 0.0;
+        if (dir == 0) {
+            out.hval[node * NH + 0] = h[0].v;
+            out.hval[node * NH + 1] = h[1].v;
+            double c0[3];
+            camera_point(pose, x, c0);
+            float* q = out.qpts + node * 3;
+            q[0] = (float)c0[0];
+            q[1] = (float)c0[1];
+            q[2] = (float)c0[2];
+        }
+    }
+}
+
+}  // namespace sdfnmpc

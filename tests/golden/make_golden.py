@@ -1,0 +1,179 @@
+"""Generate the committed golden fixtures from the REFERENCE's own code.
+
+Run only where ``/root/reference`` exists (this container):
+    python tests/golden/make_golden.py
+
+It imports the reference's torch modules (``sdf_nmpc.network.neural_df``,
+``sdf_nmpc.network.vae``, ``sdf_nmpc.utils.preprocessing``) and the numpy
+branches of ``sdf_nmpc.utils.math`` (with a stub ``casadi`` module, which those
+files import but do not need on the numeric path), loads the repo's seeded
+synthetic weights into them and stores inputs' seeds + the reference outputs.
+Weights are NOT stored: they are regenerated from the seed by
+``sdf_nmpc_b200.synth`` (numpy PCG64, platform independent).
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, '/root/reference')
+sys.modules.setdefault('casadi', types.ModuleType('casadi'))
+
+from sdf_nmpc_b200 import synth  # noqa: E402
+
+
+def ref_neural_df(net, dtype=torch.float32):
+    from sdf_nmpc.network.neural_df import NeuralDF
+    sizes = [net['W1'].shape[0], net['W2'].shape[0], net['W3'].shape[0], net['W4'].shape[0]]
+    m = NeuralDF(signed=True, size_latent=net['size_latent'], nb_freqs=net['nb_freqs'], res=net['res'],
+                 embed=net['embed'], act=net['act'], dropout_rate=0.1, w0=net['w0'], layer_sizes=sizes,
+                 max_df=net['max_df'])
+    sd = m.state_dict()
+    sd['layers.main1.0.weight'] = torch.from_numpy(net['W1']); sd['layers.main1.0.bias'] = torch.from_numpy(net['b1'])
+    sd['layers.main1.3.weight'] = torch.from_numpy(net['W2']); sd['layers.main1.3.bias'] = torch.from_numpy(net['b2'])
+    sd['layers.main2.0.weight'] = torch.from_numpy(net['W3']); sd['layers.main2.0.bias'] = torch.from_numpy(net['b3'])
+    sd['layers.main2.3.weight'] = torch.from_numpy(net['W4']); sd['layers.main2.3.bias'] = torch.from_numpy(net['b4'])
+    sd['layers.df.0.weight'] = torch.from_numpy(net['W5']); sd['layers.df.0.bias'] = torch.from_numpy(net['b5'])
+    m.load_state_dict(sd)
+    # the direction table of the synthetic net must be the reference's own buffer
+    assert np.array_equal(m.embed.dirs.numpy(), net['dirs']), 'direction table differs from the reference'
+    return m.to(dtype).eval()
+
+
+def sdf_case(name, n, **kw):
+    net = synth.make_sdf_net(**kw)
+    pts = synth.sdf_query_points(n, seed=3)
+    rng = np.random.default_rng(11)
+    n_lat = 4
+    lat = rng.standard_normal((n_lat, net['size_latent'])).astype(np.float32)
+    idx = (np.arange(n) * n_lat // n).astype(np.int32)
+    x = np.concatenate([pts, lat[idx]], 1)
+    out = {}
+    for dt, tag in ((torch.float32, 'f32'), (torch.float64, 'f64')):
+        m = ref_neural_df(net, dt)
+        xt = torch.from_numpy(x).to(dt).requires_grad_(True)
+        d = m(xt)
+        (g,) = torch.autograd.grad(d.sum(), xt)
+        out['d_' + tag] = d.detach().numpy()[:, 0]
+        out['g_' + tag] = g.detach().numpy()[:, :3]
+    # what L4CasADi executes: batch-1 forward + jacrev (gen_model.py:38-39), first 8 points
+    m32 = ref_neural_df(net, torch.float32)
+    jac = torch.func.jacrev(lambda v: m32(v[None])[0])
+    out['jacrev_f32'] = np.stack([jac(torch.from_numpy(x[i]))[0].detach().numpy() for i in range(8)])
+    # scripted module keeps the attributes the packer reads (gen_model.py:32-35)
+    ts = torch.jit.script(m32)
+    assert float(ts.max_df) == net['max_df'] and ts.res == net['res']
+    np.savez_compressed(os.path.join(HERE, f'sdf_{name}.npz'), n=n, n_lat=n_lat, lat_seed=11, pts_seed=3,
+                        kw=np.array(repr(kw)), **out)
+    print(name, 'd range', out['d_f32'].min(), out['d_f32'].max(),
+          'f32-f64 val', np.abs(out['d_f32'] - out['d_f64']).max() / np.abs(out['d_f64']).max(),
+          'grad', np.abs(out['g_f32'] - out['g_f64']).max() / np.abs(out['g_f64']).max())
+
+
+def ref_encoder(net):
+    from sdf_nmpc.network.vae import Vae
+    vae = Vae(size_latent=net['size_latent'], shape_imgs=[270, 480], dropout_rate=0.1, batchnorm=True)
+    enc = vae.encoder
+    sd = enc.state_dict()
+    t = torch.from_numpy
+    sd['layers.resnet.0.weight'] = t(net['conv0_w']); sd['layers.resnet.0.bias'] = t(net['conv0_b'])
+    for i, blk in enumerate(net['blocks']):
+        p = f'layers.resnet.{3 + i}.'
+        sd[p + 'layers.0.weight'] = t(blk['conv1_w'])
+        sd[p + 'layers.3.weight'] = t(blk['conv2_w'])
+        for j, key in ((1, 'bn1'), (4, 'bn2')):
+            sd[p + f'layers.{j}.weight'] = t(blk[key]['weight']); sd[p + f'layers.{j}.bias'] = t(blk[key]['bias'])
+            sd[p + f'layers.{j}.running_mean'] = t(blk[key]['mean']); sd[p + f'layers.{j}.running_var'] = t(blk[key]['var'])
+        if 'sc_w' in blk:
+            sd[p + 'shortcut.0.weight'] = t(blk['sc_w'])
+            sd[p + 'shortcut.1.weight'] = t(blk['sc_bn']['weight']); sd[p + 'shortcut.1.bias'] = t(blk['sc_bn']['bias'])
+            sd[p + 'shortcut.1.running_mean'] = t(blk['sc_bn']['mean']); sd[p + 'shortcut.1.running_var'] = t(blk['sc_bn']['var'])
+    sd['layers.mean.weight'] = t(net['mean_w']); sd['layers.mean.bias'] = t(net['mean_b'])
+    enc.load_state_dict(sd)
+    return enc.eval()
+
+
+def encoder_case():
+    from sdf_nmpc.utils import preprocessing
+    net = synth.make_encoder_net(seed=5)
+    enc = ref_encoder(net)
+    out = {}
+    for tag, spherical, is_depth in (('depth', False, True), ('range', True, False)):
+        frames = np.stack([synth.depth_frame(seed=1 + i, spherical=spherical) for i in range(2)])
+        pre = [preprocessing.ToDevice('cpu'), preprocessing.Reshape([1, 270, 480]), preprocessing.ClipDistance(5, 1000)]
+        if is_depth:
+            pre.append(preprocessing.Depth2Range([1, 270, 480], 0.7592, 0.4903, 'cpu'))
+        pipe = torch.nn.Sequential(*pre)
+        lat, pres = [], []
+        with torch.no_grad():
+            for f in frames:
+                img = pipe(f)                       # vae.py:31-32
+                pres.append(img.numpy()[0, 0])
+                lat.append(enc(img).numpy()[0])     # vae.py:37-40
+            enc64 = enc.double()
+            lat64 = [enc64(torch.from_numpy(p)[None, None].double()).numpy()[0] for p in pres]
+            enc.float()
+        out['latent_' + tag] = np.stack(lat)
+        out['latent64_' + tag] = np.stack(lat64)
+        pre_img = np.stack(pres)
+        out['pre_rows_' + tag] = pre_img[:, ::45, ::40].copy()   # sparse sample of the preprocessed image
+        out['pre_sum_' + tag] = pre_img.astype(np.float64).sum((1, 2))
+        print(tag, 'latent range', out['latent_' + tag].min(), out['latent_' + tag].max(),
+              'f32-f64', np.abs(out['latent_' + tag] - out['latent64_' + tag]).max() / np.abs(out['latent64_' + tag]).max())
+    # a small stand-alone ResBlock case for fast CPU tests (stride 2 with shortcut, and stride 1)
+    np.savez_compressed(os.path.join(HERE, 'encoder.npz'), seed=5, frame_seed0=1, **out)
+
+
+def model_att_case():
+    """f_expl, y, yN, h values of model 'att' composed from the reference's numpy math helpers exactly as
+    model/quad_rollpitchyawrate.py:20-55, cost_const_helpers.py:56-65 and gen_model.py:46-51 compose them."""
+    from sdf_nmpc.utils import math as rm
+    rng = np.random.default_rng(7)
+    n = 64
+    g, gam, rmax, pmax, wmax = 9.81, 20.0, 0.7, 0.7, 3.0
+    X = np.concatenate([rng.uniform(-2, 2, (n, 3)), rng.standard_normal((n, 4)), rng.uniform(-3, 3, (n, 3))], 1)
+    X[: n // 2, 3:7] /= np.linalg.norm(X[: n // 2, 3:7], axis=1, keepdims=True)   # half unit, half un-normalised
+    U = np.concatenate([rng.uniform(0, 1, (n, 1)), rng.uniform(-1, 1, (n, 3))], 1)
+    QD = rng.standard_normal((n, 4)); QD /= np.linalg.norm(QD, axis=1, keepdims=True)
+    Pco = rng.uniform(-1, 1, (n, 3))
+    eul = rng.uniform(-0.5, 0.5, (n, 3)); eul[:, 2] = rng.uniform(-np.pi, np.pi, n)
+    B_p_C = np.array([0.18, 0, -0.025]); B_R_C = rm.euler2rot(np.zeros(3)); off = 0.05
+    F, Y, Hfov, C0, RCO = [], [], [], [], []
+    for i in range(n):
+        x, u = X[i], U[i]
+        p = x[:3]; q = x[3:7] / np.linalg.norm(x[3:7]); v = x[7:]
+        th = np.arctan2(q[3], q[0]); qyaw = np.array([np.cos(th), 0, 0, np.sin(th)])
+        gamma, roll, pitch, wz = u[0] * gam, u[1] * rmax, u[2] * pmax, u[3] * wmax
+        V_R_B = rm.euler2rot(np.array([roll, pitch, 0.0])); W_R_V = rm.quat2rot(qyaw)
+        W_a = W_R_V @ V_R_B @ np.array([0, 0, gamma]) + np.array([0, 0, -g])
+        dq = rm.hamilton_prod(q, np.array([0, 0, 0, wz])) / 2
+        F.append(np.concatenate([v, dq, W_a]))
+        q_e = rm.hamilton_prod(QD[i], rm.invert(q))
+        Y.append(np.concatenate([p, [q_e[3]], v, [roll, pitch, wz, W_a[2]]]))
+        W_R_Co = rm.euler2rot(eul[i]); RCO.append(W_R_Co)
+        c0 = W_R_Co.T @ (p - Pco[i]); C0.append(c0)
+        c = c0 + B_R_C.T @ B_p_C + np.array([off, 0, 0])
+        Hfov.append([np.arctan2(c[1], c[0]), np.arctan2(c[2], np.linalg.norm(c[:2]))])
+    np.savez_compressed(os.path.join(HERE, 'model_att.npz'), X=X, U=U, QD=QD, Pco=Pco, Rco=np.array(RCO),
+                        F=np.array(F), Y=np.array(Y), Hfov=np.array(Hfov), C0=np.array(C0),
+                        vfov=rm.get_vfov(0.7592, 1.778, False))
+    print('model_att: f range', np.abs(F).max())
+
+
+if __name__ == '__main__':
+    torch.manual_seed(0)
+    torch.set_num_threads(4)
+    sdf_case('archB', 512, seed=0, **synth.ARCH_B, bias_scale=0.0)
+    sdf_case('archA_bias', 512, seed=1, **synth.ARCH_A, bias_scale=0.1)
+    sdf_case('archB_cal', 512, seed=0, **synth.ARCH_B, calibrated=True)
+    sdf_case('small_state_relu', 256, seed=4, embed='cube', nb_freqs=3, layer_sizes=(64, 64, 32, 16), res='state',
+             act='relu', w0=1.0)
+    sdf_case('small_latent_softplus', 256, seed=5, embed='ico', nb_freqs=2, layer_sizes=(64, 32, 32, 16), res='latent',
+             act='softplus', w0=1.0, size_latent=32)
+    model_att_case()
+    encoder_case()

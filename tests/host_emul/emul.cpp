@@ -1,0 +1,66 @@
+// Host emulation of the device algorithms (development aid for the CPU-only test-suite).
+// Compiles the SAME headers the CUDA kernels include, with one lane per "warp".
+// Built by tests/test_host_emulation.py:  g++ -O2 -shared -fPIC -DSDFNMPC_HOST_EMUL -x c++ emul.cpp
+#include <cstddef>
+#include <cstring>
+#include <vector>
+#include "../../sdf_nmpc_b200/csrc/linearize_core.cuh"
+#include "../../sdf_nmpc_b200/csrc/qp_core.cuh"
+
+using namespace sdfnmpc;
+using Shape = QpShape<ATT_NX, ATT_NU, ATT_NY, ATT_NH>;
+using Prob = QpProb<ATT_NX, ATT_NU, ATT_NY, ATT_NH>;
+
+extern "C" void emul_linearize(int B, int N, const double* mcv, const double* xbar, const double* ubar,
+                               const double* yref, const double* yrefN, const double* qd, const double* pose,
+                               const double* flag, const double* dt, double* AB, double* bdyn, double* J,
+                               double* yres, double* C, double* hval, float* qpts) {
+    ModelConst mc;
+    mc.g = mcv[0]; mc.gamma = mcv[1]; mc.roll = mcv[2]; mc.pitch = mcv[3]; mc.wz = mcv[4]; mc.mass = mcv[5];
+    mc.cam_off[0] = mcv[6]; mc.cam_off[1] = mcv[7]; mc.cam_off[2] = mcv[8];
+    LinIn in{xbar, ubar, yref, yrefN, qd, pose, flag, dt};
+    LinOut out{AB, bdyn, J, yres, C, hval, qpts};
+    for (int b = 0; b < B; ++b)
+        for (int k = 0; k <= N; ++k)
+            for (int d = 0; d < ATT_NW; ++d) linearize_dir(mc, N, in, out, b, k, d);
+}
+
+extern "C" void emul_qp(int B, int N, int k0, int max_iter, int nyN, double lm, double tol, double tol_res,
+                        double max_df, const double* flag, const double* AB, const double* bdyn, const double* J,
+                        const double* yres, double* C, double* hval, const double* W, const double* WN,
+                        const double* dt, const double* lbu, const double* ubu, const double* lh, const double* uh,
+                        const double* zs, const double* Zs, const float* sdf_d, const float* sdf_g,
+                        const double* pose, const double* x0, double* xbar, double* ubar, double* u0,
+                        double* lam_hard, double* lam_soft, int* status, int* iters) {
+    constexpr int NX = ATT_NX, NU = ATT_NU, NW = ATT_NW, NY = ATT_NY, NH = ATT_NH;
+    std::vector<double> work(Shape::work_doubles(N));
+    std::vector<double> sm(Shape::SMEM_DOUBLES);
+    Lanes L{0};
+    for (int b = 0; b < B; ++b) {
+        Prob P;
+        P.N = N; P.k0 = k0; P.max_iter = max_iter; P.nyN = nyN;
+        P.lm = lm; P.tol = tol; P.tol_res = tol_res; P.max_df = max_df; P.flag = flag[b];
+        P.AB = AB + (size_t)b * N * NX * NW;
+        P.bdyn = bdyn + (size_t)b * N * NX;
+        P.J = J + (size_t)b * (N + 1) * NY * NW;
+        P.yres = yres + (size_t)b * (N + 1) * NY;
+        P.C = C + (size_t)b * (N + 1) * NH * NW;
+        P.hval = hval + (size_t)b * (N + 1) * NH;
+        P.W = W + (size_t)b * N * NY;
+        P.WN = WN + (size_t)b * nyN;
+        P.dt = dt; P.lbu = lbu; P.ubu = ubu; P.lh = lh; P.uh = uh; P.zs = zs; P.Zs = Zs;
+        P.sdf_d = sdf_d + (size_t)b * (N + 1);
+        P.sdf_g = sdf_g + (size_t)b * (N + 1) * 3;
+        P.pose = pose + (size_t)b * 12;
+        P.x0 = x0 + (size_t)b * NX;
+        P.xbar = xbar + (size_t)b * (N + 1) * NX;
+        P.ubar = ubar + (size_t)b * N * NU;
+        P.work = work.data();
+        P.u0 = u0 + (size_t)b * NU;
+        P.lam_hard = lam_hard + (size_t)b * N * 2 * NU;
+        P.lam_soft = lam_soft + (size_t)b * (N + 1) * 2 * NH;
+        P.status = status + b;
+        P.iters = iters + b;
+        qp_solve_instance<NX, NU, NY, NH>(L, P, sm.data());
+    }
+}
