@@ -1,0 +1,71 @@
+"""Build the C-ABI shared library in-tree with nvcc for sm_100a.
+
+    python -m sdf_nmpc_b200.build [--force]
+
+Output: ``sdf_nmpc_b200/lib/libsdfnmpc_b200.so`` (git-ignored; travels to the GPU box with the
+gpurun snapshot).  nvcc cross-compiles without a GPU.
+"""
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+LIBDIR = os.path.join(HERE, 'lib')
+LIB = os.path.join(LIBDIR, 'libsdfnmpc_b200.so')
+SOURCES = ['sdf_api.cu', 'nmpc_api.cu', 'encoder_api.cu']
+NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
+              '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=default', '--expt-relaxed-constexpr']
+
+
+def _nvcc():
+    for c in (os.environ.get('NVCC'), '/usr/local/cuda/bin/nvcc', 'nvcc'):
+        if c and (os.path.isabs(c) and os.path.exists(c) or not os.path.isabs(c)):
+            return c
+    raise RuntimeError('nvcc not found')
+
+
+def _digest():
+    h = hashlib.sha256()
+    files = sorted(os.listdir(CSRC)) + ['../../include/sdfnmpc_b200.h']
+    for f in files:
+        p = os.path.join(CSRC, f)
+        if os.path.isfile(p):
+            h.update(f.encode())
+            h.update(open(p, 'rb').read())
+    h.update(' '.join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force=False, verbose=False):
+    os.makedirs(LIBDIR, exist_ok=True)
+    stamp = os.path.join(LIBDIR, 'build.stamp')
+    dig = _digest()
+    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
+        return LIB
+    nvcc = _nvcc()
+    objs = []
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(LIBDIR, src.replace('.cu', '.o'))
+        cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for src, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode:
+            sys.stderr.write(out)
+        if p.returncode:
+            raise RuntimeError(f'nvcc failed on {src}')
+    cmd = [nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', LIB] + objs + ['-lcudart_static', '-ldl', '-lrt', '-lpthread']
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError('link failed')
+    open(stamp, 'w').write(dig)
+    return LIB
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

@@ -1,0 +1,345 @@
+// Batched depth-image encoder (C ABI + kernels), fp32 implicit-GEMM convolutions on CUDA cores.
+//
+// Replaces VaeWrapper.set_img + encode (sdf_nmpc/vae.py:15-40): the preprocessing pipeline
+// (utils/preprocessing.py: ToDevice :263-276, Reshape :83-96, ClipDistance :67-79, Depth2Range :5-30)
+// is fused into the gather of the first convolution, BatchNorm (eval mode) is folded into the
+// convolution weights, and the ResNet-style encoder of network/vae.py:19-38 + resnet.py:32-56 runs
+// for a whole batch of frames: conv7x7/2+ELU, maxpool3/2, 4 ResBlocks, adaptive avg-pool (2,2), Linear.
+//
+// Convolution = implicit GEMM: M = Cout, N = B*OH*OW output pixels, K = Cin*KH*KW.  One CTA computes a
+// 64 x 64 tile with a 16-deep shared-memory K pipeline; each of the 256 threads owns a 4x4 register tile.
+#include <cmath>
+#include <vector>
+#include "handles.h"
+
+using namespace sdfnmpc;
+
+namespace {
+
+enum { ENC_ACT_NONE = 0, ENC_ACT_RELU = 1, ENC_ACT_ELU = 2 };
+
+struct ConvShape {
+    int Cin, Hin, Win, Cout, Hout, Wout, stride, pad;
+};
+
+constexpr int TCO = 64, TPX = 64, TK = 16;
+
+// PRE: apply clip(clip(raw/dmax,0,1)*yz,0,1) to the (single-channel) input while gathering
+template <int KS, bool PRE>
+__global__ void __launch_bounds__(256)
+conv_igemm_kernel(ConvShape s, int B, const float* __restrict__ in, const float* __restrict__ w /*[Cout][Cin*KS*KS]*/,
+                  const float* __restrict__ bias, const float* __restrict__ resid, int act, float* __restrict__ out,
+                  const float* __restrict__ yz, float dmax, int clip_dist, int depth2range) {
+    __shared__ float As[TK][TCO + 4];
+    __shared__ float Bs[TK][TPX + 4];
+    const int K = s.Cin * KS * KS;
+    const long long npix = (long long)B * s.Hout * s.Wout;
+    const int co0 = blockIdx.y * TCO;
+    const long long px0 = (long long)blockIdx.x * TPX;
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    // gather mapping: this thread always loads pixel (tid & 63), k rows (tid >> 6) + 4 j
+    const int gp = tid & 63, gk = tid >> 6;
+    const long long pix = px0 + gp;
+    const bool pvalid = pix < npix;
+    int pb = 0, oy = 0, ox = 0;
+    if (pvalid) {
+        pb = (int)(pix / (s.Hout * s.Wout));
+        const int r = (int)(pix % (s.Hout * s.Wout));
+        oy = r / s.Wout;
+        ox = r % s.Wout;
+    }
+    const int iy0 = oy * s.stride - s.pad, ix0 = ox * s.stride - s.pad;
+    const float* inb = in + (size_t)pb * s.Cin * s.Hin * s.Win;
+    // weight mapping: k row = tid & 15 (contiguous in memory), co = (tid >> 4) + 16 j
+    const int wk = tid & 15, wc = tid >> 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < K; k0 += TK) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int co = wc + 16 * j;
+            float a = 0.f;
+            if (k0 + wk < K && co0 + co < s.Cout) a = __ldg(w + (size_t)(co0 + co) * K + k0 + wk);
+            As[wk][co] = a;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int kk = gk + 4 * j, k = k0 + kk;
+            float b = 0.f;
+            if (k < K && pvalid) {
+                const int ci = k / (KS * KS), rem = k % (KS * KS), ky = rem / KS, kx = rem % KS;
+                const int iy = iy0 + ky, ix = ix0 + kx;
+                if (iy >= 0 && iy < s.Hin && ix >= 0 && ix < s.Win) {
+                    b = __ldg(inb + ((size_t)ci * s.Hin + iy) * s.Win + ix);
+                    if (PRE) {
+                        if (clip_dist) b = fminf(fmaxf(b / dmax, 0.f), 1.f);
+                        if (depth2range) b = fminf(fmaxf(b * __ldg(yz + iy * s.Win + ix), 0.f), 1.f);
+                    }
+                }
+            }
+            Bs[kk][gp] = b;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < TK; ++kk) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    const int hw = s.Hout * s.Wout;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int co = co0 + ty * 4 + i;
+        if (co >= s.Cout) continue;
+        const float bco = bias ? bias[co] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const long long p = px0 + tx * 4 + j;
+            if (p >= npix) continue;
+            const int b = (int)(p / hw), r = (int)(p % hw);
+            const size_t o = ((size_t)b * s.Cout + co) * hw + r;
+            float v = acc[i][j] + bco;
+            if (resid) v += resid[o];
+            if (act == ENC_ACT_RELU) v = fmaxf(v, 0.f);
+            else if (act == ENC_ACT_ELU) v = v > 0.f ? v : expm1f(v);
+            out[o] = v;
+        }
+    }
+}
+
+__global__ void maxpool3s2_kernel(int C, int Hin, int Win, int Hout, int Wout, long long total,
+                                  const float* __restrict__ in, float* __restrict__ out) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int ox = (int)(gid % Wout), oy = (int)((gid / Wout) % Hout);
+    const long long bc = gid / ((long long)Wout * Hout);
+    const float* p = in + (size_t)bc * Hin * Win;
+    float m = -INFINITY;
+    for (int ky = 0; ky < 3; ++ky) {
+        const int iy = oy * 2 - 1 + ky;
+        if (iy < 0 || iy >= Hin) continue;
+        for (int kx = 0; kx < 3; ++kx) {
+            const int ix = ox * 2 - 1 + kx;
+            if (ix < 0 || ix >= Win) continue;
+            m = fmaxf(m, p[iy * Win + ix]);
+        }
+    }
+    out[gid] = m;
+}
+
+// AdaptiveAvgPool2d((2,2)) + Flatten + Linear(4C -> L); one CTA per frame
+__global__ void __launch_bounds__(256)
+pool_linear_kernel(int C, int H, int W, int L, const float* __restrict__ feat, const float* __restrict__ mw,
+                   const float* __restrict__ mb, float* __restrict__ latents) {
+    extern __shared__ float f[];   // [4C]
+    const int b = blockIdx.x;
+    const float* fb = feat + (size_t)b * C * H * W;
+    for (int idx = threadIdx.x; idx < 4 * C; idx += blockDim.x) {
+        const int c = idx >> 2, py = (idx >> 1) & 1, px = idx & 1;
+        // torch adaptive pooling bins: [floor(i*In/Out), ceil((i+1)*In/Out))
+        const int y0 = (py * H) / 2, y1 = ((py + 1) * H + 1) / 2;
+        const int x0 = (px * W) / 2, x1 = ((px + 1) * W + 1) / 2;
+        float sum = 0.f;
+        for (int y = y0; y < y1; ++y)
+            for (int x = x0; x < x1; ++x) sum += fb[((size_t)c * H + y) * W + x];
+        f[idx] = sum / (float)((y1 - y0) * (x1 - x0));
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int l = warp; l < L; l += nw) {
+        const float* wr = mw + (size_t)l * 4 * C;
+        float sum = 0.f;
+        for (int j = lane; j < 4 * C; j += 32) sum = fmaf(wr[j], f[j], sum);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) latents[(size_t)b * L + l] = sum + mb[l];
+    }
+}
+
+// yz_sqrt table of Depth2Range, computed with the reference's float32 operation order (preprocessing.py:20-27)
+__global__ void yz_table_kernel(int H, int W, float tan_h, float tan_v, float* __restrict__ yz) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= H * W) return;
+    const float u = (float)(idx % W), v = (float)(idx / W);
+    const float a = tan_h * (1.f - 2.f * u / (float)W);
+    const float b = tan_v * (1.f - 2.f * v / (float)H);
+    yz[idx] = sqrtf(1.f + a * a + b * b);
+}
+
+struct Layer {
+    ConvShape s;
+    int ks;
+    float *w = nullptr, *b = nullptr;
+};
+
+}  // namespace
+
+struct sdfnmpc_encoder {
+    sdfnmpc_encoder_desc desc;
+    Layer conv0, c1[4], c2[4], sc[4];
+    bool has_sc[4];
+    float *mean_w = nullptr, *mean_b = nullptr, *yz = nullptr;
+    float *buf[4] = {nullptr, nullptr, nullptr, nullptr};   // activation ping-pong
+    size_t buf_floats = 0;
+    int Hp, Wp;       // after max-pool
+    int Hf, Wf;       // final feature map
+    float *h_img = nullptr, *h_lat = nullptr;
+};
+
+static int out_dim(int in, int k, int s, int p) { return (in + 2 * p - k) / s + 1; }
+
+static int upload(float** dst, const std::vector<float>& v) {
+    SDF_CUDA_CHECK(cudaMalloc(dst, v.size() * sizeof(float)));
+    SDF_CUDA_CHECK(cudaMemcpy(*dst, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// fold BN (weight, bias, mean, var) into conv weights [Cout][K] and a bias [Cout]
+static int make_layer(Layer& L, const float* w, const float* const bn[4], const float* conv_bias, float eps) {
+    const int K = L.s.Cin * L.ks * L.ks;
+    std::vector<float> W((size_t)L.s.Cout * K), Bv(L.s.Cout, 0.f);
+    for (int co = 0; co < L.s.Cout; ++co) {
+        float scale = 1.f, shift = conv_bias ? conv_bias[co] : 0.f;
+        if (bn && bn[0]) {
+            const float inv = 1.0f / sqrtf(bn[3][co] + eps);
+            scale = bn[0][co] * inv;
+            shift = bn[1][co] + (shift - bn[2][co]) * scale;
+        }
+        for (int k = 0; k < K; ++k) W[(size_t)co * K + k] = w[(size_t)co * K + k] * scale;
+        Bv[co] = shift;
+    }
+    if (int rc = upload(&L.w, W)) return rc;
+    return upload(&L.b, Bv);
+}
+
+extern "C" int sdfnmpc_encoder_create(sdfnmpc_encoder_t* out, const sdfnmpc_encoder_desc* d, const sdfnmpc_encoder_weights* w) {
+    if (!out || !d || !w || d->height < 16 || d->width < 16 || d->max_batch < 1 || d->size_latent < 1) return SDFNMPC_E_INVALID;
+    if (int rc = ensure_device()) return rc;
+    auto* h = new sdfnmpc_encoder();
+    h->desc = *d;
+    const int H0 = d->height, W0 = d->width;
+    h->conv0.s = {1, H0, W0, 64, out_dim(H0, 7, 2, 3), out_dim(W0, 7, 2, 3), 2, 3};
+    h->conv0.ks = 7;
+    int rc = make_layer(h->conv0, w->conv0_w, nullptr, w->conv0_b, w->bn_eps);
+    h->Hp = out_dim(h->conv0.s.Hout, 3, 2, 1);
+    h->Wp = out_dim(h->conv0.s.Wout, 3, 2, 1);
+    int C = 64, Hc = h->Hp, Wc = h->Wp;
+    size_t maxf = (size_t)64 * h->conv0.s.Hout * h->conv0.s.Wout;
+    const int strides[4] = {2, 2, 2, 1};
+    for (int i = 0; i < 4 && rc == 0; ++i) {
+        const int st = strides[i], Co = C * st;
+        const int Ho = out_dim(Hc, 3, st, 1), Wo = out_dim(Wc, 3, st, 1);
+        h->c1[i].s = {C, Hc, Wc, Co, Ho, Wo, st, 1}; h->c1[i].ks = 3;
+        h->c2[i].s = {Co, Ho, Wo, Co, Ho, Wo, 1, 1}; h->c2[i].ks = 3;
+        rc = make_layer(h->c1[i], w->conv1_w[i], w->bn1[i], nullptr, w->bn_eps);
+        if (!rc) rc = make_layer(h->c2[i], w->conv2_w[i], w->bn2[i], nullptr, w->bn_eps);
+        h->has_sc[i] = st != 1;
+        if (h->has_sc[i]) {
+            if (!w->sc_w[i]) { rc = SDFNMPC_E_INVALID; break; }
+            h->sc[i].s = {C, Hc, Wc, Co, out_dim(Hc, 1, st, 0), out_dim(Wc, 1, st, 0), st, 0}; h->sc[i].ks = 1;
+            if (!rc) rc = make_layer(h->sc[i], w->sc_w[i], w->sc_bn[i], nullptr, w->bn_eps);
+        }
+        maxf = std::max(maxf, (size_t)Co * Ho * Wo);
+        C = Co; Hc = Ho; Wc = Wo;
+    }
+    h->Hf = Hc; h->Wf = Wc;
+    if (!rc && C * 4 != 2048) rc = SDFNMPC_E_INVALID;
+    if (!rc) {
+        std::vector<float> mw(w->mean_w, w->mean_w + (size_t)d->size_latent * 2048), mb(w->mean_b, w->mean_b + d->size_latent);
+        rc = upload(&h->mean_w, mw);
+        if (!rc) rc = upload(&h->mean_b, mb);
+    }
+    h->buf_floats = maxf * (size_t)d->max_batch;
+    for (int i = 0; i < 3 && !rc; ++i) rc = (int)cudaMalloc(&h->buf[i], h->buf_floats * sizeof(float));
+    if (!rc) rc = (int)cudaMalloc(&h->yz, (size_t)H0 * W0 * sizeof(float));
+    if (!rc) {
+        // torch.tan(torch.tensor(hfov, dtype=float32)): tangent evaluated on the float32-rounded angle
+        yz_table_kernel<<<(H0 * W0 + 255) / 256, 256>>>(H0, W0, tanf((float)d->hfov), tanf((float)d->vfov), h->yz);
+        count_launch();
+        rc = (int)cudaDeviceSynchronize();
+    }
+    if (rc) { sdfnmpc_encoder_destroy(h); return rc; }
+    *out = h;
+    return 0;
+}
+
+extern "C" int sdfnmpc_encoder_destroy(sdfnmpc_encoder_t h) {
+    if (!h) return 0;
+    Layer* ls[] = {&h->conv0, &h->c1[0], &h->c1[1], &h->c1[2], &h->c1[3], &h->c2[0], &h->c2[1], &h->c2[2], &h->c2[3],
+                   &h->sc[0], &h->sc[1], &h->sc[2], &h->sc[3]};
+    for (Layer* l : ls) { cudaFree(l->w); cudaFree(l->b); }
+    cudaFree(h->mean_w); cudaFree(h->mean_b); cudaFree(h->yz);
+    for (float* b : h->buf) cudaFree(b);
+    cudaFree(h->h_img); cudaFree(h->h_lat);
+    delete h;
+    return 0;
+}
+
+template <int KS, bool PRE>
+static int launch_conv(const Layer& L, int B, const float* in, const float* resid, int act, float* out, cudaStream_t st,
+                       const float* yz = nullptr, float dmax = 1.f, int clip = 0, int d2r = 0) {
+    const long long npix = (long long)B * L.s.Hout * L.s.Wout;
+    dim3 grid((unsigned)((npix + TPX - 1) / TPX), (L.s.Cout + TCO - 1) / TCO);
+    conv_igemm_kernel<KS, PRE><<<grid, 256, 0, st>>>(L.s, B, in, L.w, L.b, resid, act, out, yz, dmax, clip, d2r);
+    count_launch();
+    SDF_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int sdfnmpc_encoder_encode(sdfnmpc_encoder_t h, const float* imgs, int32_t B, float* latents, void* stream) {
+    if (!h || !imgs || !latents || B < 1 || B > h->desc.max_batch) return SDFNMPC_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    float *a = h->buf[0], *b = h->buf[1], *c = h->buf[2];
+    int rc = launch_conv<7, true>(h->conv0, B, imgs, nullptr, ENC_ACT_ELU, a, st, h->yz, h->desc.dmax_scale,
+                                  h->desc.is_normalized ? 0 : 1, h->desc.is_depth ? 1 : 0);
+    if (rc) return rc;
+    {
+        const long long total = (long long)B * 64 * h->Hp * h->Wp;
+        maxpool3s2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(64, h->conv0.s.Hout, h->conv0.s.Wout, h->Hp, h->Wp, total, a, b);
+        count_launch();
+        SDF_CUDA_CHECK(cudaGetLastError());
+    }
+    float* x = b;          // block input
+    float* t1 = a;         // conv1 output
+    float* t2 = c;         // shortcut output / block output
+    for (int i = 0; i < 4; ++i) {
+        if ((rc = launch_conv<3, false>(h->c1[i], B, x, nullptr, ENC_ACT_RELU, t1, st))) return rc;
+        const float* resid = x;
+        if (h->has_sc[i]) {
+            if ((rc = launch_conv<1, false>(h->sc[i], B, x, nullptr, ENC_ACT_NONE, t2, st))) return rc;
+            resid = t2;
+            // conv2 writes over the (now dead) block input
+            if ((rc = launch_conv<3, false>(h->c2[i], B, t1, resid, ENC_ACT_RELU, x, st))) return rc;
+        } else {
+            if ((rc = launch_conv<3, false>(h->c2[i], B, t1, resid, ENC_ACT_RELU, t2, st))) return rc;
+            float* tmp = x; x = t2; t2 = tmp;
+        }
+    }
+    pool_linear_kernel<<<B, 256, 2048 * sizeof(float), st>>>(512, h->Hf, h->Wf, h->desc.size_latent, x, h->mean_w, h->mean_b, latents);
+    count_launch();
+    SDF_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int sdfnmpc_encoder_encode_host(sdfnmpc_encoder_t h, const float* imgs, int32_t B, float* latents) {
+    if (!h || !imgs || !latents || B < 1 || B > h->desc.max_batch) return SDFNMPC_E_INVALID;
+    const size_t img_floats = (size_t)h->desc.height * h->desc.width;
+    if (!h->h_img) SDF_CUDA_CHECK(cudaMalloc(&h->h_img, img_floats * h->desc.max_batch * sizeof(float)));
+    if (!h->h_lat) SDF_CUDA_CHECK(cudaMalloc(&h->h_lat, (size_t)h->desc.size_latent * h->desc.max_batch * sizeof(float)));
+    SDF_CUDA_CHECK(cudaMemcpyAsync(h->h_img, imgs, img_floats * B * sizeof(float), cudaMemcpyHostToDevice, 0));
+    if (int rc = sdfnmpc_encoder_encode(h, h->h_img, B, h->h_lat, nullptr)) return rc;
+    SDF_CUDA_CHECK(cudaMemcpyAsync(latents, h->h_lat, (size_t)h->desc.size_latent * B * sizeof(float), cudaMemcpyDeviceToHost, 0));
+    SDF_CUDA_CHECK(cudaStreamSynchronize(0));
+    return 0;
+}

@@ -1,0 +1,29 @@
+// Internal handle definitions shared by the C-ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <atomic>
+#include <vector>
+#include "../../include/sdfnmpc_b200.h"
+#include "common.cuh"
+#include "sdf_net.h"
+
+namespace sdfnmpc {
+extern std::atomic<uint64_t> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+int ensure_device();   // 0 if a CUDA device is usable, SDFNMPC_E_NODEVICE otherwise (no CPU path)
+}  // namespace sdfnmpc
+
+struct sdfnmpc_sdf {
+    sdfnmpc_sdf_desc desc;
+    sdfnmpc::SdfNetDev net;          // device pointers into `blob`
+    float* blob = nullptr;           // one allocation with every packed weight
+    size_t blob_floats = 0;
+    float* b1f = nullptr;            // [cap_inst][H1] folded biases
+    float* b3f = nullptr;            // [cap_inst][H3]
+    int cap_inst = 0, n_inst = 0;
+    size_t smem = 0;
+    int sm_count = 148;
+    // scratch for the host-convenience entry points
+    float *h_pts = nullptr, *h_out = nullptr, *h_lat = nullptr;
+    size_t h_cap = 0;
+};

@@ -1,0 +1,277 @@
+// C ABI + kernels of the batched SQP-RTI solver (see include/sdfnmpc_b200.h).
+//
+// One RTI step = three launches on the caller's stream (plus the latent fold when new latents
+// are given), mirroring acados' preparation + feedback phases:
+//   nmpc_linearize_kernel : thread per (instance, node, tangent direction)  -> A,B,b, J,y-yref, FoV rows
+//   sdf_eval_kernel       : fused SDF value + gradient at every node's query point
+//   nmpc_qp_kernel        : warp per instance: GN Hessian, Riccati IPM, full step
+#include "handles.h"
+#include "linearize_core.cuh"
+#include "qp_core.cuh"
+
+using namespace sdfnmpc;
+
+namespace {
+constexpr int NX = ATT_NX, NU = ATT_NU, NW = ATT_NW, NY = ATT_NY, NYN = ATT_NYN, NH = ATT_NH;
+using Shape = QpShape<NX, NU, NY, NH>;
+using Prob = QpProb<NX, NU, NY, NH>;
+constexpr int QP_WARPS = 4;     // instances per CTA
+
+struct SolverConst {
+    ModelConst mc;
+    int N, k0, qp_iter_max;
+    double lm, tol, tol_res;
+    double lbu[NU], ubu[NU], lh[NH], uh[NH], zs[NH], Zs[NH];
+    double cmd_min[4], cmd_max[4];
+};
+}  // namespace
+
+struct sdfnmpc_solver {
+    sdfnmpc_solver_desc desc;
+    SolverConst sc;
+    sdfnmpc_sdf_t sdf = nullptr;
+    int cap = 0;
+    double* dt = nullptr;                     // [N] device
+    double *xbar = nullptr, *ubar = nullptr;  // warm start
+    double *AB = nullptr, *bdyn = nullptr, *J = nullptr, *yres = nullptr, *C = nullptr, *hval = nullptr;
+    float *qpts = nullptr, *sdf_d = nullptr, *sdf_g = nullptr;
+    double *work = nullptr, *lam_hard = nullptr, *lam_soft = nullptr;
+    size_t work_per_inst = 0;
+};
+
+__global__ void nmpc_linearize_kernel(ModelConst mc, int N, int B, LinIn in, LinOut out) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)B * (N + 1) * NW;
+    if (gid >= total) return;
+    const int dir = (int)(gid % NW);
+    const long long node = gid / NW;
+    const int k = (int)(node % (N + 1));
+    const int b = (int)(node / (N + 1));
+    linearize_dir(mc, N, in, out, b, k, dir);
+}
+
+struct QpBatch {
+    const double *AB, *bdyn, *J, *yres, *W, *WN, *dt, *pose, *x0, *flag;
+    double *C, *hval, *xbar, *ubar, *work, *u0, *lam_hard, *lam_soft;
+    const float *sdf_d, *sdf_g;
+    int *status, *iters;
+    size_t work_per_inst;
+    double max_df;
+};
+
+__global__ void __launch_bounds__(QP_WARPS * 32) nmpc_qp_kernel(SolverConst sc, int B, QpBatch q) {
+    __shared__ double sm_all[QP_WARPS][Shape::SMEM_DOUBLES];
+    __shared__ SolverConst scs;
+    if (threadIdx.x == 0) scs = sc;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5;
+    const int b = blockIdx.x * QP_WARPS + warp;
+    if (b >= B) return;
+    const int N = scs.N;
+    Prob P;
+    P.N = N; P.k0 = scs.k0; P.max_iter = scs.qp_iter_max; P.nyN = NYN;
+    P.lm = scs.lm; P.tol = scs.tol; P.tol_res = scs.tol_res; P.max_df = q.max_df; P.flag = q.flag[b];
+    P.AB = q.AB + (size_t)b * N * NX * NW;
+    P.bdyn = q.bdyn + (size_t)b * N * NX;
+    P.J = q.J + (size_t)b * (N + 1) * NY * NW;
+    P.yres = q.yres + (size_t)b * (N + 1) * NY;
+    P.C = q.C + (size_t)b * (N + 1) * NH * NW;
+    P.hval = q.hval + (size_t)b * (N + 1) * NH;
+    P.W = q.W + (size_t)b * N * NY;
+    P.WN = q.WN + (size_t)b * NYN;
+    P.dt = q.dt;
+    P.lbu = scs.lbu; P.ubu = scs.ubu; P.lh = scs.lh; P.uh = scs.uh; P.zs = scs.zs; P.Zs = scs.Zs;
+    P.sdf_d = q.sdf_d + (size_t)b * (N + 1);
+    P.sdf_g = q.sdf_g + (size_t)b * (N + 1) * 3;
+    P.pose = q.pose + (size_t)b * 12;
+    P.x0 = q.x0 + (size_t)b * NX;
+    P.xbar = q.xbar + (size_t)b * (N + 1) * NX;
+    P.ubar = q.ubar + (size_t)b * N * NU;
+    P.work = q.work + (size_t)b * q.work_per_inst;
+    P.u0 = q.u0 + (size_t)b * NU;
+    P.lam_hard = q.lam_hard + (size_t)b * N * 2 * NU;
+    P.lam_soft = q.lam_soft + (size_t)b * (N + 1) * 2 * NH;
+    P.status = q.status + b;
+    P.iters = q.iters + b;
+    Lanes L{(int)(threadIdx.x & 31)};
+    qp_solve_instance<NX, NU, NY, NH>(L, P, sm_all[warp]);
+}
+
+__global__ void nmpc_init_traj_kernel(int N, int B, double u_hover, const double* __restrict__ x0,
+                                      double* __restrict__ xbar, double* __restrict__ ubar) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nx_tot = (long long)B * (N + 1) * NX;
+    if (gid < nx_tot) {
+        const int i = (int)(gid % NX);
+        const long long b = gid / ((long long)(N + 1) * NX);
+        xbar[gid] = x0[b * NX + i];
+    }
+    if (gid < (long long)B * N * NU) ubar[gid] = (gid % NU) == 0 ? u_hover : 0.0;
+}
+
+__global__ void nmpc_shift_kernel(int N, int B, int s, double* __restrict__ xbar, double* __restrict__ ubar) {
+    // Ocp.shift (ocp.py:152-156): for i in k..N-1: x[i-k] = x[i], u[i-k] = u[i]   (node N untouched)
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double* x = xbar + (size_t)b * (N + 1) * NX;
+    double* u = ubar + (size_t)b * N * NU;
+    for (int i = s; i < N; ++i) {
+        for (int j = 0; j < NX; ++j) x[(i - s) * NX + j] = x[i * NX + j];
+        for (int j = 0; j < NU; ++j) u[(i - s) * NU + j] = u[i * NU + j];
+    }
+}
+
+__global__ void nmpc_plant_kernel(ModelConst mc, int B, double dt, double* __restrict__ x, const double* __restrict__ u) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double xs[NX], us[NU], xn[NX];
+    for (int i = 0; i < NX; ++i) xs[i] = x[(size_t)b * NX + i];
+    for (int i = 0; i < NU; ++i) us[i] = u[(size_t)b * NU + i];
+    rk4_step<double>(mc, xs, us, dt, xn);
+    for (int i = 0; i < NX; ++i) x[(size_t)b * NX + i] = xn[i];
+}
+
+__global__ void nmpc_cmd_kernel(SolverConst sc, int B, const double* __restrict__ u, double* __restrict__ cmd) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double c[4];
+    u_to_TRPYr(sc.mc, u + (size_t)b * NU, c);
+    for (int i = 0; i < 4; ++i) cmd[(size_t)b * 4 + i] = fmin(fmax(c[i], sc.cmd_min[i]), sc.cmd_max[i]);
+}
+
+extern "C" int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver_desc* d, sdfnmpc_sdf_t sdf) {
+    if (!out || !d || !sdf || d->N < 1 || d->N > SDFNMPC_MAX_N || d->max_batch < 1) return SDFNMPC_E_INVALID;
+    if (int rc = ensure_device()) return rc;
+    auto* h = new sdfnmpc_solver();
+    h->desc = *d;
+    h->sdf = sdf;
+    h->cap = d->max_batch;
+    SolverConst& sc = h->sc;
+    sc.mc.g = d->g; sc.mc.gamma = d->gamma; sc.mc.roll = d->roll; sc.mc.pitch = d->pitch; sc.mc.wz = d->wz; sc.mc.mass = d->mass;
+    for (int i = 0; i < 3; ++i) sc.mc.cam_off[i] = d->cam_off[i];
+    sc.N = d->N; sc.k0 = d->h_at_node0 ? 0 : 1; sc.qp_iter_max = d->qp_iter_max;
+    sc.lm = d->lm; sc.tol = d->qp_tol; sc.tol_res = d->qp_tol_res;
+    for (int i = 0; i < NU; ++i) { sc.lbu[i] = d->lbu[i]; sc.ubu[i] = d->ubu[i]; }
+    for (int i = 0; i < NH; ++i) { sc.lh[i] = d->lh[i]; sc.uh[i] = d->uh[i]; sc.zs[i] = d->zl[i]; sc.Zs[i] = d->Zl[i]; }
+    // controller.py:21-23: thrust command clipped at limits.gamma (not gamma*mass) - kept for parity
+    const double cmin[4] = {0.0, -d->roll, -d->pitch, -d->wz}, cmax[4] = {d->gamma, d->roll, d->pitch, d->wz};
+    for (int i = 0; i < 4; ++i) { sc.cmd_min[i] = cmin[i]; sc.cmd_max[i] = cmax[i]; }
+    const size_t B = (size_t)h->cap, N = (size_t)d->N, N1 = N + 1;
+    h->work_per_inst = Shape::work_doubles(d->N);
+    cudaError_t e = cudaSuccess;
+    auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+    alloc((void**)&h->dt, N * sizeof(double));
+    alloc((void**)&h->xbar, B * N1 * NX * sizeof(double));
+    alloc((void**)&h->ubar, B * N * NU * sizeof(double));
+    alloc((void**)&h->AB, B * N * NX * NW * sizeof(double));
+    alloc((void**)&h->bdyn, B * N * NX * sizeof(double));
+    alloc((void**)&h->J, B * N1 * NY * NW * sizeof(double));
+    alloc((void**)&h->yres, B * N1 * NY * sizeof(double));
+    alloc((void**)&h->C, B * N1 * NH * NW * sizeof(double));
+    alloc((void**)&h->hval, B * N1 * NH * sizeof(double));
+    alloc((void**)&h->qpts, B * N1 * 3 * sizeof(float));
+    alloc((void**)&h->sdf_d, B * N1 * sizeof(float));
+    alloc((void**)&h->sdf_g, B * N1 * 3 * sizeof(float));
+    alloc((void**)&h->work, B * h->work_per_inst * sizeof(double));
+    alloc((void**)&h->lam_hard, B * N * 2 * NU * sizeof(double));
+    alloc((void**)&h->lam_soft, B * N1 * 2 * NH * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(h->dt, d->dt, N * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(h->xbar, 0, B * N1 * NX * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemset(h->ubar, 0, B * N * NU * sizeof(double));
+    if (e != cudaSuccess) { sdfnmpc_solver_destroy(h); return (int)e; }
+    *out = h;
+    return 0;
+}
+
+extern "C" int sdfnmpc_solver_destroy(sdfnmpc_solver_t h) {
+    if (!h) return 0;
+    void* ptrs[] = {h->dt, h->xbar, h->ubar, h->AB, h->bdyn, h->J, h->yres, h->C, h->hval, h->qpts, h->sdf_d, h->sdf_g,
+                    h->work, h->lam_hard, h->lam_soft};
+    for (void* p : ptrs) cudaFree(p);
+    delete h;
+    return 0;
+}
+
+extern "C" int sdfnmpc_solver_init_traj(sdfnmpc_solver_t h, const double* x0, int32_t B, void* stream) {
+    if (!h || !x0 || B < 1 || B > h->cap) return SDFNMPC_E_INVALID;
+    const int N = h->sc.N;
+    const long long total = (long long)B * (N + 1) * NX;
+    nmpc_init_traj_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        N, B, h->sc.mc.g / h->sc.mc.gamma, x0, h->xbar, h->ubar);
+    count_launch();
+    SDF_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int sdfnmpc_solver_shift(sdfnmpc_solver_t h, int32_t B, int32_t k, void* stream) {
+    if (!h || B < 1 || B > h->cap || k < 0) return SDFNMPC_E_INVALID;
+    if (k == 0) return 0;
+    nmpc_shift_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->sc.N, B, k, h->xbar, h->ubar);
+    count_launch();
+    SDF_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int sdfnmpc_solver_rti_step(sdfnmpc_solver_t h, int32_t B, const double* x0, const double* yref,
+                                       const double* W, const double* yrefN, const double* WN, const double* qd,
+                                       const double* pose, const double* flag, const float* latents, double* u0,
+                                       int32_t* status, int32_t* qp_iters, void* stream) {
+    if (!h || B < 1 || B > h->cap || !x0 || !yref || !W || !yrefN || !WN || !qd || !pose || !flag || !u0 || !status || !qp_iters)
+        return SDFNMPC_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = h->sc.N;
+    if (latents) {
+        if (int rc = sdfnmpc_sdf_set_latents(h->sdf, latents, B, stream)) return rc;
+    } else if (h->sdf->n_inst < B) {
+        return SDFNMPC_E_STATE;
+    }
+    LinIn in{h->xbar, h->ubar, yref, yrefN, qd, pose, flag, h->dt};
+    LinOut lo{h->AB, h->bdyn, h->J, h->yres, h->C, h->hval, h->qpts};
+    const long long total = (long long)B * (N + 1) * NW;
+    nmpc_linearize_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(h->sc.mc, N, B, in, lo);
+    count_launch();
+    SDF_CUDA_CHECK(cudaGetLastError());
+    if (int rc = sdfnmpc_sdf_eval(h->sdf, h->qpts, nullptr, N + 1, (int64_t)B * (N + 1), h->sdf_d, h->sdf_g, stream)) return rc;
+    QpBatch q;
+    q.AB = h->AB; q.bdyn = h->bdyn; q.J = h->J; q.yres = h->yres; q.W = W; q.WN = WN; q.dt = h->dt; q.pose = pose;
+    q.x0 = x0; q.flag = flag; q.C = h->C; q.hval = h->hval; q.xbar = h->xbar; q.ubar = h->ubar; q.work = h->work;
+    q.u0 = u0; q.lam_hard = h->lam_hard; q.lam_soft = h->lam_soft; q.sdf_d = h->sdf_d; q.sdf_g = h->sdf_g;
+    q.status = status; q.iters = qp_iters; q.work_per_inst = h->work_per_inst; q.max_df = (double)h->sdf->net.max_df;
+    nmpc_qp_kernel<<<(B + QP_WARPS - 1) / QP_WARPS, QP_WARPS * 32, 0, st>>>(h->sc, B, q);
+    count_launch();
+    SDF_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int sdfnmpc_solver_state(sdfnmpc_solver_t h, double** xbar, double** ubar, double** lam_hard, double** lam_soft) {
+    if (!h) return SDFNMPC_E_INVALID;
+    if (xbar) *xbar = h->xbar;
+    if (ubar) *ubar = h->ubar;
+    if (lam_hard) *lam_hard = h->lam_hard;
+    if (lam_soft) *lam_soft = h->lam_soft;
+    return 0;
+}
+
+extern "C" int sdfnmpc_solver_diag(sdfnmpc_solver_t h, double** hval, float** sdf_d, float** sdf_g) {
+    if (!h) return SDFNMPC_E_INVALID;
+    if (hval) *hval = h->hval;
+    if (sdf_d) *sdf_d = h->sdf_d;
+    if (sdf_g) *sdf_g = h->sdf_g;
+    return 0;
+}
+
+extern "C" int sdfnmpc_plant_step(sdfnmpc_solver_t h, int32_t B, double* x, const double* u, double dt, void* stream) {
+    if (!h || !x || !u || B < 1) return SDFNMPC_E_INVALID;
+    nmpc_plant_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->sc.mc, B, dt, x, u);
+    count_launch();
+    SDF_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int sdfnmpc_cmd_trpyr(sdfnmpc_solver_t h, int32_t B, const double* u, double* cmd, void* stream) {
+    if (!h || !u || !cmd || B < 1) return SDFNMPC_E_INVALID;
+    nmpc_cmd_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->sc, B, u, cmd);
+    count_launch();
+    SDF_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}

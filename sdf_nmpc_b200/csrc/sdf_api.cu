@@ -1,0 +1,325 @@
+// C ABI for the neural-SDF evaluator (see include/sdfnmpc_b200.h).
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include "handles.h"
+#include "sdf_kernels.cuh"
+
+namespace sdfnmpc {
+std::atomic<uint64_t> g_launches{0};
+
+int ensure_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        fprintf(stderr, "[sdfnmpc_b200] no CUDA device available (%s); this library has no CPU path\n",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return SDFNMPC_E_NODEVICE;
+    }
+    return 0;
+}
+}  // namespace sdfnmpc
+
+using namespace sdfnmpc;
+
+extern "C" const char* sdfnmpc_version(void) { return "sdfnmpc_b200 0.1 (sm_100a)"; }
+extern "C" uint64_t sdfnmpc_launch_count(void) { return g_launches.load(); }
+
+static inline int pad8(int v) { return (v + 7) / 8 * 8; }
+
+extern "C" int sdfnmpc_sdf_create(sdfnmpc_sdf_t* out, const sdfnmpc_sdf_desc* d, const float* dirs,
+                                  const float* W1, const float* b1, const float* W2, const float* b2,
+                                  const float* W3, const float* b3, const float* W4, const float* b4,
+                                  const float* W5, const float* b5) {
+    if (!out || !d || !dirs || !W1 || !W5) return SDFNMPC_E_INVALID;
+    if (d->n_dirs < 1 || d->nb_freqs < 0 || d->nb_freqs > 20 || d->size_latent < 0 || d->act < 0 || d->act > 2) return SDFNMPC_E_INVALID;
+    for (int i = 0; i < 4; ++i)
+        if (d->hidden[i] < 1) return SDFNMPC_E_INVALID;
+    if (int rc = ensure_device()) return rc;
+    auto* h = new sdfnmpc_sdf();
+    h->desc = *d;
+    const int D = d->n_dirs, F = d->nb_freqs, L = d->size_latent;
+    const int E = 3 + 2 * D * F, Ep = pad8(E);
+    const int h1 = d->hidden[0], h2 = d->hidden[1], h3 = d->hidden[2], h4 = d->hidden[3];
+    const int H1 = pad8(h1), H2 = pad8(h2), H3 = pad8(h3), H4 = pad8(h4);
+    const int in1 = E + L;
+    const int in3 = h2 + (d->res_state ? E : 0) + (d->res_latent ? L : 0);
+    const int offz3 = h2 + (d->res_state ? E : 0);
+    // ---- pack on the host ----
+    std::vector<float> host;
+    auto reserve = [&](size_t n) { size_t o = host.size(); host.resize(o + ((n + 3) / 4) * 4, 0.f); return o; };
+    const size_t o_dirs = reserve((size_t)3 * D);
+    const size_t o_W1e_t = reserve((size_t)Ep * H1), o_W2_t = reserve((size_t)H1 * H2), o_W3h_t = reserve((size_t)H2 * H3);
+    const size_t o_W3e_t = reserve((size_t)Ep * H3), o_W4_t = reserve((size_t)H3 * H4), o_W5 = reserve(H4);
+    const size_t o_W4 = reserve((size_t)H4 * H3), o_W3h = reserve((size_t)H3 * H2), o_W3e = reserve((size_t)H3 * Ep);
+    const size_t o_W2 = reserve((size_t)H2 * H1), o_W1e = reserve((size_t)H1 * Ep);
+    const size_t o_b2 = reserve(H2), o_b4 = reserve(H4), o_b1 = reserve(H1), o_b3 = reserve(H3);
+    const size_t o_W1z_t = reserve((size_t)(L > 0 ? L : 1) * H1), o_W3z_t = reserve((size_t)(L > 0 ? L : 1) * H3);
+    memcpy(&host[o_dirs], dirs, sizeof(float) * 3 * D);
+    for (int n = 0; n < h1; ++n) {
+        for (int k = 0; k < E; ++k) {
+            host[o_W1e_t + (size_t)k * H1 + n] = W1[(size_t)n * in1 + k];
+            host[o_W1e + (size_t)n * Ep + k] = W1[(size_t)n * in1 + k];
+        }
+        for (int l = 0; l < L; ++l) host[o_W1z_t + (size_t)l * H1 + n] = W1[(size_t)n * in1 + E + l];
+        host[o_b1 + n] = b1 ? b1[n] : 0.f;
+    }
+    for (int n = 0; n < h2; ++n) {
+        for (int k = 0; k < h1; ++k) {
+            host[o_W2_t + (size_t)k * H2 + n] = W2[(size_t)n * h1 + k];
+            host[o_W2 + (size_t)n * H1 + k] = W2[(size_t)n * h1 + k];
+        }
+        host[o_b2 + n] = b2 ? b2[n] : 0.f;
+    }
+    for (int n = 0; n < h3; ++n) {
+        for (int k = 0; k < h2; ++k) {
+            host[o_W3h_t + (size_t)k * H3 + n] = W3[(size_t)n * in3 + k];
+            host[o_W3h + (size_t)n * H2 + k] = W3[(size_t)n * in3 + k];
+        }
+        if (d->res_state)
+            for (int k = 0; k < E; ++k) {
+                host[o_W3e_t + (size_t)k * H3 + n] = W3[(size_t)n * in3 + h2 + k];
+                host[o_W3e + (size_t)n * Ep + k] = W3[(size_t)n * in3 + h2 + k];
+            }
+        if (d->res_latent)
+            for (int l = 0; l < L; ++l) host[o_W3z_t + (size_t)l * H3 + n] = W3[(size_t)n * in3 + offz3 + l];
+        host[o_b3 + n] = b3 ? b3[n] : 0.f;
+    }
+    for (int n = 0; n < h4; ++n) {
+        for (int k = 0; k < h3; ++k) {
+            host[o_W4_t + (size_t)k * H4 + n] = W4[(size_t)n * h3 + k];
+            host[o_W4 + (size_t)n * H3 + k] = W4[(size_t)n * h3 + k];
+        }
+        host[o_b4 + n] = b4 ? b4[n] : 0.f;
+        host[o_W5 + n] = W5[n];
+    }
+    h->blob_floats = host.size();
+    cudaError_t e = cudaMalloc(&h->blob, host.size() * sizeof(float));
+    if (e != cudaSuccess) { delete h; return (int)e; }
+    e = cudaMemcpy(h->blob, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(h->blob); delete h; return (int)e; }
+    SdfNetDev& n = h->net;
+    n.D = D; n.F = F; n.E = E; n.Ep = Ep; n.H1 = H1; n.H2 = H2; n.H3 = H3; n.H4 = H4; n.L = L;
+    n.res_state = d->res_state ? 1 : 0; n.res_latent = d->res_latent ? 1 : 0; n.act = d->act;
+    n.w0 = d->w0; n.max_df = d->max_df; n.b5 = b5 ? b5[0] : 0.f;
+    const float* B = h->blob;
+    n.dirs = B + o_dirs; n.W1e_t = B + o_W1e_t; n.W2_t = B + o_W2_t; n.W3h_t = B + o_W3h_t; n.W3e_t = B + o_W3e_t;
+    n.W4_t = B + o_W4_t; n.W5 = B + o_W5; n.W4 = B + o_W4; n.W3h = B + o_W3h; n.W3e = B + o_W3e; n.W2 = B + o_W2;
+    n.W1e = B + o_W1e; n.b2 = B + o_b2; n.b4 = B + o_b4; n.b1 = B + o_b1; n.b3 = B + o_b3;
+    n.W1z_t = B + o_W1z_t; n.W3z_t = B + o_W3z_t;
+    h->smem = sdf_smem_bytes(n);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, dev);
+    h->sm_count = prop.multiProcessorCount;
+    if (h->smem > (size_t)prop.sharedMemPerBlockOptin) {
+        fprintf(stderr, "[sdfnmpc_b200] network too wide for the shared-memory tiling (%zu B needed)\n", h->smem);
+        cudaFree(h->blob); delete h; return SDFNMPC_E_INVALID;
+    }
+    e = cudaFuncSetAttribute(sdf_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
+    if (e != cudaSuccess) { cudaFree(h->blob); delete h; return (int)e; }
+    *out = h;
+    return 0;
+}
+
+extern "C" int sdfnmpc_sdf_destroy(sdfnmpc_sdf_t h) {
+    if (!h) return 0;
+    cudaFree(h->blob); cudaFree(h->b1f); cudaFree(h->b3f);
+    cudaFree(h->h_pts); cudaFree(h->h_out); cudaFree(h->h_lat);
+    delete h;
+    return 0;
+}
+
+extern "C" int sdfnmpc_sdf_set_latents(sdfnmpc_sdf_t h, const float* z, int32_t n_inst, void* stream) {
+    if (!h || n_inst < 1 || (!z && h->net.L > 0)) return SDFNMPC_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_inst > h->cap_inst) {
+        cudaFree(h->b1f); cudaFree(h->b3f);
+        h->b1f = h->b3f = nullptr; h->cap_inst = 0;
+        SDF_CUDA_CHECK(cudaMalloc(&h->b1f, (size_t)n_inst * h->net.H1 * sizeof(float)));
+        SDF_CUDA_CHECK(cudaMalloc(&h->b3f, (size_t)n_inst * h->net.H3 * sizeof(float)));
+        h->cap_inst = n_inst;
+    }
+    const int ncol = h->net.H1 + h->net.H3;
+    dim3 grid((ncol + 127) / 128, n_inst);
+    sdf_fold_latent_kernel<<<grid, 128, 0, st>>>(h->net, z, n_inst, h->b1f, h->b3f);
+    count_launch();
+    SDF_CUDA_CHECK(cudaGetLastError());
+    h->n_inst = n_inst;
+    return 0;
+}
+
+extern "C" int sdfnmpc_sdf_eval(sdfnmpc_sdf_t h, const float* pts, const int32_t* pt2inst, int32_t pts_per_inst,
+                                int64_t n, float* sdf, float* grad, void* stream) {
+    if (!h || !pts || n < 0 || n > 0x7fffffff || (!pt2inst && pts_per_inst < 1)) return SDFNMPC_E_INVALID;
+    if (h->n_inst < 1) return SDFNMPC_E_STATE;
+    if (!pt2inst && (n + pts_per_inst - 1) / pts_per_inst > h->n_inst) return SDFNMPC_E_INVALID;
+    if (n == 0) return 0;
+    const int64_t tiles = (n + SDF_TM - 1) / SDF_TM;
+    const int grid = (int)(tiles < (int64_t)h->sm_count * 8 ? tiles : (int64_t)h->sm_count * 8);
+    sdf_eval_kernel<<<grid, SDF_THREADS, h->smem, (cudaStream_t)stream>>>(h->net, pts, pt2inst, pts_per_inst, h->b1f,
+                                                                         h->b3f, (int)n, sdf, grad);
+    count_launch();
+    SDF_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int sdfnmpc_sdf_eval_host(sdfnmpc_sdf_t h, const float* pts, const float* latent, int64_t n, float* sdf, float* grad) {
+    if (!h || !pts || n < 1 || (!latent && h->net.L > 0)) return SDFNMPC_E_INVALID;
+    if ((size_t)n > h->h_cap) {
+        cudaFree(h->h_pts); cudaFree(h->h_out);
+        h->h_pts = h->h_out = nullptr; h->h_cap = 0;
+        SDF_CUDA_CHECK(cudaMalloc(&h->h_pts, (size_t)n * 3 * sizeof(float)));
+        SDF_CUDA_CHECK(cudaMalloc(&h->h_out, (size_t)n * 4 * sizeof(float)));
+        h->h_cap = (size_t)n;
+    }
+    if (!h->h_lat) SDF_CUDA_CHECK(cudaMalloc(&h->h_lat, (size_t)(h->net.L > 0 ? h->net.L : 1) * sizeof(float)));
+    SDF_CUDA_CHECK(cudaMemcpyAsync(h->h_pts, pts, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, 0));
+    if (h->net.L > 0) SDF_CUDA_CHECK(cudaMemcpyAsync(h->h_lat, latent, (size_t)h->net.L * sizeof(float), cudaMemcpyHostToDevice, 0));
+    if (int rc = sdfnmpc_sdf_set_latents(h, h->h_lat, 1, nullptr)) return rc;
+    if (int rc = sdfnmpc_sdf_eval(h, h->h_pts, nullptr, (int32_t)n, n, h->h_out, grad ? h->h_out + n : nullptr, nullptr)) return rc;
+    if (sdf) SDF_CUDA_CHECK(cudaMemcpyAsync(sdf, h->h_out, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, 0));
+    if (grad) SDF_CUDA_CHECK(cudaMemcpyAsync(grad, h->h_out + n, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, 0));
+    SDF_CUDA_CHECK(cudaStreamSynchronize(0));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// CasADi external-function ABI: the symbols of L4CasADi's libsdf_l4c.so
+// (sdf_nmpc/gen_model.py:38-39 -> name='sdf_l4c', with_jacobian=True; ocp.py:100-102).
+// double in / double out, column-major dense, batch 1, model evaluated in fp32.
+// ------------------------------------------------------------------------------------------
+namespace {
+std::mutex g_l4c_mu;
+sdfnmpc_sdf_t g_l4c = nullptr;
+bool g_l4c_owned = false;
+std::vector<float> g_l4c_in;
+casadi_int g_sp_in[3], g_sp_scalar[3] = {1, 1, 1}, g_sp_jac[3];
+
+int l4c_ready() {
+    if (g_l4c) return 0;
+    const char* path = getenv("SDFNMPC_L4C_BLOB");
+    if (!path) {
+        fprintf(stderr, "[sdfnmpc_b200] sdf_l4c called before sdfnmpc_l4c_bind() and SDFNMPC_L4C_BLOB is not set\n");
+        return SDFNMPC_E_STATE;
+    }
+    return sdfnmpc_l4c_load_blob(path);
+}
+
+int l4c_eval(const double* i0, double* val, double* jac) {
+    std::lock_guard<std::mutex> lk(g_l4c_mu);
+    if (int rc = l4c_ready()) return rc;
+    const int L = g_l4c->net.L, nin = 3 + L;
+    g_l4c_in.resize(nin);
+    for (int i = 0; i < nin; ++i) g_l4c_in[i] = (float)i0[i];   // L4CasADi casts the CasADi doubles to float32
+    float out[4] = {0, 0, 0, 0};
+    int rc = sdfnmpc_sdf_eval_host(g_l4c, g_l4c_in.data(), g_l4c_in.data() + 3, 1, out, jac ? out + 1 : nullptr);
+    if (rc) return rc;
+    if (val) *val = (double)out[0];
+    if (jac) {
+        for (int i = 0; i < nin; ++i) jac[i] = 0.0;   // latent columns: p is not a decision variable
+        jac[0] = out[1]; jac[1] = out[2]; jac[2] = out[3];
+    }
+    return 0;
+}
+}  // namespace
+
+extern "C" int sdfnmpc_l4c_bind(sdfnmpc_sdf_t h) {
+    std::lock_guard<std::mutex> lk(g_l4c_mu);
+    if (g_l4c && g_l4c_owned) sdfnmpc_sdf_destroy(g_l4c);
+    g_l4c = h;
+    g_l4c_owned = false;
+    return 0;
+}
+
+// Blob: int32 magic 'SDFB', int32 version, sdfnmpc_sdf_desc, then float arrays in the order of
+// sdfnmpc_sdf_create (dirs, W1, b1, ..., W5, b5).  Written by sdf_nmpc_b200.weights.save_sdf_blob.
+extern "C" int sdfnmpc_l4c_load_blob(const char* path) {
+    FILE* f = fopen(path, "rb");
+    if (!f) { fprintf(stderr, "[sdfnmpc_b200] cannot open %s\n", path); return SDFNMPC_E_INVALID; }
+    int32_t hdr[2];
+    sdfnmpc_sdf_desc d;
+    if (fread(hdr, sizeof(hdr), 1, f) != 1 || hdr[0] != 0x42464453 || fread(&d, sizeof(d), 1, f) != 1) { fclose(f); return SDFNMPC_E_INVALID; }
+    const int E = 3 + 2 * d.n_dirs * d.nb_freqs, L = d.size_latent;
+    const int in3 = d.hidden[1] + (d.res_state ? E : 0) + (d.res_latent ? L : 0);
+    const size_t sz[11] = {(size_t)3 * d.n_dirs, (size_t)d.hidden[0] * (E + L), (size_t)d.hidden[0],
+                           (size_t)d.hidden[1] * d.hidden[0], (size_t)d.hidden[1], (size_t)d.hidden[2] * in3,
+                           (size_t)d.hidden[2], (size_t)d.hidden[3] * d.hidden[2], (size_t)d.hidden[3],
+                           (size_t)d.hidden[3], 1};
+    std::vector<std::vector<float>> a(11);
+    for (int i = 0; i < 11; ++i) {
+        a[i].resize(sz[i]);
+        if (fread(a[i].data(), sizeof(float), sz[i], f) != sz[i]) { fclose(f); return SDFNMPC_E_INVALID; }
+    }
+    fclose(f);
+    sdfnmpc_sdf_t h = nullptr;
+    int rc = sdfnmpc_sdf_create(&h, &d, a[0].data(), a[1].data(), a[2].data(), a[3].data(), a[4].data(), a[5].data(),
+                                a[6].data(), a[7].data(), a[8].data(), a[9].data(), a[10].data());
+    if (rc) return rc;
+    if (g_l4c && g_l4c_owned) sdfnmpc_sdf_destroy(g_l4c);
+    g_l4c = h;
+    g_l4c_owned = true;
+    return 0;
+}
+
+static int l4c_nin() { return g_l4c ? 3 + g_l4c->net.L : 131; }
+
+#define SDFNMPC_CASADI_COMMON(F)                                                   \
+    extern "C" int F##_alloc_mem(void) { return 0; }                               \
+    extern "C" int F##_init_mem(int) { return 0; }                                 \
+    extern "C" void F##_free_mem(int) {}                                           \
+    extern "C" int F##_checkout(void) { return 0; }                                \
+    extern "C" void F##_release(int) {}                                            \
+    extern "C" void F##_incref(void) {}                                            \
+    extern "C" void F##_decref(void) {}                                            \
+    extern "C" double F##_default_in(casadi_int) { return 0.0; }
+
+SDFNMPC_CASADI_COMMON(sdf_l4c)
+SDFNMPC_CASADI_COMMON(jac_sdf_l4c)
+
+extern "C" int sdf_l4c(const double** arg, double** res, casadi_int*, double*, int) {
+    if (!arg || !arg[0]) return 1;
+    double v = 0.0;
+    if (l4c_eval(arg[0], &v, nullptr)) return 1;
+    if (res && res[0]) res[0][0] = v;
+    return 0;
+}
+extern "C" casadi_int sdf_l4c_n_in(void) { return 1; }
+extern "C" casadi_int sdf_l4c_n_out(void) { return 1; }
+extern "C" const char* sdf_l4c_name_in(casadi_int i) { return i == 0 ? "i0" : nullptr; }
+extern "C" const char* sdf_l4c_name_out(casadi_int i) { return i == 0 ? "o0" : nullptr; }
+extern "C" const casadi_int* sdf_l4c_sparsity_in(casadi_int i) {
+    if (i != 0) return nullptr;
+    g_sp_in[0] = l4c_nin(); g_sp_in[1] = 1; g_sp_in[2] = 1;   // dense: {nrow, ncol, 1}
+    return g_sp_in;
+}
+extern "C" const casadi_int* sdf_l4c_sparsity_out(casadi_int i) { return i == 0 ? g_sp_scalar : nullptr; }
+extern "C" int sdf_l4c_work(casadi_int* a, casadi_int* r, casadi_int* iw, casadi_int* w) {
+    if (a) *a = 1; if (r) *r = 1; if (iw) *iw = 0; if (w) *w = 0;
+    return 0;
+}
+
+extern "C" int jac_sdf_l4c(const double** arg, double** res, casadi_int*, double*, int) {
+    if (!arg || !arg[0]) return 1;
+    if (!res || !res[0]) return 0;
+    return l4c_eval(arg[0], nullptr, res[0]) ? 1 : 0;
+}
+extern "C" casadi_int jac_sdf_l4c_n_in(void) { return 2; }
+extern "C" casadi_int jac_sdf_l4c_n_out(void) { return 1; }
+extern "C" const char* jac_sdf_l4c_name_in(casadi_int i) { return i == 0 ? "i0" : (i == 1 ? "out_o0" : nullptr); }
+extern "C" const char* jac_sdf_l4c_name_out(casadi_int i) { return i == 0 ? "jac_o0_i0" : nullptr; }
+extern "C" const casadi_int* jac_sdf_l4c_sparsity_in(casadi_int i) {
+    if (i == 0) return sdf_l4c_sparsity_in(0);
+    return i == 1 ? g_sp_scalar : nullptr;
+}
+extern "C" const casadi_int* jac_sdf_l4c_sparsity_out(casadi_int i) {
+    if (i != 0) return nullptr;
+    g_sp_jac[0] = 1; g_sp_jac[1] = l4c_nin(); g_sp_jac[2] = 1;
+    return g_sp_jac;
+}
+extern "C" int jac_sdf_l4c_work(casadi_int* a, casadi_int* r, casadi_int* iw, casadi_int* w) {
+    if (a) *a = 2; if (r) *r = 1; if (iw) *iw = 0; if (w) *w = 0;
+    return 0;
+}

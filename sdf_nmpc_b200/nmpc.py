@@ -1,0 +1,300 @@
+"""Command interface of the controller, batched over independent NMPC instances.
+
+``BatchedNmpc`` keeps the method names and argument meaning of ``sdf_nmpc.controller.Nmpc``
+(``sdf_nmpc/controller.py:7-142``) with a leading batch axis; ``Nmpc`` is the single-instance view with
+the reference's exact signatures (numpy float64 in/out).  Where the reference pushes ``yref/W/p`` node
+by node into acados through ctypes and calls ``solve_for_x0`` (``sdf_nmpc/ocp.py:159-170``), this class
+hands device pointers to ``sdfnmpc_solver_rti_step`` (one SQP-RTI iteration for all instances).
+
+The per-node parameter matrix ``p[N+1, 145]`` of the reference (``controller.py:35,45-61``) is stored
+de-duplicated: flag, camera pose and latent are per instance (the reference writes the same value into
+every row), only ``q_d`` is per node.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import Config
+from .sdf import SdfEvaluator, _ptr, _stream
+
+NX, NU, NY, NYN, NH = 10, 4, 11, 4, 3
+
+
+class BatchedNmpc:
+    def __init__(self, cfg, sdf_net, batch, device='cuda:0'):
+        if cfg.mpc.model != 'att':
+            raise NotImplementedError("only mpc.model == 'att' (the reference default) is built so far")
+        self.cfg = cfg
+        self.B = int(batch)
+        self.N = int(cfg.mpc.N)
+        self.T = cfg.mpc.T
+        self.device = torch.device(device)
+        self.sdf = SdfEvaluator(sdf_net, device)
+        self.lib = self.sdf.lib
+        self.L = self.sdf.size_latent
+        lim = cfg.robot.limits
+        self.g = 9.81
+        self.dt = cfg.shooting_dt()
+        lh, uh = cfg.h_bounds(self.sdf.max_df)
+        zl, Zl = cfg.slack_weights()
+        d = _lib.SolverDesc()
+        d.N, d.max_batch, d.qp_iter_max, d.h_at_node0 = self.N, self.B, int(cfg.b200.qp_iter_max), int(bool(cfg.b200.h_at_node0))
+        d.lm, d.qp_tol, d.qp_tol_res = float(cfg.mpc.lm_reg), float(cfg.b200.qp_tol), float(cfg.b200.qp_tol_res)
+        d.g, d.gamma, d.roll, d.pitch, d.wz, d.mass = self.g, lim.gamma, lim.roll, lim.pitch, lim.wz, cfg.robot.mass
+        d.cam_off = (C.c_double * 3)(*cfg.cam_offset())
+        d.lbu = (C.c_double * 4)(0, -1, -1, -1)           # quad_rollpitchyawrate.py:58-59
+        d.ubu = (C.c_double * 4)(1, 1, 1, 1)
+        d.lh, d.uh = (C.c_double * 3)(*lh), (C.c_double * 3)(*uh)
+        d.zl, d.Zl = (C.c_double * 3)(*zl), (C.c_double * 3)(*Zl)
+        for k in range(self.N):
+            d.dt[k] = float(self.dt[k])
+        self.handle = C.c_void_p()
+        _lib.check(self.lib.sdfnmpc_solver_create(C.byref(self.handle), C.byref(d), self.sdf.handle), 'sdfnmpc_solver_create')
+        # command clipping (controller.py:18-26)
+        self.cmd_TRPYr_hover = np.array([cfg.robot.mass * self.g, 0, 0, 0])
+        self.cmd_TRPYr_min = [0, -lim.roll, -lim.pitch, -lim.wz]
+        self.cmd_TRPYr_max = [lim.gamma, lim.roll, lim.pitch, lim.wz]
+        f64 = dict(dtype=torch.float64, device=self.device)
+        B, N = self.B, self.N
+        self.u0 = torch.zeros(B, NU, **f64)
+        self.status = torch.zeros(B, dtype=torch.int32, device=self.device)
+        self.qp_iters = torch.zeros(B, dtype=torch.int32, device=self.device)
+        self._pin = {}
+        self.reset()
+
+    def __del__(self):
+        h = getattr(self, 'handle', None)
+        if h:
+            self.lib.sdfnmpc_solver_destroy(h)
+            self.handle = None
+
+    # ------------------------------------------------------------------ state ----------
+    def _t(self, a, shape=None, dtype=torch.float64):
+        t = torch.as_tensor(a, dtype=dtype, device=self.device)
+        return t.reshape(shape).contiguous() if shape is not None else t.contiguous()
+
+    def reset(self):
+        """controller.py:32-42."""
+        f64 = dict(dtype=torch.float64, device=self.device)
+        B, N = self.B, self.N
+        self.x0 = None
+        self.flag = torch.zeros(B, **f64)
+        self.pose = torch.zeros(B, 12, **f64)            # W_p_Co(3), W_R_Co row-major(9)
+        self.qd = torch.zeros(B, N + 1, 4, **f64)
+        self.latent = torch.zeros(B, max(self.L, 1), dtype=torch.float32, device=self.device)
+        self.y = torch.zeros(B, N, NY, **f64)
+        self.yN = torch.zeros(B, NYN, **f64)
+        self.W = torch.zeros(B, N, NY, **f64)
+        self.WN = torch.zeros(B, NYN, **f64)
+        self.fail_count = torch.zeros(B, dtype=torch.int64, device=self.device)
+        self._latent_dirty = True
+        self.set_sdf_flag(False)
+
+    def set_sdf_flag(self, flag):
+        """controller.py:45-47 (scalar or per-instance)."""
+        self.flag[:] = self._t(flag).to(torch.float64)
+
+    def set_latent(self, latent, W_p_Bo, W_R_Bo):
+        """controller.py:50-54: camera-observation pose from the body pose at image time + latent."""
+        R = self._t(W_R_Bo, (-1, 3, 3))
+        p = self._t(W_p_Bo, (-1, 3))
+        BpC = self._t(np.asarray(self.cfg.sensor.B_p_C, float))
+        BRC = self._t(np.asarray(self.cfg.sensor.B_R_C, float))
+        self.pose[:, 0:3] = R @ BpC + p
+        self.pose[:, 3:12] = (R @ BRC).reshape(-1, 9)
+        self.latent[:] = self._t(latent, (-1, max(self.L, 1)), torch.float32)
+        self._latent_dirty = True
+
+    def reset_latent(self):
+        self.pose.zero_()
+        self.latent.zero_()
+        self._latent_dirty = True
+
+    def set_x0(self, x0):
+        """controller.py:65-69: the first call initialises the trajectory (ocp.py:144-149)."""
+        x0 = self._t(x0, (self.B, -1))[:, :NX].contiguous()
+        if self.x0 is None:
+            _lib.check(self.lib.sdfnmpc_solver_init_traj(self.handle, _ptr(x0), self.B, _stream()), 'init_traj')
+        self.x0 = x0
+
+    def set_ref_arrays(self, yref, W, yrefN, WN, qd):
+        self.y[:] = self._t(yref, (self.B, self.N, NY))
+        self.W[:] = self._t(W, (self.B, self.N, NY))
+        self.yN[:] = self._t(yrefN, (self.B, NYN))
+        self.WN[:] = self._t(WN, (self.B, NYN))
+        self.qd[:] = self._t(qd, (self.B, self.N + 1, 4))
+
+    @staticmethod
+    def formate_ref(ref):
+        """quad_rollpitchyawrate.py:62-65."""
+        yr = np.concatenate([ref.p, [0], ref.v, [0, 0], [ref.wz], [0]])
+        W = np.concatenate([ref.Wp, [ref.Wq[2]], ref.Wv, ref.Wq[:2], ref.Ww[2:], [ref.Wa]])
+        return yr, W
+
+    def set_ref(self, ref, k, instance=None):
+        """controller.py:133-142 for one node (all instances, or one)."""
+        sel = slice(None) if instance is None else instance
+        y, W = self.formate_ref(ref)
+        self.qd[sel, k] = self._t(np.asarray(ref.q, float))
+        if k < self.N:
+            self.y[sel, k] = self._t(y)
+            self.W[sel, k] = self._t(W)
+        else:
+            self.yN[sel] = self._t(y[:NYN])
+            self.WN[sel] = self._t(W[:NYN])
+
+    # ------------------------------------------------------------------ control iteration ----------
+    def shift(self, k=None):
+        k = self.cfg.mpc.shift if k is None else k
+        if k > 0:
+            _lib.check(self.lib.sdfnmpc_solver_shift(self.handle, self.B, int(k), _stream()), 'shift')
+
+    def solve(self):
+        """controller.py:72-81 - one SQP-RTI iteration for every instance; returns fail_count [B]."""
+        if self.x0 is None:
+            raise _lib.SdfNmpcError('set_x0 must be called before solve')
+        self.shift()
+        lat = _ptr(self.latent) if self._latent_dirty else C.c_void_p(0)
+        _lib.check(self.lib.sdfnmpc_solver_rti_step(
+            self.handle, self.B, _ptr(self.x0), _ptr(self.y), _ptr(self.W), _ptr(self.yN), _ptr(self.WN), _ptr(self.qd),
+            _ptr(self.pose), _ptr(self.flag), lat, _ptr(self.u0), _ptr(self.status), _ptr(self.qp_iters), _stream()),
+            'sdfnmpc_solver_rti_step')
+        self._latent_dirty = False
+        ok = self.status == 0
+        self.fail_count = torch.where(ok, torch.zeros_like(self.fail_count), self.fail_count + 1)
+        return self.fail_count
+
+    def solve_host(self, x0, out=None):
+        """End-to-end step with HOST buffers: pinned H2D of the state feedback, solve, D2H of the controls."""
+        pin = self._pin.get('x0')
+        if pin is None:
+            pin = self._pin['x0'] = torch.empty(self.B, NX, dtype=torch.float64).pin_memory()
+            self._pin['u0'] = torch.empty(self.B, NU, dtype=torch.float64).pin_memory()
+            self._pin['st'] = torch.empty(self.B, dtype=torch.int32).pin_memory()
+            self._pin['x0d'] = torch.empty(self.B, NX, dtype=torch.float64, device=self.device)
+        pin.copy_(torch.as_tensor(x0, dtype=torch.float64).reshape(self.B, -1)[:, :NX])
+        self._pin['x0d'].copy_(pin, non_blocking=True)
+        self.set_x0(self._pin['x0d'])
+        self.solve()
+        self._pin['u0'].copy_(self.u0, non_blocking=True)
+        self._pin['st'].copy_(self.status, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self._pin['u0'].numpy(), self._pin['st'].numpy()
+
+    # ------------------------------------------------------------------ getters ----------
+    def _state_ptrs(self):
+        ptrs = [C.c_void_p() for _ in range(4)]
+        _lib.check(self.lib.sdfnmpc_solver_state(self.handle, *[C.byref(p) for p in ptrs]), 'solver_state')
+        return ptrs
+
+    def _view(self, ptr, shape, dtype):
+        # zero-copy torch view of library-owned device memory, then a stream-ordered copy
+        class _Dev:
+            pass
+        d = _Dev()
+        d.__cuda_array_interface__ = dict(shape=tuple(int(s) for s in shape), typestr='<f8' if dtype == torch.float64 else '<f4',
+                                          data=(int(ptr.value), False), version=2)
+        return torch.as_tensor(d, device=self.device).clone()
+
+    def get_matrices(self):
+        """controller.py:84-92 -> (x [B,N+1,10], u [B,N,4]) device tensors (copies)."""
+        xb, ub, _, _ = self._state_ptrs()
+        return (self._view(xb, (self.B, self.N + 1, NX), torch.float64), self._view(ub, (self.B, self.N, NU), torch.float64))
+
+    def get_multipliers(self):
+        """QP multipliers of the last step: lam_hard [B,N,8] (lbu, ubu), lam_soft [B,N+1,6] (lh, uh)."""
+        _, _, lh, ls = self._state_ptrs()
+        return (self._view(lh, (self.B, self.N, 2 * NU), torch.float64), self._view(ls, (self.B, self.N + 1, 2 * NH), torch.float64))
+
+    def get_diag(self):
+        ptrs = [C.c_void_p() for _ in range(3)]
+        _lib.check(self.lib.sdfnmpc_solver_diag(self.handle, *[C.byref(p) for p in ptrs]), 'solver_diag')
+        return (self._view(ptrs[0], (self.B, self.N + 1, NH), torch.float64), self._view(ptrs[1], (self.B, self.N + 1), torch.float32),
+                self._view(ptrs[2], (self.B, self.N + 1, 3), torch.float32))
+
+    def get_u(self):
+        return self.u0
+
+    def get_cmd_TRPYr(self):
+        """controller.py:106-108: [gamma*mass, roll, pitch, wz] clipped."""
+        cmd = torch.empty(self.B, 4, dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.sdfnmpc_cmd_trpyr(self.handle, self.B, _ptr(self.u0), _ptr(cmd), _stream()), 'cmd_trpyr')
+        return cmd
+
+    def get_openloop_traj(self):
+        """controller.py:116-122: predicted (position, quaternion) per node, node 0 = x0."""
+        x, _ = self.get_matrices()
+        x[:, 0] = self.x0
+        return x[:, :, 0:3], x[:, :, 3:7]
+
+    def eval(self, k):
+        """controller.py:125-130: SDF value at node k of the current solution, ignoring the flag."""
+        x, _ = self.get_matrices()
+        R = self.pose[:, 3:12].reshape(-1, 3, 3)
+        c0 = torch.einsum('bji,bj->bi', R, x[:, k, 0:3] - self.pose[:, 0:3]).to(torch.float32)
+        if self._latent_dirty:
+            self.sdf.set_latents(self.latent)
+        d, _ = self.sdf.eval(c0, pts_per_inst=1, want_grad=False)
+        return d
+
+    def plant_step(self, x, u, dt):
+        """x <- RK4(x, u, dt) with the controller's own model (closed-loop rollouts)."""
+        _lib.check(self.lib.sdfnmpc_plant_step(self.handle, x.shape[0], _ptr(x), _ptr(u), float(dt), _stream()), 'plant_step')
+        return x
+
+
+class Nmpc:
+    """Single-instance facade with the reference's signatures (``sdf_nmpc/controller.py``)."""
+
+    def __init__(self, cfg, sdf_net, rebuild=False, device='cuda:0'):
+        self.cfg = cfg if isinstance(cfg, Config) else Config(cfg)
+        self._b = BatchedNmpc(self.cfg, sdf_net, 1, device)
+        self.N, self.T = self._b.N, self._b.T
+        self.fail_count = 0
+
+    def reset(self):
+        self._b.reset()
+        self.fail_count = 0
+
+    def set_sdf_flag(self, flag):
+        self._b.set_sdf_flag(float(flag))
+
+    def set_latent(self, latent, W_p_Bo, W_R_Bo):
+        self._b.set_latent(np.asarray(latent, np.float32).reshape(1, -1), np.asarray(W_p_Bo, float).reshape(1, 3),
+                           np.asarray(W_R_Bo, float).reshape(1, 3, 3))
+
+    def reset_latent(self):
+        self._b.reset_latent()
+
+    def set_x0(self, x0):
+        self.x0 = np.asarray(x0, float)[:NX]
+        self._b.set_x0(self.x0.reshape(1, -1))
+
+    def set_ref(self, ref, k):
+        self._b.set_ref(ref, k)
+
+    def solve(self):
+        self.fail_count = int(self._b.solve()[0].item())
+        if self.fail_count:
+            print('solver failed: status', int(self._b.status[0].item()))
+        return self.fail_count
+
+    def get_u(self):
+        return self._b.u0[0].cpu().numpy()
+
+    def get_matrices(self):
+        x, u = self._b.get_matrices()
+        return x[0].cpu().numpy(), u[0].cpu().numpy()
+
+    def get_cmd_TRPYr(self):
+        return self._b.get_cmd_TRPYr()[0].cpu().numpy()
+
+    def get_openloop_traj(self):
+        p, q = self._b.get_openloop_traj()
+        p, q = p[0].cpu().numpy(), q[0].cpu().numpy()
+        return [(p[k], q[k]) for k in range(self.N + 1)]
+
+    def eval(self, k):
+        return self._b.eval(k).cpu().numpy()

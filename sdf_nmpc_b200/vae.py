@@ -1,0 +1,97 @@
+"""Depth-image encoder wrapper, batched - host mirror of ``sdf_nmpc.vae.VaeWrapper``
+(``sdf_nmpc/vae.py:7-45``): ``set_img`` + ``encode`` keep their names and meaning, with an optional leading
+batch axis.  Preprocessing (``utils/preprocessing.py``: ToDevice, Reshape, ClipDistance, Depth2Range) is fused
+into the first convolution kernel; the decoder (visualisation only) is out of scope.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .sdf import _ptr, _stream
+
+
+def _fp(a):
+    return a.ctypes.data_as(_lib.FP)
+
+
+class VaeWrapper:
+    """``enc_net``: dict as produced by ``weights.encoder_from_module`` / ``synth.make_encoder_net``."""
+
+    def __init__(self, cfg, enc_net, max_batch=1, device='cuda:0'):
+        if not torch.cuda.is_available():
+            raise _lib.SdfNmpcError('CUDA is not available: sdf_nmpc_b200 has no CPU path')
+        self.cfg = cfg
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        s = cfg.sensor
+        self.H, self.W = int(s.shape_imgs[-2]), int(s.shape_imgs[-1])
+        self.L = int(enc_net['size_latent'])
+        self.max_batch = int(max_batch)
+        d = _lib.EncoderDesc(self.H, self.W, self.L, self.max_batch, int(bool(s.is_depth)), int(bool(s.is_normalized)),
+                             float(s.dmax / s.mm_resolution * 1000), float(s.hfov), float(s.vfov))
+        self._keep = []
+
+        def arr(a):
+            a = np.ascontiguousarray(a, np.float32)
+            self._keep.append(a)
+            return _fp(a)
+
+        w = _lib.EncoderWeights()
+        w.conv0_w, w.conv0_b = arr(enc_net['conv0_w']), arr(enc_net['conv0_b'])
+        null = C.cast(None, _lib.FP)
+        for i, blk in enumerate(enc_net['blocks']):
+            w.conv1_w[i], w.conv2_w[i] = arr(blk['conv1_w']), arr(blk['conv2_w'])
+            for j, key in enumerate(('weight', 'bias', 'mean', 'var')):
+                w.bn1[i][j], w.bn2[i][j] = arr(blk['bn1'][key]), arr(blk['bn2'][key])
+                w.sc_bn[i][j] = arr(blk['sc_bn'][key]) if 'sc_bn' in blk else null
+            w.sc_w[i] = arr(blk['sc_w']) if 'sc_w' in blk else null
+        w.mean_w, w.mean_b = arr(enc_net['mean_w']), arr(enc_net['mean_b'])
+        w.bn_eps = float(enc_net['blocks'][0]['bn1'].get('eps', 1e-5))
+        self.handle = C.c_void_p()
+        _lib.check(self.lib.sdfnmpc_encoder_create(C.byref(self.handle), C.byref(d), C.byref(w)), 'sdfnmpc_encoder_create')
+        self.img = None
+        self.latent = None
+
+    def __del__(self):
+        h = getattr(self, 'handle', None)
+        if h:
+            self.lib.sdfnmpc_encoder_destroy(h)
+            self.handle = None
+
+    def set_img(self, img):
+        """Raw sensor image(s) [H,W] or [B,H,W] (numpy or tensor), as ``vae.py:31-32`` takes them."""
+        t = torch.as_tensor(img)
+        t = t.to(self.device, torch.float32, non_blocking=True).reshape(-1, t.shape[-2], t.shape[-1])
+        if tuple(t.shape[-2:]) != (self.H, self.W):   # Reshape (preprocessing.py:92-96)
+            t = torch.nn.functional.interpolate(t[:, None], size=(self.H, self.W), mode='bilinear')[:, 0]
+        self.img = t.contiguous()
+
+    def encode(self, to_numpy=True):
+        """``vae.py:37-40``: latent mean(s) [B, L]."""
+        B = self.img.shape[0]
+        out = torch.empty(B, self.L, dtype=torch.float32, device=self.device)
+        for s in range(0, B, self.max_batch):
+            n = min(self.max_batch, B - s)
+            _lib.check(self.lib.sdfnmpc_encoder_encode(self.handle, _ptr(self.img[s:s + n]), n, _ptr(out[s:s + n]), _stream()),
+                       'sdfnmpc_encoder_encode')
+        self.latent = out
+        return out.cpu().numpy() if to_numpy else out
+
+    def encode_host(self, imgs):
+        """numpy in / numpy out through the C ABI with host buffers (H2D + D2H inside the call)."""
+        imgs = np.ascontiguousarray(imgs, np.float32).reshape(-1, self.H, self.W)
+        out = np.empty((imgs.shape[0], self.L), np.float32)
+        for s in range(0, imgs.shape[0], self.max_batch):
+            n = min(self.max_batch, imgs.shape[0] - s)
+            _lib.check(self.lib.sdfnmpc_encoder_encode_host(self.handle, imgs[s:s + n].ctypes.data_as(C.c_void_p), n,
+                                                            out[s:s + n].ctypes.data_as(C.c_void_p)), 'encode_host')
+        return out
+
+    def set_latent(self, latent):
+        self.latent = torch.as_tensor(latent, dtype=torch.float32, device=self.device)
+
+    def decode(self):
+        raise NotImplementedError('the VAE decoder is visualisation-only and out of scope (SURVEY.md 2.1 #12)')

@@ -1,0 +1,63 @@
+"""GPU parity of the batched depth encoder (fused preprocessing + conv stack) through the C ABI, against the
+committed outputs of the reference's own torch pipeline (tests/golden/encoder.npz) and the numpy oracle.
+Tolerance: 1e-4 max-norm relative on the latent (not fixed by north_star)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, relmax
+
+pytestmark = pytest.mark.gpu
+LAT_TOL = 1e-4
+
+
+def _cfg(spherical):
+    from sdf_nmpc_b200.config import Config
+    cfg = Config()
+    if spherical:
+        cfg.sensor.is_depth = False
+        cfg.sensor.is_spherical = True
+        cfg.sensor.vfov = cfg.sensor.hfov / cfg.sensor.aspect_ratio
+    return cfg
+
+
+@pytest.mark.parametrize('tag,spherical', [('depth', False), ('range', True)])
+def test_encoder_matches_reference_fixture(tag, spherical, cuda_device):
+    from sdf_nmpc_b200 import synth
+    from sdf_nmpc_b200.vae import VaeWrapper
+    G = np.load(os.path.join(GOLDEN, 'encoder.npz'))
+    net = synth.make_encoder_net(seed=int(G['seed']))
+    frames = np.stack([synth.depth_frame(seed=int(G['frame_seed0']) + i, spherical=spherical) for i in range(2)])
+    cfg = _cfg(spherical)
+    if spherical:   # the fixture used the default vfov for the range case (no Depth2Range, so fov is unused)
+        cfg.sensor.vfov = 0.4903
+    vae = VaeWrapper(cfg, net, max_batch=2, device=cuda_device)
+    vae.set_img(frames)
+    lat = vae.encode()
+    assert lat.shape == (2, 128)
+    assert relmax(lat, G['latent_' + tag]) <= LAT_TOL, relmax(lat, G['latent_' + tag])
+    assert relmax(lat, G['latent64_' + tag]) <= LAT_TOL
+    # single-image call as the reference makes it (set_img(img[H,W]); encode() -> [1, L])
+    vae.set_img(frames[1])
+    one = vae.encode()
+    assert one.shape == (1, 128) and np.array_equal(one[0], lat[1])
+    # host-buffer entry point and batch splitting (max_batch 2, 3 frames)
+    three = vae.encode_host(np.concatenate([frames, frames[:1]]))
+    assert np.array_equal(three[:2], lat) and np.array_equal(three[2], lat[0])
+
+
+def test_encoder_vs_oracle_random_weights(cuda_device):
+    from oracle import encoder as OE
+    from sdf_nmpc_b200 import synth
+    from sdf_nmpc_b200.vae import VaeWrapper
+    net = synth.make_encoder_net(seed=11)
+    frames = np.stack([synth.depth_frame(seed=40 + i) for i in range(3)])
+    frames[2, :, :] = 0.0      # all-invalid frame
+    frames[1, 100:, :] = 9.0   # beyond dmax -> clipped
+    cfg = _cfg(False)
+    vae = VaeWrapper(cfg, net, max_batch=4, device=cuda_device)
+    vae.set_img(frames)
+    lat = vae.encode()
+    ref = OE.encode(net, OE.preprocess(frames))
+    assert relmax(lat, ref) <= LAT_TOL, relmax(lat, ref)
