@@ -110,6 +110,10 @@ int sdfnmpc_solver_state(sdfnmpc_solver_t h, double** xbar_dev, double** ubar_de
                          double** lam_soft_dev);
 /* h values of the last linearisation [cap][N+1][3] and SDF query results d [cap][N+1], grad [cap][N+1][3]. */
 int sdfnmpc_solver_diag(sdfnmpc_solver_t h, double** hval_dev, float** sdf_d_dev, float** sdf_g_dev);
+/* Per-kernel device timing of the next <= max_steps rti_step calls (CUDA events on the launching stream):
+ * ms3 = summed milliseconds of {linearise, sdf, qp}; steps = number of timed calls. */
+int sdfnmpc_solver_timing_begin(sdfnmpc_solver_t h, int32_t max_steps);
+int sdfnmpc_solver_timing_end(sdfnmpc_solver_t h, float* ms3, int32_t* steps);
 /* RK4 plant step with the same model: x <- phi(x, u, dt) for closed-loop rollouts. */
 int sdfnmpc_plant_step(sdfnmpc_solver_t h, int32_t B, double* x_dev, const double* u_dev, double dt, void* stream);
 /* u_to_TRPYr + clip (controller.py:106-108): cmd [B][4]. */

@@ -40,6 +40,8 @@ def solve_dense(P, q, G, d, soft, z, Z, tol=1e-8, max_iter=100, mu0=1.0, verbose
     iters = np.zeros(B, int)
     status = np.full(B, 2, int)
     done = np.zeros(B, bool)
+    safe = np.zeros(B, bool)
+    hist = []
     s_safe = lambda: np.where(soft[None], s, 1.0)
     GT = np.swapaxes(G, 1, 2)
     for it in range(max_iter + 1):
@@ -98,14 +100,21 @@ def solve_dense(P, q, G, d, soft, z, Z, tol=1e-8, max_iter=100, mu0=1.0, verbose
                 a = np.where(mask, a, np.inf)
             return np.minimum(a.min(1), 1e30)
 
+        # Mehrotra's corrector can cycle on poorly centred iterates: once the largest product has not dropped
+        # by 30 % over two iterations an instance switches to plain damped path following (sigma >= 0.2, no
+        # second-order term).  [robustness heuristic of this repository, not HPIPM's]
+        hist.append(cmax.copy())
+        if it >= 2:
+            safe |= cmax > 0.7 * hist[-3]
+        so = np.where(safe, 0.0, 1.0)[:, None]
         dv, ds, dt, dl, dm = newton(-lam * t, -mu * s)
         a_aff = np.minimum(1.0, np.minimum.reduce([max_step(t, dt), max_step(lam, dl),
                                                    max_step(s, ds, soft[None]), max_step(mu, dm, soft[None])]))
         aa = a_aff[:, None]
         mu_aff = ((lam + aa * dl) * (t + aa * dt) + (mu + aa * dm) * (s + aa * ds)).sum(1) / ncomp
-        sig = np.clip((mu_aff / np.maximum(mubar, 1e-300)) ** 3, 0.0, 1.0)
+        sig = np.clip((mu_aff / np.maximum(mubar, 1e-300)) ** 3, np.where(safe, 0.2, 0.0), 1.0)
         tau = np.maximum(sig * mubar, 0.1 * tol)[:, None]   # do not drive products below the tolerance
-        dv, ds, dt, dl, dm = newton(tau - lam * t - dl * dt, (tau - mu * s - dm * ds) * sf)
+        dv, ds, dt, dl, dm = newton(tau - lam * t - so * dl * dt, (tau - mu * s - so * dm * ds) * sf)
         a = np.minimum(1.0, 0.995 * np.minimum.reduce([max_step(t, dt), max_step(lam, dl),
                                                        max_step(s, ds, soft[None]), max_step(mu, dm, soft[None])]))
         a = np.where(done, 0.0, a)[:, None]

@@ -37,6 +37,9 @@ struct sdfnmpc_solver {
     float *qpts = nullptr, *sdf_d = nullptr, *sdf_g = nullptr;
     double *work = nullptr, *lam_hard = nullptr, *lam_soft = nullptr;
     size_t work_per_inst = 0;
+    // optional per-kernel timing (bench.py roofline): 4 events per step on the launching stream
+    std::vector<cudaEvent_t> ev;
+    int ev_steps = 0, ev_cap = 0;
 };
 
 __global__ void nmpc_linearize_kernel(ModelConst mc, int N, int B, LinIn in, LinOut out) {
@@ -188,6 +191,7 @@ extern "C" int sdfnmpc_solver_destroy(sdfnmpc_solver_t h) {
     void* ptrs[] = {h->dt, h->xbar, h->ubar, h->AB, h->bdyn, h->J, h->yres, h->C, h->hval, h->qpts, h->sdf_d, h->sdf_g,
                     h->work, h->lam_hard, h->lam_soft};
     for (void* p : ptrs) cudaFree(p);
+    for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     delete h;
     return 0;
 }
@@ -225,13 +229,18 @@ extern "C" int sdfnmpc_solver_rti_step(sdfnmpc_solver_t h, int32_t B, const doub
     } else if (h->sdf->n_inst < B) {
         return SDFNMPC_E_STATE;
     }
+    const bool tm = h->ev_cap > 0 && h->ev_steps < h->ev_cap;
+    cudaEvent_t* ev = tm ? &h->ev[(size_t)h->ev_steps * 4] : nullptr;
+    if (tm) cudaEventRecord(ev[0], st);
     LinIn in{h->xbar, h->ubar, yref, yrefN, qd, pose, flag, h->dt};
     LinOut lo{h->AB, h->bdyn, h->J, h->yres, h->C, h->hval, h->qpts};
     const long long total = (long long)B * (N + 1) * NW;
     nmpc_linearize_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(h->sc.mc, N, B, in, lo);
     count_launch();
     SDF_CUDA_CHECK(cudaGetLastError());
+    if (tm) cudaEventRecord(ev[1], st);
     if (int rc = sdfnmpc_sdf_eval(h->sdf, h->qpts, nullptr, N + 1, (int64_t)B * (N + 1), h->sdf_d, h->sdf_g, stream)) return rc;
+    if (tm) cudaEventRecord(ev[2], st);
     QpBatch q;
     q.AB = h->AB; q.bdyn = h->bdyn; q.J = h->J; q.yres = h->yres; q.W = W; q.WN = WN; q.dt = h->dt; q.pose = pose;
     q.x0 = x0; q.flag = flag; q.C = h->C; q.hval = h->hval; q.xbar = h->xbar; q.ubar = h->ubar; q.work = h->work;
@@ -240,6 +249,35 @@ extern "C" int sdfnmpc_solver_rti_step(sdfnmpc_solver_t h, int32_t B, const doub
     nmpc_qp_kernel<<<(B + QP_WARPS - 1) / QP_WARPS, QP_WARPS * 32, 0, st>>>(h->sc, B, q);
     count_launch();
     SDF_CUDA_CHECK(cudaGetLastError());
+    if (tm) { cudaEventRecord(ev[3], st); h->ev_steps++; }
+    return 0;
+}
+
+extern "C" int sdfnmpc_solver_timing_begin(sdfnmpc_solver_t h, int32_t max_steps) {
+    if (!h || max_steps < 0) return SDFNMPC_E_INVALID;
+    while ((int)h->ev.size() < 4 * max_steps) {
+        cudaEvent_t e;
+        SDF_CUDA_CHECK(cudaEventCreate(&e));
+        h->ev.push_back(e);
+    }
+    h->ev_cap = max_steps;
+    h->ev_steps = 0;
+    return 0;
+}
+
+extern "C" int sdfnmpc_solver_timing_end(sdfnmpc_solver_t h, float* ms3, int32_t* steps) {
+    if (!h || !ms3) return SDFNMPC_E_INVALID;
+    ms3[0] = ms3[1] = ms3[2] = 0.f;
+    for (int s = 0; s < h->ev_steps; ++s) {
+        SDF_CUDA_CHECK(cudaEventSynchronize(h->ev[(size_t)s * 4 + 3]));
+        for (int k = 0; k < 3; ++k) {
+            float ms = 0.f;
+            SDF_CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev[(size_t)s * 4 + k], h->ev[(size_t)s * 4 + k + 1]));
+            ms3[k] += ms;
+        }
+    }
+    if (steps) *steps = h->ev_steps;
+    h->ev_cap = 0;
     return 0;
 }
 

@@ -218,6 +218,8 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
     L.sync();
 
     int status = 2, it = 0;
+    bool safe = false;              // conservative mode after a stall: more centering, no second-order term
+    double cm_prev1 = 1e300, cm_prev2 = 1e300;
     for (;; ++it) {
         // ================= residuals and convergence =================
         double res = 0.0, cmax = 0.0, csum = 0.0;
@@ -287,6 +289,11 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
         // two passes: 0 = affine (predictor, with factorisation), 1 = corrector (vector only).
         // The Newton system is solved in DELTA form (right-hand sides are residuals), so the step keeps
         // full relative accuracy when the iterate is close to the solution.
+        // Mehrotra's corrector can cycle on poorly centred iterates; if the largest complementarity product
+        // has not dropped by 30 % over two iterations switch (for good) to plain damped path following.
+        if (it >= 2 && cmax > 0.7 * cm_prev2) safe = true;
+        cm_prev2 = cm_prev1; cm_prev1 = cmax;
+        const double so = safe ? 0.0 : 1.0;
         double tau = 0.0;
         for (int pass = 0; pass < 2; ++pass) {
             // ---------- per-row elimination coefficients -> net Theta~ and c per node ----------
@@ -546,16 +553,16 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                 const double aa = fmin(1.0, amax);
                 for (int e = lane; e < nhr; e += NL) {
                     csum_aff += (lb[e] + aa * dlb[e]) * (tb[e] + aa * dtb[e]);
-                    pab[e] = dlb[e] * dtb[e];
+                    pab[e] = so * dlb[e] * dtb[e];
                 }
                 for (int e = lane + k0 * 2 * NH; e < nsr; e += NL) {
                     csum_aff += (ls[e] + aa * dls[e]) * (ts[e] + aa * dts[e]) + (ms[e] + aa * dms[e]) * (ss[e] + aa * dss[e]);
-                    pas[e] = dls[e] * dts[e];
-                    pbs[e] = dms[e] * dss[e];
+                    pas[e] = so * dls[e] * dts[e];
+                    pbs[e] = so * dms[e] * dss[e];
                 }
                 const double mu_aff = L.sum(csum_aff) / ncomp;
                 double sig = mu_aff / fmax(mubar, 1e-300);
-                sig = fmin(fmax(sig * sig * sig, 0.0), 1.0);
+                sig = fmin(fmax(sig * sig * sig, safe ? 0.2 : 0.0), 1.0);
                 tau = fmax(sig * mubar, 0.1 * P.tol);
                 L.sync();
             } else {
@@ -579,6 +586,14 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                     L.sync();
                 }
                 const double al = fmin(1.0, 0.995 * amax);
+#if defined(SDFNMPC_QP_DEBUG) && !defined(__CUDA_ARCH__)
+                {
+                    int wb = -1, ws = -1; double mb = 1e30, msv = 1e30; int which = 0;
+                    for (int e = 0; e < nhr; ++e) { double a1 = step_to_boundary(tb[e], dtb[e]), a2 = step_to_boundary(lb[e], dlb[e]); if (fmin(a1,a2) < mb) { mb = fmin(a1,a2); wb = e; } }
+                    for (int e = k0 * 2 * NH; e < nsr; ++e) { double a[4] = {step_to_boundary(ts[e], dts[e]), step_to_boundary(ls[e], dls[e]), step_to_boundary(ss[e], dss[e]), step_to_boundary(ms[e], dms[e])}; for (int q = 0; q < 4; ++q) if (a[q] < msv) { msv = a[q]; ws = e; which = q; } }
+                    printf("   alpha %.3e tau %.3e mubar %.3e | hard row %d a=%.3e (t %.3e l %.3e) | soft row %d var %d a=%.3e (t %.3e l %.3e s %.3e m %.3e)\n", al, tau, mubar, wb, mb, tb[wb], lb[wb], ws, which, msv, ts[ws], ls[ws], ss[ws], ms[ws]);
+                }
+#endif
                 for (int e = lane; e < (N + 1) * NW; e += NL) w[e] += al * wp[e];
                 for (int e = lane + NX; e < (N + 1) * NX; e += NL) pi[e] += al * pip[e];
                 for (int e = lane; e < nhr; e += NL) { tb[e] += al * dtb[e]; lb[e] += al * dlb[e]; }

@@ -153,8 +153,10 @@ extern "C" int sdfnmpc_sdf_set_latents(sdfnmpc_sdf_t h, const float* z, int32_t 
 
 extern "C" int sdfnmpc_sdf_eval(sdfnmpc_sdf_t h, const float* pts, const int32_t* pt2inst, int32_t pts_per_inst,
                                 int64_t n, float* sdf, float* grad, void* stream) {
-    if (!h || !pts || n < 0 || n > 0x7fffffff || (!pt2inst && pts_per_inst < 1)) return SDFNMPC_E_INVALID;
+    if (!h || n < 0 || n > 0x7fffffff || (!pt2inst && pts_per_inst < 1)) return SDFNMPC_E_INVALID;
     if (h->n_inst < 1) return SDFNMPC_E_STATE;
+    if (n == 0) return 0;
+    if (!pts) return SDFNMPC_E_INVALID;
     if (!pt2inst && (n + pts_per_inst - 1) / pts_per_inst > h->n_inst) return SDFNMPC_E_INVALID;
     if (n == 0) return 0;
     const int64_t tiles = (n + SDF_TM - 1) / SDF_TM;

@@ -239,6 +239,16 @@ class BatchedNmpc:
         d, _ = self.sdf.eval(c0, pts_per_inst=1, want_grad=False)
         return d
 
+    def timing_begin(self, max_steps):
+        """Per-kernel CUDA-event timing of the next ``max_steps`` solves (bench.py roofline)."""
+        _lib.check(self.lib.sdfnmpc_solver_timing_begin(self.handle, int(max_steps)), 'timing_begin')
+
+    def timing_end(self):
+        ms = (C.c_float * 3)()
+        steps = C.c_int32()
+        _lib.check(self.lib.sdfnmpc_solver_timing_end(self.handle, ms, C.byref(steps)), 'timing_end')
+        return dict(linearize=ms[0], sdf=ms[1], qp=ms[2]), int(steps.value)
+
     def plant_step(self, x, u, dt):
         """x <- RK4(x, u, dt) with the controller's own model (closed-loop rollouts)."""
         _lib.check(self.lib.sdfnmpc_plant_step(self.handle, x.shape[0], _ptr(x), _ptr(u), float(dt), _stream()), 'plant_step')

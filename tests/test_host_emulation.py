@@ -1,0 +1,92 @@
+"""CPU-side check of the DEVICE algorithms: tests/host_emul/emul.cpp compiles the very headers the CUDA kernels
+include (linearize_core.cuh, qp_core.cuh, model_att.cuh, dual.cuh) with one lane per warp, and the result is
+compared with the oracle.  This is a development aid for a container without a GPU; the product never loads it."""
+import ctypes
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, make_problem
+
+
+@pytest.fixture(scope='module')
+def emul():
+    out = os.path.join(tempfile.mkdtemp(prefix='sdfnmpc_emul_'), 'libhost_emul.so')
+    subprocess.run(['g++', '-O2', '-std=c++17', '-shared', '-fPIC', '-DSDFNMPC_HOST_EMUL', '-x', 'c++',
+                    os.path.join(ROOT, 'tests', 'host_emul', 'emul.cpp'), '-o', out], check=True)
+    return ctypes.CDLL(out)
+
+
+def _P(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _emul_step(lib, net, cfg, prob, xe, ue):
+    from oracle import rti, sdf as SDF
+    B, N = xe.shape[0], cfg['N']
+    pose = np.ascontiguousarray(np.concatenate([prob['W_p_Co'], prob['W_R_Co'].reshape(B, 9)], 1))
+    mcv = np.array([cfg['g'], cfg['gamma'], cfg['roll'], cfg['pitch'], cfg['wz'], cfg['mass'],
+                    *(cfg['B_R_C'].T @ cfg['B_p_C'] + np.array([cfg['fov_off'], 0, 0]))])
+    lh, uh = rti.h_bounds(cfg, net['max_df'])
+    zs, Zs = rti.slack_weights(cfg)
+    AB = np.zeros((B, N, 10, 14)); bd = np.zeros((B, N, 10)); J = np.zeros((B, N + 1, 11, 14)); yr = np.zeros((B, N + 1, 11))
+    C = np.zeros((B, N + 1, 3, 14)); hv = np.zeros((B, N + 1, 3)); qp = np.zeros((B, N + 1, 3), np.float32)
+    c = np.ascontiguousarray
+    yref, yrefN, qd, flag, W, WN, x0 = (c(prob[k]) for k in ('yref', 'yrefN', 'qd', 'flag', 'W', 'WN', 'x0'))
+    lib.emul_linearize(B, N, _P(mcv), _P(xe), _P(ue), _P(yref), _P(yrefN), _P(qd), _P(pose), _P(flag), _P(cfg['dt']),
+                       _P(AB), _P(bd), _P(J), _P(yr), _P(C), _P(hv), _P(qp))
+    lin = dict(AB=AB.copy(), b=bd.copy(), J=J.copy(), hv=hv.copy(), C=C.copy(), qp=qp.copy())
+    d, g = SDF.value_and_grad(net, qp.reshape(-1, 3), np.repeat(prob['latent'], N + 1, 0), dtype=np.float32)
+    d, g = c(d.astype(np.float32)), c(g.astype(np.float32))
+    u0 = np.zeros((B, 4)); lamh = np.zeros((B, N, 8)); lams = np.zeros((B, N + 1, 6))
+    st = np.zeros(B, np.int32); its = np.zeros(B, np.int32)
+    D = ctypes.c_double
+    lib.emul_qp(B, N, 1, 100, 4, D(cfg['lm']), D(1e-8), D(1e-7), D(net['max_df']), _P(flag), _P(AB), _P(bd), _P(J), _P(yr), _P(C),
+                _P(hv), _P(W), _P(WN), _P(cfg['dt']), _P(cfg['lbu']), _P(cfg['ubu']), _P(lh), _P(uh), _P(zs), _P(Zs), _P(d), _P(g),
+                _P(pose), _P(x0), _P(xe), _P(ue), _P(u0), _P(lamh), _P(lams), _P(st), _P(its))
+    return u0, st, its, lamh, lams, lin
+
+
+def test_linearize_and_qp_cores_match_oracle(emul):
+    from oracle import rti
+    from sdf_nmpc_b200 import synth
+    net = synth.make_sdf_net(seed=0, **synth.ARCH_B, calibrated=True)
+    cfg = rti.default_cfg()
+    B = 12
+    prob, w = make_problem(B, cfg)
+    xb, ub = rti.init_traj(prob['x0'], cfg)
+    xe, ue = np.ascontiguousarray(xb.copy()), np.ascontiguousarray(ub.copy())
+    for step in range(3):
+        xo, uo, out = rti.rti_step(net, xb, ub, prob, cfg)
+        u0, st, its, lamh, lams, lin = _emul_step(emul, net, cfg, prob, xe, ue)
+        if step == 0:   # dual-number linearisation == hand-derived analytic Jacobians of the oracle
+            L = out['lin']
+            assert np.abs(lin['AB'][..., 4:] - L['A']).max() < 1e-12 and np.abs(lin['AB'][..., :4] - L['B']).max() < 1e-12
+            assert np.abs(lin['b'] - L['b']).max() < 1e-12
+            assert np.abs(lin['hv'][:, 1:, :2] - L['hbar'][:, 1:, :2]).max() < 1e-12
+            assert np.abs(lin['C'][:, 1:, :2, 4:] - L['C'][:, 1:, :2]).max() < 1e-10
+        assert np.all(st == 0) and its.max() <= 30
+        assert np.abs(u0 - out['u0']).max() <= 1e-5
+        assert np.abs(xe - xo).max() <= 1e-4 and np.abs(ue - uo).max() <= 1e-4
+        assert np.abs(lamh[:, :, :4] - out['lam_lbu']).max() < 1e-2 and np.abs(lams[:, 1:, :3] - out['lam_lh']).max() < 1e-2
+        xb, ub = xo, uo
+
+
+def test_qp_core_robust_over_many_instances(emul):
+    """Riccati IPM converges (status 0) on a few hundred random instances over repeated RTI steps, including the
+    ones that made plain Mehrotra cycle before the stall safeguard."""
+    from oracle import rti
+    from sdf_nmpc_b200 import synth
+    net = synth.make_sdf_net(seed=0, **synth.ARCH_B, calibrated=True)
+    cfg = rti.default_cfg()
+    B = 192
+    prob, w = make_problem(B, cfg, seed=1000 + 3200)      # block containing instance 3292
+    xe, ue = rti.init_traj(prob['x0'], cfg)
+    xe, ue = np.ascontiguousarray(xe), np.ascontiguousarray(ue)
+    for step in range(12):
+        u0, st, its, *_ = _emul_step(emul, net, cfg, prob, xe, ue)
+        assert np.all(st == 0), (step, np.where(st != 0)[0])
+        assert its.max() <= 40
