@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SDFNMPC_MAX_N 64           /* maximum number of shooting intervals */
+#define SDFNMPC_MAX_N 64           /* size of the dt array; the QP kernel additionally needs N <= 31 (node k <-> lane k) */
 #define SDFNMPC_E_INVALID (-1)     /* bad argument / unsupported configuration */
 #define SDFNMPC_E_NODEVICE (-2)    /* no CUDA device: this library has no CPU path */
 #define SDFNMPC_E_STATE (-3)       /* call order violated (e.g. eval before set_latents) */
@@ -110,6 +110,8 @@ int sdfnmpc_solver_state(sdfnmpc_solver_t h, double** xbar_dev, double** ubar_de
                          double** lam_soft_dev);
 /* h values of the last linearisation [cap][N+1][3] and SDF query results d [cap][N+1], grad [cap][N+1][3]. */
 int sdfnmpc_solver_diag(sdfnmpc_solver_t h, double** hval_dev, float** sdf_d_dev, float** sdf_g_dev);
+/* Verified KKT residual (inf-norm of input stationarity and dynamics) of each instance's last QP: [cap]. */
+int sdfnmpc_solver_qp_residual(sdfnmpc_solver_t h, double** res_dev);
 /* Per-kernel device timing of the next <= max_steps rti_step calls (CUDA events on the launching stream):
  * ms3 = summed milliseconds of {linearise, sdf, qp}; steps = number of timed calls. */
 int sdfnmpc_solver_timing_begin(sdfnmpc_solver_t h, int32_t max_steps);

@@ -52,7 +52,7 @@ CASADI_COMPANIONS = ('', '_alloc_mem', '_init_mem', '_free_mem', '_checkout', '_
 EXPORTS = (['sdfnmpc_version', 'sdfnmpc_launch_count', 'sdfnmpc_sdf_create', 'sdfnmpc_sdf_destroy',
             'sdfnmpc_sdf_set_latents', 'sdfnmpc_sdf_eval', 'sdfnmpc_sdf_eval_host', 'sdfnmpc_solver_create',
             'sdfnmpc_solver_destroy', 'sdfnmpc_solver_init_traj', 'sdfnmpc_solver_shift', 'sdfnmpc_solver_rti_step',
-            'sdfnmpc_solver_state', 'sdfnmpc_solver_diag', 'sdfnmpc_solver_timing_begin', 'sdfnmpc_solver_timing_end', 'sdfnmpc_plant_step', 'sdfnmpc_cmd_trpyr',
+            'sdfnmpc_solver_state', 'sdfnmpc_solver_diag', 'sdfnmpc_solver_qp_residual', 'sdfnmpc_solver_timing_begin', 'sdfnmpc_solver_timing_end', 'sdfnmpc_plant_step', 'sdfnmpc_cmd_trpyr',
             'sdfnmpc_encoder_create', 'sdfnmpc_encoder_destroy', 'sdfnmpc_encoder_encode',
             'sdfnmpc_encoder_encode_host', 'sdfnmpc_l4c_bind', 'sdfnmpc_l4c_load_blob']
            + [f + s for f in ('sdf_l4c', 'jac_sdf_l4c') for s in CASADI_COMPANIONS])
@@ -92,6 +92,7 @@ def load():
     lib.sdfnmpc_solver_rti_step.argtypes = [vp, i32] + [dp] * 8 + [fp, dp, ip, ip, vp]
     lib.sdfnmpc_solver_state.argtypes = [vp] + [C.POINTER(vp)] * 4
     lib.sdfnmpc_solver_diag.argtypes = [vp] + [C.POINTER(vp)] * 3
+    lib.sdfnmpc_solver_qp_residual.argtypes = [vp, C.POINTER(vp)]
     lib.sdfnmpc_solver_timing_begin.argtypes = [vp, i32]
     lib.sdfnmpc_solver_timing_end.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int32)]
     lib.sdfnmpc_plant_step.argtypes = [vp, i32, dp, dp, C.c_double, vp]

@@ -35,7 +35,8 @@ struct sdfnmpc_solver {
     double *xbar = nullptr, *ubar = nullptr;  // warm start
     double *AB = nullptr, *bdyn = nullptr, *J = nullptr, *yres = nullptr, *C = nullptr, *hval = nullptr;
     float *qpts = nullptr, *sdf_d = nullptr, *sdf_g = nullptr;
-    double *work = nullptr, *lam_hard = nullptr, *lam_soft = nullptr;
+    double *work = nullptr, *lam_hard = nullptr, *lam_soft = nullptr, *qp_res = nullptr;
+    size_t qp_smem = 0;
     size_t work_per_inst = 0;
     // optional per-kernel timing (bench.py roofline): 4 events per step on the launching stream
     std::vector<cudaEvent_t> ev;
@@ -58,12 +59,13 @@ struct QpBatch {
     double *C, *hval, *xbar, *ubar, *work, *u0, *lam_hard, *lam_soft;
     const float *sdf_d, *sdf_g;
     int *status, *iters;
+    double* res_out;
     size_t work_per_inst;
     double max_df;
 };
 
 __global__ void __launch_bounds__(QP_WARPS * 32) nmpc_qp_kernel(SolverConst sc, int B, QpBatch q) {
-    __shared__ double sm_all[QP_WARPS][Shape::SMEM_DOUBLES];
+    extern __shared__ double sm_all[];
     __shared__ SolverConst scs;
     if (threadIdx.x == 0) scs = sc;
     __syncthreads();
@@ -97,7 +99,8 @@ __global__ void __launch_bounds__(QP_WARPS * 32) nmpc_qp_kernel(SolverConst sc, 
     P.status = q.status + b;
     P.iters = q.iters + b;
     Lanes L{(int)(threadIdx.x & 31)};
-    qp_solve_instance<NX, NU, NY, NH>(L, P, sm_all[warp]);
+    P.res_out = q.res_out ? q.res_out + b : nullptr;
+    qp_solve_instance<NX, NU, NY, NH>(L, P, sm_all + (size_t)warp * Shape::smem_doubles(N));
 }
 
 __global__ void nmpc_init_traj_kernel(int N, int B, double u_hover, const double* __restrict__ x0,
@@ -143,7 +146,8 @@ __global__ void nmpc_cmd_kernel(SolverConst sc, int B, const double* __restrict_
 }
 
 extern "C" int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver_desc* d, sdfnmpc_sdf_t sdf) {
-    if (!out || !d || !sdf || d->N < 1 || d->N > SDFNMPC_MAX_N || d->max_batch < 1) return SDFNMPC_E_INVALID;
+    // the QP kernel maps node k to lane k of the instance's warp: N + 1 <= 32
+    if (!out || !d || !sdf || d->N < 1 || d->N > 31 || d->N > SDFNMPC_MAX_N || d->max_batch < 1) return SDFNMPC_E_INVALID;
     if (int rc = ensure_device()) return rc;
     auto* h = new sdfnmpc_solver();
     h->desc = *d;
@@ -178,6 +182,9 @@ extern "C" int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver
     alloc((void**)&h->work, B * h->work_per_inst * sizeof(double));
     alloc((void**)&h->lam_hard, B * N * 2 * NU * sizeof(double));
     alloc((void**)&h->lam_soft, B * N1 * 2 * NH * sizeof(double));
+    alloc((void**)&h->qp_res, B * sizeof(double));
+    h->qp_smem = (size_t)QP_WARPS * Shape::smem_doubles(d->N) * sizeof(double);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(nmpc_qp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qp_smem);
     if (e == cudaSuccess) e = cudaMemcpy(h->dt, d->dt, N * sizeof(double), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemset(h->xbar, 0, B * N1 * NX * sizeof(double));
     if (e == cudaSuccess) e = cudaMemset(h->ubar, 0, B * N * NU * sizeof(double));
@@ -189,7 +196,7 @@ extern "C" int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver
 extern "C" int sdfnmpc_solver_destroy(sdfnmpc_solver_t h) {
     if (!h) return 0;
     void* ptrs[] = {h->dt, h->xbar, h->ubar, h->AB, h->bdyn, h->J, h->yres, h->C, h->hval, h->qpts, h->sdf_d, h->sdf_g,
-                    h->work, h->lam_hard, h->lam_soft};
+                    h->work, h->lam_hard, h->lam_soft, h->qp_res};
     for (void* p : ptrs) cudaFree(p);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     delete h;
@@ -246,7 +253,8 @@ extern "C" int sdfnmpc_solver_rti_step(sdfnmpc_solver_t h, int32_t B, const doub
     q.x0 = x0; q.flag = flag; q.C = h->C; q.hval = h->hval; q.xbar = h->xbar; q.ubar = h->ubar; q.work = h->work;
     q.u0 = u0; q.lam_hard = h->lam_hard; q.lam_soft = h->lam_soft; q.sdf_d = h->sdf_d; q.sdf_g = h->sdf_g;
     q.status = status; q.iters = qp_iters; q.work_per_inst = h->work_per_inst; q.max_df = (double)h->sdf->net.max_df;
-    nmpc_qp_kernel<<<(B + QP_WARPS - 1) / QP_WARPS, QP_WARPS * 32, 0, st>>>(h->sc, B, q);
+    q.res_out = h->qp_res;
+    nmpc_qp_kernel<<<(B + QP_WARPS - 1) / QP_WARPS, QP_WARPS * 32, h->qp_smem, st>>>(h->sc, B, q);
     count_launch();
     SDF_CUDA_CHECK(cudaGetLastError());
     if (tm) { cudaEventRecord(ev[3], st); h->ev_steps++; }
@@ -287,6 +295,12 @@ extern "C" int sdfnmpc_solver_state(sdfnmpc_solver_t h, double** xbar, double** 
     if (ubar) *ubar = h->ubar;
     if (lam_hard) *lam_hard = h->lam_hard;
     if (lam_soft) *lam_soft = h->lam_soft;
+    return 0;
+}
+
+extern "C" int sdfnmpc_solver_qp_residual(sdfnmpc_solver_t h, double** res) {
+    if (!h || !res) return SDFNMPC_E_INVALID;
+    *res = h->qp_res;
     return 0;
 }
 

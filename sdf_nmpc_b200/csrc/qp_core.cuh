@@ -14,9 +14,20 @@
 // one-sided row  g_i . w_k - d_i (+ s_i) = t_i >= 0  with multiplier lam_i; soft rows
 // carry a slack s_i >= 0 (multiplier mu_i) with penalty z_i s_i + 1/2 Z_i s_i^2.  Slacks,
 // t and the multipliers are eliminated from the Newton system row by row, which adds
-// Theta~_i g_i g_i' to the stage Hessian and c_i g_i to the stage gradient; the remaining
-// equality-constrained QP is solved exactly by the Riccati recursion for the *target*
-// point w+ (so the linear dynamics never need an explicit residual in the step).
+// Theta~_i g_i g_i' to the stage Hessian and coef_i g_i to the stage right-hand side; the
+// remaining equality-constrained QP in the STEP (delta form: right-hand sides are residuals,
+// so steps keep full relative accuracy near the solution) is solved by the Riccati recursion.
+//
+// Work mapping (v2).  Row phases: lane k owns node k and keeps the node's (t, lam, s, mu) in
+// registers for the whole solve - no index arithmetic, no scratch traffic.  Matrix phases
+// (Riccati): lanes split the entries of the small dense products staged in shared memory.
+// The stationarity / dynamics residuals of a Newton method on a QP contract exactly by
+// (1 - alpha) per step, so they are kept as (initial residual) x (scalar phi) and verified
+// once, explicitly, at the end (costates recovered by one backward sweep).
+//
+// Assumption encoded in HC0/HCN: the nonlinear rows h depend on the state only through the
+// columns [HC0, HC0+HCN) of w (the position), which holds for every h of the reference
+// (FoV rows and SDF row depend on W_p_B only: cost_const_helpers.py:60-65, gen_model.py:46-51).
 #pragma once
 #include "common.cuh"
 
@@ -25,21 +36,24 @@ namespace sdfnmpc {
 template <int NX, int NU, int NY, int NH>
 struct QpShape {
     static constexpr int NW = NX + NU;
-    SDF_HD static int hard_rows(int N) { return N * 2 * NU; }
-    SDF_HD static int soft_rows(int N) { return (N + 1) * 2 * NH; }
-    // doubles of per-instance scratch
+    static constexpr int TRI = NW * (NW + 1) / 2;
+    static constexpr int NCORR = NU + 6 + NU + 3;   // du, Dp(sym 3x3), gu, gp
+    static constexpr int NPROD = 2 * NU + 4 * NH;   // second-order products per node
+    SDF_HD static int kp(int N) { return N + 2; }   // padded node count of the [item][node] arrays
+    // doubles of per-instance global scratch
     SDF_HD static size_t work_doubles(int N) {
         size_t n1 = (size_t)(N + 1);
-        return 2 * n1 * NW * NW + 2 * n1 * NW      // H, Ht, g, gt
-               + 2 * n1 * NW + 2 * n1 * NX         // w, wp, pi, pip
-               + 5 * (size_t)hard_rows(N)          // tb lb dtb dlb pab
-               + 10 * (size_t)soft_rows(N)         // ts ls ss ms dts dls dss dms pas pbs
-               + 2 * (size_t)N * NU + 2 * n1 * NH  // net Theta / c per node
-               + (size_t)N * (NU * NX + NU * NU + NX + NU)    // K, Lc, PbM, kff
-               + n1 * NW + n1 * NX                            // rvec, rdyn
-               + (size_t)hard_rows(N) + 2 * (size_t)soft_rows(N);   // rpb, rps, rhos
+        return n1 * NW * NW + n1 * NW      // H, g
+               + n1 * NW + n1 * NX         // rv0, rdyn0
+               + (size_t)N * (NU * NX + NU * NU + NX)   // K, Linv, PbM
+               + n1 * NX;                  // costates (final verification)
     }
-    static constexpr int SMEM_DOUBLES = NX * NX + 2 * NX * (NW + 1) + NW * NW + NW + NU * NX + NU + 2 * NX + 4;
+    // doubles of per-lane-group shared memory
+    SDF_HD static int smem_doubles(int N) {
+        return NX * NX + 2 * NX * (NW + 1) + NW * NW + NW + NU * NX + NU + 2 * NX   // Riccati workspace
+               + 2 * NW * kp(N)                                                   // W (iterate), dW (step)
+               + (NCORR + NPROD) * kp(N) + 8;
+    }
 };
 
 template <int NX, int NU, int NY, int NH>
@@ -67,77 +81,93 @@ struct QpProb {            // all pointers are offset to ONE instance
     double* u0;            // [NU]
     double* lam_hard;      // [N][2NU] or null
     double* lam_soft;      // [N+1][2NH] or null
+    double* res_out;       // verified KKT residual (inf-norm) or null
     int* status;           // 0 ok, 2 max-iter, 4 NaN / factorisation failure (acados codes)
     int* iters;
 };
 
 namespace qpdetail {
 
-SDF_HD void tri_decode(int e, int& i, int& j) {   // e -> (i >= j), row-major lower triangle
-    int r = (int)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
-    while ((r + 1) * (r + 2) / 2 <= e) ++r;
-    while (r * (r + 1) / 2 > e) --r;
-    i = r;
-    j = e - r * (r + 1) / 2;
-}
-
-struct SoftRow {
-    double r_p, r_s, Th, D, Tht, zs;
+template <int NW>
+struct TriTable {
+    unsigned char i[NW * (NW + 1) / 2], j[NW * (NW + 1) / 2];
+    constexpr TriTable() : i(), j() {
+        int e = 0;
+        for (int a = 0; a < NW; ++a)
+            for (int b = 0; b <= a; ++b) { i[e] = (unsigned char)a; j[e] = (unsigned char)b; ++e; }
+    }
 };
 
-SDF_HD SoftRow soft_row(double t, double lam, double s, double mu, double gw, double d, double z, double Z) {
-    SoftRow r;
-    r.r_p = t - (gw - d + s);
-    r.r_s = z + Z * s - lam - mu;
-    r.Th = lam / t;
-    r.zs = Z + mu / s;
-    r.D = r.zs + r.Th;
-    r.Tht = r.Th * r.zs / r.D;
+SDF_HD double rcp(double x) { return 1.0 / x; }
+SDF_HD double step_to_boundary(double x, double dx) { return dx < 0.0 ? -x / dx : 1e30; }
+SDF_HD int sym3(int a, int b) { return a >= b ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a; }
+
+// Everything the elimination needs from one row; evaluated by ONE function so that the two places that use
+// r_p / rho (right-hand side and step) see bit-identical values.
+struct HardEval { double r_p, Th, coef; };
+struct SoftEval { double r_p, r_s, Th, D, Tht, rho, coef; };
+
+#if defined(__CUDA_ARCH__)
+#define SDF_NOINLINE __device__ __noinline__
+#else
+#define SDF_NOINLINE inline
+#endif
+
+SDF_NOINLINE HardEval hard_eval(double t, double lam, double gw, double d, double corr) {
+    HardEval r;
+    const double rt = rcp(t);
+    r.r_p = t - (gw - d);
+    r.Th = lam * rt;
+    const double kap = corr - lam * t;            // corr = 0 (affine) or tau - dlam_aff*dt_aff
+    r.coef = -kap * rt - r.Th * r.r_p;
     return r;
 }
 
-SDF_HD double step_to_boundary(double x, double dx) { return dx < 0.0 ? -x / dx : 1e30; }
+SDF_NOINLINE SoftEval soft_eval(double t, double lam, double s, double mu, double gw, double d, double z, double Z,
+                                double corr_t, double corr_s) {
+    SoftEval r;
+    const double rt = rcp(t), rs = rcp(s);
+    r.r_p = t - (gw - d + s);
+    r.r_s = z + Z * s - lam - mu;
+    r.Th = lam * rt;
+    const double zs = Z + mu * rs;
+    r.D = zs + r.Th;
+    const double rD = rcp(r.D);
+    r.Tht = r.Th * zs * rD;
+    const double kap = corr_t - lam * t, nu = corr_s - mu * s;
+    r.rho = -r.r_s + kap * rt + nu * rs + r.Th * r.r_p;
+    r.coef = -kap * rt + r.Th * (r.rho * rD - r.r_p);
+    return r;
+}
 
 }  // namespace qpdetail
 
-template <int NX, int NU, int NY, int NH>
+template <int NX, int NU, int NY, int NH, int HC0 = NU, int HCN = 3>
 SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, double* sm) {
     using namespace qpdetail;
     using S = QpShape<NX, NU, NY, NH>;
-    constexpr int NW = S::NW;
-    constexpr int NWB = NW + 1;
-    const int N = P.N, k0 = P.k0;
+    static_assert(HCN == 3, "the position block is 3 wide");
+    constexpr int NW = S::NW, NWB = NW + 1, TRI = S::TRI, NCORR = S::NCORR, NPROD = S::NPROD;
+    constexpr TriTable<NW> tri{};
+    const int N = P.N, k0 = P.k0, KP = S::kp(N);
     const int NL = Lanes::count();
     const int lane = L.lane;
-    const int nhr = S::hard_rows(N), nsr = S::soft_rows(N);
-    const int ncomp = nhr + 2 * (N + 1 - k0) * 2 * NH;
+    const int ncomp = N * 2 * NU + 2 * (N + 1 - k0) * 2 * NH;
 
-    // ---- carve the per-instance scratch ------------------------------------------------
+    // ---- global scratch ---------------------------------------------------------------------
     double* p = P.work;
     auto take = [&](size_t n) { double* r = p; p += n; return r; };
     const size_t n1 = (size_t)(N + 1);
     double* H = take(n1 * NW * NW);
-    double* Ht = take(n1 * NW * NW);
     double* g = take(n1 * NW);
-    double* gt = take(n1 * NW);
-    double* w = take(n1 * NW);
-    double* wp = take(n1 * NW);
-    double* pi = take(n1 * NX);
-    double* pip = take(n1 * NX);
-    double *tb = take(nhr), *lb = take(nhr), *dtb = take(nhr), *dlb = take(nhr), *pab = take(nhr);
-    double *ts = take(nsr), *ls = take(nsr), *ss = take(nsr), *ms = take(nsr);
-    double *dts = take(nsr), *dls = take(nsr), *dss = take(nsr), *dms = take(nsr), *pas = take(nsr), *pbs = take(nsr);
-    double *thnb = take((size_t)N * NU), *cnb = take((size_t)N * NU);
-    double *thns = take(n1 * NH), *cns = take(n1 * NH);
+    double* rv0 = take(n1 * NW);       // stationarity residual at the initial point (scaled by phi afterwards)
+    double* rd0 = take(n1 * NX);       // dynamics residual at the initial point: rd0[k+1] = AB_k w_k + b_k - w_x,k+1
     double* Kg = take((size_t)N * NU * NX);
-    double* Lg = take((size_t)N * NU * NU);
+    double* Lg = take((size_t)N * NU * NU);   // Cholesky factor of Ruu, diagonal stored INVERTED
     double* PbM = take((size_t)N * NX);
-    double* kffg = take((size_t)N * NU);
-    double *rpb = take(nhr), *rps = take(nsr), *rhos = take(nsr);   // r_p / rho per row, shared by both uses
-    double* rvec = take(n1 * NW);     // stationarity residual per node
-    double* rdyn = take(n1 * NX);     // dynamics residual: rdyn[0] = dx0 - w_x0, rdyn[k+1] = AB_k w_k + b_k - w_x,k+1
+    double* pig = take(n1 * NX);
 
-    // ---- shared (per-lane-group) workspace ------------------------------------------------
+    // ---- shared workspace -----------------------------------------------------------------------
     double* Psm = sm;                    // [NX][NX]
     double* ABb = Psm + NX * NX;         // [NX][NW+1]
     double* PAB = ABb + NX * NWB;        // [NX][NW+1]
@@ -147,418 +177,505 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
     double* kfs = Ksm + NU * NX;         // [NU]
     double* pv = kfs + NU;               // [NX]
     double* vv = pv + NX;                // [NX]
+    double* Wsm = vv + NX;               // [NW][KP]   iterate w
+    double* dW = Wsm + NW * KP;          // [NW][KP]   step
+    double* corr = dW + NW * KP;         // [NCORR][KP] du(NU) Dp(6) gu(NU) gp(3) per node
+    double* prod = corr + NCORR * KP;    // [NPROD][KP] affine second-order products
 
     auto scale = [&](int k) { return k < N ? P.dt[k] : 1.0; };
     auto wrow = [&](int k, int r) { return k < N ? P.W[k * NY + r] : (r < P.nyN ? P.WN[r] : 0.0); };
-    // row data:   hard row index e = k*2NU + a  (a < NU lower, else upper);  soft e = k*2NH + a
-    auto hard_d = [&](int k, int a) {
-        int j = a < NU ? a : a - NU;
-        double ub = P.ubar[k * NU + j];
-        return a < NU ? P.lbu[j] - ub : ub - P.ubu[j];
-    };
-    auto soft_d = [&](int k, int a) {
-        int r = a < NH ? a : a - NH;
-        double hv = P.hval[k * NH + r];
-        return a < NH ? P.lh[r] - hv : hv - P.uh[r];
-    };
-    auto c_dot = [&](int k, int r, const double* vec) {   // C_r . vec_k
-        const double* Cr = P.C + ((size_t)k * NH + r) * NW;
-        const double* v = vec + (size_t)k * NW;
-        double s = 0.0;
-        for (int i = 0; i < NW; ++i) s += Cr[i] * v[i];
-        return s;
-    };
 
     // ---- prologue: sdf row of C / h, Gauss-Newton Hessian and gradient ----------------------
     for (int k = k0 + lane; k <= N; k += NL) {
         const double* R = P.pose + 3;
         double gx = P.sdf_g[k * 3 + 0], gy = P.sdf_g[k * 3 + 1], gz = P.sdf_g[k * 3 + 2];
         double* Cr = P.C + ((size_t)k * NH + (NH - 1)) * NW;
-        for (int jj = 0; jj < 3; ++jj) Cr[NU + jj] = P.flag * (R[jj * 3 + 0] * gx + R[jj * 3 + 1] * gy + R[jj * 3 + 2] * gz);
+        for (int jj = 0; jj < 3; ++jj) Cr[HC0 + jj] = P.flag * (R[jj * 3 + 0] * gx + R[jj * 3 + 1] * gy + R[jj * 3 + 2] * gz);
         P.hval[k * NH + (NH - 1)] = P.flag * (double)P.sdf_d[k] + (1.0 - P.flag) * P.max_df;
     }
-    for (int e = lane; e < (N + 1) * NW * NW; e += NL) {
-        int k = e / (NW * NW), ij = e % (NW * NW), i = ij / NW, j = ij % NW;
+    for (int e = lane; e < (N + 1) * TRI; e += NL) {
+        const int k = e / TRI, t = e - k * TRI, i = tri.i[t], j = tri.j[t];
         const double* Jk = P.J + (size_t)k * NY * NW;
         double s = 0.0;
         for (int r = 0; r < NY; ++r) s += Jk[r * NW + i] * wrow(k, r) * Jk[r * NW + j];
         if (i == j) s += P.lm;
-        H[e] = scale(k) * s;
+        s *= scale(k);
+        H[(size_t)k * NW * NW + i * NW + j] = s;
+        H[(size_t)k * NW * NW + j * NW + i] = s;
     }
     for (int e = lane; e < (N + 1) * NW; e += NL) {
-        int k = e / NW, i = e % NW;
+        const int k = e / NW, i = e - k * NW;
         const double* Jk = P.J + (size_t)k * NY * NW;
         const double* yr = P.yres + (size_t)k * NY;
         double s = 0.0;
         for (int r = 0; r < NY; ++r) s += Jk[r * NW + i] * wrow(k, r) * yr[r];
         g[e] = scale(k) * s;
-        w[e] = (k == 0 && i >= NU) ? P.x0[i - NU] - P.xbar[i - NU] : 0.0;
-    }
-    for (int e = lane; e < (N + 1) * NX; e += NL) pi[e] = 0.0;
-    L.sync();
-    // ---- initial point -----------------------------------------------------------------------
-    for (int e = lane; e < nhr; e += NL) {
-        int k = e / (2 * NU), a = e % (2 * NU);
-        double r = -hard_d(k, a);          // w_u = 0
-        double t = fmax(r, 0.5);
-        tb[e] = t;
-        lb[e] = fmax(1.0 / t, 1e-3);
-    }
-    for (int e = lane; e < nsr; e += NL) {
-        int k = e / (2 * NH), a = e % (2 * NH);
-        int r = a < NH ? a : a - NH;
-        double sgn = a < NH ? 1.0 : -1.0;
-        double z = P.zs[r] * scale(k), Z = P.Zs[r] * scale(k);
-        double s0 = 0.5;
-        double gw = k >= k0 ? sgn * c_dot(k, r, w) : 0.0;
-        double t = fmax(gw - soft_d(k, a) + s0, 0.5);
-        double l0 = fmax(0.5 * (z + Z * s0), 1e-3);
-        ts[e] = t; ss[e] = s0; ls[e] = l0; ms[e] = l0;
+        const double w0 = (k == 0 && i >= NU) ? P.x0[i - NU] - P.xbar[i - NU] : 0.0;
+        Wsm[i * KP + k] = w0;
+        dW[i * KP + k] = 0.0;
     }
     L.sync();
+
+    // ---- per-lane node state (lane k <-> node k) ------------------------------------------------
+    double tb[2 * NU], lb[2 * NU], ts[2 * NH], ls[2 * NH], ss[2 * NH], ms[2 * NH];
+    double dtb[2 * NU], dlb[2 * NU], dts[2 * NH], dls[2 * NH], dss[2 * NH], dms[2 * NH];   // step of the node's rows
+
+    // helpers reading the node's constants (L1-resident after the first touch)
+    auto hard_d = [&](int kk, int a) {
+        const int j = a < NU ? a : a - NU;
+        const double ub = P.ubar[kk * NU + j];
+        return a < NU ? P.lbu[j] - ub : ub - P.ubu[j];
+    };
+    auto soft_d = [&](int kk, int a) {
+        const int r = a < NH ? a : a - NH;
+        const double hv = P.hval[kk * NH + r];
+        return a < NH ? P.lh[r] - hv : hv - P.uh[r];
+    };
+    auto c_pos = [&](int kk, int r, int c) { return P.C[((size_t)kk * NH + r) * NW + HC0 + c]; };
+
+#if defined(__CUDA_ARCH__)
+#define SDF_NODE_LOOP(kk) for (int kk = lane; kk <= N; kk += 32)
+#else
+#define SDF_NODE_LOOP(kk) for (int kk = 0; kk <= N; ++kk)
+#endif
+#if !defined(__CUDA_ARCH__)
+    // host emulation: one lane plays every node in turn, so the "registers" become per-node arrays
+    double* TB = new double[(size_t)(N + 1) * (4 * NU + 8 * NH)];
+    double* TD = new double[(size_t)(N + 1) * (4 * NU + 8 * NH)];
+#define SDF_LOAD_DELTA(kk)                                                                         \
+    {                                                                                              \
+        double* q_ = TD + (size_t)(kk) * (4 * NU + 8 * NH);                                        \
+        for (int a = 0; a < 2 * NU; ++a) { dtb[a] = q_[a]; dlb[a] = q_[2 * NU + a]; }              \
+        for (int a = 0; a < 2 * NH; ++a) { dts[a] = q_[4 * NU + a]; dls[a] = q_[4 * NU + 2 * NH + a]; \
+            dss[a] = q_[4 * NU + 4 * NH + a]; dms[a] = q_[4 * NU + 6 * NH + a]; }                  \
+    }
+#define SDF_STORE_DELTA(kk)                                                                        \
+    {                                                                                              \
+        double* q_ = TD + (size_t)(kk) * (4 * NU + 8 * NH);                                        \
+        for (int a = 0; a < 2 * NU; ++a) { q_[a] = dtb[a]; q_[2 * NU + a] = dlb[a]; }              \
+        for (int a = 0; a < 2 * NH; ++a) { q_[4 * NU + a] = dts[a]; q_[4 * NU + 2 * NH + a] = dls[a]; \
+            q_[4 * NU + 4 * NH + a] = dss[a]; q_[4 * NU + 6 * NH + a] = dms[a]; }                  \
+    }
+#define SDF_LOAD_STATE(kk)                                                                         \
+    {                                                                                              \
+        double* q_ = TB + (size_t)(kk) * (4 * NU + 8 * NH);                                        \
+        for (int a = 0; a < 2 * NU; ++a) { tb[a] = q_[a]; lb[a] = q_[2 * NU + a]; }                \
+        for (int a = 0; a < 2 * NH; ++a) { ts[a] = q_[4 * NU + a]; ls[a] = q_[4 * NU + 2 * NH + a]; \
+            ss[a] = q_[4 * NU + 4 * NH + a]; ms[a] = q_[4 * NU + 6 * NH + a]; }                    \
+    }
+#define SDF_STORE_STATE(kk)                                                                        \
+    {                                                                                              \
+        double* q_ = TB + (size_t)(kk) * (4 * NU + 8 * NH);                                        \
+        for (int a = 0; a < 2 * NU; ++a) { q_[a] = tb[a]; q_[2 * NU + a] = lb[a]; }                \
+        for (int a = 0; a < 2 * NH; ++a) { q_[4 * NU + a] = ts[a]; q_[4 * NU + 2 * NH + a] = ls[a]; \
+            q_[4 * NU + 4 * NH + a] = ss[a]; q_[4 * NU + 6 * NH + a] = ms[a]; }                    \
+    }
+#else
+#define SDF_LOAD_STATE(kk)
+#define SDF_STORE_STATE(kk)
+#define SDF_LOAD_DELTA(kk)
+#define SDF_STORE_DELTA(kk)
+#endif
+
+    // ---- initial point and initial residuals ------------------------------------------------
+    SDF_NODE_LOOP(kk) {
+#pragma unroll
+        for (int a = 0; a < 2 * NU; ++a) {
+            double t = 1.0, l = 1.0;
+            if (kk < N) {
+                t = fmax(-hard_d(kk, a), 0.5);          // w_u = 0
+                l = fmax(1.0 / t, 1e-3);
+            }
+            tb[a] = t; lb[a] = l;
+        }
+#pragma unroll
+        for (int a = 0; a < 2 * NH; ++a) {
+            const int r = a < NH ? a : a - NH;
+            double t = 1.0, l = 1.0, s0 = 0.5;
+            if (kk >= k0) {
+                const double z = P.zs[r] * scale(kk), Z = P.Zs[r] * scale(kk);
+                double cw = 0.0;
+                for (int c = 0; c < 3; ++c) cw += c_pos(kk, r, c) * Wsm[(HC0 + c) * KP + kk];
+                const double gw = a < NH ? cw : -cw;
+                t = fmax(gw - soft_d(kk, a) + s0, 0.5);
+                l = fmax(0.5 * (z + Z * s0), 1e-3);
+            }
+            ts[a] = t; ss[a] = s0; ls[a] = l; ms[a] = l;
+        }
+        SDF_STORE_STATE(kk);
+        // rv0_k = H_k w_k + g_k - sum lam_i gvec_i   (w = 0 except dx_0; costates 0)
+        for (int i = 0; i < NW; ++i) {
+            double s = g[(size_t)kk * NW + i];
+            if (kk == 0)
+                for (int j = NU; j < NW; ++j) s += H[i * NW + j] * Wsm[j * KP];
+            if (kk < N && i < NU) s -= lb[i] - lb[NU + i];
+            if (kk >= k0 && i >= HC0 && i < HC0 + 3)
+                for (int r = 0; r < NH; ++r) s -= (ls[r] - ls[NH + r]) * c_pos(kk, r, i - HC0);
+            if ((kk == 0 && i >= NU) || (kk == N && i < NU)) s = 0.0;
+            rv0[(size_t)kk * NW + i] = s;
+        }
+        // rd0_{k} (k >= 1) = AB_{k-1} w_{k-1} + b_{k-1} - w_x,k ; only w_x,0 is non-zero
+        for (int i = 0; i < NX; ++i) {
+            double s = 0.0;
+            if (kk >= 1) {
+                s = P.bdyn[(kk - 1) * NX + i];
+                if (kk == 1)
+                    for (int j = NU; j < NW; ++j) s += P.AB[(size_t)i * NW + j] * Wsm[j * KP];
+            }
+            rd0[(size_t)kk * NX + i] = s;
+        }
+    }
+    L.sync();
+    double res_v0 = 0.0;
+    for (int e = lane; e < (N + 1) * NW; e += NL) res_v0 = fmax(res_v0, fabs(rv0[e]));
+    for (int e = lane; e < (N + 1) * NX; e += NL) res_v0 = fmax(res_v0, fabs(rd0[e]));
+    res_v0 = L.max(res_v0);
 
     int status = 2, it = 0;
     bool safe = false;              // conservative mode after a stall: more centering, no second-order term
     double cm_prev1 = 1e300, cm_prev2 = 1e300;
+    double phi = 1.0;               // product of (1 - alpha): scale of the stationarity / dynamics residuals
+    double res_track = 0.0;
     for (;; ++it) {
-        // ================= residuals and convergence =================
-        double res = 0.0, cmax = 0.0, csum = 0.0;
-        for (int e = lane; e < nhr; e += NL) {
-            int k = e / (2 * NU), a = e % (2 * NU);
-            int j = a < NU ? a : a - NU;
-            double gw = (a < NU ? 1.0 : -1.0) * w[k * NW + j];
-            res = fmax(res, fabs(tb[e] - (gw - hard_d(k, a))));
-            double c = lb[e] * tb[e];
-            cmax = fmax(cmax, c); csum += c;
-        }
-        for (int e = lane + k0 * 2 * NH; e < nsr; e += NL) {
-            int k = e / (2 * NH), a = e % (2 * NH);
-            int r = a < NH ? a : a - NH;
-            double gw = (a < NH ? 1.0 : -1.0) * c_dot(k, r, w);
-            SoftRow sr = soft_row(ts[e], ls[e], ss[e], ms[e], gw, soft_d(k, a), P.zs[r] * scale(k), P.Zs[r] * scale(k));
-            res = fmax(res, fmax(fabs(sr.r_p), fabs(sr.r_s)));
-            double c1 = ls[e] * ts[e], c2 = ms[e] * ss[e];
-            cmax = fmax(cmax, fmax(c1, c2)); csum += c1 + c2;
-        }
-        // stationarity (free variables only: dx_0 is fixed) and dynamics
-        for (int e = lane; e < (N + 1) * NW; e += NL) {
-            int k = e / NW, i = e % NW;
-            if ((k == 0 && i >= NU) || (k == N && i < NU)) { rvec[e] = 0.0; continue; }
-            const double* Hk = H + (size_t)k * NW * NW + (size_t)i * NW;
-            const double* wk = w + (size_t)k * NW;
-            double s = g[e];
-            for (int j = 0; j < NW; ++j) s += Hk[j] * wk[j];
-            if (k < N) {
-                if (i < NU) s -= lb[k * 2 * NU + i] - lb[k * 2 * NU + NU + i];
-                const double* ABk = P.AB + (size_t)k * NX * NW;
-                const double* pn = pi + (size_t)(k + 1) * NX;
-                for (int l = 0; l < NX; ++l) s += ABk[l * NW + i] * pn[l];
-            }
-            if (k >= k0)
-                for (int r = 0; r < NH; ++r)
-                    s -= (ls[k * 2 * NH + r] - ls[k * 2 * NH + NH + r]) * P.C[((size_t)k * NH + r) * NW + i];
-            if (i >= NU) s -= pi[(size_t)k * NX + (i - NU)];
-            rvec[e] = s;
-            res = fmax(res, fabs(s));
-        }
-        for (int e = lane; e < (N + 1) * NX; e += NL) {
-            int k = e / NX, i = e % NX;
-            double s;
-            if (k == 0) {
-                s = (P.x0[i] - P.xbar[i]) - w[NU + i];
-            } else {
-                const double* ABk = P.AB + (size_t)(k - 1) * NX * NW + (size_t)i * NW;
-                const double* wk = w + (size_t)(k - 1) * NW;
-                s = P.bdyn[(k - 1) * NX + i] - w[(size_t)k * NW + NU + i];
-                for (int j = 0; j < NW; ++j) s += ABk[j] * wk[j];
-            }
-            rdyn[e] = s;
-            res = fmax(res, fabs(s));
-        }
-#if defined(SDFNMPC_QP_DEBUG) && !defined(__CUDA_ARCH__)
-        printf("it %d res %.3e cmax %.3e\n", it, res, cmax);
-#endif
-        res = L.max(res);
-        cmax = L.max(cmax);
-        const double mubar = L.sum(csum) / ncomp;
-        if (!(res == res) || !(mubar == mubar) || res > 1e300) { status = 4; break; }
-        if (res <= P.tol_res && cmax <= P.tol) { status = 0; break; }
-        if (it >= P.max_iter) { status = 2; break; }
-
-        L.sync();
-        // two passes: 0 = affine (predictor, with factorisation), 1 = corrector (vector only).
-        // The Newton system is solved in DELTA form (right-hand sides are residuals), so the step keeps
-        // full relative accuracy when the iterate is close to the solution.
-        // Mehrotra's corrector can cycle on poorly centred iterates; if the largest complementarity product
-        // has not dropped by 30 % over two iterations switch (for good) to plain damped path following.
-        if (it >= 2 && cmax > 0.7 * cm_prev2) safe = true;
-        cm_prev2 = cm_prev1; cm_prev1 = cmax;
-        const double so = safe ? 0.0 : 1.0;
-        double tau = 0.0;
-        for (int pass = 0; pass < 2; ++pass) {
-            // ---------- per-row elimination coefficients -> net Theta~ and c per node ----------
-            for (int e = lane; e < N * NU; e += NL) {
-                int k = e / NU, j = e % NU;
-                double thn = 0.0, cn = 0.0;
-                for (int side = 0; side < 2; ++side) {
-                    int row = k * 2 * NU + side * NU + j;
-                    double sgn = side == 0 ? 1.0 : -1.0;
-                    double t = tb[row], lam = lb[row];
-                    double gw = sgn * w[k * NW + j];
-                    double r_p = t - (gw - hard_d(k, side * NU + j));
-                    rpb[row] = r_p;
-                    double Th = lam / t;
-                    double kap = (pass == 0 ? 0.0 : tau - pab[row]) - lam * t;
-                    double coef = -kap / t - Th * r_p;
-                    thn += Th;
-                    cn += sgn * coef;
+        double tau = 0.0, mubar = 0.0;
+        bool stop = false;
+        for (int pass = 0; pass < 2 && !stop; ++pass) {
+            // =========== row elimination (lane = node): corrections of the stage Hessian / rhs ===========
+            double res_rows = 0.0, cmax = 0.0, csum = 0.0;
+            SDF_NODE_LOOP(kk) {
+                SDF_LOAD_STATE(kk);
+                double du[NU], gu[NU], Dp[6] = {0, 0, 0, 0, 0, 0}, gp[3] = {0, 0, 0};
+#pragma unroll
+                for (int j = 0; j < NU; ++j) {
+                    double thn = 0.0, cn = 0.0;
+                    if (kk < N) {
+                        const double wu = Wsm[j * KP + kk];
+#pragma unroll
+                        for (int side = 0; side < 2; ++side) {
+                            const int a = side * NU + j;
+                            const double sgn = side == 0 ? 1.0 : -1.0;
+                            const double cr = pass == 0 ? 0.0 : tau - prod[a * KP + kk];
+                            const HardEval ev = hard_eval(tb[a], lb[a], sgn * wu, hard_d(kk, a), cr);
+                            thn += ev.Th;
+                            cn += sgn * ev.coef;
+                            if (pass == 0) {
+                                res_rows = fmax(res_rows, fabs(ev.r_p));
+                                const double c = lb[a] * tb[a];
+                                cmax = fmax(cmax, c); csum += c;
+                            }
+                        }
+                    }
+                    du[j] = thn; gu[j] = cn;
                 }
-                thnb[e] = thn;
-                cnb[e] = cn;
-            }
-            for (int e = lane; e < (N + 1) * NH; e += NL) {
-                int k = e / NH, r = e % NH;
-                double thn = 0.0, cn = 0.0;
-                if (k >= k0) {
-                    double cw = c_dot(k, r, w);
-                    double z = P.zs[r] * scale(k), Z = P.Zs[r] * scale(k);
-                    for (int side = 0; side < 2; ++side) {
-                        int row = k * 2 * NH + side * NH + r;
-                        double sgn = side == 0 ? 1.0 : -1.0;
-                        double gw = sgn * cw;
-                        SoftRow sr = soft_row(ts[row], ls[row], ss[row], ms[row], gw, soft_d(k, side * NH + r), z, Z);
-                        double kap = (pass == 0 ? 0.0 : tau - pas[row]) - ls[row] * ts[row];
-                        double nu = (pass == 0 ? 0.0 : tau - pbs[row]) - ms[row] * ss[row];
-                        double rho = -sr.r_s + kap / ts[row] + nu / ss[row] + sr.Th * sr.r_p;
-                        rps[row] = sr.r_p;
-                        rhos[row] = rho;
-                        double coef = -kap / ts[row] + sr.Th * (rho / sr.D - sr.r_p);
-                        thn += sr.Tht;
-                        cn += sgn * coef;
+                if (kk >= k0) {
+#pragma unroll
+                    for (int r = 0; r < NH; ++r) {
+                        const double c0 = c_pos(kk, r, 0), c1 = c_pos(kk, r, 1), c2 = c_pos(kk, r, 2);
+                        const double cw = c0 * Wsm[(HC0 + 0) * KP + kk] + c1 * Wsm[(HC0 + 1) * KP + kk] + c2 * Wsm[(HC0 + 2) * KP + kk];
+                        const double z = P.zs[r] * scale(kk), Z = P.Zs[r] * scale(kk);
+                        double thn = 0.0, cn = 0.0;
+#pragma unroll
+                        for (int side = 0; side < 2; ++side) {
+                            const int a = side * NH + r;
+                            const double sgn = side == 0 ? 1.0 : -1.0;
+                            const double ct = pass == 0 ? 0.0 : tau - prod[(2 * NU + a) * KP + kk];
+                            const double cs = pass == 0 ? 0.0 : tau - prod[(2 * NU + 2 * NH + a) * KP + kk];
+                            const SoftEval ev = soft_eval(ts[a], ls[a], ss[a], ms[a], sgn * cw, soft_d(kk, a), z, Z, ct, cs);
+                            thn += ev.Tht;
+                            cn += sgn * ev.coef;
+                            if (pass == 0) {
+                                res_rows = fmax(res_rows, fmax(fabs(ev.r_p), fabs(ev.r_s)));
+                                const double ca = ls[a] * ts[a], cb = ms[a] * ss[a];
+                                cmax = fmax(cmax, fmax(ca, cb)); csum += ca + cb;
+                            }
+                        }
+                        Dp[0] += thn * c0 * c0; Dp[1] += thn * c1 * c0; Dp[2] += thn * c1 * c1;
+                        Dp[3] += thn * c2 * c0; Dp[4] += thn * c2 * c1; Dp[5] += thn * c2 * c2;
+                        gp[0] += cn * c0; gp[1] += cn * c1; gp[2] += cn * c2;
                     }
                 }
-                thns[e] = thn;
-                cns[e] = cn;
+#pragma unroll
+                for (int j = 0; j < NU; ++j) { corr[j * KP + kk] = du[j]; corr[(NU + 6 + j) * KP + kk] = gu[j]; }
+#pragma unroll
+                for (int c = 0; c < 6; ++c) corr[(NU + c) * KP + kk] = Dp[c];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) corr[(2 * NU + 6 + c) * KP + kk] = gp[c];
+            }
+            if (pass == 0) {
+                // ---- convergence test on the state BEFORE this iteration's step ----
+                res_rows = L.max(res_rows);
+                cmax = L.max(cmax);
+                mubar = L.sum(csum) / ncomp;
+                res_track = fmax(res_rows, phi * res_v0);
+#if defined(SDFNMPC_QP_DEBUG) && !defined(__CUDA_ARCH__)
+                printf("it %d res %.3e (rows %.3e) cmax %.3e phi %.3e\n", it, res_track, res_rows, cmax, phi);
+#endif
+                if (!(res_track == res_track) || !(mubar == mubar) || res_track > 1e300) { status = 4; stop = true; break; }
+                if (res_track <= P.tol_res && cmax <= P.tol) { status = 0; stop = true; break; }
+                if (it >= P.max_iter) { status = 2; stop = true; break; }
+                // Mehrotra's corrector can cycle on poorly centred iterates; if the largest complementarity product
+                // has not dropped by 30 % over two iterations switch (for good) to plain damped path following.
+                if (it >= 2 && cmax > 0.7 * cm_prev2) safe = true;
+                cm_prev2 = cm_prev1; cm_prev1 = cmax;
             }
             L.sync();
-            // ---------- modified Hessian (pass 0 only) and gradient ----------
+            // =========== backward Riccati sweep (pass 0: factorise + solve; pass 1: new right-hand side only) ===========
             if (pass == 0) {
-                for (int e = lane; e < (N + 1) * NW * NW; e += NL) {
-                    int k = e / (NW * NW), ij = e % (NW * NW), i = ij / NW, j = ij % NW;
-                    double s = H[e];
-                    if (k < N && i == j && i < NU) s += thnb[k * NU + i];
-                    if (k >= k0)
-                        for (int r = 0; r < NH; ++r) {
-                            const double* Cr = P.C + ((size_t)k * NH + r) * NW;
-                            s += thns[k * NH + r] * Cr[i] * Cr[j];
-                        }
-                    Ht[e] = s;
+                for (int e = lane; e < NX * NX; e += NL) {
+                    const int i = e / NX, j = e - i * NX;
+                    double s = H[(size_t)N * NW * NW + (size_t)(NU + i) * NW + NU + j];
+                    const int pi_ = i + NU - HC0, pj = j + NU - HC0;
+                    if (pi_ >= 0 && pi_ < 3 && pj >= 0 && pj < 3) s += corr[(NU + sym3(pi_, pj)) * KP + N];
+                    Psm[e] = s;
                 }
             }
-            for (int e = lane; e < (N + 1) * NW; e += NL) {
-                int k = e / NW, i = e % NW;
-                double s = rvec[e];
-                if (k < N && i < NU) s += cnb[k * NU + i];
-                if (k >= k0)
-                    for (int r = 0; r < NH; ++r) s += cns[k * NH + r] * P.C[((size_t)k * NH + r) * NW + i];
-                gt[e] = s;
+            for (int e = lane; e < NX; e += NL) {
+                double s = phi * rv0[(size_t)N * NW + NU + e];
+                const int pe = e + NU - HC0;
+                if (pe >= 0 && pe < 3) s += corr[(2 * NU + 6 + pe) * KP + N];
+                pv[e] = s;
             }
             L.sync();
-            // ---------- backward Riccati sweep ----------
-            if (pass == 0) {
-                for (int e = lane; e < NX * NX; e += NL) Psm[e] = Ht[(size_t)N * NW * NW + (size_t)(NU + e / NX) * NW + NU + e % NX];
-            }
-            for (int e = lane; e < NX; e += NL) pv[e] = gt[(size_t)N * NW + NU + e];
-            L.sync();
-            for (int k = N - 1; k >= 0; --k) {
-                const double* ABk = P.AB + (size_t)k * NX * NW;
+            for (int kk = N - 1; kk >= 0; --kk) {
+                const double* ABk = P.AB + (size_t)kk * NX * NW;
                 if (pass == 0) {
-                    for (int e = lane; e < NX * NW; e += NL) ABb[(e / NW) * NWB + e % NW] = ABk[e];
-                    for (int e = lane; e < NX; e += NL) ABb[e * NWB + NW] = rdyn[(k + 1) * NX + e];
+                    for (int e = lane; e < NX * NW; e += NL) { const int i = e / NW; ABb[i * NWB + (e - i * NW)] = ABk[e]; }
+                    for (int e = lane; e < NX; e += NL) ABb[e * NWB + NW] = phi * rd0[(size_t)(kk + 1) * NX + e];
                     L.sync();
                     for (int e = lane; e < NX * NWB; e += NL) {
-                        int i = e / NWB, j = e % NWB;
+                        const int i = e / NWB, j = e - i * NWB;
                         double s = 0.0;
+#pragma unroll
                         for (int l = 0; l < NX; ++l) s += Psm[i * NX + l] * ABb[l * NWB + j];
-                        if (j == NW) { PbM[k * NX + i] = s; s += pv[i]; }
+                        if (j == NW) { PbM[kk * NX + i] = s; s += pv[i]; }
                         PAB[e] = s;
                     }
                     L.sync();
-                    constexpr int TRI = NW * (NW + 1) / 2;
                     for (int e = lane; e < TRI + NW; e += NL) {
                         if (e < TRI) {
-                            int i, j;
-                            tri_decode(e, i, j);
-                            double s = Ht[(size_t)k * NW * NW + i * NW + j];
+                            const int i = tri.i[e], j = tri.j[e];
+                            double s = H[(size_t)kk * NW * NW + i * NW + j];
+#pragma unroll
                             for (int l = 0; l < NX; ++l) s += ABb[l * NWB + i] * PAB[l * NWB + j];
+                            if (i == j && i < NU) s += corr[i * KP + kk];
+                            const int pi_ = i - HC0, pj = j - HC0;
+                            if (pi_ >= 0 && pi_ < 3 && pj >= 0 && pj < 3) s += corr[(NU + sym3(pi_, pj)) * KP + kk];
                             Msm[i * NW + j] = s;
                             Msm[j * NW + i] = s;
                         } else {
-                            int i = e - TRI;
-                            double s = gt[(size_t)k * NW + i];
+                            const int i = e - TRI;
+                            double s = phi * rv0[(size_t)kk * NW + i];
+#pragma unroll
                             for (int l = 0; l < NX; ++l) s += ABb[l * NWB + i] * PAB[l * NWB + NW];
+                            if (i < NU) s += corr[(NU + 6 + i) * KP + kk];
+                            const int pi_ = i - HC0;
+                            if (pi_ >= 0 && pi_ < 3) s += corr[(2 * NU + 6 + pi_) * KP + kk];
                             rv[i] = s;
                         }
                     }
                     L.sync();
-                    // Cholesky of Ruu, redundantly in every lane
+                    // Cholesky of Ruu (every lane, redundantly, in registers); diagonal kept inverted
                     double Lr[NU][NU];
                     bool ok = true;
+#pragma unroll
                     for (int i = 0; i < NU; ++i)
+#pragma unroll
                         for (int j = 0; j <= i; ++j) {
                             double s = Msm[i * NW + j];
+#pragma unroll
                             for (int l = 0; l < j; ++l) s -= Lr[i][l] * Lr[j][l];
-                            if (i == j) { ok = ok && (s > 0.0); Lr[i][i] = sqrt(s); }
-                            else Lr[i][j] = s / Lr[j][j];
+                            if (i == j) { ok = ok && (s > 0.0); Lr[i][i] = 1.0 / sqrt(s); }
+                            else Lr[i][j] = s * Lr[j][j];
                         }
                     if (!ok) status = 4;
                     for (int c = lane; c < NX + 1; c += NL) {
                         double x[NU];
+#pragma unroll
                         for (int i = 0; i < NU; ++i) {
                             double s = c < NX ? Msm[i * NW + NU + c] : rv[i];
+#pragma unroll
                             for (int l = 0; l < i; ++l) s -= Lr[i][l] * x[l];
-                            x[i] = s / Lr[i][i];
+                            x[i] = s * Lr[i][i];
                         }
+#pragma unroll
                         for (int i = NU - 1; i >= 0; --i) {
                             double s = x[i];
+#pragma unroll
                             for (int l = i + 1; l < NU; ++l) s -= Lr[l][i] * x[l];
-                            x[i] = s / Lr[i][i];
+                            x[i] = s * Lr[i][i];
                         }
+#pragma unroll
                         for (int i = 0; i < NU; ++i) {
-                            if (c < NX) { Ksm[i * NX + c] = -x[i]; Kg[(size_t)k * NU * NX + i * NX + c] = -x[i]; }
-                            else { kfs[i] = -x[i]; kffg[k * NU + i] = -x[i]; }
+                            if (c < NX) { Ksm[i * NX + c] = -x[i]; Kg[(size_t)kk * NU * NX + i * NX + c] = -x[i]; }
+                            else kfs[i] = -x[i];
                         }
                     }
                     if (lane == 0)
                         for (int i = 0; i < NU; ++i)
-                            for (int j = 0; j < NU; ++j) Lg[(size_t)k * NU * NU + i * NU + j] = j <= i ? Lr[i][j] : 0.0;
+                            for (int j = 0; j < NU; ++j) Lg[(size_t)kk * NU * NU + i * NU + j] = j <= i ? Lr[i][j] : 0.0;
                     L.sync();
-                    for (int e = lane; e < NX * NX + NX; e += NL) {
-                        if (e < NX * NX) {
-                            int i = e / NX, j = e % NX;
+                    // P <- Qxx + Rux' K (lower triangle, mirrored: stays exactly symmetric), p <- r_x + Rux' kff
+                    constexpr int TRX = NX * (NX + 1) / 2;
+                    for (int e = lane; e < TRX + NX + NU; e += NL) {
+                        if (e < TRX) {
+                            const int i = tri.i[e], j = tri.j[e];      // same row-major lower-triangle enumeration
                             double s = Msm[(NU + i) * NW + NU + j];
+#pragma unroll
                             for (int u = 0; u < NU; ++u) s += Msm[(NU + i) * NW + u] * Ksm[u * NX + j];
-                            Psm[e] = s;
-                        } else {
-                            int i = e - NX * NX;
+                            Psm[i * NX + j] = s;
+                            Psm[j * NX + i] = s;
+                        } else if (e < TRX + NX) {
+                            const int i = e - TRX;
                             double s = rv[NU + i];
+#pragma unroll
                             for (int u = 0; u < NU; ++u) s += Msm[(NU + i) * NW + u] * kfs[u];
                             pv[i] = s;
+                        } else {
+                            const int j = e - TRX - NX;
+                            dW[j * KP + kk] = kfs[j];        // feed-forward, consumed by the roll-out
                         }
                     }
                     L.sync();
-                    // keep P symmetric against round-off drift (Msm is free again: use it as the temporary)
-                    for (int e = lane; e < NX * NX; e += NL) {
-                        int i = e / NX, j = e % NX;
-                        if (i > j) Msm[i * NW + j] = 0.5 * (Psm[i * NX + j] + Psm[j * NX + i]);
-                    }
-                    L.sync();
-                    for (int e = lane; e < NX * NX; e += NL) {
-                        int i = e / NX, j = e % NX;
-                        if (i > j) { double a = Msm[i * NW + j]; Psm[i * NX + j] = a; Psm[j * NX + i] = a; }
-                    }
-                    L.sync();
                 } else {
-                    for (int e = lane; e < NX; e += NL) vv[e] = PbM[k * NX + e] + pv[e];
+                    for (int e = lane; e < NX; e += NL) vv[e] = PbM[kk * NX + e] + pv[e];   // PbM already carries this iteration's phi
                     L.sync();
                     for (int i = lane; i < NW; i += NL) {
-                        double s = gt[(size_t)k * NW + i];
+                        double s = phi * rv0[(size_t)kk * NW + i];
+#pragma unroll
                         for (int l = 0; l < NX; ++l) s += ABk[l * NW + i] * vv[l];
+                        if (i < NU) s += corr[(NU + 6 + i) * KP + kk];
+                        const int pi_ = i - HC0;
+                        if (pi_ >= 0 && pi_ < 3) s += corr[(2 * NU + 6 + pi_) * KP + kk];
                         rv[i] = s;
                     }
                     L.sync();
-                    const double* Lk = Lg + (size_t)k * NU * NU;
+                    const double* Lk = Lg + (size_t)kk * NU * NU;
                     double x[NU];
+#pragma unroll
                     for (int i = 0; i < NU; ++i) {
                         double s = rv[i];
+#pragma unroll
                         for (int l = 0; l < i; ++l) s -= Lk[i * NU + l] * x[l];
-                        x[i] = s / Lk[i * NU + i];
+                        x[i] = s * Lk[i * NU + i];
                     }
+#pragma unroll
                     for (int i = NU - 1; i >= 0; --i) {
                         double s = x[i];
+#pragma unroll
                         for (int l = i + 1; l < NU; ++l) s -= Lk[l * NU + i] * x[l];
-                        x[i] = s / Lk[i * NU + i];
+                        x[i] = s * Lk[i * NU + i];
                     }
-                    if (lane == 0)
-                        for (int i = 0; i < NU; ++i) kffg[k * NU + i] = -x[i];
-                    const double* Kk = Kg + (size_t)k * NU * NX;
-                    for (int i = lane; i < NX; i += NL) {   // pv was last read two barriers ago
-                        double s = rv[NU + i];
-                        for (int u = 0; u < NU; ++u) s += Kk[u * NX + i] * rv[u];
-                        pv[i] = s;
+                    const double* Kk = Kg + (size_t)kk * NU * NX;
+                    for (int i = lane; i < NX + NU; i += NL) {
+                        if (i < NX) {
+                            double s = rv[NU + i];       // pv was last read two barriers ago
+#pragma unroll
+                            for (int u = 0; u < NU; ++u) s += Kk[u * NX + i] * rv[u];
+                            pv[i] = s;
+                        } else {
+                            dW[(i - NX) * KP + kk] = -x[i - NX];
+                        }
                     }
                     L.sync();
                 }
             }
-            // ---------- forward roll-out -> wp (= delta w) ----------
-            for (int i = lane; i < NX; i += NL) wp[NU + i] = rdyn[i];
+            // ---------- forward roll-out: dW = step ----------
+            for (int i = lane; i < NX; i += NL) dW[(NU + i) * KP] = 0.0;      // dx_0 = 0 (w_x0 already equals x0 - xbar_0)
             L.sync();
-            for (int k = 0; k < N; ++k) {
-                const double* Kk = Kg + (size_t)k * NU * NX;
-                double* wk = wp + (size_t)k * NW;
+            for (int kk = 0; kk < N; ++kk) {
+                const double* Kk = Kg + (size_t)kk * NU * NX;
                 for (int j = lane; j < NU; j += NL) {
-                    double s = kffg[k * NU + j];
-                    for (int i = 0; i < NX; ++i) s += Kk[j * NX + i] * wk[NU + i];
-                    wk[j] = s;
+                    double s = dW[j * KP + kk];
+#pragma unroll
+                    for (int i = 0; i < NX; ++i) s += Kk[j * NX + i] * dW[(NU + i) * KP + kk];
+                    dW[j * KP + kk] = s;
                 }
                 L.sync();
-                const double* ABk = P.AB + (size_t)k * NX * NW;
+                const double* ABk = P.AB + (size_t)kk * NX * NW;
                 for (int i = lane; i < NX; i += NL) {
-                    double s = rdyn[(k + 1) * NX + i];
-                    for (int j = 0; j < NW; ++j) s += ABk[i * NW + j] * wk[j];
-                    wk[NW + NU + i] = s;
+                    double s = phi * rd0[(size_t)(kk + 1) * NX + i];
+#pragma unroll
+                    for (int j = 0; j < NW; ++j) s += ABk[i * NW + j] * dW[j * KP + kk];
+                    dW[(NU + i) * KP + kk + 1] = s;
                 }
                 L.sync();
             }
-            for (int j = lane; j < NU; j += NL) wp[(size_t)N * NW + j] = 0.0;
-            L.sync();
-            // ---------- row steps ----------
-            double amax = 1e30, csum_aff = 0.0;
-            for (int e = lane; e < nhr; e += NL) {
-                int k = e / (2 * NU), a = e % (2 * NU);
-                int j = a < NU ? a : a - NU;
-                double sgn = a < NU ? 1.0 : -1.0;
-                double t = tb[e], lam = lb[e];
-                double gd = sgn * wp[k * NW + j];
-                double r_p = rpb[e];
-                double kap = (pass == 0 ? 0.0 : tau - pab[e]) - lam * t;
-                double dt_ = gd - r_p;
-                double dl = (kap - lam * dt_) / t;
-                dtb[e] = dt_; dlb[e] = dl;
-                amax = fmin(amax, fmin(step_to_boundary(t, dt_), step_to_boundary(lam, dl)));
-            }
-            for (int e = lane + k0 * 2 * NH; e < nsr; e += NL) {
-                int k = e / (2 * NH), a = e % (2 * NH);
-                int r = a < NH ? a : a - NH;
-                double sgn = a < NH ? 1.0 : -1.0;
-                const double* Cr = P.C + ((size_t)k * NH + r) * NW;
-                double cd = 0.0;
-                for (int i = 0; i < NW; ++i) cd += Cr[i] * wp[(size_t)k * NW + i];
-                double gd = sgn * cd;
-                double kap = (pass == 0 ? 0.0 : tau - pas[e]) - ls[e] * ts[e];
-                double nu = (pass == 0 ? 0.0 : tau - pbs[e]) - ms[e] * ss[e];
-                double Th = ls[e] / ts[e];
-                double Dd = (P.Zs[r] * scale(k) + ms[e] / ss[e]) + Th;
-                double rho = rhos[e];
-                double ds = (rho - Th * gd) / Dd;
-                double dt_ = gd + ds - rps[e];
-                double dl = (kap - ls[e] * dt_) / ts[e];
-                double dm = (nu - ms[e] * ds) / ss[e];
-                dts[e] = dt_; dls[e] = dl; dss[e] = ds; dms[e] = dm;
-                amax = fmin(amax, fmin(fmin(step_to_boundary(ts[e], dt_), step_to_boundary(ls[e], dl)),
-                                       fmin(step_to_boundary(ss[e], ds), step_to_boundary(ms[e], dm))));
+            // =========== row steps (lane = node): the node's (dt, dlam, ds, dmu) stay in registers ===========
+            double amax = 1e30;
+            SDF_NODE_LOOP(kk) {
+                SDF_LOAD_STATE(kk);
+#pragma unroll
+                for (int a = 0; a < 2 * NU; ++a) { dtb[a] = 0.0; dlb[a] = 0.0; }
+#pragma unroll
+                for (int a = 0; a < 2 * NH; ++a) { dts[a] = 0.0; dls[a] = 0.0; dss[a] = 0.0; dms[a] = 0.0; }
+                if (kk < N) {
+#pragma unroll
+                    for (int j = 0; j < NU; ++j) {
+                        const double wu = Wsm[j * KP + kk], dwu = dW[j * KP + kk];
+#pragma unroll
+                        for (int side = 0; side < 2; ++side) {
+                            const int a = side * NU + j;
+                            const double sgn = side == 0 ? 1.0 : -1.0;
+                            const double cr = pass == 0 ? 0.0 : tau - prod[a * KP + kk];
+                            const HardEval ev = hard_eval(tb[a], lb[a], sgn * wu, hard_d(kk, a), cr);
+                            const double kap = cr - lb[a] * tb[a];
+                            dtb[a] = sgn * dwu - ev.r_p;
+                            dlb[a] = (kap - lb[a] * dtb[a]) / tb[a];
+                            amax = fmin(amax, fmin(step_to_boundary(tb[a], dtb[a]), step_to_boundary(lb[a], dlb[a])));
+                        }
+                    }
+                }
+                if (kk >= k0) {
+#pragma unroll
+                    for (int r = 0; r < NH; ++r) {
+                        const double c0 = c_pos(kk, r, 0), c1 = c_pos(kk, r, 1), c2 = c_pos(kk, r, 2);
+                        const double cw = c0 * Wsm[(HC0 + 0) * KP + kk] + c1 * Wsm[(HC0 + 1) * KP + kk] + c2 * Wsm[(HC0 + 2) * KP + kk];
+                        const double cd = c0 * dW[(HC0 + 0) * KP + kk] + c1 * dW[(HC0 + 1) * KP + kk] + c2 * dW[(HC0 + 2) * KP + kk];
+                        const double z = P.zs[r] * scale(kk), Z = P.Zs[r] * scale(kk);
+#pragma unroll
+                        for (int side = 0; side < 2; ++side) {
+                            const int a = side * NH + r;
+                            const double sgn = side == 0 ? 1.0 : -1.0;
+                            const double ct = pass == 0 ? 0.0 : tau - prod[(2 * NU + a) * KP + kk];
+                            const double cs = pass == 0 ? 0.0 : tau - prod[(2 * NU + 2 * NH + a) * KP + kk];
+                            const SoftEval ev = soft_eval(ts[a], ls[a], ss[a], ms[a], sgn * cw, soft_d(kk, a), z, Z, ct, cs);
+                            const double kap = ct - ls[a] * ts[a], nu = cs - ms[a] * ss[a];
+                            const double gd = sgn * cd;
+                            dss[a] = (ev.rho - ev.Th * gd) / ev.D;
+                            dts[a] = gd + dss[a] - ev.r_p;
+                            dls[a] = (kap - ls[a] * dts[a]) / ts[a];
+                            dms[a] = (nu - ms[a] * dss[a]) / ss[a];
+                            amax = fmin(amax, fmin(fmin(step_to_boundary(ts[a], dts[a]), step_to_boundary(ls[a], dls[a])),
+                                                   fmin(step_to_boundary(ss[a], dss[a]), step_to_boundary(ms[a], dms[a]))));
+                        }
+                    }
+                }
+                SDF_STORE_DELTA(kk);
             }
             amax = L.min(amax);
             if (pass == 0) {
+                // affine step length -> centring parameter; second-order products for the corrector
                 const double aa = fmin(1.0, amax);
-                for (int e = lane; e < nhr; e += NL) {
-                    csum_aff += (lb[e] + aa * dlb[e]) * (tb[e] + aa * dtb[e]);
-                    pab[e] = so * dlb[e] * dtb[e];
-                }
-                for (int e = lane + k0 * 2 * NH; e < nsr; e += NL) {
-                    csum_aff += (ls[e] + aa * dls[e]) * (ts[e] + aa * dts[e]) + (ms[e] + aa * dms[e]) * (ss[e] + aa * dss[e]);
-                    pas[e] = so * dls[e] * dts[e];
-                    pbs[e] = so * dms[e] * dss[e];
+                const double so = safe ? 0.0 : 1.0;
+                double csum_aff = 0.0;
+                SDF_NODE_LOOP(kk) {
+                    SDF_LOAD_STATE(kk);
+                    SDF_LOAD_DELTA(kk);
+                    if (kk < N) {
+#pragma unroll
+                        for (int a = 0; a < 2 * NU; ++a) {
+                            csum_aff += (lb[a] + aa * dlb[a]) * (tb[a] + aa * dtb[a]);
+                            prod[a * KP + kk] = so * dlb[a] * dtb[a];
+                        }
+                    }
+                    if (kk >= k0) {
+#pragma unroll
+                        for (int a = 0; a < 2 * NH; ++a) {
+                            csum_aff += (ls[a] + aa * dls[a]) * (ts[a] + aa * dts[a]) + (ms[a] + aa * dms[a]) * (ss[a] + aa * dss[a]);
+                            prod[(2 * NU + a) * KP + kk] = so * dls[a] * dts[a];
+                            prod[(2 * NU + 2 * NH + a) * KP + kk] = so * dms[a] * dss[a];
+                        }
+                    }
                 }
                 const double mu_aff = L.sum(csum_aff) / ncomp;
                 double sig = mu_aff / fmax(mubar, 1e-300);
@@ -566,58 +683,88 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                 tau = fmax(sig * mubar, 0.1 * P.tol);
                 L.sync();
             } else {
-                // ---------- costate step (pip = delta pi), then the damped step ----------
-                for (int i = lane; i < NX; i += NL) {
-                    const double* Hk = Ht + (size_t)N * NW * NW + (size_t)(NU + i) * NW;
-                    double s = gt[(size_t)N * NW + NU + i];
-                    for (int j = NU; j < NW; ++j) s += Hk[j] * wp[(size_t)N * NW + j];
-                    pip[(size_t)N * NX + i] = s;
-                }
-                L.sync();
-                for (int k = N - 1; k >= 1; --k) {
-                    const double* ABk = P.AB + (size_t)k * NX * NW;
-                    for (int i = lane; i < NX; i += NL) {
-                        const double* Hk = Ht + (size_t)k * NW * NW + (size_t)(NU + i) * NW;
-                        double s = gt[(size_t)k * NW + NU + i];
-                        for (int j = 0; j < NW; ++j) s += Hk[j] * wp[(size_t)k * NW + j];
-                        for (int l = 0; l < NX; ++l) s += ABk[l * NW + NU + i] * pip[(size_t)(k + 1) * NX + l];
-                        pip[(size_t)k * NX + i] = s;
-                    }
-                    L.sync();
-                }
+                // =========== damped step ===========
                 const double al = fmin(1.0, 0.995 * amax);
-#if defined(SDFNMPC_QP_DEBUG) && !defined(__CUDA_ARCH__)
-                {
-                    int wb = -1, ws = -1; double mb = 1e30, msv = 1e30; int which = 0;
-                    for (int e = 0; e < nhr; ++e) { double a1 = step_to_boundary(tb[e], dtb[e]), a2 = step_to_boundary(lb[e], dlb[e]); if (fmin(a1,a2) < mb) { mb = fmin(a1,a2); wb = e; } }
-                    for (int e = k0 * 2 * NH; e < nsr; ++e) { double a[4] = {step_to_boundary(ts[e], dts[e]), step_to_boundary(ls[e], dls[e]), step_to_boundary(ss[e], dss[e]), step_to_boundary(ms[e], dms[e])}; for (int q = 0; q < 4; ++q) if (a[q] < msv) { msv = a[q]; ws = e; which = q; } }
-                    printf("   alpha %.3e tau %.3e mubar %.3e | hard row %d a=%.3e (t %.3e l %.3e) | soft row %d var %d a=%.3e (t %.3e l %.3e s %.3e m %.3e)\n", al, tau, mubar, wb, mb, tb[wb], lb[wb], ws, which, msv, ts[ws], ls[ws], ss[ws], ms[ws]);
+                SDF_NODE_LOOP(kk) {
+                    SDF_LOAD_STATE(kk);
+                    SDF_LOAD_DELTA(kk);
+#pragma unroll
+                    for (int a = 0; a < 2 * NU; ++a) { tb[a] += al * dtb[a]; lb[a] += al * dlb[a]; }
+#pragma unroll
+                    for (int a = 0; a < 2 * NH; ++a) { ts[a] += al * dts[a]; ls[a] += al * dls[a]; ss[a] += al * dss[a]; ms[a] += al * dms[a]; }
+                    SDF_STORE_STATE(kk);
                 }
-#endif
-                for (int e = lane; e < (N + 1) * NW; e += NL) w[e] += al * wp[e];
-                for (int e = lane + NX; e < (N + 1) * NX; e += NL) pi[e] += al * pip[e];
-                for (int e = lane; e < nhr; e += NL) { tb[e] += al * dtb[e]; lb[e] += al * dlb[e]; }
-                for (int e = lane + k0 * 2 * NH; e < nsr; e += NL) {
-                    ts[e] += al * dts[e]; ls[e] += al * dls[e]; ss[e] += al * dss[e]; ms[e] += al * dms[e];
-                }
+                for (int e = lane; e < NW * KP; e += NL) Wsm[e] += al * dW[e];
+                phi *= (1.0 - al);
                 L.sync();
             }
         }
-        if (status == 4) break;
+        if (stop || status == 4) break;
+    }
+
+    // ---- verification of the KKT residuals the iteration only tracked (costates by one backward sweep) ----
+    double res_true = 0.0;
+    {
+        SDF_NODE_LOOP(kk) {
+            SDF_LOAD_STATE(kk);
+            for (int j = 0; j < NU; ++j) corr[j * KP + kk] = kk < N ? lb[j] - lb[NU + j] : 0.0;
+            for (int r = 0; r < NH; ++r) corr[(NU + r) * KP + kk] = kk >= k0 ? ls[r] - ls[NH + r] : 0.0;
+        }
+        L.sync();
+        for (int kk = N; kk >= 0; --kk) {
+            for (int i = lane; i < NW; i += NL) {
+                if (kk == N && i < NU) continue;
+                double s = g[(size_t)kk * NW + i];
+                for (int j = 0; j < NW; ++j) s += H[(size_t)kk * NW * NW + i * NW + j] * Wsm[j * KP + kk];
+                if (i < NU) s -= corr[i * KP + kk];
+                if (i >= HC0 && i < HC0 + 3)
+                    for (int r = 0; r < NH; ++r) s -= corr[(NU + r) * KP + kk] * c_pos(kk, r, i - HC0);
+                if (kk < N)
+                    for (int l = 0; l < NX; ++l) s += P.AB[(size_t)kk * NX * NW + l * NW + i] * pig[(size_t)(kk + 1) * NX + l];
+                if (i < NU) res_true = fmax(res_true, fabs(s));      // input stationarity
+                else pig[(size_t)kk * NX + (i - NU)] = s;            // defines the costate of node kk (x-stationarity == 0)
+            }
+            if (kk < N)
+                for (int i = lane; i < NX; i += NL) {
+                    double s = P.bdyn[kk * NX + i] - Wsm[(NU + i) * KP + kk + 1];
+                    for (int j = 0; j < NW; ++j) s += P.AB[(size_t)kk * NX * NW + i * NW + j] * Wsm[j * KP + kk];
+                    res_true = fmax(res_true, fabs(s));
+                }
+            L.sync();
+        }
+        res_true = L.max(res_true);
+        if (status == 0 && !(res_true <= 100.0 * P.tol_res)) status = 3;    // tracked residual was wrong: report, do not hide
     }
 
     // ---- full SQP step and outputs -----------------------------------------------------------
     if (status != 4) {
-        for (int e = lane; e < (N + 1) * NX; e += NL) P.xbar[e] += w[(size_t)(e / NX) * NW + NU + e % NX];
-        for (int e = lane; e < N * NU; e += NL) P.ubar[e] += w[(size_t)(e / NU) * NW + e % NU];
+        for (int e = lane; e < (N + 1) * NX; e += NL) { const int kk = e / NX, i = e - kk * NX; P.xbar[e] += Wsm[(NU + i) * KP + kk]; }
+        for (int e = lane; e < N * NU; e += NL) { const int kk = e / NU, j = e - kk * NU; P.ubar[e] += Wsm[j * KP + kk]; }
     }
     L.sync();
     for (int j = lane; j < NU; j += NL) P.u0[j] = P.ubar[j];
-    if (P.lam_hard)
-        for (int e = lane; e < nhr; e += NL) P.lam_hard[e] = lb[e];
-    if (P.lam_soft)
-        for (int e = lane; e < nsr; e += NL) P.lam_soft[e] = e >= k0 * 2 * NH ? ls[e] : 0.0;
-    if (lane == 0) { *P.status = status; *P.iters = it; }
+    SDF_NODE_LOOP(kk) {
+        SDF_LOAD_STATE(kk);
+        if (P.lam_hard && kk < N)
+            for (int a = 0; a < 2 * NU; ++a) P.lam_hard[kk * 2 * NU + a] = lb[a];
+        if (P.lam_soft)
+            for (int a = 0; a < 2 * NH; ++a) P.lam_soft[kk * 2 * NH + a] = kk >= k0 ? ls[a] : 0.0;
+    }
+#if !defined(__CUDA_ARCH__)
+    delete[] TB;
+    delete[] TD;
+#endif
+    if (lane == 0) {
+        *P.status = status;
+        *P.iters = it;
+        if (P.res_out) *P.res_out = res_true;
+    }
 }
+
+#undef SDF_NODE_LOOP
+#undef SDF_LOAD_STATE
+#undef SDF_STORE_STATE
+#undef SDF_LOAD_DELTA
+#undef SDF_STORE_DELTA
 
 }  // namespace sdfnmpc

@@ -34,7 +34,7 @@ extern "C" void emul_qp(int B, int N, int k0, int max_iter, int nyN, double lm, 
                         double* lam_hard, double* lam_soft, int* status, int* iters) {
     constexpr int NX = ATT_NX, NU = ATT_NU, NW = ATT_NW, NY = ATT_NY, NH = ATT_NH;
     std::vector<double> work(Shape::work_doubles(N));
-    std::vector<double> sm(Shape::SMEM_DOUBLES);
+    std::vector<double> sm(Shape::smem_doubles(N));
     Lanes L{0};
     for (int b = 0; b < B; ++b) {
         Prob P;
@@ -59,6 +59,7 @@ extern "C" void emul_qp(int B, int N, int k0, int max_iter, int nyN, double lm, 
         P.u0 = u0 + (size_t)b * NU;
         P.lam_hard = lam_hard + (size_t)b * N * 2 * NU;
         P.lam_soft = lam_soft + (size_t)b * (N + 1) * 2 * NH;
+        P.res_out = nullptr;
         P.status = status + b;
         P.iters = iters + b;
         qp_solve_instance<NX, NU, NY, NH>(L, P, sm.data());
