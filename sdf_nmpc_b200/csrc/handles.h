@@ -23,6 +23,15 @@ struct sdfnmpc_sdf {
     int cap_inst = 0, n_inst = 0;
     size_t smem = 0;
     int sm_count = 148;
+    // tensor-core (tcgen05) path: chunk program, packed hi|lo weight chunks, per-CTA scratch
+    bool tc_ok = false;
+    void* tc_ops = nullptr;          // SdfTcOp[] (device)
+    int tc_n_ops = 0;
+    unsigned char* tc_wblob = nullptr;
+    float* tc_scratch = nullptr;
+    size_t tc_scratch_per_cta = 0;
+    int tc_sc_off[4] = {0, 0, 0, 0};
+    int tc_min_points = 2048;        // below this the CUDA-core kernel is used
     // scratch for the host-convenience entry points
     float *h_pts = nullptr, *h_out = nullptr, *h_lat = nullptr;
     size_t h_cap = 0;

@@ -5,6 +5,7 @@
 #include <string>
 #include "handles.h"
 #include "sdf_kernels.cuh"
+#include "sdf_tc_kernel.cuh"
 
 namespace sdfnmpc {
 std::atomic<uint64_t> g_launches{0};
@@ -26,7 +27,113 @@ using namespace sdfnmpc;
 extern "C" const char* sdfnmpc_version(void) { return "sdfnmpc_b200 0.1 (sm_100a)"; }
 extern "C" uint64_t sdfnmpc_launch_count(void) { return g_launches.load(); }
 
-static inline int pad8(int v) { return (v + 7) / 8 * 8; }
+static inline int pad8(int v) { return (v + 31) / 32 * 32; }   // every feature dimension is padded to the 32-wide tensor-core chunk
+
+
+// ------------------------------------------------------------------------------------------
+// Tensor-core path: chunk program + weight chunks pre-split (hi | lo TF32) and pre-laid-out in the UMMA canonical
+// K-major no-swizzle layout, so that one bulk copy lands a ready-to-use B operand in shared memory.
+// ------------------------------------------------------------------------------------------
+namespace {
+inline float tf32_rna_host(float x) {
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    u = (u + 0x1000u) & 0xFFFFE000u;       // round to nearest, ties away (cvt.rna.tf32.f32)
+    float r;
+    memcpy(&r, &u, 4);
+    return r;
+}
+
+// B[n][k] for n < N, k < K (row-major accessor); appends K/32 chunks and returns their byte offsets
+template <class Acc>
+void pack_chunks(std::vector<float>& blob, int N, int K, Acc at, std::vector<uint32_t>& offs) {
+    for (int k0 = 0; k0 < K; k0 += 32) {
+        offs.push_back((uint32_t)(blob.size() * sizeof(float)));
+        const size_t base = blob.size();
+        blob.resize(base + (size_t)N * 32 * 2, 0.f);
+        for (int n = 0; n < N; ++n)
+            for (int k = 0; k < 32; ++k) {
+                const float v = at(n, k0 + k);
+                const float hi = tf32_rna_host(v), lo = tf32_rna_host(v - hi);
+                const size_t idx = (size_t)(n >> 3) * 256 + (size_t)(k >> 2) * 32 + (size_t)(n & 7) * 4 + (k & 3);
+                blob[base + idx] = hi;
+                blob[base + (size_t)N * 32 + idx] = lo;
+            }
+    }
+}
+
+int build_tc(sdfnmpc_sdf* h, const float* W1, const float* W2, const float* W3, const float* W4) {
+    const SdfNetDev& n = h->net;
+    const sdfnmpc_sdf_desc& d = h->desc;
+    if (n.H1 > 256 || n.H2 > 256 || n.H3 > 128 || n.H4 > 64 || n.Ep > 128 || n.H1 % 32 || n.H2 % 32 || n.H3 % 32 || n.H4 % 32) return 0;
+    const int E = n.E, L = n.L, h1 = d.hidden[0], h2 = d.hidden[1], h3 = d.hidden[2], h4 = d.hidden[3];
+    const int in1 = E + L, in3 = h2 + (d.res_state ? E : 0) + (d.res_latent ? L : 0);
+    std::vector<float> blob;
+    std::vector<uint32_t> oW1, oW2, oW3h, oW3e, oW4, oW4T, oW3hT, oW3eT, oW2T, oW1T;
+    auto z = [](bool ok, float v) { return ok ? v : 0.f; };
+    pack_chunks(blob, n.H1, n.Ep, [&](int r, int k) { return z(r < h1 && k < E, (r < h1 && k < E) ? W1[(size_t)r * in1 + k] : 0.f); }, oW1);
+    pack_chunks(blob, n.H2, n.H1, [&](int r, int k) { return (r < h2 && k < h1) ? W2[(size_t)r * h1 + k] : 0.f; }, oW2);
+    pack_chunks(blob, n.H3, n.H2, [&](int r, int k) { return (r < h3 && k < h2) ? W3[(size_t)r * in3 + k] : 0.f; }, oW3h);
+    if (n.res_state) pack_chunks(blob, n.H3, n.Ep, [&](int r, int k) { return (r < h3 && k < E) ? W3[(size_t)r * in3 + h2 + k] : 0.f; }, oW3e);
+    pack_chunks(blob, n.H4, n.H3, [&](int r, int k) { return (r < h4 && k < h3) ? W4[(size_t)r * h3 + k] : 0.f; }, oW4);
+    // reverse operands: B[n = input feature][k = output feature]
+    pack_chunks(blob, n.H3, n.H4, [&](int r, int k) { return (k < h4 && r < h3) ? W4[(size_t)k * h3 + r] : 0.f; }, oW4T);
+    pack_chunks(blob, n.H2, n.H3, [&](int r, int k) { return (k < h3 && r < h2) ? W3[(size_t)k * in3 + r] : 0.f; }, oW3hT);
+    if (n.res_state) pack_chunks(blob, n.Ep, n.H3, [&](int r, int k) { return (k < h3 && r < E) ? W3[(size_t)k * in3 + h2 + r] : 0.f; }, oW3eT);
+    pack_chunks(blob, n.H1, n.H2, [&](int r, int k) { return (k < h2 && r < h1) ? W2[(size_t)k * h1 + r] : 0.f; }, oW2T);
+    pack_chunks(blob, n.Ep, n.H1, [&](int r, int k) { return (k < h1 && r < E) ? W1[(size_t)k * in1 + r] : 0.f; }, oW1T);
+
+    std::vector<SdfTcOp> ops;
+    auto add = [&](int prod, int src_col, int feat0, int layer, int wait_d, uint32_t w_off, int n_total, int d_col, int first, int last) {
+        SdfTcOp o{};
+        o.prod = prod; o.src_col = src_col; o.feat0 = feat0; o.layer = layer; o.wait_d = wait_d; o.pre_drain_ge3 = 0;
+        o.w_off = w_off; o.w_bytes = (uint32_t)n_total * 32 * 4 * 2; o.n_total = n_total; o.n_piece = 1;
+        o.d_col[0] = d_col; o.n_rows[0] = n_total; o.b_row0[0] = 0; o.d_col[1] = 0; o.n_rows[1] = 0; o.b_row0[1] = 0;
+        o.first = first; o.last = last;
+        ops.push_back(o);
+    };
+    const int c1 = n.Ep / 32, cH1 = n.H1 / 32, cH2 = n.H2 / 32, cH3 = n.H3 / 32, cH4 = n.H4 / 32;
+    // forward
+    for (int j = 0; j < c1; ++j) add(TC_PROD_EMBED, 0, 32 * j, 0, 0, oW1[j], n.H1, 0, j == 0, j == c1 - 1);
+    for (int j = 0; j < cH1; ++j) add(TC_PROD_ACT, 0 + 32 * j, 32 * j, 1, j == 0, oW2[j], n.H2, 256, j == 0, j == cH1 - 1);
+    for (int j = 0; j < cH2; ++j) add(TC_PROD_ACT, 256 + 32 * j, 32 * j, 2, j == 0, oW3h[j], n.H3, 0, j == 0, (!n.res_state) && j == cH2 - 1);
+    if (n.res_state)
+        for (int j = 0; j < c1; ++j) add(TC_PROD_EMBED, 0, 32 * j, 0, 0, oW3e[j], n.H3, 0, 0, j == c1 - 1);
+    for (int j = 0; j < cH3; ++j) add(TC_PROD_ACT, 0 + 32 * j, 32 * j, 3, j == 0, oW4[j], n.H4, 128, j == 0, j == cH3 - 1);
+    // reverse
+    for (int j = 0; j < cH4; ++j) add(TC_PROD_G4, 128 + 32 * j, 32 * j, 4, j == 0, oW4T[j], n.H3, 0, j == 0, j == cH4 - 1);
+    for (int j = 0; j < cH3; ++j) add(TC_PROD_MUL, 0 + 32 * j, 32 * j, 3, j == 0, oW3hT[j], n.H2, 128, j == 0, (!n.res_state) && j == cH3 - 1);
+    if (n.res_state)
+        for (int j = 0; j < cH3; ++j) add(TC_PROD_MUL, 0 + 32 * j, 32 * j, 3, 0, oW3eT[j], n.Ep, 384, j == 0, j == cH3 - 1);
+    for (int j = 0; j < cH2; ++j) {
+        add(TC_PROD_MUL, 128 + 32 * j, 32 * j, 2, j == 0, oW2T[j], n.H1, 0, j == 0, j == cH2 - 1);
+        SdfTcOp& o = ops.back();
+        if (j == 0 && n.res_state) o.pre_drain_ge3 = 1;
+        if (n.H1 > 128) {       // D_g1 does not fit in one free column range: rows 0..127 @0, the rest @384
+            o.n_piece = 2;
+            o.n_rows[0] = 128; o.d_col[1] = 384; o.n_rows[1] = n.H1 - 128; o.b_row0[1] = 128;
+        }
+    }
+    for (int j = 0; j < cH1; ++j) add(TC_PROD_MUL, j < 4 ? 32 * j : 384 + 32 * (j - 4), 32 * j, 1, j == 0, oW1T[j], n.Ep, 128, j == 0, j == cH1 - 1);
+
+    h->tc_n_ops = (int)ops.size();
+    SDF_CUDA_CHECK(cudaMalloc(&h->tc_ops, ops.size() * sizeof(SdfTcOp)));
+    SDF_CUDA_CHECK(cudaMemcpy(h->tc_ops, ops.data(), ops.size() * sizeof(SdfTcOp), cudaMemcpyHostToDevice));
+    SDF_CUDA_CHECK(cudaMalloc(&h->tc_wblob, blob.size() * sizeof(float)));
+    SDF_CUDA_CHECK(cudaMemcpy(h->tc_wblob, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
+    h->tc_sc_off[0] = 0;
+    h->tc_sc_off[1] = h->tc_sc_off[0] + n.H1 * TC_TM;
+    h->tc_sc_off[2] = h->tc_sc_off[1] + n.H2 * TC_TM;
+    h->tc_sc_off[3] = h->tc_sc_off[2] + n.H3 * TC_TM;
+    h->tc_scratch_per_cta = (size_t)h->tc_sc_off[3] + (size_t)n.Ep * TC_TM;
+    SDF_CUDA_CHECK(cudaMalloc(&h->tc_scratch, h->tc_scratch_per_cta * sizeof(float) * h->sm_count));
+    SDF_CUDA_CHECK(cudaFuncSetAttribute(sdf_eval_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    const char* env = getenv("SDFNMPC_SDF_IMPL");
+    h->tc_ok = !(env && strcmp(env, "ffma") == 0);
+    if (env && strcmp(env, "tc") == 0) h->tc_min_points = 1;
+    return 0;
+}
+}  // namespace
 
 extern "C" int sdfnmpc_sdf_create(sdfnmpc_sdf_t* out, const sdfnmpc_sdf_desc* d, const float* dirs,
                                   const float* W1, const float* b1, const float* W2, const float* b2,
@@ -120,6 +227,7 @@ extern "C" int sdfnmpc_sdf_create(sdfnmpc_sdf_t* out, const sdfnmpc_sdf_desc* d,
     }
     e = cudaFuncSetAttribute(sdf_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
     if (e != cudaSuccess) { cudaFree(h->blob); delete h; return (int)e; }
+    if (int rc = build_tc(h, W1, W2, W3, W4)) { sdfnmpc_sdf_destroy(h); return rc; }
     *out = h;
     return 0;
 }
@@ -128,6 +236,7 @@ extern "C" int sdfnmpc_sdf_destroy(sdfnmpc_sdf_t h) {
     if (!h) return 0;
     cudaFree(h->blob); cudaFree(h->b1f); cudaFree(h->b3f);
     cudaFree(h->h_pts); cudaFree(h->h_out); cudaFree(h->h_lat);
+    cudaFree(h->tc_ops); cudaFree(h->tc_wblob); cudaFree(h->tc_scratch);
     delete h;
     return 0;
 }
@@ -159,6 +268,20 @@ extern "C" int sdfnmpc_sdf_eval(sdfnmpc_sdf_t h, const float* pts, const int32_t
     if (!pts) return SDFNMPC_E_INVALID;
     if (!pt2inst && (n + pts_per_inst - 1) / pts_per_inst > h->n_inst) return SDFNMPC_E_INVALID;
     if (n == 0) return 0;
+    if (h->tc_ok && grad && sdf && n >= h->tc_min_points) {
+        SdfTcParams P;
+        P.net = h->net; P.ops = (const SdfTcOp*)h->tc_ops; P.n_ops = h->tc_n_ops; P.wblob = h->tc_wblob;
+        P.scratch = h->tc_scratch; P.scratch_floats_per_cta = h->tc_scratch_per_cta;
+        P.sc_off_c1 = h->tc_sc_off[0]; P.sc_off_c2 = h->tc_sc_off[1]; P.sc_off_c3 = h->tc_sc_off[2]; P.sc_off_ge3 = h->tc_sc_off[3];
+        P.b1f = h->b1f; P.b3f = h->b3f; P.pts = pts; P.pt2inst = pt2inst; P.pts_per_inst = pts_per_inst; P.n = (int)n;
+        P.sdf_out = sdf; P.grad_out = grad;
+        const int64_t tc_tiles = (n + TC_TM - 1) / TC_TM;
+        const int tc_grid = (int)(tc_tiles < h->sm_count ? tc_tiles : h->sm_count);
+        sdf_eval_tc_kernel<<<tc_grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(P);
+        count_launch();
+        SDF_CUDA_CHECK(cudaGetLastError());
+        return 0;
+    }
     const int64_t tiles = (n + SDF_TM - 1) / SDF_TM;
     const int grid = (int)(tiles < (int64_t)h->sm_count * 8 ? tiles : (int64_t)h->sm_count * 8);
     sdf_eval_kernel<<<grid, SDF_THREADS, h->smem, (cudaStream_t)stream>>>(h->net, pts, pt2inst, pts_per_inst, h->b1f,
