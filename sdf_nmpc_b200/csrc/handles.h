@@ -31,7 +31,7 @@ struct sdfnmpc_sdf {
     float* tc_scratch = nullptr;
     size_t tc_scratch_per_cta = 0;
     int tc_sc_off[4] = {0, 0, 0, 0};
-    int tc_min_points = 2048;        // below this the CUDA-core kernel is used
+    int tc_min_points = 64;          // below this the CUDA-core kernel is used (a 128-point tile would be mostly padding)
     // scratch for the host-convenience entry points
     float *h_pts = nullptr, *h_out = nullptr, *h_lat = nullptr;
     size_t h_cap = 0;

@@ -55,7 +55,8 @@ void pack_chunks(std::vector<float>& blob, int N, int K, Acc at, std::vector<uin
             for (int k = 0; k < 32; ++k) {
                 const float v = at(n, k0 + k);
                 const float hi = tf32_rna_host(v), lo = tf32_rna_host(v - hi);
-                const size_t idx = (size_t)(n >> 3) * 256 + (size_t)(k >> 2) * 32 + (size_t)(n & 7) * 4 + (k & 3);
+                // 128-byte-swizzled K-major: 8-row atoms of 1024 B, row = 32 floats, 16-byte unit index XOR row-in-atom
+                const size_t idx = (size_t)(n >> 3) * 256 + (size_t)(n & 7) * 32 + (size_t)(((k >> 2) ^ (n & 7)) * 4) + (k & 3);
                 blob[base + idx] = hi;
                 blob[base + (size_t)N * 32 + idx] = lo;
             }
@@ -275,11 +276,30 @@ extern "C" int sdfnmpc_sdf_eval(sdfnmpc_sdf_t h, const float* pts, const int32_t
         P.sc_off_c1 = h->tc_sc_off[0]; P.sc_off_c2 = h->tc_sc_off[1]; P.sc_off_c3 = h->tc_sc_off[2]; P.sc_off_ge3 = h->tc_sc_off[3];
         P.b1f = h->b1f; P.b3f = h->b3f; P.pts = pts; P.pt2inst = pt2inst; P.pts_per_inst = pts_per_inst; P.n = (int)n;
         P.sdf_out = sdf; P.grad_out = grad;
+        P.trace = nullptr;
+        if (const char* tp = getenv("SDFNMPC_TC_TRACE")) {
+            static long long* tbuf = nullptr;
+            if (!tbuf) cudaMalloc(&tbuf, 8 * TC_MAX_OPS * sizeof(long long));
+            P.trace = tbuf;
+            (void)tp;
+        }
         const int64_t tc_tiles = (n + TC_TM - 1) / TC_TM;
         const int tc_grid = (int)(tc_tiles < h->sm_count ? tc_tiles : h->sm_count);
         sdf_eval_tc_kernel<<<tc_grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(P);
         count_launch();
         SDF_CUDA_CHECK(cudaGetLastError());
+        if (P.trace) {
+            std::vector<long long> tr(8 * TC_MAX_OPS);
+            cudaMemcpy(tr.data(), P.trace, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+            FILE* f = fopen(getenv("SDFNMPC_TC_TRACE"), "w");
+            if (f) {
+                for (int i = 0; i < h->tc_n_ops; ++i) {
+                    for (int k = 0; k < 8; ++k) fprintf(f, "%lld ", tr[i * 8 + k] - tr[0]);
+                    fprintf(f, "\n");
+                }
+                fclose(f);
+            }
+        }
         return 0;
     }
     const int64_t tiles = (n + SDF_TM - 1) / SDF_TM;

@@ -26,10 +26,14 @@ namespace sdfnmpc {
 
 constexpr int TC_TM = 128;                 // points per tile = UMMA M
 constexpr int TC_KC = 32;                  // features per chunk
-constexpr int TC_THREADS = 160;
+constexpr int TC_PROD_WARPS = 16;            // producer warps: 4 TMEM lane quarters x 4 column groups of 8
+constexpr int TC_PROD_THREADS = TC_PROD_WARPS * 32;
+constexpr int TC_THREADS = TC_PROD_THREADS + 32;
 constexpr int TC_WSTAGE_BYTES = 256 * TC_KC * 4 * 2;   // 64 KB: up to 256 weight rows, hi | lo
 constexpr int TC_ASTAGE_BYTES = TC_TM * TC_KC * 4 * 2;   // 32 KB: hi | lo
-constexpr int TC_SMEM_BYTES = 2 * TC_WSTAGE_BYTES + 2 * TC_ASTAGE_BYTES + 128 + 1024;
+constexpr int TC_MAX_OPS = 80;
+constexpr int TC_AUX_BYTES = 128 /*barriers*/ + 128 * 16 /*embedding table*/ + 4 * 128 * 4 * 4 /*row partials*/ + TC_MAX_OPS * 80 /*op program*/;
+constexpr int TC_SMEM_BYTES = 2 * TC_WSTAGE_BYTES + 2 * TC_ASTAGE_BYTES + TC_AUX_BYTES + 1024;
 
 enum { TC_PROD_EMBED = 0, TC_PROD_ACT = 1, TC_PROD_MUL = 2, TC_PROD_G4 = 3 };
 
@@ -64,6 +68,7 @@ struct SdfTcParams {
     int n;
     float* sdf_out;
     float* grad_out;
+    long long* trace;               // optional [n_ops][8] clock64 samples of CTA 0's second tile (development aid)
 };
 
 namespace tc {
@@ -83,6 +88,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "bra LAB_WAIT;\n\t"
         "DONE:\n\t"
         "}" ::"r"(bar), "r"(parity) : "memory");
+}
+// producers: back off between probes so that spinning warps do not steal issue slots from the MMA issuer
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, P1;\n\t"
+            "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(32);
+    }
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -124,19 +143,50 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// 32 lanes x 8 consecutive 32-bit columns -> 8 registers per thread
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, float* v) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+// sin and cos to ~1 ulp for |x| < 8192: 3-term Cody-Waite reduction by pi/2 + the cephes sinf/cosf minimax
+// polynomials on [-pi/4, pi/4] (22 instructions instead of the generic sincosf; no MUFU approximation involved)
+__device__ __forceinline__ void fast_sincos(float x, float& s, float& c) {
+    const float q = rintf(x * 0.636619772367581343f);
+    const int n = (int)q;
+    // pi/2 = C1 + C2 + C3 with C1 = float(pi/2); each fmaf rounds the exact x - q*C once (verified in numpy: max abs
+    // error 7e-8 for |x| <= 1000, the same as a correctly rounded float32 libm)
+    float r = fmaf(q, -1.5707963705062866f, x);
+    r = fmaf(q, 4.371138828673793e-08f, r);
+    r = fmaf(q, 1.7763568394002505e-15f, r);
+    const float r2 = r * r;
+    float ps = fmaf(fmaf(fmaf(-1.9515295891e-4f, r2, 8.3321608736e-3f), r2, -1.6666654611e-1f), r2 * r, r);
+    float pc = fmaf(fmaf(fmaf(fmaf(2.443315711809948e-5f, r2, -1.388731625493765e-3f), r2, 4.166664568298827e-2f), r2, -0.5f), r2, 1.0f);
+    const bool sw = n & 1;
+    float ss = sw ? pc : ps, cc = sw ? ps : pc;
+    s = (n & 2) ? -ss : ss;
+    c = ((n + 1) & 2) ? -cc : cc;
+}
 __device__ __forceinline__ float tf32_rna(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
-// K-major, no swizzle: LBO (K direction, between the two 16-byte core-matrix columns) = 128 B,
-// SBO (M/N direction, between 8-row groups) = 1024 B; descriptor version 1 (Blackwell)
+// K-major, 128-byte swizzle (the canonical UMMA layout ((8,n),2):((8,SBO),1) o Swizzle<3,4,3>): a row is the 128 bytes
+// of one 32-feature chunk, 8 rows form a 1024-byte atom whose 16-byte units are XOR-ed with the row index; SBO (between
+// 8-row groups) = 1024 B, LBO unused (1); descriptor version 1 (Blackwell), layout type 2 = SWIZZLE_128B.
+// The unswizzled INTERLEAVE layout measured 433 cycles per 128x256x8 MMA instead of 128 (operand fetch bound).
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)((128u >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)1 << 16;
     d |= (uint64_t)((1024u >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
     return d;
 }
 __device__ __forceinline__ uint32_t make_idesc(int n) {
@@ -147,7 +197,7 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
 __device__ __forceinline__ void act_pair(int act, float w0, float a, float& h, float& dh) {
     if (act == SDF_ACT_SIN) {
         float s, c;
-        sincosf(w0 * a, &s, &c);
+        fast_sincos(w0 * a, s, c);
         h = s; dh = w0 * c;
     } else if (act == SDF_ACT_RELU) {
         h = fmaxf(a, 0.f); dh = a > 0.f ? 1.f : 0.f;
@@ -156,16 +206,19 @@ __device__ __forceinline__ void act_pair(int act, float w0, float a, float& h, f
     }
 }
 
-// write 32 features of this thread's row into the A stage (hi | lo), canonical K-major layout
-__device__ __forceinline__ void store_a_chunk(unsigned char* a_stage, int row, const float* v) {
-    unsigned char* base = a_stage + (row >> 3) * 1024 + (row & 7) * 16;
+// write this thread's 8 features (column group cg of the 32-feature chunk) of its row into the A stage (hi | lo),
+// canonical K-major layout: 8-row groups of 1024 B, eight 128-B core matrices per group along K
+__device__ __forceinline__ void store_a8(unsigned char* a_stage, int row, int cg, const float* v) {
+    unsigned char* base = a_stage + (row >> 3) * 1024 + (row & 7) * 128;
+    const int sw = row & 7;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < 2; ++q) {
+        const int unit = ((cg * 2 + q) ^ sw) * 16;        // 128-byte swizzle: 16-byte unit index XOR row-in-atom
         float hi[4], lo[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) { hi[e] = tf32_rna(v[q * 4 + e]); lo[e] = tf32_rna(v[q * 4 + e] - hi[e]); }
-        *reinterpret_cast<float4*>(base + q * 128) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<float4*>(base + TC_ASTAGE_BYTES / 2 + q * 128) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<float4*>(base + unit) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(base + TC_ASTAGE_BYTES / 2 + unit) = make_float4(lo[0], lo[1], lo[2], lo[3]);
     }
 }
 
@@ -177,8 +230,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     unsigned char* wst[2] = {smem, smem + TC_WSTAGE_BYTES};
     unsigned char* ast[2] = {smem + 2 * TC_WSTAGE_BYTES, smem + 2 * TC_WSTAGE_BYTES + TC_ASTAGE_BYTES};
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * TC_WSTAGE_BYTES + 2 * TC_ASTAGE_BYTES);
+    unsigned char* aux = smem + 2 * TC_WSTAGE_BYTES + 2 * TC_ASTAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(aux);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    float4* etab = reinterpret_cast<float4*>(aux + 128);                 // [Ep] (dir * 2^f, phase)  / identity rows
+    float* part = reinterpret_cast<float*>(aux + 128 + 128 * 16);        // [4 column groups][128 rows][4]
+    SdfTcOp* ops_s = reinterpret_cast<SdfTcOp*>(aux + 128 + 128 * 16 + 4 * 128 * 4 * 4);   // op program (global loads per field cost ~300 cycles each)
     const uint32_t wfull[2] = {smem_u32(bars + 0), smem_u32(bars + 1)};
     const uint32_t afull[2] = {smem_u32(bars + 2), smem_u32(bars + 3)};
     const uint32_t sfree[2] = {smem_u32(bars + 4), smem_u32(bars + 5)};
@@ -186,15 +243,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const SdfNetDev& net = P.net;
+    const int DF = net.D * net.F;
+    const float HALF_PI = 1.57079632679489661923f;
 
     if (tid == 0) {
         mbar_init(wfull[0], 1); mbar_init(wfull[1], 1);
-        mbar_init(afull[0], TC_TM); mbar_init(afull[1], TC_TM);
+        mbar_init(afull[0], TC_PROD_THREADS); mbar_init(afull[1], TC_PROD_THREADS);
         mbar_init(sfree[0], 1); mbar_init(sfree[1], 1);
         mbar_init(dfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    // embedding table: feature j >= 3 is sin(sx*t.x + sy*t.y + sz*t.z + t.w) with t = (dir_d * 2^f, phase); scaling the
+    // direction by the power of two is exact, so the argument is bit-identical to (s . dir) * 2^f of the reference
+    for (int j = tid; j < net.Ep; j += TC_THREADS) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j >= 3 && j < net.E) {
+            const int q = (j - 3) % DF, d = q / net.F, f = q % net.F;
+            const float sc = (float)(1 << f);
+            t = make_float4(net.dirs[d] * sc, net.dirs[net.D + d] * sc, net.dirs[2 * net.D + d] * sc, (j - 3 >= DF) ? HALF_PI : 0.f);
+        }
+        etab[j] = t;
+    }
+    for (int i = tid; i < P.n_ops * (int)(sizeof(SdfTcOp) / 4); i += TC_THREADS)
+        reinterpret_cast<int*>(ops_s)[i] = reinterpret_cast<const int*>(P.ops)[i];
+    if (warp == TC_PROD_WARPS) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -208,164 +280,172 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
     uint32_t chunk = 0;           // global chunk counter (stage = chunk & 1, phase = (chunk >> 1) & 1)
     uint32_t dphase = 0;          // parity of the accumulator-complete barrier
 
-    if (warp < 4) {
-        // ============================== producers: thread <-> point ==============================
-        const int row = tid;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    if (warp < TC_PROD_WARPS) {
+        // ============================== producers: thread <-> (point, 8-feature column group) ==============================
+        const int lq = warp & 3, cg = warp >> 2;
+        const int row = lq * 32 + (tid & 31);
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(cg * 8);
         float* scr = P.scratch + (size_t)blockIdx.x * P.scratch_floats_per_cta;
-        const int DF = net.D * net.F;
-        const float HALF_PI = 1.57079632679489661923f;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int gi = tile * TC_TM + row;
             const int ic = gi < P.n ? gi : P.n - 1;
-            const float sx = P.pts[(size_t)ic * 3], sy = P.pts[(size_t)ic * 3 + 1], sz = P.pts[(size_t)ic * 3 + 2];
-            const int inst = P.pt2inst ? P.pt2inst[ic] : ic / P.pts_per_inst;
+            const float sx = __ldg(P.pts + (size_t)ic * 3), sy = __ldg(P.pts + (size_t)ic * 3 + 1), sz = __ldg(P.pts + (size_t)ic * 3 + 2);
+            const int inst = P.pt2inst ? __ldg(P.pt2inst + ic) : ic / P.pts_per_inst;
             const float* b1 = P.b1f + (size_t)inst * net.H1;
             const float* b3 = P.b3f + (size_t)inst * net.H3;
-            float d_acc = net.b5;
+            float d_acc = 0.f;
+            const bool tr = P.trace && blockIdx.x == 0 && tile == (int)gridDim.x && tid == 0;
             for (int oi = 0; oi < n_ops; ++oi, ++chunk) {
-                const SdfTcOp& op = P.ops[oi];
+                const SdfTcOp op = ops_s[oi];
                 const int s = chunk & 1;
-                if (op.wait_d) { mbar_wait(dfull, dphase); dphase ^= 1; tc_fence_after(); }
+                const int f8 = op.feat0 + cg * 8;                 // this thread's first feature within the layer
+                if (tr) P.trace[oi * 8 + 0] = clock64();
+                if (op.wait_d) { mbar_wait_backoff(dfull, dphase); dphase ^= 1; tc_fence_after(); }
                 if (op.pre_drain_ge3) {
                     // park the skip-connection part of the embedding gradient: D_ge3 (columns 384..) -> scratch
                     for (int f0 = 0; f0 < net.Ep; f0 += 32) {
-                        float v[32];
-                        tc_ld32(lane_addr + 384 + f0, v);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            *reinterpret_cast<float4*>(scr + P.sc_off_ge3 + ((size_t)((f0 >> 2) + q) * TC_TM + row) * 4) =
-                                make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                        float v[8];
+                        tc_ld8(lane_addr + 384 + f0, v);
+                        float4* dst = reinterpret_cast<float4*>(scr + P.sc_off_ge3 + ((size_t)((f0 + cg * 8) >> 2) * TC_TM + row) * 4);
+                        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+                        dst[TC_TM] = make_float4(v[4], v[5], v[6], v[7]);
                     }
                     tc_fence_before();
                 }
-                float v[32];
+                float v[8];
                 if (op.prod == TC_PROD_EMBED) {
-#pragma unroll 4
-                    for (int i = 0; i < 32; ++i) {
-                        const int j = op.feat0 + i;
-                        float e = 0.f;
-                        if (j < 3) {
-                            e = j == 0 ? sx : (j == 1 ? sy : sz);
-                        } else if (j < net.E) {
-                            const int q = (j - 3) % DF, d = q / net.F, f = q % net.F;
-                            const float proj = fmaf(sz, net.dirs[2 * net.D + d], fmaf(sy, net.dirs[net.D + d], sx * net.dirs[d]));
-                            float xb = proj * (float)(1 << f);
-                            if (j - 3 >= DF) xb = xb + HALF_PI;
-                            e = sinf(xb);
-                        }
-                        v[i] = e;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int j = f8 + i;
+                        const float4 t = etab[j];
+                        const float arg = fmaf(sz, t.z, fmaf(sy, t.y, sx * t.x)) + t.w;
+                        float sn, cs;
+                        fast_sincos(arg, sn, cs);
+                        v[i] = j < 3 ? (j == 0 ? sx : (j == 1 ? sy : sz)) : (j < net.E ? sn : 0.f);
                     }
                 } else {
-                    tc_ld32(lane_addr + op.src_col, v);
+                    tc_ld8(lane_addr + op.src_col, v);
                     if (op.prod == TC_PROD_ACT) {
-                        const float* bias = op.layer == 1 ? b1 : (op.layer == 2 ? net.b2 : b3);
-                        float* cs = scr + (op.layer == 1 ? P.sc_off_c1 : (op.layer == 2 ? P.sc_off_c2 : P.sc_off_c3));
+                        const float* bias = (op.layer == 1 ? b1 : (op.layer == 2 ? net.b2 : b3)) + f8;
+                        float* cs = scr + (op.layer == 1 ? P.sc_off_c1 : (op.layer == 2 ? P.sc_off_c2 : P.sc_off_c3)) + ((size_t)(f8 >> 2) * TC_TM + row) * 4;
+                        const float4 bq0 = __ldg(reinterpret_cast<const float4*>(bias)), bq1 = __ldg(reinterpret_cast<const float4*>(bias) + 1);
+                        const float bb[8] = {bq0.x, bq0.y, bq0.z, bq0.w, bq1.x, bq1.y, bq1.z, bq1.w};
+                        float c[8];
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float4 bq = __ldg(reinterpret_cast<const float4*>(bias + op.feat0) + q);
-                            const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
-                            float c[4];
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) act_pair(net.act, net.w0, v[q * 4 + e] + bb[e], v[q * 4 + e], c[e]);
-                            *reinterpret_cast<float4*>(cs + ((size_t)((op.feat0 >> 2) + q) * TC_TM + row) * 4) = make_float4(c[0], c[1], c[2], c[3]);
-                        }
+                        for (int e = 0; e < 8; ++e) act_pair(net.act, net.w0, v[e] + bb[e], v[e], c[e]);
+                        reinterpret_cast<float4*>(cs)[0] = make_float4(c[0], c[1], c[2], c[3]);
+                        reinterpret_cast<float4*>(cs)[TC_TM] = make_float4(c[4], c[5], c[6], c[7]);
                     } else if (op.prod == TC_PROD_MUL) {
-                        const float* cs = scr + (op.layer == 1 ? P.sc_off_c1 : (op.layer == 2 ? P.sc_off_c2 : P.sc_off_c3));
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float4 c = *reinterpret_cast<const float4*>(cs + ((size_t)((op.feat0 >> 2) + q) * TC_TM + row) * 4);
-                            v[q * 4] *= c.x; v[q * 4 + 1] *= c.y; v[q * 4 + 2] *= c.z; v[q * 4 + 3] *= c.w;
-                        }
+                        const float* cs = scr + (op.layer == 1 ? P.sc_off_c1 : (op.layer == 2 ? P.sc_off_c2 : P.sc_off_c3)) + ((size_t)(f8 >> 2) * TC_TM + row) * 4;
+                        const float4 c0 = reinterpret_cast<const float4*>(cs)[0], c1 = reinterpret_cast<const float4*>(cs)[TC_TM];
+                        v[0] *= c0.x; v[1] *= c0.y; v[2] *= c0.z; v[3] *= c0.w; v[4] *= c1.x; v[5] *= c1.y; v[6] *= c1.z; v[7] *= c1.w;
                     } else {   // TC_PROD_G4: output layer + seed of the reverse sweep
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float w5 = __ldg(net.W5 + op.feat0 + i);
+                        for (int i = 0; i < 8; ++i) {
+                            const float w5 = __ldg(net.W5 + f8 + i);
                             float h, c;
-                            act_pair(net.act, net.w0, v[i] + __ldg(net.b4 + op.feat0 + i), h, c);
+                            act_pair(net.act, net.w0, v[i] + __ldg(net.b4 + f8 + i), h, c);
                             d_acc = fmaf(w5, h, d_acc);
                             v[i] = w5 * c;
                         }
                     }
                     tc_fence_before();
                 }
-                mbar_wait(sfree[s], ((chunk >> 1) & 1) ^ 1);
-                store_a_chunk(ast[s], row, v);
+                if (tr) P.trace[oi * 8 + 1] = clock64();
+                mbar_wait_backoff(sfree[s], ((chunk >> 1) & 1) ^ 1);
+                if (tr) P.trace[oi * 8 + 2] = clock64();
+                store_a8(ast[s], row, cg, v);
                 fence_async_smem();
                 mbar_arrive(afull[s]);
+                if (tr) P.trace[oi * 8 + 3] = clock64();
             }
             // ---- final: g_e = D_ge1 (+ parked skip part) ; chain rule through the embedding ----
-            mbar_wait(dfull, dphase); dphase ^= 1; tc_fence_after();
+            mbar_wait_backoff(dfull, dphase); dphase ^= 1; tc_fence_after();
             float gx = 0.f, gy = 0.f, gz = 0.f;
             for (int f0 = 0; f0 < net.Ep; f0 += 32) {
-                float v[32];
-                tc_ld32(lane_addr + 128 + f0, v);
+                float v[8];
+                tc_ld8(lane_addr + 128 + f0, v);
+                const int f8 = f0 + cg * 8;
                 if (net.res_state) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 c = *reinterpret_cast<const float4*>(scr + P.sc_off_ge3 + ((size_t)((f0 >> 2) + q) * TC_TM + row) * 4);
-                        v[q * 4] += c.x; v[q * 4 + 1] += c.y; v[q * 4 + 2] += c.z; v[q * 4 + 3] += c.w;
-                    }
+                    const float* gs = scr + P.sc_off_ge3 + ((size_t)(f8 >> 2) * TC_TM + row) * 4;
+                    const float4 c0 = reinterpret_cast<const float4*>(gs)[0], c1 = reinterpret_cast<const float4*>(gs)[TC_TM];
+                    v[0] += c0.x; v[1] += c0.y; v[2] += c0.z; v[3] += c0.w; v[4] += c1.x; v[5] += c1.y; v[6] += c1.z; v[7] += c1.w;
                 }
-#pragma unroll 4
-                for (int i = 0; i < 32; ++i) {
-                    const int j = f0 + i;
-                    if (j < 3) {
-                        if (j == 0) gx += v[i]; else if (j == 1) gy += v[i]; else gz += v[i];
-                    } else if (j < net.E) {
-                        const int q = (j - 3) % DF, d = q / net.F, f = q % net.F;
-                        const float dx = net.dirs[d], dy = net.dirs[net.D + d], dz = net.dirs[2 * net.D + d];
-                        const float proj = fmaf(sz, dz, fmaf(sy, dy, sx * dx));
-                        const float sc = (float)(1 << f);
-                        float xb = proj * sc;
-                        if (j - 3 >= DF) xb = xb + HALF_PI;
-                        const float t = v[i] * cosf(xb) * sc;
-                        gx = fmaf(t, dx, gx); gy = fmaf(t, dy, gy); gz = fmaf(t, dz, gz);
-                    }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int j = f8 + i;
+                    const float4 t = etab[j];
+                    const float arg = fmaf(sz, t.z, fmaf(sy, t.y, sx * t.x)) + t.w;
+                    float sn, cs;
+                    fast_sincos(arg, sn, cs);
+                    const float w = (j >= 3 && j < net.E) ? v[i] * cs : 0.f;        // d/darg sin(arg) = cos(arg)
+                    gx = fmaf(w, t.x, gx); gy = fmaf(w, t.y, gy); gz = fmaf(w, t.z, gz);
+                    if (j == 0) gx += v[i];
+                    if (j == 1) gy += v[i];
+                    if (j == 2) gz += v[i];
                 }
             }
             tc_fence_before();
-            if (gi < P.n) {
-                if (P.sdf_out) P.sdf_out[gi] = d_acc;
-                if (P.grad_out) { P.grad_out[(size_t)gi * 3] = gx; P.grad_out[(size_t)gi * 3 + 1] = gy; P.grad_out[(size_t)gi * 3 + 2] = gz; }
+            // combine the four column groups of each row
+            reinterpret_cast<float4*>(part)[cg * TC_TM + row] = make_float4(gx, gy, gz, d_acc);
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD_THREADS) : "memory");
+            if (cg == 0 && gi < P.n) {
+                const float4 p0 = reinterpret_cast<const float4*>(part)[row], p1 = reinterpret_cast<const float4*>(part)[TC_TM + row];
+                const float4 p2 = reinterpret_cast<const float4*>(part)[2 * TC_TM + row], p3 = reinterpret_cast<const float4*>(part)[3 * TC_TM + row];
+                if (P.sdf_out) P.sdf_out[gi] = ((p0.w + p1.w) + (p2.w + p3.w)) + net.b5;
+                if (P.grad_out) {
+                    P.grad_out[(size_t)gi * 3] = (p0.x + p1.x) + (p2.x + p3.x);
+                    P.grad_out[(size_t)gi * 3 + 1] = (p0.y + p1.y) + (p2.y + p3.y);
+                    P.grad_out[(size_t)gi * 3 + 2] = (p0.z + p1.z) + (p2.z + p3.z);
+                }
             }
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD_THREADS) : "memory");
         }
-    } else if (tid == 128) {
+    } else if (tid == TC_PROD_THREADS) {
         // ============================== weight streamer + MMA issuer (one thread) ==============================
         const uint64_t n_chunks_total = (uint64_t)((n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * n_ops;
         if (n_chunks_total > 0) {
-            const SdfTcOp& o0 = P.ops[0];
+            const SdfTcOp o0 = ops_s[0];
             mbar_expect_tx(wfull[0], o0.w_bytes);
             bulk_g2s(smem_u32(wst[0]), P.wblob + o0.w_off, o0.w_bytes, wfull[0]);
         }
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const bool tr = P.trace && blockIdx.x == 0 && tile == (int)gridDim.x;
             for (int oi = 0; oi < n_ops; ++oi, ++chunk) {
-                const SdfTcOp& op = P.ops[oi];
+                const SdfTcOp op = ops_s[oi];
                 const int s = chunk & 1;
+                if (tr) P.trace[oi * 8 + 4] = clock64();
                 // prefetch the next chunk's weights into the other stage once its previous MMAs have retired
                 if ((uint64_t)chunk + 1 < n_chunks_total) {
-                    const SdfTcOp& nx = P.ops[oi + 1 < n_ops ? oi + 1 : 0];
+                    const SdfTcOp nx = ops_s[oi + 1 < n_ops ? oi + 1 : 0];
                     const uint32_t c1 = chunk + 1;
                     mbar_wait(sfree[c1 & 1], ((c1 >> 1) & 1) ^ 1);
                     mbar_expect_tx(wfull[c1 & 1], nx.w_bytes);
                     bulk_g2s(smem_u32(wst[c1 & 1]), P.wblob + nx.w_off, nx.w_bytes, wfull[c1 & 1]);
                 }
+                if (tr) P.trace[oi * 8 + 5] = clock64();
                 mbar_wait(wfull[s], (chunk >> 1) & 1);
+                if (tr) P.trace[oi * 8 + 6] = clock64();
                 mbar_wait(afull[s], (chunk >> 1) & 1);
+                if (tr) P.trace[oi * 8 + 7] = clock64();
                 tc_fence_after();
-                const uint32_t a_hi = smem_u32(ast[s]), a_lo = a_hi + TC_ASTAGE_BYTES / 2;
-                const uint32_t w_hi = smem_u32(wst[s]), w_lo = w_hi + (uint32_t)op.n_total * 128u;
+                // descriptors are built once per chunk; per MMA only the start-address field advances (+32 B = +2 units
+                // per K step of 8 tf32).  The issue loop is fully unrolled: a single thread issues ~6 instructions per MMA.
+                const uint32_t a_hi = smem_u32(ast[s]), w_hi = smem_u32(wst[s]);
+                const uint64_t ad_hi = make_desc(a_hi), ad_lo = make_desc(a_hi + TC_ASTAGE_BYTES / 2);
+                const uint64_t wd_hi = make_desc(w_hi), wd_lo = make_desc(w_hi + (uint32_t)op.n_total * 128u);
+                const uint32_t first_acc = op.first ? 0u : 1u;
 #pragma unroll 1
-                for (int ks = 0; ks < TC_KC / 8; ++ks) {
-#pragma unroll 1
-                    for (int sp = 0; sp < 3; ++sp) {
-                        const uint32_t a_base = (sp == 1 ? a_lo : a_hi) + ks * 256;
-                        const uint32_t w_base = (sp == 2 ? w_lo : w_hi) + ks * 256;
-                        for (int pc = 0; pc < op.n_piece; ++pc) {
-                            const uint32_t acc = (op.first && ks == 0 && sp == 0) ? 0u : 1u;
-                            tc_mma_tf32(tmem_base + (uint32_t)op.d_col[pc], make_desc(a_base),
-                                        make_desc(w_base + (uint32_t)(op.b_row0[pc] >> 3) * 1024u), make_idesc(op.n_rows[pc]), acc);
-                        }
+                for (int pc = 0; pc < op.n_piece; ++pc) {
+                    const uint32_t dcol = tmem_base + (uint32_t)op.d_col[pc];
+                    const uint32_t idesc = make_idesc(op.n_rows[pc]);
+                    const uint64_t boff = (uint64_t)((op.b_row0[pc] >> 3) * (1024 >> 4));
+                    const uint64_t bh = wd_hi + boff, bl = wd_lo + boff;
+#pragma unroll
+                    for (int ks = 0; ks < TC_KC / 8; ++ks) {
+                        tc_mma_tf32(dcol, ad_hi + 2 * ks, bh + 2 * ks, idesc, ks == 0 ? first_acc : 1u);
+                        tc_mma_tf32(dcol, ad_lo + 2 * ks, bh + 2 * ks, idesc, 1u);
+                        tc_mma_tf32(dcol, ad_hi + 2 * ks, bl + 2 * ks, idesc, 1u);
                     }
                 }
                 tc_commit(sfree[s]);
@@ -375,7 +455,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == TC_PROD_WARPS) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
