@@ -16,6 +16,9 @@ constexpr int NX = ATT_NX, NU = ATT_NU, NW = ATT_NW, NY = ATT_NY, NYN = ATT_NYN,
 using Shape = QpShape<NX, NU, NY, NH>;
 using Prob = QpProb<NX, NU, NY, NH>;
 constexpr int QP_WARPS = 4;     // instances per CTA
+#ifndef QP_MIN_CTAS
+#define QP_MIN_CTAS 2          // 8 warps per SM (capping registers at 168 for 12 warps/SM spills 3.6 KB and is 1.5x slower)
+#endif
 
 struct SolverConst {
     ModelConst mc;
@@ -64,7 +67,8 @@ struct QpBatch {
     double max_df;
 };
 
-__global__ void __launch_bounds__(QP_WARPS * 32) nmpc_qp_kernel(SolverConst sc, int B, QpBatch q) {
+template <int NFIX>
+__global__ void __launch_bounds__(QP_WARPS * 32, QP_MIN_CTAS) nmpc_qp_kernel(SolverConst sc, int B, QpBatch q) {
     extern __shared__ double sm_all[];
     __shared__ SolverConst scs;
     if (threadIdx.x == 0) scs = sc;
@@ -100,7 +104,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32) nmpc_qp_kernel(SolverConst sc, 
     P.iters = q.iters + b;
     Lanes L{(int)(threadIdx.x & 31)};
     P.res_out = q.res_out ? q.res_out + b : nullptr;
-    qp_solve_instance<NX, NU, NY, NH>(L, P, sm_all + (size_t)warp * Shape::smem_doubles(N));
+    qp_solve_instance<NX, NU, NY, NH, NFIX>(L, P, sm_all + (size_t)warp * Shape::smem_doubles(N));
 }
 
 __global__ void nmpc_init_traj_kernel(int N, int B, double u_hover, const double* __restrict__ x0,
@@ -184,7 +188,8 @@ extern "C" int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver
     alloc((void**)&h->lam_soft, B * N1 * 2 * NH * sizeof(double));
     alloc((void**)&h->qp_res, B * sizeof(double));
     h->qp_smem = (size_t)QP_WARPS * Shape::smem_doubles(d->N) * sizeof(double);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(nmpc_qp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qp_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(nmpc_qp_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qp_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(nmpc_qp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qp_smem);
     if (e == cudaSuccess) e = cudaMemcpy(h->dt, d->dt, N * sizeof(double), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemset(h->xbar, 0, B * N1 * NX * sizeof(double));
     if (e == cudaSuccess) e = cudaMemset(h->ubar, 0, B * N * NU * sizeof(double));
@@ -254,7 +259,8 @@ extern "C" int sdfnmpc_solver_rti_step(sdfnmpc_solver_t h, int32_t B, const doub
     q.u0 = u0; q.lam_hard = h->lam_hard; q.lam_soft = h->lam_soft; q.sdf_d = h->sdf_d; q.sdf_g = h->sdf_g;
     q.status = status; q.iters = qp_iters; q.work_per_inst = h->work_per_inst; q.max_df = (double)h->sdf->net.max_df;
     q.res_out = h->qp_res;
-    nmpc_qp_kernel<<<(B + QP_WARPS - 1) / QP_WARPS, QP_WARPS * 32, h->qp_smem, st>>>(h->sc, B, q);
+    if (N == 20) nmpc_qp_kernel<20><<<(B + QP_WARPS - 1) / QP_WARPS, QP_WARPS * 32, h->qp_smem, st>>>(h->sc, B, q);
+    else nmpc_qp_kernel<0><<<(B + QP_WARPS - 1) / QP_WARPS, QP_WARPS * 32, h->qp_smem, st>>>(h->sc, B, q);
     count_launch();
     SDF_CUDA_CHECK(cudaGetLastError());
     if (tm) { cudaEventRecord(ev[3], st); h->ev_steps++; }

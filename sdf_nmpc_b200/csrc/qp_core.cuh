@@ -142,14 +142,15 @@ SDF_NOINLINE SoftEval soft_eval(double t, double lam, double s, double mu, doubl
 
 }  // namespace qpdetail
 
-template <int NX, int NU, int NY, int NH, int HC0 = NU, int HCN = 3>
+template <int NX, int NU, int NY, int NH, int NFIX = 0, int HC0 = NU, int HCN = 3>
 SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, double* sm) {
     using namespace qpdetail;
     using S = QpShape<NX, NU, NY, NH>;
     static_assert(HCN == 3, "the position block is 3 wide");
     constexpr int NW = S::NW, NWB = NW + 1, TRI = S::TRI, NCORR = S::NCORR, NPROD = S::NPROD;
     constexpr TriTable<NW> tri{};
-    const int N = P.N, k0 = P.k0, KP = S::kp(N);
+    const int N = NFIX > 0 ? NFIX : P.N;          // NFIX: horizon known at compile time (all strides become immediates)
+    const int k0 = P.k0, KP = S::kp(N);
     const int NL = Lanes::count();
     const int lane = L.lane;
     const int ncomp = N * 2 * NU + 2 * (N + 1 - k0) * 2 * NH;
@@ -233,6 +234,11 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
     };
     auto c_pos = [&](int kk, int r, int c) { return P.C[((size_t)kk * NH + r) * NW + HC0 + c]; };
 
+// entry loop over the lanes of the group, fully unrolled with predication so that the independent dot-product chains of
+// one lane interleave (the dynamic-trip-count form serialised them: `wait` stalls) - constant bounds only
+#define SDF_LANES_FOR(v, X)                                                                                       \
+    _Pragma("unroll") for (int v##_it = 0; v##_it < ((X) + SDF_WARP_LANES - 1) / SDF_WARP_LANES; ++v##_it)        \
+        if (const int v = lane + v##_it * SDF_WARP_LANES; v < (X))
 #if defined(__CUDA_ARCH__)
 #define SDF_NODE_LOOP(kk) for (int kk = lane; kk <= N; kk += 32)
 #else
@@ -421,7 +427,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
             L.sync();
             // =========== backward Riccati sweep (pass 0: factorise + solve; pass 1: new right-hand side only) ===========
             if (pass == 0) {
-                for (int e = lane; e < NX * NX; e += NL) {
+                SDF_LANES_FOR(e, NX * NX) {
                     const int i = e / NX, j = e - i * NX;
                     double s = H[(size_t)N * NW * NW + (size_t)(NU + i) * NW + NU + j];
                     const int pi_ = i + NU - HC0, pj = j + NU - HC0;
@@ -429,7 +435,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                     Psm[e] = s;
                 }
             }
-            for (int e = lane; e < NX; e += NL) {
+            SDF_LANES_FOR(e, NX) {
                 double s = phi * rv0[(size_t)N * NW + NU + e];
                 const int pe = e + NU - HC0;
                 if (pe >= 0 && pe < 3) s += corr[(2 * NU + 6 + pe) * KP + N];
@@ -439,10 +445,10 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
             for (int kk = N - 1; kk >= 0; --kk) {
                 const double* ABk = P.AB + (size_t)kk * NX * NW;
                 if (pass == 0) {
-                    for (int e = lane; e < NX * NW; e += NL) { const int i = e / NW; ABb[i * NWB + (e - i * NW)] = ABk[e]; }
-                    for (int e = lane; e < NX; e += NL) ABb[e * NWB + NW] = phi * rd0[(size_t)(kk + 1) * NX + e];
+                    SDF_LANES_FOR(e, NX * NW) { const int i = e / NW; ABb[i * NWB + (e - i * NW)] = ABk[e]; }
+                    SDF_LANES_FOR(e, NX) ABb[e * NWB + NW] = phi * rd0[(size_t)(kk + 1) * NX + e];
                     L.sync();
-                    for (int e = lane; e < NX * NWB; e += NL) {
+                    SDF_LANES_FOR(e, NX * NWB) {
                         const int i = e / NWB, j = e - i * NWB;
                         double s = 0.0;
 #pragma unroll
@@ -451,7 +457,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                         PAB[e] = s;
                     }
                     L.sync();
-                    for (int e = lane; e < TRI + NW; e += NL) {
+                    SDF_LANES_FOR(e, TRI + NW) {
                         if (e < TRI) {
                             const int i = tri.i[e], j = tri.j[e];
                             double s = H[(size_t)kk * NW * NW + i * NW + j];
@@ -488,7 +494,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                             else Lr[i][j] = s * Lr[j][j];
                         }
                     if (!ok) status = 4;
-                    for (int c = lane; c < NX + 1; c += NL) {
+                    SDF_LANES_FOR(c, NX + 1) {
                         double x[NU];
 #pragma unroll
                         for (int i = 0; i < NU; ++i) {
@@ -516,7 +522,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                     L.sync();
                     // P <- Qxx + Rux' K (lower triangle, mirrored: stays exactly symmetric), p <- r_x + Rux' kff
                     constexpr int TRX = NX * (NX + 1) / 2;
-                    for (int e = lane; e < TRX + NX + NU; e += NL) {
+                    SDF_LANES_FOR(e, TRX + NX + NU) {
                         if (e < TRX) {
                             const int i = tri.i[e], j = tri.j[e];      // same row-major lower-triangle enumeration
                             double s = Msm[(NU + i) * NW + NU + j];
@@ -537,9 +543,9 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                     }
                     L.sync();
                 } else {
-                    for (int e = lane; e < NX; e += NL) vv[e] = PbM[kk * NX + e] + pv[e];   // PbM already carries this iteration's phi
+                    SDF_LANES_FOR(e, NX) vv[e] = PbM[kk * NX + e] + pv[e];   // PbM already carries this iteration's phi
                     L.sync();
-                    for (int i = lane; i < NW; i += NL) {
+                    SDF_LANES_FOR(i, NW) {
                         double s = phi * rv0[(size_t)kk * NW + i];
 #pragma unroll
                         for (int l = 0; l < NX; ++l) s += ABk[l * NW + i] * vv[l];
@@ -566,7 +572,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                         x[i] = s * Lk[i * NU + i];
                     }
                     const double* Kk = Kg + (size_t)kk * NU * NX;
-                    for (int i = lane; i < NX + NU; i += NL) {
+                    SDF_LANES_FOR(i, NX + NU) {
                         if (i < NX) {
                             double s = rv[NU + i];       // pv was last read two barriers ago
 #pragma unroll
@@ -580,11 +586,11 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                 }
             }
             // ---------- forward roll-out: dW = step ----------
-            for (int i = lane; i < NX; i += NL) dW[(NU + i) * KP] = 0.0;      // dx_0 = 0 (w_x0 already equals x0 - xbar_0)
+            SDF_LANES_FOR(i, NX) dW[(NU + i) * KP] = 0.0;      // dx_0 = 0 (w_x0 already equals x0 - xbar_0)
             L.sync();
             for (int kk = 0; kk < N; ++kk) {
                 const double* Kk = Kg + (size_t)kk * NU * NX;
-                for (int j = lane; j < NU; j += NL) {
+                SDF_LANES_FOR(j, NU) {
                     double s = dW[j * KP + kk];
 #pragma unroll
                     for (int i = 0; i < NX; ++i) s += Kk[j * NX + i] * dW[(NU + i) * KP + kk];
@@ -592,7 +598,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                 }
                 L.sync();
                 const double* ABk = P.AB + (size_t)kk * NX * NW;
-                for (int i = lane; i < NX; i += NL) {
+                SDF_LANES_FOR(i, NX) {
                     double s = phi * rd0[(size_t)(kk + 1) * NX + i];
 #pragma unroll
                     for (int j = 0; j < NW; ++j) s += ABk[i * NW + j] * dW[j * KP + kk];
@@ -762,6 +768,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
 }
 
 #undef SDF_NODE_LOOP
+#undef SDF_LANES_FOR
 #undef SDF_LOAD_STATE
 #undef SDF_STORE_STATE
 #undef SDF_LOAD_DELTA
