@@ -65,6 +65,30 @@ struct Lanes {
     }
 };
 
+// Asynchronous global -> shared staging of `n` doubles (n even, both pointers 16-byte aligned), split over the lanes.
+// Device: cp.async (LDGSTS, .cg = served from L2, so data this group wrote with plain stores is never read from a stale
+// L1 line) - the copy proceeds while the group computes on the other buffer.  Host: plain copy.
+SDF_HD void stage_async(const Lanes& L, double* dst_smem, const double* src, int n) {
+#if defined(__CUDA_ARCH__)
+    const unsigned d0 = (unsigned)__cvta_generic_to_shared(dst_smem);
+    for (int c = L.lane; c < n / 2; c += 32)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + c * 16), "l"(src + 2 * c) : "memory");
+#else
+    for (int c = 0; c < n; ++c) dst_smem[c] = src[c];
+    (void)L;
+#endif
+}
+SDF_HD void stage_commit() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+SDF_HD void stage_wait_all() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+}
+
 }  // namespace sdfnmpc
 
 #if defined(__CUDACC__)

@@ -40,6 +40,9 @@ struct QpShape {
     static constexpr int NCORR = NU + 6 + NU + 3;   // du, Dp(sym 3x3), gu, gp
     static constexpr int NPROD = 2 * NU + 4 * NH;   // second-order products per node
     SDF_HD static int kp(int N) { return N + 2; }   // padded node count of the [item][node] arrays
+    // per-stage data staged asynchronously into shared memory: AB | H | rv0 | rd0 | PbM | L | K
+    static constexpr int ST_AB = 0, ST_H = ST_AB + NX * NW, ST_RV = ST_H + NW * NW, ST_RD = ST_RV + NW, ST_PB = ST_RD + NX,
+                         ST_L = ST_PB + NX, ST_K = ST_L + NU * NU, STAGE_DOUBLES = (ST_K + NU * NX + 1) / 2 * 2;
     // doubles of per-instance global scratch
     SDF_HD static size_t work_doubles(int N) {
         size_t n1 = (size_t)(N + 1);
@@ -52,7 +55,8 @@ struct QpShape {
     SDF_HD static int smem_doubles(int N) {
         return NX * NX + 2 * NX * (NW + 1) + NW * NW + NW + NU * NX + NU + 2 * NX   // Riccati workspace
                + 2 * NW * kp(N)                                                   // W (iterate), dW (step)
-               + (NCORR + NPROD) * kp(N) + 8;
+               + (NCORR + NPROD) * kp(N) + 8
+               + 2 * STAGE_DOUBLES;                                               // double-buffered per-stage data
     }
 };
 
@@ -182,6 +186,8 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
     double* dW = Wsm + NW * KP;          // [NW][KP]   step
     double* corr = dW + NW * KP;         // [NCORR][KP] du(NU) Dp(6) gu(NU) gp(3) per node
     double* prod = corr + NCORR * KP;    // [NPROD][KP] affine second-order products
+    double* stg = prod + NPROD * KP + ((NPROD * KP) & 1);   // 2 x STAGE_DOUBLES (16-byte aligned)
+    static_assert(NX % 2 == 0 && NW % 2 == 0 && NU % 2 == 0, "stage_async moves 16-byte units");
 
     auto scale = [&](int k) { return k < N ? P.dt[k] : 1.0; };
     auto wrow = [&](int k, int r) { return k < N ? P.W[k * NY + r] : (r < P.nyN ? P.WN[r] : 0.0); };
@@ -442,11 +448,30 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                 pv[e] = s;
             }
             L.sync();
+            // stage data of node kk is prefetched into the other half of `stg` while node kk+1 is processed
+            auto prefetch = [&](int kk, double* dst) {
+                stage_async(L, dst + S::ST_AB, P.AB + (size_t)kk * NX * NW, NX * NW);
+                stage_async(L, dst + S::ST_RV, rv0 + (size_t)kk * NW, NW);
+                if (pass == 0) {
+                    stage_async(L, dst + S::ST_H, H + (size_t)kk * NW * NW, NW * NW);
+                    stage_async(L, dst + S::ST_RD, rd0 + (size_t)(kk + 1) * NX, NX);
+                } else {
+                    stage_async(L, dst + S::ST_PB, PbM + (size_t)kk * NX, NX);
+                    stage_async(L, dst + S::ST_L, Lg + (size_t)kk * NU * NU, NU * NU);
+                    stage_async(L, dst + S::ST_K, Kg + (size_t)kk * NU * NX, NU * NX);
+                }
+                stage_commit();
+            };
+            prefetch(N - 1, stg);
             for (int kk = N - 1; kk >= 0; --kk) {
-                const double* ABk = P.AB + (size_t)kk * NX * NW;
+                const double* sb = stg + ((N - 1 - kk) & 1) * S::STAGE_DOUBLES;
+                stage_wait_all();
+                L.sync();
+                if (kk > 0) prefetch(kk - 1, stg + ((N - kk) & 1) * S::STAGE_DOUBLES);
+                const double* ABk = sb + S::ST_AB;
                 if (pass == 0) {
                     SDF_LANES_FOR(e, NX * NW) { const int i = e / NW; ABb[i * NWB + (e - i * NW)] = ABk[e]; }
-                    SDF_LANES_FOR(e, NX) ABb[e * NWB + NW] = phi * rd0[(size_t)(kk + 1) * NX + e];
+                    SDF_LANES_FOR(e, NX) ABb[e * NWB + NW] = phi * sb[S::ST_RD + e];
                     L.sync();
                     SDF_LANES_FOR(e, NX * NWB) {
                         const int i = e / NWB, j = e - i * NWB;
@@ -460,7 +485,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                     SDF_LANES_FOR(e, TRI + NW) {
                         if (e < TRI) {
                             const int i = tri.i[e], j = tri.j[e];
-                            double s = H[(size_t)kk * NW * NW + i * NW + j];
+                            double s = sb[S::ST_H + i * NW + j];
 #pragma unroll
                             for (int l = 0; l < NX; ++l) s += ABb[l * NWB + i] * PAB[l * NWB + j];
                             if (i == j && i < NU) s += corr[i * KP + kk];
@@ -470,7 +495,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                             Msm[j * NW + i] = s;
                         } else {
                             const int i = e - TRI;
-                            double s = phi * rv0[(size_t)kk * NW + i];
+                            double s = phi * sb[S::ST_RV + i];
 #pragma unroll
                             for (int l = 0; l < NX; ++l) s += ABb[l * NWB + i] * PAB[l * NWB + NW];
                             if (i < NU) s += corr[(NU + 6 + i) * KP + kk];
@@ -543,10 +568,10 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                     }
                     L.sync();
                 } else {
-                    SDF_LANES_FOR(e, NX) vv[e] = PbM[kk * NX + e] + pv[e];   // PbM already carries this iteration's phi
+                    SDF_LANES_FOR(e, NX) vv[e] = sb[S::ST_PB + e] + pv[e];   // PbM already carries this iteration's phi
                     L.sync();
                     SDF_LANES_FOR(i, NW) {
-                        double s = phi * rv0[(size_t)kk * NW + i];
+                        double s = phi * sb[S::ST_RV + i];
 #pragma unroll
                         for (int l = 0; l < NX; ++l) s += ABk[l * NW + i] * vv[l];
                         if (i < NU) s += corr[(NU + 6 + i) * KP + kk];
@@ -555,7 +580,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                         rv[i] = s;
                     }
                     L.sync();
-                    const double* Lk = Lg + (size_t)kk * NU * NU;
+                    const double* Lk = sb + S::ST_L;
                     double x[NU];
 #pragma unroll
                     for (int i = 0; i < NU; ++i) {
@@ -571,7 +596,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                         for (int l = i + 1; l < NU; ++l) s -= Lk[l * NU + i] * x[l];
                         x[i] = s * Lk[i * NU + i];
                     }
-                    const double* Kk = Kg + (size_t)kk * NU * NX;
+                    const double* Kk = sb + S::ST_K;
                     SDF_LANES_FOR(i, NX + NU) {
                         if (i < NX) {
                             double s = rv[NU + i];       // pv was last read two barriers ago
@@ -588,8 +613,19 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
             // ---------- forward roll-out: dW = step ----------
             SDF_LANES_FOR(i, NX) dW[(NU + i) * KP] = 0.0;      // dx_0 = 0 (w_x0 already equals x0 - xbar_0)
             L.sync();
+            auto prefetch_f = [&](int kk, double* dst) {
+                stage_async(L, dst + S::ST_AB, P.AB + (size_t)kk * NX * NW, NX * NW);
+                stage_async(L, dst + S::ST_RD, rd0 + (size_t)(kk + 1) * NX, NX);
+                stage_async(L, dst + S::ST_K, Kg + (size_t)kk * NU * NX, NU * NX);
+                stage_commit();
+            };
+            prefetch_f(0, stg);
             for (int kk = 0; kk < N; ++kk) {
-                const double* Kk = Kg + (size_t)kk * NU * NX;
+                const double* sb = stg + (kk & 1) * S::STAGE_DOUBLES;
+                stage_wait_all();
+                L.sync();
+                if (kk + 1 < N) prefetch_f(kk + 1, stg + ((kk + 1) & 1) * S::STAGE_DOUBLES);
+                const double* Kk = sb + S::ST_K;
                 SDF_LANES_FOR(j, NU) {
                     double s = dW[j * KP + kk];
 #pragma unroll
@@ -597,9 +633,9 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                     dW[j * KP + kk] = s;
                 }
                 L.sync();
-                const double* ABk = P.AB + (size_t)kk * NX * NW;
+                const double* ABk = sb + S::ST_AB;
                 SDF_LANES_FOR(i, NX) {
-                    double s = phi * rd0[(size_t)(kk + 1) * NX + i];
+                    double s = phi * sb[S::ST_RD + i];
 #pragma unroll
                     for (int j = 0; j < NW; ++j) s += ABk[i * NW + j] * dW[j * KP + kk];
                     dW[(NU + i) * KP + kk + 1] = s;
