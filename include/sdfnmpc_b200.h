@@ -110,7 +110,8 @@ int sdfnmpc_solver_state(sdfnmpc_solver_t h, double** xbar_dev, double** ubar_de
                          double** lam_soft_dev);
 /* h values of the last linearisation [cap][N+1][3] and SDF query results d [cap][N+1], grad [cap][N+1][3]. */
 int sdfnmpc_solver_diag(sdfnmpc_solver_t h, double** hval_dev, float** sdf_d_dev, float** sdf_g_dev);
-/* Verified KKT residual (inf-norm of input stationarity and dynamics) of each instance's last QP: [cap]. */
+/* Per instance [cap][2]: verified KKT residual of the last QP (inf-norm of input stationarity and dynamics) and
+ * inf-norm of the full SQP step [du; dx] it produced (the full-SQP termination test of BatchedNmpc.solve_sqp). */
 int sdfnmpc_solver_qp_residual(sdfnmpc_solver_t h, double** res_dev);
 /* Per-kernel device timing of the next <= max_steps rti_step calls (CUDA events on the launching stream):
  * ms3 = summed milliseconds of {linearise, sdf, qp}; steps = number of timed calls. */

@@ -180,3 +180,26 @@ def closed_loop(net, prob, cfg, steps, plant_dt=None, move_ref=True):
         hist.append(dict(x=x.copy(), u0=out['u0'].copy(), status=out['status'].copy()))
         x = M.rk4(x, out['u0'], plant_dt, cfg)
     return x, xb, ub, hist
+
+
+def sqp_solve(net, xb, ub, prob, cfg, tol=1e-6, max_iter=100):
+    """Full SQP (config 5): repeat the RTI iteration until the full step is below `tol` (inf-norm over [du; dx]) or
+    `max_iter` iterations; converged instances are frozen.  Returns (xb, ub, iters [B], converged [B], last out).
+    Termination on the Newton-type step is this repository's definition (acados tests four KKT residuals; with exact
+    QP solves and full steps the step vanishes exactly when they do)."""
+    B = xb.shape[0]
+    xb, ub = xb.copy(), ub.copy()
+    iters = np.zeros(B, int)
+    active = np.ones(B, bool)
+    out = None
+    step_hist = []
+    for _ in range(max_iter):
+        if not active.any():
+            break
+        xn, un, out = rti_step(net, xb, ub, prob, cfg)
+        step = np.maximum(np.abs(out['dx']).reshape(B, -1).max(1), np.abs(out['du']).reshape(B, -1).max(1))
+        xb[active], ub[active] = xn[active], un[active]
+        iters[active] += 1
+        step_hist.append(np.where(active, step, np.nan))
+        active &= step > tol
+    return xb, ub, iters, ~active, dict(last=out, steps=np.array(step_hist))

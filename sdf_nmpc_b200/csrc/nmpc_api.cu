@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32, QP_MIN_CTAS) nmpc_qp_kernel(Sol
     P.status = q.status + b;
     P.iters = q.iters + b;
     Lanes L{(int)(threadIdx.x & 31)};
-    P.res_out = q.res_out ? q.res_out + b : nullptr;
+    P.res_out = q.res_out ? q.res_out + 2 * (size_t)b : nullptr;
     qp_solve_instance<NX, NU, NY, NH, NFIX>(L, P, sm_all + (size_t)warp * Shape::smem_doubles(N));
 }
 
@@ -186,7 +186,7 @@ extern "C" int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver
     alloc((void**)&h->work, B * h->work_per_inst * sizeof(double));
     alloc((void**)&h->lam_hard, B * N * 2 * NU * sizeof(double));
     alloc((void**)&h->lam_soft, B * N1 * 2 * NH * sizeof(double));
-    alloc((void**)&h->qp_res, B * sizeof(double));
+    alloc((void**)&h->qp_res, 2 * B * sizeof(double));
     h->qp_smem = (size_t)QP_WARPS * Shape::smem_doubles(d->N) * sizeof(double);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(nmpc_qp_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qp_smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(nmpc_qp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qp_smem);

@@ -85,7 +85,7 @@ struct QpProb {            // all pointers are offset to ONE instance
     double* u0;            // [NU]
     double* lam_hard;      // [N][2NU] or null
     double* lam_soft;      // [N+1][2NH] or null
-    double* res_out;       // verified KKT residual (inf-norm) or null
+    double* res_out;       // [2] or null: verified KKT residual (inf-norm), inf-norm of the full step [du; dx]
     int* status;           // 0 ok, 2 max-iter, 4 NaN / factorisation failure (acados codes)
     int* iters;
 };
@@ -778,6 +778,9 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
         if (status == 0 && !(res_true <= 100.0 * P.tol_res)) status = 3;    // tracked residual was wrong: report, do not hide
     }
 
+    double step_inf = 0.0;
+    for (int e = lane; e < (N + 1) * NW; e += NL) { const int kk = e / NW, i = e - kk * NW; step_inf = fmax(step_inf, fabs(Wsm[i * KP + kk])); }
+    step_inf = L.max(step_inf);
     // ---- full SQP step and outputs -----------------------------------------------------------
     if (status != 4) {
         for (int e = lane; e < (N + 1) * NX; e += NL) { const int kk = e / NX, i = e - kk * NX; P.xbar[e] += Wsm[(NU + i) * KP + kk]; }
@@ -799,7 +802,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
     if (lane == 0) {
         *P.status = status;
         *P.iters = it;
-        if (P.res_out) *P.res_out = res_true;
+        if (P.res_out) { P.res_out[0] = res_true; P.res_out[1] = step_inf; }
     }
 }
 

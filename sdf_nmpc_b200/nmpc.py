@@ -239,6 +239,32 @@ class BatchedNmpc:
         d, _ = self.sdf.eval(c0, pts_per_inst=1, want_grad=False)
         return d
 
+    def get_qp_residual(self):
+        """[B,2]: verified KKT residual of each instance's last QP, inf-norm of the SQP step it produced."""
+        p = C.c_void_p()
+        _lib.check(self.lib.sdfnmpc_solver_qp_residual(self.handle, C.byref(p)), 'qp_residual')
+        return self._view(p, (self.B, 2), torch.float64)
+
+    def solve_sqp(self, tol=1e-6, max_iter=100):
+        """Full SQP (BASELINE configs[4]): repeat the RTI iteration until the full step [du; dx] of an instance is below
+        `tol` (inf-norm) or `max_iter` iterations.  Instances are independent, so all of them keep iterating on the
+        device; iteration count and controls of each are recorded at ITS convergence.  Returns (u0 [B,4], sqp_iters [B],
+        converged [B])."""
+        done = torch.zeros(self.B, dtype=torch.bool, device=self.device)
+        iters = torch.zeros(self.B, dtype=torch.int64, device=self.device)
+        u_conv = torch.zeros(self.B, NU, dtype=torch.float64, device=self.device)
+        for _ in range(max_iter):
+            self.solve()
+            step = self.get_qp_residual()[:, 1]
+            iters += (~done).to(torch.int64)
+            newly = (~done) & (step <= tol)
+            u_conv = torch.where(newly[:, None], self.u0, u_conv)
+            done |= newly
+            if bool(done.all()):
+                break
+        u_conv = torch.where(done[:, None], u_conv, self.u0)
+        return u_conv, iters, done
+
     def timing_begin(self, max_steps):
         """Per-kernel CUDA-event timing of the next ``max_steps`` solves (bench.py roofline)."""
         _lib.check(self.lib.sdfnmpc_solver_timing_begin(self.handle, int(max_steps)), 'timing_begin')

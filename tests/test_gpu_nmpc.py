@@ -135,3 +135,48 @@ def test_single_instance_facade(cuda_device):
     xb, ub = rti.init_traj(x0[None], ocfg)
     _, _, out = rti.rti_step(net, xb, ub, prob, ocfg)
     assert np.abs(out['u0'][0] - u).max() <= U_TOL
+
+
+def test_full_sqp_iteration_counts_match_oracle(cuda_device):
+    """Full-SQP mode (BASELINE configs[4]): iterate to convergence of the step; per-instance SQP iteration counts and
+    the controls at convergence are compared with the oracle's loop.  (With the reference's lm_reg = 10 the Gauss-Newton
+    iteration contracts slowly, so a 5e-2 step tolerance is used to finish within 40 iterations.)"""
+    B, tol, max_iter = 12, 5e-2, 40
+    torch, rti, net, ocfg, prob, w, mpc = _setup(B, cuda_device)
+    xb, ub = rti.init_traj(prob['x0'], ocfg)
+    _, _, it_o, conv_o, info = rti.sqp_solve(net, xb, ub, prob, ocfg, tol=tol, max_iter=max_iter)
+    mpc.set_x0(prob['x0'])
+    u, it_g, conv_g = mpc.solve_sqp(tol=tol, max_iter=max_iter)
+    it_g, conv_g = it_g.cpu().numpy(), conv_g.cpu().numpy()
+    assert conv_o.all() and conv_g.all()
+    # a count may differ only if the oracle's deciding step sits within 1 % of the tolerance (it does not here)
+    steps = info['steps']
+    decisive = np.array([steps[it_o[b] - 1, b] for b in range(B)])
+    assert np.all((it_g == it_o) | (np.abs(decisive - tol) < 0.01 * tol)), (it_g, it_o)
+    assert np.array_equal(it_g, it_o)
+
+
+def test_encoder_in_the_loop(cuda_device):
+    """configs[4] data flow: per-step batched encoding of range images feeds set_latent, then one RTI solve."""
+    from sdf_nmpc_b200 import synth
+    from sdf_nmpc_b200.vae import VaeWrapper
+    B = 4
+    torch, rti, net, ocfg, prob, w, mpc = _setup(B, cuda_device)
+    cfg = mpc.cfg
+    vae = VaeWrapper(cfg, synth.make_encoder_net(seed=5), max_batch=B, device=cuda_device)
+    for step in range(2):
+        frames = np.stack([synth.depth_frame(seed=100 * step + i) for i in range(B)])
+        vae.set_img(frames)
+        lat = vae.encode(to_numpy=False)
+        assert lat.shape == (B, 128) and torch.isfinite(lat).all()
+        mpc.set_latent(lat, w['W_p_Bo'], w['W_R_Bo'])
+        mpc.set_x0(prob['x0'])
+        assert int(mpc.solve().max().item()) == 0
+    # the latent actually reaches the SDF: the oracle with the encoded latent reproduces the controls
+    prob2 = dict(prob); prob2['latent'] = lat.cpu().numpy()
+    mpc2 = type(mpc)(cfg, net, B, cuda_device)
+    mpc2.set_sdf_flag(1.0); mpc2.set_latent(lat, w['W_p_Bo'], w['W_R_Bo']); mpc2.set_ref_arrays(w['yref'], w['W'], w['yrefN'], w['WN'], w['qd'])
+    mpc2.set_x0(prob['x0']); mpc2.solve()
+    xb, ub = rti.init_traj(prob['x0'], ocfg)
+    _, _, out = rti.rti_step(net, xb, ub, prob2, ocfg)
+    assert np.abs(mpc2.get_u().cpu().numpy() - out['u0']).max() <= U_TOL
