@@ -26,7 +26,7 @@ struct sdfnmpc_sdf {
     // tensor-core (tcgen05) path: chunk program, packed hi|lo weight chunks, per-CTA scratch
     bool tc_ok = false;
     void* tc_ops = nullptr;          // SdfTcOp[] (device)
-    int tc_n_ops = 0;
+    int tc_n_ops = 0, tc_n_acc = 0;
     unsigned char* tc_wblob = nullptr;
     float* tc_scratch = nullptr;
     size_t tc_scratch_per_cta = 0;

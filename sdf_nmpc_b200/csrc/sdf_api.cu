@@ -117,6 +117,17 @@ int build_tc(sdfnmpc_sdf* h, const float* W1, const float* W2, const float* W3, 
     }
     for (int j = 0; j < cH1; ++j) add(TC_PROD_MUL, j < 4 ? 32 * j : 384 + 32 * (j - 4), 32 * j, 1, j == 0, oW1T[j], n.Ep, 128, j == 0, j == cH1 - 1);
 
+    // accumulator completions: d_commit = index of the accumulator an op publishes, d_need = index a TMEM-reading op needs
+    {
+        int n_acc = 0, cur_need = -1;
+        for (SdfTcOp& o : ops) {
+            if (o.wait_d) cur_need = n_acc - 1;
+            o.d_need = o.prod == TC_PROD_EMBED ? -1 : cur_need;
+            o.d_commit = o.last ? n_acc++ : -1;
+        }
+        if (n_acc > TC_MAX_ACC || (int)ops.size() > TC_MAX_OPS) return 0;   // program does not fit: CUDA-core kernel only
+        h->tc_n_acc = n_acc;
+    }
     h->tc_n_ops = (int)ops.size();
     SDF_CUDA_CHECK(cudaMalloc(&h->tc_ops, ops.size() * sizeof(SdfTcOp)));
     SDF_CUDA_CHECK(cudaMemcpy(h->tc_ops, ops.data(), ops.size() * sizeof(SdfTcOp), cudaMemcpyHostToDevice));
@@ -275,7 +286,7 @@ extern "C" int sdfnmpc_sdf_eval(sdfnmpc_sdf_t h, const float* pts, const int32_t
         P.scratch = h->tc_scratch; P.scratch_floats_per_cta = h->tc_scratch_per_cta;
         P.sc_off_c1 = h->tc_sc_off[0]; P.sc_off_c2 = h->tc_sc_off[1]; P.sc_off_c3 = h->tc_sc_off[2]; P.sc_off_ge3 = h->tc_sc_off[3];
         P.b1f = h->b1f; P.b3f = h->b3f; P.pts = pts; P.pt2inst = pt2inst; P.pts_per_inst = pts_per_inst; P.n = (int)n;
-        P.sdf_out = sdf; P.grad_out = grad;
+        P.sdf_out = sdf; P.grad_out = grad; P.n_acc = h->tc_n_acc;
         P.trace = nullptr;
         if (const char* tp = getenv("SDFNMPC_TC_TRACE")) {
             static long long* tbuf = nullptr;

@@ -26,7 +26,9 @@ namespace sdfnmpc {
 
 constexpr int TC_TM = 128;                 // points per tile = UMMA M
 constexpr int TC_KC = 32;                  // features per chunk
-constexpr int TC_PROD_WARPS = 16;            // producer warps: 4 TMEM lane quarters x 4 column groups of 8
+constexpr int TC_PROD_WARPS = 16;            // producer warps: 2 groups (even / odd chunks) x 4 TMEM lane quarters x 2 column groups of 16
+constexpr int TC_GROUP_THREADS = TC_PROD_WARPS * 32 / 2;
+constexpr int TC_MAX_ACC = 8;                // accumulator-complete barriers per tile
 constexpr int TC_PROD_THREADS = TC_PROD_WARPS * 32;
 constexpr int TC_THREADS = TC_PROD_THREADS + 32;
 constexpr int TC_WSTAGE_BYTES = 256 * TC_KC * 4 * 2;   // 64 KB: up to 256 weight rows, hi | lo
@@ -50,6 +52,8 @@ struct SdfTcOp {
     int n_piece;         // 1 or 2 MMAs along N
     int d_col[2], n_rows[2], b_row0[2];
     int first, last;     // first chunk of an accumulator (overwrite) / last (publish accumulator)
+    int d_need;          // accumulator completion (index within the tile) the producers need before reading TMEM, -1: none
+    int d_commit;        // accumulator completion this chunk publishes (last == 1), else -1
 };
 
 struct SdfTcParams {
@@ -68,6 +72,7 @@ struct SdfTcParams {
     int n;
     float* sdf_out;
     float* grad_out;
+    int n_acc;                      // accumulator completions per tile
     long long* trace;               // optional [n_ops][8] clock64 samples of CTA 0's second tile (development aid)
 };
 
@@ -153,6 +158,17 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, float* v) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+// 32 lanes x 16 consecutive 32-bit columns -> 16 registers per thread
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
 // sin and cos to ~1 ulp for |x| < 8192: 3-term Cody-Waite reduction by pi/2 + the cephes sinf/cosf minimax
 // polynomials on [-pi/4, pi/4] (22 instructions instead of the generic sincosf; no MUFU approximation involved)
 __device__ __forceinline__ void fast_sincos(float x, float& s, float& c) {
@@ -206,14 +222,14 @@ __device__ __forceinline__ void act_pair(int act, float w0, float a, float& h, f
     }
 }
 
-// write this thread's 8 features (column group cg of the 32-feature chunk) of its row into the A stage (hi | lo),
-// canonical K-major layout: 8-row groups of 1024 B, eight 128-B core matrices per group along K
-__device__ __forceinline__ void store_a8(unsigned char* a_stage, int row, int cg, const float* v) {
+// write this thread's 16 features (column half `ch` of the 32-feature chunk) of its row into the A stage (hi | lo),
+// 128-byte-swizzled K-major layout: 8-row atoms of 1024 B, row = 128 B, 16-byte unit index XOR row-in-atom
+__device__ __forceinline__ void store_a16(unsigned char* a_stage, int row, int ch, const float* v) {
     unsigned char* base = a_stage + (row >> 3) * 1024 + (row & 7) * 128;
     const int sw = row & 7;
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const int unit = ((cg * 2 + q) ^ sw) * 16;        // 128-byte swizzle: 16-byte unit index XOR row-in-atom
+    for (int q = 0; q < 4; ++q) {
+        const int unit = ((ch * 4 + q) ^ sw) * 16;
         float hi[4], lo[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) { hi[e] = tf32_rna(v[q * 4 + e]); lo[e] = tf32_rna(v[q * 4 + e] - hi[e]); }
@@ -231,15 +247,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
     unsigned char* wst[2] = {smem, smem + TC_WSTAGE_BYTES};
     unsigned char* ast[2] = {smem + 2 * TC_WSTAGE_BYTES, smem + 2 * TC_WSTAGE_BYTES + TC_ASTAGE_BYTES};
     unsigned char* aux = smem + 2 * TC_WSTAGE_BYTES + 2 * TC_ASTAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(aux);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(aux);                   // 0-1 wfull, 2-3 afull, 4-5 sfree, 6-13 dfull ring
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
     float4* etab = reinterpret_cast<float4*>(aux + 128);                 // [Ep] (dir * 2^f, phase)  / identity rows
     float* part = reinterpret_cast<float*>(aux + 128 + 128 * 16);        // [4 column groups][128 rows][4]
-    SdfTcOp* ops_s = reinterpret_cast<SdfTcOp*>(aux + 128 + 128 * 16 + 4 * 128 * 4 * 4);   // op program (global loads per field cost ~300 cycles each)
+    SdfTcOp* ops_s = reinterpret_cast<SdfTcOp*>(aux + 128 + 128 * 16 + 4 * 128 * 4 * 4);   // op program
     const uint32_t wfull[2] = {smem_u32(bars + 0), smem_u32(bars + 1)};
     const uint32_t afull[2] = {smem_u32(bars + 2), smem_u32(bars + 3)};
     const uint32_t sfree[2] = {smem_u32(bars + 4), smem_u32(bars + 5)};
-    const uint32_t dfull = smem_u32(bars + 6);
+    const uint32_t dfull0 = smem_u32(bars + 6);                          // dfull[q] = dfull0 + 8 q
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const SdfNetDev& net = P.net;
@@ -248,9 +264,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
 
     if (tid == 0) {
         mbar_init(wfull[0], 1); mbar_init(wfull[1], 1);
-        mbar_init(afull[0], TC_PROD_THREADS); mbar_init(afull[1], TC_PROD_THREADS);
+        mbar_init(afull[0], TC_GROUP_THREADS); mbar_init(afull[1], TC_GROUP_THREADS);
         mbar_init(sfree[0], 1); mbar_init(sfree[1], 1);
-        mbar_init(dfull, 1);
+        for (int q = 0; q < TC_MAX_ACC; ++q) mbar_init(dfull0 + 8 * q, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // embedding table: feature j >= 3 is sin(sx*t.x + sy*t.y + sz*t.z + t.w) with t = (dir_d * 2^f, phase); scaling the
@@ -278,45 +294,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
     const int n_tiles = (P.n + TC_TM - 1) / TC_TM;
     const int n_ops = P.n_ops;
     uint32_t chunk = 0;           // global chunk counter (stage = chunk & 1, phase = (chunk >> 1) & 1)
-    uint32_t dphase = 0;          // parity of the accumulator-complete barrier
 
     if (warp < TC_PROD_WARPS) {
-        // ============================== producers: thread <-> (point, 8-feature column group) ==============================
-        const int lq = warp & 3, cg = warp >> 2;
+        // ===== producers.  Group g (8 warps) owns the chunks with (chunk & 1) == g and therefore smem stage g: while one
+        // group waits for its stage / fences its stores, the other one computes.  thread <-> (point, 16-feature half) =====
+        const int g = warp >> 3, wq = warp & 7, lq = wq & 3, ch = wq >> 2;
         const int row = lq * 32 + (tid & 31);
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(cg * 8);
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(lq * 32) << 16);
         float* scr = P.scratch + (size_t)blockIdx.x * P.scratch_floats_per_cta;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        uint32_t tile_it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
             const int gi = tile * TC_TM + row;
             const int ic = gi < P.n ? gi : P.n - 1;
             const float sx = __ldg(P.pts + (size_t)ic * 3), sy = __ldg(P.pts + (size_t)ic * 3 + 1), sz = __ldg(P.pts + (size_t)ic * 3 + 2);
             const int inst = P.pt2inst ? __ldg(P.pt2inst + ic) : ic / P.pts_per_inst;
             const float* b1 = P.b1f + (size_t)inst * net.H1;
             const float* b3 = P.b3f + (size_t)inst * net.H3;
+            const uint32_t dpar = tile_it & 1;                  // every dfull[q] completes exactly once per tile
             float d_acc = 0.f;
-            const bool tr = P.trace && blockIdx.x == 0 && tile == (int)gridDim.x && tid == 0;
+            const bool tr = P.trace && blockIdx.x == 0 && tile == (int)gridDim.x && (tid & 255) == 0;
             for (int oi = 0; oi < n_ops; ++oi, ++chunk) {
+                if ((int)(chunk & 1) != g) continue;
                 const SdfTcOp op = ops_s[oi];
-                const int s = chunk & 1;
-                const int f8 = op.feat0 + cg * 8;                 // this thread's first feature within the layer
+                const int f16 = op.feat0 + ch * 16;               // this thread's first feature within the layer
                 if (tr) P.trace[oi * 8 + 0] = clock64();
-                if (op.wait_d) { mbar_wait_backoff(dfull, dphase); dphase ^= 1; tc_fence_after(); }
+                if (op.d_need >= 0) { mbar_wait_backoff(dfull0 + 8 * op.d_need, dpar); tc_fence_after(); }
                 if (op.pre_drain_ge3) {
                     // park the skip-connection part of the embedding gradient: D_ge3 (columns 384..) -> scratch
                     for (int f0 = 0; f0 < net.Ep; f0 += 32) {
-                        float v[8];
-                        tc_ld8(lane_addr + 384 + f0, v);
-                        float4* dst = reinterpret_cast<float4*>(scr + P.sc_off_ge3 + ((size_t)((f0 + cg * 8) >> 2) * TC_TM + row) * 4);
-                        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-                        dst[TC_TM] = make_float4(v[4], v[5], v[6], v[7]);
+                        float v[16];
+                        tc_ld16(lane_addr + 384 + f0 + ch * 16, v);
+                        float4* dst = reinterpret_cast<float4*>(scr + P.sc_off_ge3 + ((size_t)((f0 + ch * 16) >> 2) * TC_TM + row) * 4);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) dst[q * TC_TM] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
                     }
                     tc_fence_before();
                 }
-                float v[8];
+                float v[16];
                 if (op.prod == TC_PROD_EMBED) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int j = f8 + i;
+                    for (int i = 0; i < 16; ++i) {
+                        const int j = f16 + i;
                         const float4 t = etab[j];
                         const float arg = fmaf(sz, t.z, fmaf(sy, t.y, sx * t.x)) + t.w;
                         float sn, cs;
@@ -324,27 +342,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
                         v[i] = j < 3 ? (j == 0 ? sx : (j == 1 ? sy : sz)) : (j < net.E ? sn : 0.f);
                     }
                 } else {
-                    tc_ld8(lane_addr + op.src_col, v);
                     if (op.prod == TC_PROD_ACT) {
-                        const float* bias = (op.layer == 1 ? b1 : (op.layer == 2 ? net.b2 : b3)) + f8;
-                        float* cs = scr + (op.layer == 1 ? P.sc_off_c1 : (op.layer == 2 ? P.sc_off_c2 : P.sc_off_c3)) + ((size_t)(f8 >> 2) * TC_TM + row) * 4;
-                        const float4 bq0 = __ldg(reinterpret_cast<const float4*>(bias)), bq1 = __ldg(reinterpret_cast<const float4*>(bias) + 1);
-                        const float bb[8] = {bq0.x, bq0.y, bq0.z, bq0.w, bq1.x, bq1.y, bq1.z, bq1.w};
-                        float c[8];
+                        const float* bias = (op.layer == 1 ? b1 : (op.layer == 2 ? net.b2 : b3)) + f16;
+                        float bb[16];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) act_pair(net.act, net.w0, v[e] + bb[e], v[e], c[e]);
-                        reinterpret_cast<float4*>(cs)[0] = make_float4(c[0], c[1], c[2], c[3]);
-                        reinterpret_cast<float4*>(cs)[TC_TM] = make_float4(c[4], c[5], c[6], c[7]);
+                        for (int q = 0; q < 4; ++q) {          // issue the bias loads before waiting on TMEM
+                            const float4 bq = __ldg(reinterpret_cast<const float4*>(bias) + q);
+                            bb[q * 4] = bq.x; bb[q * 4 + 1] = bq.y; bb[q * 4 + 2] = bq.z; bb[q * 4 + 3] = bq.w;
+                        }
+                        tc_ld16(lane_addr + op.src_col + ch * 16, v);
+                        float* cs = scr + (op.layer == 1 ? P.sc_off_c1 : (op.layer == 2 ? P.sc_off_c2 : P.sc_off_c3)) + ((size_t)(f16 >> 2) * TC_TM + row) * 4;
+                        float c[16];
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) act_pair(net.act, net.w0, v[e] + bb[e], v[e], c[e]);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) reinterpret_cast<float4*>(cs)[q * TC_TM] = make_float4(c[q * 4], c[q * 4 + 1], c[q * 4 + 2], c[q * 4 + 3]);
                     } else if (op.prod == TC_PROD_MUL) {
-                        const float* cs = scr + (op.layer == 1 ? P.sc_off_c1 : (op.layer == 2 ? P.sc_off_c2 : P.sc_off_c3)) + ((size_t)(f8 >> 2) * TC_TM + row) * 4;
-                        const float4 c0 = reinterpret_cast<const float4*>(cs)[0], c1 = reinterpret_cast<const float4*>(cs)[TC_TM];
-                        v[0] *= c0.x; v[1] *= c0.y; v[2] *= c0.z; v[3] *= c0.w; v[4] *= c1.x; v[5] *= c1.y; v[6] *= c1.z; v[7] *= c1.w;
-                    } else {   // TC_PROD_G4: output layer + seed of the reverse sweep
+                        const float* cs = scr + (op.layer == 1 ? P.sc_off_c1 : (op.layer == 2 ? P.sc_off_c2 : P.sc_off_c3)) + ((size_t)(f16 >> 2) * TC_TM + row) * 4;
+                        float4 c[4];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float w5 = __ldg(net.W5 + f8 + i);
+                        for (int q = 0; q < 4; ++q) c[q] = reinterpret_cast<const float4*>(cs)[q * TC_TM];
+                        tc_ld16(lane_addr + op.src_col + ch * 16, v);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) { v[q * 4] *= c[q].x; v[q * 4 + 1] *= c[q].y; v[q * 4 + 2] *= c[q].z; v[q * 4 + 3] *= c[q].w; }
+                    } else {   // TC_PROD_G4: output layer + seed of the reverse sweep
+                        tc_ld16(lane_addr + op.src_col + ch * 16, v);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float w5 = __ldg(net.W5 + f16 + i);
                             float h, c;
-                            act_pair(net.act, net.w0, v[i] + __ldg(net.b4 + f8 + i), h, c);
+                            act_pair(net.act, net.w0, v[i] + __ldg(net.b4 + f16 + i), h, c);
                             d_acc = fmaf(w5, h, d_acc);
                             v[i] = w5 * c;
                         }
@@ -352,28 +379,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
                     tc_fence_before();
                 }
                 if (tr) P.trace[oi * 8 + 1] = clock64();
-                mbar_wait_backoff(sfree[s], ((chunk >> 1) & 1) ^ 1);
+                mbar_wait_backoff(sfree[g], ((chunk >> 1) & 1) ^ 1);
                 if (tr) P.trace[oi * 8 + 2] = clock64();
-                store_a8(ast[s], row, cg, v);
+                store_a16(ast[g], row, ch, v);
                 fence_async_smem();
-                mbar_arrive(afull[s]);
+                mbar_arrive(afull[g]);
                 if (tr) P.trace[oi * 8 + 3] = clock64();
             }
-            // ---- final: g_e = D_ge1 (+ parked skip part) ; chain rule through the embedding ----
-            mbar_wait_backoff(dfull, dphase); dphase ^= 1; tc_fence_after();
+            // ---- final: g_e = D_ge1 (+ parked skip part) ; chain rule through the embedding.  Group g takes the 32-feature
+            // blocks with ((f0 / 32) & 1) == g, so the four (group, half) combinations cover a row exactly once. ----
+            mbar_wait_backoff(dfull0 + 8 * (P.n_acc - 1), dpar); tc_fence_after();
             float gx = 0.f, gy = 0.f, gz = 0.f;
-            for (int f0 = 0; f0 < net.Ep; f0 += 32) {
-                float v[8];
-                tc_ld8(lane_addr + 128 + f0, v);
-                const int f8 = f0 + cg * 8;
+            for (int f0 = 32 * g; f0 < net.Ep; f0 += 64) {
+                float v[16];
+                tc_ld16(lane_addr + 128 + f0 + ch * 16, v);
+                const int f16 = f0 + ch * 16;
                 if (net.res_state) {
-                    const float* gs = scr + P.sc_off_ge3 + ((size_t)(f8 >> 2) * TC_TM + row) * 4;
-                    const float4 c0 = reinterpret_cast<const float4*>(gs)[0], c1 = reinterpret_cast<const float4*>(gs)[TC_TM];
-                    v[0] += c0.x; v[1] += c0.y; v[2] += c0.z; v[3] += c0.w; v[4] += c1.x; v[5] += c1.y; v[6] += c1.z; v[7] += c1.w;
+                    const float* gs = scr + P.sc_off_ge3 + ((size_t)(f16 >> 2) * TC_TM + row) * 4;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 c = reinterpret_cast<const float4*>(gs)[q * TC_TM];
+                        v[q * 4] += c.x; v[q * 4 + 1] += c.y; v[q * 4 + 2] += c.z; v[q * 4 + 3] += c.w;
+                    }
                 }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int j = f8 + i;
+                for (int i = 0; i < 16; ++i) {
+                    const int j = f16 + i;
                     const float4 t = etab[j];
                     const float arg = fmaf(sz, t.z, fmaf(sy, t.y, sx * t.x)) + t.w;
                     float sn, cs;
@@ -386,10 +417,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
                 }
             }
             tc_fence_before();
-            // combine the four column groups of each row
-            reinterpret_cast<float4*>(part)[cg * TC_TM + row] = make_float4(gx, gy, gz, d_acc);
+            // combine the four (group, half) partials of each row
+            reinterpret_cast<float4*>(part)[(g * 2 + ch) * TC_TM + row] = make_float4(gx, gy, gz, d_acc);
             asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD_THREADS) : "memory");
-            if (cg == 0 && gi < P.n) {
+            if (g == 0 && ch == 0 && gi < P.n) {
                 const float4 p0 = reinterpret_cast<const float4*>(part)[row], p1 = reinterpret_cast<const float4*>(part)[TC_TM + row];
                 const float4 p2 = reinterpret_cast<const float4*>(part)[2 * TC_TM + row], p3 = reinterpret_cast<const float4*>(part)[3 * TC_TM + row];
                 if (P.sdf_out) P.sdf_out[gi] = ((p0.w + p1.w) + (p2.w + p3.w)) + net.b5;
@@ -449,7 +480,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
                     }
                 }
                 tc_commit(sfree[s]);
-                if (op.last) tc_commit(dfull);
+                if (op.d_commit >= 0) tc_commit(dfull0 + 8 * op.d_commit);
             }
         }
     }
