@@ -86,6 +86,10 @@ typedef struct {
     double lh[3], uh[3];     /* [hfov, vfov, sdf] bounds                                    */
     double zl[3], Zl[3];     /* slack L1 / L2 weights in h order (ocp.py:85-92)             */
     double dt[SDFNMPC_MAX_N];/* stage lengths (ocp.py:21-27)                                */
+    int32_t model;           /* mpc.model (gen_model.py:15-20): 0 att, 1 att_tau, 2 acc; yrefN/WN are [B][4] (7 for acc) */
+    int32_t reserved;
+    double ax, ay, az;       /* robot.limits.ax/ay/az (model acc)                           */
+    double tau_roll, tau_pitch; /* attitude lag of att_tau (0 -> 0.12 s, quad_rollpitchyawrate_tau.py:19-20) */
 } sdfnmpc_solver_desc;
 
 int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver_desc* desc, sdfnmpc_sdf_t sdf);
@@ -121,6 +125,8 @@ int sdfnmpc_solver_timing_end(sdfnmpc_solver_t h, float* ms3, int32_t* steps);
 int sdfnmpc_plant_step(sdfnmpc_solver_t h, int32_t B, double* x_dev, const double* u_dev, double dt, void* stream);
 /* u_to_TRPYr + clip (controller.py:106-108): cmd [B][4]. */
 int sdfnmpc_cmd_trpyr(sdfnmpc_solver_t h, int32_t B, const double* u_dev, double* cmd_dev, void* stream);
+/* u_to_acc + clip (controller.py:101-103): cmd [B][4] = [W_R_B^T W_a, wz] from x0 [B][10] and u [B][4]; all models. */
+int sdfnmpc_cmd_acc(sdfnmpc_solver_t h, int32_t B, const double* x0_dev, const double* u_dev, double* cmd_dev, void* stream);
 
 /* ------------------------------------------------------------------ depth encoder ------- */
 typedef struct sdfnmpc_encoder* sdfnmpc_encoder_t;

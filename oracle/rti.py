@@ -23,13 +23,17 @@ and solved by ``oracle.qp.solve_dense``.
 import numpy as np
 
 from . import model_att as M
+from . import models as MODELS
 from . import qp as QP
 from . import sdf as SDF
 
 
-def default_cfg():
+def default_cfg(model='att'):
+    """`model` in {'att', 'att_tau', 'acc'} (gen_model.py:15-17); bounds and hover input come from the model."""
     c = dict(M.DEFAULT)
-    c.update(N=20, T=1.5, lm=10.0, lbu=np.array([0.0, -1, -1, -1]), ubu=np.array([1.0, 1, 1, 1]),
+    mdl = MODELS.get(model)
+    c.update(model=model, ax=4.0, ay=4.0, az=3.0, tau_roll=0.12, tau_pitch=0.12)
+    c.update(N=20, T=1.5, lm=10.0, lbu=mdl.lbu.copy(), ubu=mdl.ubu.copy(),
              slack_df=(200.0, 50.0), slack_fov=(20.0, 0.0), size_xy=0.22, bound_margin=0.15,
              h_at_node0=False, qp_tol=1e-8, qp_iter_max=100)
     c['dt'] = np.full(c['N'], c['T'] / c['N'])
@@ -52,8 +56,7 @@ def init_traj(x0, cfg):
     """ocp.py:144-149: x_k = x0, u_k = u_hover."""
     B, N = x0.shape[0], cfg['N']
     xb = np.repeat(x0[:, None, :], N + 1, 1).copy()
-    ub = np.zeros((B, N, 4))
-    ub[:, :, 0] = cfg['g'] / cfg['gamma']
+    ub = np.broadcast_to(MODELS.get(cfg.get('model', 'att')).u_hover(cfg), (B, N, 4)).copy()
     return xb, ub
 
 
@@ -74,18 +77,20 @@ def linearize(net, xb, ub, prob, cfg):
     """All stage quantities of the OCP-QP at (xb, ub)."""
     B, N = xb.shape[0], cfg['N']
     dt = cfg['dt']
+    mdl = MODELS.get(cfg.get('model', 'att'))
+    nyN = mdl.nyN
     A = np.zeros((B, N, 10, 10)); Bm = np.zeros((B, N, 10, 4)); b = np.zeros((B, N, 10))
     H = np.zeros((B, N, 14, 14)); g = np.zeros((B, N, 14))
     C = np.zeros((B, N + 1, 3, 10)); hbar = np.zeros((B, N + 1, 3))
     for k in range(N):
-        xn, A[:, k], Bm[:, k] = M.rk4_sens(xb[:, k], ub[:, k], dt[k], cfg)
+        xn, A[:, k], Bm[:, k] = mdl.rk4_sens(xb[:, k], ub[:, k], dt[k], cfg)
         b[:, k] = xn - xb[:, k + 1]
-        y, J = M.y_fun(xb[:, k], ub[:, k], prob['qd'][:, k], cfg)
+        y, J = mdl.y_fun(xb[:, k], ub[:, k], prob['qd'][:, k], cfg)
         Wk = prob['W'][:, k]
         H[:, k] = dt[k] * (np.einsum('byi,by,byj->bij', J, Wk, J) + cfg['lm'] * np.eye(14)[None])
         g[:, k] = dt[k] * np.einsum('byi,by->bi', J, Wk * (y - prob['yref'][:, k]))
-    yN, JN = M.y_fun(xb[:, N], np.zeros((B, 4)), prob['qd'][:, N], cfg)
-    yN, JN = yN[:, :4], JN[:, :4, 4:]
+    yN, JN = mdl.y_fun(xb[:, N], np.zeros((B, 4)), prob['qd'][:, N], cfg)
+    yN, JN = yN[:, :nyN], JN[:, :nyN, 4:]
     HN = np.einsum('byi,by,byj->bij', JN, prob['WN'], JN) + cfg['lm'] * np.eye(10)[None]
     gN = np.einsum('byi,by->bi', JN, prob['WN'] * (yN - prob['yrefN']))
     k0 = 0 if cfg['h_at_node0'] else 1
@@ -178,7 +183,7 @@ def closed_loop(net, prob, cfg, steps, plant_dt=None, move_ref=True):
         p['x0'] = x
         xb, ub, out = rti_step(net, xb, ub, p, cfg)
         hist.append(dict(x=x.copy(), u0=out['u0'].copy(), status=out['status'].copy()))
-        x = M.rk4(x, out['u0'], plant_dt, cfg)
+        x = MODELS.get(cfg.get('model', 'att')).rk4(x, out['u0'], plant_dt, cfg)
     return x, xb, ub, hist
 
 

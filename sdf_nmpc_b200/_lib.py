@@ -26,7 +26,9 @@ class SolverDesc(C.Structure):
                 ('g', C.c_double), ('gamma', C.c_double), ('roll', C.c_double), ('pitch', C.c_double),
                 ('wz', C.c_double), ('mass', C.c_double), ('cam_off', C.c_double * 3),
                 ('lbu', C.c_double * 4), ('ubu', C.c_double * 4), ('lh', C.c_double * 3), ('uh', C.c_double * 3),
-                ('zl', C.c_double * 3), ('Zl', C.c_double * 3), ('dt', C.c_double * MAX_N)]
+                ('zl', C.c_double * 3), ('Zl', C.c_double * 3), ('dt', C.c_double * MAX_N),
+                ('model', C.c_int32), ('reserved', C.c_int32), ('ax', C.c_double), ('ay', C.c_double), ('az', C.c_double),
+                ('tau_roll', C.c_double), ('tau_pitch', C.c_double)]
 
 
 class EncoderDesc(C.Structure):
@@ -52,7 +54,7 @@ CASADI_COMPANIONS = ('', '_alloc_mem', '_init_mem', '_free_mem', '_checkout', '_
 EXPORTS = (['sdfnmpc_version', 'sdfnmpc_launch_count', 'sdfnmpc_sdf_create', 'sdfnmpc_sdf_destroy',
             'sdfnmpc_sdf_set_latents', 'sdfnmpc_sdf_eval', 'sdfnmpc_sdf_eval_host', 'sdfnmpc_solver_create',
             'sdfnmpc_solver_destroy', 'sdfnmpc_solver_init_traj', 'sdfnmpc_solver_shift', 'sdfnmpc_solver_rti_step',
-            'sdfnmpc_solver_state', 'sdfnmpc_solver_diag', 'sdfnmpc_solver_qp_residual', 'sdfnmpc_solver_timing_begin', 'sdfnmpc_solver_timing_end', 'sdfnmpc_plant_step', 'sdfnmpc_cmd_trpyr',
+            'sdfnmpc_solver_state', 'sdfnmpc_solver_diag', 'sdfnmpc_solver_qp_residual', 'sdfnmpc_solver_timing_begin', 'sdfnmpc_solver_timing_end', 'sdfnmpc_plant_step', 'sdfnmpc_cmd_trpyr', 'sdfnmpc_cmd_acc',
             'sdfnmpc_encoder_create', 'sdfnmpc_encoder_destroy', 'sdfnmpc_encoder_encode',
             'sdfnmpc_encoder_encode_host', 'sdfnmpc_l4c_bind', 'sdfnmpc_l4c_load_blob']
            + [f + s for f in ('sdf_l4c', 'jac_sdf_l4c') for s in CASADI_COMPANIONS])
@@ -97,6 +99,7 @@ def load():
     lib.sdfnmpc_solver_timing_end.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int32)]
     lib.sdfnmpc_plant_step.argtypes = [vp, i32, dp, dp, C.c_double, vp]
     lib.sdfnmpc_cmd_trpyr.argtypes = [vp, i32, dp, dp, vp]
+    lib.sdfnmpc_cmd_acc.argtypes = [vp, i32, dp, dp, dp, vp]
     lib.sdfnmpc_encoder_create.argtypes = [C.POINTER(vp), C.POINTER(EncoderDesc), C.POINTER(EncoderWeights)]
     lib.sdfnmpc_encoder_destroy.argtypes = [vp]
     lib.sdfnmpc_encoder_encode.argtypes = [vp, fp, i32, fp, vp]

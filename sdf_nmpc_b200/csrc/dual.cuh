@@ -46,7 +46,10 @@ SDF_HD Dual datan2(Dual y, Dual x) {
     return Dual(atan2(y.v, x.v), (x.v * y.d - y.v * x.d) / r2);
 }
 
+SDF_HD Dual dasin(Dual a) { return Dual(asin(a.v), a.d / sqrt(1.0 - a.v * a.v)); }
+
 // scalar overloads so that the model templates also instantiate on plain double
+SDF_HD double dasin(double a) { return asin(a); }
 SDF_HD double dsqrt(double a) { return sqrt(a); }
 SDF_HD double dsin(double a) { return sin(a); }
 SDF_HD double dcos(double a) { return cos(a); }

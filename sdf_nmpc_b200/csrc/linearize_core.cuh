@@ -19,6 +19,7 @@ struct LinIn {           // device pointers, whole batch
     const double* pose;  // [B][12]
     const double* flag;  // [B]
     const double* dt;    // [N]
+    int nyN;             // terminal outputs: 4 (att, att_tau) or 7 (acc)
 };
 
 struct LinOut {
@@ -31,6 +32,7 @@ struct LinOut {
     float* qpts;   // [B][N+1][3]      SDF query points Co_p_B (float32, as L4CasADi casts)
 };
 
+template <int MODEL>
 SDF_HD void linearize_dir(const ModelConst& mc, int N, const LinIn& in, const LinOut& out, int b, int k, int dir) {
     constexpr int NX = ATT_NX, NU = ATT_NU, NW = ATT_NW, NY = ATT_NY, NH = ATT_NH;
     const double* x = in.xbar + ((size_t)b * (N + 1) + k) * NX;
@@ -45,7 +47,7 @@ SDF_HD void linearize_dir(const ModelConst& mc, int N, const LinIn& in, const Li
     const size_t node = (size_t)b * (N + 1) + k;
     if (k < N) {
         Dual xn[NX];
-        rk4_step(mc, xd, ud, in.dt[k], xn);
+        rk4_step<MODEL>(mc, xd, ud, in.dt[k], xn);
         double* AB = out.AB + ((size_t)b * N + k) * NX * NW;
         for (int i = 0; i < NX; ++i) AB[i * NW + dir] = xn[i].d;
         if (dir == 0) {
@@ -56,7 +58,7 @@ SDF_HD void linearize_dir(const ModelConst& mc, int N, const LinIn& in, const Li
     }
     {
         Dual y[NY];
-        y_att(mc, xd, ud, in.qd + node * 4, y);
+        y_model<MODEL>(mc, xd, ud, in.qd + node * 4, y);
         double* J = out.J + node * NY * NW;
         for (int r = 0; r < NY; ++r) J[r * NW + dir] = y[r].d;
         if (dir == 0) {
@@ -65,8 +67,8 @@ SDF_HD void linearize_dir(const ModelConst& mc, int N, const LinIn& in, const Li
                 const double* ref = in.yref + ((size_t)b * N + k) * NY;
                 for (int r = 0; r < NY; ++r) yr[r] = y[r].v - ref[r];
             } else {
-                const double* ref = in.yrefN + (size_t)b * ATT_NYN;
-                for (int r = 0; r < NY; ++r) yr[r] = r < ATT_NYN ? y[r].v - ref[r] : 0.0;
+                const double* ref = in.yrefN + (size_t)b * in.nyN;
+                for (int r = 0; r < NY; ++r) yr[r] = r < in.nyN ? y[r].v - ref[r] : 0.0;
             }
         }
     }

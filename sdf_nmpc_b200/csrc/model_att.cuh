@@ -20,9 +20,13 @@ constexpr int ATT_NY = 11;
 constexpr int ATT_NYN = 4;
 constexpr int ATT_NH = 3;    // hfov, vfov, sdf  (gen_model.py:42,68)
 
+enum QuadModel { MODEL_ATT = 0, MODEL_ATT_TAU = 1, MODEL_ACC = 2 };   // mpc.model: att / att_tau / acc (gen_model.py:15-20)
+
 struct ModelConst {
     double g, gamma, roll, pitch, wz, mass;
     double cam_off[3];    // B_R_C^T B_p_C + (fov_const_offset, 0, 0)
+    double ax, ay, az;    // acceleration limits (model 'acc', default.yaml:101-103)
+    double tau_roll, tau_pitch;   // first-order attitude lag (model 'att_tau', quad_rollpitchyawrate_tau.py:19-20)
 };
 
 template <class T>
@@ -49,16 +53,66 @@ SDF_HD void f_att(const ModelConst& c, const T* x, const T* u, T* dx) {
     dx[9] = gam * cr * cp - c.g;
 }
 
+// Model 'att_tau' (sdf_nmpc/model/quad_rollpitchyawrate_tau.py:22-42): full-quaternion attitude, roll/pitch follow
+// their set-points with a first-order lag through the Euler-rate map of utils/math.py:209-226 (restated literally,
+// including its second row [0, cos(roll), -sin(pitch)]).
 template <class T>
+SDF_HD void f_att_tau(const ModelConst& c, const T* x, const T* u, T* dx) {
+    T q0 = x[3], q1 = x[4], q2 = x[5], q3 = x[6];
+    T inv_n = 1.0 / dsqrt(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+    q0 = q0 * inv_n; q1 = q1 * inv_n; q2 = q2 * inv_n; q3 = q3 * inv_n;
+    T roll = datan2(2.0 * (q0 * q1 + q2 * q3), 1.0 - 2.0 * (q1 * q1 + q2 * q2));     // quat2euler, utils/math.py:57-70
+    T pitch = dasin(2.0 * (q0 * q2 - q3 * q1));
+    T gam = c.gamma * u[0];
+    T wz = c.wz * u[3];
+    T dot_roll = (c.roll * u[1] - roll) / c.tau_roll;
+    T dot_pitch = (c.pitch * u[2] - pitch) / c.tau_pitch;
+    T sr = dsin(roll), cr = dcos(roll), sp = dsin(pitch), cp = dcos(pitch);
+    T w0 = dot_roll + (sp * sr / cp) * dot_pitch;
+    T w1 = cr * dot_pitch;
+    dx[0] = x[7]; dx[1] = x[8]; dx[2] = x[9];
+    dx[3] = 0.5 * (-(q1 * w0) - q2 * w1 - q3 * wz);
+    dx[4] = 0.5 * (q0 * w0 + q2 * wz - q3 * w1);
+    dx[5] = 0.5 * (q0 * w1 - q1 * wz + q3 * w0);
+    dx[6] = 0.5 * (q0 * wz + q1 * w1 - q2 * w0);
+    dx[7] = gam * (2.0 * (q1 * q3 + q0 * q2));                                       // third column of quat2rot
+    dx[8] = gam * (2.0 * (q2 * q3 - q0 * q1));
+    dx[9] = gam * (q0 * q0 - q1 * q1 - q2 * q2 + q3 * q3) - c.g;
+}
+
+// Model 'acc' (sdf_nmpc/model/quad_acc.py:20-33): world-frame acceleration inputs and yaw rate.
+template <class T>
+SDF_HD void f_acc(const ModelConst& c, const T* x, const T* u, T* dx) {
+    T q0 = x[3], q1 = x[4], q2 = x[5], q3 = x[6];
+    T inv_n = 1.0 / dsqrt(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+    T hw = 0.5 * (c.wz * u[3]);
+    dx[0] = x[7]; dx[1] = x[8]; dx[2] = x[9];
+    dx[3] = -(hw * (q3 * inv_n));
+    dx[4] = hw * (q2 * inv_n);
+    dx[5] = -(hw * (q1 * inv_n));
+    dx[6] = hw * (q0 * inv_n);
+    dx[7] = c.ax * u[0];
+    dx[8] = c.ay * u[1];
+    dx[9] = c.az * u[2];
+}
+
+template <int MODEL, class T>
+SDF_HD void f_model(const ModelConst& c, const T* x, const T* u, T* dx) {
+    if (MODEL == MODEL_ATT) f_att(c, x, u, dx);
+    else if (MODEL == MODEL_ATT_TAU) f_att_tau(c, x, u, dx);
+    else f_acc(c, x, u, dx);
+}
+
+template <int MODEL, class T>
 SDF_HD void rk4_step(const ModelConst& c, const T* x, const T* u, double dt, T* xn) {
     T k1[ATT_NX], k2[ATT_NX], k3[ATT_NX], k4[ATT_NX], xs[ATT_NX];
-    f_att(c, x, u, k1);
+    f_model<MODEL>(c, x, u, k1);
     for (int i = 0; i < ATT_NX; ++i) xs[i] = x[i] + (0.5 * dt) * k1[i];
-    f_att(c, xs, u, k2);
+    f_model<MODEL>(c, xs, u, k2);
     for (int i = 0; i < ATT_NX; ++i) xs[i] = x[i] + (0.5 * dt) * k2[i];
-    f_att(c, xs, u, k3);
+    f_model<MODEL>(c, xs, u, k3);
     for (int i = 0; i < ATT_NX; ++i) xs[i] = x[i] + dt * k3[i];
-    f_att(c, xs, u, k4);
+    f_model<MODEL>(c, xs, u, k4);
     for (int i = 0; i < ATT_NX; ++i) xn[i] = x[i] + (dt / 6.0) * (k1[i] + 2.0 * k2[i] + 2.0 * k3[i] + k4[i]);
 }
 
@@ -80,6 +134,30 @@ SDF_HD void y_att(const ModelConst& c, const T* x, const T* u, const double* qd,
     y[8] = pt;
     y[9] = c.wz * u[3];
     y[10] = (c.gamma * u[0]) * dcos(r) * dcos(pt) - c.g;
+}
+
+// att_tau: y = [p, q_e[3], v, roll_des, pitch_des, wz, W_a[2]] with the full-quaternion W_a (quad_rollpitchyawrate_tau.py:49-52)
+// acc:     y = [p, q_e[3], v, W_a(3), wz], yN = first 7                               (quad_acc.py:40-45)
+template <int MODEL, class T>
+SDF_HD void y_model(const ModelConst& c, const T* x, const T* u, const double* qd, T* y) {
+    if (MODEL == MODEL_ATT) { y_att(c, x, u, qd, y); return; }
+    T q0 = x[3], q1 = x[4], q2 = x[5], q3 = x[6];
+    T inv_n = 1.0 / dsqrt(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+    T h0 = q0 * inv_n, h1 = q1 * inv_n, h2 = q2 * inv_n, h3 = q3 * inv_n;
+    y[0] = x[0]; y[1] = x[1]; y[2] = x[2];
+    y[3] = qd[2] * h1 + qd[3] * h0 - qd[0] * h3 - qd[1] * h2;
+    y[4] = x[7]; y[5] = x[8]; y[6] = x[9];
+    if (MODEL == MODEL_ATT_TAU) {
+        y[7] = c.roll * u[1];
+        y[8] = c.pitch * u[2];
+        y[9] = c.wz * u[3];
+        y[10] = (c.gamma * u[0]) * (h0 * h0 - h1 * h1 - h2 * h2 + h3 * h3) - c.g;
+    } else {
+        y[7] = c.ax * u[0];
+        y[8] = c.ay * u[1];
+        y[9] = c.az * u[2];
+        y[10] = c.wz * u[3];
+    }
 }
 
 // Co_p_B = W_R_Co^T (p - W_p_Co); pose = [W_p_Co(3), W_R_Co row-major(9)]  (controller.py:50-54)
@@ -108,6 +186,35 @@ SDF_HD void u_to_TRPYr(const ModelConst& c, const double* u, double* cmd) {
     cmd[1] = c.roll * u[1];
     cmd[2] = c.pitch * u[2];
     cmd[3] = c.wz * u[3];
+}
+
+// [W_R_B^T W_a, wz]: u_to_acc of quad_rollpitchyawrate.py:45, quad_rollpitchyawrate_tau.py:46, quad_acc.py:36.
+// For the thrust models W_a = W_R_B (0,0,gamma) - g e_z, hence W_R_B^T W_a = (0,0,gamma) - g * (third row of W_R_B).
+template <int MODEL>
+SDF_HD void u_to_acc(const ModelConst& c, const double* x, const double* u, double* cmd) {
+    cmd[3] = c.wz * u[3];
+    if (MODEL == MODEL_ATT) {
+        double r = c.roll * u[1], pt = c.pitch * u[2];
+        cmd[0] = c.g * sin(pt);                       // third row of Rz(psi) V_R_B(roll, pitch) is (-sp, sr cp, cr cp)
+        cmd[1] = -c.g * sin(r) * cos(pt);
+        cmd[2] = c.gamma * u[0] - c.g * cos(r) * cos(pt);
+        return;
+    }
+    double inv_n = 1.0 / sqrt(x[3] * x[3] + x[4] * x[4] + x[5] * x[5] + x[6] * x[6]);
+    double q0 = x[3] * inv_n, q1 = x[4] * inv_n, q2 = x[5] * inv_n, q3 = x[6] * inv_n;
+    double R[9] = {q0 * q0 + q1 * q1 - q2 * q2 - q3 * q3, 2 * (q1 * q2 - q0 * q3), 2 * (q1 * q3 + q0 * q2),      // utils/math.py:7-23
+                   2 * (q1 * q2 + q0 * q3), q0 * q0 - q1 * q1 + q2 * q2 - q3 * q3, 2 * (q2 * q3 - q0 * q1),
+                   2 * (q1 * q3 - q0 * q2), 2 * (q2 * q3 + q0 * q1), q0 * q0 - q1 * q1 - q2 * q2 + q3 * q3};
+    if (MODEL == MODEL_ATT_TAU) {
+        cmd[0] = -c.g * R[6];
+        cmd[1] = -c.g * R[7];
+        cmd[2] = c.gamma * u[0] - c.g * R[8];
+    } else {
+        double a0 = c.ax * u[0], a1 = c.ay * u[1], a2 = c.az * u[2];
+        cmd[0] = R[0] * a0 + R[3] * a1 + R[6] * a2;
+        cmd[1] = R[1] * a0 + R[4] * a1 + R[7] * a2;
+        cmd[2] = R[2] * a0 + R[5] * a1 + R[8] * a2;
+    }
 }
 
 }  // namespace sdfnmpc

@@ -22,8 +22,8 @@ constexpr int QP_WARPS = 4;     // instances per CTA
 
 struct SolverConst {
     ModelConst mc;
-    int N, k0, qp_iter_max;
-    double lm, tol, tol_res;
+    int N, k0, qp_iter_max, model, nyN;
+    double lm, tol, tol_res, u_hover;
     double lbu[NU], ubu[NU], lh[NH], uh[NH], zs[NH], Zs[NH];
     double cmd_min[4], cmd_max[4];
 };
@@ -46,6 +46,7 @@ struct sdfnmpc_solver {
     int ev_steps = 0, ev_cap = 0;
 };
 
+template <int MODEL>
 __global__ void nmpc_linearize_kernel(ModelConst mc, int N, int B, LinIn in, LinOut out) {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)B * (N + 1) * NW;
@@ -54,7 +55,7 @@ __global__ void nmpc_linearize_kernel(ModelConst mc, int N, int B, LinIn in, Lin
     const long long node = gid / NW;
     const int k = (int)(node % (N + 1));
     const int b = (int)(node / (N + 1));
-    linearize_dir(mc, N, in, out, b, k, dir);
+    linearize_dir<MODEL>(mc, N, in, out, b, k, dir);
 }
 
 struct QpBatch {
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32, QP_MIN_CTAS) nmpc_qp_kernel(Sol
     if (b >= B) return;
     const int N = scs.N;
     Prob P;
-    P.N = N; P.k0 = scs.k0; P.max_iter = scs.qp_iter_max; P.nyN = NYN;
+    P.N = N; P.k0 = scs.k0; P.max_iter = scs.qp_iter_max; P.nyN = scs.nyN;
     P.lm = scs.lm; P.tol = scs.tol; P.tol_res = scs.tol_res; P.max_df = q.max_df; P.flag = q.flag[b];
     P.AB = q.AB + (size_t)b * N * NX * NW;
     P.bdyn = q.bdyn + (size_t)b * N * NX;
@@ -87,7 +88,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32, QP_MIN_CTAS) nmpc_qp_kernel(Sol
     P.C = q.C + (size_t)b * (N + 1) * NH * NW;
     P.hval = q.hval + (size_t)b * (N + 1) * NH;
     P.W = q.W + (size_t)b * N * NY;
-    P.WN = q.WN + (size_t)b * NYN;
+    P.WN = q.WN + (size_t)b * scs.nyN;
     P.dt = q.dt;
     P.lbu = scs.lbu; P.ubu = scs.ubu; P.lh = scs.lh; P.uh = scs.uh; P.zs = scs.zs; P.Zs = scs.Zs;
     P.sdf_d = q.sdf_d + (size_t)b * (N + 1);
@@ -131,13 +132,14 @@ __global__ void nmpc_shift_kernel(int N, int B, int s, double* __restrict__ xbar
     }
 }
 
+template <int MODEL>
 __global__ void nmpc_plant_kernel(ModelConst mc, int B, double dt, double* __restrict__ x, const double* __restrict__ u) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     double xs[NX], us[NU], xn[NX];
     for (int i = 0; i < NX; ++i) xs[i] = x[(size_t)b * NX + i];
     for (int i = 0; i < NU; ++i) us[i] = u[(size_t)b * NU + i];
-    rk4_step<double>(mc, xs, us, dt, xn);
+    rk4_step<MODEL, double>(mc, xs, us, dt, xn);
     for (int i = 0; i < NX; ++i) x[(size_t)b * NX + i] = xn[i];
 }
 
@@ -147,6 +149,16 @@ __global__ void nmpc_cmd_kernel(SolverConst sc, int B, const double* __restrict_
     double c[4];
     u_to_TRPYr(sc.mc, u + (size_t)b * NU, c);
     for (int i = 0; i < 4; ++i) cmd[(size_t)b * 4 + i] = fmin(fmax(c[i], sc.cmd_min[i]), sc.cmd_max[i]);
+}
+
+template <int MODEL>
+__global__ void nmpc_cmd_acc_kernel(ModelConst mc, int B, const double* __restrict__ x, const double* __restrict__ u, double* __restrict__ cmd) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double c[4];
+    u_to_acc<MODEL>(mc, x + (size_t)b * NX, u + (size_t)b * NU, c);
+    const double lim[4] = {mc.ax, mc.ay, mc.az, mc.wz};                  // controller.py:19-20
+    for (int i = 0; i < 4; ++i) cmd[(size_t)b * 4 + i] = fmin(fmax(c[i], -lim[i]), lim[i]);
 }
 
 extern "C" int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver_desc* d, sdfnmpc_sdf_t sdf) {
@@ -160,6 +172,12 @@ extern "C" int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver
     SolverConst& sc = h->sc;
     sc.mc.g = d->g; sc.mc.gamma = d->gamma; sc.mc.roll = d->roll; sc.mc.pitch = d->pitch; sc.mc.wz = d->wz; sc.mc.mass = d->mass;
     for (int i = 0; i < 3; ++i) sc.mc.cam_off[i] = d->cam_off[i];
+    if (d->model < 0 || d->model > 2) { delete h; return SDFNMPC_E_INVALID; }
+    sc.model = d->model;
+    sc.nyN = d->model == MODEL_ACC ? 7 : 4;                                   // quad_acc.py:15 vs quad_rollpitchyawrate*.py:15
+    sc.u_hover = d->model == MODEL_ACC ? 0.0 : d->g / d->gamma;              // quad_acc.py:35, quad_rollpitchyawrate.py:44
+    sc.mc.ax = d->ax; sc.mc.ay = d->ay; sc.mc.az = d->az;
+    sc.mc.tau_roll = d->tau_roll > 0 ? d->tau_roll : 0.12; sc.mc.tau_pitch = d->tau_pitch > 0 ? d->tau_pitch : 0.12;
     sc.N = d->N; sc.k0 = d->h_at_node0 ? 0 : 1; sc.qp_iter_max = d->qp_iter_max;
     sc.lm = d->lm; sc.tol = d->qp_tol; sc.tol_res = d->qp_tol_res;
     for (int i = 0; i < NU; ++i) { sc.lbu[i] = d->lbu[i]; sc.ubu[i] = d->ubu[i]; }
@@ -213,7 +231,7 @@ extern "C" int sdfnmpc_solver_init_traj(sdfnmpc_solver_t h, const double* x0, in
     const int N = h->sc.N;
     const long long total = (long long)B * (N + 1) * NX;
     nmpc_init_traj_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        N, B, h->sc.mc.g / h->sc.mc.gamma, x0, h->xbar, h->ubar);
+        N, B, h->sc.u_hover, x0, h->xbar, h->ubar);
     count_launch();
     SDF_CUDA_CHECK(cudaGetLastError());
     return 0;
@@ -244,10 +262,13 @@ extern "C" int sdfnmpc_solver_rti_step(sdfnmpc_solver_t h, int32_t B, const doub
     const bool tm = h->ev_cap > 0 && h->ev_steps < h->ev_cap;
     cudaEvent_t* ev = tm ? &h->ev[(size_t)h->ev_steps * 4] : nullptr;
     if (tm) cudaEventRecord(ev[0], st);
-    LinIn in{h->xbar, h->ubar, yref, yrefN, qd, pose, flag, h->dt};
+    LinIn in{h->xbar, h->ubar, yref, yrefN, qd, pose, flag, h->dt, h->sc.nyN};
     LinOut lo{h->AB, h->bdyn, h->J, h->yres, h->C, h->hval, h->qpts};
     const long long total = (long long)B * (N + 1) * NW;
-    nmpc_linearize_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(h->sc.mc, N, B, in, lo);
+    const unsigned lin_grid = (unsigned)((total + 127) / 128);
+    if (h->sc.model == MODEL_ATT) nmpc_linearize_kernel<MODEL_ATT><<<lin_grid, 128, 0, st>>>(h->sc.mc, N, B, in, lo);
+    else if (h->sc.model == MODEL_ATT_TAU) nmpc_linearize_kernel<MODEL_ATT_TAU><<<lin_grid, 128, 0, st>>>(h->sc.mc, N, B, in, lo);
+    else nmpc_linearize_kernel<MODEL_ACC><<<lin_grid, 128, 0, st>>>(h->sc.mc, N, B, in, lo);
     count_launch();
     SDF_CUDA_CHECK(cudaGetLastError());
     if (tm) cudaEventRecord(ev[1], st);
@@ -320,14 +341,28 @@ extern "C" int sdfnmpc_solver_diag(sdfnmpc_solver_t h, double** hval, float** sd
 
 extern "C" int sdfnmpc_plant_step(sdfnmpc_solver_t h, int32_t B, double* x, const double* u, double dt, void* stream) {
     if (!h || !x || !u || B < 1) return SDFNMPC_E_INVALID;
-    nmpc_plant_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->sc.mc, B, dt, x, u);
+    if (h->sc.model == MODEL_ATT) nmpc_plant_kernel<MODEL_ATT><<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->sc.mc, B, dt, x, u);
+    else if (h->sc.model == MODEL_ATT_TAU) nmpc_plant_kernel<MODEL_ATT_TAU><<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->sc.mc, B, dt, x, u);
+    else nmpc_plant_kernel<MODEL_ACC><<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->sc.mc, B, dt, x, u);
+    count_launch();
+    SDF_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int sdfnmpc_cmd_acc(sdfnmpc_solver_t h, int32_t B, const double* x0, const double* u, double* cmd, void* stream) {
+    if (!h || !x0 || !u || !cmd || B < 1) return SDFNMPC_E_INVALID;
+    const unsigned grid = (B + 127) / 128;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h->sc.model == MODEL_ATT) nmpc_cmd_acc_kernel<MODEL_ATT><<<grid, 128, 0, st>>>(h->sc.mc, B, x0, u, cmd);
+    else if (h->sc.model == MODEL_ATT_TAU) nmpc_cmd_acc_kernel<MODEL_ATT_TAU><<<grid, 128, 0, st>>>(h->sc.mc, B, x0, u, cmd);
+    else nmpc_cmd_acc_kernel<MODEL_ACC><<<grid, 128, 0, st>>>(h->sc.mc, B, x0, u, cmd);
     count_launch();
     SDF_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
 
 extern "C" int sdfnmpc_cmd_trpyr(sdfnmpc_solver_t h, int32_t B, const double* u, double* cmd, void* stream) {
-    if (!h || !u || !cmd || B < 1) return SDFNMPC_E_INVALID;
+    if (!h || !u || !cmd || B < 1 || h->sc.model == MODEL_ACC) return SDFNMPC_E_INVALID;   // 'acc' has no u_to_TRPYr (quad_acc.py)
     nmpc_cmd_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->sc, B, u, cmd);
     count_launch();
     SDF_CUDA_CHECK(cudaGetLastError());

@@ -19,13 +19,16 @@ from . import _lib
 from .config import Config
 from .sdf import SdfEvaluator, _ptr, _stream
 
-NX, NU, NY, NYN, NH = 10, 4, 11, 4, 3
+NX, NU, NY, NH = 10, 4, 11, 3
+MODEL_ID = {'att': 0, 'att_tau': 1, 'acc': 2}      # mpc.model values reachable in gen_model.py:15-17 ('props': not built)
 
 
 class BatchedNmpc:
     def __init__(self, cfg, sdf_net, batch, device='cuda:0'):
-        if cfg.mpc.model != 'att':
-            raise NotImplementedError("only mpc.model == 'att' (the reference default) is built so far")
+        if cfg.mpc.model not in MODEL_ID:
+            raise NotImplementedError(f"mpc.model == '{cfg.mpc.model}' is not built (available: {sorted(MODEL_ID)})")
+        self.model = cfg.mpc.model
+        self.nyN = 7 if self.model == 'acc' else 4        # quad_acc.py:15 / quad_rollpitchyawrate*.py:15
         self.cfg = cfg
         self.B = int(batch)
         self.N = int(cfg.mpc.N)
@@ -44,7 +47,10 @@ class BatchedNmpc:
         d.lm, d.qp_tol, d.qp_tol_res = float(cfg.mpc.lm_reg), float(cfg.b200.qp_tol), float(cfg.b200.qp_tol_res)
         d.g, d.gamma, d.roll, d.pitch, d.wz, d.mass = self.g, lim.gamma, lim.roll, lim.pitch, lim.wz, cfg.robot.mass
         d.cam_off = (C.c_double * 3)(*cfg.cam_offset())
-        d.lbu = (C.c_double * 4)(0, -1, -1, -1)           # quad_rollpitchyawrate.py:58-59
+        d.lbu = (C.c_double * 4)(-1 if self.model == 'acc' else 0, -1, -1, -1)   # quad_rollpitchyawrate.py:58-59, quad_acc.py:50-51
+        d.model = MODEL_ID[self.model]
+        d.ax, d.ay, d.az = float(lim.ax), float(lim.ay), float(lim.az)
+        d.tau_roll = d.tau_pitch = 0.12                   # quad_rollpitchyawrate_tau.py:19-20 (constants in the reference)
         d.ubu = (C.c_double * 4)(1, 1, 1, 1)
         d.lh, d.uh = (C.c_double * 3)(*lh), (C.c_double * 3)(*uh)
         d.zl, d.Zl = (C.c_double * 3)(*zl), (C.c_double * 3)(*Zl)
@@ -53,6 +59,9 @@ class BatchedNmpc:
         self.handle = C.c_void_p()
         _lib.check(self.lib.sdfnmpc_solver_create(C.byref(self.handle), C.byref(d), self.sdf.handle), 'sdfnmpc_solver_create')
         # command clipping (controller.py:18-26)
+        self.cmd_acc_hover = np.array([0, 0, 0, 0])
+        self.cmd_acc_min = [-lim.ax, -lim.ay, -lim.az, -lim.wz]
+        self.cmd_acc_max = [lim.ax, lim.ay, lim.az, lim.wz]
         self.cmd_TRPYr_hover = np.array([cfg.robot.mass * self.g, 0, 0, 0])
         self.cmd_TRPYr_min = [0, -lim.roll, -lim.pitch, -lim.wz]
         self.cmd_TRPYr_max = [lim.gamma, lim.roll, lim.pitch, lim.wz]
@@ -85,9 +94,9 @@ class BatchedNmpc:
         self.qd = torch.zeros(B, N + 1, 4, **f64)
         self.latent = torch.zeros(B, max(self.L, 1), dtype=torch.float32, device=self.device)
         self.y = torch.zeros(B, N, NY, **f64)
-        self.yN = torch.zeros(B, NYN, **f64)
+        self.yN = torch.zeros(B, self.nyN, **f64)
         self.W = torch.zeros(B, N, NY, **f64)
-        self.WN = torch.zeros(B, NYN, **f64)
+        self.WN = torch.zeros(B, self.nyN, **f64)
         self.fail_count = torch.zeros(B, dtype=torch.int64, device=self.device)
         self._latent_dirty = True
         self.set_sdf_flag(False)
@@ -122,13 +131,18 @@ class BatchedNmpc:
     def set_ref_arrays(self, yref, W, yrefN, WN, qd):
         self.y[:] = self._t(yref, (self.B, self.N, NY))
         self.W[:] = self._t(W, (self.B, self.N, NY))
-        self.yN[:] = self._t(yrefN, (self.B, NYN))
-        self.WN[:] = self._t(WN, (self.B, NYN))
+        self.yN[:] = self._t(yrefN, (self.B, self.nyN))
+        self.WN[:] = self._t(WN, (self.B, self.nyN))
         self.qd[:] = self._t(qd, (self.B, self.N + 1, 4))
 
-    @staticmethod
-    def formate_ref(ref):
-        """quad_rollpitchyawrate.py:62-65."""
+    def formate_ref(self, ref):
+        """quad_rollpitchyawrate.py:62-65 / quad_rollpitchyawrate_tau.py:61-64 (same rows).  For 'acc' the rows are those
+        of quad_acc.py:54-58; that function reads an undefined name in the reference (it cannot run there), so the row
+        order it spells out is used with the weights of `ref` itself."""
+        if self.model == 'acc':
+            yr = np.concatenate([ref.p, [0], ref.v, [0, 0, 0], [ref.wz]])
+            W = np.concatenate([ref.Wp, ref.Wq[2:], ref.Wv, [ref.Wa, ref.Wa, ref.Wa], [ref.Ww[2]]])
+            return yr, W
         yr = np.concatenate([ref.p, [0], ref.v, [0, 0], [ref.wz], [0]])
         W = np.concatenate([ref.Wp, [ref.Wq[2]], ref.Wv, ref.Wq[:2], ref.Ww[2:], [ref.Wa]])
         return yr, W
@@ -142,8 +156,8 @@ class BatchedNmpc:
             self.y[sel, k] = self._t(y)
             self.W[sel, k] = self._t(W)
         else:
-            self.yN[sel] = self._t(y[:NYN])
-            self.WN[sel] = self._t(W[:NYN])
+            self.yN[sel] = self._t(y[:self.nyN])
+            self.WN[sel] = self._t(W[:self.nyN])
 
     # ------------------------------------------------------------------ control iteration ----------
     def shift(self, k=None):
@@ -189,19 +203,29 @@ class BatchedNmpc:
         _lib.check(self.lib.sdfnmpc_solver_state(self.handle, *[C.byref(p) for p in ptrs]), 'solver_state')
         return ptrs
 
-    def _view(self, ptr, shape, dtype):
+    def _view(self, ptr, shape, dtype, copy=True):
         # zero-copy torch view of library-owned device memory, then a stream-ordered copy
         class _Dev:
             pass
         d = _Dev()
         d.__cuda_array_interface__ = dict(shape=tuple(int(s) for s in shape), typestr='<f8' if dtype == torch.float64 else '<f4',
                                           data=(int(ptr.value), False), version=2)
-        return torch.as_tensor(d, device=self.device).clone()
+        t = torch.as_tensor(d, device=self.device)
+        return t.clone() if copy else t
 
     def get_matrices(self):
         """controller.py:84-92 -> (x [B,N+1,10], u [B,N,4]) device tensors (copies)."""
         xb, ub, _, _ = self._state_ptrs()
         return (self._view(xb, (self.B, self.N + 1, NX), torch.float64), self._view(ub, (self.B, self.N, NU), torch.float64))
+
+    def set_matrices(self, x, u):
+        """Overwrite the SQP iterate (x [B,N+1,10], u [B,N,4]) - the batched form of the per-node ``solver.set(k, 'x'|'u', .)``
+        calls of ``ocp.py:144-149``; used to warm-start from an external trajectory."""
+        xb, ub, _, _ = self._state_ptrs()
+        self._view(xb, (self.B, self.N + 1, NX), torch.float64, copy=False).copy_(self._t(x, (self.B, self.N + 1, NX)))
+        self._view(ub, (self.B, self.N, NU), torch.float64, copy=False).copy_(self._t(u, (self.B, self.N, NU)))
+        if self.x0 is None:
+            self.x0 = self._t(x, (self.B, self.N + 1, NX))[:, 0].contiguous()
 
     def get_multipliers(self):
         """QP multipliers of the last step: lam_hard [B,N,8] (lbu, ubu), lam_soft [B,N+1,6] (lh, uh)."""
@@ -221,6 +245,12 @@ class BatchedNmpc:
         """controller.py:106-108: [gamma*mass, roll, pitch, wz] clipped."""
         cmd = torch.empty(self.B, 4, dtype=torch.float64, device=self.device)
         _lib.check(self.lib.sdfnmpc_cmd_trpyr(self.handle, self.B, _ptr(self.u0), _ptr(cmd), _stream()), 'cmd_trpyr')
+        return cmd
+
+    def get_cmd_acc(self):
+        """controller.py:101-103: [W_R_B^T W_a, wz] clipped to the acceleration limits."""
+        cmd = torch.empty(self.B, 4, dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.sdfnmpc_cmd_acc(self.handle, self.B, _ptr(self.x0), _ptr(self.u0), _ptr(cmd), _stream()), 'cmd_acc')
         return cmd
 
     def get_openloop_traj(self):
@@ -326,6 +356,9 @@ class Nmpc:
 
     def get_cmd_TRPYr(self):
         return self._b.get_cmd_TRPYr()[0].cpu().numpy()
+
+    def get_cmd_acc(self):
+        return self._b.get_cmd_acc()[0].cpu().numpy()
 
     def get_openloop_traj(self):
         p, q = self._b.get_openloop_traj()

@@ -111,18 +111,26 @@ def yaw2quat(yaw):
     return np.stack([np.cos(0.5 * yaw), z, z, np.sin(0.5 * yaw)], -1)
 
 
-def nmpc_instances(B, N=20, dt=0.075, seed=1000, vref=3.0, weights=None, first=0):
+def _qmul(a, b):
+    return np.array([a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3], a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2],
+                     a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1], a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0]])
+
+
+def nmpc_instances(B, N=20, dt=0.075, seed=1000, vref=3.0, weights=None, first=0, model='att'):
     """Config 3/4: B randomised NMPC instances (per-instance seed ``seed + first + i``).
 
     Returns a dict of float64 arrays: x0 [B,10], yref [B,N,11], W [B,N,11], yrefN [B,4], WN [B,4],
     qd [B,N+1,4], W_p_Bo [B,3], W_R_Bo [B,3,3], latent [B,128] (float32).
     ``weights`` = dict(pos,vel,att,rates,acc); default = constraints-on set (default.yaml:43-48).
+    ``model``: 'att' (default), 'att_tau' (x0 additionally tilted by up to 0.2 rad in roll/pitch) or 'acc' (yrefN/WN
+    are [B,7] and the output rows follow quad_acc.py:40-58).
     """
     if weights is None:
         weights = dict(pos=[0, 0, 5], vel=[3, 3, 3], att=[50, 50, 10], rates=[0, 0, 3], acc=0.05)
     x0 = np.zeros((B, 10))
     yref = np.zeros((B, N, 11))
-    yrefN = np.zeros((B, 4))
+    nyN = 7 if model == 'acc' else 4
+    yrefN = np.zeros((B, nyN))
     qd = np.zeros((B, N + 1, 4))
     lat = np.zeros((B, 128), np.float32)
     Rbo = np.zeros((B, 3, 3))
@@ -139,6 +147,10 @@ def nmpc_instances(B, N=20, dt=0.075, seed=1000, vref=3.0, weights=None, first=0
         d /= np.linalg.norm(d)
         v_ref = vref * d
         x0[i, :3], x0[i, 3:7], x0[i, 7:] = p, yaw2quat(yaw), v
+        if model == 'att_tau':
+            r, pt = rng.uniform(-0.2, 0.2, 2)
+            qr = np.array([np.cos(r / 2), np.sin(r / 2), 0, 0]); qp = np.array([np.cos(pt / 2), 0, np.sin(pt / 2), 0])
+            x0[i, 3:7] = _qmul(_qmul(yaw2quat(yaw), qp), qr)
         k = np.arange(N + 1)[:, None]
         p_ref = p[None] + v_ref[None] * k * dt
         yaw_ref = np.arctan2(v_ref[1], v_ref[0])
@@ -146,12 +158,16 @@ def nmpc_instances(B, N=20, dt=0.075, seed=1000, vref=3.0, weights=None, first=0
         yref[i, :, 0:3] = p_ref[:N]
         yref[i, :, 4:7] = v_ref
         yrefN[i, 0:3] = p_ref[N]
+        if model == 'acc':
+            yrefN[i, 4:7] = v_ref
         c, s = np.cos(yaw), np.sin(yaw)
         Rbo[i] = np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]])
     w = weights
     Wrow = np.array(list(w['pos']) + [w['att'][2]] + list(w['vel']) + [w['att'][0], w['att'][1], w['rates'][2], w['acc']], float)
+    if model == 'acc':
+        Wrow = np.array(list(w['pos']) + [w['att'][2]] + list(w['vel']) + [w['acc']] * 3 + [w['rates'][2]], float)
     W = np.broadcast_to(Wrow, (B, N, 11)).copy()
-    WN = np.broadcast_to(Wrow[:4], (B, 4)).copy()
+    WN = np.broadcast_to(Wrow[:nyN], (B, nyN)).copy()
     return dict(x0=x0, yref=yref, W=W, yrefN=yrefN, WN=WN, qd=qd, W_p_Bo=x0[:, :3].copy(), W_R_Bo=Rbo, latent=lat)
 
 

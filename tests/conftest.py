@@ -43,10 +43,10 @@ def relmax(a, b):
     return float(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max() / np.abs(np.asarray(b, np.float64)).max())
 
 
-def make_problem(B, cfg, seed=1000, flag=1.0):
+def make_problem(B, cfg, seed=1000, flag=1.0, model='att'):
     """Oracle-side problem dict for B randomised instances."""
     from sdf_nmpc_b200 import synth
-    w = synth.nmpc_instances(B, N=cfg['N'], dt=cfg['dt'][0], seed=seed)
+    w = synth.nmpc_instances(B, N=cfg['N'], dt=cfg['dt'][0], seed=seed, model=model)
     prob = dict(x0=w['x0'], yref=w['yref'], W=w['W'], yrefN=w['yrefN'], WN=w['WN'], qd=w['qd'],
                 flag=np.full(B, float(flag)), latent=w['latent'])
     prob['W_p_Co'] = np.einsum('bij,j->bi', w['W_R_Bo'], cfg['B_p_C']) + w['W_p_Bo']

@@ -165,6 +165,54 @@ def model_att_case():
     print('model_att: f range', np.abs(F).max())
 
 
+def model_variants_case():
+    """f_expl, y of models 'att_tau' and 'acc' composed from the reference's numpy math helpers exactly as
+    model/quad_rollpitchyawrate_tau.py:22-52 and model/quad_acc.py:20-45 compose them (same X, U, QD as model_att.npz,
+    attitudes kept away from the pitch singularity of the Euler map)."""
+    from sdf_nmpc.utils import math as rm
+    G = np.load(os.path.join(HERE, 'model_att.npz'))
+    X, U, QD = G['X'].copy(), G['U'], G['QD']
+    rng = np.random.default_rng(11)
+    n = len(X)
+    eul = np.stack([rng.uniform(-0.6, 0.6, n), rng.uniform(-0.6, 0.6, n), rng.uniform(-np.pi, np.pi, n)], 1)
+    scale = np.where(np.arange(n) < n // 2, 1.0, rng.uniform(0.5, 2.0, n))     # half unit, half un-normalised
+    for i in range(n):
+        cy, sy, cp, sp, cr, sr = (f(a / 2) for a in eul[i, ::-1] for f in (np.cos, np.sin))
+        X[i, 3:7] = scale[i] * np.array([cr * cp * cy + sr * sp * sy, sr * cp * cy - cr * sp * sy,
+                                         cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy])
+    g, gam, rmax, pmax, wmax, ax, ay, az, tau = 9.81, 20.0, 0.7, 0.7, 3.0, 4.0, 4.0, 3.0, 0.12
+    Ft, Yt, Fa, Ya = [], [], [], []
+    cmd = dict(att=[], att_tau=[], acc=[])     # u_to_acc of each model: [W_R_B^T W_a, wz]
+    for i in range(n):
+        x, u = X[i], U[i]
+        p = x[:3]; q = x[3:7] / np.linalg.norm(x[3:7]); v = x[7:]
+        q_e = rm.hamilton_prod(QD[i], rm.invert(q))
+        # att_tau
+        eta = rm.quat2euler(q)
+        gamma, roll_des, pitch_des, wz = u[0] * gam, u[1] * rmax, u[2] * pmax, u[3] * wmax
+        W_R_B = rm.quat2rot(q)
+        W_a = W_R_B @ np.array([0, 0, gamma]) + np.array([0, 0, -g])
+        w = rm.deuler_avel_map(eta) @ np.array([(roll_des - eta[0]) / tau, (pitch_des - eta[1]) / tau, 0])
+        dq = rm.hamilton_prod(q, np.array([0, w[0], w[1], wz])) / 2
+        cmd['att_tau'].append(np.concatenate([W_R_B.T @ W_a, [wz]]))
+        Ft.append(np.concatenate([v, dq, W_a]))
+        Yt.append(np.concatenate([p, [q_e[3]], v, [roll_des, pitch_des, wz, W_a[2]]]))
+        # acc
+        W_a = np.array([u[0] * ax, u[1] * ay, u[2] * az])
+        dq = rm.hamilton_prod(q, np.array([0, 0, 0, wz])) / 2
+        cmd['acc'].append(np.concatenate([W_R_B.T @ W_a, [wz]]))
+        Fa.append(np.concatenate([v, dq, W_a]))
+        Ya.append(np.concatenate([p, [q_e[3]], v, W_a, [wz]]))
+        # att (quad_rollpitchyawrate.py:27-45)
+        th = np.arctan2(q[3], q[0]); qyaw = np.array([np.cos(th), 0, 0, np.sin(th)])
+        R_att = rm.quat2rot(qyaw) @ rm.euler2rot(np.array([roll_des, pitch_des, 0.0]))
+        W_a = R_att @ np.array([0, 0, gamma]) + np.array([0, 0, -g])
+        cmd['att'].append(np.concatenate([R_att.T @ W_a, [wz]]))
+    np.savez_compressed(os.path.join(HERE, 'model_variants.npz'), X=X, U=U, QD=QD, F_att_tau=np.array(Ft), Y_att_tau=np.array(Yt),
+                        F_acc=np.array(Fa), Y_acc=np.array(Ya), **{'CMDACC_' + k: np.array(v) for k, v in cmd.items()})
+    print('model_variants: f range', np.abs(Ft).max(), np.abs(Fa).max())
+
+
 if __name__ == '__main__':
     torch.manual_seed(0)
     torch.set_num_threads(4)
@@ -176,4 +224,5 @@ if __name__ == '__main__':
     sdf_case('small_latent_softplus', 256, seed=5, embed='ico', nb_freqs=2, layer_sizes=(64, 32, 32, 16), res='latent',
              act='softplus', w0=1.0, size_latent=32)
     model_att_case()
+    model_variants_case()
     encoder_case()

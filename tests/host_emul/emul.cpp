@@ -11,18 +11,23 @@ using namespace sdfnmpc;
 using Shape = QpShape<ATT_NX, ATT_NU, ATT_NY, ATT_NH>;
 using Prob = QpProb<ATT_NX, ATT_NU, ATT_NY, ATT_NH>;
 
-extern "C" void emul_linearize(int B, int N, const double* mcv, const double* xbar, const double* ubar,
+extern "C" void emul_linearize(int model, int nyN, int B, int N, const double* mcv, const double* xbar, const double* ubar,
                                const double* yref, const double* yrefN, const double* qd, const double* pose,
                                const double* flag, const double* dt, double* AB, double* bdyn, double* J,
                                double* yres, double* C, double* hval, float* qpts) {
     ModelConst mc;
     mc.g = mcv[0]; mc.gamma = mcv[1]; mc.roll = mcv[2]; mc.pitch = mcv[3]; mc.wz = mcv[4]; mc.mass = mcv[5];
     mc.cam_off[0] = mcv[6]; mc.cam_off[1] = mcv[7]; mc.cam_off[2] = mcv[8];
-    LinIn in{xbar, ubar, yref, yrefN, qd, pose, flag, dt};
+    mc.ax = mcv[9]; mc.ay = mcv[10]; mc.az = mcv[11]; mc.tau_roll = mcv[12]; mc.tau_pitch = mcv[13];
+    LinIn in{xbar, ubar, yref, yrefN, qd, pose, flag, dt, nyN};
     LinOut out{AB, bdyn, J, yres, C, hval, qpts};
     for (int b = 0; b < B; ++b)
         for (int k = 0; k <= N; ++k)
-            for (int d = 0; d < ATT_NW; ++d) linearize_dir(mc, N, in, out, b, k, d);
+            for (int d = 0; d < ATT_NW; ++d) {
+                if (model == MODEL_ATT) linearize_dir<MODEL_ATT>(mc, N, in, out, b, k, d);
+                else if (model == MODEL_ATT_TAU) linearize_dir<MODEL_ATT_TAU>(mc, N, in, out, b, k, d);
+                else linearize_dir<MODEL_ACC>(mc, N, in, out, b, k, d);
+            }
 }
 
 extern "C" void emul_qp(int B, int N, int k0, int max_iter, int nyN, double lm, double tol, double tol_res,

@@ -28,15 +28,18 @@ def _emul_step(lib, net, cfg, prob, xe, ue):
     from oracle import rti, sdf as SDF
     B, N = xe.shape[0], cfg['N']
     pose = np.ascontiguousarray(np.concatenate([prob['W_p_Co'], prob['W_R_Co'].reshape(B, 9)], 1))
+    from oracle import models
+    mid, nyN = models.MODEL_ID[cfg['model']], models.get(cfg['model']).nyN
     mcv = np.array([cfg['g'], cfg['gamma'], cfg['roll'], cfg['pitch'], cfg['wz'], cfg['mass'],
-                    *(cfg['B_R_C'].T @ cfg['B_p_C'] + np.array([cfg['fov_off'], 0, 0]))])
+                    *(cfg['B_R_C'].T @ cfg['B_p_C'] + np.array([cfg['fov_off'], 0, 0])),
+                    cfg['ax'], cfg['ay'], cfg['az'], cfg['tau_roll'], cfg['tau_pitch']])
     lh, uh = rti.h_bounds(cfg, net['max_df'])
     zs, Zs = rti.slack_weights(cfg)
     AB = np.zeros((B, N, 10, 14)); bd = np.zeros((B, N, 10)); J = np.zeros((B, N + 1, 11, 14)); yr = np.zeros((B, N + 1, 11))
     C = np.zeros((B, N + 1, 3, 14)); hv = np.zeros((B, N + 1, 3)); qp = np.zeros((B, N + 1, 3), np.float32)
     c = np.ascontiguousarray
     yref, yrefN, qd, flag, W, WN, x0 = (c(prob[k]) for k in ('yref', 'yrefN', 'qd', 'flag', 'W', 'WN', 'x0'))
-    lib.emul_linearize(B, N, _P(mcv), _P(xe), _P(ue), _P(yref), _P(yrefN), _P(qd), _P(pose), _P(flag), _P(cfg['dt']),
+    lib.emul_linearize(mid, nyN, B, N, _P(mcv), _P(xe), _P(ue), _P(yref), _P(yrefN), _P(qd), _P(pose), _P(flag), _P(cfg['dt']),
                        _P(AB), _P(bd), _P(J), _P(yr), _P(C), _P(hv), _P(qp))
     lin = dict(AB=AB.copy(), b=bd.copy(), J=J.copy(), hv=hv.copy(), C=C.copy(), qp=qp.copy())
     d, g = SDF.value_and_grad(net, qp.reshape(-1, 3), np.repeat(prob['latent'], N + 1, 0), dtype=np.float32)
@@ -44,25 +47,26 @@ def _emul_step(lib, net, cfg, prob, xe, ue):
     u0 = np.zeros((B, 4)); lamh = np.zeros((B, N, 8)); lams = np.zeros((B, N + 1, 6))
     st = np.zeros(B, np.int32); its = np.zeros(B, np.int32)
     D = ctypes.c_double
-    lib.emul_qp(B, N, 1, 100, 4, D(cfg['lm']), D(1e-8), D(1e-7), D(net['max_df']), _P(flag), _P(AB), _P(bd), _P(J), _P(yr), _P(C),
+    lib.emul_qp(B, N, 1, 100, nyN, D(cfg['lm']), D(1e-8), D(1e-7), D(net['max_df']), _P(flag), _P(AB), _P(bd), _P(J), _P(yr), _P(C),
                 _P(hv), _P(W), _P(WN), _P(cfg['dt']), _P(cfg['lbu']), _P(cfg['ubu']), _P(lh), _P(uh), _P(zs), _P(Zs), _P(d), _P(g),
                 _P(pose), _P(x0), _P(xe), _P(ue), _P(u0), _P(lamh), _P(lams), _P(st), _P(its))
     return u0, st, its, lamh, lams, lin
 
 
-def test_linearize_and_qp_cores_match_oracle(emul):
+@pytest.mark.parametrize('model', ['att', 'att_tau', 'acc'])
+def test_linearize_and_qp_cores_match_oracle(emul, model):
     from oracle import rti
     from sdf_nmpc_b200 import synth
     net = synth.make_sdf_net(seed=0, **synth.ARCH_B, calibrated=True)
-    cfg = rti.default_cfg()
+    cfg = rti.default_cfg(model)
     B = 12
-    prob, w = make_problem(B, cfg)
+    prob, w = make_problem(B, cfg, model=model)
     xb, ub = rti.init_traj(prob['x0'], cfg)
     xe, ue = np.ascontiguousarray(xb.copy()), np.ascontiguousarray(ub.copy())
     for step in range(3):
         xo, uo, out = rti.rti_step(net, xb, ub, prob, cfg)
         u0, st, its, lamh, lams, lin = _emul_step(emul, net, cfg, prob, xe, ue)
-        if step == 0:   # dual-number linearisation == hand-derived analytic Jacobians of the oracle
+        if step == 0:   # dual-number linearisation == the oracle's Jacobians (hand-derived for 'att')
             L = out['lin']
             assert np.abs(lin['AB'][..., 4:] - L['A']).max() < 1e-12 and np.abs(lin['AB'][..., :4] - L['B']).max() < 1e-12
             assert np.abs(lin['b'] - L['b']).max() < 1e-12
