@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'lib', 'libsdfnmpc_b200.so')
+# SDFNMPC_LIB selects another build of the SAME library (kernel A/B experiments, tools/qp_ab.py); default = the in-tree build
+LIB_PATH = os.environ.get('SDFNMPC_LIB') or os.path.join(HERE, 'lib', 'libsdfnmpc_b200.so')
 MAX_N = 64
 
 _lib = None

@@ -65,29 +65,91 @@ struct Lanes {
     }
 };
 
-// Asynchronous global -> shared staging of `n` doubles (n even, both pointers 16-byte aligned), split over the lanes.
-// Device: cp.async (LDGSTS, .cg = served from L2, so data this group wrote with plain stores is never read from a stale
-// L1 line) - the copy proceeds while the group computes on the other buffer.  Host: plain copy.
-SDF_HD void stage_async(const Lanes& L, double* dst_smem, const double* src, int n) {
+// Asynchronous global -> shared staging with the bulk-copy engine (TMA, cp.async.bulk / UBLKCP): ONE instruction issued
+// by lane 0 moves a whole contiguous array (bytes a multiple of 16, both addresses 16-byte aligned) and signals an
+// mbarrier owned by the lane group; the other lanes spend no issue slots on the copy.  `StagePipe` is a two-slot pipeline:
+// slot s is filled with begin(s, total bytes) + copy(...) and consumed after wait(s).  The copy engine reads global
+// memory through the async proxy, so publish() orders the group's earlier generic-proxy stores before it with a proxy
+// fence (the caller has synchronised the lanes).  Host emulation: plain copies.
+struct StagePipe {
+    unsigned bar[2];      // shared-window addresses of the two mbarriers
+    unsigned parity;      // bit s = phase parity slot s waits for next
+
+    SDF_HD void init(const Lanes& L, unsigned long long* bars) {
 #if defined(__CUDA_ARCH__)
-    const unsigned d0 = (unsigned)__cvta_generic_to_shared(dst_smem);
-    for (int c = L.lane; c < n / 2; c += 32)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + c * 16), "l"(src + 2 * c) : "memory");
+        bar[0] = (unsigned)__cvta_generic_to_shared(bars);
+        bar[1] = bar[0] + 8;
+        parity = 0;
+        if (L.lane == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar[0]) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar[1]) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        L.sync();
 #else
-    for (int c = 0; c < n; ++c) dst_smem[c] = src[c];
-    (void)L;
+        (void)L; (void)bars; parity = 0;
 #endif
-}
-SDF_HD void stage_commit() {
-#if defined(__CUDA_ARCH__)
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    // Make the group's earlier generic-proxy global stores visible to the copy engine (call after a lane barrier, once
+    // per sweep: a sweep only stages data written before it started).
+    SDF_HD void publish(const Lanes& L) const {
+#if defined(__CUDA_ARCH__) && defined(SDFNMPC_STAGE_BULK)
+        if (L.lane == 0) asm volatile("fence.proxy.async;" ::: "memory");
+#else
+        (void)L;
 #endif
-}
-SDF_HD void stage_wait_all() {
-#if defined(__CUDA_ARCH__)
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    SDF_HD void begin(const Lanes& L, int slot, unsigned bytes) const {
+#if defined(__CUDA_ARCH__) && !defined(SDFNMPC_STAGE_BULK)
+        (void)L; (void)slot; (void)bytes;
+#elif defined(__CUDA_ARCH__)
+        if (L.lane == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar[slot]), "r"(bytes) : "memory");
+#else
+        (void)L; (void)slot; (void)bytes;
 #endif
-}
+    }
+    SDF_HD void copy(const Lanes& L, int slot, double* dst_smem, const double* src, int n) const {
+#if defined(__CUDA_ARCH__) && !defined(SDFNMPC_STAGE_BULK)
+        // development variant: per-lane 16-byte cp.async (LDGSTS) instead of the bulk engine
+        const unsigned d0 = (unsigned)__cvta_generic_to_shared(dst_smem);
+        for (int c = L.lane; c < n / 2; c += 32)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + c * 16), "l"(src + 2 * c) : "memory");
+        (void)slot;
+#elif defined(__CUDA_ARCH__)
+        if (L.lane == 0)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             (unsigned)__cvta_generic_to_shared(dst_smem)),
+                         "l"(src), "r"(n * 8), "r"(bar[slot])
+                         : "memory");
+#else
+        for (int c = 0; c < n; ++c) dst_smem[c] = src[c];
+        (void)L; (void)slot;
+#endif
+    }
+    SDF_HD void wait(const Lanes& L, int slot) {
+#if defined(__CUDA_ARCH__) && !defined(SDFNMPC_STAGE_BULK)
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        L.sync();
+        (void)slot;
+#elif defined(__CUDA_ARCH__)
+        (void)L;
+        const unsigned ph = (parity >> slot) & 1u;
+        unsigned done = 0;
+        while (!done)
+            asm volatile(
+                "{\n\t.reg .pred P1;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+                "selp.b32 %0, 1, 0, P1;\n\t}"
+                : "=r"(done)
+                : "r"(bar[slot]), "r"(ph)
+                : "memory");
+        parity ^= 1u << slot;
+#else
+        (void)L; (void)slot;
+#endif
+    }
+};
 
 }  // namespace sdfnmpc
 

@@ -15,9 +15,13 @@ namespace {
 constexpr int NX = ATT_NX, NU = ATT_NU, NW = ATT_NW, NY = ATT_NY, NYN = ATT_NYN, NH = ATT_NH;
 using Shape = QpShape<NX, NU, NY, NH>;
 using Prob = QpProb<NX, NU, NY, NH>;
-constexpr int QP_WARPS = 4;     // instances per CTA
+#ifndef QP_WARPS_PER_CTA
+#define QP_WARPS_PER_CTA 2
+#endif
+constexpr int QP_WARPS = QP_WARPS_PER_CTA;     // instances per CTA
 #ifndef QP_MIN_CTAS
-#define QP_MIN_CTAS 2          // 8 warps per SM (capping registers at 168 for 12 warps/SM spills 3.6 KB and is 1.5x slower)
+#define QP_MIN_CTAS 4          // x 2 warps = 8 warps per SM (capping registers at 168 for 12 warps/SM spills 3.6 KB and is 1.5x slower;
+                               // 1 / 2 / 4 warps per CTA at 8 warps per SM: 6.9 / 6.4 / 6.5 ms)
 #endif
 
 struct SolverConst {

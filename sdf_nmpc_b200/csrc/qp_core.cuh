@@ -40,15 +40,23 @@ struct QpShape {
     static constexpr int NCORR = NU + 6 + NU + 3;   // du, Dp(sym 3x3), gu, gp
     static constexpr int NPROD = 2 * NU + 4 * NH;   // second-order products per node
     SDF_HD static int kp(int N) { return N + 2; }   // padded node count of the [item][node] arrays
-    // per-stage data staged asynchronously into shared memory: AB | H | rv0 | rd0 | PbM | L | K
-    static constexpr int ST_AB = 0, ST_H = ST_AB + NX * NW, ST_RV = ST_H + NW * NW, ST_RD = ST_RV + NW, ST_PB = ST_RD + NX,
-                         ST_L = ST_PB + NX, ST_K = ST_L + NU * NU, STAGE_DOUBLES = (ST_K + NU * NX + 1) / 2 * 2;
+    // Per-stage data travels global -> shared by bulk copies, so what one sweep needs of a stage is contiguous in the
+    // global scratch:  record A_k = [ rv0_k | rd0_{k+1} | H_k ]  (written once per solve),
+    //                  record F_k = [ PbM_k | L_k | K_k ]         (written by the factorising sweep of every iteration).
+    static constexpr int RA_RV = 0, RA_RD = NW, RA_H = NW + NX, REC_A = NW + NX + NW * NW;
+    static constexpr int RF_PB = 0, RF_L = NX, RF_K = NX + NU * NU, REC_F = NX + NU * NU + NU * NX;
+    // shared stage slot: AB | record A | record F
+    static constexpr int ST_AB = 0, ST_A = NX * NW, ST_RV = ST_A + RA_RV, ST_RD = ST_A + RA_RD, ST_H = ST_A + RA_H,
+                         ST_F = ST_A + REC_A, ST_PB = ST_F + RF_PB, ST_L = ST_F + RF_L, ST_K = ST_F + RF_K,
+                         STAGE_DOUBLES = ST_F + REC_F;
+    static_assert(NX % 2 == 0 && NW % 2 == 0 && NU % 2 == 0 && REC_A % 2 == 0 && REC_F % 2 == 0 && STAGE_DOUBLES % 2 == 0,
+                  "bulk copies move 16-byte units");
     // doubles of per-instance global scratch
     SDF_HD static size_t work_doubles(int N) {
         size_t n1 = (size_t)(N + 1);
-        return n1 * NW * NW + n1 * NW      // H, g
-               + n1 * NW + n1 * NX         // rv0, rdyn0
-               + (size_t)N * (NU * NX + NU * NU + NX)   // K, Linv, PbM
+        return n1 * REC_A                  // rv0, rd0, H per node
+               + n1 * NW                   // g
+               + (size_t)N * REC_F         // PbM, Linv, K per stage
                + n1 * NX;                  // costates (final verification)
     }
     // doubles of per-lane-group shared memory
@@ -56,7 +64,7 @@ struct QpShape {
         return NX * NX + 2 * NX * (NW + 1) + NW * NW + NW + NU * NX + NU + 2 * NX   // Riccati workspace
                + 2 * NW * kp(N)                                                   // W (iterate), dW (step)
                + (NCORR + NPROD) * kp(N) + 8
-               + 2 * STAGE_DOUBLES;                                               // double-buffered per-stage data
+               + 2 * STAGE_DOUBLES + 2;                                           // double-buffered per-stage data, 2 mbarriers
     }
 };
 
@@ -90,6 +98,18 @@ struct QpProb {            // all pointers are offset to ONE instance
     int* iters;
 };
 
+// Initial point of the interior-point iteration.  tools/qp_init_sweep.py: smaller floors / mu0 or an 'inactive-row' split of
+// the soft multipliers change the mean iteration count by less than +-0.3 (9.7 cold), so the plain choice stays.
+#ifndef SDFNMPC_QP_T0
+#define SDFNMPC_QP_T0 0.5          // floor of the initial constraint slacks t
+#endif
+#ifndef SDFNMPC_QP_MU0
+#define SDFNMPC_QP_MU0 1.0         // initial complementarity lam * t of rows that start interior
+#endif
+#ifndef SDFNMPC_QP_S0
+#define SDFNMPC_QP_S0 0.5          // initial soft-constraint slack s
+#endif
+
 namespace qpdetail {
 
 template <int NW>
@@ -103,13 +123,22 @@ struct TriTable {
 };
 
 SDF_HD double rcp(double x) { return 1.0 / x; }
-SDF_HD double step_to_boundary(double x, double dx) { return dx < 0.0 ? -x / dx : 1e30; }
+SDF_HD double rsqrt_d(double x) {
+#if defined(__CUDA_ARCH__)
+    return rsqrt(x);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+// Step to the boundary x + alpha dx >= 0 without a division per row: rows report the ratio -dx/x (through the
+// reciprocal of x they already hold); alpha_max = 1 / max ratio is formed once per lane.
+SDF_HD double boundary_ratio(double dx, double rx) { return -dx * rx; }
 SDF_HD int sym3(int a, int b) { return a >= b ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a; }
 
 // Everything the elimination needs from one row; evaluated by ONE function so that the two places that use
 // r_p / rho (right-hand side and step) see bit-identical values.
-struct HardEval { double r_p, Th, coef; };
-struct SoftEval { double r_p, r_s, Th, D, Tht, rho, coef; };
+struct HardEval { double r_p, Th, coef, rt, rl; };                       // rt = 1/t, rl = 1/lam
+struct SoftEval { double r_p, r_s, Th, rD, Tht, rho, coef, rt, rl, rs, rm; };   // rD = 1/D, rs = 1/s, rm = 1/mu
 
 #if defined(__CUDA_ARCH__)
 #define SDF_NOINLINE __device__ __noinline__
@@ -117,28 +146,43 @@ struct SoftEval { double r_p, r_s, Th, D, Tht, rho, coef; };
 #define SDF_NOINLINE inline
 #endif
 
-SDF_NOINLINE HardEval hard_eval(double t, double lam, double gw, double d, double corr) {
+// Inlined: the independent rows of a node interleave their reciprocal / FMA chains (measured 5 % faster than calls;
+// -DSDFNMPC_QP_NOINLINE_EVAL restores the out-of-line form for A/B runs, tools/qp_ab.py).
+#if defined(SDFNMPC_QP_NOINLINE_EVAL)
+#define SDF_HARD_LINKAGE SDF_NOINLINE
+#define SDF_SOFT_LINKAGE SDF_NOINLINE
+#else
+#define SDF_HARD_LINKAGE SDF_HD
+#define SDF_SOFT_LINKAGE SDF_HD
+#endif
+
+SDF_HARD_LINKAGE HardEval hard_eval(double t, double lam, double gw, double d, double corr) {
     HardEval r;
-    const double rt = rcp(t);
+    const double c = lam * t, rc = rcp(c);        // one reciprocal serves both 1/t and 1/lam
+    const double rt = lam * rc;
+    r.rt = rt; r.rl = t * rc;
     r.r_p = t - (gw - d);
     r.Th = lam * rt;
-    const double kap = corr - lam * t;            // corr = 0 (affine) or tau - dlam_aff*dt_aff
+    const double kap = corr - c;                  // corr = 0 (affine) or tau - dlam_aff*dt_aff
     r.coef = -kap * rt - r.Th * r.r_p;
     return r;
 }
 
-SDF_NOINLINE SoftEval soft_eval(double t, double lam, double s, double mu, double gw, double d, double z, double Z,
+SDF_SOFT_LINKAGE SoftEval soft_eval(double t, double lam, double s, double mu, double gw, double d, double z, double Z,
                                 double corr_t, double corr_s) {
     SoftEval r;
-    const double rt = rcp(t), rs = rcp(s);
+    const double c1 = lam * t, c2 = mu * s;
+    const double rc1 = rcp(c1), rc2 = rcp(c2);
+    const double rt = lam * rc1, rs = mu * rc2;
+    r.rt = rt; r.rl = t * rc1; r.rs = rs; r.rm = s * rc2;
     r.r_p = t - (gw - d + s);
     r.r_s = z + Z * s - lam - mu;
     r.Th = lam * rt;
     const double zs = Z + mu * rs;
-    r.D = zs + r.Th;
-    const double rD = rcp(r.D);
+    const double rD = rcp(zs + r.Th);
+    r.rD = rD;
     r.Tht = r.Th * zs * rD;
-    const double kap = corr_t - lam * t, nu = corr_s - mu * s;
+    const double kap = corr_t - c1, nu = corr_s - c2;
     r.rho = -r.r_s + kap * rt + nu * rs + r.Th * r.r_p;
     r.coef = -kap * rt + r.Th * (r.rho * rD - r.r_p);
     return r;
@@ -163,14 +207,18 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
     double* p = P.work;
     auto take = [&](size_t n) { double* r = p; p += n; return r; };
     const size_t n1 = (size_t)(N + 1);
-    double* H = take(n1 * NW * NW);
+    double* recA = take(n1 * S::REC_A);        // per node: rv0 | rd0 (of the NEXT node) | H
     double* g = take(n1 * NW);
-    double* rv0 = take(n1 * NW);       // stationarity residual at the initial point (scaled by phi afterwards)
-    double* rd0 = take(n1 * NX);       // dynamics residual at the initial point: rd0[k+1] = AB_k w_k + b_k - w_x,k+1
-    double* Kg = take((size_t)N * NU * NX);
-    double* Lg = take((size_t)N * NU * NU);   // Cholesky factor of Ruu, diagonal stored INVERTED
-    double* PbM = take((size_t)N * NX);
+    double* recF = take((size_t)N * S::REC_F);  // per stage: PbM | Linv | K
     double* pig = take(n1 * NX);
+    // rv0: stationarity residual at the initial point (scaled by phi afterwards); rd0[k] = AB_{k-1} w_{k-1} + b_{k-1} - w_x,k
+    // lives in record k-1 (the stage that produces node k); H: Gauss-Newton Hessian; L: Cholesky factor of Ruu, diagonal INVERTED
+    auto Hk = [&](int k) { return recA + (size_t)k * S::REC_A + S::RA_H; };
+    auto rv0k = [&](int k) { return recA + (size_t)k * S::REC_A + S::RA_RV; };
+    auto rd0k = [&](int k) { return recA + (size_t)(k - 1) * S::REC_A + S::RA_RD; };   // k >= 1
+    auto PbMk = [&](int k) { return recF + (size_t)k * S::REC_F + S::RF_PB; };
+    auto Lgk = [&](int k) { return recF + (size_t)k * S::REC_F + S::RF_L; };
+    auto Kgk = [&](int k) { return recF + (size_t)k * S::REC_F + S::RF_K; };
 
     // ---- shared workspace -----------------------------------------------------------------------
     double* Psm = sm;                    // [NX][NX]
@@ -187,7 +235,8 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
     double* corr = dW + NW * KP;         // [NCORR][KP] du(NU) Dp(6) gu(NU) gp(3) per node
     double* prod = corr + NCORR * KP;    // [NPROD][KP] affine second-order products
     double* stg = prod + NPROD * KP + ((NPROD * KP) & 1);   // 2 x STAGE_DOUBLES (16-byte aligned)
-    static_assert(NX % 2 == 0 && NW % 2 == 0 && NU % 2 == 0, "stage_async moves 16-byte units");
+    StagePipe pipe;
+    pipe.init(L, reinterpret_cast<unsigned long long*>(stg + 2 * S::STAGE_DOUBLES));
 
     auto scale = [&](int k) { return k < N ? P.dt[k] : 1.0; };
     auto wrow = [&](int k, int r) { return k < N ? P.W[k * NY + r] : (r < P.nyN ? P.WN[r] : 0.0); };
@@ -207,8 +256,8 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
         for (int r = 0; r < NY; ++r) s += Jk[r * NW + i] * wrow(k, r) * Jk[r * NW + j];
         if (i == j) s += P.lm;
         s *= scale(k);
-        H[(size_t)k * NW * NW + i * NW + j] = s;
-        H[(size_t)k * NW * NW + j * NW + i] = s;
+        Hk(k)[i * NW + j] = s;
+        Hk(k)[j * NW + i] = s;
     }
     for (int e = lane; e < (N + 1) * NW; e += NL) {
         const int k = e / NW, i = e - k * NW;
@@ -295,52 +344,51 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
         for (int a = 0; a < 2 * NU; ++a) {
             double t = 1.0, l = 1.0;
             if (kk < N) {
-                t = fmax(-hard_d(kk, a), 0.5);          // w_u = 0
-                l = fmax(1.0 / t, 1e-3);
+                t = fmax(-hard_d(kk, a), SDFNMPC_QP_T0);          // w_u = 0
+                l = fmax(SDFNMPC_QP_MU0 / t, 1e-3 * SDFNMPC_QP_MU0);
             }
             tb[a] = t; lb[a] = l;
         }
 #pragma unroll
         for (int a = 0; a < 2 * NH; ++a) {
             const int r = a < NH ? a : a - NH;
-            double t = 1.0, l = 1.0, s0 = 0.5;
+            double t = 1.0, l = 1.0, m = 1.0, s0 = SDFNMPC_QP_S0;
             if (kk >= k0) {
                 const double z = P.zs[r] * scale(kk), Z = P.Zs[r] * scale(kk);
                 double cw = 0.0;
                 for (int c = 0; c < 3; ++c) cw += c_pos(kk, r, c) * Wsm[(HC0 + c) * KP + kk];
                 const double gw = a < NH ? cw : -cw;
-                t = fmax(gw - soft_d(kk, a) + s0, 0.5);
-                l = fmax(0.5 * (z + Z * s0), 1e-3);
+                t = fmax(gw - soft_d(kk, a) + s0, SDFNMPC_QP_T0);
+                l = fmax(0.5 * (z + Z * s0), 1e-3);     // lam = mu: slack stationarity z + Z s - lam - mu = 0 split evenly
+                m = l;
             }
-            ts[a] = t; ss[a] = s0; ls[a] = l; ms[a] = l;
+            ts[a] = t; ss[a] = s0; ls[a] = l; ms[a] = m;
         }
         SDF_STORE_STATE(kk);
         // rv0_k = H_k w_k + g_k - sum lam_i gvec_i   (w = 0 except dx_0; costates 0)
         for (int i = 0; i < NW; ++i) {
             double s = g[(size_t)kk * NW + i];
             if (kk == 0)
-                for (int j = NU; j < NW; ++j) s += H[i * NW + j] * Wsm[j * KP];
+                for (int j = NU; j < NW; ++j) s += Hk(0)[i * NW + j] * Wsm[j * KP];
             if (kk < N && i < NU) s -= lb[i] - lb[NU + i];
             if (kk >= k0 && i >= HC0 && i < HC0 + 3)
                 for (int r = 0; r < NH; ++r) s -= (ls[r] - ls[NH + r]) * c_pos(kk, r, i - HC0);
             if ((kk == 0 && i >= NU) || (kk == N && i < NU)) s = 0.0;
-            rv0[(size_t)kk * NW + i] = s;
+            rv0k(kk)[i] = s;
         }
         // rd0_{k} (k >= 1) = AB_{k-1} w_{k-1} + b_{k-1} - w_x,k ; only w_x,0 is non-zero
-        for (int i = 0; i < NX; ++i) {
-            double s = 0.0;
-            if (kk >= 1) {
-                s = P.bdyn[(kk - 1) * NX + i];
+        if (kk >= 1)
+            for (int i = 0; i < NX; ++i) {
+                double s = P.bdyn[(kk - 1) * NX + i];
                 if (kk == 1)
                     for (int j = NU; j < NW; ++j) s += P.AB[(size_t)i * NW + j] * Wsm[j * KP];
+                rd0k(kk)[i] = s;
             }
-            rd0[(size_t)kk * NX + i] = s;
-        }
     }
     L.sync();
     double res_v0 = 0.0;
-    for (int e = lane; e < (N + 1) * NW; e += NL) res_v0 = fmax(res_v0, fabs(rv0[e]));
-    for (int e = lane; e < (N + 1) * NX; e += NL) res_v0 = fmax(res_v0, fabs(rd0[e]));
+    for (int e = lane; e < (N + 1) * NW; e += NL) { const int k = e / NW; res_v0 = fmax(res_v0, fabs(rv0k(k)[e - k * NW])); }
+    for (int e = lane; e < N * NX; e += NL) { const int k = e / NX; res_v0 = fmax(res_v0, fabs(rd0k(k + 1)[e - k * NX])); }
     res_v0 = L.max(res_v0);
 
     int status = 2, it = 0;
@@ -435,39 +483,41 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
             if (pass == 0) {
                 SDF_LANES_FOR(e, NX * NX) {
                     const int i = e / NX, j = e - i * NX;
-                    double s = H[(size_t)N * NW * NW + (size_t)(NU + i) * NW + NU + j];
+                    double s = Hk(N)[(NU + i) * NW + NU + j];
                     const int pi_ = i + NU - HC0, pj = j + NU - HC0;
                     if (pi_ >= 0 && pi_ < 3 && pj >= 0 && pj < 3) s += corr[(NU + sym3(pi_, pj)) * KP + N];
                     Psm[e] = s;
                 }
             }
             SDF_LANES_FOR(e, NX) {
-                double s = phi * rv0[(size_t)N * NW + NU + e];
+                double s = phi * rv0k(N)[NU + e];
                 const int pe = e + NU - HC0;
                 if (pe >= 0 && pe < 3) s += corr[(2 * NU + 6 + pe) * KP + N];
                 pv[e] = s;
             }
             L.sync();
             // stage data of node kk is prefetched into the other half of `stg` while node kk+1 is processed
-            auto prefetch = [&](int kk, double* dst) {
-                stage_async(L, dst + S::ST_AB, P.AB + (size_t)kk * NX * NW, NX * NW);
-                stage_async(L, dst + S::ST_RV, rv0 + (size_t)kk * NW, NW);
+            // (every stage body ends with a lane barrier, so the slot being refilled is no longer read)
+            auto prefetch = [&](int kk, int slot) {
+                double* dst = stg + slot * S::STAGE_DOUBLES;
                 if (pass == 0) {
-                    stage_async(L, dst + S::ST_H, H + (size_t)kk * NW * NW, NW * NW);
-                    stage_async(L, dst + S::ST_RD, rd0 + (size_t)(kk + 1) * NX, NX);
+                    pipe.begin(L, slot, (NX * NW + S::REC_A) * 8);
+                    pipe.copy(L, slot, dst + S::ST_AB, P.AB + (size_t)kk * NX * NW, NX * NW);
+                    pipe.copy(L, slot, dst + S::ST_A, recA + (size_t)kk * S::REC_A, S::REC_A);
                 } else {
-                    stage_async(L, dst + S::ST_PB, PbM + (size_t)kk * NX, NX);
-                    stage_async(L, dst + S::ST_L, Lg + (size_t)kk * NU * NU, NU * NU);
-                    stage_async(L, dst + S::ST_K, Kg + (size_t)kk * NU * NX, NU * NX);
+                    pipe.begin(L, slot, (NX * NW + NW + S::REC_F) * 8);
+                    pipe.copy(L, slot, dst + S::ST_AB, P.AB + (size_t)kk * NX * NW, NX * NW);
+                    pipe.copy(L, slot, dst + S::ST_RV, rv0k(kk), NW);
+                    pipe.copy(L, slot, dst + S::ST_F, recF + (size_t)kk * S::REC_F, S::REC_F);
                 }
-                stage_commit();
             };
-            prefetch(N - 1, stg);
+            pipe.publish(L);
+            prefetch(N - 1, 0);
             for (int kk = N - 1; kk >= 0; --kk) {
-                const double* sb = stg + ((N - 1 - kk) & 1) * S::STAGE_DOUBLES;
-                stage_wait_all();
-                L.sync();
-                if (kk > 0) prefetch(kk - 1, stg + ((N - kk) & 1) * S::STAGE_DOUBLES);
+                const int slot = (N - 1 - kk) & 1;
+                const double* sb = stg + slot * S::STAGE_DOUBLES;
+                pipe.wait(L, slot);
+                if (kk > 0) prefetch(kk - 1, slot ^ 1);
                 const double* ABk = sb + S::ST_AB;
                 if (pass == 0) {
                     SDF_LANES_FOR(e, NX * NW) { const int i = e / NW; ABb[i * NWB + (e - i * NW)] = ABk[e]; }
@@ -478,7 +528,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                         double s = 0.0;
 #pragma unroll
                         for (int l = 0; l < NX; ++l) s += Psm[i * NX + l] * ABb[l * NWB + j];
-                        if (j == NW) { PbM[kk * NX + i] = s; s += pv[i]; }
+                        if (j == NW) { PbMk(kk)[i] = s; s += pv[i]; }
                         PAB[e] = s;
                     }
                     L.sync();
@@ -515,7 +565,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                             double s = Msm[i * NW + j];
 #pragma unroll
                             for (int l = 0; l < j; ++l) s -= Lr[i][l] * Lr[j][l];
-                            if (i == j) { ok = ok && (s > 0.0); Lr[i][i] = 1.0 / sqrt(s); }
+                            if (i == j) { ok = ok && (s > 0.0); Lr[i][i] = rsqrt_d(s); }
                             else Lr[i][j] = s * Lr[j][j];
                         }
                     if (!ok) status = 4;
@@ -537,13 +587,13 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                         }
 #pragma unroll
                         for (int i = 0; i < NU; ++i) {
-                            if (c < NX) { Ksm[i * NX + c] = -x[i]; Kg[(size_t)kk * NU * NX + i * NX + c] = -x[i]; }
+                            if (c < NX) { Ksm[i * NX + c] = -x[i]; Kgk(kk)[i * NX + c] = -x[i]; }
                             else kfs[i] = -x[i];
                         }
                     }
                     if (lane == 0)
                         for (int i = 0; i < NU; ++i)
-                            for (int j = 0; j < NU; ++j) Lg[(size_t)kk * NU * NU + i * NU + j] = j <= i ? Lr[i][j] : 0.0;
+                            for (int j = 0; j < NU; ++j) Lgk(kk)[i * NU + j] = j <= i ? Lr[i][j] : 0.0;
                     L.sync();
                     // P <- Qxx + Rux' K (lower triangle, mirrored: stays exactly symmetric), p <- r_x + Rux' kff
                     constexpr int TRX = NX * (NX + 1) / 2;
@@ -613,18 +663,20 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
             // ---------- forward roll-out: dW = step ----------
             SDF_LANES_FOR(i, NX) dW[(NU + i) * KP] = 0.0;      // dx_0 = 0 (w_x0 already equals x0 - xbar_0)
             L.sync();
-            auto prefetch_f = [&](int kk, double* dst) {
-                stage_async(L, dst + S::ST_AB, P.AB + (size_t)kk * NX * NW, NX * NW);
-                stage_async(L, dst + S::ST_RD, rd0 + (size_t)(kk + 1) * NX, NX);
-                stage_async(L, dst + S::ST_K, Kg + (size_t)kk * NU * NX, NU * NX);
-                stage_commit();
+            auto prefetch_f = [&](int kk, int slot) {
+                double* dst = stg + slot * S::STAGE_DOUBLES;
+                pipe.begin(L, slot, (NX * NW + NX + NU * NX) * 8);
+                pipe.copy(L, slot, dst + S::ST_AB, P.AB + (size_t)kk * NX * NW, NX * NW);
+                pipe.copy(L, slot, dst + S::ST_RD, rd0k(kk + 1), NX);
+                pipe.copy(L, slot, dst + S::ST_K, Kgk(kk), NU * NX);
             };
-            prefetch_f(0, stg);
+            pipe.publish(L);
+            prefetch_f(0, 0);
             for (int kk = 0; kk < N; ++kk) {
-                const double* sb = stg + (kk & 1) * S::STAGE_DOUBLES;
-                stage_wait_all();
-                L.sync();
-                if (kk + 1 < N) prefetch_f(kk + 1, stg + ((kk + 1) & 1) * S::STAGE_DOUBLES);
+                const int slot = kk & 1;
+                const double* sb = stg + slot * S::STAGE_DOUBLES;
+                pipe.wait(L, slot);
+                if (kk + 1 < N) prefetch_f(kk + 1, slot ^ 1);
                 const double* Kk = sb + S::ST_K;
                 SDF_LANES_FOR(j, NU) {
                     double s = dW[j * KP + kk];
@@ -643,7 +695,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                 L.sync();
             }
             // =========== row steps (lane = node): the node's (dt, dlam, ds, dmu) stay in registers ===========
-            double amax = 1e30;
+            double rmax = 0.0;              // largest -dx/x over the lane's rows
             SDF_NODE_LOOP(kk) {
                 SDF_LOAD_STATE(kk);
 #pragma unroll
@@ -662,8 +714,8 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                             const HardEval ev = hard_eval(tb[a], lb[a], sgn * wu, hard_d(kk, a), cr);
                             const double kap = cr - lb[a] * tb[a];
                             dtb[a] = sgn * dwu - ev.r_p;
-                            dlb[a] = (kap - lb[a] * dtb[a]) / tb[a];
-                            amax = fmin(amax, fmin(step_to_boundary(tb[a], dtb[a]), step_to_boundary(lb[a], dlb[a])));
+                            dlb[a] = (kap - lb[a] * dtb[a]) * ev.rt;
+                            rmax = fmax(rmax, fmax(boundary_ratio(dtb[a], ev.rt), boundary_ratio(dlb[a], ev.rl)));
                         }
                     }
                 }
@@ -683,18 +735,19 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                             const SoftEval ev = soft_eval(ts[a], ls[a], ss[a], ms[a], sgn * cw, soft_d(kk, a), z, Z, ct, cs);
                             const double kap = ct - ls[a] * ts[a], nu = cs - ms[a] * ss[a];
                             const double gd = sgn * cd;
-                            dss[a] = (ev.rho - ev.Th * gd) / ev.D;
+                            dss[a] = (ev.rho - ev.Th * gd) * ev.rD;
                             dts[a] = gd + dss[a] - ev.r_p;
-                            dls[a] = (kap - ls[a] * dts[a]) / ts[a];
-                            dms[a] = (nu - ms[a] * dss[a]) / ss[a];
-                            amax = fmin(amax, fmin(fmin(step_to_boundary(ts[a], dts[a]), step_to_boundary(ls[a], dls[a])),
-                                                   fmin(step_to_boundary(ss[a], dss[a]), step_to_boundary(ms[a], dms[a]))));
+                            dls[a] = (kap - ls[a] * dts[a]) * ev.rt;
+                            dms[a] = (nu - ms[a] * dss[a]) * ev.rs;
+                            rmax = fmax(rmax, fmax(fmax(boundary_ratio(dts[a], ev.rt), boundary_ratio(dls[a], ev.rl)),
+                                                   fmax(boundary_ratio(dss[a], ev.rs), boundary_ratio(dms[a], ev.rm))));
                         }
                     }
                 }
                 SDF_STORE_DELTA(kk);
             }
-            amax = L.min(amax);
+            rmax = L.max(rmax);
+            const double amax = rmax > 1e-30 ? 1.0 / rmax : 1e30;
             if (pass == 0) {
                 // affine step length -> centring parameter; second-order products for the corrector
                 const double aa = fmin(1.0, amax);
@@ -757,7 +810,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
             for (int i = lane; i < NW; i += NL) {
                 if (kk == N && i < NU) continue;
                 double s = g[(size_t)kk * NW + i];
-                for (int j = 0; j < NW; ++j) s += H[(size_t)kk * NW * NW + i * NW + j] * Wsm[j * KP + kk];
+                for (int j = 0; j < NW; ++j) s += Hk(kk)[i * NW + j] * Wsm[j * KP + kk];
                 if (i < NU) s -= corr[i * KP + kk];
                 if (i >= HC0 && i < HC0 + 3)
                     for (int r = 0; r < NH; ++r) s -= corr[(NU + r) * KP + kk] * c_pos(kk, r, i - HC0);

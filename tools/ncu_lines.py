@@ -3,9 +3,11 @@ usage: python tools/ncu_lines.py <report.ncu-rep> <kernel substring> <cubin file
 import collections, csv, os, re, subprocess, sys, tempfile
 rep, kern, stem = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 30
+binary = sys.argv[5] if len(sys.argv) > 5 else None      # object / library the report was taken with (default: in-tree build)
+ranges = sys.argv[6] if len(sys.argv) > 6 else None      # 'name:lo-hi,name:lo-hi' line ranges of qp_core.cuh to aggregate
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tmp = tempfile.mkdtemp()
-subprocess.run(['cuobjdump', '-xelf', 'all', os.path.join(root, 'sdf_nmpc_b200/lib/libsdfnmpc_b200.so')], cwd=tmp, capture_output=True)
+subprocess.run(['cuobjdump', '-xelf', 'all', binary or os.path.join(root, 'sdf_nmpc_b200/lib/libsdfnmpc_b200.so')], cwd=tmp, capture_output=True)
 cubin = [f for f in os.listdir(tmp) if f.startswith(stem)][0]
 sass = subprocess.run(['nvdisasm', '--print-line-info', os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.split('\n')
 amap, cur, infunc = {}, None, False
@@ -24,10 +26,15 @@ for l in sass:
     m = re.match(r'\s*/\*([0-9a-f]{4,})\*/\s+(.*?);', l)
     if m:
         amap[int(m.group(1), 16)] = (cur, m.group(2))
-src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
+src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '-k', 'regex:' + kern], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.split('\n')))
 rows = [r for r in rows if len(r) > 5]
-hdr = rows[0]; idx = {h: i for i, h in enumerate(hdr)}; data = rows[1:]
+hdr = rows[0]; idx = {h: i for i, h in enumerate(hdr)}
+data = []
+for r in rows[1:]:          # first launch of the kernel only (the report may hold several)
+    if r[0] == hdr[0]:
+        break
+    data.append(r)
 base = int(data[0][0], 16)
 inst, samp, stall = collections.Counter(), collections.Counter(), collections.defaultdict(collections.Counter)
 stall_cols = [h for h in hdr if h.startswith('stall_') and 'Not Issued' not in h]
@@ -50,3 +57,21 @@ for key, c in samp.most_common(top):
     txt = files[f][n - 1].strip()[:80] if files[f] and 0 < n <= len(files[f]) else ''
     st = ' '.join(f'{k[6:]}={v}' for k, v in stall[key].most_common(2))
     print(f'{f}:{n:4d} samp {100 * c / ts:5.1f}% inst {100 * inst[key] / ti:5.1f}% [{st}] {txt}')
+
+if ranges:
+    print('--- phases (qp_core.cuh line ranges) ---')
+    acc = collections.OrderedDict()
+    spec = [(r.split(':')[0], *map(int, r.split(':')[1].split('-'))) for r in ranges.split(',')]
+    for key in samp:
+        f, n = key
+        name = 'other:' + f
+        if f == 'qp_core.cuh':
+            name = 'qp_core:unassigned'
+            for nm, lo, hi in spec:
+                if lo <= n <= hi:
+                    name = nm
+                    break
+        a = acc.setdefault(name, [0, 0])
+        a[0] += samp[key]; a[1] += inst[key]
+    for name, (sa, ins) in sorted(acc.items(), key=lambda kv: -kv[1][0]):
+        print(f'{name:28s} samp {100 * sa / ts:5.1f}%  inst {100 * ins / ti:5.1f}%')
