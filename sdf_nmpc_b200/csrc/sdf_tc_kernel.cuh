@@ -210,10 +210,24 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_TM >> 4) << 24);
 }
 
+// SIREN activations: the special-function unit (MUFU.SIN / MUFU.COS after the hardware range reduction) instead of the
+// polynomial pair.  Arguments w0*a of a SIREN stay within a few periods (|w0 a| <= 6.1 on the synthetic networks), where
+// the unit's absolute error is ~2^-21 + |x| 2^-24; propagated through the network this moves the SDF value by < 1e-6 and
+// its gradient by ~1e-6 (relative, max-norm; tolerances 1e-5 / 1e-4, tests/test_gpu_sdf.py).  The embedding keeps the
+// ~1-ulp fast_sincos: its arguments reach 2^(F-1) * |s| ~ 100 rad.  -DSDFNMPC_SDF_POLY_SINCOS selects the polynomial pair.
+__device__ __forceinline__ void act_sincos(float x, float& s, float& c) {
+#if defined(SDFNMPC_SDF_POLY_SINCOS)
+    fast_sincos(x, s, c);
+#else
+    s = __sinf(x);
+    c = __cosf(x);
+#endif
+}
+
 __device__ __forceinline__ void act_pair(int act, float w0, float a, float& h, float& dh) {
     if (act == SDF_ACT_SIN) {
         float s, c;
-        fast_sincos(w0 * a, s, c);
+        act_sincos(w0 * a, s, c);
         h = s; dh = w0 * c;
     } else if (act == SDF_ACT_RELU) {
         h = fmaxf(a, 0.f); dh = a > 0.f ? 1.f : 0.f;

@@ -22,8 +22,9 @@ def build(specs):
         for src in B.SOURCES:
             obj = os.path.join(VDIR, f'{tag}_{src[:-3]}.o')
             base_obj = os.path.join(B.LIBDIR, src.replace('.cu', '.o'))
-            if src != 'nmpc_api.cu' and os.path.exists(base_obj):
-                objs.append(base_obj)          # only the solver TU depends on the experiment flags
+            tu = 'sdf_api.cu' if tag.startswith('sdf') else 'nmpc_api.cu'
+            if src != tu and os.path.exists(base_obj):
+                objs.append(base_obj)          # only one TU depends on the experiment flags (tags 'sdf*': the SDF TU)
                 continue
             cmd = [B._nvcc()] + B.NVCC_FLAGS + flags.split() + ['-c', os.path.join(B.CSRC, src), '-o', obj]
             subprocess.run(cmd, check=True)
@@ -58,7 +59,21 @@ def one(Bn):
         step()
         its += float(mpc.qp_iters.double().mean().item())
     ms, n = mpc.timing_end()
-    print(json.dumps(dict(qp_ms=ms['qp'] / n, lin_ms=ms['linearize'] / n, sdf_ms=ms['sdf'] / n, iters=its / 10,
+    from sdf_nmpc_b200.sdf import SdfEvaluator
+    ev = SdfEvaluator(net)
+    ev.set_latents(torch.from_numpy(synth.latent(seed=2)).cuda())
+    n = 1_000_000
+    pts = torch.from_numpy(synth.sdf_query_points(n, seed=3)).cuda()
+    sdf = torch.empty(n, device='cuda'); grad = torch.empty(n, 3, device='cuda')
+    for _ in range(3):
+        ev.eval(pts, out=(sdf, grad))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        ev.eval(pts, out=(sdf, grad))
+    e1.record(); torch.cuda.synchronize()
+    sweep = n / (e0.elapsed_time(e1) / 10 * 1e-3) / 1e6
+    print(json.dumps(dict(sdf_mpts=sweep, qp_ms=ms['qp'] / n, lin_ms=ms['linearize'] / n, sdf_ms=ms['sdf'] / n, iters=its / 10,
                           ok=int((mpc.status == 0).sum().item()))))
 
 
