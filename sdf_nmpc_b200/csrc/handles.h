@@ -26,6 +26,7 @@ struct sdfnmpc_sdf {
     // tensor-core (tcgen05) path: chunk program, packed hi|lo weight chunks, per-CTA scratch
     bool tc_ok = false;
     void* tc_ops = nullptr;          // SdfTcOp[] (device)
+    void* tc_ops_host = nullptr;     // the same program on the host (passed by value in the kernel parameters)
     int tc_n_ops = 0, tc_n_acc = 0;
     unsigned char* tc_wblob = nullptr;
     float* tc_scratch = nullptr;

@@ -131,6 +131,9 @@ int build_tc(sdfnmpc_sdf* h, const float* W1, const float* W2, const float* W3, 
     h->tc_n_ops = (int)ops.size();
     SDF_CUDA_CHECK(cudaMalloc(&h->tc_ops, ops.size() * sizeof(SdfTcOp)));
     SDF_CUDA_CHECK(cudaMemcpy(h->tc_ops, ops.data(), ops.size() * sizeof(SdfTcOp), cudaMemcpyHostToDevice));
+    h->tc_ops_host = malloc(ops.size() * sizeof(SdfTcOp));
+    if (!h->tc_ops_host) return SDFNMPC_E_INVALID;
+    memcpy(h->tc_ops_host, ops.data(), ops.size() * sizeof(SdfTcOp));
     SDF_CUDA_CHECK(cudaMalloc(&h->tc_wblob, blob.size() * sizeof(float)));
     SDF_CUDA_CHECK(cudaMemcpy(h->tc_wblob, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
     h->tc_sc_off[0] = 0;
@@ -249,6 +252,7 @@ extern "C" int sdfnmpc_sdf_destroy(sdfnmpc_sdf_t h) {
     cudaFree(h->blob); cudaFree(h->b1f); cudaFree(h->b3f);
     cudaFree(h->h_pts); cudaFree(h->h_out); cudaFree(h->h_lat);
     cudaFree(h->tc_ops); cudaFree(h->tc_wblob); cudaFree(h->tc_scratch);
+    free(h->tc_ops_host);
     delete h;
     return 0;
 }
@@ -283,6 +287,7 @@ extern "C" int sdfnmpc_sdf_eval(sdfnmpc_sdf_t h, const float* pts, const int32_t
     if (h->tc_ok && grad && sdf && n >= h->tc_min_points) {
         SdfTcParams P;
         P.net = h->net; P.ops = (const SdfTcOp*)h->tc_ops; P.n_ops = h->tc_n_ops; P.wblob = h->tc_wblob;
+        memcpy(P.opsv, h->tc_ops_host, (size_t)h->tc_n_ops * sizeof(SdfTcOp));
         P.scratch = h->tc_scratch; P.scratch_floats_per_cta = h->tc_scratch_per_cta;
         P.sc_off_c1 = h->tc_sc_off[0]; P.sc_off_c2 = h->tc_sc_off[1]; P.sc_off_c3 = h->tc_sc_off[2]; P.sc_off_ge3 = h->tc_sc_off[3];
         P.b1f = h->b1f; P.b3f = h->b3f; P.pts = pts; P.pt2inst = pt2inst; P.pts_per_inst = pts_per_inst; P.n = (int)n;

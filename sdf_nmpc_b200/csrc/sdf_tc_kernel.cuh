@@ -33,6 +33,10 @@ constexpr int TC_PROD_THREADS = TC_PROD_WARPS * 32;
 constexpr int TC_THREADS = TC_PROD_THREADS + 32;
 constexpr int TC_WSTAGE_BYTES = 256 * TC_KC * 4 * 2;   // 64 KB: up to 256 weight rows, hi | lo
 constexpr int TC_ASTAGE_BYTES = TC_TM * TC_KC * 4 * 2;   // 32 KB: hi | lo
+// Timing-only ablations for development (results are wrong): -DTC_EXP_NO_STORE (producers skip the A-stage stores),
+// -DTC_EXP_ONE_MMA (hi*hi only), -DTC_EXP_NO_TMA (16-byte weight copies).  Measured at 1e6 points: base 151 Mpts/s, no
+// store 191, one MMA 181, no TMA 159, all three 278 - no single limiter; the producer skeleton alone costs 136 k cycles
+// per tile against 57 k of MMA floor.
 constexpr int TC_MAX_OPS = 80;
 constexpr int TC_AUX_BYTES = 128 /*barriers*/ + 128 * 16 /*embedding table*/ + 4 * 128 * 4 * 4 /*row partials*/ + TC_MAX_OPS * 80 /*op program*/;
 constexpr int TC_SMEM_BYTES = 2 * TC_WSTAGE_BYTES + 2 * TC_ASTAGE_BYTES + TC_AUX_BYTES + 1024;
@@ -58,7 +62,9 @@ struct SdfTcOp {
 
 struct SdfTcParams {
     SdfNetDev net;
-    const SdfTcOp* ops;
+    const SdfTcOp* ops;             // op program in global memory (producers copy it to shared memory)
+    SdfTcOp opsv[TC_MAX_OPS];       // the same program by value: the MMA-issuing warp reads it from the constant bank, so
+                                    // descriptors and TMEM columns are warp-uniform values (uniform registers, no R2UR)
     int n_ops;
     const unsigned char* wblob;     // packed weight chunks
     float* scratch;                 // per CTA: c1 | c2 | c3 | ge3, each [(feat/4)][128][4]
@@ -131,6 +137,23 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uin
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// One lane of the converged warp (elect.sync).  Unlike a lane-id comparison, the compiler knows that exactly one lane is
+// active inside `if (elect_one())`, so tcgen05 operands are broadcast once instead of through a per-lane waterfall loop
+// (ELECT + 7 R2UR + branch around every MMA: measured ~150 cycles per MMA issue).
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred = 0, laneid = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 %%rx;\n\t"
+        ".reg .pred %%px;\n\t"
+        "elect.sync %%rx|%%px, %2;\n\t"
+        "@%%px mov.s32 %1, 1;\n\t"
+        "mov.s32 %0, %%rx;\n\t"
+        "}"
+        : "+r"(laneid), "+r"(pred)
+        : "r"(0xFFFFFFFFu));
+    return pred;
 }
 // 32 lanes x 32 consecutive 32-bit columns -> 32 registers per thread
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
@@ -271,7 +294,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
     const uint32_t sfree[2] = {smem_u32(bars + 4), smem_u32(bars + 5)};
     const uint32_t dfull0 = smem_u32(bars + 6);                          // dfull[q] = dfull0 + 8 q
 
-    const int tid = threadIdx.x, warp = tid >> 5;
+    // warp index through a lane-0 shuffle: the compiler then knows it is warp-uniform, which keeps the role branches and
+    // everything computed inside the issuer role on the uniform datapath
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const SdfNetDev& net = P.net;
     const int DF = net.D * net.F;
     const float HALF_PI = 1.57079632679489661923f;
@@ -303,7 +328,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     const int n_tiles = (P.n + TC_TM - 1) / TC_TM;
     const int n_ops = P.n_ops;
@@ -395,7 +420,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
                 if (tr) P.trace[oi * 8 + 1] = clock64();
                 mbar_wait_backoff(sfree[g], ((chunk >> 1) & 1) ^ 1);
                 if (tr) P.trace[oi * 8 + 2] = clock64();
+#if !defined(TC_EXP_NO_STORE)
                 store_a16(ast[g], row, ch, v);
+#endif
                 fence_async_smem();
                 mbar_arrive(afull[g]);
                 if (tr) P.trace[oi * 8 + 3] = clock64();
@@ -446,33 +473,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
             }
             asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD_THREADS) : "memory");
         }
-    } else if (tid == TC_PROD_THREADS) {
-        // ============================== weight streamer + MMA issuer (one thread) ==============================
+    } else {
+        // ============================== weight streamer + MMA issuer ==============================
+        // The whole warp runs this loop converged, on warp-uniform values (op program from the constant bank), so that
+        // descriptors live in uniform registers; lane 0 alone executes the TMA / MMA / commit instructions.
+        const uint32_t leader = elect_one();
         const uint64_t n_chunks_total = (uint64_t)((n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * n_ops;
-        if (n_chunks_total > 0) {
-            const SdfTcOp o0 = ops_s[0];
-            mbar_expect_tx(wfull[0], o0.w_bytes);
-            bulk_g2s(smem_u32(wst[0]), P.wblob + o0.w_off, o0.w_bytes, wfull[0]);
+        if (n_chunks_total > 0 && leader) {
+            mbar_expect_tx(wfull[0], P.opsv[0].w_bytes);
+            bulk_g2s(smem_u32(wst[0]), P.wblob + P.opsv[0].w_off, P.opsv[0].w_bytes, wfull[0]);
         }
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const bool tr = P.trace && blockIdx.x == 0 && tile == (int)gridDim.x;
             for (int oi = 0; oi < n_ops; ++oi, ++chunk) {
-                const SdfTcOp op = ops_s[oi];
+                const SdfTcOp& op = P.opsv[oi];
                 const int s = chunk & 1;
-                if (tr) P.trace[oi * 8 + 4] = clock64();
-                // prefetch the next chunk's weights into the other stage once its previous MMAs have retired
+                if (tr && leader) P.trace[oi * 8 + 4] = clock64();
+                // prefetch the next chunk's weights into the other stage once its previous MMAs have retired.  (Queuing this
+                // chunk's MMAs before the wait was measured slower, 151 vs 158 Mpts/s: the weights then arrive late.)
                 if ((uint64_t)chunk + 1 < n_chunks_total) {
-                    const SdfTcOp nx = ops_s[oi + 1 < n_ops ? oi + 1 : 0];
+                    const SdfTcOp& nx = P.opsv[oi + 1 < n_ops ? oi + 1 : 0];
                     const uint32_t c1 = chunk + 1;
                     mbar_wait(sfree[c1 & 1], ((c1 >> 1) & 1) ^ 1);
-                    mbar_expect_tx(wfull[c1 & 1], nx.w_bytes);
-                    bulk_g2s(smem_u32(wst[c1 & 1]), P.wblob + nx.w_off, nx.w_bytes, wfull[c1 & 1]);
+                    if (leader) {
+#if defined(TC_EXP_NO_TMA)
+                        mbar_expect_tx(wfull[c1 & 1], 16);
+                        bulk_g2s(smem_u32(wst[c1 & 1]), P.wblob + nx.w_off, 16, wfull[c1 & 1]);
+#else
+                        mbar_expect_tx(wfull[c1 & 1], nx.w_bytes);
+                        bulk_g2s(smem_u32(wst[c1 & 1]), P.wblob + nx.w_off, nx.w_bytes, wfull[c1 & 1]);
+#endif
+                    }
                 }
-                if (tr) P.trace[oi * 8 + 5] = clock64();
+                if (tr && leader) P.trace[oi * 8 + 5] = clock64();
                 mbar_wait(wfull[s], (chunk >> 1) & 1);
-                if (tr) P.trace[oi * 8 + 6] = clock64();
+                if (tr && leader) P.trace[oi * 8 + 6] = clock64();
                 mbar_wait(afull[s], (chunk >> 1) & 1);
-                if (tr) P.trace[oi * 8 + 7] = clock64();
+                if (tr && leader) P.trace[oi * 8 + 7] = clock64();
                 tc_fence_after();
                 // descriptors are built once per chunk; per MMA only the start-address field advances (+32 B = +2 units
                 // per K step of 8 tf32).  The issue loop is fully unrolled: a single thread issues ~6 instructions per MMA.
@@ -480,6 +517,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
                 const uint64_t ad_hi = make_desc(a_hi), ad_lo = make_desc(a_hi + TC_ASTAGE_BYTES / 2);
                 const uint64_t wd_hi = make_desc(w_hi), wd_lo = make_desc(w_hi + (uint32_t)op.n_total * 128u);
                 const uint32_t first_acc = op.first ? 0u : 1u;
+                if (elect_one()) {
 #pragma unroll 1
                 for (int pc = 0; pc < op.n_piece; ++pc) {
                     const uint32_t dcol = tmem_base + (uint32_t)op.d_col[pc];
@@ -489,12 +527,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
 #pragma unroll
                     for (int ks = 0; ks < TC_KC / 8; ++ks) {
                         tc_mma_tf32(dcol, ad_hi + 2 * ks, bh + 2 * ks, idesc, ks == 0 ? first_acc : 1u);
+#if !defined(TC_EXP_ONE_MMA)
                         tc_mma_tf32(dcol, ad_lo + 2 * ks, bh + 2 * ks, idesc, 1u);
                         tc_mma_tf32(dcol, ad_hi + 2 * ks, bl + 2 * ks, idesc, 1u);
+#endif
                     }
                 }
-                tc_commit(sfree[s]);
-                if (op.d_commit >= 0) tc_commit(dfull0 + 8 * op.d_commit);
+                    tc_commit(sfree[s]);
+                    if (op.d_commit >= 0) tc_commit(dfull0 + 8 * op.d_commit);
+                }
+                __syncwarp();
+
             }
         }
     }
