@@ -261,17 +261,20 @@ __device__ __forceinline__ void act_pair(int act, float w0, float a, float& h, f
 
 // write this thread's 16 features (column half `ch` of the 32-feature chunk) of its row into the A stage (hi | lo),
 // 128-byte-swizzled K-major layout: 8-row atoms of 1024 B, row = 128 B, 16-byte unit index XOR row-in-atom
-__device__ __forceinline__ void store_a16(unsigned char* a_stage, int row, int ch, const float* v) {
+// The tf32 hi / lo split is done by split_a16 BEFORE the producer waits for its stage to be free, so that only the
+// eight 16-byte stores remain between "stage free" and "stage full".
+__device__ __forceinline__ void split_a16(const float* v, float* hi, float* lo) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) { hi[e] = tf32_rna(v[e]); lo[e] = tf32_rna(v[e] - hi[e]); }
+}
+__device__ __forceinline__ void store_a16(unsigned char* a_stage, int row, int ch, const float* hi, const float* lo) {
     unsigned char* base = a_stage + (row >> 3) * 1024 + (row & 7) * 128;
     const int sw = row & 7;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const int unit = ((ch * 4 + q) ^ sw) * 16;
-        float hi[4], lo[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { hi[e] = tf32_rna(v[q * 4 + e]); lo[e] = tf32_rna(v[q * 4 + e] - hi[e]); }
-        *reinterpret_cast<float4*>(base + unit) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<float4*>(base + TC_ASTAGE_BYTES / 2 + unit) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<float4*>(base + unit) = make_float4(hi[q * 4], hi[q * 4 + 1], hi[q * 4 + 2], hi[q * 4 + 3]);
+        *reinterpret_cast<float4*>(base + TC_ASTAGE_BYTES / 2 + unit) = make_float4(lo[q * 4], lo[q * 4 + 1], lo[q * 4 + 2], lo[q * 4 + 3]);
     }
 }
 
@@ -417,11 +420,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
                     }
                     tc_fence_before();
                 }
+                float vhi[16], vlo[16];
+                split_a16(v, vhi, vlo);
                 if (tr) P.trace[oi * 8 + 1] = clock64();
                 mbar_wait_backoff(sfree[g], ((chunk >> 1) & 1) ^ 1);
                 if (tr) P.trace[oi * 8 + 2] = clock64();
 #if !defined(TC_EXP_NO_STORE)
-                store_a16(ast[g], row, ch, v);
+                store_a16(ast[g], row, ch, vhi, vlo);
 #endif
                 fence_async_smem();
                 mbar_arrive(afull[g]);
