@@ -213,6 +213,64 @@ def model_variants_case():
     print('model_variants: f range', np.abs(Ft).max(), np.abs(Fa).max())
 
 
+def refgen_case():
+    """Trajectories of the reference's own RefGen (sdf_nmpc/ref_gen.py) on random states / way-points for every yaw mode,
+    with and without stop-and-turn, plus joystick references."""
+    import copy
+    from sdf_nmpc.ref_gen import RefGen
+    from sdf_nmpc.utils.config import Config
+    from sdf_nmpc.utils.reference import Waypoint
+    from sdf_nmpc.utils.math import yaw2quat
+    cfg0 = Config('/root/reference/sdf_nmpc/config/default.yaml')
+    rng = np.random.default_rng(21)
+    out = {}
+    B, Wmax, N = 16, 4, cfg0.mpc.N
+    X0 = np.concatenate([rng.uniform(-2, 2, (B, 3)), np.zeros((B, 4)), rng.uniform(-1, 1, (B, 3))], 1)
+    X0[:, 3:7] = np.array([yaw2quat(y) for y in rng.uniform(-np.pi, np.pi, B)])
+    nw = rng.integers(1, Wmax + 1, B)
+    WP = X0[:, None, :3] + rng.uniform(-3, 3, (B, Wmax, 3))
+    WP[0, 0] = X0[0, :3] + np.array([0.03, 0.02, 0.0])          # closer than yaw_align_dmin
+    WP[1, 0] = X0[1, :3] + np.array([0.5, 0.2, 0.1]); nw[1] = 1  # shorter than vref: vref saturates
+    WP[2] = X0[2, None, :3] + np.cumsum(rng.uniform(0.2, 0.6, (Wmax, 3)), 0); nw[2] = Wmax   # ends inside the horizon
+    WQ = np.array([[yaw2quat(y) for y in row] for row in rng.uniform(-np.pi, np.pi, (B, Wmax))])
+    out.update(X0=X0, WP=WP, WQ=WQ, nw=nw)
+    for mode in ('align', 'ref', 'current', 'zero'):
+        for sat in (False, True):
+            cfg = copy.deepcopy(cfg0)
+            cfg.ref.yaw_mode = mode
+            cfg.ref.stop_and_turn.enable = sat
+            cfg.ref.align_yaw_offset = 0.1 if mode == 'align' else 0
+            P, Q, V, Wz = [], [], [], []
+            for b in range(B):
+                rg = RefGen(cfg)
+                rg.x0 = X0[b]
+                traj = rg.gen_ref_list_wps([Waypoint(WP[b, j], WQ[b, j]) for j in range(nw[b])])
+                traj = list(traj) + [traj[-1]] * (N + 1 - len(traj))        # stop-and-turn returns N entries
+                P.append([np.asarray(r.p, float) for r in traj[:N + 1]]); Q.append([np.asarray(r.q, float) for r in traj[:N + 1]])
+                V.append([np.asarray(r.v, float) for r in traj[:N + 1]]); Wz.append([float(r.wz) for r in traj[:N + 1]])
+            tag = f'{mode}_{int(sat)}'
+            out.update({f'P_{tag}': np.array(P), f'Q_{tag}': np.array(Q), f'V_{tag}': np.array(V), f'Wz_{tag}': np.array(Wz)})
+    VW = rng.uniform(-1, 1, (B, 4)); VW[0, :2] = 0.01
+    out['VW'] = VW
+    for mode in ('align', 'zero'):
+        cfg = copy.deepcopy(cfg0); cfg.ref.yaw_mode = mode
+        P, Q, V, Wz = [], [], [], []
+        for b in range(B):
+            rg = RefGen(cfg); rg.x0 = X0[b]
+            traj = rg.gen_ref_joystick(VW[b])
+            P.append([np.asarray(r.p, float) for r in traj]); Q.append([np.asarray(r.q, float) for r in traj])
+            V.append([np.asarray(r.v, float) for r in traj]); Wz.append([float(r.wz) for r in traj])
+        out.update({f'JP_{mode}': np.array(P), f'JQ_{mode}': np.array(Q), f'JV_{mode}': np.array(V), f'JWz_{mode}': np.array(Wz)})
+    rg = RefGen(cfg0)
+    hov = []
+    for b in range(B):
+        rg.x0 = X0[b]; r = rg.from_x0()[0]
+        hov.append(np.concatenate([r.p, r.q, r.v, [r.wz]]))
+    out['HOVER'] = np.array(hov)
+    np.savez_compressed(os.path.join(HERE, 'refgen.npz'), **out)
+    print('refgen: cases', len(out))
+
+
 if __name__ == '__main__':
     torch.manual_seed(0)
     torch.set_num_threads(4)
@@ -225,4 +283,5 @@ if __name__ == '__main__':
              act='softplus', w0=1.0, size_latent=32)
     model_att_case()
     model_variants_case()
+    refgen_case()
     encoder_case()

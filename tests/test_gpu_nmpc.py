@@ -232,3 +232,34 @@ def test_encoder_in_the_loop(cuda_device):
     xb, ub = rti.init_traj(prob['x0'], ocfg)
     _, _, out = rti.rti_step(net, xb, ub, prob2, ocfg)
     assert np.abs(mpc2.get_u().cpu().numpy() - out['u0']).max() <= U_TOL
+
+
+def test_batched_refgen_feeds_controller(cuda_device):
+    """Reference generation on the device (ref_gen.BatchedRefGen) -> set_ref_arrays -> RTI steps: way-point following
+    moves every instance towards its first way-point."""
+    import torch
+    from sdf_nmpc_b200 import synth
+    from sdf_nmpc_b200.config import Config
+    from sdf_nmpc_b200.nmpc import BatchedNmpc
+    from sdf_nmpc_b200.ref_gen import BatchedRefGen
+    B = 16
+    cfg = Config()
+    net = synth.make_sdf_net(seed=0, **synth.ARCH_B, calibrated=True)
+    w = synth.nmpc_instances(B)
+    mpc = BatchedNmpc(cfg, net, B, cuda_device)
+    mpc.set_sdf_flag(0.0)                                    # obstacle-free: pure reference tracking
+    mpc.set_latent(w['latent'], w['W_p_Bo'], w['W_R_Bo'])
+    x = torch.from_numpy(w['x0']).cuda()
+    x[:, 7:] = 0
+    goal = x[:, :3] + torch.tensor([4.0, 1.0, 0.5], dtype=torch.float64, device='cuda')
+    rg = BatchedRefGen(cfg)
+    d0 = torch.linalg.norm(goal - x[:, :3], dim=1)
+    for step in range(15):
+        rg.set_x0(x)
+        tr = rg.gen_ref_list_wps(goal[:, None, :])
+        mpc.set_ref_arrays(*tr.arrays('att', cfg.mpc.weights.set_const_off))
+        mpc.set_x0(x)
+        assert int(mpc.solve().max().item()) == 0
+        x = mpc.plant_step(x.clone(), mpc.get_u(), 0.075)
+    d1 = torch.linalg.norm(goal - x[:, :3], dim=1)
+    assert torch.isfinite(x).all() and bool((d1 < d0 - 0.5).all()), (d0, d1)
