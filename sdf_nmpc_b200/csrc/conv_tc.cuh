@@ -1,0 +1,198 @@
+// Encoder convolutions on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// Implicit GEMM of one Conv2d(+folded BatchNorm)+residual+activation layer of the depth encoder
+// (sdf_nmpc/network/resnet.py:32-56, network/vae.py:19-38):   D[pixel][cout] = sum_k A[pixel][k] * W[cout][k],
+// k = (ci, ky, kx), M = 128 output pixels per tile, N = NT output channels per tile (<= 256), K in chunks of 32.
+// fp32-grade arithmetic from the tf32 hi / lo split (3 MMAs per product, fp32 accumulation in TMEM), as in the SDF kernel.
+//
+// One persistent CTA per SM, 17 warps:
+//   * 16 producer warps in two ping-pong groups: thread <-> (pixel row, 16 of the chunk's 32 k values); they gather the
+//     im2col patch values from the NCHW activation (lanes = consecutive pixels: coalesced for every k), split them into
+//     tf32 hi | lo and store the A chunk in the 128-byte-swizzled K-major UMMA layout; after the K loop the same warps
+//     drain the accumulator (tcgen05.ld) through bias + residual + activation to the NCHW output (again pixel-coalesced).
+//   * 1 issuer warp: streams the matching weight chunk (pre-split hi | lo and pre-laid-out on the host, one cp.async.bulk
+//     per chunk) through a 2-stage ring and issues the tcgen05.mma from one elected lane on uniform operands.
+// The accumulator is double-buffered in TMEM (2 x 256 columns), so the MMAs of the next work item start while the
+// previous item's accumulator is still being drained by the slower producer group.
+#pragma once
+#include "tc_common.cuh"
+
+namespace sdfnmpc {
+
+constexpr int CV_PROD_WARPS = 16;
+constexpr int CV_GROUP_THREADS = CV_PROD_WARPS * 32 / 2;
+constexpr int CV_PROD_THREADS = CV_PROD_WARPS * 32;
+constexpr int CV_THREADS = CV_PROD_THREADS + 32;
+constexpr int CV_WSTAGE_BYTES = 256 * TC_KC * 4 * 2;     // up to 256 output channels, hi | lo
+constexpr int CV_SMEM_BYTES = 2 * CV_WSTAGE_BYTES + 2 * TC_ASTAGE_BYTES + 256 + 1024;
+
+enum { CV_ACT_NONE = 0, CV_ACT_RELU = 1, CV_ACT_ELU = 2 };
+
+struct ConvTcParams {
+    int Cin, Hin, Win, Cout, Hout, Wout, stride, pad;
+    long long npix;               // B * Hout * Wout
+    int NT;                       // output channels per N tile: 64, 128, 192 or 256 (Cout % NT == 0)
+    int n_ntiles, n_kchunks;
+    const float* in;              // [B][Cin][Hin][Win]
+    const unsigned char* wblob;   // [n_ntiles][n_kchunks][hi: NT x 128 B swizzled | lo]
+    const int4* ktab;             // [n_kchunks * 32]: {(ci*Hin + ky)*Win + kx, ky, kx, k < K}
+    const float* bias;            // [Cout] (folded BatchNorm shift)
+    const float* resid;           // [B][Cout][Hout][Wout] or null
+    int act;
+    float* out;                   // [B][Cout][Hout][Wout]
+};
+
+__global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcParams P) {
+    using namespace tc;
+    extern __shared__ __align__(1024) unsigned char cv_smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)cv_smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char* wst[2] = {smem, smem + CV_WSTAGE_BYTES};
+    unsigned char* ast[2] = {smem + 2 * CV_WSTAGE_BYTES, smem + 2 * CV_WSTAGE_BYTES + TC_ASTAGE_BYTES};
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * CV_WSTAGE_BYTES + 2 * TC_ASTAGE_BYTES);   // 0-1 wfull, 2-3 afull, 4-5 sfree, 6 dfull
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    const uint32_t wfull[2] = {smem_u32(bars + 0), smem_u32(bars + 1)};
+    const uint32_t afull[2] = {smem_u32(bars + 2), smem_u32(bars + 3)};
+    const uint32_t sfree[2] = {smem_u32(bars + 4), smem_u32(bars + 5)};
+    const uint32_t dfull = smem_u32(bars + 6);
+
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    if (tid == 0) {
+        mbar_init(wfull[0], 1); mbar_init(wfull[1], 1);
+        mbar_init(afull[0], CV_GROUP_THREADS); mbar_init(afull[1], CV_GROUP_THREADS);
+        mbar_init(sfree[0], 1); mbar_init(sfree[1], 1);
+        mbar_init(dfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == CV_PROD_WARPS) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+    const int n_ptiles = (int)((P.npix + TC_TM - 1) / TC_TM);
+    const int n_items = n_ptiles * P.n_ntiles;                       // item = pixel tile * n_ntiles + n tile
+    const int nk = P.n_kchunks;
+    const int hw = P.Hout * P.Wout;
+    uint32_t chunk = 0;                                              // stage = chunk & 1, phase = (chunk >> 1) & 1
+
+    if (warp < CV_PROD_WARPS) {
+        const int g = warp >> 3, wq = warp & 7, lq = wq & 3, ch = wq >> 2;
+        const int row = lq * 32 + (tid & 31);
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(lq * 32) << 16);
+        uint32_t item_it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_it) {
+            const int pt = item / P.n_ntiles, nt = item - pt * P.n_ntiles;
+            const long long pix = (long long)pt * TC_TM + row;
+            const bool pvalid = pix < P.npix;
+            int pb = 0, oy = 0, ox = 0, r = 0;
+            if (pvalid) {
+                pb = (int)(pix / hw);
+                r = (int)(pix - (long long)pb * hw);
+                oy = r / P.Wout;
+                ox = r - oy * P.Wout;
+            }
+            const int iy0 = oy * P.stride - P.pad, ix0 = ox * P.stride - P.pad;
+            const float* inb = P.in + (size_t)pb * P.Cin * P.Hin * P.Win + (long long)iy0 * P.Win + ix0;
+            for (int kc = 0; kc < nk; ++kc, ++chunk) {
+                if ((int)(chunk & 1) != g) continue;
+                const int4* kt = P.ktab + kc * TC_KC + ch * 16;
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int4 t = __ldg(kt + i);                    // same entry for the whole warp: one broadcast load
+                    const int iy = iy0 + t.y, ix = ix0 + t.z;
+                    const bool ok = pvalid && t.w && iy >= 0 && iy < P.Hin && ix >= 0 && ix < P.Win;
+                    v[i] = ok ? __ldg(inb + t.x) : 0.f;
+                }
+                float vhi[16], vlo[16];
+                split_a16(v, vhi, vlo);
+                mbar_wait_backoff(sfree[g], ((chunk >> 1) & 1) ^ 1);
+                store_a16(ast[g], row, ch, vhi, vlo);
+                fence_async_smem();
+                mbar_arrive(afull[g]);
+            }
+            // ---- epilogue: accumulator -> bias, residual, activation -> NCHW output.  The four (group, half) combinations
+            // of a row take a quarter of the NT columns each. ----
+            mbar_wait_backoff(dfull, item_it & 1);
+            tc_fence_after();
+            const uint32_t acc = lane_addr + (item_it & 1) * 256u;
+            const int ncol = P.NT >> 2, c_begin = (g * 2 + ch) * ncol;
+            for (int c0 = c_begin; c0 < c_begin + ncol; c0 += 16) {
+                float v[16];
+                tc_ld16(acc + c0, v);
+                if (pvalid) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const int co = nt * P.NT + c0 + e;
+                        const size_t o = ((size_t)pb * P.Cout + co) * hw + r;
+                        float val = v[e] + __ldg(P.bias + co);
+                        if (P.resid) val += __ldg(P.resid + o);
+                        if (P.act == CV_ACT_RELU) val = fmaxf(val, 0.f);
+                        else if (P.act == CV_ACT_ELU) val = val > 0.f ? val : expm1f(val);
+                        P.out[o] = val;
+                    }
+                }
+            }
+            tc_fence_before();
+        }
+    } else {
+        // ============================== weight streamer + MMA issuer ==============================
+        const uint32_t leader = elect_one();
+        const size_t wchunk_bytes = (size_t)P.NT * TC_KC * 4 * 2;
+        const int my_items = blockIdx.x < n_items ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+        const uint64_t n_chunks_total = (uint64_t)my_items * nk;
+        const uint32_t idesc = make_idesc(P.NT);
+        if (n_chunks_total > 0 && leader) {
+            const int nt0 = (int)blockIdx.x % P.n_ntiles;
+            mbar_expect_tx(wfull[0], (uint32_t)wchunk_bytes);
+            bulk_g2s(smem_u32(wst[0]), P.wblob + (size_t)nt0 * nk * wchunk_bytes, (uint32_t)wchunk_bytes, wfull[0]);
+        }
+        uint32_t item_it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_it) {
+            const int nt = item % P.n_ntiles;
+            const uint32_t dcol = tmem_base + (item_it & 1) * 256u;
+            for (int kc = 0; kc < nk; ++kc, ++chunk) {
+                const int s = chunk & 1;
+                // prefetch the next chunk's weights (possibly the first chunk of the next item) into the other stage
+                if ((uint64_t)chunk + 1 < n_chunks_total) {
+                    const bool same = kc + 1 < nk;
+                    const int nnt = same ? nt : (item + (int)gridDim.x) % P.n_ntiles;
+                    const int nkc = same ? kc + 1 : 0;
+                    const uint32_t c1 = chunk + 1;
+                    mbar_wait(sfree[c1 & 1], ((c1 >> 1) & 1) ^ 1);
+                    if (leader) {
+                        mbar_expect_tx(wfull[c1 & 1], (uint32_t)wchunk_bytes);
+                        bulk_g2s(smem_u32(wst[c1 & 1]), P.wblob + ((size_t)nnt * nk + nkc) * wchunk_bytes, (uint32_t)wchunk_bytes, wfull[c1 & 1]);
+                    }
+                }
+                mbar_wait(wfull[s], (chunk >> 1) & 1);
+                mbar_wait(afull[s], (chunk >> 1) & 1);
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(ast[s]), w_hi = smem_u32(wst[s]);
+                const uint64_t ad_hi = make_desc(a_hi), ad_lo = make_desc(a_hi + TC_ASTAGE_BYTES / 2);
+                const uint64_t wd_hi = make_desc(w_hi), wd_lo = make_desc(w_hi + (uint32_t)P.NT * 128u);
+                if (elect_one()) {
+#pragma unroll
+                    for (int ks = 0; ks < TC_KC / 8; ++ks) {
+                        tc_mma_tf32(dcol, ad_hi + 2 * ks, wd_hi + 2 * ks, idesc, (kc == 0 && ks == 0) ? 0u : 1u);
+                        tc_mma_tf32(dcol, ad_lo + 2 * ks, wd_hi + 2 * ks, idesc, 1u);
+                        tc_mma_tf32(dcol, ad_hi + 2 * ks, wd_lo + 2 * ks, idesc, 1u);
+                    }
+                    tc_commit(sfree[s]);
+                    if (kc == nk - 1) tc_commit(dfull);
+                }
+                __syncwarp();
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == CV_PROD_WARPS) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+}  // namespace sdfnmpc

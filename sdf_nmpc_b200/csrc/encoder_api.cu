@@ -9,8 +9,11 @@
 // Convolution = implicit GEMM: M = Cout, N = B*OH*OW output pixels, K = Cin*KH*KW.  One CTA computes a
 // 64 x 64 tile with a 16-deep shared-memory K pipeline; each of the 256 threads owns a 4x4 register tile.
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 #include "handles.h"
+#include "conv_tc.cuh"
 
 using namespace sdfnmpc;
 
@@ -181,7 +184,20 @@ struct Layer {
     ConvShape s;
     int ks;
     float *w = nullptr, *b = nullptr;
+    // tensor-core form (conv_tc.cuh): weight chunks [n tile][k chunk][hi | lo] in the swizzled UMMA layout + im2col table
+    unsigned char* wblob_tc = nullptr;
+    int4* ktab = nullptr;
+    int NT = 0, n_ntiles = 0, n_kchunks = 0;
 };
+
+inline float tf32_rna_host(float x) {
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    u = (u + 0x1000u) & 0xFFFFE000u;       // round to nearest, ties away (cvt.rna.tf32.f32)
+    float r;
+    memcpy(&r, &u, 4);
+    return r;
+}
 
 }  // namespace
 
@@ -220,7 +236,43 @@ static int make_layer(Layer& L, const float* w, const float* const bn[4], const 
         Bv[co] = shift;
     }
     if (int rc = upload(&L.w, W)) return rc;
-    return upload(&L.b, Bv);
+    if (int rc = upload(&L.b, Bv)) return rc;
+    // ---- tensor-core operands (layers with Cout a multiple of 64; conv0 with its fused preprocessing stays on the
+    // CUDA-core kernel) ----
+    const int NT = L.s.Cout <= 256 ? L.s.Cout : 256;
+    if (L.s.Cin < 8 || NT % 64 || L.s.Cout % NT) return 0;
+    const int nk = (K + TC_KC - 1) / TC_KC;
+    L.NT = NT; L.n_ntiles = L.s.Cout / NT; L.n_kchunks = nk;
+    std::vector<float> blob((size_t)L.n_ntiles * nk * NT * TC_KC * 2, 0.f);
+    for (int nt = 0; nt < L.n_ntiles; ++nt)
+        for (int kc = 0; kc < nk; ++kc) {
+            const size_t base = ((size_t)nt * nk + kc) * NT * TC_KC * 2;
+            for (int n = 0; n < NT; ++n)
+                for (int k = 0; k < TC_KC; ++k) {
+                    const int kk = kc * TC_KC + k;
+                    const float v = kk < K ? W[(size_t)(nt * NT + n) * K + kk] : 0.f;
+                    const float hi = tf32_rna_host(v), lo = tf32_rna_host(v - hi);
+                    // 128-byte-swizzled K-major: 8-row atoms of 1024 B, row = 32 floats, 16-byte unit index XOR row-in-atom
+                    const size_t idx = (size_t)(n >> 3) * 256 + (size_t)(n & 7) * 32 + (size_t)(((k >> 2) ^ (n & 7)) * 4) + (k & 3);
+                    blob[base + idx] = hi;
+                    blob[base + (size_t)NT * TC_KC + idx] = lo;
+                }
+        }
+    float* dblob = nullptr;
+    if (int rc = upload(&dblob, blob)) return rc;
+    L.wblob_tc = reinterpret_cast<unsigned char*>(dblob);
+    std::vector<int4> kt((size_t)nk * TC_KC);
+    for (int k = 0; k < nk * TC_KC; ++k) {
+        int4 t = make_int4(0, 0, 0, 0);
+        if (k < K) {
+            const int ci = k / (L.ks * L.ks), rem = k % (L.ks * L.ks), ky = rem / L.ks, kx = rem % L.ks;
+            t = make_int4((ci * L.s.Hin + ky) * L.s.Win + kx, ky, kx, 1);
+        }
+        kt[k] = t;
+    }
+    SDF_CUDA_CHECK(cudaMalloc(&L.ktab, kt.size() * sizeof(int4)));
+    SDF_CUDA_CHECK(cudaMemcpy(L.ktab, kt.data(), kt.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    return 0;
 }
 
 extern "C" int sdfnmpc_encoder_create(sdfnmpc_encoder_t* out, const sdfnmpc_encoder_desc* d, const sdfnmpc_encoder_weights* w) {
@@ -278,7 +330,7 @@ extern "C" int sdfnmpc_encoder_destroy(sdfnmpc_encoder_t h) {
     if (!h) return 0;
     Layer* ls[] = {&h->conv0, &h->c1[0], &h->c1[1], &h->c1[2], &h->c1[3], &h->c2[0], &h->c2[1], &h->c2[2], &h->c2[3],
                    &h->sc[0], &h->sc[1], &h->sc[2], &h->sc[3]};
-    for (Layer* l : ls) { cudaFree(l->w); cudaFree(l->b); }
+    for (Layer* l : ls) { cudaFree(l->w); cudaFree(l->b); cudaFree(l->wblob_tc); cudaFree(l->ktab); }
     cudaFree(h->mean_w); cudaFree(h->mean_b); cudaFree(h->yz);
     for (float* b : h->buf) cudaFree(b);
     cudaFree(h->h_img); cudaFree(h->h_lat);
@@ -286,9 +338,46 @@ extern "C" int sdfnmpc_encoder_destroy(sdfnmpc_encoder_t h) {
     return 0;
 }
 
+// SDFNMPC_ENC_IMPL=ffma forces the CUDA-core kernels (A/B runs and the cross-check in tests/test_gpu_encoder.py)
+static bool enc_use_tc() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SDFNMPC_ENC_IMPL");
+        v = (e && !strcmp(e, "ffma")) ? 0 : 1;
+    }
+    return v == 1;
+}
+
+static int launch_conv_tc(const Layer& L, int B, const float* in, const float* resid, int act, float* out, cudaStream_t st) {
+    static int sm_count = 0;
+    static bool attr_set = false;
+    if (!sm_count) {
+        int dev = 0;
+        SDF_CUDA_CHECK(cudaGetDevice(&dev));
+        SDF_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    if (!attr_set) {
+        SDF_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM_BYTES));
+        attr_set = true;
+    }
+    ConvTcParams P;
+    P.Cin = L.s.Cin; P.Hin = L.s.Hin; P.Win = L.s.Win; P.Cout = L.s.Cout; P.Hout = L.s.Hout; P.Wout = L.s.Wout;
+    P.stride = L.s.stride; P.pad = L.s.pad;
+    P.npix = (long long)B * L.s.Hout * L.s.Wout;
+    P.NT = L.NT; P.n_ntiles = L.n_ntiles; P.n_kchunks = L.n_kchunks;
+    P.in = in; P.wblob = L.wblob_tc; P.ktab = L.ktab; P.bias = L.b; P.resid = resid; P.act = act; P.out = out;
+    const long long n_items = (P.npix + TC_TM - 1) / TC_TM * L.n_ntiles;
+    const int grid = (int)(n_items < sm_count ? n_items : sm_count);
+    conv_tc_kernel<<<grid, CV_THREADS, CV_SMEM_BYTES, st>>>(P);
+    count_launch();
+    SDF_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
 template <int KS, bool PRE>
 static int launch_conv(const Layer& L, int B, const float* in, const float* resid, int act, float* out, cudaStream_t st,
                        const float* yz = nullptr, float dmax = 1.f, int clip = 0, int d2r = 0) {
+    if (!PRE && L.wblob_tc && enc_use_tc()) return launch_conv_tc(L, B, in, resid, act, out, st);
     const long long npix = (long long)B * L.s.Hout * L.s.Wout;
     dim3 grid((unsigned)((npix + TPX - 1) / TPX), (L.s.Cout + TCO - 1) / TCO);
     conv_igemm_kernel<KS, PRE><<<grid, 256, 0, st>>>(L.s, B, in, L.w, L.b, resid, act, out, yz, dmax, clip, d2r);
