@@ -240,6 +240,8 @@ static int make_layer(Layer& L, const float* w, const float* const bn[4], const 
     // ---- tensor-core operands (layers with Cout a multiple of 64; conv0 with its fused preprocessing stays on the
     // CUDA-core kernel) ----
     const int NT = L.s.Cout <= 256 ? L.s.Cout : 256;
+    // (conv0 - Cin = 1, K = 49: two chunks per tile - was measured on this kernel too: 2.0 ms vs 1.14 ms at B = 64; a
+    // tile that short is all pipeline fill / epilogue, so it stays on the CUDA cores)
     if (L.s.Cin < 8 || NT % 64 || L.s.Cout % NT) return 0;
     const int nk = (K + TC_KC - 1) / TC_KC;
     L.NT = NT; L.n_ntiles = L.s.Cout / NT; L.n_kchunks = nk;

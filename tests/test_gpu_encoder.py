@@ -61,3 +61,29 @@ def test_encoder_vs_oracle_random_weights(cuda_device):
     lat = vae.encode()
     ref = OE.encode(net, OE.preprocess(frames))
     assert relmax(lat, ref) <= LAT_TOL, relmax(lat, ref)
+
+
+def test_tensor_core_and_cuda_core_convolutions_agree(cuda_device):
+    """The tcgen05 convolution path (default) and the CUDA-core path (SDFNMPC_ENC_IMPL=ffma, read once per process, hence
+    the subprocess) produce the same latents within the parity tolerance, for a batch that leaves partial pixel tiles."""
+    import subprocess
+    import sys
+    import tempfile
+    from conftest import ROOT
+    from sdf_nmpc_b200 import synth
+    from sdf_nmpc_b200.vae import VaeWrapper
+    net = synth.make_encoder_net(seed=7)
+    frames = np.stack([synth.depth_frame(seed=60 + i) for i in range(3)])
+    vae = VaeWrapper(_cfg(False), net, max_batch=3, device=cuda_device)
+    vae.set_img(frames)
+    lat_tc = vae.encode()
+    out = os.path.join(tempfile.mkdtemp(), 'lat.npy')
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests');"
+            "from test_gpu_encoder import _cfg; from sdf_nmpc_b200 import synth; from sdf_nmpc_b200.vae import VaeWrapper;"
+            "frames = np.stack([synth.depth_frame(seed=60 + i) for i in range(3)]);"
+            "vae = VaeWrapper(_cfg(False), synth.make_encoder_net(seed=7), max_batch=3); vae.set_img(frames);"
+            "np.save(%r, vae.encode())") % (ROOT, ROOT, out)
+    subprocess.run([sys.executable, '-c', code], check=True, env=dict(os.environ, SDFNMPC_ENC_IMPL='ffma'))
+    lat_ffma = np.load(out)
+    assert relmax(lat_tc, lat_ffma) <= LAT_TOL, relmax(lat_tc, lat_ffma)
+    assert not np.array_equal(lat_tc, lat_ffma)        # the two paths are really different code
