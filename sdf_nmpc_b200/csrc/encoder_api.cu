@@ -141,6 +141,107 @@ __global__ void maxpool3s2_kernel(int C, int Hin, int Win, int Hout, int Wout, l
     out[gid] = m;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// First layer fused: preprocessing -> Conv2d(1, 64, 7, stride 2, pad 3) -> +bias -> ELU -> MaxPool2d(3, 2, 1)
+// (network/vae.py:20-22).  Direct convolution on the CUDA cores: with Cin = 1 the GEMM depth is only 49, too short for the
+// tensor-core pipeline (measured), and the 530 MB conv0 activation never goes to HBM.  ELU is monotonic, so it (and the
+// bias) is applied after the max.
+// One CTA = 8 x 16 pooled pixels x 64 channels of one frame: conv region 17 x 36 (33 needed), input patch 39 x 77 in smem.
+// A thread computes 4 adjacent conv pixels x 16 channels: per kernel row 13 patch values and 7 x 16 weights feed 448 FMAs.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int C0_PH = 8, C0_PW = 16, C0_CR = 2 * C0_PH + 1, C0_CC = 36, C0_IR = 2 * C0_CR + 5, C0_IC = 2 * C0_CC + 5;
+constexpr int C0_THREADS = 320, C0_CH = 64, C0_CPR = 32;     // channels per round
+constexpr int C0_PATCH_FLOATS = (C0_IR * C0_IC + 3) / 4 * 4;      // keeps the float4 regions behind it 16-byte aligned
+constexpr int C0_SMEM_FLOATS = C0_PATCH_FLOATS + 49 * C0_CH + C0_CPR * C0_CR * C0_CC;
+
+__global__ void __launch_bounds__(C0_THREADS, 2)
+conv0_pool_kernel(int Hin, int Win, int Hc, int Wc, int Hp, int Wp, const float* __restrict__ img, const float* __restrict__ w /*[64][49]*/,
+                  const float* __restrict__ bias, const float* __restrict__ yz, float dmax, int clip_dist, int depth2range,
+                  float* __restrict__ out /*[B][64][Hp][Wp]*/) {
+    extern __shared__ __align__(16) float c0sm[];
+    float* patch = c0sm;                               // [C0_IR][C0_IC]
+    float* wsm = patch + C0_PATCH_FLOATS;              // [49][64]
+    float* csm = wsm + 49 * C0_CH;                     // [32][C0_CR][C0_CC]
+    const int b = blockIdx.z, py0 = blockIdx.y * C0_PH, px0 = blockIdx.x * C0_PW;
+    const int cy0 = 2 * py0 - 1, cx0 = 2 * px0 - 1;    // first conv row / col of the region
+    const int iy0 = 2 * cy0 - 3, ix0 = 2 * cx0 - 3;    // first input row / col of the patch
+    const float* im = img + (size_t)b * Hin * Win;
+    for (int i = threadIdx.x; i < C0_IR * C0_IC; i += C0_THREADS) {
+        const int r = i / C0_IC, c = i - r * C0_IC, iy = iy0 + r, ix = ix0 + c;
+        float v = 0.f;
+        if (iy >= 0 && iy < Hin && ix >= 0 && ix < Win) {
+            v = __ldg(im + (size_t)iy * Win + ix);
+            if (clip_dist) v = fminf(fmaxf(v / dmax, 0.f), 1.f);
+            if (depth2range) v = fminf(fmaxf(v * __ldg(yz + iy * Win + ix), 0.f), 1.f);
+        }
+        patch[i] = v;
+    }
+    for (int i = threadIdx.x; i < 49 * C0_CH; i += C0_THREADS) {
+        const int tap = i / C0_CH, c = i - tap * C0_CH;
+        wsm[i] = __ldg(w + c * 49 + tap);
+    }
+    __syncthreads();
+    constexpr int TASKS = C0_CR * (C0_CC / 4);          // (conv row, group of 4 conv columns) = 153
+    const int t = threadIdx.x;
+    const bool active = t < 2 * TASKS;
+    const int cgl = active ? t / TASKS : 0, rem = active ? t - cgl * TASKS : 0, cr = rem / (C0_CC / 4), cgp = rem - cr * (C0_CC / 4);
+    for (int round = 0; round < 2; ++round) {
+        if (active) {
+            const int cbase = round * C0_CPR + cgl * 16;
+            float acc[4][16];
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+#pragma unroll
+                for (int c = 0; c < 16; ++c) acc[p][c] = 0.f;
+#pragma unroll 1
+            for (int ky = 0; ky < 7; ++ky) {
+                float seg[13];
+                const float* pr = patch + (2 * cr + ky) * C0_IC + 8 * cgp;
+#pragma unroll
+                for (int i = 0; i < 13; ++i) seg[i] = pr[i];
+#pragma unroll
+                for (int kx = 0; kx < 7; ++kx) {
+                    const float4* wp = reinterpret_cast<const float4*>(wsm + (ky * 7 + kx) * C0_CH + cbase);
+                    const float4 w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
+                    const float wv[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        const float x = seg[2 * p + kx];
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) acc[p][c] = fmaf(x, wv[c], acc[p][c]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 16; ++c)
+                *reinterpret_cast<float4*>(csm + ((cgl * 16 + c) * C0_CR + cr) * C0_CC + 4 * cgp) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < C0_CPR * C0_PH * C0_PW; i += C0_THREADS) {
+            const int c = i / (C0_PH * C0_PW), q = i - c * (C0_PH * C0_PW), pyl = q / C0_PW, pxl = q - pyl * C0_PW;
+            const int py = py0 + pyl, px = px0 + pxl;
+            if (py >= Hp || px >= Wp) continue;
+            float m = -INFINITY;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const int cy = cy0 + 2 * pyl + ky;
+                if (cy < 0 || cy >= Hc) continue;
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int cx = cx0 + 2 * pxl + kx;
+                    if (cx < 0 || cx >= Wc) continue;
+                    m = fmaxf(m, csm[(c * C0_CR + 2 * pyl + ky) * C0_CC + 2 * pxl + kx]);
+                }
+            }
+            const int cglob = round * C0_CPR + c;
+            const float v = m + __ldg(bias + cglob);
+            out[(((size_t)b * C0_CH + cglob) * Hp + py) * Wp + px] = v > 0.f ? v : expm1f(v);
+        }
+        __syncthreads();
+    }
+}
+
 // AdaptiveAvgPool2d((2,2)) + Flatten + Linear(4C -> L); one CTA per frame
 __global__ void __launch_bounds__(256)
 pool_linear_kernel(int C, int H, int W, int L, const float* __restrict__ feat, const float* __restrict__ mw,
@@ -392,10 +493,24 @@ extern "C" int sdfnmpc_encoder_encode(sdfnmpc_encoder_t h, const float* imgs, in
     if (!h || !imgs || !latents || B < 1 || B > h->desc.max_batch) return SDFNMPC_E_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     float *a = h->buf[0], *b = h->buf[1], *c = h->buf[2];
-    int rc = launch_conv<7, true>(h->conv0, B, imgs, nullptr, ENC_ACT_ELU, a, st, h->yz, h->desc.dmax_scale,
+    int rc = 0;
+    if (enc_use_tc()) {
+        // fused preprocessing + conv0 + ELU + max-pool (the CUDA-core reference path below keeps the separate kernels)
+        static bool attr_set = false;
+        if (!attr_set) {
+            SDF_CUDA_CHECK(cudaFuncSetAttribute(conv0_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C0_SMEM_FLOATS * (int)sizeof(float)));
+            attr_set = true;
+        }
+        dim3 grid((h->Wp + C0_PW - 1) / C0_PW, (h->Hp + C0_PH - 1) / C0_PH, B);
+        conv0_pool_kernel<<<grid, C0_THREADS, C0_SMEM_FLOATS * sizeof(float), st>>>(
+            h->desc.height, h->desc.width, h->conv0.s.Hout, h->conv0.s.Wout, h->Hp, h->Wp, imgs, h->conv0.w, h->conv0.b, h->yz,
+            h->desc.dmax_scale, h->desc.is_normalized ? 0 : 1, h->desc.is_depth ? 1 : 0, b);
+        count_launch();
+        SDF_CUDA_CHECK(cudaGetLastError());
+    } else {
+        rc = launch_conv<7, true>(h->conv0, B, imgs, nullptr, ENC_ACT_ELU, a, st, h->yz, h->desc.dmax_scale,
                                   h->desc.is_normalized ? 0 : 1, h->desc.is_depth ? 1 : 0);
-    if (rc) return rc;
-    {
+        if (rc) return rc;
         const long long total = (long long)B * 64 * h->Hp * h->Wp;
         maxpool3s2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(64, h->conv0.s.Hout, h->conv0.s.Wout, h->Hp, h->Wp, total, a, b);
         count_launch();
