@@ -259,9 +259,10 @@ def run_ours(args, rank, local_rank, world):
     if os.path.exists(tr_path):
         roof['traffic'] = json.load(open(tr_path)).get(dom, {}).get('dram_bytes_per_launch')
     # secondary metric of BASELINE.json (configs[1]): fused SDF value+gradient, fixed latent, 1e4..1e8 points
-    sweep = {}
+    sweep, enc_sweep = {}, {}
     if world == 1 and not args.no_sweep:
         sweep = sdf_microbench(net, peaks)
+        enc_sweep = encoder_microbench(peaks)
     cpu_v, cpu_info = (None, None)
     if world == 1 and not args.no_cpu:
         cpu_v, cpu_info = cpu_oracle_throughput(8, 2, os.cpu_count() or 1)
@@ -280,6 +281,7 @@ def run_ours(args, rank, local_rank, world):
                 status_ok=status_ok, instances=int(allrec.shape[0]), qp_iters_mean=qp_it_mean)
     if sweep:
         line['sdf_microbench'] = sweep
+        line['encoder_microbench'] = enc_sweep
     if cpu_v is not None:
         line['cpu_baseline'] = dict(value=cpu_v, unit=UNIT, cores=cpu_info['workers'], kind='port',
                                     sample=f"{cpu_info['workers']} processes x 8 instances x 2 closed-loop RTI steps of the same workload "
@@ -316,6 +318,41 @@ def sdf_microbench(net, peaks):
         del pts, sdf, grad
     out['note'] = ('algorithmic FLOPs (615168 per point) counted once; the hidden-layer GEMMs run as 3 TF32 tcgen05 MMAs each '
                    '(2-way split for fp32 parity), so at most 1/6 of the bf16 peak is reachable by this accounting')
+    return out
+
+
+ENC_FLOP_FRAME = 4.34e9          # conv + linear FLOPs of one 270 x 480 frame
+
+
+def encoder_microbench(peaks):
+    """Part (4) of the path (configs[4] data flow): batched depth-frame encoding, device-resident frames [B,270,480] fp32
+    in, latents [B,128] out; CUDA events around 5 launches after 2 warm-ups.  The 3x3 / 1x1 layers run as 3xTF32 tcgen05
+    implicit GEMMs, conv0 + ELU + max-pool as one CUDA-core kernel."""
+    import numpy as np
+    import torch
+    from sdf_nmpc_b200 import synth
+    from sdf_nmpc_b200.config import Config
+    from sdf_nmpc_b200.vae import VaeWrapper
+    out = {}
+    vae = VaeWrapper(Config(), synth.make_encoder_net(seed=5), max_batch=256)
+    base = np.stack([synth.depth_frame(seed=1 + i) for i in range(4)])
+    for nb in (1, 64, 256):
+        vae.set_img(np.concatenate([base] * ((nb + 3) // 4))[:nb])
+        for _ in range(2):
+            vae.encode(to_numpy=False)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        e0.record()
+        for _ in range(reps):
+            vae.encode(to_numpy=False)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        tf = nb * ENC_FLOP_FRAME / ms / 1e9
+        out[str(nb)] = dict(ms=ms, frames_per_s=nb / ms * 1e3, tflops=tf, frac_bf16_sustained=tf / peaks['bf16_tflops_sustained'],
+                            frac_of_3xtf32_ceiling=tf / (peaks['bf16_tflops_sustained'] / 6.0))
+    out['note'] = 'algorithmic FLOPs (4.34 GFLOP per frame) counted once; tensor-core layers use 3 TF32 MMAs per product'
     return out
 
 
