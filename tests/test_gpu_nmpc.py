@@ -263,3 +263,59 @@ def test_batched_refgen_feeds_controller(cuda_device):
         x = mpc.plant_step(x.clone(), mpc.get_u(), 0.075)
     d1 = torch.linalg.norm(goal - x[:, :3], dim=1)
     assert torch.isfinite(x).all() and bool((d1 < d0 - 0.5).all()), (d0, d1)
+
+
+def test_full_size_properties(cuda_device):
+    """BASELINE configs[2] size (4096 instances): size-independent properties of the batched step.
+    * every QP converges and its explicitly verified KKT residual is small;
+    * instances are independent: a sub-batch solved alone gives bit-identical controls (shard invariance - what the
+      multi-GPU partition relies on), and so does a permutation of the batch;
+    * multipliers are non-negative, bounds are respected; a random sample agrees with the oracle within U_TOL."""
+    import torch
+    from oracle import rti
+    from sdf_nmpc_b200 import synth
+    from sdf_nmpc_b200.config import Config
+    from sdf_nmpc_b200.nmpc import BatchedNmpc
+    B = 4096
+    net = synth.make_sdf_net(seed=0, **synth.ARCH_B, calibrated=True)
+    w = synth.nmpc_instances(B)
+    cfg = Config()
+
+    def run(idx):
+        mpc = BatchedNmpc(cfg, net, len(idx), cuda_device)
+        mpc.set_sdf_flag(1.0)
+        mpc.set_latent(w['latent'][idx], w['W_p_Bo'][idx], w['W_R_Bo'][idx])
+        mpc.set_ref_arrays(w['yref'][idx], w['W'][idx], w['yrefN'][idx], w['WN'][idx], w['qd'][idx])
+        x = torch.from_numpy(w['x0'][idx]).cuda()
+        for _ in range(2):
+            mpc.set_x0(x)
+            mpc.solve()
+            x = mpc.plant_step(x.clone(), mpc.get_u(), 0.075)
+        return mpc
+
+    full = run(np.arange(B))
+    assert int((full.status != 0).sum().item()) == 0
+    res = full.get_qp_residual().cpu().numpy()
+    assert res[:, 0].max() <= 1e-5 and np.isfinite(res).all()
+    u_full = full.get_u().cpu().numpy()
+    assert np.all(u_full[:, 0] >= -1e-9) and np.all(np.abs(u_full) <= 1 + 1e-9)
+    lam_h, lam_s = (t.cpu().numpy() for t in full.get_multipliers())
+    assert lam_h.min() >= 0 and lam_s.min() >= 0
+    # shard invariance: instances [1024, 1536) alone
+    sub = np.arange(1024, 1536)
+    assert np.array_equal(run(sub).get_u().cpu().numpy(), u_full[sub])
+    # permutation invariance on a shuffled sub-batch
+    perm = np.random.default_rng(0).permutation(B)[:768]
+    assert np.array_equal(run(perm).get_u().cpu().numpy(), u_full[perm])
+    # oracle agreement on a sample (first step only is cheap on the CPU: re-run one step from the same start)
+    samp = np.sort(np.random.default_rng(1).choice(B, 12, replace=False))
+    ocfg = rti.default_cfg()
+    prob, _ = make_problem(B, ocfg)
+    ps = {k: (v[samp] if isinstance(v, np.ndarray) and v.shape[:1] == (B,) else v) for k, v in prob.items()}
+    xb, ub = rti.init_traj(ps['x0'], ocfg)
+    _, _, out = rti.rti_step(net, xb, ub, ps, ocfg)
+    one = BatchedNmpc(cfg, net, len(samp), cuda_device)
+    one.set_sdf_flag(1.0); one.set_latent(w['latent'][samp], w['W_p_Bo'][samp], w['W_R_Bo'][samp])
+    one.set_ref_arrays(w['yref'][samp], w['W'][samp], w['yrefN'][samp], w['WN'][samp], w['qd'][samp])
+    one.set_x0(w['x0'][samp]); one.solve()
+    assert np.abs(one.get_u().cpu().numpy() - out['u0']).max() <= U_TOL
