@@ -12,6 +12,8 @@
 //     drain the accumulator (tcgen05.ld) through bias + residual + activation to the NCHW output (again pixel-coalesced).
 //   * 1 issuer warp: streams the matching weight chunk (pre-split hi | lo and pre-laid-out on the host, one cp.async.bulk
 //     per chunk) through a 2-stage ring and issues the tcgen05.mma from one elected lane on uniform operands.
+// K is ordered (ci, ky, kx): the 9 taps of a channel sit in the same chunk and reuse the same L1 lines.  The (ky, kx, ci) order
+// (one bounds test per chunk, no table) was measured slower, 3.25 vs 2.94 ms per 64 frames: no reuse inside a chunk.
 // The accumulator is double-buffered in TMEM (2 x 256 columns), so the MMAs of the next work item start while the
 // previous item's accumulator is still being drained by the slower producer group.
 #pragma once
