@@ -14,6 +14,11 @@
 //     per chunk) through a 2-stage ring and issues the tcgen05.mma from one elected lane on uniform operands.
 // K is ordered (ci, ky, kx): the 9 taps of a channel sit in the same chunk and reuse the same L1 lines.  The (ky, kx, ci) order
 // (one bounds test per chunk, no table) was measured slower, 3.25 vs 2.94 ms per 64 frames: no reuse inside a chunk.
+// Measured alternatives (64 frames, tensor-core layers 2.1 ms of the 2.94 ms total): NHWC activations with a (ky, kx, ci)
+// K order (4 x LDG.128 per thread and chunk instead of 16 table-driven loads) 3.05 ms - the gather is not the limiter;
+// a 3-deep A ring 3.30 ms; timing-only ablations: no A-stage stores -29 % of the tensor-core time, 1 of 3 MMAs -22 %,
+// no weight TMA 0 %, all three -57 %.  As in the SDF kernel the chunk period (~4 k cycles at N = 256 against a 1.5 k MMA
+// floor) is set by shared-memory traffic that the operand fetch, the A stores and their proxy fences share.
 // The accumulator is double-buffered in TMEM (2 x 256 columns), so the MMAs of the next work item start while the
 // previous item's accumulator is still being drained by the slower producer group.
 #pragma once
