@@ -10,8 +10,13 @@
 //     im2col patch values from the NCHW activation (lanes = consecutive pixels: coalesced for every k), split them into
 //     tf32 hi | lo and store the A chunk in the 128-byte-swizzled K-major UMMA layout; after the K loop the same warps
 //     drain the accumulator (tcgen05.ld) through bias + residual + activation to the NCHW output (again pixel-coalesced).
-//   * 1 issuer warp: streams the matching weight chunk (pre-split hi | lo and pre-laid-out on the host, one cp.async.bulk
-//     per chunk) through a 2-stage ring and issues the tcgen05.mma from one elected lane on uniform operands.
+//   * 1 weight-streaming warp: the weights (pre-split hi | lo and pre-laid-out on the host) travel as sub-chunks of <= 128
+//     output channels x 32 k (32 KB, one cp.async.bulk each) through a 4-stage ring.
+//   * 1 MMA warp: waits for operands and issues the tcgen05.mma from one elected lane on uniform operands; it does
+//     nothing else.  (With the bulk copies issued from the MMA warp - 500-800 cycles per copy in that thread, measured with
+//     the clock64 trace - and a 2 x 64 KB ring that waited for "previous chunk retired" before every issue, the tensor pipe
+//     idled as long as it worked: 4 k cycles per N = 256 chunk against 1.5 k of MMA.  tools/mma_rate.cu shows the pipe
+//     itself sustains exactly 128 / 64 cycles per N = 256 / 128 MMA next to store and TMA traffic.)
 // K is ordered (ci, ky, kx): the 9 taps of a channel sit in the same chunk and reuse the same L1 lines.  The (ky, kx, ci) order
 // (one bounds test per chunk, no table) was measured slower, 3.25 vs 2.94 ms per 64 frames: no reuse inside a chunk.
 // Measured alternatives (64 frames, tensor-core layers 2.1 ms of the 2.94 ms total): NHWC activations with a (ky, kx, ci)
@@ -29,9 +34,11 @@ namespace sdfnmpc {
 constexpr int CV_PROD_WARPS = 16;
 constexpr int CV_GROUP_THREADS = CV_PROD_WARPS * 32 / 2;
 constexpr int CV_PROD_THREADS = CV_PROD_WARPS * 32;
-constexpr int CV_THREADS = CV_PROD_THREADS + 32;
-constexpr int CV_WSTAGE_BYTES = 256 * TC_KC * 4 * 2;     // up to 256 output channels, hi | lo
-constexpr int CV_SMEM_BYTES = 2 * CV_WSTAGE_BYTES + 2 * TC_ASTAGE_BYTES + 256 + 1024;
+constexpr int CV_THREADS = CV_PROD_THREADS + 64;         // + MMA issuer warp + weight-streaming warp
+constexpr int CV_NSUB = 128;                             // output channels per weight sub-chunk
+constexpr int CV_WSTAGES = 4;
+constexpr int CV_WSTAGE_BYTES = CV_NSUB * TC_KC * 4 * 2; // 32 KB: hi | lo
+constexpr int CV_SMEM_BYTES = CV_WSTAGES * CV_WSTAGE_BYTES + 2 * TC_ASTAGE_BYTES + 256 + 1024;
 
 enum { CV_ACT_NONE = 0, CV_ACT_RELU = 1, CV_ACT_ELU = 2 };
 
@@ -41,32 +48,33 @@ struct ConvTcParams {
     int NT;                       // output channels per N tile: 64, 128, 192 or 256 (Cout % NT == 0)
     int n_ntiles, n_kchunks;
     const float* in;              // [B][Cin][Hin][Win]
-    const unsigned char* wblob;   // [n_ntiles][n_kchunks][hi: NT x 128 B swizzled | lo]
+    const unsigned char* wblob;   // [n_ntiles][n_kchunks][NT / NS sub-chunks][hi: NS x 128 B swizzled | lo], NS = min(NT, 128)
     const int4* ktab;             // [n_kchunks * 32]: {(ci*Hin + ky)*Win + kx, ky, kx, k < K}
     const float* bias;            // [Cout] (folded BatchNorm shift)
     const float* resid;           // [B][Cout][Hout][Wout] or null
     int act;
     float* out;                   // [B][Cout][Hout][Wout]
+    long long* trace;             // development: clock64 samples of CTA 0's issuer, [sub-chunk][4] (null = off)
 };
 
 __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcParams P) {
     using namespace tc;
     extern __shared__ __align__(1024) unsigned char cv_smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)cv_smem_raw + 1023) & ~(uintptr_t)1023);
-    unsigned char* wst[2] = {smem, smem + CV_WSTAGE_BYTES};
-    unsigned char* ast[2] = {smem + 2 * CV_WSTAGE_BYTES, smem + 2 * CV_WSTAGE_BYTES + TC_ASTAGE_BYTES};
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * CV_WSTAGE_BYTES + 2 * TC_ASTAGE_BYTES);   // 0-1 wfull, 2-3 afull, 4-5 sfree, 6 dfull
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-    const uint32_t wfull[2] = {smem_u32(bars + 0), smem_u32(bars + 1)};
-    const uint32_t afull[2] = {smem_u32(bars + 2), smem_u32(bars + 3)};
-    const uint32_t sfree[2] = {smem_u32(bars + 4), smem_u32(bars + 5)};
-    const uint32_t dfull = smem_u32(bars + 6);
+    unsigned char* wst0 = smem;                                                               // CV_WSTAGES x 32 KB
+    unsigned char* ast0 = smem + CV_WSTAGES * CV_WSTAGE_BYTES;                                // 2 x 32 KB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + CV_WSTAGES * CV_WSTAGE_BYTES + 2 * TC_ASTAGE_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    const uint32_t wfull0 = smem_u32(bars + 0), wfree0 = smem_u32(bars + 4);                  // + 8 * W stage
+    // (stage addresses are computed, not looked up: a dynamically indexed local array costs a local-memory load per use)
+    const uint32_t afull0 = smem_u32(bars + 8), sfree0 = smem_u32(bars + 10);                 // + 8 * A stage; sfree = consumed
+    const uint32_t dfull = smem_u32(bars + 12);
 
     const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     if (tid == 0) {
-        mbar_init(wfull[0], 1); mbar_init(wfull[1], 1);
-        mbar_init(afull[0], CV_GROUP_THREADS); mbar_init(afull[1], CV_GROUP_THREADS);
-        mbar_init(sfree[0], 1); mbar_init(sfree[1], 1);
+        for (int q = 0; q < CV_WSTAGES; ++q) { mbar_init(wfull0 + 8 * q, 1); mbar_init(wfree0 + 8 * q, 1); }
+        mbar_init(afull0, CV_GROUP_THREADS); mbar_init(afull0 + 8, CV_GROUP_THREADS);
+        mbar_init(sfree0, 1); mbar_init(sfree0 + 8, 1);
         mbar_init(dfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -116,10 +124,10 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
                 }
                 float vhi[16], vlo[16];
                 split_a16(v, vhi, vlo);
-                mbar_wait_backoff(sfree[g], ((chunk >> 1) & 1) ^ 1);
-                store_a16(ast[g], row, ch, vhi, vlo);
+                mbar_wait_backoff(sfree0 + 8 * g, ((chunk >> 1) & 1) ^ 1);
+                store_a16(ast0 + g * TC_ASTAGE_BYTES, row, ch, vhi, vlo);
                 fence_async_smem();
-                mbar_arrive(afull[g]);
+                mbar_arrive(afull0 + 8 * g);
             }
             // ---- epilogue: accumulator -> bias, residual, activation -> NCHW output.  The four (group, half) combinations
             // of a row take a quarter of the NT columns each. ----
@@ -146,52 +154,66 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
             tc_fence_before();
         }
     } else {
-        // ============================== weight streamer + MMA issuer ==============================
         const uint32_t leader = elect_one();
-        const size_t wchunk_bytes = (size_t)P.NT * TC_KC * 4 * 2;
+        const int NS = P.NT < CV_NSUB ? P.NT : CV_NSUB, nsub = P.NT / NS;       // sub-chunks per chunk
+        const uint32_t sub_bytes = (uint32_t)NS * TC_KC * 4 * 2;
         const int my_items = blockIdx.x < n_items ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-        const uint64_t n_chunks_total = (uint64_t)my_items * nk;
-        const uint32_t idesc = make_idesc(P.NT);
-        if (n_chunks_total > 0 && leader) {
-            const int nt0 = (int)blockIdx.x % P.n_ntiles;
-            mbar_expect_tx(wfull[0], (uint32_t)wchunk_bytes);
-            bulk_g2s(smem_u32(wst[0]), P.wblob + (size_t)nt0 * nk * wchunk_bytes, (uint32_t)wchunk_bytes, wfull[0]);
-        }
-        uint32_t item_it = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_it) {
-            const int nt = item % P.n_ntiles;
-            const uint32_t dcol = tmem_base + (item_it & 1) * 256u;
-            for (int kc = 0; kc < nk; ++kc, ++chunk) {
-                const int s = chunk & 1;
-                // prefetch the next chunk's weights (possibly the first chunk of the next item) into the other stage
-                if ((uint64_t)chunk + 1 < n_chunks_total) {
-                    const bool same = kc + 1 < nk;
-                    const int nnt = same ? nt : (item + (int)gridDim.x) % P.n_ntiles;
-                    const int nkc = same ? kc + 1 : 0;
-                    const uint32_t c1 = chunk + 1;
-                    mbar_wait(sfree[c1 & 1], ((c1 >> 1) & 1) ^ 1);
-                    if (leader) {
-                        mbar_expect_tx(wfull[c1 & 1], (uint32_t)wchunk_bytes);
-                        bulk_g2s(smem_u32(wst[c1 & 1]), P.wblob + ((size_t)nnt * nk + nkc) * wchunk_bytes, (uint32_t)wchunk_bytes, wfull[c1 & 1]);
-                    }
-                }
-                mbar_wait(wfull[s], (chunk >> 1) & 1);
-                mbar_wait(afull[s], (chunk >> 1) & 1);
-                tc_fence_after();
-                const uint32_t a_hi = smem_u32(ast[s]), w_hi = smem_u32(wst[s]);
-                const uint64_t ad_hi = make_desc(a_hi), ad_lo = make_desc(a_hi + TC_ASTAGE_BYTES / 2);
-                const uint64_t wd_hi = make_desc(w_hi), wd_lo = make_desc(w_hi + (uint32_t)P.NT * 128u);
-                if (elect_one()) {
-#pragma unroll
-                    for (int ks = 0; ks < TC_KC / 8; ++ks) {
-                        tc_mma_tf32(dcol, ad_hi + 2 * ks, wd_hi + 2 * ks, idesc, (kc == 0 && ks == 0) ? 0u : 1u);
-                        tc_mma_tf32(dcol, ad_lo + 2 * ks, wd_hi + 2 * ks, idesc, 1u);
-                        tc_mma_tf32(dcol, ad_hi + 2 * ks, wd_lo + 2 * ks, idesc, 1u);
-                    }
-                    tc_commit(sfree[s]);
-                    if (kc == nk - 1) tc_commit(dfull);
+        const uint64_t n_sub_total = (uint64_t)my_items * nk * nsub;
+        if (warp == CV_PROD_WARPS + 1) {
+            // ============================== weight streamer ==============================
+            int pf_item = blockIdx.x, pf_kc = 0, pf_h = 0;
+            for (uint64_t pf = 0; pf < n_sub_total; ++pf) {
+                const uint32_t q = (uint32_t)(pf % CV_WSTAGES);
+                mbar_wait(wfree0 + 8 * q, (uint32_t)(((pf / CV_WSTAGES) & 1) ^ 1));      // previous user of the slot has retired
+                if (leader) {
+                    const int pnt = pf_item % P.n_ntiles;
+                    mbar_expect_tx(wfull0 + 8 * q, sub_bytes);
+                    bulk_g2s(smem_u32(wst0 + q * CV_WSTAGE_BYTES), P.wblob + (((size_t)pnt * nk + pf_kc) * nsub + pf_h) * sub_bytes, sub_bytes,
+                             wfull0 + 8 * q);
                 }
                 __syncwarp();
+                if (++pf_h == nsub) { pf_h = 0; if (++pf_kc == nk) { pf_kc = 0; pf_item += gridDim.x; } }
+            }
+        } else {
+            // ============================== MMA issuer ==============================
+            const uint32_t idesc = make_idesc(NS);
+            uint32_t item_it = 0;
+            uint64_t jj = 0;                                                         // sub-chunk counter (W stage = jj % 4)
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_it) {
+                const uint32_t dcol = tmem_base + (item_it & 1) * 256u;
+                for (int kc = 0; kc < nk; ++kc, ++chunk) {
+                    const int s = chunk & 1;
+                    const uint32_t a_hi = smem_u32(ast0) + (uint32_t)s * TC_ASTAGE_BYTES;
+                    const uint64_t ad_hi = make_desc(a_hi), ad_lo = make_desc(a_hi + TC_ASTAGE_BYTES / 2);
+                    for (int h = 0; h < nsub; ++h, ++jj) {
+                        const uint32_t q = (uint32_t)(jj % CV_WSTAGES);
+                        const bool tr = P.trace && blockIdx.x == 0 && jj < 512 && leader;
+                        if (tr) P.trace[jj * 4 + 0] = clock64();
+                        mbar_wait(wfull0 + 8 * q, (uint32_t)((jj / CV_WSTAGES) & 1));
+                        if (tr) P.trace[jj * 4 + 1] = clock64();
+                        if (h == 0) mbar_wait(afull0 + 8 * s, (chunk >> 1) & 1);
+                        if (tr) P.trace[jj * 4 + 2] = clock64();
+                        tc_fence_after();
+                        const uint32_t w_hi = smem_u32(wst0 + q * CV_WSTAGE_BYTES);
+                        const uint64_t wd_hi = make_desc(w_hi), wd_lo = make_desc(w_hi + (uint32_t)NS * 128u);
+                        const uint32_t dc = dcol + (uint32_t)(h * NS);
+                        if (elect_one()) {
+#pragma unroll
+                            for (int ks = 0; ks < TC_KC / 8; ++ks) {
+                                tc_mma_tf32(dc, ad_hi + 2 * ks, wd_hi + 2 * ks, idesc, (kc == 0 && ks == 0) ? 0u : 1u);
+                                tc_mma_tf32(dc, ad_lo + 2 * ks, wd_hi + 2 * ks, idesc, 1u);
+                                tc_mma_tf32(dc, ad_hi + 2 * ks, wd_lo + 2 * ks, idesc, 1u);
+                            }
+                            tc_commit(wfree0 + 8 * q);
+                            if (h == nsub - 1) {
+                                tc_commit(sfree0 + 8 * s);
+                                if (kc == nk - 1) tc_commit(dfull);
+                            }
+                        }
+                        __syncwarp();
+                        if (tr) P.trace[jj * 4 + 3] = clock64();
+                    }
+                }
             }
         }
     }

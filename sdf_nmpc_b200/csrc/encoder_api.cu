@@ -346,21 +346,24 @@ static int make_layer(Layer& L, const float* w, const float* const bn[4], const 
     if (L.s.Cin < 8 || NT % 64 || L.s.Cout % NT) return 0;
     const int nk = (K + TC_KC - 1) / TC_KC;
     L.NT = NT; L.n_ntiles = L.s.Cout / NT; L.n_kchunks = nk;
+    // sub-chunks of NS = min(NT, 128) output channels: [n tile][k chunk][sub][hi | lo], each one bulk copy (conv_tc.cuh)
+    const int NS = NT < CV_NSUB ? NT : CV_NSUB, nsub = NT / NS;
     std::vector<float> blob((size_t)L.n_ntiles * nk * NT * TC_KC * 2, 0.f);
     for (int nt = 0; nt < L.n_ntiles; ++nt)
-        for (int kc = 0; kc < nk; ++kc) {
-            const size_t base = ((size_t)nt * nk + kc) * NT * TC_KC * 2;
-            for (int n = 0; n < NT; ++n)
-                for (int k = 0; k < TC_KC; ++k) {
-                    const int kk = kc * TC_KC + k;
-                    const float v = kk < K ? W[(size_t)(nt * NT + n) * K + kk] : 0.f;
-                    const float hi = tf32_rna_host(v), lo = tf32_rna_host(v - hi);
-                    // 128-byte-swizzled K-major: 8-row atoms of 1024 B, row = 32 floats, 16-byte unit index XOR row-in-atom
-                    const size_t idx = (size_t)(n >> 3) * 256 + (size_t)(n & 7) * 32 + (size_t)(((k >> 2) ^ (n & 7)) * 4) + (k & 3);
-                    blob[base + idx] = hi;
-                    blob[base + (size_t)NT * TC_KC + idx] = lo;
-                }
-        }
+        for (int kc = 0; kc < nk; ++kc)
+            for (int hs = 0; hs < nsub; ++hs) {
+                const size_t base = (((size_t)nt * nk + kc) * nsub + hs) * NS * TC_KC * 2;
+                for (int n = 0; n < NS; ++n)
+                    for (int k = 0; k < TC_KC; ++k) {
+                        const int kk = kc * TC_KC + k;
+                        const float v = kk < K ? W[(size_t)(nt * NT + hs * NS + n) * K + kk] : 0.f;
+                        const float hi = tf32_rna_host(v), lo = tf32_rna_host(v - hi);
+                        // 128-byte-swizzled K-major: 8-row atoms of 1024 B, row = 32 floats, 16-byte unit index XOR row-in-atom
+                        const size_t idx = (size_t)(n >> 3) * 256 + (size_t)(n & 7) * 32 + (size_t)(((k >> 2) ^ (n & 7)) * 4) + (k & 3);
+                        blob[base + idx] = hi;
+                        blob[base + (size_t)NS * TC_KC + idx] = lo;
+                    }
+            }
     float* dblob = nullptr;
     if (int rc = upload(&dblob, blob)) return rc;
     L.wblob_tc = reinterpret_cast<unsigned char*>(dblob);
@@ -471,7 +474,25 @@ static int launch_conv_tc(const Layer& L, int B, const float* in, const float* r
     P.in = in; P.wblob = L.wblob_tc; P.ktab = L.ktab; P.bias = L.b; P.resid = resid; P.act = act; P.out = out;
     const long long n_items = (P.npix + TC_TM - 1) / TC_TM * L.n_ntiles;
     const int grid = (int)(n_items < sm_count ? n_items : sm_count);
+    P.trace = nullptr;
+    static long long* tbuf = nullptr;
+    const char* tp = getenv("SDFNMPC_CV_TRACE");          // development: "<Cin>x<Cout>:<file>" traces that layer's issuer
+    int tci = 0, tco = 0; char tfile[256] = {0};
+    const bool want = tp && sscanf(tp, "%dx%d:%255s", &tci, &tco, tfile) == 3 && tci == L.s.Cin && tco == L.s.Cout && L.ks == 3;
+    if (want) {
+        if (!tbuf) cudaMalloc(&tbuf, 512 * 5 * sizeof(long long));
+        cudaMemset(tbuf, 0, 512 * 5 * sizeof(long long));
+        P.trace = tbuf;
+    }
     conv_tc_kernel<<<grid, CV_THREADS, CV_SMEM_BYTES, st>>>(P);
+    if (want) {
+        std::vector<long long> tr(512 * 5);
+        cudaMemcpy(tr.data(), tbuf, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        if (FILE* f = fopen(tfile, "w")) {
+            for (int i = 0; i < 512; ++i) fprintf(f, "%lld %lld %lld %lld %lld\n", tr[i * 4] - tr[0], tr[i * 4 + 1] - tr[0], tr[i * 4 + 2] - tr[0], tr[i * 4 + 3] - tr[0], tr[2048 + i] - tr[0]);
+            fclose(f);
+        }
+    }
     count_launch();
     SDF_CUDA_CHECK(cudaGetLastError());
     return 0;

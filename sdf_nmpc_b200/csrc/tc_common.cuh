@@ -33,6 +33,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 // producers: back off between probes so that spinning warps do not steal issue slots from the MMA issuer
 __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+#if defined(TC_EXP_NO_BACKOFF)
+    mbar_wait(bar, parity);
+    return;
+#endif
     uint32_t done = 0;
     while (true) {
         asm volatile(

@@ -22,7 +22,7 @@ def build(specs):
         for src in B.SOURCES:
             obj = os.path.join(VDIR, f'{tag}_{src[:-3]}.o')
             base_obj = os.path.join(B.LIBDIR, src.replace('.cu', '.o'))
-            tu = 'sdf_api.cu' if tag.startswith('sdf') else 'nmpc_api.cu'
+            tu = 'sdf_api.cu' if tag.startswith('sdf') else ('encoder_api.cu' if tag.startswith('enc') else 'nmpc_api.cu')
             if src != tu and os.path.exists(base_obj):
                 objs.append(base_obj)          # only one TU depends on the experiment flags (tags 'sdf*': the SDF TU)
                 continue
@@ -73,7 +73,18 @@ def one(Bn):
         ev.eval(pts, out=(sdf, grad))
     e1.record(); torch.cuda.synchronize()
     sweep = n / (e0.elapsed_time(e1) / 10 * 1e-3) / 1e6
-    print(json.dumps(dict(sdf_mpts=sweep, qp_ms=ms['qp'] / n, lin_ms=ms['linearize'] / n, sdf_ms=ms['sdf'] / n, iters=its / 10,
+    from sdf_nmpc_b200.vae import VaeWrapper
+    import numpy as np
+    vae = VaeWrapper(Config(), synth.make_encoder_net(seed=5), max_batch=64)
+    vae.set_img(np.stack([synth.depth_frame(seed=i % 4) for i in range(64)]))
+    for _ in range(2):
+        vae.encode(to_numpy=False)
+    e0.record()
+    for _ in range(5):
+        vae.encode(to_numpy=False)
+    e1.record(); torch.cuda.synchronize()
+    enc_ms = e0.elapsed_time(e1) / 5
+    print(json.dumps(dict(enc64_ms=enc_ms, sdf_mpts=sweep, qp_ms=ms['qp'] / n, lin_ms=ms['linearize'] / n, sdf_ms=ms['sdf'] / n, iters=its / 10,
                           ok=int((mpc.status == 0).sum().item()))))
 
 
