@@ -29,7 +29,7 @@ constexpr int TC_PROD_WARPS = 16;            // producer warps: 2 groups (even /
 constexpr int TC_GROUP_THREADS = TC_PROD_WARPS * 32 / 2;
 constexpr int TC_MAX_ACC = 8;                // accumulator-complete barriers per tile
 constexpr int TC_PROD_THREADS = TC_PROD_WARPS * 32;
-constexpr int TC_THREADS = TC_PROD_THREADS + 32;
+constexpr int TC_THREADS = TC_PROD_THREADS + 64;          // + MMA issuer warp + weight-streaming warp
 constexpr int TC_WSTAGE_BYTES = 256 * TC_KC * 4 * 2;   // 64 KB: up to 256 weight rows, hi | lo
 // Timing-only ablations for development (results are wrong): -DTC_EXP_NO_STORE (producers skip the A-stage stores),
 // -DTC_EXP_ONE_MMA (hi*hi only), -DTC_EXP_NO_TMA (16-byte weight copies).  Measured at 1e6 points: base 151 Mpts/s, no
@@ -134,17 +134,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
     using namespace tc;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    unsigned char* wst[2] = {smem, smem + TC_WSTAGE_BYTES};
-    unsigned char* ast[2] = {smem + 2 * TC_WSTAGE_BYTES, smem + 2 * TC_WSTAGE_BYTES + TC_ASTAGE_BYTES};
+    // stage addresses and barriers are computed from the stage index (a dynamically indexed local array costs a
+    // local-memory load per use - measured in the convolution kernel's issuer)
+    unsigned char* wst0 = smem;                                   // 2 x TC_WSTAGE_BYTES
+    unsigned char* ast0 = smem + 2 * TC_WSTAGE_BYTES;             // 2 x TC_ASTAGE_BYTES
     unsigned char* aux = smem + 2 * TC_WSTAGE_BYTES + 2 * TC_ASTAGE_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(aux);                   // 0-1 wfull, 2-3 afull, 4-5 sfree, 6-13 dfull ring
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
     float4* etab = reinterpret_cast<float4*>(aux + 128);                 // [Ep] (dir * 2^f, phase)  / identity rows
     float* part = reinterpret_cast<float*>(aux + 128 + 128 * 16);        // [4 column groups][128 rows][4]
     SdfTcOp* ops_s = reinterpret_cast<SdfTcOp*>(aux + 128 + 128 * 16 + 4 * 128 * 4 * 4);   // op program
-    const uint32_t wfull[2] = {smem_u32(bars + 0), smem_u32(bars + 1)};
-    const uint32_t afull[2] = {smem_u32(bars + 2), smem_u32(bars + 3)};
-    const uint32_t sfree[2] = {smem_u32(bars + 4), smem_u32(bars + 5)};
+    const uint32_t wfull0 = smem_u32(bars + 0), afull0 = smem_u32(bars + 2), sfree0 = smem_u32(bars + 4);   // + 8 * stage
     const uint32_t dfull0 = smem_u32(bars + 6);                          // dfull[q] = dfull0 + 8 q
 
     // warp index through a lane-0 shuffle: the compiler then knows it is warp-uniform, which keeps the role branches and
@@ -155,9 +155,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
     const float HALF_PI = 1.57079632679489661923f;
 
     if (tid == 0) {
-        mbar_init(wfull[0], 1); mbar_init(wfull[1], 1);
-        mbar_init(afull[0], TC_GROUP_THREADS); mbar_init(afull[1], TC_GROUP_THREADS);
-        mbar_init(sfree[0], 1); mbar_init(sfree[1], 1);
+        mbar_init(wfull0, 1); mbar_init(wfull0 + 8, 1);
+        mbar_init(afull0, TC_GROUP_THREADS); mbar_init(afull0 + 8, TC_GROUP_THREADS);
+        mbar_init(sfree0, 1); mbar_init(sfree0 + 8, 1);
         for (int q = 0; q < TC_MAX_ACC; ++q) mbar_init(dfull0 + 8 * q, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -273,13 +273,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
                 float vhi[16], vlo[16];
                 split_a16(v, vhi, vlo);
                 if (tr) P.trace[oi * 8 + 1] = clock64();
-                mbar_wait_backoff(sfree[g], ((chunk >> 1) & 1) ^ 1);
+                mbar_wait_backoff(sfree0 + 8 * g, ((chunk >> 1) & 1) ^ 1);
                 if (tr) P.trace[oi * 8 + 2] = clock64();
 #if !defined(TC_EXP_NO_STORE)
-                store_a16(ast[g], row, ch, vhi, vlo);
+                store_a16(ast0 + g * TC_ASTAGE_BYTES, row, ch, vhi, vlo);
 #endif
                 fence_async_smem();
-                mbar_arrive(afull[g]);
+                mbar_arrive(afull0 + 8 * g);
                 if (tr) P.trace[oi * 8 + 3] = clock64();
             }
             // ---- final: g_e = D_ge1 (+ parked skip part) ; chain rule through the embedding.  Group g takes the 32-feature
@@ -328,71 +328,72 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
             }
             asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD_THREADS) : "memory");
         }
-    } else {
-        // ============================== weight streamer + MMA issuer ==============================
-        // The whole warp runs this loop converged, on warp-uniform values (op program from the constant bank), so that
-        // descriptors live in uniform registers; lane 0 alone executes the TMA / MMA / commit instructions.
+    } else if (warp == TC_PROD_WARPS + 1) {
+        // ============================== weight streamer ==============================
+        // One bulk copy per chunk into the stage its MMAs will read, as soon as the stage's previous MMAs have retired.
+        // (Issued from the MMA warp these copies cost that thread 500-800 cycles each - clock64 trace - during which no MMA
+        // was queued.)
         const uint32_t leader = elect_one();
         const uint64_t n_chunks_total = (uint64_t)((n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * n_ops;
-        if (n_chunks_total > 0 && leader) {
-            mbar_expect_tx(wfull[0], P.opsv[0].w_bytes);
-            bulk_g2s(smem_u32(wst[0]), P.wblob + P.opsv[0].w_off, P.opsv[0].w_bytes, wfull[0]);
+        int oi = 0;
+        for (uint64_t c = 0; c < n_chunks_total; ++c) {
+            const SdfTcOp& op = P.opsv[oi];
+            const uint32_t q = (uint32_t)(c & 1);
+            mbar_wait(sfree0 + 8 * q, (uint32_t)(((c >> 1) & 1) ^ 1));
+            if (leader) {
+#if defined(TC_EXP_NO_TMA)
+                mbar_expect_tx(wfull0 + 8 * q, 16);
+                bulk_g2s(smem_u32(wst0 + q * TC_WSTAGE_BYTES), P.wblob + op.w_off, 16, wfull0 + 8 * q);
+#else
+                mbar_expect_tx(wfull0 + 8 * q, op.w_bytes);
+                bulk_g2s(smem_u32(wst0 + q * TC_WSTAGE_BYTES), P.wblob + op.w_off, op.w_bytes, wfull0 + 8 * q);
+#endif
+            }
+            __syncwarp();
+            if (++oi == n_ops) oi = 0;
         }
+    } else {
+        // ============================== MMA issuer ==============================
+        // The whole warp runs this loop converged, on warp-uniform values (op program from the constant bank), so that
+        // descriptors live in uniform registers; one elected lane executes the MMA / commit instructions.
+        const uint32_t leader = elect_one();
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const bool tr = P.trace && blockIdx.x == 0 && tile == (int)gridDim.x;
             for (int oi = 0; oi < n_ops; ++oi, ++chunk) {
                 const SdfTcOp& op = P.opsv[oi];
-                const int s = chunk & 1;
-                if (tr && leader) P.trace[oi * 8 + 4] = clock64();
-                // prefetch the next chunk's weights into the other stage once its previous MMAs have retired.  (Queuing this
-                // chunk's MMAs before the wait was measured slower, 151 vs 158 Mpts/s: the weights then arrive late.)
-                if ((uint64_t)chunk + 1 < n_chunks_total) {
-                    const SdfTcOp& nx = P.opsv[oi + 1 < n_ops ? oi + 1 : 0];
-                    const uint32_t c1 = chunk + 1;
-                    mbar_wait(sfree[c1 & 1], ((c1 >> 1) & 1) ^ 1);
-                    if (leader) {
-#if defined(TC_EXP_NO_TMA)
-                        mbar_expect_tx(wfull[c1 & 1], 16);
-                        bulk_g2s(smem_u32(wst[c1 & 1]), P.wblob + nx.w_off, 16, wfull[c1 & 1]);
-#else
-                        mbar_expect_tx(wfull[c1 & 1], nx.w_bytes);
-                        bulk_g2s(smem_u32(wst[c1 & 1]), P.wblob + nx.w_off, nx.w_bytes, wfull[c1 & 1]);
-#endif
-                    }
-                }
-                if (tr && leader) P.trace[oi * 8 + 5] = clock64();
-                mbar_wait(wfull[s], (chunk >> 1) & 1);
+                const uint32_t s = chunk & 1;
+                if (tr && leader) { P.trace[oi * 8 + 4] = clock64(); P.trace[oi * 8 + 5] = clock64(); }
+                mbar_wait(wfull0 + 8 * s, (chunk >> 1) & 1);
                 if (tr && leader) P.trace[oi * 8 + 6] = clock64();
-                mbar_wait(afull[s], (chunk >> 1) & 1);
+                mbar_wait(afull0 + 8 * s, (chunk >> 1) & 1);
                 if (tr && leader) P.trace[oi * 8 + 7] = clock64();
                 tc_fence_after();
                 // descriptors are built once per chunk; per MMA only the start-address field advances (+32 B = +2 units
-                // per K step of 8 tf32).  The issue loop is fully unrolled: a single thread issues ~6 instructions per MMA.
-                const uint32_t a_hi = smem_u32(ast[s]), w_hi = smem_u32(wst[s]);
+                // per K step of 8 tf32)
+                const uint32_t a_hi = smem_u32(ast0) + s * TC_ASTAGE_BYTES, w_hi = smem_u32(wst0) + s * TC_WSTAGE_BYTES;
                 const uint64_t ad_hi = make_desc(a_hi), ad_lo = make_desc(a_hi + TC_ASTAGE_BYTES / 2);
                 const uint64_t wd_hi = make_desc(w_hi), wd_lo = make_desc(w_hi + (uint32_t)op.n_total * 128u);
                 const uint32_t first_acc = op.first ? 0u : 1u;
                 if (elect_one()) {
 #pragma unroll 1
-                for (int pc = 0; pc < op.n_piece; ++pc) {
-                    const uint32_t dcol = tmem_base + (uint32_t)op.d_col[pc];
-                    const uint32_t idesc = make_idesc(op.n_rows[pc]);
-                    const uint64_t boff = (uint64_t)((op.b_row0[pc] >> 3) * (1024 >> 4));
-                    const uint64_t bh = wd_hi + boff, bl = wd_lo + boff;
+                    for (int pc = 0; pc < op.n_piece; ++pc) {
+                        const uint32_t dcol = tmem_base + (uint32_t)op.d_col[pc];
+                        const uint32_t idesc = make_idesc(op.n_rows[pc]);
+                        const uint64_t boff = (uint64_t)((op.b_row0[pc] >> 3) * (1024 >> 4));
+                        const uint64_t bh = wd_hi + boff, bl = wd_lo + boff;
 #pragma unroll
-                    for (int ks = 0; ks < TC_KC / 8; ++ks) {
-                        tc_mma_tf32(dcol, ad_hi + 2 * ks, bh + 2 * ks, idesc, ks == 0 ? first_acc : 1u);
+                        for (int ks = 0; ks < TC_KC / 8; ++ks) {
+                            tc_mma_tf32(dcol, ad_hi + 2 * ks, bh + 2 * ks, idesc, ks == 0 ? first_acc : 1u);
 #if !defined(TC_EXP_ONE_MMA)
-                        tc_mma_tf32(dcol, ad_lo + 2 * ks, bh + 2 * ks, idesc, 1u);
-                        tc_mma_tf32(dcol, ad_hi + 2 * ks, bl + 2 * ks, idesc, 1u);
+                            tc_mma_tf32(dcol, ad_lo + 2 * ks, bh + 2 * ks, idesc, 1u);
+                            tc_mma_tf32(dcol, ad_hi + 2 * ks, bl + 2 * ks, idesc, 1u);
 #endif
+                        }
                     }
-                }
-                    tc_commit(sfree[s]);
+                    tc_commit(sfree0 + 8 * s);
                     if (op.d_commit >= 0) tc_commit(dfull0 + 8 * op.d_commit);
                 }
                 __syncwarp();
-
             }
         }
     }
