@@ -5,16 +5,17 @@
 // tile run as tcgen05.mma kind::tf32 with fp32 accumulators in TMEM.  fp32-equivalent accuracy comes from the
 // 2-way TF32 split: x = hi + lo, D += A_hi B_hi + A_lo B_hi + A_hi B_lo.
 //
-// Structure of one CTA (160 threads, one CTA per SM, persistent over tiles of 128 points):
-//   * warps 0-3 ("producers", thread t <-> point t <-> TMEM lane t): build the A operand of the next GEMM in
-//     32-feature chunks directly in the UMMA canonical K-major (no-swizzle) shared-memory layout, as hi and lo
-//     TF32 parts: the embedding for layer 1 / the skip connection, act(D + bias) read back from TMEM with
-//     tcgen05.ld for the hidden layers, D * act' for the reverse sweep.  act' values and the partial embedding
-//     gradient are parked in an L2-resident per-CTA scratch (TMEM and smem are full).
-//   * warp 4, one elected thread: streams the matching 32-column weight chunk (pre-split hi|lo, pre-laid-out in the
-//     canonical layout on the host) with ONE bulk TMA copy (cp.async.bulk, UBLKCP) per chunk and issues the
-//     tcgen05.mma instructions; tcgen05.commit releases the 2-stage smem ring and publishes finished accumulators.
-//   A chunk "program" (SdfTcOp[]) built on the host drives both roles in lock-step.
+// Structure of one CTA (576 threads = 18 warps, one CTA per SM, persistent over tiles of 128 points):
+//   * warps 0-15 ("producers", two ping-pong groups of 8; thread <-> (point = TMEM lane, 16 of the chunk's 32 features)):
+//     build the A operand of the next GEMM in 32-feature chunks in the 128-byte-swizzled K-major UMMA layout, as hi and lo
+//     TF32 parts: the embedding for layer 1 / the skip connection, act(D + bias) read back from TMEM with tcgen05.ld for
+//     the hidden layers, D * act' for the reverse sweep.  act' values and the partial embedding gradient are parked in an
+//     L2-resident per-CTA scratch (TMEM and smem are full).  Group g owns the chunks with (chunk & 1) == g and stage g.
+//   * warp 16 (MMA issuer): waits for operands and issues the tcgen05.mma from one elected lane on warp-uniform operands;
+//     tcgen05.commit releases the 2-stage smem ring and publishes finished accumulators.
+//   * warp 17 (weight streamer): ONE bulk copy (cp.async.bulk, UBLKCP) per 32-column weight chunk (pre-split hi|lo,
+//     pre-laid-out on the host) into the stage whose previous MMAs have retired.
+//   A chunk "program" (SdfTcOp[]) built on the host drives all roles in lock-step.
 // TMEM column plan (512 columns, all allocated): forward D1 @0, D2 @256, D3 @0, D4 @128; reverse D_g3 @0,
 // D_g2 @128, D_ge3 @384 (drained to scratch), D_g1 @0 (rows 0..127 of W2^T) + @384 (rest), D_ge1 @128.
 #pragma once
