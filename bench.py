@@ -28,8 +28,17 @@ import time
 
 import numpy as np
 
-# stdout carries exactly one JSON line: NCCL's own banner / debug lines (printed on stdout by default) go to stderr
-os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+# stdout carries exactly ONE JSON line.  Libraries write there too (NCCL prints its version banner on file descriptor 1
+# when NCCL_DEBUG is set on the box), so descriptor 1 is pointed at stderr for the whole run and the JSON line goes to a
+# private duplicate of the original stdout.
+_REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+os.dup2(2, 1)
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + '\n')
+    _REAL_STDOUT.flush()
+
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -154,7 +163,7 @@ def run_reference(args, rank, world):
                 e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 note='CPU restatement (numpy float64 oracle) of acados 0.3.1 + L4CasADi 1.4.1 semantics with seeded synthetic weights - '
                      'not the original binaries, which cannot be installed offline')
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -289,7 +298,7 @@ def run_ours(args, rank, local_rank, world):
         line['cpu_baseline'] = dict(value=cpu_v, unit=UNIT, cores=cpu_info['workers'], kind='port',
                                     sample=f"{cpu_info['workers']} processes x 8 instances x 2 closed-loop RTI steps of the same workload "
                                            f"({cpu_info['solves']} solves, {cpu_info['busy_s']:.1f} s busy)")
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def sdf_microbench(net, peaks):
