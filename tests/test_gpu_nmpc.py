@@ -319,3 +319,45 @@ def test_full_size_properties(cuda_device):
     one.set_ref_arrays(w['yref'][samp], w['W'][samp], w['yrefN'][samp], w['WN'][samp], w['qd'][samp])
     one.set_x0(w['x0'][samp]); one.solve()
     assert np.abs(one.get_u().cpu().numpy() - out['u0']).max() <= U_TOL
+
+
+@pytest.mark.parametrize('variant', ['N12', 'nonuniform_dt', 'shift1'])
+def test_config_variants_match_oracle(variant, cuda_device):
+    """Configuration options of the reference OCP other than the defaults: a different horizon (generic-N kernel path),
+    the non-uniform time grid of ocp.py:21-27 and the iterate shift of ocp.py:152-156, each against the oracle."""
+    import torch
+    from oracle import rti
+    from sdf_nmpc_b200 import synth
+    from sdf_nmpc_b200.config import Config
+    from sdf_nmpc_b200.nmpc import BatchedNmpc
+    B = 10
+    net = synth.make_sdf_net(seed=0, **synth.ARCH_B, calibrated=True)
+    cfg = Config()
+    ocfg = rti.default_cfg()
+    if variant == 'N12':
+        cfg.mpc.N = 12
+        ocfg['N'] = 12
+    elif variant == 'nonuniform_dt':
+        cfg.mpc.uniform_dt = False
+    elif variant == 'shift1':
+        cfg.mpc.shift = 1
+    ocfg['dt'] = np.asarray(cfg.shooting_dt(), float)
+    assert len(ocfg['dt']) == cfg.mpc.N and abs(ocfg['dt'].sum() - cfg.mpc.T) < 1e-12
+    if variant == 'nonuniform_dt':
+        assert ocfg['dt'][0] == pytest.approx(0.01) and ocfg['dt'].max() > 0.07
+    prob, w = make_problem(B, ocfg)
+    mpc = BatchedNmpc(cfg, net, B, cuda_device)
+    mpc.set_sdf_flag(1.0)
+    mpc.set_latent(w['latent'], w['W_p_Bo'], w['W_R_Bo'])
+    mpc.set_ref_arrays(w['yref'], w['W'], w['yrefN'], w['WN'], w['qd'])
+    xb, ub = rti.init_traj(prob['x0'], ocfg)
+    for step in range(3):
+        if variant == 'shift1' and step > 0:          # Ocp.shift(1): x[i-1] = x[i], u[i-1] = u[i] for i in 1..N-1; node N kept
+            xb[:, :-2], ub[:, :-1] = xb[:, 1:-1].copy(), ub[:, 1:].copy()
+        mpc.set_x0(prob['x0'])
+        assert int(mpc.solve().max().item()) == 0
+        xb, ub, out = rti.rti_step(net, xb, ub, prob, ocfg)
+        assert np.array_equal(mpc.status.cpu().numpy(), out['status'])
+        assert np.abs(mpc.get_u().cpu().numpy() - out['u0']).max() <= U_TOL, (variant, step)
+        x, u = mpc.get_matrices()
+        assert np.abs(x.cpu().numpy() - xb).max() <= 1e-3 and np.abs(u.cpu().numpy() - ub).max() <= 1e-3
