@@ -68,6 +68,7 @@ struct QpBatch {
     const float *sdf_d, *sdf_g;
     int *status, *iters;
     double* res_out;
+    long long* trace;
     size_t work_per_inst;
     double max_df;
 };
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32, QP_MIN_CTAS) nmpc_qp_kernel(Sol
     P.iters = q.iters + b;
     Lanes L{(int)(threadIdx.x & 31)};
     P.res_out = q.res_out ? q.res_out + 2 * (size_t)b : nullptr;
+    P.trace = b == 0 ? q.trace : nullptr;
     qp_solve_instance<NX, NU, NY, NH, NFIX>(L, P, sm_all + (size_t)warp * Shape::smem_doubles(N));
 }
 
@@ -284,11 +286,30 @@ extern "C" int sdfnmpc_solver_rti_step(sdfnmpc_solver_t h, int32_t B, const doub
     q.u0 = u0; q.lam_hard = h->lam_hard; q.lam_soft = h->lam_soft; q.sdf_d = h->sdf_d; q.sdf_g = h->sdf_g;
     q.status = status; q.iters = qp_iters; q.work_per_inst = h->work_per_inst; q.max_df = (double)h->sdf->net.max_df;
     q.res_out = h->qp_res;
+    q.trace = nullptr;
+#if defined(SDFNMPC_QP_TRACE)
+    static long long* qtrace = nullptr;          // development: per-phase cycles of instance 0, IPM iteration 2
+    if (getenv("SDFNMPC_QP_TRACE_FILE")) {
+        if (!qtrace) cudaMalloc(&qtrace, 32 * sizeof(long long));
+        cudaMemsetAsync(qtrace, 0, 32 * sizeof(long long), st);
+        q.trace = qtrace;
+    }
+#endif
     if (N == 20) nmpc_qp_kernel<20><<<(B + QP_WARPS - 1) / QP_WARPS, QP_WARPS * 32, h->qp_smem, st>>>(h->sc, B, q);
     else nmpc_qp_kernel<0><<<(B + QP_WARPS - 1) / QP_WARPS, QP_WARPS * 32, h->qp_smem, st>>>(h->sc, B, q);
     count_launch();
     SDF_CUDA_CHECK(cudaGetLastError());
     if (tm) { cudaEventRecord(ev[3], st); h->ev_steps++; }
+#if defined(SDFNMPC_QP_TRACE)
+    if (q.trace) {
+        long long tr[32];
+        cudaMemcpy(tr, q.trace, sizeof(tr), cudaMemcpyDeviceToHost);
+        if (FILE* f = fopen(getenv("SDFNMPC_QP_TRACE_FILE"), "w")) {
+            for (int i = 0; i < 32; ++i) fprintf(f, "%lld\n", tr[i]);
+            fclose(f);
+        }
+    }
+#endif
     return 0;
 }
 

@@ -96,6 +96,7 @@ struct QpProb {            // all pointers are offset to ONE instance
     double* res_out;       // [2] or null: verified KKT residual (inf-norm), inf-norm of the full step [du; dx]
     int* status;           // 0 ok, 2 max-iter, 4 NaN / factorisation failure (acados codes)
     int* iters;
+    long long* trace;      // development (-DSDFNMPC_QP_TRACE): cycles per phase of IPM iteration 2, [pass][16]; null = off
 };
 
 // Initial point of the interior-point iteration.  tools/qp_init_sweep.py: smaller floors / mu0 or an 'inactive-row' split of
@@ -392,6 +393,20 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
     res_v0 = L.max(res_v0);
 
     int status = 2, it = 0;
+#if defined(SDFNMPC_QP_TRACE) && defined(__CUDA_ARCH__)
+    long long qpt_last = clock64();
+    int qpt_pass = 0;
+#define QPT(id)                                                                          \
+    {                                                                                    \
+        if (P.trace && lane == 0) {                                                      \
+            const long long now_ = clock64();                                            \
+            if (it == 2) P.trace[qpt_pass * 16 + (id)] += now_ - qpt_last;               \
+            qpt_last = now_;                                                             \
+        }                                                                                \
+    }
+#else
+#define QPT(id)
+#endif
     bool safe = false;              // conservative mode after a stall: more centering, no second-order term
     double cm_prev1 = 1e300, cm_prev2 = 1e300;
     double phi = 1.0;               // product of (1 - alpha): scale of the stationarity / dynamics residuals
@@ -400,6 +415,9 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
         double tau = 0.0, mubar = 0.0;
         bool stop = false;
         for (int pass = 0; pass < 2 && !stop; ++pass) {
+#if defined(SDFNMPC_QP_TRACE) && defined(__CUDA_ARCH__)
+            qpt_pass = pass;
+#endif
             // =========== row elimination (lane = node): corrections of the stage Hessian / rhs ===========
             double res_rows = 0.0, cmax = 0.0, csum = 0.0;
             SDF_NODE_LOOP(kk) {
@@ -479,6 +497,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                 cm_prev2 = cm_prev1; cm_prev1 = cmax;
             }
             L.sync();
+                QPT(0);
             // =========== backward Riccati sweep (pass 0: factorise + solve; pass 1: new right-hand side only) ===========
             if (pass == 0) {
                 SDF_LANES_FOR(e, NX * NX) {
@@ -496,6 +515,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                 pv[e] = s;
             }
             L.sync();
+                QPT(2);
             // stage data of node kk is prefetched into the other half of `stg` while node kk+1 is processed
             // (every stage body ends with a lane barrier, so the slot being refilled is no longer read)
             auto prefetch = [&](int kk, int slot) {
@@ -517,37 +537,46 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                 const int slot = (N - 1 - kk) & 1;
                 const double* sb = stg + slot * S::STAGE_DOUBLES;
                 pipe.wait(L, slot);
+                QPT(3);
                 if (kk > 0) prefetch(kk - 1, slot ^ 1);
                 const double* ABk = sb + S::ST_AB;
                 if (pass == 0) {
-                    SDF_LANES_FOR(e, NX * NW) { const int i = e / NW; ABb[i * NWB + (e - i * NW)] = ABk[e]; }
-                    SDF_LANES_FOR(e, NX) ABb[e * NWB + NW] = phi * sb[S::ST_RD + e];
-                    L.sync();
+                    // PAB = P [A B | phi rd], read straight from the staged [A B] block and the staged residual
                     SDF_LANES_FOR(e, NX * NWB) {
-                        const int i = e / NWB, j = e - i * NWB;
                         double s = 0.0;
+                        if (e < NX * NW) {
+                            const int i = e / NW, j = e - i * NW;
 #pragma unroll
-                        for (int l = 0; l < NX; ++l) s += Psm[i * NX + l] * ABb[l * NWB + j];
-                        if (j == NW) { PbMk(kk)[i] = s; s += pv[i]; }
-                        PAB[e] = s;
+                            for (int l = 0; l < NX; ++l) s += Psm[i * NX + l] * ABk[l * NW + j];
+                            PAB[i * NWB + j] = s;
+                        } else {
+                            const int i = e - NX * NW;
+#pragma unroll
+                            for (int l = 0; l < NX; ++l) s += Psm[i * NX + l] * (phi * sb[S::ST_RD + l]);
+                            PbMk(kk)[i] = s;
+                            PAB[i * NWB + NW] = s + pv[i];
+                        }
                     }
                     L.sync();
+                QPT(5);
                     SDF_LANES_FOR(e, TRI + NW) {
                         if (e < TRI) {
                             const int i = tri.i[e], j = tri.j[e];
+                            const int ca = (i == j && i < NU) ? i : 15;
+                            const int pi_ = i - HC0, pj = j - HC0;
+                            const int cb = (pi_ >= 0 && pi_ < 3 && pj >= 0 && pj < 3) ? sym3(pi_, pj) : 15;
                             double s = sb[S::ST_H + i * NW + j];
 #pragma unroll
-                            for (int l = 0; l < NX; ++l) s += ABb[l * NWB + i] * PAB[l * NWB + j];
-                            if (i == j && i < NU) s += corr[i * KP + kk];
-                            const int pi_ = i - HC0, pj = j - HC0;
-                            if (pi_ >= 0 && pi_ < 3 && pj >= 0 && pj < 3) s += corr[(NU + sym3(pi_, pj)) * KP + kk];
+                            for (int l = 0; l < NX; ++l) s += ABk[l * NW + i] * PAB[l * NWB + j];
+                            if (ca != 15) s += corr[ca * KP + kk];
+                            if (cb != 15) s += corr[(NU + cb) * KP + kk];
                             Msm[i * NW + j] = s;
                             Msm[j * NW + i] = s;
                         } else {
                             const int i = e - TRI;
                             double s = phi * sb[S::ST_RV + i];
 #pragma unroll
-                            for (int l = 0; l < NX; ++l) s += ABb[l * NWB + i] * PAB[l * NWB + NW];
+                            for (int l = 0; l < NX; ++l) s += ABk[l * NW + i] * PAB[l * NWB + NW];
                             if (i < NU) s += corr[(NU + 6 + i) * KP + kk];
                             const int pi_ = i - HC0;
                             if (pi_ >= 0 && pi_ < 3) s += corr[(2 * NU + 6 + pi_) * KP + kk];
@@ -555,6 +584,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                         }
                     }
                     L.sync();
+                QPT(6);
                     // Cholesky of Ruu (every lane, redundantly, in registers); diagonal kept inverted
                     double Lr[NU][NU];
                     bool ok = true;
@@ -595,6 +625,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                         for (int i = 0; i < NU; ++i)
                             for (int j = 0; j < NU; ++j) Lgk(kk)[i * NU + j] = j <= i ? Lr[i][j] : 0.0;
                     L.sync();
+                QPT(7);
                     // P <- Qxx + Rux' K (lower triangle, mirrored: stays exactly symmetric), p <- r_x + Rux' kff
                     constexpr int TRX = NX * (NX + 1) / 2;
                     SDF_LANES_FOR(e, TRX + NX + NU) {
@@ -617,6 +648,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                         }
                     }
                     L.sync();
+                QPT(8);
                 } else {
                     SDF_LANES_FOR(e, NX) vv[e] = sb[S::ST_PB + e] + pv[e];   // PbM already carries this iteration's phi
                     L.sync();
@@ -658,11 +690,13 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                         }
                     }
                     L.sync();
+                QPT(9);
                 }
             }
             // ---------- forward roll-out: dW = step ----------
             SDF_LANES_FOR(i, NX) dW[(NU + i) * KP] = 0.0;      // dx_0 = 0 (w_x0 already equals x0 - xbar_0)
             L.sync();
+                QPT(10);
             auto prefetch_f = [&](int kk, int slot) {
                 double* dst = stg + slot * S::STAGE_DOUBLES;
                 pipe.begin(L, slot, (NX * NW + NX + NU * NX) * 8);
@@ -676,6 +710,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                 const int slot = kk & 1;
                 const double* sb = stg + slot * S::STAGE_DOUBLES;
                 pipe.wait(L, slot);
+                QPT(11);
                 if (kk + 1 < N) prefetch_f(kk + 1, slot ^ 1);
                 const double* Kk = sb + S::ST_K;
                 SDF_LANES_FOR(j, NU) {
@@ -693,6 +728,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                     dW[(NU + i) * KP + kk + 1] = s;
                 }
                 L.sync();
+                QPT(12);
             }
             // =========== row steps (lane = node): the node's (dt, dlam, ds, dmu) stay in registers ===========
             double rmax = 0.0;              // largest -dx/x over the lane's rows
@@ -777,6 +813,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                 sig = fmin(fmax(sig * sig * sig, safe ? 0.2 : 0.0), 1.0);
                 tau = fmax(sig * mubar, 0.1 * P.tol);
                 L.sync();
+                QPT(14);
             } else {
                 // =========== damped step ===========
                 const double al = fmin(1.0, 0.995 * amax);
@@ -792,6 +829,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                 for (int e = lane; e < NW * KP; e += NL) Wsm[e] += al * dW[e];
                 phi *= (1.0 - al);
                 L.sync();
+                QPT(15);
             }
         }
         if (stop || status == 4) break;
@@ -859,6 +897,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
     }
 }
 
+#undef QPT
 #undef SDF_NODE_LOOP
 #undef SDF_LANES_FOR
 #undef SDF_LOAD_STATE

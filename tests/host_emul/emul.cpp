@@ -65,6 +65,7 @@ extern "C" void emul_qp(int B, int N, int k0, int max_iter, int nyN, double lm, 
         P.lam_hard = lam_hard + (size_t)b * N * 2 * NU;
         P.lam_soft = lam_soft + (size_t)b * (N + 1) * 2 * NH;
         P.res_out = nullptr;
+        P.trace = nullptr;
         P.status = status + b;
         P.iters = iters + b;
         qp_solve_instance<NX, NU, NY, NH>(L, P, sm.data());
