@@ -97,9 +97,11 @@ int build_tc(sdfnmpc_sdf* h, const float* W1, const float* W2, const float* W3, 
     // forward
     for (int j = 0; j < c1; ++j) add(TC_PROD_EMBED, 0, 32 * j, 0, 0, oW1[j], n.H1, 0, j == 0, j == c1 - 1);
     for (int j = 0; j < cH1; ++j) add(TC_PROD_ACT, 0 + 32 * j, 32 * j, 1, j == 0, oW2[j], n.H2, 256, j == 0, j == cH1 - 1);
-    for (int j = 0; j < cH2; ++j) add(TC_PROD_ACT, 256 + 32 * j, 32 * j, 2, j == 0, oW3h[j], n.H3, 0, j == 0, (!n.res_state) && j == cH2 - 1);
+    // layer 3 input [h2; e]: the skip-connection (embedding) chunks go FIRST - they do not read TMEM, so the producers build
+    // them while the last MMAs of layer 2 drain, instead of idling at the layer boundary
     if (n.res_state)
-        for (int j = 0; j < c1; ++j) add(TC_PROD_EMBED, 0, 32 * j, 0, 0, oW3e[j], n.H3, 0, 0, j == c1 - 1);
+        for (int j = 0; j < c1; ++j) add(TC_PROD_EMBED, 0, 32 * j, 0, 0, oW3e[j], n.H3, 0, j == 0, 0);
+    for (int j = 0; j < cH2; ++j) add(TC_PROD_ACT, 256 + 32 * j, 32 * j, 2, j == 0, oW3h[j], n.H3, 0, (!n.res_state) && j == 0, j == cH2 - 1);
     for (int j = 0; j < cH3; ++j) add(TC_PROD_ACT, 0 + 32 * j, 32 * j, 3, j == 0, oW4[j], n.H4, 128, j == 0, j == cH3 - 1);
     // reverse
     for (int j = 0; j < cH4; ++j) add(TC_PROD_G4, 128 + 32 * j, 32 * j, 4, j == 0, oW4T[j], n.H3, 0, j == 0, j == cH4 - 1);
