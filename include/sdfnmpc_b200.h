@@ -90,6 +90,7 @@ typedef struct {
     int32_t reserved;
     double ax, ay, az;       /* robot.limits.ax/ay/az (model acc)                           */
     double tau_roll, tau_pitch; /* attitude lag of att_tau (0 -> 0.12 s, quad_rollpitchyawrate_tau.py:19-20) */
+    double sdf_cost_w;       /* flags.sdf_cost: weight of the stage cost row (1 - 0.5 sdf)^4 (gen_model.py:65-66: 20); 0 = off */
 } sdfnmpc_solver_desc;
 
 int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver_desc* desc, sdfnmpc_sdf_t sdf);

@@ -89,6 +89,12 @@ def linearize(net, xb, ub, prob, cfg):
         Wk = prob['W'][:, k]
         H[:, k] = dt[k] * (np.einsum('byi,by,byj->bij', J, Wk, J) + cfg['lm'] * np.eye(14)[None])
         g[:, k] = dt[k] * np.einsum('byi,by->bi', J, Wk * (y - prob['yref'][:, k]))
+        if cfg.get('sdf_cost_w', 0.0) > 0:      # flags.sdf_cost: stage cost row (1 - 0.5 sdf)^4, weight 20 (gen_model.py:65-66)
+            hk, Jp = eval_h(net, xb[:, k], prob, cfg)
+            qq = 1.0 - 0.5 * hk[:, 2]
+            rr, Jr = qq ** 4, -2.0 * (qq ** 3)[:, None] * Jp[:, 2, :]
+            H[:, k, 4:7, 4:7] += dt[k] * cfg['sdf_cost_w'] * np.einsum('bi,bj->bij', Jr, Jr)
+            g[:, k, 4:7] += dt[k] * cfg['sdf_cost_w'] * rr[:, None] * Jr
     yN, JN = mdl.y_fun(xb[:, N], np.zeros((B, 4)), prob['qd'][:, N], cfg)
     yN, JN = yN[:, :nyN], JN[:, :nyN, 4:]
     HN = np.einsum('byi,by,byj->bij', JN, prob['WN'], JN) + cfg['lm'] * np.eye(10)[None]
@@ -133,15 +139,19 @@ def condense(lin, xb, ub, prob, cfg, max_df):
     CG = np.einsum('bkrx,bkxn->bkrn', lin['C'][:, k0:], Gam[:, k0:]).reshape(B, nk * 3, nv)
     Cg = np.einsum('bkrx,bkx->bkr', lin['C'][:, k0:], gam[:, k0:]).reshape(B, nk * 3)
     hb = lin['hbar'][:, k0:].reshape(B, nk * 3)
+    # rows the mission flags switch off (gen_model.py:41,67-70) are REMOVED here: cfg['h_off'] = bool[3] in h order
+    keep = np.tile(~np.asarray(cfg.get('h_off', [False] * 3), bool), nk)
+    CG, Cg, hb = CG[:, keep], Cg[:, keep], hb[:, keep]
+    nh = int(keep.sum())
     rows_G += [CG, -CG]
-    rows_d += [np.tile(lh, nk)[None] - hb - Cg, -(np.tile(uh, nk)[None] - hb - Cg)]
+    rows_d += [np.tile(lh, nk)[keep][None] - hb - Cg, -(np.tile(uh, nk)[keep][None] - hb - Cg)]
     G = np.concatenate(rows_G, 1); d = np.concatenate(rows_d, 1)
-    soft = np.concatenate([np.zeros(2 * nv, bool), np.ones(2 * nk * 3, bool)])
+    soft = np.concatenate([np.zeros(2 * nv, bool), np.ones(2 * nh, bool)])
     # slack penalties of stage rows (nodes k0..N-1) are scaled by Ts_k, terminal rows by 1
     sc = np.concatenate([np.repeat(cfg['dt'][k0:N], 3), np.ones(3)])
-    zz = np.concatenate([np.zeros(2 * nv), np.tile(zl, nk) * sc, np.tile(zl, nk) * sc])
-    ZZ = np.concatenate([np.zeros(2 * nv), np.tile(Zl, nk) * sc, np.tile(Zl, nk) * sc])
-    return dict(P=P, q=q, G=G, d=d, soft=soft, z=zz, Z=ZZ, Gam=Gam, gam=gam, nk=nk)
+    zz = np.concatenate([np.zeros(2 * nv), (np.tile(zl, nk) * sc)[keep], (np.tile(zl, nk) * sc)[keep]])
+    ZZ = np.concatenate([np.zeros(2 * nv), (np.tile(Zl, nk) * sc)[keep], (np.tile(Zl, nk) * sc)[keep]])
+    return dict(P=P, q=q, G=G, d=d, soft=soft, z=zz, Z=ZZ, Gam=Gam, gam=gam, nk=nk, keep=keep)
 
 
 def rti_step(net, xb, ub, prob, cfg):
@@ -157,10 +167,18 @@ def rti_step(net, xb, ub, prob, cfg):
     un = ub + U.reshape(B, N, 4)
     nv, nk = 4 * N, cq['nk']
     lam = sol['lam']
+    keep = cq['keep']
+    nh = int(keep.sum())
+
+    def full(v):            # removed rows report zero multiplier / slack
+        o = np.zeros((B, nk * 3))
+        o[:, keep] = v
+        return o.reshape(B, nk, 3)
+
     out = dict(u0=un[:, 0].copy(), status=sol['status'], qp_iters=sol['iters'],
                lam_lbu=lam[:, :nv].reshape(B, N, 4), lam_ubu=lam[:, nv:2 * nv].reshape(B, N, 4),
-               lam_lh=lam[:, 2 * nv:2 * nv + 3 * nk].reshape(B, nk, 3), lam_uh=lam[:, 2 * nv + 3 * nk:].reshape(B, nk, 3),
-               slack_l=sol['s'][:, 2 * nv:2 * nv + 3 * nk].reshape(B, nk, 3), slack_u=sol['s'][:, 2 * nv + 3 * nk:].reshape(B, nk, 3),
+               lam_lh=full(lam[:, 2 * nv:2 * nv + nh]), lam_uh=full(lam[:, 2 * nv + nh:]),
+               slack_l=full(sol['s'][:, 2 * nv:2 * nv + nh]), slack_u=full(sol['s'][:, 2 * nv + nh:]),
                du=U.reshape(B, N, 4), dx=dx, lin=lin, qp=cq)
     return xn, un, out
 

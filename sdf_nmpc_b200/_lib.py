@@ -29,7 +29,7 @@ class SolverDesc(C.Structure):
                 ('lbu', C.c_double * 4), ('ubu', C.c_double * 4), ('lh', C.c_double * 3), ('uh', C.c_double * 3),
                 ('zl', C.c_double * 3), ('Zl', C.c_double * 3), ('dt', C.c_double * MAX_N),
                 ('model', C.c_int32), ('reserved', C.c_int32), ('ax', C.c_double), ('ay', C.c_double), ('az', C.c_double),
-                ('tau_roll', C.c_double), ('tau_pitch', C.c_double)]
+                ('tau_roll', C.c_double), ('tau_pitch', C.c_double), ('sdf_cost_w', C.c_double)]
 
 
 class EncoderDesc(C.Structure):

@@ -27,7 +27,7 @@ constexpr int QP_WARPS = QP_WARPS_PER_CTA;     // instances per CTA
 struct SolverConst {
     ModelConst mc;
     int N, k0, qp_iter_max, model, nyN;
-    double lm, tol, tol_res, u_hover;
+    double lm, tol, tol_res, u_hover, sdf_cost_w;
     double lbu[NU], ubu[NU], lh[NH], uh[NH], zs[NH], Zs[NH];
     double cmd_min[4], cmd_max[4];
 };
@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32, QP_MIN_CTAS) nmpc_qp_kernel(Sol
     Prob P;
     P.N = N; P.k0 = scs.k0; P.max_iter = scs.qp_iter_max; P.nyN = scs.nyN;
     P.lm = scs.lm; P.tol = scs.tol; P.tol_res = scs.tol_res; P.max_df = q.max_df; P.flag = q.flag[b];
+    P.sdf_cost_w = scs.sdf_cost_w;
     P.AB = q.AB + (size_t)b * N * NX * NW;
     P.bdyn = q.bdyn + (size_t)b * N * NX;
     P.J = q.J + (size_t)b * (N + 1) * NY * NW;
@@ -185,7 +186,7 @@ extern "C" int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver
     sc.mc.ax = d->ax; sc.mc.ay = d->ay; sc.mc.az = d->az;
     sc.mc.tau_roll = d->tau_roll > 0 ? d->tau_roll : 0.12; sc.mc.tau_pitch = d->tau_pitch > 0 ? d->tau_pitch : 0.12;
     sc.N = d->N; sc.k0 = d->h_at_node0 ? 0 : 1; sc.qp_iter_max = d->qp_iter_max;
-    sc.lm = d->lm; sc.tol = d->qp_tol; sc.tol_res = d->qp_tol_res;
+    sc.lm = d->lm; sc.tol = d->qp_tol; sc.tol_res = d->qp_tol_res; sc.sdf_cost_w = d->sdf_cost_w > 0 ? d->sdf_cost_w : 0.0;
     for (int i = 0; i < NU; ++i) { sc.lbu[i] = d->lbu[i]; sc.ubu[i] = d->ubu[i]; }
     for (int i = 0; i < NH; ++i) { sc.lh[i] = d->lh[i]; sc.uh[i] = d->uh[i]; sc.zs[i] = d->zl[i]; sc.Zs[i] = d->Zl[i]; }
     // controller.py:21-23: thrust command clipped at limits.gamma (not gamma*mass) - kept for parity

@@ -72,6 +72,7 @@ template <int NX, int NU, int NY, int NH>
 struct QpProb {            // all pointers are offset to ONE instance
     int N, k0, max_iter, nyN;
     double lm, tol, tol_res, max_df, flag;
+    double sdf_cost_w;     // weight of the optional stage cost row (1 - 0.5 sdf)^4 (flags.sdf_cost, gen_model.py:65-66); 0 = off
     const double* AB;      // [N][NX][NW]
     const double* bdyn;    // [N][NX]
     const double* J;       // [N+1][NY][NW]
@@ -243,19 +244,33 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
     auto wrow = [&](int k, int r) { return k < N ? P.W[k * NY + r] : (r < P.nyN ? P.WN[r] : 0.0); };
 
     // ---- prologue: sdf row of C / h, Gauss-Newton Hessian and gradient ----------------------
-    for (int k = k0 + lane; k <= N; k += NL) {
+    const bool sdf_cost = P.sdf_cost_w > 0.0;          // the cost row also needs the SDF at node 0
+    for (int k = (sdf_cost ? 0 : k0) + lane; k <= N; k += NL) {
         const double* R = P.pose + 3;
         double gx = P.sdf_g[k * 3 + 0], gy = P.sdf_g[k * 3 + 1], gz = P.sdf_g[k * 3 + 2];
         double* Cr = P.C + ((size_t)k * NH + (NH - 1)) * NW;
         for (int jj = 0; jj < 3; ++jj) Cr[HC0 + jj] = P.flag * (R[jj * 3 + 0] * gx + R[jj * 3 + 1] * gy + R[jj * 3 + 2] * gz);
         P.hval[k * NH + (NH - 1)] = P.flag * (double)P.sdf_d[k] + (1.0 - P.flag) * P.max_df;
     }
+    if (sdf_cost) L.sync();
+    // optional cost row r = (1 - 0.5 d)^4 on the stage nodes: dr/dp = -2 (1 - 0.5 d)^3 dd/dp, only the position block
+    auto cost_r = [&](int k, double& r, double* Jr) {
+        const double q = 1.0 - 0.5 * P.hval[k * NH + (NH - 1)];
+        const double* Cr = P.C + ((size_t)k * NH + (NH - 1)) * NW;
+        r = q * q * q * q;
+        for (int c = 0; c < 3; ++c) Jr[c] = -2.0 * q * q * q * Cr[HC0 + c];
+    };
     for (int e = lane; e < (N + 1) * TRI; e += NL) {
         const int k = e / TRI, t = e - k * TRI, i = tri.i[t], j = tri.j[t];
         const double* Jk = P.J + (size_t)k * NY * NW;
         double s = 0.0;
         for (int r = 0; r < NY; ++r) s += Jk[r * NW + i] * wrow(k, r) * Jk[r * NW + j];
         if (i == j) s += P.lm;
+        if (sdf_cost && k < N && i >= HC0 && i < HC0 + 3 && j >= HC0 && j < HC0 + 3) {
+            double r, Jr[3];
+            cost_r(k, r, Jr);
+            s += P.sdf_cost_w * Jr[i - HC0] * Jr[j - HC0];
+        }
         s *= scale(k);
         Hk(k)[i * NW + j] = s;
         Hk(k)[j * NW + i] = s;
@@ -266,6 +281,11 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
         const double* yr = P.yres + (size_t)k * NY;
         double s = 0.0;
         for (int r = 0; r < NY; ++r) s += Jk[r * NW + i] * wrow(k, r) * yr[r];
+        if (sdf_cost && k < N && i >= HC0 && i < HC0 + 3) {
+            double r, Jr[3];
+            cost_r(k, r, Jr);
+            s += P.sdf_cost_w * r * Jr[i - HC0];
+        }
         g[e] = scale(k) * s;
         const double w0 = (k == 0 && i >= NU) ? P.x0[i - NU] - P.xbar[i - NU] : 0.0;
         Wsm[i * KP + k] = w0;

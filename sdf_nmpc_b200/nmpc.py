@@ -41,6 +41,14 @@ class BatchedNmpc:
         self.g = 9.81
         self.dt = cfg.shooting_dt()
         lh, uh = cfg.h_bounds(self.sdf.max_df)
+        # mission flags (gen_model.py:26-70): a row the reference would not add is kept with bounds that can never be
+        # active, which leaves the optimum unchanged (slack 0, multiplier 0)
+        fl = cfg.get('flags', {})
+        off = [not fl.get('enable_sdf', True) or not (cfg.sensor.hfov < 3.14),
+               not fl.get('enable_sdf', True) or not fl.get('vfov_constraint', True),
+               not fl.get('enable_sdf', True) or not fl.get('sdf_constraint', True)]
+        lh, uh = np.where(off, -1e6, lh), np.where(off, 1e6, uh)
+        self.sdf_cost_w = 20.0 if (fl.get('enable_sdf', True) and fl.get('sdf_cost', False)) else 0.0
         zl, Zl = cfg.slack_weights()
         d = _lib.SolverDesc()
         d.N, d.max_batch, d.qp_iter_max, d.h_at_node0 = self.N, self.B, int(cfg.b200.qp_iter_max), int(bool(cfg.b200.h_at_node0))
@@ -51,6 +59,7 @@ class BatchedNmpc:
         d.model = MODEL_ID[self.model]
         d.ax, d.ay, d.az = float(lim.ax), float(lim.ay), float(lim.az)
         d.tau_roll = d.tau_pitch = 0.12                   # quad_rollpitchyawrate_tau.py:19-20 (constants in the reference)
+        d.sdf_cost_w = self.sdf_cost_w
         d.ubu = (C.c_double * 4)(1, 1, 1, 1)
         d.lh, d.uh = (C.c_double * 3)(*lh), (C.c_double * 3)(*uh)
         d.zl, d.Zl = (C.c_double * 3)(*zl), (C.c_double * 3)(*Zl)

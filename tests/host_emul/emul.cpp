@@ -30,7 +30,7 @@ extern "C" void emul_linearize(int model, int nyN, int B, int N, const double* m
             }
 }
 
-extern "C" void emul_qp(int B, int N, int k0, int max_iter, int nyN, double lm, double tol, double tol_res,
+extern "C" void emul_qp(int B, int N, int k0, int max_iter, int nyN, double sdf_cost_w, double lm, double tol, double tol_res,
                         double max_df, const double* flag, const double* AB, const double* bdyn, const double* J,
                         const double* yres, double* C, double* hval, const double* W, const double* WN,
                         const double* dt, const double* lbu, const double* ubu, const double* lh, const double* uh,
@@ -45,6 +45,7 @@ extern "C" void emul_qp(int B, int N, int k0, int max_iter, int nyN, double lm, 
         Prob P;
         P.N = N; P.k0 = k0; P.max_iter = max_iter; P.nyN = nyN;
         P.lm = lm; P.tol = tol; P.tol_res = tol_res; P.max_df = max_df; P.flag = flag[b];
+        P.sdf_cost_w = sdf_cost_w;
         P.AB = AB + (size_t)b * N * NX * NW;
         P.bdyn = bdyn + (size_t)b * N * NX;
         P.J = J + (size_t)b * (N + 1) * NY * NW;

@@ -361,3 +361,48 @@ def test_config_variants_match_oracle(variant, cuda_device):
         assert np.abs(mpc.get_u().cpu().numpy() - out['u0']).max() <= U_TOL, (variant, step)
         x, u = mpc.get_matrices()
         assert np.abs(x.cpu().numpy() - xb).max() <= 1e-3 and np.abs(u.cpu().numpy() - ub).max() <= 1e-3
+
+
+@pytest.mark.parametrize('variant', ['sdf_cost', 'no_vfov', 'no_sdf_constraint', 'cost_only'])
+def test_mission_flags_match_oracle(variant, cuda_device):
+    """Mission flags of the reference NLP (gen_model.py:26-70): the optional SDF cost row (1 - 0.5 sdf)^4 and switching
+    individual constraint rows off.  The oracle REMOVES switched-off rows; the product keeps them with unreachable bounds."""
+    import torch
+    from oracle import rti
+    from sdf_nmpc_b200 import synth
+    from sdf_nmpc_b200.config import Config
+    from sdf_nmpc_b200.nmpc import BatchedNmpc
+    B = 12
+    net = synth.make_sdf_net(seed=0, **synth.ARCH_B, calibrated=True)
+    cfg = Config()
+    ocfg = rti.default_cfg()
+    if variant in ('sdf_cost', 'cost_only'):
+        cfg.flags.sdf_cost = True
+        ocfg['sdf_cost_w'] = 20.0
+    if variant == 'no_vfov':
+        cfg.flags.vfov_constraint = False
+        ocfg['h_off'] = [False, True, False]
+    if variant in ('no_sdf_constraint', 'cost_only'):
+        cfg.flags.sdf_constraint = False
+        ocfg['h_off'] = [False, False, True]
+    prob, w = make_problem(B, ocfg)
+    mpc = BatchedNmpc(cfg, net, B, cuda_device)
+    mpc.set_sdf_flag(1.0)
+    mpc.set_latent(w['latent'], w['W_p_Bo'], w['W_R_Bo'])
+    mpc.set_ref_arrays(w['yref'], w['W'], w['yrefN'], w['WN'], w['qd'])
+    xb, ub = rti.init_traj(prob['x0'], ocfg)
+    u_plain = None
+    for step in range(3):
+        mpc.set_x0(prob['x0'])
+        assert int(mpc.solve().max().item()) == 0
+        xb, ub, out = rti.rti_step(net, xb, ub, prob, ocfg)
+        assert np.abs(mpc.get_u().cpu().numpy() - out['u0']).max() <= U_TOL, (variant, step)
+    # the flag really changes the problem: controls differ from the default configuration
+    ocfg0 = rti.default_cfg()
+    xb0, ub0 = rti.init_traj(prob['x0'], ocfg0)
+    for step in range(3):
+        xb0, ub0, out0 = rti.rti_step(net, xb0, ub0, prob, ocfg0)
+    assert np.abs(out0['u0'] - out['u0']).max() > 1e-4
+    _, lam_s = mpc.get_multipliers()
+    if variant == 'no_vfov':
+        assert float(lam_s[:, :, [1, 4]].abs().max()) < 1e-6

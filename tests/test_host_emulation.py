@@ -47,7 +47,7 @@ def _emul_step(lib, net, cfg, prob, xe, ue):
     u0 = np.zeros((B, 4)); lamh = np.zeros((B, N, 8)); lams = np.zeros((B, N + 1, 6))
     st = np.zeros(B, np.int32); its = np.zeros(B, np.int32)
     D = ctypes.c_double
-    lib.emul_qp(B, N, 1, 100, nyN, D(cfg['lm']), D(1e-8), D(1e-7), D(net['max_df']), _P(flag), _P(AB), _P(bd), _P(J), _P(yr), _P(C),
+    lib.emul_qp(B, N, 1, 100, nyN, D(cfg.get('sdf_cost_w', 0.0)), D(cfg['lm']), D(1e-8), D(1e-7), D(net['max_df']), _P(flag), _P(AB), _P(bd), _P(J), _P(yr), _P(C),
                 _P(hv), _P(W), _P(WN), _P(cfg['dt']), _P(cfg['lbu']), _P(cfg['ubu']), _P(lh), _P(uh), _P(zs), _P(Zs), _P(d), _P(g),
                 _P(pose), _P(x0), _P(xe), _P(ue), _P(u0), _P(lamh), _P(lams), _P(st), _P(its))
     return u0, st, its, lamh, lams, lin
