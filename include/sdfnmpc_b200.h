@@ -129,6 +129,15 @@ int sdfnmpc_cmd_trpyr(sdfnmpc_solver_t h, int32_t B, const double* u_dev, double
 /* u_to_acc + clip (controller.py:101-103): cmd [B][4] = [W_R_B^T W_a, wz] from x0 [B][10] and u [B][4]; all models. */
 int sdfnmpc_cmd_acc(sdfnmpc_solver_t h, int32_t B, const double* x0_dev, const double* u_dev, double* cmd_dev, void* stream);
 
+/* ------------------------------------------------------------------ collision labels ----- */
+/* ColChecker.check_image_points (sdf_nmpc/utils/collision_checker.py:23-125): ground-truth collision label of each point
+ * (Cartesian, sensor frame, metres) against the range / depth image it belongs to.  imgs [B][H][W] normalised by dmax;
+ * p2i [n] image index per point or NULL (points are then split evenly, in order, over the B images);
+ * outside: 0 free, 1 collision, 2 extrapolate (clamp to the frustum); out [n] 0 / 1.  All pointers are device pointers. */
+int sdfnmpc_colcheck(const float* imgs_dev, int32_t B, int32_t H, int32_t W, const float* pts_dev, const int32_t* p2i_dev, int64_t n,
+                     float dmax, float hfov, float vfov, float safe_ball, int32_t outside, int32_t is_depth, int32_t is_spherical,
+                     uint8_t* out_dev, void* stream);
+
 /* ------------------------------------------------------------------ depth encoder ------- */
 typedef struct sdfnmpc_encoder* sdfnmpc_encoder_t;
 

@@ -559,6 +559,67 @@ extern "C" int sdfnmpc_encoder_encode(sdfnmpc_encoder_t h, const float* imgs, in
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Ground-truth collision labels of points against range / depth images: the function of the Warp kernel
+// ColChecker._kernel_colcheck (sdf_nmpc/utils/collision_checker.py:23-91), one thread per point.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void colcheck_kernel(const float* __restrict__ img, int H, int W, const float* __restrict__ pts, const int* __restrict__ p2i,
+                                long long n, long long pts_per_img, float dmax, float hfov, float vfov, float safe_ball, int outside,
+                                int is_depth, int is_spherical, unsigned char* __restrict__ out) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= n) return;
+    const float px = pts[tid * 3], py = pts[tid * 3 + 1], pz = pts[tid * 3 + 2];
+    unsigned char col = 0;
+    const float len = sqrtf(px * px + py * py + pz * pz);
+    if (len > safe_ball) {                                  // inside the safe ball around the sensor: never in collision
+        const float val = is_depth ? px : len;
+        if (val >= dmax) {
+            col = 1;                                        // past dmax is unsafe by default
+        } else {
+            float az = atan2f(py, px);
+            float el = is_spherical ? atan2f(pz, sqrtf(px * px + py * py)) : atan2f(pz, px);
+            bool inside = true;
+            if (outside == 2) {                             // extrapolate: clamp to the frustum
+                az = fminf(fmaxf(az, -hfov), hfov);
+                el = fminf(fmaxf(el, -vfov), vfov);
+            } else if (fabsf(az) >= hfov || fabsf(el) >= vfov) {
+                col = outside == 1 ? 1 : 0;
+                inside = false;
+            }
+            if (inside) {
+                const float w = (float)W, h = (float)H;
+                int u, v;
+                if (is_spherical) {
+                    u = (int)(w / 2.f * (1.f - az / hfov));
+                    v = (int)(h / 2.f * (1.f - el / vfov));
+                } else {
+                    u = (int)(w / 2.f * (1.f - tanf(az) / tanf(hfov)));
+                    v = (int)(h / 2.f * (1.f - tanf(el) / tanf(vfov)));
+                }
+                u = min(max(u, 0), W - 1);
+                v = min(max(v, 0), H - 1);
+                const long long ii = p2i ? (long long)p2i[tid] : tid / pts_per_img;
+                if (val >= img[(ii * H + v) * W + u] * dmax) col = 1;
+            }
+        }
+    }
+    out[tid] = col;
+}
+
+extern "C" int sdfnmpc_colcheck(const float* imgs, int32_t B, int32_t H, int32_t W, const float* pts, const int32_t* p2i, int64_t n,
+                                float dmax, float hfov, float vfov, float safe_ball, int32_t outside, int32_t is_depth,
+                                int32_t is_spherical, uint8_t* out, void* stream) {
+    if (n == 0) return 0;
+    if (!imgs || !pts || !out || B < 1 || H < 1 || W < 1 || n < 0 || outside < 0 || outside > 2) return SDFNMPC_E_INVALID;
+    if (int rc = ensure_device()) return rc;
+    const long long ppi = (n + B - 1) / B;
+    colcheck_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(imgs, H, W, pts, p2i, n, ppi, dmax, hfov, vfov, safe_ball,
+                                                                                  outside, is_depth, is_spherical, out);
+    count_launch();
+    SDF_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int sdfnmpc_encoder_encode_host(sdfnmpc_encoder_t h, const float* imgs, int32_t B, float* latents) {
     if (!h || !imgs || !latents || B < 1 || B > h->desc.max_batch) return SDFNMPC_E_INVALID;
     const size_t img_floats = (size_t)h->desc.height * h->desc.width;
