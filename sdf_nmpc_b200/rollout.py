@@ -31,7 +31,7 @@ def rollout(cfg, sdf_net, enc_net, n_env, steps, first=0, mode='rti', encode_eve
     scene = torch.from_numpy((np.arange(first, first + n_env) % n_scenes).astype(np.int64)).to(dev)
     pool_d = torch.from_numpy(pool).to(dev)
     frames = pool_d[scene]                                             # [n_env, H, W] raw sensor images
-    vae = VaeWrapper(cfg, enc_net, max_batch=n_env, device=device)
+    vae = VaeWrapper(cfg, enc_net, max_batch=min(n_env, 256), device=device)      # encode() walks larger batches in chunks of 256
     mpc = BatchedNmpc(cfg, sdf_net, n_env, device)
     rg = BatchedRefGen(cfg)
     cc = ColChecker(cfg.sensor.dmax, cfg.sensor.hfov, cfg.sensor.vfov, cfg.robot.size.xy, is_depth=bool(cfg.sensor.is_depth),
