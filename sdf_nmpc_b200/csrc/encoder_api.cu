@@ -242,26 +242,41 @@ conv0_pool_kernel(int Hin, int Win, int Hc, int Wc, int Hp, int Wp, const float*
     }
 }
 
-// AdaptiveAvgPool2d((2,2)) + Flatten + Linear(4C -> L); one CTA per frame
+// AdaptiveAvgPool2d((2,2)) + Flatten + Linear(4C -> L).  Grid (frames, PL_SPLIT): every CTA pools the frame's whole feature
+// map (a warp per channel, lanes over the H*W contiguous pixels: coalesced) and computes L / PL_SPLIT of the outputs, so
+// that a batch of 64 frames fills the GPU instead of 64 SMs.
+constexpr int PL_SPLIT = 4;
 __global__ void __launch_bounds__(256)
 pool_linear_kernel(int C, int H, int W, int L, const float* __restrict__ feat, const float* __restrict__ mw,
                    const float* __restrict__ mb, float* __restrict__ latents) {
-    extern __shared__ float f[];   // [4C]
+    extern __shared__ float f[];   // [4C], index c*4 + py*2 + px (the Flatten order of [C, 2, 2])
     const int b = blockIdx.x;
     const float* fb = feat + (size_t)b * C * H * W;
-    for (int idx = threadIdx.x; idx < 4 * C; idx += blockDim.x) {
-        const int c = idx >> 2, py = (idx >> 1) & 1, px = idx & 1;
-        // torch adaptive pooling bins: [floor(i*In/Out), ceil((i+1)*In/Out))
-        const int y0 = (py * H) / 2, y1 = ((py + 1) * H + 1) / 2;
-        const int x0 = (px * W) / 2, x1 = ((px + 1) * W + 1) / 2;
-        float sum = 0.f;
-        for (int y = y0; y < y1; ++y)
-            for (int x = x0; x < x1; ++x) sum += fb[((size_t)c * H + y) * W + x];
-        f[idx] = sum / (float)((y1 - y0) * (x1 - x0));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    // torch adaptive pooling bins: [floor(i*In/Out), ceil((i+1)*In/Out)) - with an odd size the middle row / column is in both
+    const int ya1 = (H + 1) / 2, yb0 = H / 2, xa1 = (W + 1) / 2, xb0 = W / 2;
+    const float inv[4] = {1.f / (float)(ya1 * xa1), 1.f / (float)(ya1 * (W - xb0)), 1.f / (float)((H - yb0) * xa1), 1.f / (float)((H - yb0) * (W - xb0))};
+    for (int c = warp; c < C; c += nw) {
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int p = lane; p < H * W; p += 32) {
+            const int y = p / W, x = p - y * W;
+            const float v = fb[(size_t)c * H * W + p];
+            const bool ta = y < ya1, tb = y >= yb0, la = x < xa1, lb = x >= xb0;
+            if (ta && la) s[0] += v;
+            if (ta && lb) s[1] += v;
+            if (tb && la) s[2] += v;
+            if (tb && lb) s[3] += v;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
+        }
+        if (lane < 4) f[c * 4 + lane] = s[lane] * inv[lane];
     }
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    for (int l = warp; l < L; l += nw) {
+    const int lper = (L + PL_SPLIT - 1) / PL_SPLIT, l0 = blockIdx.y * lper, l1 = min(L, l0 + lper);
+    for (int l = l0 + warp; l < l1; l += nw) {
         const float* wr = mw + (size_t)l * 4 * C;
         float sum = 0.f;
         for (int j = lane; j < 4 * C; j += 32) sum = fmaf(wr[j], f[j], sum);
@@ -553,7 +568,7 @@ extern "C" int sdfnmpc_encoder_encode(sdfnmpc_encoder_t h, const float* imgs, in
             float* tmp = x; x = t2; t2 = tmp;
         }
     }
-    pool_linear_kernel<<<B, 256, 2048 * sizeof(float), st>>>(512, h->Hf, h->Wf, h->desc.size_latent, x, h->mean_w, h->mean_b, latents);
+    pool_linear_kernel<<<dim3(B, PL_SPLIT), 256, 2048 * sizeof(float), st>>>(512, h->Hf, h->Wf, h->desc.size_latent, x, h->mean_w, h->mean_b, latents);
     count_launch();
     SDF_CUDA_CHECK(cudaGetLastError());
     return 0;
