@@ -117,7 +117,9 @@ int build_tc(sdfnmpc_sdf* h, const float* W1, const float* W2, const float* W3, 
             o.n_rows[0] = 128; o.d_col[1] = 384; o.n_rows[1] = n.H1 - 128; o.b_row0[1] = 128;
         }
     }
-    for (int j = 0; j < cH1; ++j) add(TC_PROD_MUL, j < 4 ? 32 * j : 384 + 32 * (j - 4), 32 * j, 1, j == 0, oW1T[j], n.Ep, 128, j == 0, j == cH1 - 1);
+    // D_ge1 @256 (D_g2 is dead by then): columns 0..255 stay free for the NEXT tile's D1, whose first chunks the producers
+    // build before they drain this tile's result (sdf_tc_kernel.cuh)
+    for (int j = 0; j < cH1; ++j) add(TC_PROD_MUL, j < 4 ? 32 * j : 384 + 32 * (j - 4), 32 * j, 1, j == 0, oW1T[j], n.Ep, 256, j == 0, j == cH1 - 1);
 
     // accumulator completions: d_commit = index of the accumulator an op publishes, d_need = index a TMEM-reading op needs
     {

@@ -17,7 +17,7 @@
 //     pre-laid-out on the host) into the stage whose previous MMAs have retired.
 //   A chunk "program" (SdfTcOp[]) built on the host drives all roles in lock-step.
 // TMEM column plan (512 columns, all allocated): forward D1 @0, D2 @256, D3 @0, D4 @128; reverse D_g3 @0,
-// D_g2 @128, D_ge3 @384 (drained to scratch), D_g1 @0 (rows 0..127 of W2^T) + @384 (rest), D_ge1 @128.
+// D_g2 @128, D_ge3 @384 (drained to scratch), D_g1 @0 (rows 0..127 of W2^T) + @384 (rest), D_ge1 @256.
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -196,6 +196,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
         const uint32_t lane_addr = tmem_base + ((uint32_t)(lq * 32) << 16);
         float* scr = P.scratch + (size_t)blockIdx.x * P.scratch_floats_per_cta;
         uint32_t tile_it = 0;
+        // Software pipelining across tiles: this group's first chunk of a tile (op g, an embedding chunk: no TMEM input) is
+        // built for the NEXT tile before the current tile's result is drained, so the MMAs of the next tile start while
+        // the producers are still in the epilogue (the accumulator D_ge1 sits at columns 256.., clear of the next D1).
+        const bool can_pre = (n_ops % 2 == 0) && ops_s[g].prod == TC_PROD_EMBED;
+        bool pre_done = false;
+        auto embed_chunk = [&](int oi, uint32_t chunk_id, float px, float py, float pz) {
+            const int f16 = ops_s[oi].feat0 + ch * 16;
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int j = f16 + i;
+                const float4 t = etab[j];
+                const float arg = fmaf(pz, t.z, fmaf(py, t.y, px * t.x)) + t.w;
+                float sn, cs;
+                fast_sincos(arg, sn, cs);
+                v[i] = j < 3 ? (j == 0 ? px : (j == 1 ? py : pz)) : (j < net.E ? sn : 0.f);
+            }
+            float vhi[16], vlo[16];
+            split_a16(v, vhi, vlo);
+            mbar_wait_backoff(sfree0 + 8 * g, ((chunk_id >> 1) & 1) ^ 1);
+            store_a16(ast0 + g * TC_ASTAGE_BYTES, row, ch, vhi, vlo);
+            fence_async_smem();
+            mbar_arrive(afull0 + 8 * g);
+        };
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
             const int gi = tile * TC_TM + row;
             const int ic = gi < P.n ? gi : P.n - 1;
@@ -208,6 +232,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
             const bool tr = P.trace && blockIdx.x == 0 && tile == (int)gridDim.x && (tid & 255) == 0;
             for (int oi = 0; oi < n_ops; ++oi, ++chunk) {
                 if ((int)(chunk & 1) != g) continue;
+                if (pre_done && oi == g) continue;                 // already built during the previous tile's epilogue
                 const SdfTcOp op = ops_s[oi];
                 const int f16 = op.feat0 + ch * 16;               // this thread's first feature within the layer
                 if (tr) P.trace[oi * 8 + 0] = clock64();
@@ -283,13 +308,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
                 mbar_arrive(afull0 + 8 * g);
                 if (tr) P.trace[oi * 8 + 3] = clock64();
             }
+            pre_done = false;
+            if (can_pre && tile + (int)gridDim.x < n_tiles) {
+                const int ngi = (tile + (int)gridDim.x) * TC_TM + row;
+                const int nic = ngi < P.n ? ngi : P.n - 1;
+                embed_chunk(g, chunk + g, __ldg(P.pts + (size_t)nic * 3), __ldg(P.pts + (size_t)nic * 3 + 1), __ldg(P.pts + (size_t)nic * 3 + 2));
+                pre_done = true;
+            }
             // ---- final: g_e = D_ge1 (+ parked skip part) ; chain rule through the embedding.  Group g takes the 32-feature
             // blocks with ((f0 / 32) & 1) == g, so the four (group, half) combinations cover a row exactly once. ----
             mbar_wait_backoff(dfull0 + 8 * (P.n_acc - 1), dpar); tc_fence_after();
             float gx = 0.f, gy = 0.f, gz = 0.f;
             for (int f0 = 32 * g; f0 < net.Ep; f0 += 64) {
                 float v[16];
-                tc_ld16(lane_addr + 128 + f0 + ch * 16, v);
+                tc_ld16(lane_addr + 256 + f0 + ch * 16, v);
                 const int f16 = f0 + ch * 16;
                 if (net.res_state) {
                     const float* gs = scr + P.sc_off_ge3 + ((size_t)(f16 >> 2) * TC_TM + row) * 4;
