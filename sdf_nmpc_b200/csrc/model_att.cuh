@@ -29,17 +29,36 @@ struct ModelConst {
     double tau_roll, tau_pitch;   // first-order attitude lag (model 'att_tau', quad_rollpitchyawrate_tau.py:19-20)
 };
 
+// Input-only trigonometry of model 'att': the inputs are constant over the RK4 stages of a node, so cos / sin of the roll
+// and pitch set-points are evaluated once per node instead of once per stage.
 template <class T>
-SDF_HD void f_att(const ModelConst& c, const T* x, const T* u, T* dx) {
+struct AttInputTrig {
+    T cr, sr, cp, sp;
+    bool valid;
+};
+template <class T>
+SDF_HD AttInputTrig<T> att_input_trig(const ModelConst& c, const T* u) {
+    AttInputTrig<T> t;
+    const T r = c.roll * u[1], pt = c.pitch * u[2];
+    t.cr = dcos(r); t.sr = dsin(r); t.cp = dcos(pt); t.sp = dsin(pt);
+    t.valid = true;
+    return t;
+}
+
+template <class T>
+SDF_HD void f_att(const ModelConst& c, const T* x, const T* u, T* dx, const AttInputTrig<T>* it = nullptr) {
     T q0 = x[3], q1 = x[4], q2 = x[5], q3 = x[6];
     T inv_n = 1.0 / dsqrt(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
     T h0 = q0 * inv_n, h1 = q1 * inv_n, h2 = q2 * inv_n, h3 = q3 * inv_n;
-    // yaw-only rotation: theta_z = atan2(q3, q0), W_R_V = Rz(2 theta_z)
-    T psi = 2.0 * datan2(h3, h0);
-    T cps = dcos(psi), sps = dsin(psi);
+    // yaw-only rotation: theta_z = atan2(q3, q0), W_R_V = Rz(2 theta_z).  With rho^2 = q0^2 + q3^2 the double-angle
+    // identities give cos(2 theta_z) = (q0^2 - q3^2) / rho^2 and sin(2 theta_z) = 2 q0 q3 / rho^2 without atan2 / sin / cos.
+    T irho2 = 1.0 / (q0 * q0 + q3 * q3);
+    T cps = (q0 * q0 - q3 * q3) * irho2, sps = (2.0 * (q0 * q3)) * irho2;
     T gam = c.gamma * u[0];
-    T r = c.roll * u[1], pt = c.pitch * u[2], wz = c.wz * u[3];
-    T cr = dcos(r), sr = dsin(r), cp = dcos(pt), sp = dsin(pt);
+    T wz = c.wz * u[3];
+    T cr, sr, cp, sp;
+    if (it) { cr = it->cr; sr = it->sr; cp = it->cp; sp = it->sp; }
+    else { T r = c.roll * u[1], pt = c.pitch * u[2]; cr = dcos(r); sr = dsin(r); cp = dcos(pt); sp = dsin(pt); }
     dx[0] = x[7];
     dx[1] = x[8];
     dx[2] = x[9];
@@ -97,8 +116,8 @@ SDF_HD void f_acc(const ModelConst& c, const T* x, const T* u, T* dx) {
 }
 
 template <int MODEL, class T>
-SDF_HD void f_model(const ModelConst& c, const T* x, const T* u, T* dx) {
-    if (MODEL == MODEL_ATT) f_att(c, x, u, dx);
+SDF_HD void f_model(const ModelConst& c, const T* x, const T* u, T* dx, const AttInputTrig<T>* it = nullptr) {
+    if (MODEL == MODEL_ATT) f_att(c, x, u, dx, it);
     else if (MODEL == MODEL_ATT_TAU) f_att_tau(c, x, u, dx);
     else f_acc(c, x, u, dx);
 }
@@ -106,13 +125,16 @@ SDF_HD void f_model(const ModelConst& c, const T* x, const T* u, T* dx) {
 template <int MODEL, class T>
 SDF_HD void rk4_step(const ModelConst& c, const T* x, const T* u, double dt, T* xn) {
     T k1[ATT_NX], k2[ATT_NX], k3[ATT_NX], k4[ATT_NX], xs[ATT_NX];
-    f_model<MODEL>(c, x, u, k1);
+    AttInputTrig<T> trig;
+    const AttInputTrig<T>* it = nullptr;
+    if (MODEL == MODEL_ATT) { trig = att_input_trig(c, u); it = &trig; }
+    f_model<MODEL>(c, x, u, k1, it);
     for (int i = 0; i < ATT_NX; ++i) xs[i] = x[i] + (0.5 * dt) * k1[i];
-    f_model<MODEL>(c, xs, u, k2);
+    f_model<MODEL>(c, xs, u, k2, it);
     for (int i = 0; i < ATT_NX; ++i) xs[i] = x[i] + (0.5 * dt) * k2[i];
-    f_model<MODEL>(c, xs, u, k3);
+    f_model<MODEL>(c, xs, u, k3, it);
     for (int i = 0; i < ATT_NX; ++i) xs[i] = x[i] + dt * k3[i];
-    f_model<MODEL>(c, xs, u, k4);
+    f_model<MODEL>(c, xs, u, k4, it);
     for (int i = 0; i < ATT_NX; ++i) xn[i] = x[i] + (dt / 6.0) * (k1[i] + 2.0 * k2[i] + 2.0 * k3[i] + k4[i]);
 }
 
