@@ -225,8 +225,9 @@ def run_ours(args, rank, local_rank, world):
 
     def step_e2e():
         # state feedback arrives in host memory: pinned H2D of x0 [B,10] f64, solve, D2H of u0 [B,4] f64 + status [B] i32
-        mpc.solve_host(x_pin)
-        # simulated plant (device) and its measurement copied back to the host for the next control step
+        mpc.solve_host(x_pin, sync=False)
+        # simulated plant (device) and its measurement copied back to the host for the next control step; ONE
+        # synchronisation per step, after which u0 / status / the new state are all in host memory
         mpc.plant_step(mpc.x0, mpc.u0, dt)
         x_pin.copy_(mpc.x0, non_blocking=True)
         torch.cuda.current_stream().synchronize()

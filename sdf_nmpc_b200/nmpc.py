@@ -189,8 +189,10 @@ class BatchedNmpc:
         self.fail_count = torch.where(ok, torch.zeros_like(self.fail_count), self.fail_count + 1)
         return self.fail_count
 
-    def solve_host(self, x0, out=None):
-        """End-to-end step with HOST buffers: pinned H2D of the state feedback, solve, D2H of the controls."""
+    def solve_host(self, x0, out=None, sync=True):
+        """End-to-end step with HOST buffers: pinned H2D of the state feedback, solve, D2H of the controls.  With
+        ``sync=False`` the copies are only enqueued: the returned pinned arrays are valid after the caller synchronises the
+        stream (lets a caller append its own device work and read everything back with ONE synchronisation)."""
         pin = self._pin.get('x0')
         if pin is None:
             pin = self._pin['x0'] = torch.empty(self.B, NX, dtype=torch.float64).pin_memory()
@@ -203,7 +205,8 @@ class BatchedNmpc:
         self.solve()
         self._pin['u0'].copy_(self.u0, non_blocking=True)
         self._pin['st'].copy_(self.status, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        if sync:
+            torch.cuda.current_stream().synchronize()
         return self._pin['u0'].numpy(), self._pin['st'].numpy()
 
     # ------------------------------------------------------------------ getters ----------
