@@ -122,6 +122,8 @@ int sdfnmpc_solver_qp_residual(sdfnmpc_solver_t h, double** res_dev);
  * ms3 = summed milliseconds of {linearise, sdf, qp}; steps = number of timed calls. */
 int sdfnmpc_solver_timing_begin(sdfnmpc_solver_t h, int32_t max_steps);
 int sdfnmpc_solver_timing_end(sdfnmpc_solver_t h, float* ms3, int32_t* steps);
+/* controller.py:74-81 bookkeeping for a batch: fail_count[b] = status[b] == 0 ? 0 : fail_count[b] + 1 (device pointers). */
+int sdfnmpc_fail_count_update(const int32_t* status_dev, int64_t* fail_count_dev, int32_t B, void* stream);
 /* RK4 plant step with the same model: x <- phi(x, u, dt) for closed-loop rollouts. */
 int sdfnmpc_plant_step(sdfnmpc_solver_t h, int32_t B, double* x_dev, const double* u_dev, double dt, void* stream);
 /* u_to_TRPYr + clip (controller.py:106-108): cmd [B][4]. */

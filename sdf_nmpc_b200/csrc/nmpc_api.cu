@@ -351,6 +351,19 @@ extern "C" int sdfnmpc_solver_state(sdfnmpc_solver_t h, double** xbar, double** 
     return 0;
 }
 
+__global__ void nmpc_fail_count_kernel(int B, const int* __restrict__ status, long long* __restrict__ fail) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) fail[b] = status[b] == 0 ? 0 : fail[b] + 1;
+}
+
+extern "C" int sdfnmpc_fail_count_update(const int32_t* status, int64_t* fail_count, int32_t B, void* stream) {
+    if (!status || !fail_count || B < 1) return SDFNMPC_E_INVALID;
+    nmpc_fail_count_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(B, status, (long long*)fail_count);
+    count_launch();
+    SDF_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int sdfnmpc_solver_qp_residual(sdfnmpc_solver_t h, double** res) {
     if (!h || !res) return SDFNMPC_E_INVALID;
     *res = h->qp_res;

@@ -185,8 +185,7 @@ class BatchedNmpc:
             _ptr(self.pose), _ptr(self.flag), lat, _ptr(self.u0), _ptr(self.status), _ptr(self.qp_iters), _stream()),
             'sdfnmpc_solver_rti_step')
         self._latent_dirty = False
-        ok = self.status == 0
-        self.fail_count = torch.where(ok, torch.zeros_like(self.fail_count), self.fail_count + 1)
+        _lib.check(self.lib.sdfnmpc_fail_count_update(_ptr(self.status), _ptr(self.fail_count), self.B, _stream()), 'fail_count_update')
         return self.fail_count
 
     def solve_host(self, x0, out=None, sync=True):
