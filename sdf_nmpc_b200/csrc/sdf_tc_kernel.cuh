@@ -268,13 +268,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
                             const float4 bq = __ldg(reinterpret_cast<const float4*>(bias) + q);
                             bb[q * 4] = bq.x; bb[q * 4 + 1] = bq.y; bb[q * 4 + 2] = bq.z; bb[q * 4 + 3] = bq.w;
                         }
+#if defined(TC_TRACE_PROD)
+                        if (tr) P.trace[oi * 8 + 4] = clock64();
+#endif
                         tc_ld16(lane_addr + op.src_col + ch * 16, v);
+#if defined(TC_TRACE_PROD)
+                        if (tr) P.trace[oi * 8 + 5] = clock64();
+#endif
                         float* cs = scr + (op.layer == 1 ? P.sc_off_c1 : (op.layer == 2 ? P.sc_off_c2 : P.sc_off_c3)) + ((size_t)(f16 >> 2) * TC_TM + row) * 4;
                         float c[16];
 #pragma unroll
                         for (int e = 0; e < 16; ++e) act_pair(net.act, net.w0, v[e] + bb[e], v[e], c[e]);
+#if defined(TC_TRACE_PROD)
+                        if (tr) P.trace[oi * 8 + 6] = clock64() + (long long)(v[3] == 123.456f);
+#endif
 #pragma unroll
                         for (int q = 0; q < 4; ++q) reinterpret_cast<float4*>(cs)[q * TC_TM] = make_float4(c[q * 4], c[q * 4 + 1], c[q * 4 + 2], c[q * 4 + 3]);
+#if defined(TC_TRACE_PROD)
+                        if (tr) P.trace[oi * 8 + 7] = clock64();
+#endif
                     } else if (op.prod == TC_PROD_MUL) {
                         const float* cs = scr + (op.layer == 1 ? P.sc_off_c1 : (op.layer == 2 ? P.sc_off_c2 : P.sc_off_c3)) + ((size_t)(f16 >> 2) * TC_TM + row) * 4;
                         float4 c[4];
@@ -395,11 +407,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
             for (int oi = 0; oi < n_ops; ++oi, ++chunk) {
                 const SdfTcOp& op = P.opsv[oi];
                 const uint32_t s = chunk & 1;
+#if !defined(TC_TRACE_PROD)
                 if (tr && leader) { P.trace[oi * 8 + 4] = clock64(); P.trace[oi * 8 + 5] = clock64(); }
+#endif
                 mbar_wait(wfull0 + 8 * s, (chunk >> 1) & 1);
+#if !defined(TC_TRACE_PROD)
                 if (tr && leader) P.trace[oi * 8 + 6] = clock64();
+#endif
                 mbar_wait(afull0 + 8 * s, (chunk >> 1) & 1);
+#if !defined(TC_TRACE_PROD)
                 if (tr && leader) P.trace[oi * 8 + 7] = clock64();
+#endif
                 tc_fence_after();
                 // descriptors are built once per chunk; per MMA only the start-address field advances (+32 B = +2 units
                 // per K step of 8 tf32)
