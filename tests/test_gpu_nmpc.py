@@ -321,7 +321,7 @@ def test_full_size_properties(cuda_device):
     assert np.abs(one.get_u().cpu().numpy() - out['u0']).max() <= U_TOL
 
 
-@pytest.mark.parametrize('variant', ['N12', 'nonuniform_dt', 'shift1'])
+@pytest.mark.parametrize('variant', ['N12', 'nonuniform_dt', 'shift1', 'h_at_node0'])
 def test_config_variants_match_oracle(variant, cuda_device):
     """Configuration options of the reference OCP other than the defaults: a different horizon (generic-N kernel path),
     the non-uniform time grid of ocp.py:21-27 and the iterate shift of ocp.py:152-156, each against the oracle."""
@@ -341,6 +341,9 @@ def test_config_variants_match_oracle(variant, cuda_device):
         cfg.mpc.uniform_dt = False
     elif variant == 'shift1':
         cfg.mpc.shift = 1
+    elif variant == 'h_at_node0':      # nonlinear rows also on the initial node (the other reading of acados' h placement)
+        cfg.b200.h_at_node0 = True
+        ocfg['h_at_node0'] = True
     ocfg['dt'] = np.asarray(cfg.shooting_dt(), float)
     assert len(ocfg['dt']) == cfg.mpc.N and abs(ocfg['dt'].sum() - cfg.mpc.T) < 1e-12
     if variant == 'nonuniform_dt':
