@@ -61,7 +61,7 @@ struct QpShape {
     }
     // doubles of per-lane-group shared memory
     SDF_HD static int smem_doubles(int N) {
-        return NX * NX + 2 * NX * (NW + 1) + NW * NW + NW + NU * NX + NU + 2 * NX   // Riccati workspace
+        return NX * NX + NX * (NW + 1) + NW * NW + NW + NU * NX + NU + 2 * NX       // Riccati workspace
                + 2 * NW * kp(N)                                                   // W (iterate), dW (step)
                + (NCORR + NPROD) * kp(N) + 8
                + 2 * STAGE_DOUBLES + 2;                                           // double-buffered per-stage data, 2 mbarriers
@@ -224,8 +224,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
 
     // ---- shared workspace -----------------------------------------------------------------------
     double* Psm = sm;                    // [NX][NX]
-    double* ABb = Psm + NX * NX;         // [NX][NW+1]
-    double* PAB = ABb + NX * NWB;        // [NX][NW+1]
+    double* PAB = Psm + NX * NX;         // [NX][NW+1]  P [A B | phi rd]
     double* Msm = PAB + NX * NWB;        // [NW][NW]
     double* rv = Msm + NW * NW;          // [NW]
     double* Ksm = rv + NW;               // [NU][NX]

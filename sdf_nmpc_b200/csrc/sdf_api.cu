@@ -32,7 +32,7 @@ static inline int pad8(int v) { return (v + 31) / 32 * 32; }   // every feature 
 
 // ------------------------------------------------------------------------------------------
 // Tensor-core path: chunk program + weight chunks pre-split (hi | lo TF32) and pre-laid-out in the UMMA canonical
-// K-major no-swizzle layout, so that one bulk copy lands a ready-to-use B operand in shared memory.
+// 128-byte-swizzled K-major layout, so that one bulk copy lands a ready-to-use B operand in shared memory.
 // ------------------------------------------------------------------------------------------
 namespace {
 inline float tf32_rna_host(float x) {
