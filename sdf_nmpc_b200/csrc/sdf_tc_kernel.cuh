@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
 
     if (tid == 0) {
         mbar_init(wfull0, 1); mbar_init(wfull0 + 8, 1);
-        mbar_init(afull0, TC_GROUP_THREADS); mbar_init(afull0 + 8, TC_GROUP_THREADS);
+        mbar_init(afull0, TC_PROD_THREADS); mbar_init(afull0 + 8, TC_PROD_THREADS);
         mbar_init(sfree0, 1); mbar_init(sfree0 + 8, 1);
         for (int q = 0; q < TC_MAX_ACC; ++q) mbar_init(dfull0 + 8 * q, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -189,36 +189,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
     uint32_t chunk = 0;           // global chunk counter (stage = chunk & 1, phase = (chunk >> 1) & 1)
 
     if (warp < TC_PROD_WARPS) {
-        // ===== producers.  Group g (8 warps) owns the chunks with (chunk & 1) == g and therefore smem stage g: while one
-        // group waits for its stage / fences its stores, the other one computes.  thread <-> (point, 16-feature half) =====
-        const int g = warp >> 3, wq = warp & 7, lq = wq & 3, ch = wq >> 2;
+        // ===== producers: all 16 warps build EVERY chunk together.  thread <-> (point = TMEM lane, 8 of the chunk's 32
+        // features): warp w reads TMEM lane quarter w % 4 and owns feature quarter w / 4.  Chunks alternate between the two
+        // A stages, so building chunk c + 1 overlaps the MMAs of chunk c; with half the work per thread the first chunk
+        // after a layer boundary is ready in half the time (the drain at a boundary is what a tile loses most cycles to).
+        const int lq = warp & 3, cg = warp >> 2;
         const int row = lq * 32 + (tid & 31);
         const uint32_t lane_addr = tmem_base + ((uint32_t)(lq * 32) << 16);
         float* scr = P.scratch + (size_t)blockIdx.x * P.scratch_floats_per_cta;
         uint32_t tile_it = 0;
-        // Software pipelining across tiles: this group's first chunk of a tile (op g, an embedding chunk: no TMEM input) is
-        // built for the NEXT tile before the current tile's result is drained, so the MMAs of the next tile start while
-        // the producers are still in the epilogue (the accumulator D_ge1 sits at columns 256.., clear of the next D1).
-        const bool can_pre = (n_ops % 2 == 0) && ops_s[g].prod == TC_PROD_EMBED;
-        bool pre_done = false;
-        auto embed_chunk = [&](int oi, uint32_t chunk_id, float px, float py, float pz) {
-            const int f16 = ops_s[oi].feat0 + ch * 16;
-            float v[16];
+        // Software pipelining across tiles: the first two chunks of a tile (embedding chunks: no TMEM input) are built
+        // for the NEXT tile before the current tile's result is drained, so its MMAs start during the epilogue (the
+        // accumulator D_ge1 sits at columns 256.., clear of the next D1).
+        // (Two chunks fit the two A stages before the epilogue; the remaining leading embedding chunks follow in the middle of
+        // the epilogue, once the TMEM reads are done and the first two stages have been consumed.)
+        int n_lead = 0;                                        // leading embedding chunks of a tile
+        while (n_lead < n_ops && n_lead < 4 && ops_s[n_lead].prod == TC_PROD_EMBED) ++n_lead;
+        const int n_pre = (n_ops % 2 == 0 && n_lead >= 2) ? 2 : 0;
+        const int n_pre2 = n_pre ? n_lead : 0;                 // total pre-built chunks once the epilogue is through
+        int pre_done = 0;
+        auto publish = [&](uint32_t chunk_id, const float* v) {
+            float vhi[8], vlo[8];
+            split_a8(v, vhi, vlo);
+            const uint32_t s = chunk_id & 1;
+            mbar_wait_backoff(sfree0 + 8 * s, ((chunk_id >> 1) & 1) ^ 1);
+#if !defined(TC_EXP_NO_STORE)
+            store_a8(ast0 + s * TC_ASTAGE_BYTES, row, cg, vhi, vlo);
+#endif
+            fence_async_smem();
+            mbar_arrive(afull0 + 8 * s);
+        };
+        auto embed8 = [&](int f8, float px, float py, float pz, float* v) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int j = f16 + i;
+            for (int i = 0; i < 8; ++i) {
+                const int j = f8 + i;
                 const float4 t = etab[j];
                 const float arg = fmaf(pz, t.z, fmaf(py, t.y, px * t.x)) + t.w;
                 float sn, cs;
                 fast_sincos(arg, sn, cs);
                 v[i] = j < 3 ? (j == 0 ? px : (j == 1 ? py : pz)) : (j < net.E ? sn : 0.f);
             }
-            float vhi[16], vlo[16];
-            split_a16(v, vhi, vlo);
-            mbar_wait_backoff(sfree0 + 8 * g, ((chunk_id >> 1) & 1) ^ 1);
-            store_a16(ast0 + g * TC_ASTAGE_BYTES, row, ch, vhi, vlo);
-            fence_async_smem();
-            mbar_arrive(afull0 + 8 * g);
         };
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
             const int gi = tile * TC_TM + row;
@@ -229,123 +239,101 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
             const float* b3 = P.b3f + (size_t)inst * net.H3;
             const uint32_t dpar = tile_it & 1;                  // every dfull[q] completes exactly once per tile
             float d_acc = 0.f;
-            const bool tr = P.trace && blockIdx.x == 0 && tile == (int)gridDim.x && (tid & 255) == 0;
+            const bool tr = P.trace && blockIdx.x == 0 && tile == (int)gridDim.x && tid == 0;
             for (int oi = 0; oi < n_ops; ++oi, ++chunk) {
-                if ((int)(chunk & 1) != g) continue;
-                if (pre_done && oi == g) continue;                 // already built during the previous tile's epilogue
+                if (oi < pre_done) continue;                       // already built during the previous tile's epilogue
                 const SdfTcOp op = ops_s[oi];
-                const int f16 = op.feat0 + ch * 16;               // this thread's first feature within the layer
+                const int f8 = op.feat0 + cg * 8;                  // this thread's first feature within the layer
                 if (tr) P.trace[oi * 8 + 0] = clock64();
                 if (op.d_need >= 0) { mbar_wait_backoff(dfull0 + 8 * op.d_need, dpar); tc_fence_after(); }
                 if (op.pre_drain_ge3) {
                     // park the skip-connection part of the embedding gradient: D_ge3 (columns 384..) -> scratch
                     for (int f0 = 0; f0 < net.Ep; f0 += 32) {
-                        float v[16];
-                        tc_ld16(lane_addr + 384 + f0 + ch * 16, v);
-                        float4* dst = reinterpret_cast<float4*>(scr + P.sc_off_ge3 + ((size_t)((f0 + ch * 16) >> 2) * TC_TM + row) * 4);
+                        float v[8];
+                        tc_ld8(lane_addr + 384 + f0 + cg * 8, v);
+                        float4* dst = reinterpret_cast<float4*>(scr + P.sc_off_ge3 + ((size_t)((f0 + cg * 8) >> 2) * TC_TM + row) * 4);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) dst[q * TC_TM] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                        for (int q = 0; q < 2; ++q) dst[q * TC_TM] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
                     }
                     tc_fence_before();
                 }
-                float v[16];
+                float v[8];
                 if (op.prod == TC_PROD_EMBED) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int j = f16 + i;
-                        const float4 t = etab[j];
-                        const float arg = fmaf(sz, t.z, fmaf(sy, t.y, sx * t.x)) + t.w;
-                        float sn, cs;
-                        fast_sincos(arg, sn, cs);
-                        v[i] = j < 3 ? (j == 0 ? sx : (j == 1 ? sy : sz)) : (j < net.E ? sn : 0.f);
-                    }
+                    embed8(f8, sx, sy, sz, v);
                 } else {
                     if (op.prod == TC_PROD_ACT) {
-                        const float* bias = (op.layer == 1 ? b1 : (op.layer == 2 ? net.b2 : b3)) + f16;
-                        float bb[16];
+                        const float* bias = (op.layer == 1 ? b1 : (op.layer == 2 ? net.b2 : b3)) + f8;
+                        float bb[8];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {          // issue the bias loads before waiting on TMEM
+                        for (int q = 0; q < 2; ++q) {          // issue the bias loads before waiting on TMEM
                             const float4 bq = __ldg(reinterpret_cast<const float4*>(bias) + q);
                             bb[q * 4] = bq.x; bb[q * 4 + 1] = bq.y; bb[q * 4 + 2] = bq.z; bb[q * 4 + 3] = bq.w;
                         }
-#if defined(TC_TRACE_PROD)
-                        if (tr) P.trace[oi * 8 + 4] = clock64();
-#endif
-                        tc_ld16(lane_addr + op.src_col + ch * 16, v);
-#if defined(TC_TRACE_PROD)
-                        if (tr) P.trace[oi * 8 + 5] = clock64();
-#endif
-                        float* cs = scr + (op.layer == 1 ? P.sc_off_c1 : (op.layer == 2 ? P.sc_off_c2 : P.sc_off_c3)) + ((size_t)(f16 >> 2) * TC_TM + row) * 4;
-                        float c[16];
+                        tc_ld8(lane_addr + op.src_col + cg * 8, v);
+                        float* cs = scr + (op.layer == 1 ? P.sc_off_c1 : (op.layer == 2 ? P.sc_off_c2 : P.sc_off_c3)) + ((size_t)(f8 >> 2) * TC_TM + row) * 4;
+                        float c[8];
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) act_pair(net.act, net.w0, v[e] + bb[e], v[e], c[e]);
-#if defined(TC_TRACE_PROD)
-                        if (tr) P.trace[oi * 8 + 6] = clock64() + (long long)(v[3] == 123.456f);
-#endif
+                        for (int e = 0; e < 8; ++e) act_pair(net.act, net.w0, v[e] + bb[e], v[e], c[e]);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) reinterpret_cast<float4*>(cs)[q * TC_TM] = make_float4(c[q * 4], c[q * 4 + 1], c[q * 4 + 2], c[q * 4 + 3]);
-#if defined(TC_TRACE_PROD)
-                        if (tr) P.trace[oi * 8 + 7] = clock64();
-#endif
+                        for (int q = 0; q < 2; ++q) reinterpret_cast<float4*>(cs)[q * TC_TM] = make_float4(c[q * 4], c[q * 4 + 1], c[q * 4 + 2], c[q * 4 + 3]);
                     } else if (op.prod == TC_PROD_MUL) {
-                        const float* cs = scr + (op.layer == 1 ? P.sc_off_c1 : (op.layer == 2 ? P.sc_off_c2 : P.sc_off_c3)) + ((size_t)(f16 >> 2) * TC_TM + row) * 4;
-                        float4 c[4];
+                        const float* cs = scr + (op.layer == 1 ? P.sc_off_c1 : (op.layer == 2 ? P.sc_off_c2 : P.sc_off_c3)) + ((size_t)(f8 >> 2) * TC_TM + row) * 4;
+                        float4 c[2];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) c[q] = reinterpret_cast<const float4*>(cs)[q * TC_TM];
-                        tc_ld16(lane_addr + op.src_col + ch * 16, v);
+                        for (int q = 0; q < 2; ++q) c[q] = reinterpret_cast<const float4*>(cs)[q * TC_TM];
+                        tc_ld8(lane_addr + op.src_col + cg * 8, v);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) { v[q * 4] *= c[q].x; v[q * 4 + 1] *= c[q].y; v[q * 4 + 2] *= c[q].z; v[q * 4 + 3] *= c[q].w; }
+                        for (int q = 0; q < 2; ++q) { v[q * 4] *= c[q].x; v[q * 4 + 1] *= c[q].y; v[q * 4 + 2] *= c[q].z; v[q * 4 + 3] *= c[q].w; }
                     } else {   // TC_PROD_G4: output layer + seed of the reverse sweep
-                        tc_ld16(lane_addr + op.src_col + ch * 16, v);
+                        tc_ld8(lane_addr + op.src_col + cg * 8, v);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const float w5 = __ldg(net.W5 + f16 + i);
+                        for (int i = 0; i < 8; ++i) {
+                            const float w5 = __ldg(net.W5 + f8 + i);
                             float h, c;
-                            act_pair(net.act, net.w0, v[i] + __ldg(net.b4 + f16 + i), h, c);
+                            act_pair(net.act, net.w0, v[i] + __ldg(net.b4 + f8 + i), h, c);
                             d_acc = fmaf(w5, h, d_acc);
                             v[i] = w5 * c;
                         }
                     }
                     tc_fence_before();
                 }
-                float vhi[16], vlo[16];
-                split_a16(v, vhi, vlo);
                 if (tr) P.trace[oi * 8 + 1] = clock64();
-                mbar_wait_backoff(sfree0 + 8 * g, ((chunk >> 1) & 1) ^ 1);
-                if (tr) P.trace[oi * 8 + 2] = clock64();
-#if !defined(TC_EXP_NO_STORE)
-                store_a16(ast0 + g * TC_ASTAGE_BYTES, row, ch, vhi, vlo);
-#endif
-                fence_async_smem();
-                mbar_arrive(afull0 + 8 * g);
+                publish(chunk, v);
                 if (tr) P.trace[oi * 8 + 3] = clock64();
             }
-            pre_done = false;
-            if (can_pre && tile + (int)gridDim.x < n_tiles) {
+            pre_done = 0;
+            const bool has_next = n_pre && tile + (int)gridDim.x < n_tiles;
+            float nx = 0.f, ny = 0.f, nz = 0.f;
+            if (has_next) {
                 const int ngi = (tile + (int)gridDim.x) * TC_TM + row;
                 const int nic = ngi < P.n ? ngi : P.n - 1;
-                embed_chunk(g, chunk + g, __ldg(P.pts + (size_t)nic * 3), __ldg(P.pts + (size_t)nic * 3 + 1), __ldg(P.pts + (size_t)nic * 3 + 2));
-                pre_done = true;
+                nx = __ldg(P.pts + (size_t)nic * 3); ny = __ldg(P.pts + (size_t)nic * 3 + 1); nz = __ldg(P.pts + (size_t)nic * 3 + 2);
+                for (int q = 0; q < n_pre; ++q) {
+                    float v[8];
+                    embed8(ops_s[q].feat0 + cg * 8, nx, ny, nz, v);
+                    publish(chunk + q, v);
+                }
+                pre_done = n_pre;
             }
-            // ---- final: g_e = D_ge1 (+ parked skip part) ; chain rule through the embedding.  Group g takes the 32-feature
-            // blocks with ((f0 / 32) & 1) == g, so the four (group, half) combinations cover a row exactly once. ----
+            // ---- final: g_e = D_ge1 (+ parked skip part) ; chain rule through the embedding.  Every thread takes its 8-feature
+            // quarter of every 32-feature block, so the four quarters cover a row exactly once. ----
             mbar_wait_backoff(dfull0 + 8 * (P.n_acc - 1), dpar); tc_fence_after();
             float gx = 0.f, gy = 0.f, gz = 0.f;
-            for (int f0 = 32 * g; f0 < net.Ep; f0 += 64) {
-                float v[16];
-                tc_ld16(lane_addr + 256 + f0 + ch * 16, v);
-                const int f16 = f0 + ch * 16;
+            for (int f0 = 0; f0 < net.Ep; f0 += 32) {
+                float v[8];
+                tc_ld8(lane_addr + 256 + f0 + cg * 8, v);
+                const int f8 = f0 + cg * 8;
                 if (net.res_state) {
-                    const float* gs = scr + P.sc_off_ge3 + ((size_t)(f16 >> 2) * TC_TM + row) * 4;
+                    const float* gs = scr + P.sc_off_ge3 + ((size_t)(f8 >> 2) * TC_TM + row) * 4;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int q = 0; q < 2; ++q) {
                         const float4 c = reinterpret_cast<const float4*>(gs)[q * TC_TM];
                         v[q * 4] += c.x; v[q * 4 + 1] += c.y; v[q * 4 + 2] += c.z; v[q * 4 + 3] += c.w;
                     }
                 }
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int j = f16 + i;
+                for (int i = 0; i < 8; ++i) {
+                    const int j = f8 + i;
                     const float4 t = etab[j];
                     const float arg = fmaf(sz, t.z, fmaf(sy, t.y, sx * t.x)) + t.w;
                     float sn, cs;
@@ -358,10 +346,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
                 }
             }
             tc_fence_before();
-            // combine the four (group, half) partials of each row
-            reinterpret_cast<float4*>(part)[(g * 2 + ch) * TC_TM + row] = make_float4(gx, gy, gz, d_acc);
+            if (has_next) {
+                for (int q = n_pre; q < n_pre2; ++q) {
+                    float v[8];
+                    embed8(ops_s[q].feat0 + cg * 8, nx, ny, nz, v);
+                    publish(chunk + q, v);
+                }
+                pre_done = n_pre2;
+            }
+            // combine the four feature-quarter partials of each row
+            reinterpret_cast<float4*>(part)[cg * TC_TM + row] = make_float4(gx, gy, gz, d_acc);
             asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD_THREADS) : "memory");
-            if (g == 0 && ch == 0 && gi < P.n) {
+            if (cg == 0 && gi < P.n) {
                 const float4 p0 = reinterpret_cast<const float4*>(part)[row], p1 = reinterpret_cast<const float4*>(part)[TC_TM + row];
                 const float4 p2 = reinterpret_cast<const float4*>(part)[2 * TC_TM + row], p3 = reinterpret_cast<const float4*>(part)[3 * TC_TM + row];
                 if (P.sdf_out) P.sdf_out[gi] = ((p0.w + p1.w) + (p2.w + p3.w)) + net.b5;

@@ -167,6 +167,22 @@ __device__ __forceinline__ void store_a16(unsigned char* a_stage, int row, int c
     }
 }
 
+// 8-feature variants (thread <-> row, quarter `cg` of the 32-feature chunk): two 16-byte units of hi and of lo
+__device__ __forceinline__ void split_a8(const float* v, float* hi, float* lo) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { hi[e] = tf32_rna(v[e]); lo[e] = tf32_rna(v[e] - hi[e]); }
+}
+__device__ __forceinline__ void store_a8(unsigned char* a_stage, int row, int cg, const float* hi, const float* lo) {
+    unsigned char* base = a_stage + (row >> 3) * 1024 + (row & 7) * 128;
+    const int sw = row & 7;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int unit = ((cg * 2 + q) ^ sw) * 16;
+        *reinterpret_cast<float4*>(base + unit) = make_float4(hi[q * 4], hi[q * 4 + 1], hi[q * 4 + 2], hi[q * 4 + 3]);
+        *reinterpret_cast<float4*>(base + TC_ASTAGE_BYTES / 2 + unit) = make_float4(lo[q * 4], lo[q * 4 + 1], lo[q * 4 + 2], lo[q * 4 + 3]);
+    }
+}
+
 }  // namespace tc
 
 }  // namespace sdfnmpc
