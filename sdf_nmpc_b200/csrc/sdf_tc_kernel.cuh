@@ -6,11 +6,12 @@
 // 2-way TF32 split: x = hi + lo, D += A_hi B_hi + A_lo B_hi + A_hi B_lo.
 //
 // Structure of one CTA (576 threads = 18 warps, one CTA per SM, persistent over tiles of 128 points):
-//   * warps 0-15 ("producers", two ping-pong groups of 8; thread <-> (point = TMEM lane, 16 of the chunk's 32 features)):
+//   * warps 0-15 ("producers"; all build every chunk: thread <-> (point = TMEM lane, 8 of the chunk's 32 features)):
 //     build the A operand of the next GEMM in 32-feature chunks in the 128-byte-swizzled K-major UMMA layout, as hi and lo
 //     TF32 parts: the embedding for layer 1 / the skip connection, act(D + bias) read back from TMEM with tcgen05.ld for
 //     the hidden layers, D * act' for the reverse sweep.  act' values and the partial embedding gradient are parked in an
-//     L2-resident per-CTA scratch (TMEM and smem are full).  Group g owns the chunks with (chunk & 1) == g and stage g.
+//     L2-resident per-CTA scratch (TMEM and smem are full).  Chunk c uses A stage (c & 1); the leading embedding chunks of
+//     the NEXT tile are built around the current tile's epilogue.
 //   * warp 16 (MMA issuer): waits for operands and issues the tcgen05.mma from one elected lane on warp-uniform operands;
 //     tcgen05.commit releases the 2-stage smem ring and publishes finished accumulators.
 //   * warp 17 (weight streamer): ONE bulk copy (cp.async.bulk, UBLKCP) per 32-column weight chunk (pre-split hi|lo,
@@ -26,8 +27,7 @@
 
 namespace sdfnmpc {
 
-constexpr int TC_PROD_WARPS = 16;            // producer warps: 2 groups (even / odd chunks) x 4 TMEM lane quarters x 2 column groups of 16
-constexpr int TC_GROUP_THREADS = TC_PROD_WARPS * 32 / 2;
+constexpr int TC_PROD_WARPS = 16;            // producer warps: 4 TMEM lane quarters x 4 column groups of 8 features
 constexpr int TC_MAX_ACC = 8;                // accumulator-complete barriers per tile
 constexpr int TC_PROD_THREADS = TC_PROD_WARPS * 32;
 constexpr int TC_THREADS = TC_PROD_THREADS + 64;          // + MMA issuer warp + weight-streaming warp
