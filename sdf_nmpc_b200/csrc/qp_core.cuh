@@ -259,36 +259,68 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
         r = q * q * q * q;
         for (int c = 0; c < 3; ++c) Jr[c] = -2.0 * q * q * q * Cr[HC0 + c];
     };
-    for (int e = lane; e < (N + 1) * TRI; e += NL) {
-        const int k = e / TRI, t = e - k * TRI, i = tri.i[t], j = tri.j[t];
-        const double* Jk = P.J + (size_t)k * NY * NW;
-        double s = 0.0;
-        for (int r = 0; r < NY; ++r) s += Jk[r * NW + i] * wrow(k, r) * Jk[r * NW + j];
-        if (i == j) s += P.lm;
-        if (sdf_cost && k < N && i >= HC0 && i < HC0 + 3 && j >= HC0 && j < HC0 + 3) {
-            double r, Jr[3];
-            cost_r(k, r, Jr);
-            s += P.sdf_cost_w * Jr[i - HC0] * Jr[j - HC0];
+    // J_k travels through the (still idle) stage buffers, node k + 1's copy in flight while node k is reduced: read straight
+    // from global memory the dependent loads of this loop were 13 % of the kernel's warp time (ncu source samples, r1g).
+    {
+        auto jslot = [&](int k) { return stg + (k & 1) * S::STAGE_DOUBLES; };
+        auto fetch = [&](int k) {
+            pipe.begin(L, k & 1, NY * NW * 8);
+            pipe.copy(L, k & 1, jslot(k), P.J + (size_t)k * NY * NW, NY * NW);
+        };
+        static_assert((NY * NW) % 2 == 0 && NY * NW + 2 * NY <= S::STAGE_DOUBLES, "J_k + weights + residual fit a stage slot");
+        fetch(0);
+        double w_nx = 0.0, y_nx = 0.0;                   // lane r < NY: weight and residual of row r of the next node
+        if (lane < NY || NL == 1) { w_nx = wrow(0, NL == 1 ? 0 : lane); y_nx = P.yres[NL == 1 ? 0 : lane]; }
+        for (int k = 0; k <= N; ++k) {
+            pipe.wait(L, k & 1);
+            const double* Jk = jslot(k);
+            double* wk = jslot(k) + NY * NW;            // [NY] weights | [NY] residual
+#ifdef QP_PRO_NOPF
+            if (true) {
+                for (int r = lane; r < NY; r += NL) { wk[r] = wrow(k, r); wk[NY + r] = P.yres[(size_t)k * NY + r]; }
+            } else if (lane < NY) {
+#else
+            if (NL == 1) {
+                for (int r = 0; r < NY; ++r) { wk[r] = wrow(k, r); wk[NY + r] = P.yres[(size_t)k * NY + r]; }
+            } else if (lane < NY) {
+#endif
+                wk[lane] = w_nx; wk[NY + lane] = y_nx;
+            }
+            if (k < N) {
+                fetch(k + 1);
+#ifndef QP_PRO_NOPF
+                if (NL != 1 && lane < NY) { w_nx = wrow(k + 1, lane); y_nx = P.yres[(size_t)(k + 1) * NY + lane]; }
+#endif
+            }
+            L.sync();
+            for (int t = lane; t < TRI; t += NL) {
+                const int i = tri.i[t], j = tri.j[t];
+                double s = 0.0;
+                for (int r = 0; r < NY; ++r) s += Jk[r * NW + i] * wk[r] * Jk[r * NW + j];
+                if (i == j) s += P.lm;
+                if (sdf_cost && k < N && i >= HC0 && i < HC0 + 3 && j >= HC0 && j < HC0 + 3) {
+                    double r, Jr[3];
+                    cost_r(k, r, Jr);
+                    s += P.sdf_cost_w * Jr[i - HC0] * Jr[j - HC0];
+                }
+                s *= scale(k);
+                Hk(k)[i * NW + j] = s;
+                Hk(k)[j * NW + i] = s;
+            }
+            for (int i = lane; i < NW; i += NL) {
+                double s = 0.0;
+                for (int r = 0; r < NY; ++r) s += Jk[r * NW + i] * wk[r] * wk[NY + r];
+                if (sdf_cost && k < N && i >= HC0 && i < HC0 + 3) {
+                    double r, Jr[3];
+                    cost_r(k, r, Jr);
+                    s += P.sdf_cost_w * r * Jr[i - HC0];
+                }
+                g[k * NW + i] = scale(k) * s;
+                const double w0 = (k == 0 && i >= NU) ? P.x0[i - NU] - P.xbar[i - NU] : 0.0;
+                Wsm[i * KP + k] = w0;
+                dW[i * KP + k] = 0.0;
+            }
         }
-        s *= scale(k);
-        Hk(k)[i * NW + j] = s;
-        Hk(k)[j * NW + i] = s;
-    }
-    for (int e = lane; e < (N + 1) * NW; e += NL) {
-        const int k = e / NW, i = e - k * NW;
-        const double* Jk = P.J + (size_t)k * NY * NW;
-        const double* yr = P.yres + (size_t)k * NY;
-        double s = 0.0;
-        for (int r = 0; r < NY; ++r) s += Jk[r * NW + i] * wrow(k, r) * yr[r];
-        if (sdf_cost && k < N && i >= HC0 && i < HC0 + 3) {
-            double r, Jr[3];
-            cost_r(k, r, Jr);
-            s += P.sdf_cost_w * r * Jr[i - HC0];
-        }
-        g[e] = scale(k) * s;
-        const double w0 = (k == 0 && i >= NU) ? P.x0[i - NU] - P.xbar[i - NU] : 0.0;
-        Wsm[i * KP + k] = w0;
-        dW[i * KP + k] = 0.0;
     }
     L.sync();
 
