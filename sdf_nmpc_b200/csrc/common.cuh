@@ -127,9 +127,17 @@ struct StagePipe {
         (void)L; (void)slot;
 #endif
     }
+    // closes the batch of copies of one stage: the group is committed right behind its copies, so the later wait is a plain
+    // scoreboard test (`cp.async.wait_all` commits at wait time).  Measured: QP 5.36 -> 5.34 ms, i.e. within noise.
+    SDF_HD void commit(const Lanes& L) const {
+#if defined(__CUDA_ARCH__) && !defined(SDFNMPC_STAGE_BULK)
+        asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+        (void)L;
+    }
     SDF_HD void wait(const Lanes& L, int slot) {
 #if defined(__CUDA_ARCH__) && !defined(SDFNMPC_STAGE_BULK)
-        asm volatile("cp.async.wait_all;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         L.sync();
         (void)slot;
 #elif defined(__CUDA_ARCH__)

@@ -266,6 +266,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
         auto fetch = [&](int k) {
             pipe.begin(L, k & 1, NY * NW * 8);
             pipe.copy(L, k & 1, jslot(k), P.J + (size_t)k * NY * NW, NY * NW);
+            pipe.commit(L);
         };
         static_assert((NY * NW) % 2 == 0 && NY * NW + 2 * NY <= S::STAGE_DOUBLES, "J_k + weights + residual fit a stage slot");
         fetch(0);
@@ -581,6 +582,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                     pipe.copy(L, slot, dst + S::ST_RV, rv0k(kk), NW);
                     pipe.copy(L, slot, dst + S::ST_F, recF + (size_t)kk * S::REC_F, S::REC_F);
                 }
+                pipe.commit(L);
             };
             pipe.publish(L);
             prefetch(N - 1, 0);
@@ -754,6 +756,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                 pipe.copy(L, slot, dst + S::ST_AB, P.AB + (size_t)kk * NX * NW, NX * NW);
                 pipe.copy(L, slot, dst + S::ST_RD, rd0k(kk + 1), NX);
                 pipe.copy(L, slot, dst + S::ST_K, Kgk(kk), NU * NX);
+                pipe.commit(L);
             };
             pipe.publish(L);
             prefetch_f(0, 0);
