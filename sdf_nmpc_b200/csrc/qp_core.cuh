@@ -57,7 +57,7 @@ struct QpShape {
         return n1 * REC_A                  // rv0, rd0, H per node
                + n1 * NW                   // g
                + (size_t)N * REC_F         // PbM, Linv, K per stage
-               + n1 * NX;                  // costates (final verification)
+               + ((n1 * NH * 3 + 1) & ~(size_t)1);   // position blocks of the constraint rows (even: instances stay 16-byte aligned)
     }
     // doubles of per-lane-group shared memory
     SDF_HD static int smem_doubles(int N) {
@@ -212,7 +212,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
     double* recA = take(n1 * S::REC_A);        // per node: rv0 | rd0 (of the NEXT node) | H
     double* g = take(n1 * NW);
     double* recF = take((size_t)N * S::REC_F);  // per stage: PbM | Linv | K
-    double* pig = take(n1 * NX);
+    double* cpos = take(n1 * NH * 3);          // per node: position block [NH][3] of the constraint rows
     // rv0: stationarity residual at the initial point (scaled by phi afterwards); rd0[k] = AB_{k-1} w_{k-1} + b_{k-1} - w_x,k
     // lives in record k-1 (the stage that produces node k); H: Gauss-Newton Hessian; L: Cholesky factor of Ruu, diagonal INVERTED
     auto Hk = [&](int k) { return recA + (size_t)k * S::REC_A + S::RA_H; };
@@ -244,12 +244,18 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
 
     // ---- prologue: sdf row of C / h, Gauss-Newton Hessian and gradient ----------------------
     const bool sdf_cost = P.sdf_cost_w > 0.0;          // the cost row also needs the SDF at node 0
-    for (int k = (sdf_cost ? 0 : k0) + lane; k <= N; k += NL) {
-        const double* R = P.pose + 3;
-        double gx = P.sdf_g[k * 3 + 0], gy = P.sdf_g[k * 3 + 1], gz = P.sdf_g[k * 3 + 2];
-        double* Cr = P.C + ((size_t)k * NH + (NH - 1)) * NW;
-        for (int jj = 0; jj < 3; ++jj) Cr[HC0 + jj] = P.flag * (R[jj * 3 + 0] * gx + R[jj * 3 + 1] * gy + R[jj * 3 + 2] * gz);
-        P.hval[k * NH + (NH - 1)] = P.flag * (double)P.sdf_d[k] + (1.0 - P.flag) * P.max_df;
+    for (int k = lane; k <= N; k += NL) {
+        if (k >= (sdf_cost ? 0 : k0)) {
+            const double* R = P.pose + 3;
+            double gx = P.sdf_g[k * 3 + 0], gy = P.sdf_g[k * 3 + 1], gz = P.sdf_g[k * 3 + 2];
+            double* Cr = P.C + ((size_t)k * NH + (NH - 1)) * NW;
+            for (int jj = 0; jj < 3; ++jj) Cr[HC0 + jj] = P.flag * (R[jj * 3 + 0] * gx + R[jj * 3 + 1] * gy + R[jj * 3 + 2] * gz);
+            P.hval[k * NH + (NH - 1)] = P.flag * (double)P.sdf_d[k] + (1.0 - P.flag) * P.max_df;
+        }
+        // compact copy of the rows' position blocks: the row phases read only these 3 of a row's NW entries, and through the
+        // full-width C they touched every cache line of it (7 KB per instance, 8 instances per SM against 60 KB of L1)
+        for (int r = 0; r < NH; ++r)
+            for (int c = 0; c < 3; ++c) cpos[(k * NH + r) * 3 + c] = P.C[((size_t)k * NH + r) * NW + HC0 + c];
     }
     if (sdf_cost) L.sync();
     // optional cost row r = (1 - 0.5 d)^4 on the stage nodes: dr/dp = -2 (1 - 0.5 d)^3 dd/dp, only the position block
@@ -275,6 +281,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
         for (int k = 0; k <= N; ++k) {
             pipe.wait(L, k & 1);
             const double* Jk = jslot(k);
+            const double sck = scale(k);                // requested ahead of the lane barrier below
             double* wk = jslot(k) + NY * NW;            // [NY] weights | [NY] residual
 #ifdef QP_PRO_NOPF
             if (true) {
@@ -304,7 +311,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                     cost_r(k, r, Jr);
                     s += P.sdf_cost_w * Jr[i - HC0] * Jr[j - HC0];
                 }
-                s *= scale(k);
+                s *= sck;
                 Hk(k)[i * NW + j] = s;
                 Hk(k)[j * NW + i] = s;
             }
@@ -316,7 +323,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                     cost_r(k, r, Jr);
                     s += P.sdf_cost_w * r * Jr[i - HC0];
                 }
-                g[k * NW + i] = scale(k) * s;
+                g[k * NW + i] = sck * s;
                 const double w0 = (k == 0 && i >= NU) ? P.x0[i - NU] - P.xbar[i - NU] : 0.0;
                 Wsm[i * KP + k] = w0;
                 dW[i * KP + k] = 0.0;
@@ -340,7 +347,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
         const double hv = P.hval[kk * NH + r];
         return a < NH ? P.lh[r] - hv : hv - P.uh[r];
     };
-    auto c_pos = [&](int kk, int r, int c) { return P.C[((size_t)kk * NH + r) * NW + HC0 + c]; };
+    auto c_pos = [&](int kk, int r, int c) { return cpos[(kk * NH + r) * 3 + c]; };
 
 // entry loop over the lanes of the group, fully unrolled with predication so that the independent dot-product chains of
 // one lane interleave (the dynamic-trip-count form serialised them: `wait` stalls) - constant bounds only
@@ -898,23 +905,43 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
             for (int r = 0; r < NH; ++r) corr[(NU + r) * KP + kk] = kk >= k0 ? ls[r] - ls[NH + r] : 0.0;
         }
         L.sync();
-        for (int kk = N; kk >= 0; --kk) {
+        // stage data (H_k inside record A, [A B]_k) travels through the stage ring like in the sweeps; the costates ping-pong
+        // between two shared vectors.  Not run after a numerical breakdown (copies of the aborted sweep may be in flight).
+        auto fetch_v = [&](int kk, int slot) {
+            double* dst = stg + slot * S::STAGE_DOUBLES;
+            pipe.begin(L, slot, ((kk < N ? NX * NW : 0) + S::REC_A) * 8);
+            if (kk < N) pipe.copy(L, slot, dst + S::ST_AB, P.AB + (size_t)kk * NX * NW, NX * NW);
+            pipe.copy(L, slot, dst + S::ST_A, recA + (size_t)kk * S::REC_A, S::REC_A);
+            pipe.commit(L);
+        };
+        if (status != 4) {
+            pipe.publish(L);
+            fetch_v(N, 0);
+        }
+        for (int kk = N; kk >= 0 && status != 4; --kk) {
+            const int slot = (N - kk) & 1;
+            const double* sb = stg + slot * S::STAGE_DOUBLES;
+            pipe.wait(L, slot);
+            if (kk > 0) fetch_v(kk - 1, slot ^ 1);
+            const double* pin = slot ? pv : vv;       // costate of node kk + 1
+            double* pout = slot ? vv : pv;            // costate of node kk
+            const double bd = (kk < N && lane < NX) ? P.bdyn[kk * NX + lane] : 0.0;
             for (int i = lane; i < NW; i += NL) {
                 if (kk == N && i < NU) continue;
                 double s = g[(size_t)kk * NW + i];
-                for (int j = 0; j < NW; ++j) s += Hk(kk)[i * NW + j] * Wsm[j * KP + kk];
+                for (int j = 0; j < NW; ++j) s += sb[S::ST_H + i * NW + j] * Wsm[j * KP + kk];
                 if (i < NU) s -= corr[i * KP + kk];
                 if (i >= HC0 && i < HC0 + 3)
                     for (int r = 0; r < NH; ++r) s -= corr[(NU + r) * KP + kk] * c_pos(kk, r, i - HC0);
                 if (kk < N)
-                    for (int l = 0; l < NX; ++l) s += P.AB[(size_t)kk * NX * NW + l * NW + i] * pig[(size_t)(kk + 1) * NX + l];
+                    for (int l = 0; l < NX; ++l) s += sb[S::ST_AB + l * NW + i] * pin[l];
                 if (i < NU) res_true = fmax(res_true, fabs(s));      // input stationarity
-                else pig[(size_t)kk * NX + (i - NU)] = s;            // defines the costate of node kk (x-stationarity == 0)
+                else pout[i - NU] = s;                               // defines the costate of node kk (x-stationarity == 0)
             }
             if (kk < N)
                 for (int i = lane; i < NX; i += NL) {
-                    double s = P.bdyn[kk * NX + i] - Wsm[(NU + i) * KP + kk + 1];
-                    for (int j = 0; j < NW; ++j) s += P.AB[(size_t)kk * NX * NW + i * NW + j] * Wsm[j * KP + kk];
+                    double s = (NL == 1 ? P.bdyn[kk * NX + i] : bd) - Wsm[(NU + i) * KP + kk + 1];
+                    for (int j = 0; j < NW; ++j) s += sb[S::ST_AB + i * NW + j] * Wsm[j * KP + kk];
                     res_true = fmax(res_true, fabs(s));
                 }
             L.sync();
