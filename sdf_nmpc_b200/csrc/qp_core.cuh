@@ -276,6 +276,15 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
         };
         static_assert((NY * NW) % 2 == 0 && NY * NW + 2 * NY <= S::STAGE_DOUBLES, "J_k + weights + residual fit a stage slot");
         fetch(0);
+        // the lane's (i, j) pairs of the lower triangle, packed 4 + 4 bits each: looked up once, not once per node
+        constexpr int TRI_PER_LANE = (TRI + Lanes::count() - 1) / Lanes::count();
+        constexpr bool TRI_PACK = TRI_PER_LANE <= 4 && NW <= 16;
+        unsigned ijp = 0;
+        if (TRI_PACK)
+            for (int m = 0; m < TRI_PER_LANE; ++m) {
+                const int t = lane + m * NL;
+                if (t < TRI) ijp |= ((unsigned)tri.i[t] | ((unsigned)tri.j[t] << 4)) << (8 * m);
+            }
         double w_nx = 0.0, y_nx = 0.0;                   // lane r < NY: weight and residual of row r of the next node
         if (lane < NY || NL == 1) { w_nx = wrow(0, NL == 1 ? 0 : lane); y_nx = P.yres[NL == 1 ? 0 : lane]; }
         for (int k = 0; k <= N; ++k) {
@@ -301,8 +310,9 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
 #endif
             }
             L.sync();
-            for (int t = lane; t < TRI; t += NL) {
-                const int i = tri.i[t], j = tri.j[t];
+            for (int t = lane, m = 0; t < TRI; t += NL, ++m) {
+                const int i = TRI_PACK ? (int)((ijp >> (8 * m)) & 15u) : (int)tri.i[t];
+                const int j = TRI_PACK ? (int)((ijp >> (8 * m + 4)) & 15u) : (int)tri.j[t];
                 double s = 0.0;
                 for (int r = 0; r < NY; ++r) s += Jk[r * NW + i] * wk[r] * Jk[r * NW + j];
                 if (i == j) s += P.lm;
