@@ -74,7 +74,12 @@ struct QpBatch {
 };
 
 template <int NFIX>
-__global__ void __launch_bounds__(QP_WARPS * 32, QP_MIN_CTAS) nmpc_qp_kernel(SolverConst sc, int B, QpBatch q) {
+#ifdef QP_MAXNREG
+__global__ void __maxnreg__(QP_MAXNREG) nmpc_qp_kernel(
+#else
+__global__ void __launch_bounds__(QP_WARPS * 32, QP_MIN_CTAS) nmpc_qp_kernel(
+#endif
+    SolverConst sc, int B, QpBatch q) {
     extern __shared__ double sm_all[];
     __shared__ SolverConst scs;
     if (threadIdx.x == 0) scs = sc;
