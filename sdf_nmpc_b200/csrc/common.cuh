@@ -109,6 +109,31 @@ struct StagePipe {
         (void)L; (void)slot; (void)bytes;
 #endif
     }
+    // Compile-time-sized copy: per lane one base address pair, then one LDGSTS per 16-byte chunk with the chunk offset as an
+    // immediate (the generic loop below spent ~7 instructions per chunk on 64-bit address arithmetic and predicates: 11 % of
+    // the QP kernel's instructions).
+    template <int NDOUBLES>
+    SDF_HD void copy(const Lanes& L, int slot, double* dst_smem, const double* src) const {
+        static_assert(NDOUBLES % 2 == 0, "16-byte units");
+#if defined(__CUDA_ARCH__) && !defined(SDFNMPC_STAGE_BULK) && !defined(SDFNMPC_STAGE_GENERIC_COPY)
+        const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem) + (unsigned)L.lane * 16u;
+        const char* g = reinterpret_cast<const char*>(src) + L.lane * 16;
+        chunk<NDOUBLES / 2, 0>(d, g, L.lane);
+        (void)slot;
+#else
+        copy(L, slot, dst_smem, src, NDOUBLES);
+#endif
+    }
+#if defined(__CUDA_ARCH__)
+    template <int NCH, int IT>
+    __device__ __forceinline__ static void chunk(unsigned d, const char* g, int lane) {
+        if constexpr (IT * 32 < NCH) {
+            if (IT * 32 + 31 < NCH || IT * 32 + lane < NCH)
+                asm volatile("cp.async.cg.shared.global [%0+%2], [%1+%2], 16;" ::"r"(d), "l"(g), "n"(IT * 512) : "memory");
+            chunk<NCH, IT + 1>(d, g, lane);
+        }
+    }
+#endif
     SDF_HD void copy(const Lanes& L, int slot, double* dst_smem, const double* src, int n) const {
 #if defined(__CUDA_ARCH__) && !defined(SDFNMPC_STAGE_BULK)
         // development variant: per-lane 16-byte cp.async (LDGSTS) instead of the bulk engine

@@ -287,7 +287,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
         auto jslot = [&](int k) { return stg + (k & 1) * S::STAGE_DOUBLES; };
         auto fetch = [&](int k) {
             pipe.begin(L, k & 1, NY * NW * 8);
-            pipe.copy(L, k & 1, jslot(k), P.J + (size_t)k * NY * NW, NY * NW);
+            pipe.template copy<NY * NW>(L, k & 1, jslot(k), P.J + (size_t)k * NY * NW);
             pipe.commit(L);
         };
         static_assert((NY * NW) % 2 == 0 && NY * NW + 2 * NY <= S::STAGE_DOUBLES, "J_k + weights + residual fit a stage slot");
@@ -652,13 +652,13 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                 double* dst = stg + slot * S::STAGE_DOUBLES;
                 if (pass == 0) {
                     pipe.begin(L, slot, (NX * NW + S::REC_A) * 8);
-                    pipe.copy(L, slot, dst + S::ST_AB, P.AB + (size_t)kk * NX * NW, NX * NW);
-                    pipe.copy(L, slot, dst + S::ST_A, recA + (size_t)kk * S::REC_A, S::REC_A);
+                    pipe.template copy<NX * NW>(L, slot, dst + S::ST_AB, P.AB + (size_t)kk * NX * NW);
+                    pipe.template copy<S::REC_A>(L, slot, dst + S::ST_A, recA + (size_t)kk * S::REC_A);
                 } else {
                     pipe.begin(L, slot, (NX * NW + NW + S::REC_F) * 8);
-                    pipe.copy(L, slot, dst + S::ST_AB, P.AB + (size_t)kk * NX * NW, NX * NW);
-                    pipe.copy(L, slot, dst + S::ST_RV, rv0k(kk), NW);
-                    pipe.copy(L, slot, dst + S::ST_F, recF + (size_t)kk * S::REC_F, S::REC_F);
+                    pipe.template copy<NX * NW>(L, slot, dst + S::ST_AB, P.AB + (size_t)kk * NX * NW);
+                    pipe.template copy<NW>(L, slot, dst + S::ST_RV, rv0k(kk));
+                    pipe.template copy<S::REC_F>(L, slot, dst + S::ST_F, recF + (size_t)kk * S::REC_F);
                 }
                 pipe.commit(L);
             };
@@ -831,9 +831,9 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
             auto prefetch_f = [&](int kk, int slot) {
                 double* dst = stg + slot * S::STAGE_DOUBLES;
                 pipe.begin(L, slot, (NX * NW + NX + NU * NX) * 8);
-                pipe.copy(L, slot, dst + S::ST_AB, P.AB + (size_t)kk * NX * NW, NX * NW);
-                pipe.copy(L, slot, dst + S::ST_RD, rd0k(kk + 1), NX);
-                pipe.copy(L, slot, dst + S::ST_K, Kgk(kk), NU * NX);
+                pipe.template copy<NX * NW>(L, slot, dst + S::ST_AB, P.AB + (size_t)kk * NX * NW);
+                pipe.template copy<NX>(L, slot, dst + S::ST_RD, rd0k(kk + 1));
+                pipe.template copy<NU * NX>(L, slot, dst + S::ST_K, Kgk(kk));
                 pipe.commit(L);
             };
             pipe.publish(L);
@@ -981,8 +981,8 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
         auto fetch_v = [&](int kk, int slot) {
             double* dst = stg + slot * S::STAGE_DOUBLES;
             pipe.begin(L, slot, ((kk < N ? NX * NW : 0) + S::REC_A) * 8);
-            if (kk < N) pipe.copy(L, slot, dst + S::ST_AB, P.AB + (size_t)kk * NX * NW, NX * NW);
-            pipe.copy(L, slot, dst + S::ST_A, recA + (size_t)kk * S::REC_A, S::REC_A);
+            if (kk < N) pipe.template copy<NX * NW>(L, slot, dst + S::ST_AB, P.AB + (size_t)kk * NX * NW);
+            pipe.template copy<S::REC_A>(L, slot, dst + S::ST_A, recA + (size_t)kk * S::REC_A);
             pipe.commit(L);
         };
         if (status != 4) {
