@@ -541,6 +541,25 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
     res_v0 = L.max(res_v0);
 
     int status = 2, it = 0;
+    // (i, j) of the lane's entries of the lower triangle of M and the correction rows they receive (ca: diagonal input
+    // entries, cb: position block), 4 bits each, resolved once instead of once per stage and iteration
+    auto m_entry = [&](int e, int& i, int& j, int& ca, int& cb) {
+        i = tri.i[e]; j = tri.j[e];
+        ca = (i == j && i < NU) ? i : 15;
+        const int pi_ = i - HC0, pj = j - HC0;
+        cb = (pi_ >= 0 && pi_ < 3 && pj >= 0 && pj < 3) ? sym3(pi_, pj) : 15;
+    };
+    constexpr bool M_PACK = (TRI + NW + Lanes::count() - 1) / Lanes::count() <= 4 && NW <= 15;
+    unsigned long long mpk = 0;
+    if (M_PACK)
+        for (int m = 0; m < 4; ++m) {
+            const int e = lane + m * NL;
+            if (e < TRI) {
+                int i, j, ca, cb;
+                m_entry(e, i, j, ca, cb);
+                mpk |= (unsigned long long)(i | (j << 4) | (ca << 8) | (cb << 12)) << (16 * m);
+            }
+        }
 #if defined(SDFNMPC_QP_TRACE) && defined(__CUDA_ARCH__)
     long long qpt_last = clock64();
     int qpt_pass = 0;
@@ -718,10 +737,13 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                 QPT(5);
                     SDF_LANES_FOR(e, TRI + NW) {
                         if (e < TRI) {
-                            const int i = tri.i[e], j = tri.j[e];
-                            const int ca = (i == j && i < NU) ? i : 15;
-                            const int pi_ = i - HC0, pj = j - HC0;
-                            const int cb = (pi_ >= 0 && pi_ < 3 && pj >= 0 && pj < 3) ? sym3(pi_, pj) : 15;
+                            int i, j, ca, cb;
+                            if (M_PACK) {
+                                const unsigned f = (unsigned)(mpk >> (16 * e_it));
+                                i = f & 15u; j = (f >> 4) & 15u; ca = (f >> 8) & 15u; cb = (f >> 12) & 15u;
+                            } else {
+                                m_entry(e, i, j, ca, cb);
+                            }
                             double s = sb[S::ST_H + i * NW + j];
 #pragma unroll
                             for (int l = 0; l < NX; ++l) s += ABk[l * NW + i] * PAB[l * NWB + j];
