@@ -50,8 +50,11 @@ struct sdfnmpc_solver {
     int ev_steps = 0, ev_cap = 0;
 };
 
+#ifndef LIN_MIN_BLOCKS
+#define LIN_MIN_BLOCKS 4      // 128 registers: 0.229 ms per 4096 instances against 0.299 ms at the 238 the compiler takes unbounded
+#endif
 template <int MODEL>
-__global__ void nmpc_linearize_kernel(ModelConst mc, int N, int B, LinIn in, LinOut out) {
+__global__ void __launch_bounds__(128, LIN_MIN_BLOCKS) nmpc_linearize_kernel(ModelConst mc, int N, int B, LinIn in, LinOut out) {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)B * (N + 1) * NW;
     if (gid >= total) return;
