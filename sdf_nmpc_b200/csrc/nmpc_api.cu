@@ -16,12 +16,12 @@ constexpr int NX = ATT_NX, NU = ATT_NU, NW = ATT_NW, NY = ATT_NY, NYN = ATT_NYN,
 using Shape = QpShape<NX, NU, NY, NH>;
 using Prob = QpProb<NX, NU, NY, NH>;
 #ifndef QP_WARPS_PER_CTA
-#define QP_WARPS_PER_CTA 2
+#define QP_WARPS_PER_CTA 1
 #endif
 constexpr int QP_WARPS = QP_WARPS_PER_CTA;     // instances per CTA
 #ifndef QP_MIN_CTAS
-#define QP_MIN_CTAS 4          // x 2 warps = 8 warps per SM (capping registers at 168 for 12 warps/SM spills 3.6 KB and is 1.5x slower;
-                               // 1 / 2 / 4 warps per CTA at 8 warps per SM: 6.9 / 6.4 / 6.5 ms)
+#define QP_MIN_CTAS 8          // 8 warps per SM.  1 / 2 / 4 warps per CTA: 3.95 / 4.02 / 4.03 ms per 4096 solves (a finished instance
+                               // frees its slot at once); with the row state parked, 10 warps / SM at 200 registers 4.82 vs 4.65 ms
 #endif
 
 struct SolverConst {
