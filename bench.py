@@ -195,6 +195,9 @@ def run_ours(args, rank, local_rank, world):
 
     for _ in range(W_):
         step_device()
+    # warm-up of the result gather too: the first all-gather on a communicator sets up its channels (~15 ms at N = 2, which
+    # a 20-step timed region would otherwise carry)
+    D.gather_records(D.pack_records(mpc.u0, mpc.status, mpc.qp_iters, x))
     torch.cuda.synchronize()
     # ---- device-resident timed region ----
     sampler = ClockSampler(local_rank)

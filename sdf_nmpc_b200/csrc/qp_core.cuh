@@ -440,6 +440,8 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
     // Riccati sweeps, three quarters of the time - they are parked in L2 ([item][node]: the lanes' accesses coalesce), which
     // leaves the sweeps the whole register file: 234 registers and no spills instead of 255 + 434 B, QP 5.21 -> 4.65 ms per
     // 4096 solves (-DSDFNMPC_QP_NO_PARK keeps the state in registers; 10 warps / SM at 200 registers: 4.82 ms).
+    // Even the two back-to-back row phases (steps formed / steps consumed) go through L2: keeping the 80 doubles live across
+    // them brings back 288 B of spills and costs 4.84 vs 3.93 ms.
     double* TB = take((size_t)(4 * NU + 8 * NH) * KP);
     double* TD = take((size_t)(4 * NU + 8 * NH) * KP);
 #define SDF_PARK_LD(p_) __ldcg(p_)
