@@ -61,14 +61,57 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  NVML is queried in-process
+    every few milliseconds (a 20-step timed region is ~90 ms: `nvidia-smi -lms` often delivers its first line after it ended);
+    `nvidia-smi` remains the fallback when the NVML bindings are missing."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    REASON_BITS = (('hw_slowdown', 0x8), ('hw_thermal_slowdown', 0x40), ('sw_thermal_slowdown', 0x20), ('sw_power_cap', 0x4))
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.nvml, self.handle, self.stop_flag, self.thread = None, None, False, None
+        self.sm, self.mx, self.mask = [], None, 0
+
+    def _nvml_open(self):
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            handle = None
+            try:                                         # the CUDA ordinal may be remapped (CUDA_VISIBLE_DEVICES): match by UUID
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+                uuid = uuid if uuid.startswith('GPU-') else 'GPU-' + uuid
+                handle = pynvml.nvmlDeviceGetHandleByUUID(uuid if isinstance(uuid, bytes) else uuid.encode())
+            except Exception:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)
+            self.nvml, self.handle = pynvml, handle
+            return True
+        except Exception:
+            return False
+
+    def _poll(self):
+        nv, h = self.nvml, self.handle
+        reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or getattr(nv, 'nvmlDeviceGetCurrentClocksThrottleReasons', None)
+        try:
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        except Exception:
+            self.mx = None
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                if reasons:
+                    self.mask |= int(reasons(h))
+            except Exception:
+                break
+            time.sleep(0.003)
 
     def start(self):
+        if self._nvml_open():
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
                                           '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -81,6 +124,12 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(',')])
 
     def stop(self):
+        if self.thread:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            reasons = sorted(n for n, bit in self.REASON_BITS if self.mask & bit)
+            return dict(sm_mhz=float(np.median(self.sm)) if self.sm else None, sm_max_mhz=self.mx, reasons=reasons,
+                        samples=len(self.sm), source='nvml')
         if self.proc:
             self.proc.terminate()
         sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace('.', '').isdigit()]
@@ -88,7 +137,7 @@ class ClockSampler:
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith('active')})
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
-                    samples=len(sm))
+                    samples=len(sm), source='nvidia-smi')
 
 
 # ----------------------------------------------------------------------------------------------------
