@@ -18,9 +18,12 @@
 // remaining equality-constrained QP in the STEP (delta form: right-hand sides are residuals,
 // so steps keep full relative accuracy near the solution) is solved by the Riccati recursion.
 //
-// Work mapping (v2).  Row phases: lane k owns node k and keeps the node's (t, lam, s, mu) in
-// registers for the whole solve - no index arithmetic, no scratch traffic.  Matrix phases
-// (Riccati): lanes split the entries of the small dense products staged in shared memory.
+// Work mapping (v3).  Row phases: lane k owns node k and holds the node's (t, lam, s, mu) and
+// their steps in registers INSIDE a row phase; between the phases (during the Riccati sweeps)
+// they are parked in an L2-resident [item][node] block, so the sweeps have the register file
+// to themselves.  Matrix phases (Riccati): lanes split the entries of the small dense products;
+// the per-stage operands ([A B], H, gains) stream global -> shared through a two-slot ring of
+// cp.async copies issued one stage ahead (the prologue and the final verification use the same ring).
 // The stationarity / dynamics residuals of a Newton method on a QP contract exactly by
 // (1 - alpha) per step, so they are kept as (initial residual) x (scalar phi) and verified
 // once, explicitly, at the end (costates recovered by one backward sweep).
