@@ -221,6 +221,7 @@ extern "C" int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver
     alloc((void**)&h->lam_soft, B * N1 * 2 * NH * sizeof(double));
     alloc((void**)&h->qp_res, 2 * B * sizeof(double));
     h->qp_smem = (size_t)QP_WARPS * Shape::smem_doubles(d->N) * sizeof(double);
+    if (const char* pad = getenv("SDFNMPC_QP_SMEM_PAD")) h->qp_smem += (size_t)atoi(pad);   // development: fewer resident CTAs per SM (8 / 7 / 5 warps per SM: 4.12 / 4.15 / 4.55 ms)
     if (e == cudaSuccess) e = cudaFuncSetAttribute(nmpc_qp_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qp_smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(nmpc_qp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qp_smem);
     if (e == cudaSuccess) e = cudaMemcpy(h->dt, d->dt, N * sizeof(double), cudaMemcpyHostToDevice);
