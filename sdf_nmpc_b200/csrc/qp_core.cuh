@@ -329,22 +329,14 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
             const double* Jk = jslot(k);
             const double sck = scale(k);                // requested ahead of the lane barrier below
             double* wk = jslot(k) + NY * NW;            // [NY] weights | [NY] residual
-#ifdef QP_PRO_NOPF
-            if (true) {
-                for (int r = lane; r < NY; r += NL) { wk[r] = wrow(k, r); wk[NY + r] = P.yres[(size_t)k * NY + r]; }
-            } else if (lane < NY) {
-#else
             if (NL == 1) {
                 for (int r = 0; r < NY; ++r) { wk[r] = wrow(k, r); wk[NY + r] = P.yres[(size_t)k * NY + r]; }
             } else if (lane < NY) {
-#endif
                 wk[lane] = w_nx; wk[NY + lane] = y_nx;
             }
             if (k < N) {
                 fetch(k + 1);
-#ifndef QP_PRO_NOPF
                 if (NL != 1 && lane < NY) { w_nx = wrow(k + 1, lane); y_nx = P.yres[(size_t)(k + 1) * NY + lane]; }
-#endif
             }
             L.sync();
             for (int t = lane, m = 0; t < TRI; t += NL, ++m) {
