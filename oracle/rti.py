@@ -10,7 +10,9 @@ below restate SURVEY.md section 8a-5 [from memory of acados 0.3.1] and define wh
      (``ocp.py:54-61,85-92``; acados cost "scaling").
   2. Levenberg-Marquardt: + Ts_k*lm*I on the (nu+nx) stage block, + lm*I at N
      (``ocp.py:119-120``).
-  3. QP variables per stage [du; dx]; dx_0 = x0 - xbar_0 (``ocp.py:160-161,169``).
+  3. QP variables per stage [du; dx]; ``Ocp.solve`` writes the measured state into node 0 of the iterate
+     (``solver.set(0, 'x', x0)``, ``ocp.py:161``) BEFORE the RTI step, so node 0 is linearised at x0 and
+     dx_0 = x0 - xbar_0 = 0 (``ocp.py:160-161,169``).
   4. nonlinear rows h (hfov, vfov, sdf - order ``gen_model.py:42,68``) at nodes
      1..N-1 and N; none at node 0 (switch ``h_at_node0``).
   5. soft rows: lh <= h + s_l, h - s_u <= uh, s >= 0, penalty z's + 1/2 s'Zs
@@ -157,6 +159,8 @@ def condense(lin, xb, ub, prob, cfg, max_df):
 def rti_step(net, xb, ub, prob, cfg):
     """One SQP-RTI iteration (preparation + feedback).  Returns new (xb, ub) and diagnostics."""
     B, N = xb.shape[0], cfg['N']
+    xb = xb.copy()
+    xb[:, 0] = prob['x0']                      # ocp.py:161: solver.set(0, 'x', x0) precedes the solve
     lin = linearize(net, xb, ub, prob, cfg)
     cq = condense(lin, xb, ub, prob, cfg, net['max_df'])
     sol = QP.solve_dense(cq['P'], cq['q'], cq['G'], cq['d'], cq['soft'], cq['z'], cq['Z'],

@@ -11,7 +11,7 @@
 namespace sdfnmpc {
 
 struct LinIn {           // device pointers, whole batch
-    const double* xbar;  // [B][N+1][NX]
+    double* xbar;        // [B][N+1][NX]   node 0 is overwritten with x0 (see linearize_dir)
     const double* ubar;  // [B][N][NU]
     const double* yref;  // [B][N][NY]
     const double* yrefN; // [B][NYN]
@@ -20,6 +20,8 @@ struct LinIn {           // device pointers, whole batch
     const double* flag;  // [B]
     const double* dt;    // [N]
     int nyN;             // terminal outputs: 4 (att, att_tau) or 7 (acc)
+    const double* x0;    // [B][NX] measured state: node 0 is linearised THERE (ocp.py:161 `solver.set(0, 'x', x0)` precedes
+                         // the RTI step, so dx_0 = 0); null = linearise node 0 at xbar_0 (the QP then carries dx_0 = x0 - xbar_0)
 };
 
 struct LinOut {
@@ -35,7 +37,11 @@ struct LinOut {
 template <int MODEL>
 SDF_HD void linearize_dir(const ModelConst& mc, int N, const LinIn& in, const LinOut& out, int b, int k, int dir) {
     constexpr int NX = ATT_NX, NU = ATT_NU, NW = ATT_NW, NY = ATT_NY, NH = ATT_NH;
-    const double* x = in.xbar + ((size_t)b * (N + 1) + k) * NX;
+    double* xb = in.xbar + ((size_t)b * (N + 1) + k) * NX;
+    const double* x = (k == 0 && in.x0) ? in.x0 + (size_t)b * NX : xb;
+    // only the threads of node 0 read x0 and none of them reads xbar_0, so the direction-0 thread may store it
+    if (k == 0 && in.x0 && dir == 0)
+        for (int i = 0; i < NX; ++i) xb[i] = x[i];
     Dual xd[NX], ud[NU];
     for (int i = 0; i < NX; ++i) xd[i] = Dual(x[i], (dir - NU) == i ? 1.0 : 0.0);
     if (k < N) {
@@ -51,7 +57,7 @@ SDF_HD void linearize_dir(const ModelConst& mc, int N, const LinIn& in, const Li
         double* AB = out.AB + ((size_t)b * N + k) * NX * NW;
         for (int i = 0; i < NX; ++i) AB[i * NW + dir] = xn[i].d;
         if (dir == 0) {
-            const double* x1 = x + NX;
+            const double* x1 = xb + NX;
             double* bd = out.bdyn + ((size_t)b * N + k) * NX;
             for (int i = 0; i < NX; ++i) bd[i] = xn[i].v - x1[i];
         }

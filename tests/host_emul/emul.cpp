@@ -11,15 +11,15 @@ using namespace sdfnmpc;
 using Shape = QpShape<ATT_NX, ATT_NU, ATT_NY, ATT_NH>;
 using Prob = QpProb<ATT_NX, ATT_NU, ATT_NY, ATT_NH>;
 
-extern "C" void emul_linearize(int model, int nyN, int B, int N, const double* mcv, const double* xbar, const double* ubar,
+extern "C" void emul_linearize(int model, int nyN, int B, int N, const double* mcv, double* xbar, const double* ubar,
                                const double* yref, const double* yrefN, const double* qd, const double* pose,
                                const double* flag, const double* dt, double* AB, double* bdyn, double* J,
-                               double* yres, double* C, double* hval, float* qpts) {
+                               double* yres, double* C, double* hval, float* qpts, const double* x0) {
     ModelConst mc;
     mc.g = mcv[0]; mc.gamma = mcv[1]; mc.roll = mcv[2]; mc.pitch = mcv[3]; mc.wz = mcv[4]; mc.mass = mcv[5];
     mc.cam_off[0] = mcv[6]; mc.cam_off[1] = mcv[7]; mc.cam_off[2] = mcv[8];
     mc.ax = mcv[9]; mc.ay = mcv[10]; mc.az = mcv[11]; mc.tau_roll = mcv[12]; mc.tau_pitch = mcv[13];
-    LinIn in{xbar, ubar, yref, yrefN, qd, pose, flag, dt, nyN};
+    LinIn in{xbar, ubar, yref, yrefN, qd, pose, flag, dt, nyN, x0};
     LinOut out{AB, bdyn, J, yres, C, hval, qpts};
     for (int b = 0; b < B; ++b)
         for (int k = 0; k <= N; ++k)
@@ -67,6 +67,7 @@ extern "C" void emul_qp(int B, int N, int k0, int max_iter, int nyN, double sdf_
         P.lam_soft = lam_soft + (size_t)b * (N + 1) * 2 * NH;
         P.res_out = nullptr;
         P.trace = nullptr;
+        P.debug = 0;
         P.status = status + b;
         P.iters = iters + b;
         qp_solve_instance<NX, NU, NY, NH>(L, P, sm.data());

@@ -40,7 +40,7 @@ def _emul_step(lib, net, cfg, prob, xe, ue):
     c = np.ascontiguousarray
     yref, yrefN, qd, flag, W, WN, x0 = (c(prob[k]) for k in ('yref', 'yrefN', 'qd', 'flag', 'W', 'WN', 'x0'))
     lib.emul_linearize(mid, nyN, B, N, _P(mcv), _P(xe), _P(ue), _P(yref), _P(yrefN), _P(qd), _P(pose), _P(flag), _P(cfg['dt']),
-                       _P(AB), _P(bd), _P(J), _P(yr), _P(C), _P(hv), _P(qp))
+                       _P(AB), _P(bd), _P(J), _P(yr), _P(C), _P(hv), _P(qp), _P(x0))
     lin = dict(AB=AB.copy(), b=bd.copy(), J=J.copy(), hv=hv.copy(), C=C.copy(), qp=qp.copy())
     d, g = SDF.value_and_grad(net, qp.reshape(-1, 3), np.repeat(prob['latent'], N + 1, 0), dtype=np.float32)
     d, g = c(d.astype(np.float32)), c(g.astype(np.float32))
