@@ -8,13 +8,18 @@
 #include "handles.h"
 #include "linearize_core.cuh"
 #include "qp_core.cuh"
+#include "qp_mma.cuh"
 
 using namespace sdfnmpc;
 
 namespace {
 constexpr int NX = ATT_NX, NU = ATT_NU, NW = ATT_NW, NY = ATT_NY, NYN = ATT_NYN, NH = ATT_NH;
-using Shape = QpShape<NX, NU, NY, NH>;
 using Prob = QpProb<NX, NU, NY, NH>;
+#if defined(SDFNMPC_QP_SCALAR)
+using Shape = QpShape<NX, NU, NY, NH>;        // A/B builds: the scalar statement of the solver (qp_core.cuh)
+#else
+using Shape = QpMmaShape;                     // product: tensor-core sweeps (qp_mma.cuh)
+#endif
 #ifndef QP_WARPS_PER_CTA
 #define QP_WARPS_PER_CTA 1
 #endif
@@ -141,7 +146,11 @@ __global__ void __launch_bounds__(QP_WARPS * 32, QP_MIN_CTAS) nmpc_qp_kernel(
 #else
     P.debug = 0;
 #endif
+#if defined(SDFNMPC_QP_SCALAR)
     qp_solve_instance<NX, NU, NY, NH, NFIX>(L, P, sm_all + (size_t)warp * Shape::smem_doubles(N));
+#else
+    qp_solve_mma<NFIX>(L, P, sm_all + (size_t)warp * Shape::smem_doubles(N));
+#endif
     __syncwarp();
     }
 }

@@ -45,7 +45,7 @@ struct QpShape {
     SDF_HD static int kp(int N) { return N + 2; }   // padded node count of the [item][node] arrays
     // Per-stage data travels global -> shared by bulk copies, so what one sweep needs of a stage is contiguous in the
     // global scratch:  record A_k = [ rv0_k | rd0_{k+1} | H_k ]  (written once per solve),
-    //                  record F_k = [ PbM_k | LDL' of Muu_k | K_k ]         (written by the factorising sweep of every iteration).
+    //                  record F_k = [ PbM_k | L_k | K_k ]         (written by the factorising sweep of every iteration).
     static constexpr int RA_RV = 0, RA_RD = NW, RA_H = NW + NX, REC_A = NW + NX + NW * NW;
     static constexpr int RF_PB = 0, RF_L = NX, RF_K = NX + NU * NU, REC_F = NX + NU * NU + NU * NX;
     // shared stage slot: AB | rv0 | rd0 | { H (factorising sweep, verification)  or  record F (the other sweeps) }
@@ -53,14 +53,6 @@ struct QpShape {
                          ST_F = ST_H, ST_PB = ST_F + RF_PB, ST_L = ST_F + RF_L, ST_K = ST_F + RF_K,
                          STAGE_DOUBLES = ST_A + REC_A;
     static_assert(REC_F <= NW * NW, "record F overlays H in a stage slot");
-    // Tensor-core (DMMA m8n8k4) factorising sweep: the augmented stage variable w~ = [u; x; 1] lives on 16 POSITIONS chosen so
-    // that the accumulator fragment of one product is, register for register, an operand fragment of the next (no shuffles, no
-    // shared-memory round trip): positions 0..7 = x0..x7, 8 / 10 / 12 / 14 = x8, x9, the affine column, a zero pad,
-    // 9 / 11 / 13 / 15 = u0..u3.  HP_k: H~_k as a full 16 x 16 matrix by position (gradient residual rv0 in the affine row /
-    // column); ABT_k: [A B | rd]~ transposed, [16 positions][12 contraction slots] (slot s < 10 = x_s, 10 = affine, 11 = pad).
-    static constexpr bool MMA = (NX == 10 && NU == 4);
-    static constexpr int HP = 256, ABT = 192;
-    SDF_HD static constexpr int wpos(int i) { return i < NU ? 9 + 2 * i : (i < NU + 8 ? i - NU : 8 + 2 * (i - NU - 8)); }
     static_assert(NX % 2 == 0 && NW % 2 == 0 && NU % 2 == 0 && REC_A % 2 == 0 && REC_F % 2 == 0 && STAGE_DOUBLES % 2 == 0,
                   "bulk copies move 16-byte units");
     // doubles of per-instance global scratch
@@ -70,14 +62,13 @@ struct QpShape {
                + n1 * NW                   // g
                + (size_t)N * REC_F         // PbM, Linv, K per stage
                + ((n1 * NH * 3 + 1) & ~(size_t)1)    // position blocks of the constraint rows (even: instances stay 16-byte aligned)
-               + 2 * (size_t)(4 * NU + 8 * NH) * kp(N)    // parked row state and row steps, [item][node]
-               + (MMA ? n1 * HP + (size_t)N * ABT : 0);   // operands of the tensor-core sweep
+               + 2 * (size_t)(4 * NU + 8 * NH) * kp(N);   // parked row state and row steps, [item][node]
     }
     // doubles of per-lane-group shared memory
     SDF_HD static int smem_doubles(int N) {
         return NX * NX + NX * (NW + 1) + NW * NW + NW + NU * NX + NU + 2 * NX       // Riccati workspace
                + 2 * NW * kp(N)                                                   // W (iterate), dW (step)
-               + (NCORR + 1 + NPROD) * kp(N) + 8                                  // + one zero row behind corr
+               + (NCORR + NPROD) * kp(N) + 8
                + 2 * STAGE_DOUBLES + 2;                                           // double-buffered per-stage data, 2 mbarriers
     }
 };
@@ -184,16 +175,6 @@ SDF_HD Pair ld2(const double* p) {
 }
 SDF_HD int sym3(int a, int b) { return a >= b ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a; }
 
-#if defined(__CUDA_ARCH__)
-// D (8 x 8) += A (8 x 4) B (4 x 8) on the fp64 tensor pipe (SASS DMMA.8x8x4; measured on B200: 26 cycles dependent, one per
-// 16 cycles and SM sub-partition - the same 16 MAC / cycle as DFMA, in 1 / 8 of the issue slots and with register operands).
-// Lane l = 4 g + q holds A[g][q], B[q][g], D[g][2q], D[g][2q + 1].
-struct Acc2 { double x, y; };
-__device__ __forceinline__ void dmma(Acc2& d, double a, double b) {
-    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d.x), "+d"(d.y) : "d"(a), "d"(b));
-}
-#endif
-
 // Everything the elimination needs from one row; evaluated by ONE function so that the two places that use
 // r_p / rho (right-hand side and step) see bit-identical values.
 struct HardEval { double r_p, Th, coef, rt, rl; };                       // rt = 1/t, rl = 1/lam
@@ -269,14 +250,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
     double* recA = take(n1 * S::REC_A);        // per node: rv0 | rd0 (of the NEXT node) | H
     double* g = take(n1 * NW);
     double* recF = take((size_t)N * S::REC_F);  // per stage: PbM | Linv | K
-    double* cpos = take((n1 * NH * 3 + 1) & ~(size_t)1);   // per node: position block [NH][3] of the constraint rows
-#if defined(__CUDA_ARCH__) && !defined(SDFNMPC_QP_SCALAR)
-    constexpr bool MMA = S::MMA;               // tensor-core factorising sweep (device only; the host emulation keeps the scalar one)
-#else
-    constexpr bool MMA = false;
-#endif
-    double* Hp = MMA ? take(n1 * S::HP) : nullptr;          // [node][16][16] by position
-    double* ABt = MMA ? take((size_t)N * S::ABT) : nullptr; // [stage][16 positions][12 slots]
+    double* cpos = take(n1 * NH * 3);          // per node: position block [NH][3] of the constraint rows
     // rv0: stationarity residual at the initial point (scaled by phi afterwards); rd0[k] = AB_{k-1} w_{k-1} + b_{k-1} - w_x,k
     // lives in record k-1 (the stage that produces node k); H: Gauss-Newton Hessian; L: Cholesky factor of Ruu, diagonal INVERTED
     auto Hk = [&](int k) { return recA + (size_t)k * S::REC_A + S::RA_H; };
@@ -298,7 +272,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
     double* Wsm = vv + NX;               // [NW][KP]   iterate w
     double* dW = Wsm + NW * KP;          // [NW][KP]   step
     double* corr = dW + NW * KP;         // [NCORR][KP] du(NU) Dp(6) gu(NU) gp(3) per node
-    double* prod = corr + (NCORR + 1) * KP;   // [NPROD][KP] affine second-order products (row NCORR of corr stays zero)
+    double* prod = corr + NCORR * KP;    // [NPROD][KP] affine second-order products
     double* stg = prod + NPROD * KP + ((NPROD * KP) & 1);   // 2 x STAGE_DOUBLES (16-byte aligned)
     StagePipe pipe;
     pipe.init(L, reinterpret_cast<unsigned long long*>(stg + 2 * S::STAGE_DOUBLES));
@@ -321,20 +295,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
         for (int r = 0; r < NH; ++r)
             for (int c = 0; c < 3; ++c) cpos[(k * NH + r) * 3 + c] = P.C[((size_t)k * NH + r) * NW + HC0 + c];
     }
-    if (MMA) {
-        // operands of the tensor-core sweep: everything the loops below do not write (pads, affine row of [A B]~, the input
-        // rows / columns of the terminal node) must read as zero
-        for (size_t e = lane; e < n1 * S::HP; e += NL) Hp[e] = 0.0;
-        for (size_t e = lane; e < (size_t)N * S::ABT; e += NL) ABt[e] = 0.0;
-    }
-    if (sdf_cost || MMA) L.sync();
-    if (MMA) {
-        for (int e = lane; e < N * NX * NW; e += NL) {
-            const int k = e / (NX * NW), r = e - k * (NX * NW), i = r / NW, j = r - i * NW;
-            ABt[(size_t)k * S::ABT + S::wpos(j) * 12 + i] = P.AB[e];
-        }
-        for (int k = lane; k < N; k += NL) ABt[(size_t)k * S::ABT + 12 * 12 + 10] = 1.0;   // affine row: [0 .. 0 1]
-    }
+    if (sdf_cost) L.sync();
     // optional cost row r = (1 - 0.5 d)^4 on the stage nodes: dr/dp = -2 (1 - 0.5 d)^3 dd/dp, only the position block
     auto cost_r = [&](int k, double& r, double* Jr) {
         const double q = 1.0 - 0.5 * P.hval[k * NH + (NH - 1)];
@@ -393,10 +354,6 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                 s *= sck;
                 Hk(k)[i * NW + j] = s;
                 Hk(k)[j * NW + i] = s;
-                if (MMA) {
-                    Hp[(size_t)k * S::HP + S::wpos(i) * 16 + S::wpos(j)] = s;
-                    Hp[(size_t)k * S::HP + S::wpos(j) * 16 + S::wpos(i)] = s;
-                }
             }
             for (int i = lane; i < NW; i += NL) {
                 double s = 0.0;
@@ -413,7 +370,6 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
             }
         }
     }
-    for (int e = lane; e < KP; e += NL) corr[NCORR * KP + e] = 0.0;
     L.sync();
 
     // ---- per-lane node state (lane k <-> node k) ------------------------------------------------
@@ -566,7 +522,6 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                 for (int r = 0; r < NH; ++r) s -= (ls[r] - ls[NH + r]) * c_pos(kk, r, i - HC0);
             if ((kk == 0 && i >= NU) || (kk == N && i < NU)) s = 0.0;
             rv0k(kk)[i] = s;
-            if (MMA) { Hp[(size_t)kk * S::HP + S::wpos(i) * 16 + 12] = s; Hp[(size_t)kk * S::HP + 12 * 16 + S::wpos(i)] = s; }
         }
         // rd0_{k} (k >= 1) = AB_{k-1} w_{k-1} + b_{k-1} - w_x,k ; only w_x,0 is non-zero
         if (kk >= 1)
@@ -575,7 +530,6 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                 if (kk == 1)
                     for (int j = NU; j < NW; ++j) s += P.AB[(size_t)i * NW + j] * Wsm[j * KP];
                 rd0k(kk)[i] = s;
-                if (MMA) ABt[(size_t)(kk - 1) * S::ABT + 12 * 12 + i] = s;
             }
     }
     L.sync();
@@ -604,31 +558,6 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                 mpk |= (unsigned long long)(i | (j << 4) | (ca << 8) | (cb << 12)) << (16 * m);
             }
         }
-#if defined(__CUDA_ARCH__) && !defined(SDFNMPC_QP_SCALAR)
-    // tensor-core sweep: which correction row of `corr` each of the lane's 8 accumulator registers receives (NCORR = the zero
-    // row) and whether it belongs to the affine row / column (scaled by phi); register e = (ri, rj, c) holds the entry at
-    // position (8 ri + g, 8 rj + 2 q + c)
-    static_assert(!S::MMA || HC0 == NU, "position block = first three states");
-    unsigned long long mm_ci = 0;
-    unsigned mm_aff = 0;
-    if (MMA) {
-        const int g_ = lane >> 2, q_ = lane & 3;
-        auto upos = [](int p_) { return (p_ >= 9 && (p_ & 1)) ? (p_ - 9) >> 1 : -1; };
-        for (int e = 0; e < 8; ++e) {
-            const int row = 8 * (e >> 2) + g_, col = 8 * ((e >> 1) & 1) + 2 * q_ + (e & 1);
-            int ci = NCORR;
-            if (row == col && upos(row) >= 0) ci = upos(row);
-            else if (row < 3 && col < 3) ci = NU + sym3(row, col);
-            else if ((row == 12) != (col == 12)) {
-                const int o = row == 12 ? col : row;
-                if (upos(o) >= 0) ci = NU + 6 + upos(o);
-                else if (o < 3) ci = 2 * NU + 6 + o;
-            }
-            mm_ci |= (unsigned long long)ci << (5 * e);
-            if (row == 12 || col == 12) mm_aff |= 1u << e;
-        }
-    }
-#endif
 #if defined(SDFNMPC_QP_TRACE) && defined(__CUDA_ARCH__)
     long long qpt_last = clock64();
     int qpt_pass = 0;
@@ -737,145 +666,6 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
             L.sync();
                 QPT(0);
             // =========== backward Riccati sweep (pass 0: factorise + solve; pass 1: new right-hand side only) ===========
-#if defined(__CUDA_ARCH__) && !defined(SDFNMPC_QP_SCALAR)
-            if (MMA && pass == 0) {
-                // ---- factorising sweep on the fp64 tensor pipe, the recursion's matrices never leave the register file ----
-                // With w~ = [u; x; 1] (affine terms ride along as one more column) a stage is
-                //   X' = T' P~          T = [A B | phi rd; 0 1]~ (12 contraction slots x 16 positions), P~ = [P p; p' .]
-                //   M~ = H~ + X' T      H~ = [H rv; rv' .] + this iteration's row-elimination terms
-                //   K~ = -Muu^-1 Mu.    (feedback | feed-forward), Muu^-1 in closed 2 x 2 block form
-                //   P~ <- M~ + M.u K~
-                // i.e. 12 + 12 + 4 DMMA.8x8x4.  Positions are ordered so that an accumulator fragment IS the next operand
-                // fragment: P~ (symmetric) read by columns is the B operand of the first product, X' is the A operand of the
-                // second, column c = 1 of the M~ tiles (., 1) holds the four input columns = A operand of the update, and the
-                // gain of a quad's row, kept by lane q for input q, is its B operand.
-                const int g_ = lane >> 2, q_ = lane & 3;
-                auto ld_h = [&](int kk, Acc2 (&h)[2][2]) {
-                    const double* b_ = Hp + (size_t)kk * S::HP + g_ * 16 + 2 * q_;
-#pragma unroll
-                    for (int ri = 0; ri < 2; ++ri)
-#pragma unroll
-                        for (int rj = 0; rj < 2; ++rj) {
-                            const double2 v = __ldcg(reinterpret_cast<const double2*>(b_ + ri * 128 + rj * 8));
-                            h[ri][rj].x = v.x; h[ri][rj].y = v.y;
-                        }
-                };
-                auto ld_ab = [&](int kk, double (&f0)[2], double (&f1)[2], double (&f2)[2]) {
-                    const double* b_ = ABt + (size_t)kk * S::ABT + g_ * 12;
-#pragma unroll
-                    for (int r = 0; r < 2; ++r) {
-                        const double2 v = __ldcg(reinterpret_cast<const double2*>(b_ + r * 96 + 2 * q_));
-                        f0[r] = v.x; f1[r] = v.y;
-                        f2[r] = __ldcg(b_ + r * 96 + 8 + q_);
-                    }
-                };
-                auto inject = [&](Acc2 (&h)[2][2], int kk) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int ci = (int)((mm_ci >> (5 * e)) & 31u);
-                        const double f = ((mm_aff >> e) & 1u) ? phi : 1.0;
-                        double& v = (e & 1) ? h[e >> 2][(e >> 1) & 1].y : h[e >> 2][(e >> 1) & 1].x;
-                        v = fma(v, f, corr[ci * KP + kk]);
-                    }
-                };
-                Acc2 Pf[2][2], Hn[2][2];
-                double a0[2], a1[2], a2[2];
-                ld_h(N, Pf);
-                ld_h(N - 1, Hn);
-                ld_ab(N - 1, a0, a1, a2);
-                inject(Pf, N);
-                bool ok = true;
-                for (int kk = N - 1; kk >= 0; --kk) {
-                    Acc2 M[2][2];
-                    double f0[2], f1[2], f2[2];
-#pragma unroll
-                    for (int r = 0; r < 2; ++r) { f0[r] = a0[r]; f1[r] = a1[r]; f2[r] = a2[r]; M[r][0] = Hn[r][0]; M[r][1] = Hn[r][1]; }
-                    if (kk > 0) { ld_h(kk - 1, Hn); ld_ab(kk - 1, a0, a1, a2); }     // next stage's operands in flight
-                    inject(M, kk);
-                    // the affine column of T (position 12: tile 1, g = 4) carries phi rd; its own entry (slot 10) stays 1
-                    if (g_ == 4) { f0[1] *= phi; f1[1] *= phi; if (q_ != 2) f2[1] *= phi; }
-                    Acc2 X[2][2];
-#pragma unroll
-                    for (int ri = 0; ri < 2; ++ri)
-#pragma unroll
-                        for (int rm = 0; rm < 2; ++rm) {
-                            X[ri][rm].x = 0.0; X[ri][rm].y = 0.0;
-                            dmma(X[ri][rm], f0[ri], Pf[rm][0].x);
-                            dmma(X[ri][rm], f1[ri], Pf[rm][0].y);
-                            dmma(X[ri][rm], f2[ri], Pf[rm][1].x);
-                        }
-                    // affine row of X' = P (phi rd) + p: the corrector's sweep re-uses P (phi rd)
-                    if (g_ == 4) {
-                        PbMk(kk)[2 * q_] = X[1][0].x - Pf[1][0].x;
-                        PbMk(kk)[2 * q_ + 1] = X[1][0].y - Pf[1][0].y;
-                        if (q_ < 2) PbMk(kk)[8 + q_] = X[1][1].x - Pf[1][1].x;
-                    }
-#pragma unroll
-                    for (int ri = 0; ri < 2; ++ri)
-#pragma unroll
-                        for (int rj = 0; rj < 2; ++rj) {
-                            dmma(M[ri][rj], X[ri][0].x, f0[rj]);
-                            dmma(M[ri][rj], X[ri][0].y, f1[rj]);
-                            dmma(M[ri][rj], X[ri][1].x, f2[rj]);
-                        }
-                    // Muu (positions 9, 11, 13, 15): entry (a, b) sits in lane 4 (1 + 2 a) + b, register y of tile (1, 1)
-                    const double mu_ = M[1][1].y;
-                    const double m00 = __shfl_sync(0xffffffffu, mu_, 4), m10 = __shfl_sync(0xffffffffu, mu_, 12),
-                                 m11 = __shfl_sync(0xffffffffu, mu_, 13), m20 = __shfl_sync(0xffffffffu, mu_, 20),
-                                 m21 = __shfl_sync(0xffffffffu, mu_, 21), m22 = __shfl_sync(0xffffffffu, mu_, 22),
-                                 m30 = __shfl_sync(0xffffffffu, mu_, 28), m31 = __shfl_sync(0xffffffffu, mu_, 29),
-                                 m32 = __shfl_sync(0xffffffffu, mu_, 30), m33 = __shfl_sync(0xffffffffu, mu_, 31);
-                    // LDL' of Muu, redundantly in every lane (a closed-form inverse by 2 x 2 blocks needs only two dependent
-                    // reciprocals, but is not backward stable: late iterations carry ~1e10 rank-one barrier terms that cancel in
-                    // the Schur complement below, and the recursion lost definiteness on 1.4 % of the instances)
-                    const double r0 = rcp(m00);
-                    const double l10 = m10 * r0, l20 = m20 * r0, l30 = m30 * r0;
-                    const double d1 = m11 - l10 * m10;
-                    const double r1 = rcp(d1);
-                    const double t21 = m21 - l20 * m10, t31 = m31 - l30 * m10;
-                    const double l21 = t21 * r1, l31 = t31 * r1;
-                    const double d2 = m22 - l20 * m20 - l21 * t21;
-                    const double r2 = rcp(d2);
-                    const double t32 = m32 - l30 * m20 - l31 * t21;
-                    const double l32 = t32 * r2;
-                    const double d3 = m33 - l30 * m30 - l31 * t31 - l32 * t32;
-                    const double r3 = rcp(d3);
-                    ok = ok && (m00 > 0.0) && (d1 > 0.0) && (d2 > 0.0) && (d3 > 0.0);
-                    double kq[2];
-                    const double mxu[2] = {M[0][1].y, M[1][1].y};        // M~[8 ri + g][u_q]
-#pragma unroll
-                    for (int ri = 0; ri < 2; ++ri) {
-                        const int qb = lane & ~3;
-                        const double v0 = __shfl_sync(0xffffffffu, mxu[ri], qb), v1 = __shfl_sync(0xffffffffu, mxu[ri], qb + 1),
-                                     v2 = __shfl_sync(0xffffffffu, mxu[ri], qb + 2), v3 = __shfl_sync(0xffffffffu, mxu[ri], qb + 3);
-                        const double y1 = v1 - l10 * v0, y2 = v2 - l20 * v0 - l21 * y1, y3 = v3 - l30 * v0 - l31 * y1 - l32 * y2;
-                        const double z3 = y3 * r3, z2 = y2 * r2 - l32 * z3, z1 = y1 * r1 - l21 * z2 - l31 * z3,
-                                     z0 = v0 * r0 - l10 * z1 - l20 * z2 - l30 * z3;
-                        kq[ri] = -(q_ == 0 ? z0 : (q_ == 1 ? z1 : (q_ == 2 ? z2 : z3)));
-                    }
-                    // P~ <- M~ + M.u K~
-#pragma unroll
-                    for (int ri = 0; ri < 2; ++ri)
-#pragma unroll
-                        for (int rj = 0; rj < 2; ++rj) {
-                            Pf[ri][rj] = M[ri][rj];
-                            dmma(Pf[ri][rj], mxu[ri], kq[rj]);
-                        }
-                    // what the corrector's sweep and the roll-outs read: gain, feed-forward, inverse of Muu
-                    Kgk(kk)[q_ * NX + g_] = kq[0];
-                    if (g_ == 0 || g_ == 2) Kgk(kk)[q_ * NX + 8 + (g_ >> 1)] = kq[1];
-                    if (g_ == 4) dW[q_ * KP + kk] = kq[1];
-                    if (lane == 0) {
-                        double2* o = reinterpret_cast<double2*>(Lgk(kk));      // inverse pivots | unit lower factor
-                        o[0] = make_double2(r0, r1); o[1] = make_double2(r2, r3);
-                        o[2] = make_double2(l10, l20); o[3] = make_double2(l30, l21); o[4] = make_double2(l31, l32);
-                    }
-                }
-                if (!ok) status = 4;
-                L.sync();
-            } else
-#endif
-            {
             if (pass == 0) {
                 SDF_LANES_FOR(e, NX * NX) {
                     const int i = e / NX, j = e - i * NX;
@@ -1010,15 +800,9 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                             else kfs[i] = -x[i];
                         }
                     }
-                    if (lane == 0) {
-                        // record of the factor as LDL': inverse pivots, then the unit lower factor column by column
-                        double* o = Lgk(kk);
-                        int e = NU;
-                        for (int j = 0; j < NU; ++j) {
-                            o[j] = Lr[j][j] * Lr[j][j];
-                            for (int i = j + 1; i < NU; ++i) o[e++] = Lr[i][j] * Lr[j][j];
-                        }
-                    }
+                    if (lane == 0)
+                        for (int i = 0; i < NU; ++i)
+                            for (int j = 0; j < NU; ++j) Lgk(kk)[i * NU + j] = j <= i ? Lr[i][j] : 0.0;
                     L.sync();
                 QPT(7);
                     // P <- Qxx + Rux' K (lower triangle, mirrored: stays exactly symmetric), p <- r_x + Rux' kff
@@ -1057,21 +841,21 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                         rv[i] = s;
                     }
                     L.sync();
-                    const double* Fk = sb + S::ST_L;       // LDL' of Muu: inverse pivots [NU] | unit lower factor by columns
+                    const double* Lk = sb + S::ST_L;
                     double x[NU];
 #pragma unroll
                     for (int i = 0; i < NU; ++i) {
                         double s = rv[i];
 #pragma unroll
-                        for (int l = 0; l < i; ++l) s -= Fk[NU + l * NU - l * (l + 1) / 2 + (i - l - 1)] * x[l];
-                        x[i] = s;
+                        for (int l = 0; l < i; ++l) s -= Lk[i * NU + l] * x[l];
+                        x[i] = s * Lk[i * NU + i];
                     }
 #pragma unroll
                     for (int i = NU - 1; i >= 0; --i) {
-                        double s = x[i] * Fk[i];
+                        double s = x[i];
 #pragma unroll
-                        for (int l = i + 1; l < NU; ++l) s -= Fk[NU + i * NU - i * (i + 1) / 2 + (l - i - 1)] * x[l];
-                        x[i] = s;
+                        for (int l = i + 1; l < NU; ++l) s -= Lk[l * NU + i] * x[l];
+                        x[i] = s * Lk[i * NU + i];
                     }
                     const double* Kk = sb + S::ST_K;
                     SDF_LANES_FOR(i, NX + NU) {
@@ -1087,7 +871,6 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                     L.sync();
                 QPT(9);
                 }
-            }
             }
             // ---------- forward roll-out: dW = step ----------
             SDF_LANES_FOR(i, NX) dW[(NU + i) * KP] = 0.0;      // dx_0 = 0 (w_x0 already equals x0 - xbar_0)

@@ -1,0 +1,919 @@
+// Batched OCP-QP solver, tensor-core form (device only): the interior-point method of qp_core.cuh - same formulation, same
+// iterates up to rounding - with every Riccati sweep running on the fp64 tensor pipe (mma.sync m8n8k4 f64, SASS DMMA.8x8x4)
+// and the recursion's matrices living in the register file.  qp_core.cuh stays the scalar statement of the algorithm (host
+// emulation, -DSDFNMPC_QP_SCALAR builds); this file is what libsdfnmpc_b200.so runs for the reference's stage shape
+// (nx 10, nu 4, ny 11, nh 3: models att / att_tau / acc).
+//
+// Role in the reference: the QP acados hands to HPIPM at every SQP-RTI iteration (sdf_nmpc/ocp.py:109-120).
+//
+// Layout idea.  The augmented stage variable w~ = [u; x; 1] (the affine terms ride along as one more column) lives on 16
+// POSITIONS: 0..7 = x0..x7, 8 / 10 / 12 / 14 = x8, x9, the affine entry, a zero pad, 9 / 11 / 13 / 15 = u0..u3; the contraction
+// index of the dynamics lives on 12 SLOTS (slot s < 10 = x_s, 10 = affine, 11 = pad; slot s sits at position s for s < 8 and at
+// 8 + 2 (s - 8) above).  With the m8n8k4 fragment layout (lane 4 g + q holds A[g][q], B[q][g], D[g][2q], D[g][2q+1]) this
+// ordering makes the accumulator fragment of one product, register for register, an operand fragment of the next:
+//   X' = T' P~        T = [A B | phi rd; 0 1]~ (12 slots x 16 positions),  P~ = [P p; p' .] read by columns (symmetric)
+//   M~ = H~ + X' T    H~ = [H rv; rv' .] + this iteration's row-elimination terms
+//   K~ = -Muu^-1 Mu.  LDL' of the 4 x 4 input block in every lane, one row per quad
+//   P~ <- M~ + M.u K~
+// = 12 + 12 + 4 DMMA per stage, no shared-memory round trip and no barrier inside a sweep.  Roll-outs and the corrector's
+// right-hand-side sweep are chains of matrix-vector DMMAs (vector in column 0 of the B operand, result in column 0 of the
+// accumulators, a few shuffles put it back into operand position).  Stage operands come from L2 through a register pipeline
+// several stages deep (`pipelined_stages`).
+//
+// Measured on B200 (tools/dmma_rate.cu): DMMA.8x8x4 26 cycles dependent, one per 16 cycles and SM sub-partition - the same
+// 16 MAC / cycle as DFMA, in 1 / 8 of the issue slots and with register operands.
+#pragma once
+#include "qp_core.cuh"
+
+#if defined(__CUDACC__)
+namespace sdfnmpc {
+
+struct QpMmaShape {
+    static constexpr int NX = 10, NU = 4, NW = 14, NY = 11, NH = 3;
+    static constexpr int NCORR = NU + 6 + NU + 3;   // du, Dp (sym 3x3), gu, gp
+    static constexpr int NPROD = 2 * NU + 4 * NH;
+    static constexpr int NROW = 4 * NU + 8 * NH;    // parked doubles per node: (t, lam) of 8 hard rows, (t, lam, s, mu) of 6 soft rows
+    static constexpr int HP = 256;                  // H~_k, 16 x 16 by position (row-major)
+    static constexpr int ABT = 192;                 // T_k transposed: [16 positions][12 slots]
+    static constexpr int KF = 64;                   // K~_k as fragments: [tile][lane] = K~[q][position 8 tile + g]
+    static constexpr int LF = 16;                   // LDL' of Muu_k: inverse pivots [4] | unit lower factor by columns [6]
+    static constexpr int GP = 16;                   // cost gradient by position
+    SDF_HD static int kp(int N) { return N + 2; }
+    SDF_HD static constexpr int wpos(int i) { return i < NU ? 9 + 2 * i : (i < NU + 8 ? i - NU : 8 + 2 * (i - NU - 8)); }
+    // doubles of global scratch per warp slot
+    SDF_HD static size_t work_doubles(int N) {
+        const size_t n1 = (size_t)N + 1;
+        return n1 * HP + (size_t)N * ABT + (size_t)N * KF + (size_t)N * LF + n1 * GP + ((n1 * NH * 3 + 1) & ~(size_t)1) +
+               2 * (size_t)NROW * kp(N);
+    }
+    // doubles of shared memory per warp: iterate, step, elimination terms (+ a zero row), second-order products, corrector
+    // feed-forward, costate ping-pong of the verification
+    SDF_HD static int smem_doubles(int N) { return (2 * NW + NCORR + 1 + NPROD + NU) * kp(N) + 2 * 16; }
+};
+
+// Lane-strided loops in this file run a WARP-UNIFORM number of trips with the tail predicated (`QM_LANES(e, n)`): a loop whose
+// lanes leave at different trips is a divergent exit, and on this toolchain (nvcc 12.9, sm_100a) the lanes of such a loop -
+// the partially unrolled scatter of [A B], 2800 entries = 87.5 trips - did NOT re-join behind it: the warp went on as two
+// halves, the compiler (which assumes they re-join) had removed the __syncwarp() that followed, and every mma.sync behind it
+// multiplied half-warp fragments only (found with __activemask() probes; -DQM_ASSERT_CONVERGED keeps them as traps).
+#define QM_LANES(v, n) for (int v##_0 = 0; v##_0 < (n); v##_0 += 32) if (const int v = v##_0 + lane; v < (n))
+#if defined(QM_ASSERT_CONVERGED)
+#define QM_CONVERGED() { if (__activemask() != 0xffffffffu) __trap(); }
+#else
+#define QM_CONVERGED()
+#endif
+
+namespace qpdetail {
+
+struct Acc2 { double x, y; };
+__device__ __forceinline__ void dmma(Acc2& d, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d.x), "+d"(d.y) : "d"(a), "d"(b));
+}
+
+// Stage loop with the operands of the next D - 1 stages in flight IN REGISTERS: D operand sets, the loop unrolled by D so
+// that every set keeps its own registers from the load to its use D stages later (a rotating copy o0 = o1 waits for the load
+// at the copy: measured, a stage then takes one full L2 latency, ~1300 cycles, whatever its arithmetic).
+template <int D, class Ops, class Ld, class St>
+__device__ __forceinline__ void pipelined_stages(int n, Ld&& ld, St&& stage) {
+    Ops o[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) o[d] = ld(d < n ? d : n - 1);
+    int i = 0;
+#pragma unroll 1
+    for (; i + D <= n; i += D) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            stage(i + d, o[d]);
+            const int nx = i + d + D;
+            o[d] = ld(nx < n ? nx : n - 1);
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < D - 1; ++d)
+        if (i + d < n) stage(i + d, o[d]);
+}
+
+}  // namespace qpdetail
+
+template <int NFIX = 0>
+__device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, double* sm) {
+    using namespace qpdetail;
+    using S = QpMmaShape;
+    constexpr int NX = S::NX, NU = S::NU, NW = S::NW, NY = S::NY, NH = S::NH, NCORR = S::NCORR, NPROD = S::NPROD;
+    constexpr int HC0 = NU;                       // position block of the constraint rows = first three states
+    const int N = NFIX > 0 ? NFIX : P.N;
+    const int k0 = P.k0, KP = S::kp(N);
+    const int lane = L.lane, g_ = lane >> 2, q_ = lane & 3;
+    const int ncomp = N * 2 * NU + 2 * (N + 1 - k0) * 2 * NH;
+    constexpr unsigned FULL = 0xffffffffu;
+
+    // ---- global scratch (one block per resident warp) ----
+    double* p = P.work;
+    auto take = [&](size_t n) { double* r = p; p += n; return r; };
+    const size_t n1 = (size_t)N + 1;
+    double* Hp = take(n1 * S::HP);
+    double* ABt = take((size_t)N * S::ABT);
+    double* Kf = take((size_t)N * S::KF);
+    double* Lf = take((size_t)N * S::LF);
+    double* gpos = take(n1 * S::GP);
+    double* cpos = take((n1 * NH * 3 + 1) & ~(size_t)1);
+    double* TB = take((size_t)S::NROW * KP);
+    double* TD = take((size_t)S::NROW * KP);
+
+    // ---- shared workspace ----
+    double* Wsm = sm;                             // [NW][KP]   iterate w
+    double* dW = Wsm + NW * KP;                   // [NW][KP]   step
+    double* corr = dW + NW * KP;                  // [NCORR + 1][KP] du(NU) Dp(6) gu(NU) gp(3) per node, then a zero row
+    double* prod = corr + (NCORR + 1) * KP;       // [NPROD][KP] affine second-order products
+    double* ffd = prod + NPROD * KP;              // [NU][KP]   input residual / feed-forward of the corrector's sweep
+    double* pp = ffd + NU * KP;                   // [2][16]    costate ping-pong of the verification
+
+    auto scale = [&](int k) { return k < N ? P.dt[k] : 1.0; };
+    auto wrow = [&](int k, int r) { return k < N ? P.W[k * NY + r] : (r < P.nyN ? P.WN[r] : 0.0); };
+    auto c_pos = [&](int kk, int r, int c) { return cpos[(kk * NH + r) * 3 + c]; };
+    // position -> index into w = [u; x] (14 = affine, 15 = pad)
+    auto widx = [](int pos) { return pos < 8 ? NU + pos : ((pos & 1) ? (pos - 9) >> 1 : (pos == 8 ? NU + 8 : (pos == 10 ? NU + 9 : (pos == 12 ? 14 : 15)))); };
+
+    // =====================================================================================================
+    // prologue: SDF row of C / h, operands of the sweeps
+    // =====================================================================================================
+    const bool sdf_cost = P.sdf_cost_w > 0.0;     // the cost row also needs the SDF at node 0
+    QM_LANES(k, N + 1) {
+        if (k >= (sdf_cost ? 0 : k0)) {
+            const double* R = P.pose + 3;
+            const double gx = P.sdf_g[k * 3 + 0], gy = P.sdf_g[k * 3 + 1], gz = P.sdf_g[k * 3 + 2];
+            double* Cr = P.C + ((size_t)k * NH + (NH - 1)) * NW;
+            for (int jj = 0; jj < 3; ++jj) Cr[HC0 + jj] = P.flag * (R[jj * 3 + 0] * gx + R[jj * 3 + 1] * gy + R[jj * 3 + 2] * gz);
+            P.hval[k * NH + (NH - 1)] = P.flag * (double)P.sdf_d[k] + (1.0 - P.flag) * P.max_df;
+        }
+        for (int r = 0; r < NH; ++r)
+            for (int c = 0; c < 3; ++c) cpos[(k * NH + r) * 3 + c] = P.C[((size_t)k * NH + r) * NW + HC0 + c];
+    }
+    // T_k: zero everything the scatter below does not write (pads, affine row), then [A B] by (position, slot)
+    QM_LANES(e, N * S::ABT) __stcg(ABt + e, 0.0);
+    QM_LANES(e, (N + 1) * S::GP) __stcg(gpos + e, 0.0);
+    QM_LANES(e, NW * KP) { Wsm[e] = 0.0; dW[e] = 0.0; }
+    QM_LANES(e, KP) corr[NCORR * KP + e] = 0.0;
+    L.sync();
+    QM_LANES(e, N * NX * NW) {
+        const int k = e / (NX * NW), r = e - k * (NX * NW), i = r / NW, j = r - i * NW;
+        __stcg(ABt + (size_t)k * S::ABT + S::wpos(j) * 12 + i, P.AB[e]);
+    }
+    QM_LANES(k, N) __stcg(ABt + (size_t)k * S::ABT + 12 * 12 + 10, 1.0);   // affine row: [0 .. 0 1]
+    QM_LANES(i, NX) Wsm[(NU + i) * KP] = P.x0[i] - P.xbar[i];       // dx_0 (0 when node 0 was linearised at x0)
+    // H~_k = J~' (W dt) J~ + lm dt I with J~ = [J | y - yref]: 12 DMMA per node straight from the linearisation's J; the affine
+    // column comes out as the cost gradient.
+    // mma.sync.aligned needs the WHOLE warp at the instruction: see QM_LANES above for why every loop before this point has a
+    // warp-uniform trip count.
+    L.sync();
+    {
+        struct HOps { double v[3][2], a[3][2]; };          // J~ entries and the same entries times their row weight
+        // the lane's operand entries: J~[row 4 s + q][position 8 t + g]
+        const int wi0 = widx(g_), wi1 = widx(8 + g_);
+        auto ld_ops = [&](int k) {
+            // every load is unconditional (rows past NY are clamped and carry weight 0, the pad position is masked): nothing
+            // here is predicated
+            HOps o;
+            const double* Jk = P.J + (size_t)k * NY * NW;
+            const double* yk = P.yres + (size_t)k * NY;
+            const double sck = scale(k);
+            const double m1 = wi1 == 15 ? 0.0 : 1.0;
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                const int r = 4 * s + q_;
+                const int rc = r < NY ? r : NY - 1;
+                const double w = r < NY ? wrow(k, rc) * sck : 0.0;
+                o.v[s][0] = Jk[rc * NW + wi0];
+                const double* src = wi1 < NW ? Jk + rc * NW + wi1 : yk + rc;
+                o.v[s][1] = *src * m1;
+                // the weighted copies are formed HERE, a pipeline stage before the products that consume them
+                o.a[s][0] = o.v[s][0] * w;
+                o.a[s][1] = o.v[s][1] * w;
+            }
+            return o;
+        };
+        auto stage = [&](int k, const HOps& o) {
+            L.sync();
+            QM_CONVERGED()
+            // accumulators start from the Levenberg-Marquardt diagonal (and the optional SDF cost row), then J~' (W dt) J~
+            Acc2 H[2][2];
+            const double lmk = P.lm * scale(k);
+            double cr = 0.0, cJ[3] = {0.0, 0.0, 0.0}, wk = 0.0;
+            if (sdf_cost && k < N) {       // optional cost row r = (1 - 0.5 d)^4, position block only (gen_model.py:65-66)
+                const double qq = 1.0 - 0.5 * P.hval[k * NH + (NH - 1)];
+                const double* Cr = P.C + ((size_t)k * NH + (NH - 1)) * NW;
+                cr = qq * qq * qq * qq;
+                for (int c = 0; c < 3; ++c) cJ[c] = -2.0 * qq * qq * qq * Cr[HC0 + c];
+                wk = P.sdf_cost_w * scale(k);
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int row = 8 * (e >> 2) + g_, col = 8 * ((e >> 1) & 1) + 2 * q_ + (e & 1);
+                double v = (row == col && row != 12 && row != 14) ? lmk : 0.0;
+                if (sdf_cost) {
+                    const double jr = row == 0 ? cJ[0] : (row == 1 ? cJ[1] : cJ[2]), jc = col == 0 ? cJ[0] : (col == 1 ? cJ[1] : cJ[2]);
+                    if (row < 3 && col < 3) v += wk * jr * jc;
+                    if (row < 3 && col == 12) v += wk * cr * jr;
+                    if (col < 3 && row == 12) v += wk * cr * jc;
+                }
+                if (e & 1) H[e >> 2][(e >> 1) & 1].y = v; else H[e >> 2][(e >> 1) & 1].x = v;
+            }
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                    for (int s = 0; s < 3; ++s) dmma(H[mt][nt], o.a[s][mt], o.v[s][nt]);
+            double* hb = Hp + (size_t)k * S::HP + g_ * 16 + 2 * q_;
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt)
+                    __stcg(reinterpret_cast<double2*>(hb + mt * 128 + nt * 8), make_double2(H[mt][nt].x, H[mt][nt].y));
+            // cost gradient (affine column, position 12 = tile 1, q 2, register x)
+            if (q_ == 2) { __stcg(gpos + k * S::GP + g_, H[0][1].x); __stcg(gpos + k * S::GP + 8 + g_, H[1][1].x); }
+        };
+        pipelined_stages<2, HOps>(N + 1, ld_ops, stage);
+    }
+    L.sync();
+
+    // =====================================================================================================
+    // per-lane node state (lane k <-> node k), parked in L2 between the row phases ([item][node]: coalesced)
+    // =====================================================================================================
+    double tb[2 * NU], lb[2 * NU], ts[2 * NH], ls[2 * NH], ss[2 * NH], ms[2 * NH];
+    double dtb[2 * NU], dlb[2 * NU], dts[2 * NH], dls[2 * NH], dss[2 * NH], dms[2 * NH];
+    auto hard_d = [&](int kk, int a) {
+        const int j = a < NU ? a : a - NU;
+        const double ub = P.ubar[kk * NU + j];
+        return a < NU ? P.lbu[j] - ub : ub - P.ubu[j];
+    };
+    auto soft_d = [&](int kk, int a) {
+        const int r = a < NH ? a : a - NH;
+        const double hv = P.hval[kk * NH + r];
+        return a < NH ? P.lh[r] - hv : hv - P.uh[r];
+    };
+#define QM_LD(p_) __ldcg(p_)
+#define QM_ST(p_, v_) __stcg(p_, v_)
+#define QM_LOAD(BASE, A, B, C4, D4, E4, F4, kk)                                                                      \
+    {                                                                                                                \
+        const double* q__ = BASE + (kk);                                                                             \
+        _Pragma("unroll") for (int a = 0; a < 2 * NU; ++a) { A[a] = QM_LD(q__ + a * KP); B[a] = QM_LD(q__ + (2 * NU + a) * KP); } \
+        _Pragma("unroll") for (int a = 0; a < 2 * NH; ++a) {                                                         \
+            C4[a] = QM_LD(q__ + (4 * NU + a) * KP); D4[a] = QM_LD(q__ + (4 * NU + 2 * NH + a) * KP);                   \
+            E4[a] = QM_LD(q__ + (4 * NU + 4 * NH + a) * KP); F4[a] = QM_LD(q__ + (4 * NU + 6 * NH + a) * KP);          \
+        }                                                                                                            \
+    }
+#define QM_STORE(BASE, A, B, C4, D4, E4, F4, kk)                                                                     \
+    {                                                                                                                \
+        double* q__ = BASE + (kk);                                                                                   \
+        _Pragma("unroll") for (int a = 0; a < 2 * NU; ++a) { QM_ST(q__ + a * KP, A[a]); QM_ST(q__ + (2 * NU + a) * KP, B[a]); } \
+        _Pragma("unroll") for (int a = 0; a < 2 * NH; ++a) {                                                         \
+            QM_ST(q__ + (4 * NU + a) * KP, C4[a]); QM_ST(q__ + (4 * NU + 2 * NH + a) * KP, D4[a]);                    \
+            QM_ST(q__ + (4 * NU + 4 * NH + a) * KP, E4[a]); QM_ST(q__ + (4 * NU + 6 * NH + a) * KP, F4[a]);            \
+        }                                                                                                            \
+    }
+#define QM_LOAD_STATE(kk) QM_LOAD(TB, tb, lb, ts, ls, ss, ms, kk)
+#define QM_STORE_STATE(kk) QM_STORE(TB, tb, lb, ts, ls, ss, ms, kk)
+#define QM_LOAD_DELTA(kk) QM_LOAD(TD, dtb, dlb, dts, dls, dss, dms, kk)
+#define QM_STORE_DELTA(kk) QM_STORE(TD, dtb, dlb, dts, dls, dss, dms, kk)
+#define QM_NODE_LOOP(kk) QM_LANES(kk, N + 1)
+
+    // ---- initial point and initial residuals (w = 0 except dx_0, costates 0) ----
+    double res_v0 = 0.0;
+    QM_NODE_LOOP(kk) {
+#pragma unroll
+        for (int a = 0; a < 2 * NU; ++a) {
+            double t = 1.0, l = 1.0;
+            if (kk < N) {
+                t = fmax(-hard_d(kk, a), SDFNMPC_QP_T0);
+                l = fmax(SDFNMPC_QP_MU0 / t, 1e-3 * SDFNMPC_QP_MU0);
+            }
+            tb[a] = t; lb[a] = l;
+        }
+#pragma unroll
+        for (int a = 0; a < 2 * NH; ++a) {
+            const int r = a < NH ? a : a - NH;
+            double t = 1.0, l = 1.0, m = 1.0, s0 = SDFNMPC_QP_S0;
+            if (kk >= k0) {
+                const double z = P.zs[r] * scale(kk), Z = P.Zs[r] * scale(kk);
+                double cw = 0.0;
+                for (int c = 0; c < 3; ++c) cw += c_pos(kk, r, c) * Wsm[(HC0 + c) * KP + kk];
+                const double gw = a < NH ? cw : -cw;
+                t = fmax(gw - soft_d(kk, a) + s0, SDFNMPC_QP_T0);
+                l = fmax(0.5 * (z + Z * s0), 1e-3);
+                m = l;
+            }
+            ts[a] = t; ss[a] = s0; ls[a] = l; ms[a] = m;
+        }
+        QM_STORE_STATE(kk);
+        // rv0_k = H_k w_k + g_k - sum lam_i gvec_i -> affine row / column of H~_k (inputs, then states: no dynamically
+        // indexed register arrays)
+        double* hk = Hp + (size_t)kk * S::HP;
+        auto h_w0 = [&](int pi) {           // H_0[., x] dx_0
+            double s = 0.0;
+            for (int j = NU; j < NW; ++j) s += __ldcg(hk + pi * 16 + S::wpos(j)) * Wsm[j * KP];
+            return s;
+        };
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+            const int pi = S::wpos(i);
+            double s = __ldcg(gpos + kk * S::GP + pi);
+            if (kk == 0) s += h_w0(pi);
+            if (kk < N) s -= lb[i] - lb[NU + i];
+            if (kk == N) s = 0.0;
+            __stcg(hk + pi * 16 + 12, s); __stcg(hk + 12 * 16 + pi, s);
+            res_v0 = fmax(res_v0, fabs(s));
+        }
+        const double lsd[NH] = {ls[0] - ls[NH], ls[1] - ls[NH + 1], ls[2] - ls[NH + 2]};
+#pragma unroll 1
+        for (int i = NU; i < NW; ++i) {
+            const int pi = S::wpos(i);
+            double s = __ldcg(gpos + kk * S::GP + pi);
+            if (kk >= k0 && i < HC0 + 3) s -= lsd[0] * c_pos(kk, 0, i - HC0) + lsd[1] * c_pos(kk, 1, i - HC0) + lsd[2] * c_pos(kk, 2, i - HC0);
+            if (kk == 0) s = 0.0;
+            __stcg(hk + pi * 16 + 12, s); __stcg(hk + 12 * 16 + pi, s);
+            res_v0 = fmax(res_v0, fabs(s));
+        }
+        // rd0_k (k >= 1) = AB_{k-1} w_{k-1} + b_{k-1} - w_x,k -> affine column of T_{k-1}
+        if (kk >= 1) {
+            double* tk = ABt + (size_t)(kk - 1) * S::ABT + 12 * 12;
+#pragma unroll 1
+            for (int i = 0; i < NX; ++i) {
+                double s = P.bdyn[(kk - 1) * NX + i];
+                if (kk == 1)
+                    for (int j = NU; j < NW; ++j) s += P.AB[(size_t)i * NW + j] * Wsm[j * KP];
+                __stcg(tk + i, s);
+                res_v0 = fmax(res_v0, fabs(s));
+            }
+        }
+    }
+    res_v0 = L.max(res_v0);
+    L.sync();
+
+    // per-lane metadata of the factorising sweep: which row of `corr` each of the lane's 8 accumulator registers receives
+    // (NCORR = the zero row) and whether it belongs to the affine row / column (scaled by phi); register e = (ri, rj, c)
+    // holds the entry at position (8 ri + g, 8 rj + 2 q + c)
+    unsigned long long mm_ci = 0;
+    unsigned mm_aff = 0;
+    {
+        auto upos = [](int p_) { return (p_ >= 9 && (p_ & 1)) ? (p_ - 9) >> 1 : -1; };
+        for (int e = 0; e < 8; ++e) {
+            const int row = 8 * (e >> 2) + g_, col = 8 * ((e >> 1) & 1) + 2 * q_ + (e & 1);
+            int ci = NCORR;
+            if (row == col && upos(row) >= 0) ci = upos(row);
+            else if (row < 3 && col < 3) ci = NU + sym3(row, col);
+            else if ((row == 12) != (col == 12)) {
+                const int o = row == 12 ? col : row;
+                if (upos(o) >= 0) ci = NU + 6 + upos(o);
+                else if (o < 3) ci = 2 * NU + 6 + o;
+            }
+            mm_ci |= (unsigned long long)ci << (5 * e);
+            if (row == 12 || col == 12) mm_aff |= 1u << e;
+        }
+    }
+
+    // stage operands in the lane layouts of the three kinds of sweeps
+    auto ld_h = [&](int kk, Acc2 (&h)[2][2]) {                       // H~ tiles as accumulators
+        const double* b_ = Hp + (size_t)kk * S::HP + g_ * 16 + 2 * q_;
+#pragma unroll
+        for (int ri = 0; ri < 2; ++ri)
+#pragma unroll
+            for (int rj = 0; rj < 2; ++rj) {
+                const double2 v = __ldcg(reinterpret_cast<const double2*>(b_ + ri * 128 + rj * 8));
+                h[ri][rj].x = v.x; h[ri][rj].y = v.y;
+            }
+    };
+    struct TOps { double f0[2], f1[2], f2[2]; };                      // T'[position 8 r + g][slots 2q, 2q+1, 8+q]
+    auto ld_t = [&](int kk) {
+        TOps o;
+        const double* b_ = ABt + (size_t)kk * S::ABT + g_ * 12;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const double2 v = __ldcg(reinterpret_cast<const double2*>(b_ + r * 96 + 2 * q_));
+            o.f0[r] = v.x; o.f1[r] = v.y;
+            o.f2[r] = __ldcg(b_ + r * 96 + 8 + q_);
+        }
+        return o;
+    };
+    auto inject = [&](Acc2 (&h)[2][2], int kk, double phi_) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int ci = (int)((mm_ci >> (5 * e)) & 31u);
+            const double f = ((mm_aff >> e) & 1u) ? phi_ : 1.0;
+            double& v = (e & 1) ? h[e >> 2][(e >> 1) & 1].y : h[e >> 2][(e >> 1) & 1].x;
+            v = fma(v, f, corr[ci * KP + kk]);
+        }
+    };
+
+    int status = 2, it = 0;
+    bool safe = false;              // conservative mode after a stall: more centring, no second-order term
+    double cm_prev1 = 1e300, cm_prev2 = 1e300;
+    double phi = 1.0;               // product of (1 - alpha): scale of the stationarity / dynamics residuals
+    double res_track = 0.0;
+    for (;; ++it) {
+        double tau = 0.0, mubar = 0.0;
+        bool stop = false;
+        for (int pass = 0; pass < 2 && !stop; ++pass) {
+            // =========== row elimination (lane = node): corrections of the stage Hessian / rhs ===========
+            double res_rows = 0.0, cmax = 0.0, csum = 0.0;
+            QM_NODE_LOOP(kk) {
+                QM_LOAD_STATE(kk);
+                double du[NU], gu[NU], Dp[6] = {0, 0, 0, 0, 0, 0}, gp[3] = {0, 0, 0};
+#pragma unroll
+                for (int j = 0; j < NU; ++j) {
+                    double thn = 0.0, cn = 0.0;
+                    if (kk < N) {
+                        const double wu = Wsm[j * KP + kk];
+#pragma unroll
+                        for (int side = 0; side < 2; ++side) {
+                            const int a = side * NU + j;
+                            const double sgn = side == 0 ? 1.0 : -1.0;
+                            const double cr = pass == 0 ? 0.0 : tau - prod[a * KP + kk];
+                            const HardEval ev = hard_eval(tb[a], lb[a], sgn * wu, hard_d(kk, a), cr);
+                            thn += ev.Th;
+                            cn += sgn * ev.coef;
+                            if (pass == 0) {
+                                res_rows = fmax(res_rows, fabs(ev.r_p));
+                                const double c = lb[a] * tb[a];
+                                cmax = fmax(cmax, c); csum += c;
+                            }
+                        }
+                    }
+                    du[j] = thn; gu[j] = cn;
+                }
+                if (kk >= k0) {
+#pragma unroll
+                    for (int r = 0; r < NH; ++r) {
+                        const double c0 = c_pos(kk, r, 0), c1 = c_pos(kk, r, 1), c2 = c_pos(kk, r, 2);
+                        const double cw = c0 * Wsm[(HC0 + 0) * KP + kk] + c1 * Wsm[(HC0 + 1) * KP + kk] + c2 * Wsm[(HC0 + 2) * KP + kk];
+                        const double z = P.zs[r] * scale(kk), Z = P.Zs[r] * scale(kk);
+                        double thn = 0.0, cn = 0.0;
+#pragma unroll
+                        for (int side = 0; side < 2; ++side) {
+                            const int a = side * NH + r;
+                            const double sgn = side == 0 ? 1.0 : -1.0;
+                            const double ct = pass == 0 ? 0.0 : tau - prod[(2 * NU + a) * KP + kk];
+                            const double cs = pass == 0 ? 0.0 : tau - prod[(2 * NU + 2 * NH + a) * KP + kk];
+                            const SoftEval ev = soft_eval(ts[a], ls[a], ss[a], ms[a], sgn * cw, soft_d(kk, a), z, Z, ct, cs);
+                            thn += ev.Tht;
+                            cn += sgn * ev.coef;
+                            if (pass == 0) {
+                                res_rows = fmax(res_rows, fmax(fabs(ev.r_p), fabs(ev.r_s)));
+                                const double ca = ls[a] * ts[a], cb = ms[a] * ss[a];
+                                cmax = fmax(cmax, fmax(ca, cb)); csum += ca + cb;
+                            }
+                        }
+                        Dp[0] += thn * c0 * c0; Dp[1] += thn * c1 * c0; Dp[2] += thn * c1 * c1;
+                        Dp[3] += thn * c2 * c0; Dp[4] += thn * c2 * c1; Dp[5] += thn * c2 * c2;
+                        gp[0] += cn * c0; gp[1] += cn * c1; gp[2] += cn * c2;
+                    }
+                }
+                // the corrector solves for the CHANGE of the step, so its right-hand side is the change of the elimination
+                // terms against the predictor's (same lane, same slots)
+#pragma unroll
+                for (int j = 0; j < NU; ++j) {
+                    if (pass == 0) { corr[j * KP + kk] = du[j]; corr[(NU + 6 + j) * KP + kk] = gu[j]; }
+                    else corr[(NU + 6 + j) * KP + kk] = gu[j] - corr[(NU + 6 + j) * KP + kk];
+                }
+                if (pass == 0) {
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) corr[(NU + c) * KP + kk] = Dp[c];
+                }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) corr[(2 * NU + 6 + c) * KP + kk] = pass == 0 ? gp[c] : gp[c] - corr[(2 * NU + 6 + c) * KP + kk];
+            }
+            if (pass == 0) {
+                // ---- convergence test on the state BEFORE this iteration's step ----
+                res_rows = L.max(res_rows);
+                cmax = L.max(cmax);
+                mubar = L.sum(csum) / ncomp;
+                res_track = fmax(res_rows, phi * res_v0);
+#if defined(SDFNMPC_QP_DEBUG_INST)
+                if (P.debug && lane == 0) printf("it %d res %.3e (rows %.3e) cmax %.3e phi %.3e mubar %.3e\n", it, res_track, res_rows, cmax, phi, mubar);
+#endif
+                if (!(res_track == res_track) || !(mubar == mubar) || res_track > 1e300) {
+                    if (lane == 0 && P.res_out) { P.res_out[0] = res_v0; P.res_out[1] = res_rows + 1e3 * mubar; }   // breakdown diagnostics
+                    status = 4; stop = true; break;
+                }
+                if (res_track <= P.tol_res && cmax <= P.tol) { status = 0; stop = true; break; }
+                if (it >= P.max_iter) { status = 2; stop = true; break; }
+                // Mehrotra's corrector can cycle on poorly centred iterates; if the largest complementarity product
+                // has not dropped by 30 % over two iterations switch (for good) to plain damped path following.
+                if (it >= 2 && cmax > 0.7 * cm_prev2) safe = true;
+                cm_prev2 = cm_prev1; cm_prev1 = cmax;
+            }
+            L.sync();
+            if (pass == 0) {
+                // =========== factorising backward sweep ===========
+                struct FacOps { Acc2 h[2][2]; TOps t; };
+                auto ld_ops = [&](int i_) {
+                    FacOps o;
+                    ld_h(N - 1 - i_, o.h);
+                    o.t = ld_t(N - 1 - i_);
+                    return o;
+                };
+                Acc2 Pf[2][2];
+                ld_h(N, Pf);
+                inject(Pf, N, phi);
+                bool ok = true;
+                auto stage = [&](int i_, const FacOps& o) {
+                    L.sync();
+                    QM_CONVERGED()
+                    const int kk = N - 1 - i_;
+                    Acc2 M[2][2];
+                    double f0[2], f1[2], f2[2];
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) { f0[r] = o.t.f0[r]; f1[r] = o.t.f1[r]; f2[r] = o.t.f2[r]; M[r][0] = o.h[r][0]; M[r][1] = o.h[r][1]; }
+                    inject(M, kk, phi);
+                    // the affine column of T (position 12: tile 1, g = 4) carries phi rd; its own entry (slot 10) stays 1
+                    if (g_ == 4) { f0[1] *= phi; f1[1] *= phi; if (q_ != 2) f2[1] *= phi; }
+                    Acc2 X[2][2];
+                    // tile row 1 first: it holds the input block, whose (scalar) factorisation then runs under the tensor
+                    // work of tile row 0
+#pragma unroll
+                    for (int ri = 1; ri >= 0; --ri)
+#pragma unroll
+                        for (int rm = 0; rm < 2; ++rm) {
+                            X[ri][rm].x = 0.0; X[ri][rm].y = 0.0;
+                            dmma(X[ri][rm], f0[ri], Pf[rm][0].x);
+                            dmma(X[ri][rm], f1[ri], Pf[rm][0].y);
+                            dmma(X[ri][rm], f2[ri], Pf[rm][1].x);
+                        }
+#pragma unroll
+                    for (int ri = 1; ri >= 0; --ri)
+#pragma unroll
+                        for (int rj = 1; rj >= 0; --rj) {
+                            dmma(M[ri][rj], X[ri][0].x, f0[rj]);
+                            dmma(M[ri][rj], X[ri][0].y, f1[rj]);
+                            dmma(M[ri][rj], X[ri][1].x, f2[rj]);
+                        }
+                    // Muu (positions 9, 11, 13, 15): entry (a, b) sits in lane 4 (1 + 2 a) + b, register y of tile (1, 1)
+                    const double mu_ = M[1][1].y;
+                    const double m00 = __shfl_sync(FULL, mu_, 4), m10 = __shfl_sync(FULL, mu_, 12), m11 = __shfl_sync(FULL, mu_, 13),
+                                 m20 = __shfl_sync(FULL, mu_, 20), m21 = __shfl_sync(FULL, mu_, 21), m22 = __shfl_sync(FULL, mu_, 22),
+                                 m30 = __shfl_sync(FULL, mu_, 28), m31 = __shfl_sync(FULL, mu_, 29), m32 = __shfl_sync(FULL, mu_, 30),
+                                 m33 = __shfl_sync(FULL, mu_, 31);
+                    // LDL' of Muu, redundantly in every lane (a closed-form inverse by 2 x 2 blocks needs only two dependent
+                    // reciprocals, but is not backward stable: late iterations carry ~1e10 rank-one barrier terms that cancel in
+                    // the Schur complement below, and the recursion lost definiteness on 1.4 % of the instances)
+                    const double r0 = rcp(m00);
+                    const double l10 = m10 * r0, l20 = m20 * r0, l30 = m30 * r0;
+                    const double d1 = m11 - l10 * m10;
+                    const double r1 = rcp(d1);
+                    const double t21 = m21 - l20 * m10, t31 = m31 - l30 * m10;
+                    const double l21 = t21 * r1, l31 = t31 * r1;
+                    const double d2 = m22 - l20 * m20 - l21 * t21;
+                    const double r2 = rcp(d2);
+                    const double t32 = m32 - l30 * m20 - l31 * t21;
+                    const double l32 = t32 * r2;
+                    const double d3 = m33 - l30 * m30 - l31 * t31 - l32 * t32;
+                    const double r3 = rcp(d3);
+                    ok = ok && (m00 > 0.0) && (d1 > 0.0) && (d2 > 0.0) && (d3 > 0.0);
+                    double kq[2];
+                    const double mxu[2] = {M[0][1].y, M[1][1].y};        // M~[8 ri + g][u_q]
+#pragma unroll
+                    for (int ri = 0; ri < 2; ++ri) {
+                        const int qb = lane & ~3;
+                        const double v0 = __shfl_sync(FULL, mxu[ri], qb), v1 = __shfl_sync(FULL, mxu[ri], qb + 1),
+                                     v2 = __shfl_sync(FULL, mxu[ri], qb + 2), v3 = __shfl_sync(FULL, mxu[ri], qb + 3);
+                        const double y1 = v1 - l10 * v0, y2 = v2 - l20 * v0 - l21 * y1, y3 = v3 - l30 * v0 - l31 * y1 - l32 * y2;
+                        const double z3 = y3 * r3, z2 = y2 * r2 - l32 * z3, z1 = y1 * r1 - l21 * z2 - l31 * z3,
+                                     z0 = v0 * r0 - l10 * z1 - l20 * z2 - l30 * z3;
+                        kq[ri] = -(q_ == 0 ? z0 : (q_ == 1 ? z1 : (q_ == 2 ? z2 : z3)));
+                    }
+                    // P~ <- M~ + M.u K~
+#pragma unroll
+                    for (int ri = 0; ri < 2; ++ri)
+#pragma unroll
+                        for (int rj = 0; rj < 2; ++rj) {
+                            Pf[ri][rj] = M[ri][rj];
+                            dmma(Pf[ri][rj], mxu[ri], kq[rj]);
+                        }
+                    // for the roll-outs and the corrector: gains (with the feed-forward in the affine position) and the factor
+                    __stcg(Kf + (size_t)kk * S::KF + lane, kq[0]);
+                    __stcg(Kf + (size_t)kk * S::KF + 32 + lane, kq[1]);
+                    if (lane == 0) {
+                        double2* lo = reinterpret_cast<double2*>(Lf + (size_t)kk * S::LF);
+                        __stcg(lo + 0, make_double2(r0, r1)); __stcg(lo + 1, make_double2(r2, r3));
+                        __stcg(lo + 2, make_double2(l10, l20)); __stcg(lo + 3, make_double2(l30, l21)); __stcg(lo + 4, make_double2(l31, l32));
+                    }
+                };
+                pipelined_stages<2, FacOps>(N, ld_ops, stage);
+                if (!ok) status = 4;
+            } else {
+                // =========== corrector: same matrix, right-hand side = change of the elimination terms, no dynamics residual ===========
+                //   r~_k = delta r_k + T_k' p_{k+1},   p_k = r~_k + K_k' r~_k,u     (column 0 of the accumulators, lanes 4 g)
+                // 8 DMMA per stage; the input residuals r~_k,u are left in `ffd` and turned into feed-forwards for all stages
+                // at once afterwards (lane = stage), which keeps the 4 x 4 solves out of the recursion.
+                const int cr0 = (q_ == 0 && g_ < 3) ? 2 * NU + 6 + g_ : NCORR;
+                const int cr1 = (q_ == 0 && (g_ & 1)) ? NU + 6 + (g_ >> 1) : NCORR;
+                struct BackOps { TOps t; double kf[2]; };
+                auto ld_ops = [&](int i_) {
+                    BackOps o;
+                    const int kk = N - 1 - i_;
+                    o.t = ld_t(kk);
+                    o.kf[0] = __ldcg(Kf + (size_t)kk * S::KF + lane);
+                    o.kf[1] = __ldcg(Kf + (size_t)kk * S::KF + 32 + lane);
+                    return o;
+                };
+                double bA = 2 * q_ < 3 ? corr[(2 * NU + 6 + 2 * q_) * KP + N] : 0.0;
+                double bB = q_ == 0 ? corr[(2 * NU + 6 + 1) * KP + N] : 0.0;
+                double bC = 0.0;
+                auto stage = [&](int i_, const BackOps& o) {
+                    L.sync();
+                    QM_CONVERGED()
+                    const int kk = N - 1 - i_;
+                    Acc2 R[2];
+                    R[0].x = corr[cr0 * KP + kk]; R[0].y = 0.0;
+                    R[1].x = corr[cr1 * KP + kk]; R[1].y = 0.0;
+                    dmma(R[0], o.t.f0[0], bA); dmma(R[1], o.t.f0[1], bA);
+                    dmma(R[0], o.t.f1[0], bB); dmma(R[1], o.t.f1[1], bB);
+                    dmma(R[0], o.t.f2[0], bC); dmma(R[1], o.t.f2[1], bC);
+                    if (q_ == 0 && (g_ & 1)) ffd[(g_ >> 1) * KP + kk] = R[1].x;
+                    const double bR = __shfl_sync(FULL, R[1].x, 4 * (1 + 2 * q_));
+                    dmma(R[0], o.kf[0], bR); dmma(R[1], o.kf[1], bR);
+                    bA = __shfl_sync(FULL, R[0].x, 8 * q_);
+                    bB = __shfl_sync(FULL, R[0].x, 8 * q_ + 4);
+                    bC = __shfl_sync(FULL, R[1].x, 8 * q_);
+                    if (q_ >= 2) bC = 0.0;
+                };
+                pipelined_stages<4, BackOps>(N, ld_ops, stage);
+                L.sync();
+                // feed-forward of every stage: -Muu^-1 r~_u with the factor the predictor's sweep left (lane = stage)
+                QM_LANES(kk, N) {
+                    double Fk[10];
+#pragma unroll
+                    for (int e = 0; e < 10; e += 2) {
+                        const double2 v = __ldcg(reinterpret_cast<const double2*>(Lf + (size_t)kk * S::LF + e));
+                        Fk[e] = v.x; Fk[e + 1] = v.y;
+                    }
+                    double x[NU];
+#pragma unroll
+                    for (int i = 0; i < NU; ++i) {
+                        double s_ = ffd[i * KP + kk];
+#pragma unroll
+                        for (int l = 0; l < i; ++l) s_ -= Fk[NU + l * NU - l * (l + 1) / 2 + (i - l - 1)] * x[l];
+                        x[i] = s_;
+                    }
+#pragma unroll
+                    for (int i = NU - 1; i >= 0; --i) {
+                        double s_ = x[i] * Fk[i];
+#pragma unroll
+                        for (int l = i + 1; l < NU; ++l) s_ -= Fk[NU + i * NU - i * (i + 1) / 2 + (l - i - 1)] * x[l];
+                        x[i] = s_;
+                    }
+#pragma unroll
+                    for (int i = 0; i < NU; ++i) ffd[i * KP + kk] = -x[i];
+                }
+            }
+            L.sync();
+            // =========== forward roll-out ===========
+            // x~_k = [dx_k; 1] sits in column 0 of the B operand (lanes 0..3); u_k = K~_k x~_k and x~_{k+1} = T_k [u_k; x~_k]
+            // come out in column 0 of the accumulators (lanes 4 g); four shuffles put them back into operand position.
+            // 11 DMMA per stage.  Predictor: the feed-forward is the affine column of K~.  Corrector: the CHANGE of the step
+            // (affine entry 0, feed-forward from `ffd`), accumulated onto the predictor's step.
+            {
+                struct RollOps { double tA[2], tB[2], tC[2], tU[2], kA, kB, kC; };
+                auto ld_ops = [&](int kk) {
+                    RollOps o;
+                    const double* a_ = ABt + (size_t)kk * S::ABT + g_;
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        const bool in = mt == 0 || g_ < 4;        // output slots 12..15 do not exist
+                        o.tA[mt] = in ? __ldcg(a_ + (2 * q_) * 12 + 8 * mt) : 0.0;
+                        o.tB[mt] = in ? __ldcg(a_ + (2 * q_ + 1) * 12 + 8 * mt) : 0.0;
+                        o.tC[mt] = in ? __ldcg(a_ + (8 + 2 * q_) * 12 + 8 * mt) : 0.0;
+                        o.tU[mt] = in ? __ldcg(a_ + (9 + 2 * q_) * 12 + 8 * mt) : 0.0;
+                    }
+                    // K~[u = g][slot]: slot s sits at position s (s < 8) or 8 + 2 (s - 8), fragment entry [tile][4 (pos % 8) + u]
+                    const double* k_ = Kf + (size_t)kk * S::KF + g_;
+                    const bool ku = g_ < NU;
+                    o.kA = ku ? __ldcg(k_ + 4 * (2 * q_)) : 0.0;
+                    o.kB = ku ? __ldcg(k_ + 4 * (2 * q_ + 1)) : 0.0;
+                    o.kC = ku ? __ldcg(k_ + 32 + 4 * (2 * q_)) : 0.0;
+                    return o;
+                };
+                const bool delta = pass == 1;
+                double bA = 0.0, bB = 0.0, bC = (q_ == 2 && !delta) ? 1.0 : 0.0;       // x~_0 = [0; 1] (dx_0 is part of w already)
+                if (lane < NX) dW[(NU + lane) * KP] = 0.0;
+                L.sync();
+                auto stage = [&](int kk, const RollOps& o) {
+                    L.sync();
+                    QM_CONVERGED()
+                    // affine column of T (position 12: step C, q = 2) carries phi rd; its own entry (slot 10) stays 1
+                    const double tC0 = q_ == 2 ? o.tC[0] * phi : o.tC[0];
+                    const double tC1 = (q_ == 2 && g_ != 2) ? o.tC[1] * phi : o.tC[1];
+                    Acc2 U, Xn[2];
+                    U.x = (delta && q_ == 0 && g_ < NU) ? ffd[g_ * KP + kk] : 0.0;
+                    U.y = 0.0;
+                    Xn[0].x = 0.0; Xn[0].y = 0.0; Xn[1].x = 0.0; Xn[1].y = 0.0;
+                    dmma(U, o.kA, bA); dmma(Xn[0], o.tA[0], bA); dmma(Xn[1], o.tA[1], bA);
+                    dmma(U, o.kB, bB); dmma(Xn[0], o.tB[0], bB); dmma(Xn[1], o.tB[1], bB);
+                    dmma(U, o.kC, bC); dmma(Xn[0], tC0, bC); dmma(Xn[1], tC1, bC);
+                    const double bU = __shfl_sync(FULL, U.x, 4 * q_);
+                    dmma(Xn[0], o.tU[0], bU); dmma(Xn[1], o.tU[1], bU);
+                    if (q_ == 0) {
+                        if (delta) {
+                            if (g_ < NU) dW[g_ * KP + kk] += U.x;
+                            dW[(NU + g_) * KP + kk + 1] += Xn[0].x;
+                            if (g_ < 2) dW[(NU + 8 + g_) * KP + kk + 1] += Xn[1].x;
+                        } else {
+                            if (g_ < NU) dW[g_ * KP + kk] = U.x;
+                            dW[(NU + g_) * KP + kk + 1] = Xn[0].x;
+                            if (g_ < 2) dW[(NU + 8 + g_) * KP + kk + 1] = Xn[1].x;
+                        }
+                    }
+                    bA = __shfl_sync(FULL, Xn[0].x, 8 * q_);
+                    bB = __shfl_sync(FULL, Xn[0].x, 8 * q_ + 4);
+                    bC = __shfl_sync(FULL, Xn[1].x, 4 * q_);
+                };
+                pipelined_stages<4, RollOps>(N, ld_ops, stage);
+            }
+            L.sync();
+            // =========== row steps (lane = node) ===========
+            double rmax = 0.0;              // largest -dx/x over the lane's rows
+            QM_NODE_LOOP(kk) {
+                QM_LOAD_STATE(kk);
+#pragma unroll
+                for (int a = 0; a < 2 * NU; ++a) { dtb[a] = 0.0; dlb[a] = 0.0; }
+#pragma unroll
+                for (int a = 0; a < 2 * NH; ++a) { dts[a] = 0.0; dls[a] = 0.0; dss[a] = 0.0; dms[a] = 0.0; }
+                if (kk < N) {
+#pragma unroll
+                    for (int j = 0; j < NU; ++j) {
+                        const double wu = Wsm[j * KP + kk], dwu = dW[j * KP + kk];
+#pragma unroll
+                        for (int side = 0; side < 2; ++side) {
+                            const int a = side * NU + j;
+                            const double sgn = side == 0 ? 1.0 : -1.0;
+                            const double cr = pass == 0 ? 0.0 : tau - prod[a * KP + kk];
+                            const HardEval ev = hard_eval(tb[a], lb[a], sgn * wu, hard_d(kk, a), cr);
+                            const double kap = cr - lb[a] * tb[a];
+                            dtb[a] = sgn * dwu - ev.r_p;
+                            dlb[a] = (kap - lb[a] * dtb[a]) * ev.rt;
+                            rmax = fmax(rmax, fmax(boundary_ratio(dtb[a], ev.rt), boundary_ratio(dlb[a], ev.rl)));
+                        }
+                    }
+                }
+                if (kk >= k0) {
+#pragma unroll
+                    for (int r = 0; r < NH; ++r) {
+                        const double c0 = c_pos(kk, r, 0), c1 = c_pos(kk, r, 1), c2 = c_pos(kk, r, 2);
+                        const double cw = c0 * Wsm[(HC0 + 0) * KP + kk] + c1 * Wsm[(HC0 + 1) * KP + kk] + c2 * Wsm[(HC0 + 2) * KP + kk];
+                        const double cd = c0 * dW[(HC0 + 0) * KP + kk] + c1 * dW[(HC0 + 1) * KP + kk] + c2 * dW[(HC0 + 2) * KP + kk];
+                        const double z = P.zs[r] * scale(kk), Z = P.Zs[r] * scale(kk);
+#pragma unroll
+                        for (int side = 0; side < 2; ++side) {
+                            const int a = side * NH + r;
+                            const double sgn = side == 0 ? 1.0 : -1.0;
+                            const double ct = pass == 0 ? 0.0 : tau - prod[(2 * NU + a) * KP + kk];
+                            const double cs = pass == 0 ? 0.0 : tau - prod[(2 * NU + 2 * NH + a) * KP + kk];
+                            const SoftEval ev = soft_eval(ts[a], ls[a], ss[a], ms[a], sgn * cw, soft_d(kk, a), z, Z, ct, cs);
+                            const double kap = ct - ls[a] * ts[a], nu = cs - ms[a] * ss[a];
+                            const double gd = sgn * cd;
+                            dss[a] = (ev.rho - ev.Th * gd) * ev.rD;
+                            dts[a] = gd + dss[a] - ev.r_p;
+                            dls[a] = (kap - ls[a] * dts[a]) * ev.rt;
+                            dms[a] = (nu - ms[a] * dss[a]) * ev.rs;
+                            rmax = fmax(rmax, fmax(fmax(boundary_ratio(dts[a], ev.rt), boundary_ratio(dls[a], ev.rl)),
+                                                   fmax(boundary_ratio(dss[a], ev.rs), boundary_ratio(dms[a], ev.rm))));
+                        }
+                    }
+                }
+                QM_STORE_DELTA(kk);
+            }
+            rmax = L.max(rmax);
+            const double amax = rmax > 1e-30 ? 1.0 / rmax : 1e30;
+            if (pass == 0) {
+                // affine step length -> centring parameter; second-order products for the corrector
+                const double aa = fmin(1.0, amax);
+                const double so = safe ? 0.0 : 1.0;
+                double csum_aff = 0.0;
+                QM_NODE_LOOP(kk) {
+                    QM_LOAD_STATE(kk);
+                    QM_LOAD_DELTA(kk);
+                    if (kk < N) {
+#pragma unroll
+                        for (int a = 0; a < 2 * NU; ++a) {
+                            csum_aff += (lb[a] + aa * dlb[a]) * (tb[a] + aa * dtb[a]);
+                            prod[a * KP + kk] = so * dlb[a] * dtb[a];
+                        }
+                    }
+                    if (kk >= k0) {
+#pragma unroll
+                        for (int a = 0; a < 2 * NH; ++a) {
+                            csum_aff += (ls[a] + aa * dls[a]) * (ts[a] + aa * dts[a]) + (ms[a] + aa * dms[a]) * (ss[a] + aa * dss[a]);
+                            prod[(2 * NU + a) * KP + kk] = so * dls[a] * dts[a];
+                            prod[(2 * NU + 2 * NH + a) * KP + kk] = so * dms[a] * dss[a];
+                        }
+                    }
+                }
+                const double mu_aff = L.sum(csum_aff) / ncomp;
+                double sig = mu_aff / fmax(mubar, 1e-300);
+                sig = fmin(fmax(sig * sig * sig, safe ? 0.2 : 0.0), 1.0);
+                tau = fmax(sig * mubar, 0.1 * P.tol);
+                L.sync();
+            } else {
+                // =========== damped step ===========
+                const double al = fmin(1.0, 0.995 * amax);
+                QM_NODE_LOOP(kk) {
+                    QM_LOAD_STATE(kk);
+                    QM_LOAD_DELTA(kk);
+#pragma unroll
+                    for (int a = 0; a < 2 * NU; ++a) { tb[a] += al * dtb[a]; lb[a] += al * dlb[a]; }
+#pragma unroll
+                    for (int a = 0; a < 2 * NH; ++a) { ts[a] += al * dts[a]; ls[a] += al * dls[a]; ss[a] += al * dss[a]; ms[a] += al * dms[a]; }
+                    QM_STORE_STATE(kk);
+                }
+                QM_LANES(e, NW * KP) Wsm[e] += al * dW[e];
+                phi *= (1.0 - al);
+                L.sync();
+            }
+        }
+        if (stop || status == 4) break;
+    }
+
+    // =====================================================================================================
+    // verification of the KKT residuals the iteration only tracked (costates by one backward sweep); once per solve, plain
+    // loads of the operands by position
+    // =====================================================================================================
+    double res_true = 0.0;
+    {
+        QM_NODE_LOOP(kk) {
+            QM_LOAD_STATE(kk);
+            for (int j = 0; j < NU; ++j) corr[j * KP + kk] = kk < N ? lb[j] - lb[NU + j] : 0.0;
+            for (int r = 0; r < NH; ++r) corr[(NU + r) * KP + kk] = kk >= k0 ? ls[r] - ls[NH + r] : 0.0;
+        }
+        L.sync();
+        for (int kk = N; kk >= 0 && status != 4; --kk) {
+            const double* pin = pp + ((N - kk) & 1) * 16;        // costate of node kk + 1
+            double* pout = pp + (((N - kk) & 1) ^ 1) * 16;       // costate of node kk
+            const double* hk = Hp + (size_t)kk * S::HP;
+            if (lane < NW && !(kk == N && lane < NU)) {
+                const int i = lane, pi = S::wpos(i);
+                double s = __ldcg(gpos + kk * S::GP + pi);
+#pragma unroll
+                for (int j = 0; j < NW; ++j) s += __ldcg(hk + pi * 16 + S::wpos(j)) * Wsm[j * KP + kk];
+                if (i < NU) s -= corr[i * KP + kk];
+                if (i >= HC0 && i < HC0 + 3)
+                    for (int r = 0; r < NH; ++r) s -= corr[(NU + r) * KP + kk] * c_pos(kk, r, i - HC0);
+                if (kk < N) {
+                    const double* tk = ABt + (size_t)kk * S::ABT + pi * 12;
+#pragma unroll
+                    for (int l = 0; l < NX; ++l) s += __ldcg(tk + l) * pin[l];
+                }
+                if (i < NU) res_true = fmax(res_true, fabs(s));      // input stationarity
+                else pout[i - NU] = s;                               // defines the costate of node kk (x-stationarity == 0)
+            }
+            if (kk < N && lane >= 16 && lane < 16 + NX) {
+                const int i = lane - 16;
+                double s = P.bdyn[kk * NX + i] - Wsm[(NU + i) * KP + kk + 1];
+                const double* tk = ABt + (size_t)kk * S::ABT + i;
+#pragma unroll
+                for (int j = 0; j < NW; ++j) s += __ldcg(tk + S::wpos(j) * 12) * Wsm[j * KP + kk];
+                res_true = fmax(res_true, fabs(s));
+            }
+            L.sync();
+        }
+        res_true = L.max(res_true);
+        if (status == 0 && !(res_true <= 100.0 * P.tol_res)) status = 3;    // tracked residual was wrong: report, do not hide
+    }
+
+    double step_inf = 0.0;
+    QM_LANES(e, (N + 1) * NW) { const int kk = e / NW, i = e - kk * NW; step_inf = fmax(step_inf, fabs(Wsm[i * KP + kk])); }
+    step_inf = L.max(step_inf);
+    // ---- full SQP step and outputs ----
+    if (status != 4) {
+        QM_LANES(e, (N + 1) * NX) { const int kk = e / NX, i = e - kk * NX; P.xbar[e] += Wsm[(NU + i) * KP + kk]; }
+        QM_LANES(e, N * NU) { const int kk = e / NU, j = e - kk * NU; P.ubar[e] += Wsm[j * KP + kk]; }
+    }
+    L.sync();
+    QM_LANES(j, NU) P.u0[j] = P.ubar[j];
+    QM_NODE_LOOP(kk) {
+        QM_LOAD_STATE(kk);
+        if (P.lam_hard && kk < N)
+            for (int a = 0; a < 2 * NU; ++a) P.lam_hard[kk * 2 * NU + a] = lb[a];
+        if (P.lam_soft)
+            for (int a = 0; a < 2 * NH; ++a) P.lam_soft[kk * 2 * NH + a] = kk >= k0 ? ls[a] : 0.0;
+    }
+    if (lane == 0) {
+        *P.status = status;
+        *P.iters = it;
+        if (P.res_out && status != 4) { P.res_out[0] = res_true; P.res_out[1] = step_inf; }
+    }
+}
+
+#undef QM_LD
+#undef QM_ST
+#undef QM_LOAD
+#undef QM_STORE
+#undef QM_LOAD_STATE
+#undef QM_STORE_STATE
+#undef QM_LOAD_DELTA
+#undef QM_STORE_DELTA
+#undef QM_NODE_LOOP
+#undef QM_LANES
+#undef QM_CONVERGED
+
+}  // namespace sdfnmpc
+#endif  // __CUDACC__

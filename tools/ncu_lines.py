@@ -26,7 +26,7 @@ for l in sass:
     m = re.match(r'\s*/\*([0-9a-f]{4,})\*/\s+(.*?);', l)
     if m:
         amap[int(m.group(1), 16)] = (cur, m.group(2))
-src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '-k', 'regex:' + kern], capture_output=True, text=True).stdout
+src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '-k', 'regex:' + re.split(r'I[A-Z]', kern)[0]], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.split('\n')))
 rows = [r for r in rows if len(r) > 5]
 hdr = rows[0]; idx = {h: i for i, h in enumerate(hdr)}
