@@ -43,12 +43,12 @@ struct QpMmaShape {
     // doubles of global scratch per warp slot
     SDF_HD static size_t work_doubles(int N) {
         const size_t n1 = (size_t)N + 1;
-        return n1 * HP + (size_t)N * ABT + (size_t)N * KF + (size_t)N * LF + n1 * GP + ((n1 * NH * 3 + 1) & ~(size_t)1) +
-               2 * (size_t)NROW * kp(N);
+        return n1 * HP + (size_t)N * ABT + (size_t)N * LF + n1 * GP + ((n1 * NH * 3 + 1) & ~(size_t)1) + 2 * (size_t)NROW * kp(N);
     }
     // doubles of shared memory per warp: iterate, step, elimination terms (+ a zero row), second-order products, corrector
-    // feed-forward, costate ping-pong of the verification
-    SDF_HD static int smem_doubles(int N) { return (2 * NW + NCORR + 1 + NPROD + NU) * kp(N) + 2 * 16; }
+    // feed-forward, costate ping-pong of the verification, and the gains K~_k of every stage (written by the factorising sweep,
+    // read by three more sweeps per iteration: 10 KB that would otherwise cycle through L2)
+    SDF_HD static int smem_doubles(int N) { return (2 * NW + NCORR + 1 + NPROD + NU) * kp(N) + 2 * 16 + N * KF; }
 };
 
 // Lane-strided loops in this file run a WARP-UNIFORM number of trips with the tail predicated (`QM_LANES(e, n)`): a loop whose
@@ -113,7 +113,6 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
     const size_t n1 = (size_t)N + 1;
     double* Hp = take(n1 * S::HP);
     double* ABt = take((size_t)N * S::ABT);
-    double* Kf = take((size_t)N * S::KF);
     double* Lf = take((size_t)N * S::LF);
     double* gpos = take(n1 * S::GP);
     double* cpos = take((n1 * NH * 3 + 1) & ~(size_t)1);
@@ -127,6 +126,7 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
     double* prod = corr + (NCORR + 1) * KP;       // [NPROD][KP] affine second-order products
     double* ffd = prod + NPROD * KP;              // [NU][KP]   input residual / feed-forward of the corrector's sweep
     double* pp = ffd + NU * KP;                   // [2][16]    costate ping-pong of the verification
+    double* Kf = pp + 2 * 16;                     // [N][2][32] gains as fragments
 
     auto scale = [&](int k) { return k < N ? P.dt[k] : 1.0; };
     auto wrow = [&](int k, int r) { return k < N ? P.W[k * NY + r] : (r < P.nyN ? P.WN[r] : 0.0); };
@@ -134,6 +134,21 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
     // position -> index into w = [u; x] (14 = affine, 15 = pad)
     auto widx = [](int pos) { return pos < 8 ? NU + pos : ((pos & 1) ? (pos - 9) >> 1 : (pos == 8 ? NU + 8 : (pos == 10 ? NU + 9 : (pos == 12 ? 14 : 15)))); };
 
+#if defined(SDFNMPC_QP_TRACE)
+    // development: cycles per phase of IPM iteration 2 ([pass][8]: elimination, backward sweep, roll-out, row steps) and of
+    // the once-per-solve parts ([16..]: prologue operands, Hessian build, initial point, verification + outputs)
+    long long qpt_last = clock64();
+#define QPT(slot, cond)                                                        \
+    {                                                                          \
+        if (P.trace && lane == 0) {                                            \
+            const long long now_ = clock64();                                  \
+            if (cond) P.trace[slot] += now_ - qpt_last;                        \
+            qpt_last = now_;                                                   \
+        }                                                                      \
+    }
+#else
+#define QPT(slot, cond)
+#endif
     // =====================================================================================================
     // prologue: SDF row of C / h, operands of the sweeps
     // =====================================================================================================
@@ -161,6 +176,7 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
     }
     QM_LANES(k, N) __stcg(ABt + (size_t)k * S::ABT + 12 * 12 + 10, 1.0);   // affine row: [0 .. 0 1]
     QM_LANES(i, NX) Wsm[(NU + i) * KP] = P.x0[i] - P.xbar[i];       // dx_0 (0 when node 0 was linearised at x0)
+    QPT(16, true)
     // H~_k = J~' (W dt) J~ + lm dt I with J~ = [J | y - yref]: 12 DMMA per node straight from the linearisation's J; the affine
     // column comes out as the cost gradient.
     // mma.sync.aligned needs the WHOLE warp at the instruction: see QM_LANES above for why every loop before this point has a
@@ -237,6 +253,7 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
     }
     L.sync();
 
+    QPT(17, true)
     // =====================================================================================================
     // per-lane node state (lane k <-> node k), parked in L2 between the row phases ([item][node]: coalesced)
     // =====================================================================================================
@@ -405,6 +422,7 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
         }
     };
 
+    QPT(18, true)
     int status = 2, it = 0;
     bool safe = false;              // conservative mode after a stall: more centring, no second-order term
     double cm_prev1 = 1e300, cm_prev2 = 1e300;
@@ -503,6 +521,7 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
                 cm_prev2 = cm_prev1; cm_prev1 = cmax;
             }
             L.sync();
+            QPT(pass * 8 + 0, it == 2)
             if (pass == 0) {
                 // =========== factorising backward sweep ===========
                 struct FacOps { Acc2 h[2][2]; TOps t; };
@@ -571,15 +590,29 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
                     ok = ok && (m00 > 0.0) && (d1 > 0.0) && (d2 > 0.0) && (d3 > 0.0);
                     double kq[2];
                     const double mxu[2] = {M[0][1].y, M[1][1].y};        // M~[8 ri + g][u_q]
-#pragma unroll
-                    for (int ri = 0; ri < 2; ++ri) {
+                    {
+                        // the two rows of the lane's quads are solved side by side (two independent dependency chains); the lane
+                        // keeps component q of each, picked with selects on two predicates (no branches)
                         const int qb = lane & ~3;
-                        const double v0 = __shfl_sync(FULL, mxu[ri], qb), v1 = __shfl_sync(FULL, mxu[ri], qb + 1),
-                                     v2 = __shfl_sync(FULL, mxu[ri], qb + 2), v3 = __shfl_sync(FULL, mxu[ri], qb + 3);
-                        const double y1 = v1 - l10 * v0, y2 = v2 - l20 * v0 - l21 * y1, y3 = v3 - l30 * v0 - l31 * y1 - l32 * y2;
-                        const double z3 = y3 * r3, z2 = y2 * r2 - l32 * z3, z1 = y1 * r1 - l21 * z2 - l31 * z3,
-                                     z0 = v0 * r0 - l10 * z1 - l20 * z2 - l30 * z3;
-                        kq[ri] = -(q_ == 0 ? z0 : (q_ == 1 ? z1 : (q_ == 2 ? z2 : z3)));
+                        double v0[2], v1[2], v2[2], v3[2], z0[2], z1[2], z2[2], z3[2];
+#pragma unroll
+                        for (int ri = 0; ri < 2; ++ri) {
+                            v0[ri] = __shfl_sync(FULL, mxu[ri], qb); v1[ri] = __shfl_sync(FULL, mxu[ri], qb + 1);
+                            v2[ri] = __shfl_sync(FULL, mxu[ri], qb + 2); v3[ri] = __shfl_sync(FULL, mxu[ri], qb + 3);
+                        }
+#pragma unroll
+                        for (int ri = 0; ri < 2; ++ri) {
+                            const double y1 = v1[ri] - l10 * v0[ri], y2 = v2[ri] - l20 * v0[ri] - l21 * y1,
+                                         y3 = v3[ri] - l30 * v0[ri] - l31 * y1 - l32 * y2;
+                            z3[ri] = y3 * r3; z2[ri] = y2 * r2 - l32 * z3[ri]; z1[ri] = y1 * r1 - l21 * z2[ri] - l31 * z3[ri];
+                            z0[ri] = v0[ri] * r0 - l10 * z1[ri] - l20 * z2[ri] - l30 * z3[ri];
+                        }
+                        const bool qlo = (q_ & 1) == 0, qhi = q_ < 2;
+#pragma unroll
+                        for (int ri = 0; ri < 2; ++ri) {
+                            const double a_ = qlo ? z0[ri] : z1[ri], b_ = qlo ? z2[ri] : z3[ri];
+                            kq[ri] = -(qhi ? a_ : b_);
+                        }
                     }
                     // P~ <- M~ + M.u K~
 #pragma unroll
@@ -590,8 +623,8 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
                             dmma(Pf[ri][rj], mxu[ri], kq[rj]);
                         }
                     // for the roll-outs and the corrector: gains (with the feed-forward in the affine position) and the factor
-                    __stcg(Kf + (size_t)kk * S::KF + lane, kq[0]);
-                    __stcg(Kf + (size_t)kk * S::KF + 32 + lane, kq[1]);
+                    Kf[kk * S::KF + lane] = kq[0];
+                    Kf[kk * S::KF + 32 + lane] = kq[1];
                     if (lane == 0) {
                         double2* lo = reinterpret_cast<double2*>(Lf + (size_t)kk * S::LF);
                         __stcg(lo + 0, make_double2(r0, r1)); __stcg(lo + 1, make_double2(r2, r3));
@@ -612,8 +645,8 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
                     BackOps o;
                     const int kk = N - 1 - i_;
                     o.t = ld_t(kk);
-                    o.kf[0] = __ldcg(Kf + (size_t)kk * S::KF + lane);
-                    o.kf[1] = __ldcg(Kf + (size_t)kk * S::KF + 32 + lane);
+                    o.kf[0] = Kf[kk * S::KF + lane];
+                    o.kf[1] = Kf[kk * S::KF + 32 + lane];
                     return o;
                 };
                 double bA = 2 * q_ < 3 ? corr[(2 * NU + 6 + 2 * q_) * KP + N] : 0.0;
@@ -667,6 +700,7 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
                 }
             }
             L.sync();
+            QPT(pass * 8 + 1, it == 2)
             // =========== forward roll-out ===========
             // x~_k = [dx_k; 1] sits in column 0 of the B operand (lanes 0..3); u_k = K~_k x~_k and x~_{k+1} = T_k [u_k; x~_k]
             // come out in column 0 of the accumulators (lanes 4 g); four shuffles put them back into operand position.
@@ -686,11 +720,11 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
                         o.tU[mt] = in ? __ldcg(a_ + (9 + 2 * q_) * 12 + 8 * mt) : 0.0;
                     }
                     // K~[u = g][slot]: slot s sits at position s (s < 8) or 8 + 2 (s - 8), fragment entry [tile][4 (pos % 8) + u]
-                    const double* k_ = Kf + (size_t)kk * S::KF + g_;
+                    const double* k_ = Kf + kk * S::KF + g_;
                     const bool ku = g_ < NU;
-                    o.kA = ku ? __ldcg(k_ + 4 * (2 * q_)) : 0.0;
-                    o.kB = ku ? __ldcg(k_ + 4 * (2 * q_ + 1)) : 0.0;
-                    o.kC = ku ? __ldcg(k_ + 32 + 4 * (2 * q_)) : 0.0;
+                    o.kA = ku ? k_[4 * (2 * q_)] : 0.0;
+                    o.kB = ku ? k_[4 * (2 * q_ + 1)] : 0.0;
+                    o.kC = ku ? k_[32 + 4 * (2 * q_)] : 0.0;
                     return o;
                 };
                 const bool delta = pass == 1;
@@ -730,6 +764,7 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
                 pipelined_stages<4, RollOps>(N, ld_ops, stage);
             }
             L.sync();
+            QPT(pass * 8 + 2, it == 2)
             // =========== row steps (lane = node) ===========
             double rmax = 0.0;              // largest -dx/x over the lane's rows
             QM_NODE_LOOP(kk) {
@@ -813,6 +848,7 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
                 sig = fmin(fmax(sig * sig * sig, safe ? 0.2 : 0.0), 1.0);
                 tau = fmax(sig * mubar, 0.1 * P.tol);
                 L.sync();
+                QPT(3, it == 2)
             } else {
                 // =========== damped step ===========
                 const double al = fmin(1.0, 0.995 * amax);
@@ -828,6 +864,7 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
                 QM_LANES(e, NW * KP) Wsm[e] += al * dW[e];
                 phi *= (1.0 - al);
                 L.sync();
+                QPT(11, it == 2)
             }
         }
         if (stop || status == 4) break;
@@ -896,6 +933,7 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
         if (P.lam_soft)
             for (int a = 0; a < 2 * NH; ++a) P.lam_soft[kk * 2 * NH + a] = kk >= k0 ? ls[a] : 0.0;
     }
+    QPT(19, true)
     if (lane == 0) {
         *P.status = status;
         *P.iters = it;
@@ -911,6 +949,7 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
 #undef QM_STORE_STATE
 #undef QM_LOAD_DELTA
 #undef QM_STORE_DELTA
+#undef QPT
 #undef QM_NODE_LOOP
 #undef QM_LANES
 #undef QM_CONVERGED

@@ -4,7 +4,8 @@ import collections, csv, os, re, subprocess, sys, tempfile
 rep, kern, stem = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 30
 binary = sys.argv[5] if len(sys.argv) > 5 else None      # object / library the report was taken with (default: in-tree build)
-ranges = sys.argv[6] if len(sys.argv) > 6 else None      # 'name:lo-hi,name:lo-hi' line ranges of qp_core.cuh to aggregate
+ranges = sys.argv[6] if len(sys.argv) > 6 else None      # 'name:lo-hi,name:lo-hi' line ranges of the phase file to aggregate
+phase_file = sys.argv[7] if len(sys.argv) > 7 else 'qp_core.cuh'
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tmp = tempfile.mkdtemp()
 subprocess.run(['cuobjdump', '-xelf', 'all', binary or os.path.join(root, 'sdf_nmpc_b200/lib/libsdfnmpc_b200.so')], cwd=tmp, capture_output=True)
@@ -65,8 +66,8 @@ if ranges:
     for key in samp:
         f, n = key
         name = 'other:' + f
-        if f == 'qp_core.cuh':
-            name = 'qp_core:unassigned'
+        if f == phase_file:
+            name = phase_file + ':unassigned'
             for nm, lo, hi in spec:
                 if lo <= n <= hi:
                     name = nm
