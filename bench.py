@@ -14,7 +14,9 @@ The JSON line carries, besides the base contract:
   e2e        same metric through the public API with HOST buffers (pinned H2D of x0 and D2H of u0/status per step)
   roofline   dominant kernel of the step, timed live with CUDA events on the launching stream
   kernels    per-kernel share of the step and the SDF kernel's own roofline numbers
-  cpu_baseline  the float64 oracle (CPU restatement of the reference's acados+L4CasADi path) on the host cores
+  latency    p50 / p99 wall microseconds of solve() with host buffers for 1, 8, 64 instances (metric iii, configs[0])
+  cpu_baseline  the CPU restatement of the reference's acados+L4CasADi path on the host cores: C++ linearisation + IPM
+             (oracle/_ref/libhost_emul.so) and libtorch batch-1 SDF forward / jacrev per node, one process per core
 `--impl reference` times that CPU restatement as the reference arm (the original acados / L4CasADi binaries
 cannot be installed offline - see DESIGN.md).
 """
@@ -143,10 +145,15 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------
 # CPU side: the oracle (only the cpu_baseline leg and --impl reference may touch it)
 # ----------------------------------------------------------------------------------------------------
-def _oracle_worker(args):
-    first, count, steps = args
-    os.environ.setdefault('OMP_NUM_THREADS', '1')
+_W = {}          # per-process state of a CPU worker
+
+
+def _cpu_worker_init(first, count, engine):
+    """Build one block of the seeded workload inside a worker process (closed loop, warm start kept between steps)."""
+    for k in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+        os.environ[k] = '1'
     from oracle import rti
+    from oracle import models as MODELS
     from sdf_nmpc_b200 import synth
     net = synth.make_sdf_net(seed=0, **synth.ARCH_B, calibrated=True)
     cfg = rti.default_cfg()
@@ -154,64 +161,106 @@ def _oracle_worker(args):
     prob = dict(x0=w['x0'], yref=w['yref'], W=w['W'], yrefN=w['yrefN'], WN=w['WN'], qd=w['qd'], flag=np.ones(count), latent=w['latent'])
     prob['W_p_Co'] = np.einsum('bij,j->bi', w['W_R_Bo'], cfg['B_p_C']) + w['W_p_Bo']
     prob['W_R_Co'] = w['W_R_Bo'] @ cfg['B_R_C']
-    from oracle import model_att as M
-    x = prob['x0'].copy()
-    xb, ub = rti.init_traj(x, cfg)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        p = dict(prob)
-        p['x0'] = x
-        xb, ub, out = rti.rti_step(net, xb, ub, p, cfg)
-        x = M.rk4(x, out['u0'], cfg['dt'][0], cfg)
-    return time.perf_counter() - t0, count * steps
+    _W.update(net=net, cfg=cfg, prob=prob, x=prob['x0'].copy(), mdl=MODELS.get('att'), engine=engine, count=count)
+    if engine == 'cxx':
+        from oracle import cxx_port
+        _W['rti'] = cxx_port.CxxRti(net, cfg, prob, sdf='torch')
+    else:
+        _W['xb'], _W['ub'] = rti.init_traj(_W['x'], cfg)
+    return True
 
 
-def cpu_oracle_throughput(per_worker=8, steps=2, workers=None):
-    """solves/s of the CPU restatement on `workers` processes (each: `per_worker` instances x `steps` RTI steps)."""
-    import multiprocessing as mp
-    workers = min(workers or max(1, (os.cpu_count() or 1)), 128)
-    ctx = mp.get_context('spawn')
-    saved = {k: os.environ.get(k) for k in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS')}
-    for k in saved:
-        os.environ[k] = '1'          # one BLAS thread per worker process: the pool already uses every core
+def _cpu_worker_step(_):
+    """One closed-loop SQP-RTI step of the worker's block; returns (busy seconds, solves, failures)."""
     t0 = time.perf_counter()
+    cfg = _W['cfg']
+    if _W['engine'] == 'cxx':
+        u0, st, _its = _W['rti'].step(_W['x'])
+        bad = int((st != 0).sum())
+    else:
+        from oracle import rti
+        p = dict(_W['prob'])
+        p['x0'] = _W['x']
+        _W['xb'], _W['ub'], out = rti.rti_step(_W['net'], _W['xb'], _W['ub'], p, cfg)
+        u0, bad = out['u0'], int((out['status'] != 0).sum())
+    _W['x'] = _W['mdl'].rk4(_W['x'], u0.copy(), cfg['dt'][0], cfg)
+    return time.perf_counter() - t0, _W['count'], bad
+
+
+class CpuArm:
+    """The CPU restatement of the reference's path on `workers` processes, each stepping `per_worker` instances of the same
+    seeded workload in closed loop.  engine 'cxx': C++ linearisation + structure-exploiting IPM (oracle/_ref/libhost_emul.so)
+    + libtorch batch-1 SDF forward / traced jacrev per node (what L4CasADi executes); engine 'numpy': oracle/rti.py."""
+
+    def __init__(self, per_worker, workers=None, engine='cxx'):
+        import multiprocessing as mp
+        self.workers = min(workers or max(1, (os.cpu_count() or 1)), 128)
+        self.per_worker, self.engine = per_worker, engine
+        self.ctx = mp.get_context('spawn')
+        # one single-worker pool per block so that every block keeps its own process (state lives in the process)
+        self.pools = [self.ctx.Pool(1) for _ in range(self.workers)]
+        res = [p.apply_async(_cpu_worker_init, (i * per_worker, per_worker, engine)) for i, p in enumerate(self.pools)]
+        for r in res:
+            r.get()
+
+    def step(self):
+        """All blocks advance one control step; returns (wall seconds, solves, failures)."""
+        t0 = time.perf_counter()
+        res = [p.apply_async(_cpu_worker_step, (0,)) for p in self.pools]
+        out = [r.get() for r in res]
+        return time.perf_counter() - t0, sum(o[1] for o in out), sum(o[2] for o in out)
+
+    def close(self):
+        for p in self.pools:
+            p.terminate()
+
+
+def cpu_port_throughput(per_worker, steps, engine='cxx', workers=None, warmup=1):
+    arm = CpuArm(per_worker, workers, engine)
     try:
-        with ctx.Pool(workers) as pool:
-            res = pool.map(_oracle_worker, [(i * per_worker, per_worker, steps) for i in range(workers)])
+        for _ in range(warmup):
+            arm.step()
+        wall, solves, bad = 0.0, 0, 0
+        for _ in range(steps):
+            w, n, b = arm.step()
+            wall, solves, bad = wall + w, solves + n, bad + b
     finally:
-        for k, v in saved.items():
-            if v is None:
-                os.environ.pop(k, None)
-            else:
-                os.environ[k] = v
-    wall = time.perf_counter() - t0
-    solves = sum(r[1] for r in res)
-    busy = max(r[0] for r in res)           # excludes interpreter start-up / imports
-    return solves / busy, dict(workers=workers, solves=solves, busy_s=busy, wall_s=wall)
+        arm.close()
+    return solves / wall, dict(workers=arm.workers, solves=solves, wall_s=wall, failures=bad, engine=engine, per_worker=per_worker, steps=steps)
+
+
+CPU_KIND_NOTE = ('CPU restatement of the reference path (acados 0.3.1 + L4CasADi 1.4.1 cannot be installed offline): C++ dynamics / '
+                 'sensitivities / linearisation + structure-exploiting interior-point QP (oracle/_ref/libhost_emul.so) and the '
+                 'SDF through libtorch on the CPU exactly as L4CasADi calls it (1 thread, batch 1, TorchScript forward + traced '
+                 'jacrev per shooting node); one process per core')
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_worker = 8
-    vals = []
-    for _ in range(args.warmup if args.warmup < 1 else 1):
-        cpu_oracle_throughput(per_worker, 1, cores)
-    t0 = time.perf_counter()
-    for _ in range(max(1, min(args.steps, 3))):
-        v, info = cpu_oracle_throughput(per_worker, 2, cores)
-        vals.append(v)
-    v = float(np.mean(vals))
-    sample = f'{cores} processes x {per_worker} instances x 2 closed-loop RTI steps of the same seeded workload per bench step'
-    line = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=len(vals), warmup=1, ms_per_step=1e3 * (time.perf_counter() - t0) / len(vals),
-                higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64', data='synthetic', impl='reference',
-                config=dict(workload='4096 independent quadrotor SDF-NMPC instances per GPU, closed-loop SQP-RTI (configs[2]); CPU arm runs a bounded sample',
-                            N=20, nx=10, nu=4, sdf_arch='dod F5 [256,256,128,64]'),
-                cpu_baseline=dict(value=v, unit=UNIT, cores=cores, kind='port', sample=sample),
+    per_worker = 16
+    K, W_ = max(1, args.steps), max(0, args.warmup)
+    arm = CpuArm(per_worker, cores, 'cxx')
+    try:
+        for _ in range(W_):
+            arm.step()
+        wall, solves, bad = 0.0, 0, 0
+        for _ in range(K):
+            w, n, b = arm.step()
+            wall, solves, bad = wall + w, solves + n, bad + b
+    finally:
+        arm.close()
+    v = solves / wall
+    sample = (f'{arm.workers} processes x {per_worker} instances of the same seeded workload, closed loop; a bench step is one '
+              f'SQP-RTI step of all {arm.workers * per_worker} sampled instances (4096 per GPU in the GPU arm)')
+    line = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=K, warmup=W_, ms_per_step=1e3 * wall / K,
+                higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64 (solver) + f32 (SDF network)', data='synthetic', impl='reference',
+                config=dict(workload='4096 independent quadrotor SDF-NMPC instances per GPU, closed-loop SQP-RTI, 1 iteration per step (BASELINE configs[2]); '
+                                     'CPU arm runs a bounded sample', N=20, nx=10, nu=4, sdf_arch='dod F5 [256,256,128,64] synthetic calibrated seed 0'),
+                cpu_baseline=dict(value=v, unit=UNIT, cores=arm.workers, kind='port', sample=sample, failures=bad),
                 e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-                note='CPU restatement (numpy float64 oracle) of acados 0.3.1 + L4CasADi 1.4.1 semantics with seeded synthetic weights - '
-                     'not the original binaries, which cannot be installed offline')
+                note=CPU_KIND_NOTE)
     emit(line)
 
 
@@ -328,9 +377,14 @@ def run_ours(args, rank, local_rank, world):
     if world == 1 and not args.no_sweep:
         sweep = sdf_microbench(net, peaks)
         enc_sweep = encoder_microbench(peaks)
-    cpu_v, cpu_info = (None, None)
+    latency = {}
+    if world == 1 and not args.no_sweep:
+        latency = latency_bench(net, cfg)
+    cpu_v, cpu_info, cpu_np = (None, None, None)
     if world == 1 and not args.no_cpu:
-        cpu_v, cpu_info = cpu_oracle_throughput(8, 2, os.cpu_count() or 1)
+        cpu_v, cpu_info = cpu_port_throughput(16, 6, 'cxx', os.cpu_count() or 1)
+        if not args.no_sweep:
+            cpu_np = cpu_port_throughput(4, 1, 'numpy', os.cpu_count() or 1, warmup=0)
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W_, ms_per_step=ms_total / K, higher_is_better=True,
                 scaling='weak', vs_baseline=None, dtype='f64 (solver) + f32 (SDF network)', data='synthetic',
                 config=dict(workload=f'{B} independent quadrotor SDF-NMPC instances per GPU, closed-loop SQP-RTI, 1 iteration per step (BASELINE configs[2])',
@@ -347,11 +401,172 @@ def run_ours(args, rank, local_rank, world):
     if sweep:
         line['sdf_microbench'] = sweep
         line['encoder_microbench'] = enc_sweep
+    if latency:
+        line['latency'] = latency
     if cpu_v is not None:
         line['cpu_baseline'] = dict(value=cpu_v, unit=UNIT, cores=cpu_info['workers'], kind='port',
-                                    sample=f"{cpu_info['workers']} processes x 8 instances x 2 closed-loop RTI steps of the same workload "
-                                           f"({cpu_info['solves']} solves, {cpu_info['busy_s']:.1f} s busy)")
+                                    sample=f"{cpu_info['workers']} processes x {cpu_info['per_worker']} instances x {cpu_info['steps']} closed-loop "
+                                           f"RTI steps of the same workload ({cpu_info['solves']} solves, {cpu_info['wall_s']:.1f} s wall, "
+                                           f"{cpu_info['failures']} failures)",
+                                    note=CPU_KIND_NOTE)
+        if cpu_np is not None:
+            line['cpu_baseline']['numpy_oracle'] = dict(value=cpu_np[0], unit=UNIT, cores=cpu_np[1]['workers'],
+                                                        sample=f"{cpu_np[1]['solves']} solves, dense condensed IPM in numpy (oracle/rti.py)")
     emit(line)
+
+
+class _Ref:
+    """Reference sample in the shape ``Nmpc.set_ref`` takes (``sdf_nmpc/utils/reference.py:6-28`` + the weights the caller
+    attaches)."""
+
+    def __init__(self, p, q, v, wz, wts):
+        self.p, self.q, self.v, self.wz = p, q, v, wz
+        self.Wp, self.Wv, self.Wq, self.Ww, self.Wa = wts['pos'], wts['vel'], wts['att'], wts['rates'], wts['acc']
+
+
+def latency_bench(net, cfg, steps=200):
+    """BASELINE metric (iii), configs[0]: closed-loop control steps through the reference's call sequence with HOST buffers,
+    wall-clock time of ``solve()`` (what ``ocp.py:170,177-178`` reports as time_tot), p50 / p99 in microseconds.
+    B = 1: ``Nmpc`` exactly as ``controller.py`` is driven (set_x0, set_ref for every node, solve, get_u).  B = 8, 64:
+    ``BatchedNmpc.solve_host`` (pinned H2D of the states, CUDA-graph replay, D2H of controls + status)."""
+    import torch
+    from sdf_nmpc_b200 import synth
+    from sdf_nmpc_b200.nmpc import BatchedNmpc, Nmpc
+    out = {}
+    wts = dict(pos=[0, 0, 5], vel=[3, 3, 3], att=[50, 50, 10], rates=[0, 0, 3], acc=0.05)
+    # ---- B = 1, reference call sequence (SURVEY 8d config 1)
+    mpc = Nmpc(cfg, sdf_net=net)
+    mpc.set_sdf_flag(True)
+    x = np.array([0, 0, 2, 1, 0, 0, 0, 0, 0, 0], float)
+    mpc.set_latent(synth.latent(seed=2), x[:3], np.eye(3))
+    vref, dt = np.array([3.0, 0.0, 0.0]), float(cfg.shooting_dt()[0])
+    xd = torch.zeros(1, 10, dtype=torch.float64, device='cuda')
+    ts, dev = [], []
+    for step in range(steps + 20):
+        mpc.set_x0(x)
+        for k in range(mpc.N + 1):
+            mpc.set_ref(_Ref(x[:3] + vref * k * dt, np.array([1.0, 0, 0, 0]), vref, 0.0, wts), k)
+        t0 = time.perf_counter()
+        mpc.solve()
+        t1 = time.perf_counter()
+        u = mpc.get_u()
+        if step >= 20:
+            ts.append(1e6 * (t1 - t0)); dev.append(1e6 * mpc.get_t())
+        xd.copy_(torch.from_numpy(x)[None])
+        mpc._b.plant_step(xd, torch.from_numpy(u)[None].cuda(), dt)
+        x = xd[0].cpu().numpy()
+    out['1'] = dict(p50_us=float(np.percentile(ts, 50)), p99_us=float(np.percentile(ts, 99)), mean_us=float(np.mean(ts)),
+                    device_p50_us=float(np.percentile(dev, 50)), steps=steps, fail=int(mpc.fail_count),
+                    api='Nmpc: set_x0, set_ref x21, solve (one pinned H2D block, CUDA-graph replay, D2H of u0/status), get_u')
+    del mpc
+    # ---- B = 8, 64: batched host-buffer step
+    for B in (8, 64):
+        w = synth.nmpc_instances(B)
+        b = BatchedNmpc(cfg, net, B)
+        b.set_sdf_flag(1.0); b.set_latent(w['latent'], w['W_p_Bo'], w['W_R_Bo'])
+        b.set_ref_arrays(w['yref'], w['W'], w['yrefN'], w['WN'], w['qd'])
+        xh = w['x0'].copy()
+        xdev = torch.from_numpy(xh).cuda()
+        ts = []
+        for step in range(steps + 20):
+            if step == 5:
+                b.enable_graph()
+            t0 = time.perf_counter()
+            u, st = b.solve_host(xh)
+            t1 = time.perf_counter()
+            if step >= 20:
+                ts.append(1e6 * (t1 - t0))
+            xdev.copy_(torch.from_numpy(xh))
+            b.plant_step(xdev, b.u0, dt)
+            xh = xdev.cpu().numpy()
+        out[str(B)] = dict(p50_us=float(np.percentile(ts, 50)), p99_us=float(np.percentile(ts, 99)), mean_us=float(np.mean(ts)),
+                           steps=steps, status_ok=int((st == 0).sum()), api='BatchedNmpc.solve_host (pinned H2D x0, CUDA-graph replay, D2H u0/status)')
+        del b
+    out['note'] = ('wall-clock microseconds of solve() with host buffers, closed loop, 200 steps after 20 warm-up steps; the reference budgets '
+                   '10 ms per control step (config/default.yaml:55)')
+    return out
+
+
+def sdf_cpu_microbench(net):
+    """configs[1], CPU side: the SDF through libtorch on the host - (a) what L4CasADi executes per shooting
+    node: 1 thread, batch 1, TorchScript forward and traced jacrev (gen_model.py:27,38-39); (b) batched forward + autograd
+    gradient on all cores."""
+    import torch
+    from oracle import torch_ref
+    from sdf_nmpc_b200 import synth
+    out = {}
+    nthr = torch.get_num_threads()
+    torch.set_num_threads(1)
+    fwd, jac = torch_ref.sdf_l4c_pair(net)
+    x = torch.zeros(1, 3 + int(net['size_latent']))
+    x[0, 3:] = torch.from_numpy(synth.latent(seed=2))
+    pts = synth.sdf_query_points(2000, seed=3)
+    with torch.no_grad():
+        for name, fn in (('forward', fwd), ('jacrev', jac)):
+            for i in range(50):
+                x[0, :3] = torch.from_numpy(pts[i]); fn(x)
+            t0 = time.perf_counter()
+            for i in range(1000):
+                x[0, :3] = torch.from_numpy(pts[i]); fn(x)
+            out[f'batch1_{name}_us'] = 1e6 * (time.perf_counter() - t0) / 1000
+    out['batch1_pts_per_s_1thread'] = 1e6 / (out['batch1_forward_us'] + out['batch1_jacrev_us'])
+    torch.set_num_threads(max(nthr, os.cpu_count() or 1))
+    m = torch_ref.SdfTorch(net).eval()
+    for n in (10_000, 100_000, 1_000_000):
+        p = torch.from_numpy(synth.sdf_query_points(n, seed=3))
+        xin = torch.cat([p, x[:, 3:].expand(n, -1)], 1).requires_grad_(True)
+        reps, t0 = 0, time.perf_counter()
+        while reps < 3 and (time.perf_counter() - t0 < 8.0 or reps == 0):
+            d = m(xin)
+            (g,) = torch.autograd.grad(d.sum(), xin)
+            reps += 1
+        dt_ = (time.perf_counter() - t0) / reps
+        out[f'batched_{n}'] = dict(ms=1e3 * dt_, mpts_per_s=n / dt_ / 1e6, threads=torch.get_num_threads())
+    torch.set_num_threads(nthr)
+    out['note'] = 'libtorch CPU kernels on a torch restatement of NeuralDF (oracle/torch_ref.py, pinned to the reference fixtures); value + gradient'
+    return out
+
+
+def encoder_torch_baseline():
+    """Part (4) as the reference runs it (vae.py:11-13,37-40): the same layer sequence on torch - cuDNN on the GPU with TF32
+    as torch defaults and with TF32 off, and libtorch on the CPU.  A LIBRARY comparison, not part of the product path."""
+    import torch
+    from oracle import torch_ref
+    from sdf_nmpc_b200 import synth
+    enc = torch_ref.EncoderTorch(synth.make_encoder_net(seed=5)).eval()
+    base = np.stack([synth.depth_frame(seed=1 + i) for i in range(4)])
+    out = {}
+    encg = enc.cuda()
+    with torch.no_grad():
+        for tf32 in (True, False):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            for nb in (1, 64, 256):
+                img = torch.from_numpy(np.concatenate([base] * ((nb + 3) // 4))[:nb]).cuda()
+                for _ in range(3):
+                    encg(img)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                reps = 10 if nb == 1 else 5
+                e0.record()
+                for _ in range(reps):
+                    encg(img)
+                e1.record(); torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / reps
+                out[f"cudnn_tf32_{'on' if tf32 else 'off'}_{nb}"] = dict(ms=ms, frames_per_s=nb / ms * 1e3, tflops=nb * ENC_FLOP_FRAME / ms / 1e9)
+        torch.backends.cudnn.allow_tf32 = True
+        encc = enc.cpu()
+        for nb in (1, 8):
+            img = torch.from_numpy(np.concatenate([base] * ((nb + 3) // 4))[:nb])
+            encc(img)
+            t0 = time.perf_counter()
+            for _ in range(2):
+                encc(img)
+            ms = 1e3 * (time.perf_counter() - t0) / 2
+            out[f'cpu_{nb}'] = dict(ms=ms, frames_per_s=nb / ms * 1e3, threads=torch.get_num_threads())
+    out['note'] = ('torch restatement of preprocessing + Vae.encoder (oracle/torch_ref.py, pinned to the reference fixtures) on cuDNN / libtorch: '
+                   'the library path the reference uses, measured on the same box; eager, batch as stated, device-resident frames')
+    return out
 
 
 def sdf_microbench(net, peaks):
@@ -383,6 +598,8 @@ def sdf_microbench(net, peaks):
         del pts, sdf, grad
     out['note'] = ('algorithmic FLOPs (615168 per point) counted once; the hidden-layer GEMMs run as 3 TF32 tcgen05 MMAs each '
                    '(2-way split for fp32 parity), so at most 1/6 of the bf16 peak is reachable by this accounting')
+    del ev
+    out['cpu'] = sdf_cpu_microbench(net)
     return out
 
 
@@ -418,6 +635,8 @@ def encoder_microbench(peaks):
         out[str(nb)] = dict(ms=ms, frames_per_s=nb / ms * 1e3, tflops=tf, frac_bf16_sustained=tf / peaks['bf16_tflops_sustained'],
                             frac_of_3xtf32_ceiling=tf / (peaks['bf16_tflops_sustained'] / 6.0))
     out['note'] = 'algorithmic FLOPs (4.34 GFLOP per frame) counted once; tensor-core layers use 3 TF32 MMAs per product'
+    del vae
+    out['torch_cudnn'] = encoder_torch_baseline()
     return out
 
 

@@ -47,7 +47,7 @@ class SdfTorch(torch.nn.Module):
         s, z = x[:, :3], x[:, 3:]
         if self.nf > 0:
             proj = s @ self.dirs
-            xb = (proj[..., None] * self.freq).reshape(s.shape[0], -1)
+            xb = (proj[..., None] * self.freq).flatten(1)
             e = torch.cat([s, torch.sin(xb), torch.sin(xb + 0.5 * math.pi)], 1)
         else:
             e = s
@@ -65,10 +65,14 @@ class SdfTorch(torch.nn.Module):
 def sdf_l4c_pair(net):
     """(forward, jacobian) callables the way L4CasADi 1.4.1 builds them for ``model_expects_batch_dim=True``
     (``gen_model.py:38-39``): TorchScript forward on [1, 131] and a ``torch.jit.trace`` of ``jacrev``."""
+    from torch.fx.experimental.proxy_tensor import make_fx
     m = SdfTorch(net).eval()
     fwd = torch.jit.script(m)
     x0 = torch.zeros(1, 3 + int(net['size_latent']))
-    jac = torch.jit.trace(torch.func.jacrev(lambda v: m(v)[0]), x0, check_trace=False)
+    # L4CasADi 1.4.1 traces functorch's jacrev with torch.jit.trace directly; under torch 2.11 that trace fails inside vmap, so
+    # the jacrev is first lowered to an aten graph (make_fx) and THAT graph is traced: the same TorchScript executor, the same
+    # kernels (one forward, one reverse sweep, batch 1)
+    jac = torch.jit.trace(make_fx(torch.func.jacrev(lambda v: m(v)[0]))(x0), x0, check_trace=False)
     return fwd, jac
 
 

@@ -21,6 +21,7 @@ struct sdfnmpc_sdf {
     float* b1f = nullptr;            // [cap_inst][H1] folded biases
     float* b3f = nullptr;            // [cap_inst][H3]
     int cap_inst = 0, n_inst = 0;
+    float *h_b1f = nullptr, *h_b3f = nullptr;   // folded biases of the host / CasADi path (its own: the batched state above is not touched)
     size_t smem = 0;
     int sm_count = 148;
     // tensor-core (tcgen05) path: chunk program, packed hi|lo weight chunks, per-CTA scratch

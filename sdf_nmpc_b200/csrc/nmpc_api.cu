@@ -411,7 +411,10 @@ extern "C" int sdfnmpc_solver_state(sdfnmpc_solver_t h, double** xbar, double** 
 
 __global__ void nmpc_fail_count_kernel(int B, const int* __restrict__ status, long long* __restrict__ fail) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < B) fail[b] = status[b] == 0 ? 0 : fail[b] + 1;
+    // acados SQP_RTI applies the step and returns success when the QP stops at its iteration limit (status 2), so
+    // Nmpc.solve resets fail_count there (controller.py:72-81); failures are a broken factorisation (4) and a step whose
+    // verified KKT residual disagrees with the tracked one (3, this library's own check).  status[] keeps the raw code.
+    if (b < B) fail[b] = (status[b] == 0 || status[b] == 2) ? 0 : fail[b] + 1;
 }
 
 extern "C" int sdfnmpc_fail_count_update(const int32_t* status, int64_t* fail_count, int32_t B, void* stream) {

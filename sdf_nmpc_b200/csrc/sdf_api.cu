@@ -254,7 +254,7 @@ extern "C" int sdfnmpc_sdf_create(sdfnmpc_sdf_t* out, const sdfnmpc_sdf_desc* d,
 extern "C" int sdfnmpc_sdf_destroy(sdfnmpc_sdf_t h) {
     if (!h) return 0;
     cudaFree(h->blob); cudaFree(h->b1f); cudaFree(h->b3f);
-    cudaFree(h->h_pts); cudaFree(h->h_out); cudaFree(h->h_lat);
+    cudaFree(h->h_pts); cudaFree(h->h_out); cudaFree(h->h_lat); cudaFree(h->h_b1f); cudaFree(h->h_b3f);
     cudaFree(h->tc_ops); cudaFree(h->tc_wblob); cudaFree(h->tc_scratch);
     free(h->tc_ops_host);
     delete h;
@@ -343,8 +343,17 @@ extern "C" int sdfnmpc_sdf_eval_host(sdfnmpc_sdf_t h, const float* pts, const fl
     if (!h->h_lat) SDF_CUDA_CHECK(cudaMalloc(&h->h_lat, (size_t)(h->net.L > 0 ? h->net.L : 1) * sizeof(float)));
     SDF_CUDA_CHECK(cudaMemcpyAsync(h->h_pts, pts, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, 0));
     if (h->net.L > 0) SDF_CUDA_CHECK(cudaMemcpyAsync(h->h_lat, latent, (size_t)h->net.L * sizeof(float), cudaMemcpyHostToDevice, 0));
-    if (int rc = sdfnmpc_sdf_set_latents(h, h->h_lat, 1, nullptr)) return rc;
-    if (int rc = sdfnmpc_sdf_eval(h, h->h_pts, nullptr, (int32_t)n, n, h->h_out, grad ? h->h_out + n : nullptr, nullptr)) return rc;
+    // The host path folds its latent into its OWN bias buffers: a handle that is bound to the CasADi entry points and also
+    // serves a batched solver keeps the solver's per-instance biases and instance count.
+    if (!h->h_b1f) SDF_CUDA_CHECK(cudaMalloc(&h->h_b1f, (size_t)h->net.H1 * sizeof(float)));
+    if (!h->h_b3f) SDF_CUDA_CHECK(cudaMalloc(&h->h_b3f, (size_t)h->net.H3 * sizeof(float)));
+    float *sb1 = h->b1f, *sb3 = h->b3f;
+    const int scap = h->cap_inst, sn = h->n_inst;
+    h->b1f = h->h_b1f; h->b3f = h->h_b3f; h->cap_inst = 1; h->n_inst = 0;
+    int rc_ = sdfnmpc_sdf_set_latents(h, h->h_lat, 1, nullptr);
+    if (!rc_) rc_ = sdfnmpc_sdf_eval(h, h->h_pts, nullptr, (int32_t)n, n, h->h_out, grad ? h->h_out + n : nullptr, nullptr);
+    h->b1f = sb1; h->b3f = sb3; h->cap_inst = scap; h->n_inst = sn;
+    if (rc_) return rc_;
     if (sdf) SDF_CUDA_CHECK(cudaMemcpyAsync(sdf, h->h_out, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, 0));
     if (grad) SDF_CUDA_CHECK(cudaMemcpyAsync(grad, h->h_out + n, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, 0));
     SDF_CUDA_CHECK(cudaStreamSynchronize(0));
@@ -406,7 +415,12 @@ extern "C" int sdfnmpc_l4c_load_blob(const char* path) {
     if (!f) { fprintf(stderr, "[sdfnmpc_b200] cannot open %s\n", path); return SDFNMPC_E_INVALID; }
     int32_t hdr[2];
     sdfnmpc_sdf_desc d;
-    if (fread(hdr, sizeof(hdr), 1, f) != 1 || hdr[0] != 0x42464453 || fread(&d, sizeof(d), 1, f) != 1) { fclose(f); return SDFNMPC_E_INVALID; }
+    if (fread(hdr, sizeof(hdr), 1, f) != 1 || hdr[0] != 0x42464453 || hdr[1] != 1 || fread(&d, sizeof(d), 1, f) != 1) { fclose(f); return SDFNMPC_E_INVALID; }
+    // the descriptor comes from a file: range-check it before it sizes any allocation (sdfnmpc_sdf_create repeats the checks)
+    auto bad = [](int v, int lo, int hi) { return v < lo || v > hi; };
+    if (bad(d.n_dirs, 1, 64) || bad(d.nb_freqs, 0, 16) || bad(d.size_latent, 0, 4096) || bad(d.hidden[0], 1, 4096) ||
+        bad(d.hidden[1], 1, 4096) || bad(d.hidden[2], 1, 4096) || bad(d.hidden[3], 1, 4096)) { fclose(f); return SDFNMPC_E_INVALID; }
+    try {
     const int E = 3 + 2 * d.n_dirs * d.nb_freqs, L = d.size_latent;
     const int in3 = d.hidden[1] + (d.res_state ? E : 0) + (d.res_latent ? L : 0);
     const size_t sz[11] = {(size_t)3 * d.n_dirs, (size_t)d.hidden[0] * (E + L), (size_t)d.hidden[0],
@@ -419,6 +433,7 @@ extern "C" int sdfnmpc_l4c_load_blob(const char* path) {
         if (fread(a[i].data(), sizeof(float), sz[i], f) != sz[i]) { fclose(f); return SDFNMPC_E_INVALID; }
     }
     fclose(f);
+    f = nullptr;
     sdfnmpc_sdf_t h = nullptr;
     int rc = sdfnmpc_sdf_create(&h, &d, a[0].data(), a[1].data(), a[2].data(), a[3].data(), a[4].data(), a[5].data(),
                                 a[6].data(), a[7].data(), a[8].data(), a[9].data(), a[10].data());
@@ -427,6 +442,10 @@ extern "C" int sdfnmpc_l4c_load_blob(const char* path) {
     g_l4c = h;
     g_l4c_owned = true;
     return 0;
+    } catch (...) {      // nothing may unwind through an extern "C" boundary
+        if (f) fclose(f);
+        return SDFNMPC_E_INVALID;
+    }
 }
 
 static int l4c_nin() { return g_l4c ? 3 + g_l4c->net.L : 131; }

@@ -24,7 +24,12 @@ MODEL_ID = {'att': 0, 'att_tau': 1, 'acc': 2}      # mpc.model values reachable 
 
 
 class BatchedNmpc:
-    def __init__(self, cfg, sdf_net, batch, device='cuda:0'):
+    def __init__(self, cfg, sdf_net=None, batch=1, device='cuda:0'):
+        """``sdf_net``: packed network (``weights.sdf_from_module`` / ``synth.make_sdf_net``); ``None`` loads the TorchScript file
+        ``cfg.nn.sdf_weights`` from the data directory like ``gen_model.py:32`` does."""
+        if sdf_net is None:
+            from . import weights
+            sdf_net = weights.load_sdf(cfg)
         if cfg.mpc.model not in MODEL_ID:
             raise NotImplementedError(f"mpc.model == '{cfg.mpc.model}' is not built (available: {sorted(MODEL_ID)})")
         self.model = cfg.mpc.model
@@ -44,6 +49,11 @@ class BatchedNmpc:
         # mission flags (gen_model.py:26-70): a row the reference would not add is kept with bounds that can never be
         # active, which leaves the optimum unchanged (slack 0, multiplier 0)
         fl = cfg.get('flags', {})
+        for name in ('recursive_feasibility', 'stability'):
+            if fl.get(name, False):
+                # gen_model.py:69-142 changes the OCP for these (terminal SDF row dropped, braking-distance row, terminal FoV at the
+                # braking point, terminal velocity box, p_term cost): solving the plain OCP instead would be silently wrong
+                raise NotImplementedError(f"flags.{name} is not built: the terminal ingredients of gen_model.py:73-149 are missing")
         off = [not fl.get('enable_sdf', True) or not (cfg.sensor.hfov < 3.14),
                not fl.get('enable_sdf', True) or not fl.get('vfov_constraint', True),
                not fl.get('enable_sdf', True) or not fl.get('sdf_constraint', True)]
@@ -77,6 +87,8 @@ class BatchedNmpc:
         f64 = dict(dtype=torch.float64, device=self.device)
         B, N = self.B, self.N
         self.u0 = torch.zeros(B, NU, **f64)
+        self._ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        self._timed = False
         self.status = torch.zeros(B, dtype=torch.int32, device=self.device)
         self.qp_iters = torch.zeros(B, dtype=torch.int32, device=self.device)
         self._pin = {}
@@ -93,21 +105,35 @@ class BatchedNmpc:
         t = torch.as_tensor(a, dtype=dtype, device=self.device)
         return t.reshape(shape).contiguous() if shape is not None else t.contiguous()
 
+    def _layout(self):
+        """Offsets (in doubles) of the per-step inputs inside ONE device block: a host caller fills a pinned mirror with the
+        same layout and uploads it with a single copy (``Nmpc``)."""
+        B, N = self.B, self.N
+        sizes = (('x0', (B, NX)), ('y', (B, N, NY)), ('W', (B, N, NY)), ('yN', (B, self.nyN)), ('WN', (B, self.nyN)),
+                 ('qd', (B, N + 1, 4)), ('flag', (B,)), ('pose', (B, 12)))
+        off, lay = 0, {}
+        for name, shp in sizes:
+            n = int(np.prod(shp))
+            lay[name] = (off, n, shp)
+            off += n
+        return lay, off
+
     def reset(self):
         """controller.py:32-42."""
-        f64 = dict(dtype=torch.float64, device=self.device)
-        B, N = self.B, self.N
+        B = self.B
+        lay, total = self._layout()
+        self._in = torch.zeros(total, dtype=torch.float64, device=self.device)
+        view = lambda k: self._in[lay[k][0]:lay[k][0] + lay[k][1]].view(lay[k][2])
+        self._x0 = view('x0')                             # static address: the RTI step may be replayed as a CUDA graph
         self.x0 = None
-        self.flag = torch.zeros(B, **f64)
-        self.pose = torch.zeros(B, 12, **f64)            # W_p_Co(3), W_R_Co row-major(9)
-        self.qd = torch.zeros(B, N + 1, 4, **f64)
+        self.flag = view('flag')
+        self.pose = view('pose')                          # W_p_Co(3), W_R_Co row-major(9)
+        self.qd = view('qd')
         self.latent = torch.zeros(B, max(self.L, 1), dtype=torch.float32, device=self.device)
-        self.y = torch.zeros(B, N, NY, **f64)
-        self.yN = torch.zeros(B, self.nyN, **f64)
-        self.W = torch.zeros(B, N, NY, **f64)
-        self.WN = torch.zeros(B, self.nyN, **f64)
+        self.y, self.yN, self.W, self.WN = view('y'), view('yN'), view('W'), view('WN')
         self.fail_count = torch.zeros(B, dtype=torch.int64, device=self.device)
         self._latent_dirty = True
+        self._graph = None
         self.set_sdf_flag(False)
 
     def set_sdf_flag(self, flag):
@@ -120,8 +146,9 @@ class BatchedNmpc:
         p = self._t(W_p_Bo, (-1, 3))
         BpC = self._t(np.asarray(self.cfg.sensor.B_p_C, float))
         BRC = self._t(np.asarray(self.cfg.sensor.B_R_C, float))
-        self.pose[:, 0:3] = R @ BpC + p
-        self.pose[:, 3:12] = (R @ BRC).reshape(-1, 9)
+        # 3 x 3 products written out as broadcast sums: no library GEMM launches on this path
+        self.pose[:, 0:3] = (R * BpC).sum(-1) + p
+        self.pose[:, 3:12] = (R[:, :, :, None] * BRC[None]).sum(2).reshape(-1, 9)
         self.latent[:] = self._t(latent, (-1, max(self.L, 1)), torch.float32)
         self._latent_dirty = True
 
@@ -132,10 +159,11 @@ class BatchedNmpc:
 
     def set_x0(self, x0):
         """controller.py:65-69: the first call initialises the trajectory (ocp.py:144-149)."""
-        x0 = self._t(x0, (self.B, -1))[:, :NX].contiguous()
+        if x0 is not self._x0:
+            self._x0.copy_(torch.as_tensor(x0, dtype=torch.float64).reshape(self.B, -1)[:, :NX], non_blocking=True)
         if self.x0 is None:
-            _lib.check(self.lib.sdfnmpc_solver_init_traj(self.handle, _ptr(x0), self.B, _stream()), 'init_traj')
-        self.x0 = x0
+            _lib.check(self.lib.sdfnmpc_solver_init_traj(self.handle, _ptr(self._x0), self.B, _stream()), 'init_traj')
+        self.x0 = self._x0
 
     def set_ref_arrays(self, yref, W, yrefN, WN, qd):
         self.y[:] = self._t(yref, (self.B, self.N, NY))
@@ -178,15 +206,53 @@ class BatchedNmpc:
         """controller.py:72-81 - one SQP-RTI iteration for every instance; returns fail_count [B]."""
         if self.x0 is None:
             raise _lib.SdfNmpcError('set_x0 must be called before solve')
+        if self._graph is not None:
+            if self._latent_dirty:
+                self.sdf.set_latents(self.latent)
+                self._latent_dirty = False
+            self._ev[0].record()
+            self._graph.replay()
+            self._ev[1].record()
+            self._timed = True
+            return self.fail_count
         self.shift()
+        self._rti_iteration()
+        _lib.check(self.lib.sdfnmpc_fail_count_update(_ptr(self.status), _ptr(self.fail_count), self.B, _stream()), 'fail_count_update')
+        return self.fail_count
+
+    def enable_graph(self):
+        """Capture one control step (warm-start shift, linearise, SDF, QP, fail count) as a CUDA graph; ``solve()`` then
+        replays it: one launch instead of four to six, which is what a single-instance caller pays for (``--workload
+        single``).  Inputs live at static addresses (``_layout``); latents are folded outside the graph when they change."""
+        if self.x0 is None:
+            raise _lib.SdfNmpcError('set_x0 must be called before enable_graph')
+        if self._latent_dirty:
+            self.sdf.set_latents(self.latent)
+            self._latent_dirty = False
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                self.shift()
+                self._rti_iteration(timed=False)
+                _lib.check(self.lib.sdfnmpc_fail_count_update(_ptr(self.status), _ptr(self.fail_count), self.B, _stream()), 'fail_count_update')
+        torch.cuda.current_stream().wait_stream(side)
+        self._graph = g
+
+    def _rti_iteration(self, timed=True):
+        """ocp.py:159-170 without the warm-start shift and the fail-count bookkeeping (both belong to the control step)."""
         lat = _ptr(self.latent) if self._latent_dirty else C.c_void_p(0)
+        if timed:
+            self._ev[0].record()
         _lib.check(self.lib.sdfnmpc_solver_rti_step(
             self.handle, self.B, _ptr(self.x0), _ptr(self.y), _ptr(self.W), _ptr(self.yN), _ptr(self.WN), _ptr(self.qd),
             _ptr(self.pose), _ptr(self.flag), lat, _ptr(self.u0), _ptr(self.status), _ptr(self.qp_iters), _stream()),
             'sdfnmpc_solver_rti_step')
+        if timed:
+            self._ev[1].record()
+            self._timed = True
         self._latent_dirty = False
-        _lib.check(self.lib.sdfnmpc_fail_count_update(_ptr(self.status), _ptr(self.fail_count), self.B, _stream()), 'fail_count_update')
-        return self.fail_count
 
     def solve_host(self, x0, out=None, sync=True):
         """End-to-end step with HOST buffers: pinned H2D of the state feedback, solve, D2H of the controls.  With
@@ -197,10 +263,9 @@ class BatchedNmpc:
             pin = self._pin['x0'] = torch.empty(self.B, NX, dtype=torch.float64).pin_memory()
             self._pin['u0'] = torch.empty(self.B, NU, dtype=torch.float64).pin_memory()
             self._pin['st'] = torch.empty(self.B, dtype=torch.int32).pin_memory()
-            self._pin['x0d'] = torch.empty(self.B, NX, dtype=torch.float64, device=self.device)
         pin.copy_(torch.as_tensor(x0, dtype=torch.float64).reshape(self.B, -1)[:, :NX])
-        self._pin['x0d'].copy_(pin, non_blocking=True)
-        self.set_x0(self._pin['x0d'])
+        self._x0.copy_(pin, non_blocking=True)
+        self.set_x0(self._x0)
         self.solve()
         self._pin['u0'].copy_(self.u0, non_blocking=True)
         self._pin['st'].copy_(self.status, non_blocking=True)
@@ -280,6 +345,14 @@ class BatchedNmpc:
         d, _ = self.sdf.eval(c0, pts_per_inst=1, want_grad=False)
         return d
 
+    def get_t(self):
+        """``Ocp.get_t`` (``ocp.py:170,177-178``): time of the last solve in seconds - here the device time of the last
+        SQP-RTI iteration (linearise + SDF + QP), from CUDA events on the launching stream."""
+        if not self._timed:
+            return 0.0
+        self._ev[1].synchronize()
+        return 1e-3 * self._ev[0].elapsed_time(self._ev[1])
+
     def get_qp_residual(self):
         """[B,2]: verified KKT residual of each instance's last QP, inf-norm of the SQP step it produced."""
         p = C.c_void_p()
@@ -294,8 +367,11 @@ class BatchedNmpc:
         done = torch.zeros(self.B, dtype=torch.bool, device=self.device)
         iters = torch.zeros(self.B, dtype=torch.int64, device=self.device)
         u_conv = torch.zeros(self.B, NU, dtype=torch.float64, device=self.device)
+        if self.x0 is None:
+            raise _lib.SdfNmpcError('set_x0 must be called before solve_sqp')
+        self.shift()                       # once per control step, not once per SQP iteration
         for _ in range(max_iter):
-            self.solve()
+            self._rti_iteration()
             step = self.get_qp_residual()[:, 1]
             iters += (~done).to(torch.int64)
             newly = (~done) & (step <= tol)
@@ -304,6 +380,7 @@ class BatchedNmpc:
             if bool(done.all()):
                 break
         u_conv = torch.where(done[:, None], u_conv, self.u0)
+        _lib.check(self.lib.sdfnmpc_fail_count_update(_ptr(self.status), _ptr(self.fail_count), self.B, _stream()), 'fail_count_update')
         return u_conv, iters, done
 
     def timing_begin(self, max_steps):
@@ -323,43 +400,92 @@ class BatchedNmpc:
 
 
 class Nmpc:
-    """Single-instance facade with the reference's signatures (``sdf_nmpc/controller.py``)."""
+    """Single-instance facade with the reference's signatures (``sdf_nmpc/controller.py``).
 
-    def __init__(self, cfg, sdf_net, rebuild=False, device='cuda:0'):
+    Like the reference, the setters only write host (numpy) arrays; ``solve()`` pushes everything at once
+    (``ocp.py:159-168`` pushes yref / W / p node by node into acados): here ONE pinned host-to-device copy of the input block,
+    one CUDA-graph replay of the control step and one read-back of (u0, status, fail count)."""
+
+    def __init__(self, cfg, rebuild=False, sdf_net=None, device='cuda:0', use_graph=True):
+        """``Nmpc(cfg, rebuild=False)`` as in ``controller.py:9``: the SDF comes from ``cfg.nn.sdf_weights`` in the data
+        directory (``gen_model.py:32``); ``rebuild`` is accepted and ignored (nothing is code-generated here).  A packed
+        network may be given instead, as ``sdf_net=`` or in second position."""
+        if isinstance(rebuild, dict):
+            sdf_net, rebuild = rebuild, False
         self.cfg = cfg if isinstance(cfg, Config) else Config(cfg)
         self._b = BatchedNmpc(self.cfg, sdf_net, 1, device)
         self.N, self.T = self._b.N, self._b.T
-        self.fail_count = 0
+        self._use_graph = bool(use_graph)
+        lay, total = self._b._layout()
+        self._lay = lay
+        self._h = torch.zeros(total, dtype=torch.float64).pin_memory()
+        hv = self._h.numpy()
+        self._hv = {k: hv[o:o + n].reshape(shp) for k, (o, n, shp) in lay.items()}
+        self._u0 = torch.zeros(NU, dtype=torch.float64).pin_memory()
+        self._st = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._fc = torch.zeros(1, dtype=torch.int64).pin_memory()
+        self.cmd_acc_hover, self.cmd_acc_min, self.cmd_acc_max = self._b.cmd_acc_hover, self._b.cmd_acc_min, self._b.cmd_acc_max
+        self.cmd_TRPYr_hover, self.cmd_TRPYr_min, self.cmd_TRPYr_max = self._b.cmd_TRPYr_hover, self._b.cmd_TRPYr_min, self._b.cmd_TRPYr_max
+        self.reset()
 
     def reset(self):
         self._b.reset()
+        self._h.zero_()
+        self.x0 = None
         self.fail_count = 0
 
     def set_sdf_flag(self, flag):
-        self._b.set_sdf_flag(float(flag))
+        self._hv['flag'][:] = float(flag)
 
     def set_latent(self, latent, W_p_Bo, W_R_Bo):
-        self._b.set_latent(np.asarray(latent, np.float32).reshape(1, -1), np.asarray(W_p_Bo, float).reshape(1, 3),
-                           np.asarray(W_R_Bo, float).reshape(1, 3, 3))
+        R = np.asarray(W_R_Bo, float).reshape(3, 3)
+        self._hv['pose'][0, 0:3] = R @ np.asarray(self.cfg.sensor.B_p_C, float) + np.asarray(W_p_Bo, float).reshape(3)
+        self._hv['pose'][0, 3:12] = (R @ np.asarray(self.cfg.sensor.B_R_C, float)).reshape(9)
+        self._b.latent[:] = torch.as_tensor(np.asarray(latent, np.float32).reshape(1, -1))
+        self._b._latent_dirty = True
 
     def reset_latent(self):
-        self._b.reset_latent()
+        self._hv['pose'][:] = 0.0
+        self._b.latent.zero_()
+        self._b._latent_dirty = True
 
     def set_x0(self, x0):
         self.x0 = np.asarray(x0, float)[:NX]
-        self._b.set_x0(self.x0.reshape(1, -1))
+        self._hv['x0'][0] = self.x0
 
     def set_ref(self, ref, k):
-        self._b.set_ref(ref, k)
+        y, W = self._b.formate_ref(ref)
+        self._hv['qd'][0, k] = np.asarray(ref.q, float)
+        if k < self.N:
+            self._hv['y'][0, k], self._hv['W'][0, k] = y, W
+        else:
+            self._hv['yN'][0], self._hv['WN'][0] = y[:self._b.nyN], W[:self._b.nyN]
 
     def solve(self):
-        self.fail_count = int(self._b.solve()[0].item())
+        if self.x0 is None:
+            raise _lib.SdfNmpcError('set_x0 must be called before solve')
+        b = self._b
+        b._in.copy_(self._h, non_blocking=True)
+        b.set_x0(b._x0)                      # first call: Ocp.init (ocp.py:144-149) from the uploaded state
+        if self._use_graph and b._graph is None:
+            b.solve()                        # one eager step first (module loading), then capture
+            b.enable_graph()
+        else:
+            b.solve()
+        self._u0.copy_(b.u0[0], non_blocking=True)
+        self._st.copy_(b.status, non_blocking=True)
+        self._fc.copy_(b.fail_count, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        self.fail_count = int(self._fc[0])
         if self.fail_count:
-            print('solver failed: status', int(self._b.status[0].item()))
+            print('solver failed: status', int(self._st[0]))
         return self.fail_count
 
     def get_u(self):
-        return self._b.u0[0].cpu().numpy()
+        return self._u0.numpy().copy()
+
+    def get_t(self):
+        return self._b.get_t()
 
     def get_matrices(self):
         x, u = self._b.get_matrices()

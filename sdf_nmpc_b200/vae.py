@@ -19,9 +19,14 @@ def _fp(a):
 class VaeWrapper:
     """``enc_net``: dict as produced by ``weights.encoder_from_module`` / ``synth.make_encoder_net``."""
 
-    def __init__(self, cfg, enc_net, max_batch=1, device='cuda:0'):
+    def __init__(self, cfg, enc_net=None, max_batch=1, device='cuda:0'):
+        """``VaeWrapper(cfg)`` as in ``vae.py:8``: the encoder comes from the TorchScript file ``cfg.nn.vae_weights`` in the
+        data directory (``vae.py:11-13``) unless a packed ``enc_net`` is given."""
         if not torch.cuda.is_available():
             raise _lib.SdfNmpcError('CUDA is not available: sdf_nmpc_b200 has no CPU path')
+        if enc_net is None:
+            from . import weights
+            enc_net = weights.load_encoder(cfg)
         self.cfg = cfg
         self.lib = _lib.load()
         self.device = torch.device(device)

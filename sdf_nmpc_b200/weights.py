@@ -58,6 +58,34 @@ def encoder_from_module(encoder):
     return net
 
 
+def load_sdf(cfg):
+    """``gen_model.py:32-34``: ``torch.jit.load(default_data_dir() / cfg.nn.sdf_weights)`` -> packed dictionary."""
+    import os
+
+    import torch
+
+    from . import default_data_dir
+    path = os.path.join(default_data_dir(), cfg.nn.sdf_weights)
+    if not os.path.isfile(path) or os.path.getsize(path) < 1024:
+        raise FileNotFoundError(f'{path}: TorchScript SDF weights not found (the reference ships them through Git LFS); '
+                                'put the file there, call sdf_nmpc_b200.set_data_dir(...) or pass sdf_net=')
+    return sdf_from_module(torch.jit.load(path, map_location='cpu').eval())
+
+
+def load_encoder(cfg):
+    """``vae.py:11-13``: ``torch.jit.load(default_data_dir() / cfg.nn.vae_weights)`` -> packed encoder dictionary."""
+    import os
+
+    import torch
+
+    from . import default_data_dir
+    path = os.path.join(default_data_dir(), cfg.nn.vae_weights)
+    if not os.path.isfile(path) or os.path.getsize(path) < 1024:
+        raise FileNotFoundError(f'{path}: TorchScript VAE weights not found (the reference ships them through Git LFS); '
+                                'put the file there, call sdf_nmpc_b200.set_data_dir(...) or pass enc_net=')
+    return encoder_from_module(torch.jit.load(path, map_location='cpu').eval().encoder)
+
+
 def sdf_desc_fields(net):
     E = 3 + 2 * int(net['nb_freqs']) * net['dirs'].shape[1]
     return dict(n_dirs=int(net['dirs'].shape[1]), nb_freqs=int(net['nb_freqs']),

@@ -94,3 +94,28 @@ def test_qp_core_robust_over_many_instances(emul):
         u0, st, its, *_ = _emul_step(emul, net, cfg, prob, xe, ue)
         assert np.all(st == 0), (step, np.where(st != 0)[0])
         assert its.max() <= 40
+
+
+def test_cxx_port_matches_numpy_oracle():
+    """oracle/cxx_port.CxxRti (the CPU arm bench.py times: C++ linearisation + IPM, libtorch batch-1 SDF) gives the numpy
+    oracle's controls on the same closed-loop steps."""
+    import subprocess as sp
+    from oracle import cxx_port, rti, models
+    from sdf_nmpc_b200 import synth
+    if not os.path.exists(cxx_port.LIB):
+        os.makedirs(os.path.dirname(cxx_port.LIB), exist_ok=True)
+        sp.run(['g++', '-O3', '-std=c++17', '-shared', '-fPIC', '-DSDFNMPC_HOST_EMUL', '-x', 'c++',
+                os.path.join(ROOT, 'tests', 'host_emul', 'emul.cpp'), '-o', cxx_port.LIB], check=True)
+    net = synth.make_sdf_net(seed=0, **synth.ARCH_B, calibrated=True)
+    cfg = rti.default_cfg()
+    B = 3
+    prob, w = make_problem(B, cfg)
+    port = cxx_port.CxxRti(net, cfg, prob, sdf='torch')
+    xb, ub = rti.init_traj(prob['x0'], cfg)
+    x = prob['x0'].copy()
+    for step in range(2):
+        p = dict(prob); p['x0'] = x
+        xb, ub, out = rti.rti_step(net, xb, ub, p, cfg)
+        u0, st, its = port.step(x)
+        assert np.all(st == 0) and np.abs(u0 - out['u0']).max() <= 2e-5
+        x = models.get('att').rk4(x, out['u0'], cfg['dt'][0], cfg)
