@@ -3,15 +3,18 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
 
-Workload (config.workload): BASELINE.json configs[2] - 4096 independent quadrotor SDF-NMPC instances per
-GPU (seeded random states / latents / references), closed loop: every step is ONE
-SQP-RTI iteration for every instance (linearise -> fused SDF value+gradient -> Riccati IPM -> full step)
-followed by an RK4 plant step.  N > 1 (torchrun, one rank per GPU): the instances shard as contiguous blocks,
-no data-path collective; one NCCL all-gather of the per-instance result records closes the timed region.
+Workload (config.workload).  One GPU: BASELINE.json configs[2] - 4096 independent quadrotor SDF-NMPC instances
+(seeded random states / latents / references), closed loop: every step is ONE SQP-RTI
+iteration for every instance (linearise -> fused SDF value+gradient -> Riccati IPM -> full step) followed by an
+RK4 plant step.  N > 1 (torchrun, one rank per GPU): BASELINE.json configs[3] - 65 536 environments sharded as
+contiguous blocks over the ranks, full closed-loop rollout step (device reference generation -> SQP-RTI -> plant ->
+collision label), no data-path collective, one NCCL all-gather of the per-environment result records inside the
+timed region; the configs[2] measurement of the same run (4096 instances per GPU) is kept in `extra.solver_only`.
 
 The JSON line carries, besides the base contract:
   value      device-resident throughput (inputs already in HBM), whole job, max-over-ranks time
-  e2e        same metric through the public API with HOST buffers (pinned H2D of x0 and D2H of u0/status per step)
+  e2e        same metric through the public API with HOST buffers: per step a pinned H2D of everything the reference pushes
+             into its solver (x0, yref, W, q_d, flag, camera pose of every instance) and a D2H of u0 / status / new state
   roofline   dominant kernel of the step, timed live with CUDA events on the launching stream
   kernels    per-kernel share of the step and the SDF kernel's own roofline numbers
   latency    p50 / p99 wall microseconds of solve() with host buffers for 1, 8, 64 instances (metric iii, configs[0])
@@ -321,16 +324,27 @@ def run_ours(args, rank, local_rank, world):
     status_ok = int((allrec[:, 4] == 0).sum().item())
     qp_it_mean = float(allrec[:, 5].mean().item())
     # ---- end-to-end timed region: host buffers every step ----
-    x_pin = torch.empty(B, 10, dtype=torch.float64).pin_memory()
-    x_pin.copy_(x)
+    # What the reference pushes into its solver at every control step (ocp.py:159-168: x0, and yref / W / p for every node)
+    # arrives from HOST memory here too: one pinned block [x0 | yref | W | yrefN | WN | q_d | flag | camera pose] per step
+    # (555 doubles per instance), then the solve, then u0 / status / the plant's new state back to the host.
+    lay, total_in = mpc._layout()
+    h_pin = torch.empty(total_in, dtype=torch.float64).pin_memory()
+    h_pin.copy_(mpc._in)
+    x_off = lay['x0'][0]
+    x_pin = h_pin[x_off:x_off + B * 10].view(B, 10)
+    u_pin = torch.empty(B, 4, dtype=torch.float64).pin_memory()
+    s_pin = torch.empty(B, dtype=torch.int32).pin_memory()
 
     def step_e2e():
-        # state feedback arrives in host memory: pinned H2D of x0 [B,10] f64, solve, D2H of u0 [B,4] f64 + status [B] i32
-        mpc.solve_host(x_pin, sync=False)
+        mpc._in.copy_(h_pin, non_blocking=True)
+        mpc.set_x0(mpc._x0)
+        mpc.solve()
+        u_pin.copy_(mpc.u0, non_blocking=True)
+        s_pin.copy_(mpc.status, non_blocking=True)
         # simulated plant (device) and its measurement copied back to the host for the next control step; ONE
         # synchronisation per step, after which u0 / status / the new state are all in host memory
-        mpc.plant_step(mpc.x0, mpc.u0, dt)
-        x_pin.copy_(mpc.x0, non_blocking=True)
+        mpc.plant_step(mpc._x0, mpc.u0, dt)
+        x_pin.copy_(mpc._x0, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
     for _ in range(2):
@@ -342,6 +356,19 @@ def run_ours(args, rank, local_rank, world):
         step_e2e()
     torch.cuda.synchronize()
     e2e_ms = D.max_over_ranks(1e3 * (time.perf_counter() - t0), dev)
+    e2e_h2d, e2e_d2h = total_in * 8, B * 4 * 8 + B * 4 + B * 10 * 8
+    # ---- a longer device-resident run (200 steps): the 20-step region of the driver is only ~80 ms
+    long_ms = None
+    if not args.no_sweep:
+        x.copy_(mpc._x0)
+        e0.record()
+        for _ in range(200):
+            step_device()
+        e1.record()
+        torch.cuda.synchronize()
+        long_ms = D.max_over_ranks(e0.elapsed_time(e1), dev)
+    # ---- BASELINE configs[3]: 65 536 environments sharded over the GPUs, full closed-loop rollout step (N > 1: the headline)
+    roll = measure_rollout(args, rank, local_rank, world, cfg, net, K, W_) if (world > 1 or not args.no_sweep) else None
     if rank != 0:
         return
     peaks = load_peaks()
@@ -391,13 +418,30 @@ def run_ours(args, rank, local_rank, world):
                             instances_per_gpu=B, N=20, nx=10, nu=4, sdf_arch='dod F5 [256,256,128,64] synthetic calibrated seed 0',
                             parallelism=f'instances sharded x{world}, no data-path collective; one all-gather of result records',
                             l2='per-step working set ~%d MB exceeds the 126 MB L2 (no flush needed)' % (B * mpc_work_mb())),
-                e2e=dict(value=total_solves / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=B * 10 * 8, d2h_bytes_per_step=B * 4 * 8 + B * 4 + B * 10 * 8,
-                         ms_per_step=e2e_ms / K),
+                e2e=dict(value=total_solves / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=e2e_h2d, d2h_bytes_per_step=e2e_d2h,
+                         ms_per_step=e2e_ms / K,
+                         note='per step: pinned H2D of x0, yref, W, yrefN, WN, q_d, flag and camera pose of every instance (what ocp.py:159-168 pushes), '
+                              'D2H of u0, status and the new state'),
                 gpu_launches=int(launches), clocks=clocks, roofline=roof, kernels=kern,
                 sdf_kernel=dict(points_per_launch=pts, mpts_per_s=pts / sdf_k['ms'] / 1e3, tflops=sdf_k['tflops'],
                                 frac_bf16_sustained=sdf_k['tflops'] / peaks['bf16_tflops_sustained'],
                                 frac_of_3xtf32_ceiling=sdf_k['tflops'] / (peaks['bf16_tflops_sustained'] / 6.0)),
                 status_ok=status_ok, instances=int(allrec.shape[0]), qp_iters_mean=qp_it_mean)
+    extra = {}
+    if long_ms is not None:
+        extra['long_run'] = dict(steps=200, ms_per_step=long_ms / 200, value=B * world * 200 / (long_ms * 1e-3), unit=UNIT)
+    if roll is not None and world > 1:
+        # N > 1: the headline is configs[3]; the configs[2] measurement of this same run moves to `extra`
+        extra['solver_only'] = dict(value=line['value'], unit=UNIT, ms_per_step=line['ms_per_step'], instances_per_gpu=B,
+                                    e2e=line['e2e'], workload=line['config']['workload'])
+        line.update(value=roll['value'], ms_per_step=roll['ms_per_step'], scaling='strong', e2e=roll['e2e'], gpu_launches=roll['gpu_launches'],
+                    status_ok=roll['status_ok'], instances=roll['instances'], qp_iters_mean=roll['qp_iters_mean'])
+        line['config'] = roll['config']
+        line['rollout'] = roll['stats']
+    elif roll is not None:
+        extra['rollout_configs3_shard'] = roll
+    if extra:
+        line['extra'] = extra
     if sweep:
         line['sdf_microbench'] = sweep
         line['encoder_microbench'] = enc_sweep
@@ -413,6 +457,71 @@ def run_ours(args, rank, local_rank, world):
             line['cpu_baseline']['numpy_oracle'] = dict(value=cpu_np[0], unit=UNIT, cores=cpu_np[1]['workers'],
                                                         sample=f"{cpu_np[1]['solves']} solves, dense condensed IPM in numpy (oracle/rti.py)")
     emit(line)
+
+
+ROLLOUT_TOTAL = 65536
+
+
+def measure_rollout(args, rank, local_rank, world, cfg, net, K, W_):
+    """BASELINE configs[3]: 65 536 environments sharded as contiguous blocks over the ranks (one GPU: the 8-GPU shard, 8192),
+    closed-loop rollout - device reference generation -> SQP-RTI -> statistics -> RK4 plant -> collision label against the
+    environment's depth scene - with the per-environment result records gathered by ONE all-gather inside the timed region.
+    The control step is captured once as a CUDA graph and replayed.  Called by every rank."""
+    import torch
+    from sdf_nmpc_b200 import _lib, dist as D, synth
+    from sdf_nmpc_b200.rollout import Rollout
+    dev = torch.device('cuda', local_rank)
+    total = ROLLOUT_TOTAL if world > 1 else ROLLOUT_TOTAL // 8
+    lo, hi = D.shard_range(total, rank, world)
+    enc = synth.make_encoder_net(seed=5)
+    r = Rollout(cfg, net, enc, hi - lo, first=lo, mode='rti', encode_every=0, device=dev)      # construction: outside the timed region
+    for _ in range(max(W_, 3)):
+        r.step()
+    l0 = _lib.launch_count()
+    r.capture()
+    per_step_launches = _lib.launch_count() - l0
+    r.step()
+    D.gather_records(r.records())
+    torch.cuda.synchronize()
+    D.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        r.step()
+    allrec = D.gather_records(r.records())
+    e1.record()
+    torch.cuda.synchronize()
+    D.barrier()
+    ms = D.max_over_ranks(e0.elapsed_time(e1), dev)
+    # end to end: the environment lives on the host - every step the states go down (pinned H2D) and the new states, controls
+    # and status come back (D2H)
+    n = hi - lo
+    x_pin = torch.empty(n, 10, dtype=torch.float64).pin_memory(); x_pin.copy_(r.x)
+    u_pin = torch.empty(n, 4, dtype=torch.float64).pin_memory()
+    s_pin = torch.empty(n, dtype=torch.int32).pin_memory()
+    D.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        r.x.copy_(x_pin, non_blocking=True)
+        r.step()
+        x_pin.copy_(r.x, non_blocking=True); u_pin.copy_(r.mpc.u0, non_blocking=True); s_pin.copy_(r.mpc.status, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e2e_ms = D.max_over_ranks(1e3 * (time.perf_counter() - t0), dev)
+    if rank != 0:
+        return None
+    rec = allrec.cpu().numpy()
+    return dict(value=total * K / (ms * 1e-3), unit=UNIT, ms_per_step=ms / K, gpu_launches=int(per_step_launches * K),
+                e2e=dict(value=total * K / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=n * 80, d2h_bytes_per_step=n * (80 + 32 + 4),
+                         ms_per_step=e2e_ms / K, note='per step: pinned H2D of the states, D2H of new states, controls and status; references generated on the device'),
+                status_ok=int((rec[:, 10] == 0).sum()), instances=int(rec.shape[0]), qp_iters_mean=float(rec[:, 13].mean()),
+                config=dict(workload=f'{total} environments sharded over {world} GPU(s), closed-loop Monte-Carlo rollout: device reference generation -> SQP-RTI '
+                                     '-> RK4 plant -> collision label, NCCL all-gather of the result records inside the timed region (BASELINE configs[3])',
+                            instances_per_gpu=n, N=20, nx=10, nu=4, sdf_arch='dod F5 [256,256,128,64] synthetic calibrated seed 0',
+                            parallelism=f'environments sharded x{world} as contiguous blocks, no data-path collective; one all-gather of 16-double records',
+                            l2='per-step working set of a shard exceeds the 126 MB L2 (no flush needed)', control_step='one CUDA graph per step'),
+                stats=dict(fail_steps=float(rec[:, 10].sum()), envs_with_collision=int((rec[:, 11] > 0).sum()), min_sdf_seen=float(rec[:, 12].min()),
+                           mean_goal_dist=float(rec[:, 15].mean()), kernel_launches_per_step=int(per_step_launches)))
 
 
 class _Ref:

@@ -144,8 +144,10 @@ class BatchedNmpc:
         """controller.py:50-54: camera-observation pose from the body pose at image time + latent."""
         R = self._t(W_R_Bo, (-1, 3, 3))
         p = self._t(W_p_Bo, (-1, 3))
-        BpC = self._t(np.asarray(self.cfg.sensor.B_p_C, float))
-        BRC = self._t(np.asarray(self.cfg.sensor.B_R_C, float))
+        if not hasattr(self, '_BpC'):
+            self._BpC = self._t(np.asarray(self.cfg.sensor.B_p_C, float))
+            self._BRC = self._t(np.asarray(self.cfg.sensor.B_R_C, float))
+        BpC, BRC = self._BpC, self._BRC
         # 3 x 3 products written out as broadcast sums: no library GEMM launches on this path
         self.pose[:, 0:3] = (R * BpC).sum(-1) + p
         self.pose[:, 3:12] = (R[:, :, :, None] * BRC[None]).sum(2).reshape(-1, 9)
@@ -216,7 +218,7 @@ class BatchedNmpc:
             self._timed = True
             return self.fail_count
         self.shift()
-        self._rti_iteration()
+        self._rti_iteration(timed=not torch.cuda.is_current_stream_capturing())    # an outer graph may be capturing this step
         _lib.check(self.lib.sdfnmpc_fail_count_update(_ptr(self.status), _ptr(self.fail_count), self.B, _stream()), 'fail_count_update')
         return self.fail_count
 
@@ -337,9 +339,9 @@ class BatchedNmpc:
 
     def eval(self, k):
         """controller.py:125-130: SDF value at node k of the current solution, ignoring the flag."""
-        x, _ = self.get_matrices()
+        xb = self._view(self._state_ptrs()[0], (self.B, self.N + 1, NX), torch.float64, copy=False)   # node k read in place
         R = self.pose[:, 3:12].reshape(-1, 3, 3)
-        c0 = torch.einsum('bji,bj->bi', R, x[:, k, 0:3] - self.pose[:, 0:3]).to(torch.float32)
+        c0 = torch.einsum('bji,bj->bi', R, xb[:, k, 0:3] - self.pose[:, 0:3]).to(torch.float32)
         if self._latent_dirty:
             self.sdf.set_latents(self.latent)
         d, _ = self.sdf.eval(c0, pts_per_inst=1, want_grad=False)

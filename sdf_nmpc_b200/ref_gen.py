@@ -34,6 +34,15 @@ def yaw2quat(yaw):
     return torch.stack([torch.cos(h), z, z, torch.sin(h)], -1)
 
 
+_WROW = {}
+
+
+def _unit_quat(B, dev, dt):
+    q = torch.zeros(B, 4, dtype=dt, device=dev)
+    q[:, 0] = 1.0
+    return q
+
+
 @dataclass
 class RefTraj:
     p: torch.Tensor     # [B,N+1,3]
@@ -59,7 +68,10 @@ class RefTraj:
             y = torch.cat([self.p, zero, self.v, zero, zero, self.wz[..., None], zero], -1)
             Wrow = Wp + [Wq[2]] + Wv + [Wq[0], Wq[1]] + [Ww[2]] + [Wa]
             nyN = 4
-        W = torch.tensor(Wrow, device=dev, dtype=dt).expand(B, N1, 11)
+        key = (model, tuple(Wrow), str(dev), dt)
+        if key not in _WROW:             # device constant, built once (no host-to-device copy per control step)
+            _WROW[key] = torch.tensor(Wrow, device=dev, dtype=dt)
+        W = _WROW[key].expand(B, N1, 11)
         return (y[:, :-1].contiguous(), W[:, :-1].contiguous(), y[:, -1, :nyN].contiguous(), W[:, -1, :nyN].contiguous(),
                 self.q.contiguous())
 
@@ -100,7 +112,7 @@ class BatchedRefGen:
             far = torch.linalg.norm(v[:, :2], dim=1) > float(self.cfg.ref.yaw_align_dmin)
             q = torch.where(far[:, None], yaw2quat(torch.atan2(v[:, 1], v[:, 0])), q_cur)
         else:
-            q = torch.tensor([1.0, 0, 0, 0], dtype=x0.dtype, device=x0.device).expand(x0.shape[0], 4)
+            q = _unit_quat(x0.shape[0], x0.device, x0.dtype)
         tr = self._const(x0[:, :3], q, v, wz)
         k = torch.arange(self.N + 1, dtype=x0.dtype, device=x0.device)
         tr.p = x0[:, None, :3] + v[:, None, :] * (k[None, :, None] * float(self.cfg.mpc.T) / self.N)
@@ -116,7 +128,7 @@ class BatchedRefGen:
         wps_p = torch.as_tensor(wps_p, dtype=dt, device=dev)
         B, Wn, _ = wps_p.shape
         if wps_q is None:
-            wps_q = torch.tensor([1.0, 0, 0, 0], dtype=dt, device=dev).expand(B, Wn, 4)
+            wps_q = _unit_quat(B, dev, dt)[:, None].expand(B, Wn, 4)
         wps_q = torch.as_tensor(wps_q, dtype=dt, device=dev)
         n_wps = torch.full((B,), Wn, device=dev, dtype=torch.long) if n_wps is None else torch.as_tensor(n_wps, device=dev).long()
         path_p = torch.cat([x0[:, None, :3], wps_p], 1)                       # [B,W+1,3]
@@ -154,7 +166,7 @@ class BatchedRefGen:
             qa = yaw2quat(torch.atan2(v[..., 1], v[..., 0]) + float(cfg.ref.align_yaw_offset))
             q = torch.where(far[:, None, None], qa, q0[:, None].expand(B, N + 1, 4))
         else:
-            q = torch.tensor([1.0, 0, 0, 0], dtype=dt, device=dev).expand(B, N + 1, 4)
+            q = _unit_quat(B, dev, dt)[:, None].expand(B, N + 1, 4)
         # padding: repeat the last generated (p, q) with zero velocity; empty trajectory -> last way-point
         valid = k[None, :] < n_even[:, None]
         last = (n_even - 1).clamp(min=0)

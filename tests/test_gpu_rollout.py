@@ -25,3 +25,15 @@ def test_rollout_runs_and_is_shard_invariant(mode, cuda_device):
     # shard invariance: environments [4, 12) run alone reproduce their rows (what the multi-GPU partition relies on)
     part = rollout(cfg, net, enc, 8, 6, first=4, **kw).cpu().numpy()
     assert np.array_equal(part, rec[4:])
+
+
+def test_captured_rollout_step_is_bit_identical(cuda_device):
+    """The RTI rollout step replayed as one CUDA graph gives exactly the records of the eager loop."""
+    from sdf_nmpc_b200 import synth
+    from sdf_nmpc_b200.config import Config
+    from sdf_nmpc_b200.rollout import rollout
+    cfg = Config()
+    net, enc = synth.make_sdf_net(seed=0, **synth.ARCH_B, calibrated=True), synth.make_encoder_net(seed=5)
+    a = rollout(cfg, net, enc, 16, 8, mode='rti', encode_every=0, device=cuda_device).cpu().numpy()
+    b = rollout(cfg, net, enc, 16, 8, mode='rti', encode_every=0, device=cuda_device, graph=True).cpu().numpy()
+    assert np.array_equal(a, b)
