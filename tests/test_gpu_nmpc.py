@@ -46,8 +46,13 @@ def test_rti_steps_match_oracle(flag, model, cuda_device):
         assert np.array_equal(mpc.status.cpu().numpy(), out['status']), (step, mpc.status, out['status'])
         assert int(fail.max().item()) == 0
         assert np.abs(u0 - out['u0']).max() <= U_TOL, (step, np.abs(u0 - out['u0']).max())
+        # the WHOLE open-loop solution, not only u0.  From identical iterates (step 0) every input and state of the horizon agrees
+        # within U_TOL (measured: u <= 4.0e-5, x <= 3.1e-5 over the three models).  From step 1 on each side continues from its OWN
+        # iterate (fp32 SDF evaluated at slightly different points), so the horizons drift: measured maxima after three steps are
+        # 5.3e-5 / 4.2e-5 / 2.7e-4 on u (att / att_tau / acc) and 1.1e-4 on x while u0 stays <= 5.3e-5 - bounded here at 5e-4 / 2e-4.
         x, u = mpc.get_matrices()
-        assert np.abs(x.cpu().numpy() - xo).max() <= 1e-3 and np.abs(u.cpu().numpy() - uo).max() <= 1e-3
+        eu, ex = np.abs(u.cpu().numpy() - uo).max(), np.abs(x.cpu().numpy() - xo).max()
+        assert (eu <= U_TOL and ex <= U_TOL) if step == 0 else (eu <= 5e-4 and ex <= 2e-4), (step, eu, ex)
         # active sets (node 0 carries no h rows)
         lam_h, lam_s = (t.cpu().numpy() for t in mpc.get_multipliers())
         gl = dict(lam_lbu=lam_h[:, :, :4], lam_ubu=lam_h[:, :, 4:], lam_lh=lam_s[:, 1:, :3], lam_uh=lam_s[:, 1:, 3:])
@@ -208,6 +213,25 @@ def test_full_sqp_iteration_counts_match_oracle(cuda_device):
     assert np.array_equal(it_g, it_o)
 
 
+def test_full_sqp_at_spec_tolerance(cuda_device):
+    """BASELINE configs[4] as specified: iterate until the full step is below 1e-6 (inf-norm over [du; dx]) or 100 iterations.
+    With the reference's lm_reg = 10 the Gauss-Newton iteration contracts slowly, so instances may run into the iteration
+    limit - on both sides alike: per-instance counts, convergence flags and the controls are compared with the oracle's loop."""
+    B, tol, max_iter = 4, 1e-6, 100
+    torch, rti, net, ocfg, prob, w, mpc = _setup(B, cuda_device)
+    xb, ub = rti.init_traj(prob['x0'], ocfg)
+    xo, uo, it_o, conv_o, info = rti.sqp_solve(net, xb, ub, prob, ocfg, tol=tol, max_iter=max_iter)
+    mpc.set_x0(prob['x0'])
+    u, it_g, conv_g = mpc.solve_sqp(tol=tol, max_iter=max_iter)
+    it_g, conv_g = it_g.cpu().numpy(), conv_g.cpu().numpy()
+    assert np.array_equal(conv_g, conv_o), (conv_g, conv_o)
+    steps = info['steps']
+    decisive = np.array([steps[min(it_o[b], steps.shape[0]) - 1, b] for b in range(B)])
+    # near 1e-6 the step norm sits on the noise floor of the fp32 SDF: a count may differ where the deciding step is within 30 % of tol
+    assert np.all((it_g == it_o) | (np.abs(decisive - tol) < 0.3 * tol)), (it_g, it_o, decisive)
+    assert np.abs(u.cpu().numpy() - uo[:, 0]).max() <= U_TOL
+
+
 def test_encoder_in_the_loop(cuda_device):
     """configs[4] data flow: per-step batched encoding of range images feeds set_latent, then one RTI solve."""
     from sdf_nmpc_b200 import synth
@@ -307,18 +331,27 @@ def test_full_size_properties(cuda_device):
     # permutation invariance on a shuffled sub-batch
     perm = np.random.default_rng(0).permutation(B)[:768]
     assert np.array_equal(run(perm).get_u().cpu().numpy(), u_full[perm])
-    # oracle agreement on a sample (first step only is cheap on the CPU: re-run one step from the same start)
-    samp = np.sort(np.random.default_rng(1).choice(B, 12, replace=False))
+    # oracle agreement on a sample of 256 of the 4096 instances over three closed-loop steps (the oracle's plant on its side,
+    # the device plant on the other; both sides keep their own iterates)
+    from oracle import models
+    samp = np.sort(np.random.default_rng(1).choice(B, 256, replace=False))
     ocfg = rti.default_cfg()
     prob, _ = make_problem(B, ocfg)
     ps = {k: (v[samp] if isinstance(v, np.ndarray) and v.shape[:1] == (B,) else v) for k, v in prob.items()}
     xb, ub = rti.init_traj(ps['x0'], ocfg)
-    _, _, out = rti.rti_step(net, xb, ub, ps, ocfg)
     one = BatchedNmpc(cfg, net, len(samp), cuda_device)
     one.set_sdf_flag(1.0); one.set_latent(w['latent'][samp], w['W_p_Bo'][samp], w['W_R_Bo'][samp])
     one.set_ref_arrays(w['yref'][samp], w['W'][samp], w['yrefN'][samp], w['WN'][samp], w['qd'][samp])
-    one.set_x0(w['x0'][samp]); one.solve()
-    assert np.abs(one.get_u().cpu().numpy() - out['u0']).max() <= U_TOL
+    xo, xg = ps['x0'].copy(), torch.from_numpy(ps['x0']).cuda()
+    for step in range(3):
+        p = dict(ps); p['x0'] = xo
+        xb, ub, out = rti.rti_step(net, xb, ub, p, ocfg)
+        one.set_x0(xg); one.solve()
+        assert np.array_equal(one.status.cpu().numpy(), out['status'])
+        err = np.abs(one.get_u().cpu().numpy() - out['u0']).max()
+        assert err <= (U_TOL if step == 0 else 3 * U_TOL), (step, err)      # steps 1, 2: independent closed loops drift (see above)
+        xo = models.get('att').rk4(xo, out['u0'], ocfg['dt'][0], ocfg)
+        xg = one.plant_step(xg.clone(), one.get_u(), ocfg['dt'][0])
 
 
 @pytest.mark.parametrize('variant', ['N12', 'nonuniform_dt', 'shift1', 'h_at_node0'])
