@@ -32,7 +32,13 @@ struct LinOut {
     double* C;     // [B][N+1][NH][NW] rows 0,1 = FoV; row 2 (sdf) is filled by the QP prologue
     double* hval;  // [B][N+1][NH]
     float* qpts;   // [B][N+1][3]      SDF query points Co_p_B (float32, as L4CasADi casts)
+    double* ABt;   // [B][N][16][12]   optional: the same [A B | b] in the operand layout of the tensor-core QP sweeps
+                   //                  (qp_mma.cuh): rows = 16 positions of [u; x; 1; pad], columns = 12 slots of [x; 1; pad]
 };
+
+// position of entry i of w~ = [u (4); x (10); 1; pad] in the tensor-core layout (qp_mma.cuh): x0..x7 -> 0..7, x8 / x9 / affine /
+// pad -> 8 / 10 / 12 / 14, u0..u3 -> 9 / 11 / 13 / 15
+SDF_HD constexpr int mma_wpos(int i) { return i < ATT_NU ? 9 + 2 * i : (i < ATT_NU + 8 ? i - ATT_NU : 8 + 2 * (i - ATT_NU - 8)); }
 
 template <int MODEL>
 SDF_HD void linearize_dir(const ModelConst& mc, int N, const LinIn& in, const LinOut& out, int b, int k, int dir) {
@@ -56,10 +62,22 @@ SDF_HD void linearize_dir(const ModelConst& mc, int N, const LinIn& in, const Li
         rk4_step<MODEL>(mc, xd, ud, in.dt[k], xn);
         double* AB = out.AB + ((size_t)b * N + k) * NX * NW;
         for (int i = 0; i < NX; ++i) AB[i * NW + dir] = xn[i].d;
+        double* T = out.ABt ? out.ABt + ((size_t)b * N + k) * 192 : nullptr;
+        if (T) {
+            double* row = T + mma_wpos(dir) * 12;
+            for (int i = 0; i < NX; ++i) row[i] = xn[i].d;
+            row[10] = 0.0; row[11] = 0.0;                    // affine slot, pad slot
+        }
         if (dir == 0) {
             const double* x1 = xb + NX;
             double* bd = out.bdyn + ((size_t)b * N + k) * NX;
             for (int i = 0; i < NX; ++i) bd[i] = xn[i].v - x1[i];
+            if (T) {
+                // affine column (position 12): the dynamics defect, and the 1 that carries the affine entry along; pad row zero
+                for (int i = 0; i < NX; ++i) T[12 * 12 + i] = xn[i].v - x1[i];
+                T[12 * 12 + 10] = 1.0; T[12 * 12 + 11] = 0.0;
+                for (int i = 0; i < 12; ++i) T[14 * 12 + i] = 0.0;
+            }
         }
     }
     {

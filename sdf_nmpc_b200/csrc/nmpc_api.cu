@@ -45,6 +45,7 @@ struct sdfnmpc_solver {
     int cap = 0;
     double* dt = nullptr;                     // [N] device
     double *xbar = nullptr, *ubar = nullptr;  // warm start
+    double *ABt = nullptr;                    // [B][N][16][12] [A B | b] in the tensor-core operand layout
     double *AB = nullptr, *bdyn = nullptr, *J = nullptr, *yres = nullptr, *C = nullptr, *hval = nullptr;
     float *qpts = nullptr, *sdf_d = nullptr, *sdf_g = nullptr;
     double *work = nullptr, *lam_hard = nullptr, *lam_soft = nullptr, *qp_res = nullptr;
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(128, LIN_MIN_BLOCKS) nmpc_linearize_kernel(Mod
 }
 
 struct QpBatch {
-    const double *AB, *bdyn, *J, *yres, *W, *WN, *dt, *pose, *x0, *flag;
+    const double *AB, *ABt, *bdyn, *J, *yres, *W, *WN, *dt, *pose, *x0, *flag;
     double *C, *hval, *xbar, *ubar, *work, *u0, *lam_hard, *lam_soft;
     const float *sdf_d, *sdf_g;
     int *status, *iters;
@@ -117,6 +118,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32, QP_MIN_CTAS) nmpc_qp_kernel(
     P.lm = scs.lm; P.tol = scs.tol; P.tol_res = scs.tol_res; P.max_df = q.max_df; P.flag = q.flag[b];
     P.sdf_cost_w = scs.sdf_cost_w;
     P.AB = q.AB + (size_t)b * N * NX * NW;
+    P.ABt = q.ABt ? q.ABt + (size_t)b * N * 192 : nullptr;
     P.bdyn = q.bdyn + (size_t)b * N * NX;
     P.J = q.J + (size_t)b * (N + 1) * NY * NW;
     P.yres = q.yres + (size_t)b * (N + 1) * NY;
@@ -240,6 +242,9 @@ extern "C" int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver
     alloc((void**)&h->xbar, B * N1 * NX * sizeof(double));
     alloc((void**)&h->ubar, B * N * NU * sizeof(double));
     alloc((void**)&h->AB, B * N * NX * NW * sizeof(double));
+#if !defined(SDFNMPC_QP_SCALAR)
+    alloc((void**)&h->ABt, B * N * 192 * sizeof(double));
+#endif
     alloc((void**)&h->bdyn, B * N * NX * sizeof(double));
     alloc((void**)&h->J, B * N1 * NY * NW * sizeof(double));
     alloc((void**)&h->yres, B * N1 * NY * sizeof(double));
@@ -280,7 +285,7 @@ extern "C" int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver
 
 extern "C" int sdfnmpc_solver_destroy(sdfnmpc_solver_t h) {
     if (!h) return 0;
-    void* ptrs[] = {h->dt, h->xbar, h->ubar, h->AB, h->bdyn, h->J, h->yres, h->C, h->hval, h->qpts, h->sdf_d, h->sdf_g,
+    void* ptrs[] = {h->dt, h->xbar, h->ubar, h->ABt, h->AB, h->bdyn, h->J, h->yres, h->C, h->hval, h->qpts, h->sdf_d, h->sdf_g,
                     h->work, h->lam_hard, h->lam_soft, h->qp_res, h->qp_counter};
     for (void* p : ptrs) cudaFree(p);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
@@ -325,7 +330,7 @@ extern "C" int sdfnmpc_solver_rti_step(sdfnmpc_solver_t h, int32_t B, const doub
     cudaEvent_t* ev = tm ? &h->ev[(size_t)h->ev_steps * 4] : nullptr;
     if (tm) cudaEventRecord(ev[0], st);
     LinIn in{h->xbar, h->ubar, yref, yrefN, qd, pose, flag, h->dt, h->sc.nyN, x0};
-    LinOut lo{h->AB, h->bdyn, h->J, h->yres, h->C, h->hval, h->qpts};
+    LinOut lo{h->AB, h->bdyn, h->J, h->yres, h->C, h->hval, h->qpts, h->ABt};
     const long long total = (long long)B * (N + 1) * NW;
     const unsigned lin_grid = (unsigned)((total + 127) / 128);
     if (h->sc.model == MODEL_ATT) nmpc_linearize_kernel<MODEL_ATT><<<lin_grid, 128, 0, st>>>(h->sc.mc, N, B, in, lo);
@@ -337,7 +342,7 @@ extern "C" int sdfnmpc_solver_rti_step(sdfnmpc_solver_t h, int32_t B, const doub
     if (int rc = sdfnmpc_sdf_eval(h->sdf, h->qpts, nullptr, N + 1, (int64_t)B * (N + 1), h->sdf_d, h->sdf_g, stream)) return rc;
     if (tm) cudaEventRecord(ev[2], st);
     QpBatch q;
-    q.AB = h->AB; q.bdyn = h->bdyn; q.J = h->J; q.yres = h->yres; q.W = W; q.WN = WN; q.dt = h->dt; q.pose = pose;
+    q.AB = h->AB; q.ABt = h->ABt; q.bdyn = h->bdyn; q.J = h->J; q.yres = h->yres; q.W = W; q.WN = WN; q.dt = h->dt; q.pose = pose;
     q.x0 = x0; q.flag = flag; q.C = h->C; q.hval = h->hval; q.xbar = h->xbar; q.ubar = h->ubar; q.work = h->work;
     q.u0 = u0; q.lam_hard = h->lam_hard; q.lam_soft = h->lam_soft; q.sdf_d = h->sdf_d; q.sdf_g = h->sdf_g;
     q.status = status; q.iters = qp_iters; q.work_per_inst = h->work_per_inst; q.max_df = (double)h->sdf->net.max_df;

@@ -79,6 +79,7 @@ struct QpProb {            // all pointers are offset to ONE instance
     double lm, tol, tol_res, max_df, flag;
     double sdf_cost_w;     // weight of the optional stage cost row (1 - 0.5 sdf)^4 (flags.sdf_cost, gen_model.py:65-66); 0 = off
     const double* AB;      // [N][NX][NW]
+    const double* ABt;     // [N][16][12] the same in the tensor-core operand layout (qp_mma.cuh); unused by the scalar solver
     const double* bdyn;    // [N][NX]
     const double* J;       // [N+1][NY][NW]
     const double* yres;    // [N+1][NY]

@@ -34,7 +34,7 @@ struct QpMmaShape {
     static constexpr int NPROD = 2 * NU + 4 * NH;
     static constexpr int NROW = 4 * NU + 8 * NH;    // parked doubles per node: (t, lam) of 8 hard rows, (t, lam, s, mu) of 6 soft rows
     static constexpr int HP = 256;                  // H~_k, 16 x 16 by position (row-major)
-    static constexpr int ABT = 192;                 // T_k transposed: [16 positions][12 slots]
+    static constexpr int ABT = 192;                 // T_k transposed: [16 positions][12 slots] - written by the linearisation kernel (LinOut::ABt)
     static constexpr int KF = 64;                   // K~_k as fragments: [tile][lane] = K~[q][position 8 tile + g]
     static constexpr int LF = 16;                   // LDL' of Muu_k: inverse pivots [4] | unit lower factor by columns [6]
     static constexpr int GP = 16;                   // cost gradient by position
@@ -43,7 +43,7 @@ struct QpMmaShape {
     // doubles of global scratch per warp slot
     SDF_HD static size_t work_doubles(int N) {
         const size_t n1 = (size_t)N + 1;
-        return n1 * HP + (size_t)N * ABT + (size_t)N * LF + n1 * GP + ((n1 * NH * 3 + 1) & ~(size_t)1) + 2 * (size_t)NROW * kp(N);
+        return n1 * HP + (size_t)N * LF + n1 * GP + ((n1 * NH * 3 + 1) & ~(size_t)1) + 2 * (size_t)NROW * kp(N);
     }
     // doubles of shared memory per warp: iterate, step, elimination terms (+ a zero row), second-order products, corrector
     // feed-forward, costate ping-pong of the verification, and the gains K~_k of every stage (written by the factorising sweep,
@@ -112,7 +112,7 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
     auto take = [&](size_t n) { double* r = p; p += n; return r; };
     const size_t n1 = (size_t)N + 1;
     double* Hp = take(n1 * S::HP);
-    double* ABt = take((size_t)N * S::ABT);
+    const double* ABt = P.ABt;                    // [A B | b]~ by (position, slot), straight from the linearisation kernel
     double* Lf = take((size_t)N * S::LF);
     double* gpos = take(n1 * S::GP);
     double* cpos = take((n1 * NH * 3 + 1) & ~(size_t)1);
@@ -164,18 +164,11 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
         for (int r = 0; r < NH; ++r)
             for (int c = 0; c < 3; ++c) cpos[(k * NH + r) * 3 + c] = P.C[((size_t)k * NH + r) * NW + HC0 + c];
     }
-    // T_k: zero everything the scatter below does not write (pads, affine row), then [A B] by (position, slot)
-    QM_LANES(e, N * S::ABT) __stcg(ABt + e, 0.0);
+    // T_k = [A B | b; 0 1]~ by (position, slot) comes ready-made from the linearisation kernel.  Node 0 is linearised at the measured
+    // state (ocp.py:161), so dx_0 = x0 - xbar_0 = 0: the iterate starts at w = 0 and the dynamics defect IS the affine column.
     QM_LANES(e, (N + 1) * S::GP) __stcg(gpos + e, 0.0);
     QM_LANES(e, NW * KP) { Wsm[e] = 0.0; dW[e] = 0.0; }
     QM_LANES(e, KP) corr[NCORR * KP + e] = 0.0;
-    L.sync();
-    QM_LANES(e, N * NX * NW) {
-        const int k = e / (NX * NW), r = e - k * (NX * NW), i = r / NW, j = r - i * NW;
-        __stcg(ABt + (size_t)k * S::ABT + S::wpos(j) * 12 + i, P.AB[e]);
-    }
-    QM_LANES(k, N) __stcg(ABt + (size_t)k * S::ABT + 12 * 12 + 10, 1.0);   // affine row: [0 .. 0 1]
-    QM_LANES(i, NX) Wsm[(NU + i) * KP] = P.x0[i] - P.xbar[i];       // dx_0 (0 when node 0 was linearised at x0)
     QPT(16, true)
     // H~_k = J~' (W dt) J~ + lm dt I with J~ = [J | y - yref]: 12 DMMA per node straight from the linearisation's J; the affine
     // column comes out as the cost gradient.
@@ -183,7 +176,7 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
     // warp-uniform trip count.
     L.sync();
     {
-        struct HOps { double v[3][2], a[3][2]; };          // J~ entries and the same entries times their row weight
+        struct HOps { double v[3][2], w[3]; };             // J~ entries and their row weights
         // the lane's operand entries: J~[row 4 s + q][position 8 t + g]
         const int wi0 = widx(g_), wi1 = widx(8 + g_);
         auto ld_ops = [&](int k) {
@@ -192,19 +185,15 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
             HOps o;
             const double* Jk = P.J + (size_t)k * NY * NW;
             const double* yk = P.yres + (size_t)k * NY;
-            const double sck = scale(k);
-            const double m1 = wi1 == 15 ? 0.0 : 1.0;
 #pragma unroll
             for (int s = 0; s < 3; ++s) {
                 const int r = 4 * s + q_;
                 const int rc = r < NY ? r : NY - 1;
-                const double w = r < NY ? wrow(k, rc) * sck : 0.0;
+                // loads only: any arithmetic on the loaded values here would wait for them and undo the pipelining
+                o.w[s] = wrow(k, rc);
                 o.v[s][0] = Jk[rc * NW + wi0];
                 const double* src = wi1 < NW ? Jk + rc * NW + wi1 : yk + rc;
-                o.v[s][1] = *src * m1;
-                // the weighted copies are formed HERE, a pipeline stage before the products that consume them
-                o.a[s][0] = o.v[s][0] * w;
-                o.a[s][1] = o.v[s][1] * w;
+                o.v[s][1] = *src;
             }
             return o;
         };
@@ -234,12 +223,21 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
                 }
                 if (e & 1) H[e >> 2][(e >> 1) & 1].y = v; else H[e >> 2][(e >> 1) & 1].x = v;
             }
+            // rows past NY carry weight 0, the pad position (15 in w~) is masked
+            double a[3][2], v1[3][2];
+            const double sck = scale(k), m1 = wi1 == 15 ? 0.0 : 1.0;
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                const double w = (4 * s + q_ < NY) ? o.w[s] * sck : 0.0;
+                v1[s][0] = o.v[s][0]; v1[s][1] = o.v[s][1] * m1;
+                a[s][0] = v1[s][0] * w; a[s][1] = v1[s][1] * w;
+            }
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
                 for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-                    for (int s = 0; s < 3; ++s) dmma(H[mt][nt], o.a[s][mt], o.v[s][nt]);
+                    for (int s = 0; s < 3; ++s) dmma(H[mt][nt], a[s][mt], v1[s][nt]);
             double* hb = Hp + (size_t)k * S::HP + g_ * 16 + 2 * q_;
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
@@ -249,7 +247,7 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
             // cost gradient (affine column, position 12 = tile 1, q 2, register x)
             if (q_ == 2) { __stcg(gpos + k * S::GP + g_, H[0][1].x); __stcg(gpos + k * S::GP + 8 + g_, H[1][1].x); }
         };
-        pipelined_stages<2, HOps>(N + 1, ld_ops, stage);
+        pipelined_stages<4, HOps>(N + 1, ld_ops, stage);
     }
     L.sync();
 
@@ -326,16 +324,10 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
         // rv0_k = H_k w_k + g_k - sum lam_i gvec_i -> affine row / column of H~_k (inputs, then states: no dynamically
         // indexed register arrays)
         double* hk = Hp + (size_t)kk * S::HP;
-        auto h_w0 = [&](int pi) {           // H_0[., x] dx_0
-            double s = 0.0;
-            for (int j = NU; j < NW; ++j) s += __ldcg(hk + pi * 16 + S::wpos(j)) * Wsm[j * KP];
-            return s;
-        };
 #pragma unroll
         for (int i = 0; i < NU; ++i) {
             const int pi = S::wpos(i);
             double s = __ldcg(gpos + kk * S::GP + pi);
-            if (kk == 0) s += h_w0(pi);
             if (kk < N) s -= lb[i] - lb[NU + i];
             if (kk == N) s = 0.0;
             __stcg(hk + pi * 16 + 12, s); __stcg(hk + 12 * 16 + pi, s);
@@ -351,17 +343,10 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
             __stcg(hk + pi * 16 + 12, s); __stcg(hk + 12 * 16 + pi, s);
             res_v0 = fmax(res_v0, fabs(s));
         }
-        // rd0_k (k >= 1) = AB_{k-1} w_{k-1} + b_{k-1} - w_x,k -> affine column of T_{k-1}
+        // the dynamics defect b_{k-1} (affine column of T_{k-1}) only enters the residual norm here
         if (kk >= 1) {
-            double* tk = ABt + (size_t)(kk - 1) * S::ABT + 12 * 12;
 #pragma unroll 1
-            for (int i = 0; i < NX; ++i) {
-                double s = P.bdyn[(kk - 1) * NX + i];
-                if (kk == 1)
-                    for (int j = NU; j < NW; ++j) s += P.AB[(size_t)i * NW + j] * Wsm[j * KP];
-                __stcg(tk + i, s);
-                res_v0 = fmax(res_v0, fabs(s));
-            }
+            for (int i = 0; i < NX; ++i) res_v0 = fmax(res_v0, fabs(P.bdyn[(kk - 1) * NX + i]));
         }
     }
     res_v0 = L.max(res_v0);
@@ -882,35 +867,74 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
             for (int r = 0; r < NH; ++r) corr[(NU + r) * KP + kk] = kk >= k0 ? ls[r] - ls[NH + r] : 0.0;
         }
         L.sync();
-        for (int kk = N; kk >= 0 && status != 4; --kk) {
-            const double* pin = pp + ((N - kk) & 1) * 16;        // costate of node kk + 1
-            double* pout = pp + (((N - kk) & 1) ^ 1) * 16;       // costate of node kk
-            const double* hk = Hp + (size_t)kk * S::HP;
-            if (lane < NW && !(kk == N && lane < NU)) {
-                const int i = lane, pi = S::wpos(i);
-                double s = __ldcg(gpos + kk * S::GP + pi);
+        QPT(21, true)
+        // pass 1, every node on its own (no recursion: the loads of consecutive nodes overlap): q_k = g_k + H_k w_k - (multiplier
+        // terms) into dW (free after the last iteration), and the dynamics residuals
+        if (status != 4) {
+            // nodes are taken VC at a time with all their loads issued before the first use: one memory round trip per chunk
+            // (node by node the loop paid a loaded L2 round trip, ~3.5 k cycles, 21 times: 75 k cycles per solve; 7 at a time needs 210 registers and spills)
+            constexpr int VC = 3;
+            const bool row_lane = lane < NW, dyn_lane = lane >= 16 && lane < 16 + NX;
+            const int vi = row_lane ? lane : (dyn_lane ? lane - 16 : 0), vpi = S::wpos(row_lane ? lane : 0);
+            for (int k0_ = 0; k0_ <= N; k0_ += VC) {
+                double hv[VC][NW], gv[VC];
 #pragma unroll
-                for (int j = 0; j < NW; ++j) s += __ldcg(hk + pi * 16 + S::wpos(j)) * Wsm[j * KP + kk];
-                if (i < NU) s -= corr[i * KP + kk];
-                if (i >= HC0 && i < HC0 + 3)
-                    for (int r = 0; r < NH; ++r) s -= corr[(NU + r) * KP + kk] * c_pos(kk, r, i - HC0);
-                if (kk < N) {
-                    const double* tk = ABt + (size_t)kk * S::ABT + pi * 12;
+                for (int t = 0; t < VC; ++t) {
+                    const int kk = k0_ + t <= N ? k0_ + t : N, kt = kk < N ? kk : (N > 0 ? N - 1 : 0);
+                    // row lanes: row of H~_kk and the gradient entry; dynamics lanes: row of [A B]_kk and the defect
+                    const double* src = row_lane ? Hp + (size_t)kk * S::HP + vpi * 16 : ABt + (size_t)kt * S::ABT + vi;
+                    const int stride = row_lane ? 1 : 12;
 #pragma unroll
-                    for (int l = 0; l < NX; ++l) s += __ldcg(tk + l) * pin[l];
+                    for (int j = 0; j < NW; ++j) hv[t][j] = __ldcg(src + S::wpos(j) * stride);
+                    gv[t] = row_lane ? __ldcg(gpos + kk * S::GP + vpi) : P.bdyn[kt * NX + vi];
                 }
-                if (i < NU) res_true = fmax(res_true, fabs(s));      // input stationarity
-                else pout[i - NU] = s;                               // defines the costate of node kk (x-stationarity == 0)
-            }
-            if (kk < N && lane >= 16 && lane < 16 + NX) {
-                const int i = lane - 16;
-                double s = P.bdyn[kk * NX + i] - Wsm[(NU + i) * KP + kk + 1];
-                const double* tk = ABt + (size_t)kk * S::ABT + i;
 #pragma unroll
-                for (int j = 0; j < NW; ++j) s += __ldcg(tk + S::wpos(j) * 12) * Wsm[j * KP + kk];
-                res_true = fmax(res_true, fabs(s));
+                for (int t = 0; t < VC; ++t) {
+                    const int kk = k0_ + t;
+                    if (kk > N) break;
+                    double s = gv[t];
+#pragma unroll
+                    for (int j = 0; j < NW; ++j) s += hv[t][j] * Wsm[j * KP + kk];
+                    if (row_lane) {
+                        if (vi < NU) s -= corr[vi * KP + kk];
+                        if (vi >= HC0 && vi < HC0 + 3)
+                            for (int r = 0; r < NH; ++r) s -= corr[(NU + r) * KP + kk] * c_pos(kk, r, vi - HC0);
+                        dW[vi * KP + kk] = s;
+                    } else if (dyn_lane && kk < N) {
+                        res_true = fmax(res_true, fabs(s - Wsm[(NU + vi) * KP + kk + 1]));
+                    }
+                }
             }
             L.sync();
+            QPT(22, true)
+            // pass 2, the costate recursion: stationarity of node kk = q_kk + [A B]_kk' costate_{kk+1}; its state rows DEFINE the
+            // costate of node kk, its input rows are residuals.  The column of [A B] a lane needs is fetched one node ahead.
+            double tcol[NX], tnext[NX];
+            const int pi = lane < NW ? S::wpos(lane) : 0;
+#pragma unroll
+            for (int l = 0; l < NX; ++l) tnext[l] = N >= 1 ? __ldcg(ABt + (size_t)(N - 1) * S::ABT + pi * 12 + l) : 0.0;
+            for (int kk = N; kk >= 0; --kk) {
+                const double* pin = pp + ((N - kk) & 1) * 16;        // costate of node kk + 1
+                double* pout = pp + (((N - kk) & 1) ^ 1) * 16;       // costate of node kk
+                if (kk < N) {
+#pragma unroll
+                    for (int l = 0; l < NX; ++l) tcol[l] = tnext[l];
+                    if (kk >= 1) {
+#pragma unroll
+                        for (int l = 0; l < NX; ++l) tnext[l] = __ldcg(ABt + (size_t)(kk - 1) * S::ABT + pi * 12 + l);
+                    }
+                }
+                if (lane < NW && !(kk == N && lane < NU)) {
+                    double s = dW[lane * KP + kk];
+                    if (kk < N) {
+#pragma unroll
+                        for (int l = 0; l < NX; ++l) s += tcol[l] * pin[l];
+                    }
+                    if (lane < NU) res_true = fmax(res_true, fabs(s));      // input stationarity
+                    else pout[lane - NU] = s;                               // costate of node kk (x-stationarity == 0)
+                }
+                L.sync();
+            }
         }
         res_true = L.max(res_true);
         if (status == 0 && !(res_true <= 100.0 * P.tol_res)) status = 3;    // tracked residual was wrong: report, do not hide
@@ -920,9 +944,24 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
     QM_LANES(e, (N + 1) * NW) { const int kk = e / NW, i = e - kk * NW; step_inf = fmax(step_inf, fabs(Wsm[i * KP + kk])); }
     step_inf = L.max(step_inf);
     // ---- full SQP step and outputs ----
+    QPT(19, true)
     if (status != 4) {
-        QM_LANES(e, (N + 1) * NX) { const int kk = e / NX, i = e - kk * NX; P.xbar[e] += Wsm[(NU + i) * KP + kk]; }
-        QM_LANES(e, N * NU) { const int kk = e / NU, j = e - kk * NU; P.ubar[e] += Wsm[j * KP + kk]; }
+        // every lane's loads of the iterate go out together (a read-modify-write per trip would pay the memory latency per trip)
+        constexpr int XT = NFIX > 0 ? ((NFIX + 1) * NX + 31) / 32 : 1, UT = NFIX > 0 ? (NFIX * NU + 31) / 32 : 1;
+        if (NFIX > 0) {
+            double xv[XT], uv[UT];
+#pragma unroll
+            for (int t = 0; t < XT; ++t) { const int e = t * 32 + lane; xv[t] = e < (N + 1) * NX ? P.xbar[e] : 0.0; }
+#pragma unroll
+            for (int t = 0; t < UT; ++t) { const int e = t * 32 + lane; uv[t] = e < N * NU ? P.ubar[e] : 0.0; }
+#pragma unroll
+            for (int t = 0; t < XT; ++t) { const int e = t * 32 + lane; if (e < (N + 1) * NX) { const int kk = e / NX, i = e - kk * NX; P.xbar[e] = xv[t] + Wsm[(NU + i) * KP + kk]; } }
+#pragma unroll
+            for (int t = 0; t < UT; ++t) { const int e = t * 32 + lane; if (e < N * NU) { const int kk = e / NU, j = e - kk * NU; P.ubar[e] = uv[t] + Wsm[j * KP + kk]; } }
+        } else {
+            QM_LANES(e, (N + 1) * NX) { const int kk = e / NX, i = e - kk * NX; P.xbar[e] += Wsm[(NU + i) * KP + kk]; }
+            QM_LANES(e, N * NU) { const int kk = e / NU, j = e - kk * NU; P.ubar[e] += Wsm[j * KP + kk]; }
+        }
     }
     L.sync();
     QM_LANES(j, NU) P.u0[j] = P.ubar[j];
@@ -933,7 +972,7 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
         if (P.lam_soft)
             for (int a = 0; a < 2 * NH; ++a) P.lam_soft[kk * 2 * NH + a] = kk >= k0 ? ls[a] : 0.0;
     }
-    QPT(19, true)
+    QPT(20, true)
     if (lane == 0) {
         *P.status = status;
         *P.iters = it;

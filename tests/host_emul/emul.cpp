@@ -20,7 +20,7 @@ extern "C" void emul_linearize(int model, int nyN, int B, int N, const double* m
     mc.cam_off[0] = mcv[6]; mc.cam_off[1] = mcv[7]; mc.cam_off[2] = mcv[8];
     mc.ax = mcv[9]; mc.ay = mcv[10]; mc.az = mcv[11]; mc.tau_roll = mcv[12]; mc.tau_pitch = mcv[13];
     LinIn in{xbar, ubar, yref, yrefN, qd, pose, flag, dt, nyN, x0};
-    LinOut out{AB, bdyn, J, yres, C, hval, qpts};
+    LinOut out{AB, bdyn, J, yres, C, hval, qpts, nullptr};
     for (int b = 0; b < B; ++b)
         for (int k = 0; k <= N; ++k)
             for (int d = 0; d < ATT_NW; ++d) {
@@ -47,6 +47,7 @@ extern "C" void emul_qp(int B, int N, int k0, int max_iter, int nyN, double sdf_
         P.lm = lm; P.tol = tol; P.tol_res = tol_res; P.max_df = max_df; P.flag = flag[b];
         P.sdf_cost_w = sdf_cost_w;
         P.AB = AB + (size_t)b * N * NX * NW;
+        P.ABt = nullptr;
         P.bdyn = bdyn + (size_t)b * N * NX;
         P.J = J + (size_t)b * (N + 1) * NY * NW;
         P.yres = yres + (size_t)b * (N + 1) * NY;

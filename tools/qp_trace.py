@@ -6,7 +6,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 NAMES = {0: 'elim0', 1: 'factor', 2: 'rollout0', 3: 'steps0', 8: 'elim1', 9: 'corr sweep', 10: 'rollout1', 11: 'steps1',
-         16: 'prologue operands', 17: 'hessian build', 18: 'initial point', 19: 'verify+outputs'}
+         16: 'prologue operands', 17: 'hessian build', 18: 'initial point', 19: 'verify pass 2', 20: 'outputs', 21: 'verify multipliers', 22: 'verify pass 1'}
 for B in sys.argv[1:] or ['148', '1184', '4096']:
     f = os.path.join(ROOT, 'gpurun_out', f'qpt_{B}.txt')
     env = dict(os.environ, SDFNMPC_QP_TRACE_FILE=f, SDFNMPC_LIB=os.path.join(ROOT, 'sdf_nmpc_b200/lib/variants/lib_trace.so'))
