@@ -57,6 +57,19 @@ struct QpMmaShape {
 // halves, the compiler (which assumes they re-join) had removed the __syncwarp() that followed, and every mma.sync behind it
 // multiplied half-warp fragments only (found with __activemask() probes; -DQM_ASSERT_CONVERGED keeps them as traps).
 #define QM_LANES(v, n) for (int v##_0 = 0; v##_0 < (n); v##_0 += 32) if (const int v = v##_0 + lane; v < (n))
+// register-pipeline depths of the corrector's sweep and the roll-outs (A/B knobs; tools/qp_ab.py)
+#ifndef QM_D_BACK
+#define QM_D_BACK 2
+#endif
+#ifndef QM_D_ROLL
+#define QM_D_ROLL 2
+#endif
+#ifndef QM_D_FAC
+#define QM_D_FAC 2
+#endif
+#ifndef QM_D_HES
+#define QM_D_HES 2
+#endif
 #if defined(QM_ASSERT_CONVERGED)
 #define QM_CONVERGED() { if (__activemask() != 0xffffffffu) __trap(); }
 #else
@@ -247,7 +260,7 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
             // cost gradient (affine column, position 12 = tile 1, q 2, register x)
             if (q_ == 2) { __stcg(gpos + k * S::GP + g_, H[0][1].x); __stcg(gpos + k * S::GP + 8 + g_, H[1][1].x); }
         };
-        pipelined_stages<4, HOps>(N + 1, ld_ops, stage);
+        pipelined_stages<QM_D_HES, HOps>(N + 1, ld_ops, stage);
     }
     L.sync();
 
@@ -616,7 +629,7 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
                         __stcg(lo + 2, make_double2(l10, l20)); __stcg(lo + 3, make_double2(l30, l21)); __stcg(lo + 4, make_double2(l31, l32));
                     }
                 };
-                pipelined_stages<2, FacOps>(N, ld_ops, stage);
+                pipelined_stages<QM_D_FAC, FacOps>(N, ld_ops, stage);
                 if (!ok) status = 4;
             } else {
                 // =========== corrector: same matrix, right-hand side = change of the elimination terms, no dynamics residual ===========
@@ -655,7 +668,7 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
                     bC = __shfl_sync(FULL, R[1].x, 8 * q_);
                     if (q_ >= 2) bC = 0.0;
                 };
-                pipelined_stages<4, BackOps>(N, ld_ops, stage);
+                pipelined_stages<QM_D_BACK, BackOps>(N, ld_ops, stage);
                 L.sync();
                 // feed-forward of every stage: -Muu^-1 r~_u with the factor the predictor's sweep left (lane = stage)
                 QM_LANES(kk, N) {
@@ -746,7 +759,7 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
                     bB = __shfl_sync(FULL, Xn[0].x, 8 * q_ + 4);
                     bC = __shfl_sync(FULL, Xn[1].x, 4 * q_);
                 };
-                pipelined_stages<4, RollOps>(N, ld_ops, stage);
+                pipelined_stages<QM_D_ROLL, RollOps>(N, ld_ops, stage);
             }
             L.sync();
             QPT(pass * 8 + 2, it == 2)
