@@ -438,8 +438,15 @@ def run_ours(args, rank, local_rank, world):
                     status_ok=roll['status_ok'], instances=roll['instances'], qp_iters_mean=roll['qp_iters_mean'])
         line['config'] = roll['config']
         line['rollout'] = roll['stats']
+        extra['scaling_note'] = ('the N = 1 line of this bench is configs[2] (4096 solver instances per GPU, "weak"); this line is configs[3] '
+                                 '(65536 environments over all ranks, "strong").  Same-workload references: extra.solver_only (configs[2] at this N, '
+                                 'per-GPU work fixed) and the N = 1 line\'s extra.rollout_configs3_shard (one 8192-environment shard of configs[3] = '
+                                 'the per-rank share at N = 8, on one GPU)')
     elif roll is not None:
         extra['rollout_configs3_shard'] = roll
+        extra['scaling_note'] = ('at N > 1 the headline of this bench becomes configs[3] (65536 environments sharded over the ranks, full rollout '
+                                 'step); extra.rollout_configs3_shard is one 8192-environment shard of it on this GPU (the per-rank share at N = 8), so '
+                                 'value(N = 8) / (8 x that) is the efficiency on that workload; the configs[2] figure at N > 1 is extra.solver_only')
     if extra:
         line['extra'] = extra
     if sweep:

@@ -2,7 +2,7 @@
 
 Same tables as the reference's ``PositionEmbedding`` registers as the buffer
 ``dirs`` (``sdf_nmpc/utils/embeddings.py:24-100``): unit columns, float32,
-shape [3, D].  When a real TorchScript SDF is packed (``weights.pack_sdf``) the
+shape [3, D].  When a real TorchScript SDF is loaded (``weights.sdf_from_module``) the
 buffer is read from the module instead; this table is for synthetic networks.
 """
 import itertools
