@@ -255,6 +255,15 @@ extern "C" int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver
     alloc((void**)&h->sdf_g, B * N1 * 3 * sizeof(float));
     // the QP kernel runs as persistent warps: as many as fit the device at once, each owning one block of scratch
     h->qp_smem = (size_t)QP_WARPS * Shape::smem_doubles(d->N) * sizeof(double);
+#if defined(QP_CARVEOUT)
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(nmpc_qp_kernel<20>, cudaFuncAttributePreferredSharedMemoryCarveout, QP_CARVEOUT);
+#endif
+#if defined(QP_MAX_PER_SM)
+    {   // development: unused shared memory so that at most QP_MAX_PER_SM CTAs are resident per SM (tools/qp_ab.py)
+        const size_t want = (size_t)(227 * 1024) / QP_MAX_PER_SM - 1280;
+        if (h->qp_smem < want) h->qp_smem = want;
+    }
+#endif
     if (e == cudaSuccess) e = cudaFuncSetAttribute(nmpc_qp_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qp_smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(nmpc_qp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qp_smem);
     {
@@ -266,6 +275,9 @@ extern "C" int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver
             else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nmpc_qp_kernel<0>, QP_WARPS * 32, h->qp_smem);
         }
         if (e == cudaSuccess && per_sm < 1) e = cudaErrorLaunchOutOfResources;
+#if defined(QP_SLOTS_PER_SM)
+        if (per_sm > QP_SLOTS_PER_SM) per_sm = QP_SLOTS_PER_SM;      // development: fewer resident warps without touching the carve-out
+#endif
         const long long slots = (long long)sms * per_sm * QP_WARPS;
         h->qp_slots = (int)(slots < (long long)B ? slots : (long long)((B + QP_WARPS - 1) / QP_WARPS * QP_WARPS));
     }

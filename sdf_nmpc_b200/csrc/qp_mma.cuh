@@ -38,17 +38,22 @@ struct QpMmaShape {
     static constexpr int KF = 64;                   // K~_k as fragments: [tile][lane] = K~[q][position 8 tile + g]
     static constexpr int LF = 16;                   // LDL' of Muu_k: inverse pivots [4] | unit lower factor by columns [6]
     static constexpr int GP = 16;                   // cost gradient by position
+#if defined(QM_KF_GLOBAL)
+    static constexpr bool KF_SHARED = false;        // gains in the slot's global scratch (L2): 12.8 KB of shared memory per warp
+#else
+    static constexpr bool KF_SHARED = true;         // gains in shared memory: 22.8 KB per warp
+#endif
     SDF_HD static int kp(int N) { return N + 2; }
     SDF_HD static constexpr int wpos(int i) { return i < NU ? 9 + 2 * i : (i < NU + 8 ? i - NU : 8 + 2 * (i - NU - 8)); }
     // doubles of global scratch per warp slot
     SDF_HD static size_t work_doubles(int N) {
         const size_t n1 = (size_t)N + 1;
-        return n1 * HP + (size_t)N * LF + n1 * GP + ((n1 * NH * 3 + 1) & ~(size_t)1) + 2 * (size_t)NROW * kp(N);
+        return n1 * HP + (size_t)N * LF + n1 * GP + ((n1 * NH * 3 + 1) & ~(size_t)1) + 2 * (size_t)NROW * kp(N) + (KF_SHARED ? 0 : (size_t)N * KF);
     }
     // doubles of shared memory per warp: iterate, step, elimination terms (+ a zero row), second-order products, corrector
     // feed-forward, costate ping-pong of the verification, and the gains K~_k of every stage (written by the factorising sweep,
     // read by three more sweeps per iteration: 10 KB that would otherwise cycle through L2)
-    SDF_HD static int smem_doubles(int N) { return (2 * NW + NCORR + 1 + NPROD + NU) * kp(N) + 2 * 16 + N * KF; }
+    SDF_HD static int smem_doubles(int N) { return (2 * NW + NCORR + 1 + NPROD + NU) * kp(N) + 2 * 16 + (KF_SHARED ? N * KF : 0); }
 };
 
 // Lane-strided loops in this file run a WARP-UNIFORM number of trips with the tail predicated (`QM_LANES(e, n)`): a loop whose
@@ -139,7 +144,15 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
     double* prod = corr + (NCORR + 1) * KP;       // [NPROD][KP] affine second-order products
     double* ffd = prod + NPROD * KP;              // [NU][KP]   input residual / feed-forward of the corrector's sweep
     double* pp = ffd + NU * KP;                   // [2][16]    costate ping-pong of the verification
-    double* Kf = pp + 2 * 16;                     // [N][2][32] gains as fragments
+    double* Kf;                                   // [N][2][32] gains as fragments
+    if constexpr (S::KF_SHARED) Kf = pp + 2 * 16; else Kf = take((size_t)N * S::KF);
+#if defined(QM_KF_GLOBAL) && !defined(QM_KF_L1)
+#define QM_KLD(p_) __ldcg(p_)
+#define QM_KST(p_, v_) __stcg(p_, v_)
+#else
+#define QM_KLD(p_) (*(p_))
+#define QM_KST(p_, v_) (*(p_) = (v_))
+#endif
 
     auto scale = [&](int k) { return k < N ? P.dt[k] : 1.0; };
     auto wrow = [&](int k, int r) { return k < N ? P.W[k * NY + r] : (r < P.nyN ? P.WN[r] : 0.0); };
@@ -621,8 +634,8 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
                             dmma(Pf[ri][rj], mxu[ri], kq[rj]);
                         }
                     // for the roll-outs and the corrector: gains (with the feed-forward in the affine position) and the factor
-                    Kf[kk * S::KF + lane] = kq[0];
-                    Kf[kk * S::KF + 32 + lane] = kq[1];
+                    QM_KST(Kf + kk * S::KF + lane, kq[0]);
+                    QM_KST(Kf + kk * S::KF + 32 + lane, kq[1]);
                     if (lane == 0) {
                         double2* lo = reinterpret_cast<double2*>(Lf + (size_t)kk * S::LF);
                         __stcg(lo + 0, make_double2(r0, r1)); __stcg(lo + 1, make_double2(r2, r3));
@@ -643,8 +656,8 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
                     BackOps o;
                     const int kk = N - 1 - i_;
                     o.t = ld_t(kk);
-                    o.kf[0] = Kf[kk * S::KF + lane];
-                    o.kf[1] = Kf[kk * S::KF + 32 + lane];
+                    o.kf[0] = QM_KLD(Kf + kk * S::KF + lane);
+                    o.kf[1] = QM_KLD(Kf + kk * S::KF + 32 + lane);
                     return o;
                 };
                 double bA = 2 * q_ < 3 ? corr[(2 * NU + 6 + 2 * q_) * KP + N] : 0.0;
@@ -720,9 +733,9 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
                     // K~[u = g][slot]: slot s sits at position s (s < 8) or 8 + 2 (s - 8), fragment entry [tile][4 (pos % 8) + u]
                     const double* k_ = Kf + kk * S::KF + g_;
                     const bool ku = g_ < NU;
-                    o.kA = ku ? k_[4 * (2 * q_)] : 0.0;
-                    o.kB = ku ? k_[4 * (2 * q_ + 1)] : 0.0;
-                    o.kC = ku ? k_[32 + 4 * (2 * q_)] : 0.0;
+                    o.kA = ku ? QM_KLD(k_ + 4 * (2 * q_)) : 0.0;
+                    o.kB = ku ? QM_KLD(k_ + 4 * (2 * q_ + 1)) : 0.0;
+                    o.kC = ku ? QM_KLD(k_ + 32 + 4 * (2 * q_)) : 0.0;
                     return o;
                 };
                 const bool delta = pass == 1;
