@@ -31,10 +31,14 @@ from . import sdf as SDF
 
 
 def default_cfg(model='att'):
-    """`model` in {'att', 'att_tau', 'acc'} (gen_model.py:15-17); bounds and hover input come from the model."""
+    """`model` in {'att', 'att_tau', 'acc', 'props'} (gen_model.py:15-20); bounds and hover input come from the model."""
     c = dict(M.DEFAULT)
     mdl = MODELS.get(model)
     c.update(model=model, ax=4.0, ay=4.0, az=3.0, tau_roll=0.12, tau_pitch=0.12)
+    if model == 'props':        # robot.alloc / inertia / limits.wp of config/default.yaml:79-87,108
+        motors = [[0.09, -0.09, -0.005, 0, 0, -1], [-0.09, 0.09, -0.005, 0, 0, -1], [0.09, 0.09, -0.005, 0, 0, 1], [-0.09, -0.09, -0.005, 0, 0, 1]]
+        Gf, Gt = MODELS.props_allocation(motors, 0.02246, 0.00020673)
+        c.update(cf=0.02246, ct=0.00020673, motors=motors, Gf=Gf, Gt=Gt, inertia=np.array([0.017, 0.018, 0.028]), wp_max=25.0)
     c.update(N=20, T=1.5, lm=10.0, lbu=mdl.lbu.copy(), ubu=mdl.ubu.copy(),
              slack_df=(200.0, 50.0), slack_fov=(20.0, 0.0), size_xy=0.22, bound_margin=0.15,
              h_at_node0=False, qp_tol=1e-8, qp_iter_max=100)
@@ -80,16 +84,17 @@ def linearize(net, xb, ub, prob, cfg):
     B, N = xb.shape[0], cfg['N']
     dt = cfg['dt']
     mdl = MODELS.get(cfg.get('model', 'att'))
-    nyN = mdl.nyN
-    A = np.zeros((B, N, 10, 10)); Bm = np.zeros((B, N, 10, 4)); b = np.zeros((B, N, 10))
-    H = np.zeros((B, N, 14, 14)); g = np.zeros((B, N, 14))
-    C = np.zeros((B, N + 1, 3, 10)); hbar = np.zeros((B, N + 1, 3))
+    nyN, nx = mdl.nyN, mdl.nx
+    nw = nx + 4
+    A = np.zeros((B, N, nx, nx)); Bm = np.zeros((B, N, nx, 4)); b = np.zeros((B, N, nx))
+    H = np.zeros((B, N, nw, nw)); g = np.zeros((B, N, nw))
+    C = np.zeros((B, N + 1, 3, nx)); hbar = np.zeros((B, N + 1, 3))
     for k in range(N):
         xn, A[:, k], Bm[:, k] = mdl.rk4_sens(xb[:, k], ub[:, k], dt[k], cfg)
         b[:, k] = xn - xb[:, k + 1]
         y, J = mdl.y_fun(xb[:, k], ub[:, k], prob['qd'][:, k], cfg)
         Wk = prob['W'][:, k]
-        H[:, k] = dt[k] * (np.einsum('byi,by,byj->bij', J, Wk, J) + cfg['lm'] * np.eye(14)[None])
+        H[:, k] = dt[k] * (np.einsum('byi,by,byj->bij', J, Wk, J) + cfg['lm'] * np.eye(nw)[None])
         g[:, k] = dt[k] * np.einsum('byi,by->bi', J, Wk * (y - prob['yref'][:, k]))
         if cfg.get('sdf_cost_w', 0.0) > 0:      # flags.sdf_cost: stage cost row (1 - 0.5 sdf)^4, weight 20 (gen_model.py:65-66)
             hk, Jp = eval_h(net, xb[:, k], prob, cfg)
@@ -99,7 +104,7 @@ def linearize(net, xb, ub, prob, cfg):
             g[:, k, 4:7] += dt[k] * cfg['sdf_cost_w'] * rr[:, None] * Jr
     yN, JN = mdl.y_fun(xb[:, N], np.zeros((B, 4)), prob['qd'][:, N], cfg)
     yN, JN = yN[:, :nyN], JN[:, :nyN, 4:]
-    HN = np.einsum('byi,by,byj->bij', JN, prob['WN'], JN) + cfg['lm'] * np.eye(10)[None]
+    HN = np.einsum('byi,by,byj->bij', JN, prob['WN'], JN) + cfg['lm'] * np.eye(nx)[None]
     gN = np.einsum('byi,by->bi', JN, prob['WN'] * (yN - prob['yrefN']))
     k0 = 0 if cfg['h_at_node0'] else 1
     for k in range(k0, N + 1):
@@ -113,7 +118,8 @@ def condense(lin, xb, ub, prob, cfg, max_df):
     rows = [u lower (N*4), u upper (N*4), h lower (nodes k0..N, 3 each), h upper (same)]."""
     B, N = xb.shape[0], cfg['N']
     nv = 4 * N
-    Gam = np.zeros((B, N + 1, 10, nv)); gam = np.zeros((B, N + 1, 10))
+    nx = xb.shape[2]
+    Gam = np.zeros((B, N + 1, nx, nv)); gam = np.zeros((B, N + 1, nx))
     gam[:, 0] = prob['x0'] - xb[:, 0]
     for k in range(N):
         Gam[:, k + 1] = lin['A'][:, k] @ Gam[:, k]
@@ -121,7 +127,7 @@ def condense(lin, xb, ub, prob, cfg, max_df):
         gam[:, k + 1] = np.einsum('bij,bj->bi', lin['A'][:, k], gam[:, k]) + lin['b'][:, k]
     P = np.zeros((B, nv, nv)); q = np.zeros((B, nv))
     for k in range(N):
-        T = np.zeros((B, 14, nv)); T[:, np.arange(4), 4 * k + np.arange(4)] = 1.0; T[:, 4:] = Gam[:, k]
+        T = np.zeros((B, nx + 4, nv)); T[:, np.arange(4), 4 * k + np.arange(4)] = 1.0; T[:, 4:] = Gam[:, k]
         t = np.concatenate([np.zeros((B, 4)), gam[:, k]], 1)
         HT = lin['H'][:, k] @ T
         P += np.swapaxes(T, 1, 2) @ HT

@@ -42,7 +42,8 @@ SDF_HD constexpr int mma_wpos(int i) { return i < ATT_NU ? 9 + 2 * i : (i < ATT_
 
 template <int MODEL>
 SDF_HD void linearize_dir(const ModelConst& mc, int N, const LinIn& in, const LinOut& out, int b, int k, int dir) {
-    constexpr int NX = ATT_NX, NU = ATT_NU, NW = ATT_NW, NY = ATT_NY, NH = ATT_NH;
+    using D_ = ModelDims<MODEL>;
+    constexpr int NX = D_::NX, NU = D_::NU, NW = D_::NW, NY = D_::NY, NH = D_::NH;
     double* xb = in.xbar + ((size_t)b * (N + 1) + k) * NX;
     const double* x = (k == 0 && in.x0) ? in.x0 + (size_t)b * NX : xb;
     // only the threads of node 0 read x0 and none of them reads xbar_0, so the direction-0 thread may store it
@@ -62,7 +63,7 @@ SDF_HD void linearize_dir(const ModelConst& mc, int N, const LinIn& in, const Li
         rk4_step<MODEL>(mc, xd, ud, in.dt[k], xn);
         double* AB = out.AB + ((size_t)b * N + k) * NX * NW;
         for (int i = 0; i < NX; ++i) AB[i * NW + dir] = xn[i].d;
-        double* T = out.ABt ? out.ABt + ((size_t)b * N + k) * 192 : nullptr;
+        double* T = (out.ABt && NX == ATT_NX) ? out.ABt + ((size_t)b * N + k) * 192 : nullptr;     // 10-state models only
         if (T) {
             double* row = T + mma_wpos(dir) * 12;
             for (int i = 0; i < NX; ++i) row[i] = xn[i].d;

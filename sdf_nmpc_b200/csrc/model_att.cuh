@@ -20,13 +20,29 @@ constexpr int ATT_NY = 11;
 constexpr int ATT_NYN = 4;
 constexpr int ATT_NH = 3;    // hfov, vfov, sdf  (gen_model.py:42,68)
 
-enum QuadModel { MODEL_ATT = 0, MODEL_ATT_TAU = 1, MODEL_ACC = 2 };   // mpc.model: att / att_tau / acc (gen_model.py:15-20)
+enum QuadModel { MODEL_ATT = 0, MODEL_ATT_TAU = 1, MODEL_ACC = 2, MODEL_PROPS = 3 };   // mpc.model: att / att_tau / acc / props (gen_model.py:15-20)
+
+// Stage dimensions by model.  'props' (sdf_nmpc/model/quad_props.py:12-15) has 13 states [p, q, v, w], 4 rotor-speed inputs,
+// 16 / 12 outputs; on the device its state carries ONE PAD ENTRY (index 13: zero dynamics, not in any output or constraint, so
+// its step is exactly zero) because the QP's staging copies move 16-byte units and need even row lengths.
+template <int MODEL>
+struct ModelDims {
+    static constexpr int NX = ATT_NX, NU = ATT_NU, NW = ATT_NW, NY = ATT_NY, NH = ATT_NH;
+};
+template <>
+struct ModelDims<MODEL_PROPS> {
+    static constexpr int NX = 14, NU = 4, NW = 18, NY = 16, NH = 3;
+};
+constexpr int PROPS_NX_REF = 13, PROPS_NYN = 12;
 
 struct ModelConst {
     double g, gamma, roll, pitch, wz, mass;
     double cam_off[3];    // B_R_C^T B_p_C + (fov_const_offset, 0, 0)
     double ax, ay, az;    // acceleration limits (model 'acc', default.yaml:101-103)
     double tau_roll, tau_pitch;   // first-order attitude lag (model 'att_tau', quad_rollpitchyawrate_tau.py:19-20)
+    // model 'props' (quad_props.py:18-38): rotor speed scale, allocation matrices with cf folded in - Gf / mass and J^-1 Gt,
+    // row-major [3][4] - and the diagonal inertia
+    double wp_max, Gf_m[12], JGt[12], inertia[3];
 };
 
 // Input-only trigonometry of model 'att': the inputs are constant over the RK4 stages of a node, so cos / sin of the roll
@@ -115,15 +131,49 @@ SDF_HD void f_acc(const ModelConst& c, const T* x, const T* u, T* dx) {
     dx[9] = c.az * u[2];
 }
 
+// Model 'props' (sdf_nmpc/model/quad_props.py:29-50): rigid body driven by four rotor speeds wp = u * limits.wp through the
+// allocation matrices of a generically tilted multi-rotor (utils/math.py:385-396), quaternion normalised first (line 30).
+template <class T>
+SDF_HD void f_props(const ModelConst& c, const T* x, const T* u, T* dx) {
+    T q0 = x[3], q1 = x[4], q2 = x[5], q3 = x[6];
+    T inv_n = 1.0 / dsqrt(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+    q0 = q0 * inv_n; q1 = q1 * inv_n; q2 = q2 * inv_n; q3 = q3 * inv_n;
+    const T w0 = x[10], w1 = x[11], w2 = x[12];
+    T s[4];
+    for (int j = 0; j < 4; ++j) { T wp = c.wp_max * u[j]; s[j] = wp * wp; }
+    T F[3], M[3];
+    for (int i = 0; i < 3; ++i) {
+        F[i] = c.Gf_m[i * 4 + 0] * s[0] + c.Gf_m[i * 4 + 1] * s[1] + c.Gf_m[i * 4 + 2] * s[2] + c.Gf_m[i * 4 + 3] * s[3];
+        M[i] = c.JGt[i * 4 + 0] * s[0] + c.JGt[i * 4 + 1] * s[1] + c.JGt[i * 4 + 2] * s[2] + c.JGt[i * 4 + 3] * s[3];
+    }
+    dx[0] = x[7]; dx[1] = x[8]; dx[2] = x[9];
+    dx[3] = 0.5 * (-(q1 * w0) - q2 * w1 - q3 * w2);                                  // hamilton_prod(q, (0, w)) / 2
+    dx[4] = 0.5 * (q0 * w0 + q2 * w2 - q3 * w1);
+    dx[5] = 0.5 * (q0 * w1 - q1 * w2 + q3 * w0);
+    dx[6] = 0.5 * (q0 * w2 + q1 * w1 - q2 * w0);
+    // W_R_B (quat2rot, utils/math.py:7-23) times the body-frame specific force
+    dx[7] = (q0 * q0 + q1 * q1 - q2 * q2 - q3 * q3) * F[0] + (2.0 * (q1 * q2 - q0 * q3)) * F[1] + (2.0 * (q1 * q3 + q0 * q2)) * F[2];
+    dx[8] = (2.0 * (q1 * q2 + q0 * q3)) * F[0] + (q0 * q0 - q1 * q1 + q2 * q2 - q3 * q3) * F[1] + (2.0 * (q2 * q3 - q0 * q1)) * F[2];
+    dx[9] = (2.0 * (q1 * q3 - q0 * q2)) * F[0] + (2.0 * (q2 * q3 + q0 * q1)) * F[1] + (q0 * q0 - q1 * q1 - q2 * q2 + q3 * q3) * F[2] - c.g;
+    // J^-1 (Gt wp^2 - w x J w), J diagonal
+    const double J0 = c.inertia[0], J1 = c.inertia[1], J2 = c.inertia[2];
+    dx[10] = M[0] - ((J2 - J1) / J0) * (w1 * w2);
+    dx[11] = M[1] - ((J0 - J2) / J1) * (w2 * w0);
+    dx[12] = M[2] - ((J1 - J0) / J2) * (w0 * w1);
+    dx[13] = T(0.0);                                                                 // pad state
+}
+
 template <int MODEL, class T>
 SDF_HD void f_model(const ModelConst& c, const T* x, const T* u, T* dx, const AttInputTrig<T>* it = nullptr) {
     if (MODEL == MODEL_ATT) f_att(c, x, u, dx, it);
     else if (MODEL == MODEL_ATT_TAU) f_att_tau(c, x, u, dx);
+    else if (MODEL == MODEL_PROPS) f_props(c, x, u, dx);
     else f_acc(c, x, u, dx);
 }
 
 template <int MODEL, class T>
 SDF_HD void rk4_step(const ModelConst& c, const T* x, const T* u, double dt, T* xn) {
+    constexpr int ATT_NX = ModelDims<MODEL>::NX;
     T k1[ATT_NX], k2[ATT_NX], k3[ATT_NX], k4[ATT_NX], xs[ATT_NX];
     AttInputTrig<T> trig;
     const AttInputTrig<T>* it = nullptr;
@@ -160,12 +210,22 @@ SDF_HD void y_att(const ModelConst& c, const T* x, const T* u, const double* qd,
 
 // att_tau: y = [p, q_e[3], v, roll_des, pitch_des, wz, W_a[2]] with the full-quaternion W_a (quad_rollpitchyawrate_tau.py:49-52)
 // acc:     y = [p, q_e[3], v, W_a(3), wz], yN = first 7                               (quad_acc.py:40-45)
+// props:   y = [p, roll, pitch, q_e[3], v, w, wp(4)], yN = first 12                    (quad_props.py:56-59)
 template <int MODEL, class T>
 SDF_HD void y_model(const ModelConst& c, const T* x, const T* u, const double* qd, T* y) {
     if (MODEL == MODEL_ATT) { y_att(c, x, u, qd, y); return; }
     T q0 = x[3], q1 = x[4], q2 = x[5], q3 = x[6];
     T inv_n = 1.0 / dsqrt(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
     T h0 = q0 * inv_n, h1 = q1 * inv_n, h2 = q2 * inv_n, h3 = q3 * inv_n;
+    if (MODEL == MODEL_PROPS) {
+        y[0] = x[0]; y[1] = x[1]; y[2] = x[2];
+        y[3] = datan2(2.0 * (h0 * h1 + h2 * h3), 1.0 - 2.0 * (h1 * h1 + h2 * h2));     // quat2euler, utils/math.py:57-70
+        y[4] = dasin(2.0 * (h0 * h2 - h3 * h1));
+        y[5] = qd[2] * h1 + qd[3] * h0 - qd[0] * h3 - qd[1] * h2;
+        for (int i = 0; i < 6; ++i) y[6 + i] = x[7 + i];
+        for (int j = 0; j < 4; ++j) y[12 + j] = c.wp_max * u[j];
+        return;
+    }
     y[0] = x[0]; y[1] = x[1]; y[2] = x[2];
     y[3] = qd[2] * h1 + qd[3] * h0 - qd[0] * h3 - qd[1] * h2;
     y[4] = x[7]; y[5] = x[8]; y[6] = x[9];
@@ -212,9 +272,10 @@ SDF_HD void u_to_TRPYr(const ModelConst& c, const double* u, double* cmd) {
 
 // [W_R_B^T W_a, wz]: u_to_acc of quad_rollpitchyawrate.py:45, quad_rollpitchyawrate_tau.py:46, quad_acc.py:36.
 // For the thrust models W_a = W_R_B (0,0,gamma) - g e_z, hence W_R_B^T W_a = (0,0,gamma) - g * (third row of W_R_B).
+// props: W_a = W_R_B F - g e_z with F = Gf wp^2 / m, hence W_R_B^T W_a = F - g * (third row of W_R_B); fourth entry w_z.
 template <int MODEL>
 SDF_HD void u_to_acc(const ModelConst& c, const double* x, const double* u, double* cmd) {
-    cmd[3] = c.wz * u[3];
+    cmd[3] = MODEL == MODEL_PROPS ? x[12] : c.wz * u[3];
     if (MODEL == MODEL_ATT) {
         double r = c.roll * u[1], pt = c.pitch * u[2];
         cmd[0] = c.g * sin(pt);                       // third row of Rz(psi) V_R_B(roll, pitch) is (-sp, sr cp, cr cp)
@@ -231,6 +292,11 @@ SDF_HD void u_to_acc(const ModelConst& c, const double* x, const double* u, doub
         cmd[0] = -c.g * R[6];
         cmd[1] = -c.g * R[7];
         cmd[2] = c.gamma * u[0] - c.g * R[8];
+    } else if (MODEL == MODEL_PROPS) {
+        double s[4];
+        for (int j = 0; j < 4; ++j) { const double wp = c.wp_max * u[j]; s[j] = wp * wp; }
+        for (int i = 0; i < 3; ++i)
+            cmd[i] = c.Gf_m[i * 4 + 0] * s[0] + c.Gf_m[i * 4 + 1] * s[1] + c.Gf_m[i * 4 + 2] * s[2] + c.Gf_m[i * 4 + 3] * s[3] - c.g * R[6 + i];
     } else {
         double a0 = c.ax * u[0], a1 = c.ay * u[1], a2 = c.az * u[2];
         cmd[0] = R[0] * a0 + R[3] * a1 + R[6] * a2;

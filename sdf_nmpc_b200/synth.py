@@ -116,6 +116,9 @@ def _qmul(a, b):
                      a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1], a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0]])
 
 
+PROPS_WH = float(np.sqrt(1.46 * 9.81 / 4 / 0.02246))     # hover rotor speed sqrt(m g / 4 / cf), quad_props.py:51 with default.yaml:78-81
+
+
 def nmpc_instances(B, N=20, dt=0.075, seed=1000, vref=3.0, weights=None, first=0, model='att'):
     """Config 3/4: B randomised NMPC instances (per-instance seed ``seed + first + i``).
 
@@ -123,13 +126,15 @@ def nmpc_instances(B, N=20, dt=0.075, seed=1000, vref=3.0, weights=None, first=0
     qd [B,N+1,4], W_p_Bo [B,3], W_R_Bo [B,3,3], latent [B,128] (float32).
     ``weights`` = dict(pos,vel,att,rates,acc); default = constraints-on set (default.yaml:43-48).
     ``model``: 'att' (default), 'att_tau' (x0 additionally tilted by up to 0.2 rad in roll/pitch) or 'acc' (yrefN/WN
-    are [B,7] and the output rows follow quad_acc.py:40-58).
+    are [B,7] and the output rows follow quad_acc.py:40-58) or 'props' (x0 [B,13] with a tilted attitude and a small body
+    rate, yref / W [B,N,16], yrefN / WN [B,12], rows of quad_props.py:56-69 with the hover rotor speed as input reference).
     """
     if weights is None:
         weights = dict(pos=[0, 0, 5], vel=[3, 3, 3], att=[50, 50, 10], rates=[0, 0, 3], acc=0.05)
-    x0 = np.zeros((B, 10))
-    yref = np.zeros((B, N, 11))
-    nyN = 7 if model == 'acc' else 4
+    nx, ny = (13, 16) if model == 'props' else (10, 11)
+    x0 = np.zeros((B, nx))
+    yref = np.zeros((B, N, ny))
+    nyN = 7 if model == 'acc' else (12 if model == 'props' else 4)
     yrefN = np.zeros((B, nyN))
     qd = np.zeros((B, N + 1, 4))
     lat = np.zeros((B, 128), np.float32)
@@ -146,18 +151,25 @@ def nmpc_instances(B, N=20, dt=0.075, seed=1000, vref=3.0, weights=None, first=0
         d = rng.standard_normal(3)
         d /= np.linalg.norm(d)
         v_ref = vref * d
-        x0[i, :3], x0[i, 3:7], x0[i, 7:] = p, yaw2quat(yaw), v
-        if model == 'att_tau':
+        x0[i, :3], x0[i, 3:7], x0[i, 7:10] = p, yaw2quat(yaw), v
+        if model in ('att_tau', 'props'):
             r, pt = rng.uniform(-0.2, 0.2, 2)
             qr = np.array([np.cos(r / 2), np.sin(r / 2), 0, 0]); qp = np.array([np.cos(pt / 2), 0, np.sin(pt / 2), 0])
             x0[i, 3:7] = _qmul(_qmul(yaw2quat(yaw), qp), qr)
+        if model == 'props':
+            x0[i, 10:13] = rng.uniform(-0.3, 0.3, 3)
         k = np.arange(N + 1)[:, None]
         p_ref = p[None] + v_ref[None] * k * dt
         yaw_ref = np.arctan2(v_ref[1], v_ref[0])
         qd[i] = yaw2quat(yaw_ref)
         yref[i, :, 0:3] = p_ref[:N]
-        yref[i, :, 4:7] = v_ref
         yrefN[i, 0:3] = p_ref[N]
+        if model == 'props':
+            yref[i, :, 6:9] = v_ref
+            yref[i, :, 12:16] = PROPS_WH
+            yrefN[i, 6:9] = v_ref
+        else:
+            yref[i, :, 4:7] = v_ref
         if model == 'acc':
             yrefN[i, 4:7] = v_ref
         c, s = np.cos(yaw), np.sin(yaw)
@@ -166,7 +178,9 @@ def nmpc_instances(B, N=20, dt=0.075, seed=1000, vref=3.0, weights=None, first=0
     Wrow = np.array(list(w['pos']) + [w['att'][2]] + list(w['vel']) + [w['att'][0], w['att'][1], w['rates'][2], w['acc']], float)
     if model == 'acc':
         Wrow = np.array(list(w['pos']) + [w['att'][2]] + list(w['vel']) + [w['acc']] * 3 + [w['rates'][2]], float)
-    W = np.broadcast_to(Wrow, (B, N, 11)).copy()
+    if model == 'props':
+        Wrow = np.array(list(w['pos']) + list(w['att']) + list(w['vel']) + list(w['rates']) + [w['acc']] * 4, float)
+    W = np.broadcast_to(Wrow, (B, N, ny)).copy()
     WN = np.broadcast_to(Wrow[:nyN], (B, nyN)).copy()
     return dict(x0=x0, yref=yref, W=W, yrefN=yrefN, WN=WN, qd=qd, W_p_Bo=x0[:, :3].copy(), W_R_Bo=Rbo, latent=lat)
 

@@ -213,6 +213,51 @@ def model_variants_case():
     print('model_variants: f range', np.abs(Ft).max(), np.abs(Fa).max())
 
 
+def model_props_case():
+    """Model 'props': allocation matrices from the reference's GTMRP_matrix / axis_rot on the robot.alloc block of the reference's
+    default.yaml, and f_expl, y, u_to_acc, u_to_props composed from its numpy math helpers exactly as model/quad_props.py:18-59
+    composes them (same X[:, :10], U, QD as model_variants.npz; body rates drawn here; inputs mapped to [0, 1])."""
+    from math import pi
+    from sdf_nmpc.utils import math as rm
+    from sdf_nmpc.utils.config import Config
+    cfg = Config('/root/reference/sdf_nmpc/config/default.yaml')
+    G = np.load(os.path.join(HERE, 'model_variants.npz'))
+    rng = np.random.default_rng(31)
+    n = len(G['X'])
+    X = np.concatenate([G['X'], rng.uniform(-2, 2, (n, 3))], 1)
+    U = 0.5 * (G['U'] + 1.0) * np.array([1.0, 0.5, 0.5, 0.5]) + np.array([0.0, 0.25, 0.25, 0.25])
+    QD = G['QD']
+    # quad_props.py:18-27
+    px, py, pz, alpha, beta, sign = zip(*cfg.robot.alloc.motors)
+    cf = [cfg.robot.alloc.cf] * len(sign)
+    ct = [cfg.robot.alloc.ct] * len(sign)
+    R = [rm.axis_rot('z', i * (pi / (len(sign) / 2))) @ rm.axis_rot('y', beta[i]) @ rm.axis_rot('x', (-1) ** i * alpha[i]) for i in range(len(sign))]
+    p = np.array([px, py, pz]).T
+    Gf, Gt = rm.GTMRP_matrix(R, p, sign, cf, ct)
+    Gf = cf * Gf
+    Gt = cf * Gt
+    m, g = cfg.robot.mass, 9.81
+    J = np.diag(cfg.robot.inertia); Jinv = np.linalg.inv(J)
+    F, Y, CA, CP = [], [], [], []
+    for i in range(n):
+        x, u = X[i], U[i]
+        p_ = x[0:3]; q = x[3:7] / np.linalg.norm(x[3:7]); eta = rm.quat2euler(q); v = x[7:10]; w = x[10:]
+        wp = u * cfg.robot.limits.wp
+        W_R_B = rm.quat2rot(q)
+        W_a = W_R_B @ Gf @ wp ** 2 / m + np.array([0, 0, -g])
+        F.append(np.concatenate([v, rm.hamilton_prod(q, np.concatenate([[0], w])) / 2, W_a, Jinv @ (Gt @ wp ** 2 - np.cross(w, J @ w))]))
+        q_e = rm.hamilton_prod(QD[i], rm.invert(q))
+        Y.append(np.concatenate([p_, eta[:2], [q_e[3]], v, w, wp]))
+        CA.append(np.concatenate([W_R_B.T @ W_a, [w[2]]]))
+        CP.append(wp)
+    wh = np.sqrt(m * g / 4 / cfg.robot.alloc.cf)
+    np.savez_compressed(os.path.join(HERE, 'model_props.npz'), X=X, U=U, QD=QD, Gf=Gf, Gt=Gt, F=np.array(F), Y=np.array(Y),
+                        CMDACC=np.array(CA), CMDPROPS=np.array(CP), wh=wh, wp_max=float(cfg.robot.limits.wp),
+                        inertia=np.array(cfg.robot.inertia, float), mass=m, cf=cfg.robot.alloc.cf, ct=cfg.robot.alloc.ct,
+                        motors=np.array(cfg.robot.alloc.motors, float))
+    print('model_props: f range', np.abs(F).max(), 'Gt', np.abs(Gt).max())
+
+
 def refgen_case():
     """Trajectories of the reference's own RefGen (sdf_nmpc/ref_gen.py) on random states / way-points for every yaw mode,
     with and without stop-and-turn, plus joystick references."""
@@ -283,5 +328,6 @@ if __name__ == '__main__':
              act='softplus', w0=1.0, size_latent=32)
     model_att_case()
     model_variants_case()
+    model_props_case()
     refgen_case()
     encoder_case()

@@ -8,8 +8,6 @@
 #include "../../sdf_nmpc_b200/csrc/qp_core.cuh"
 
 using namespace sdfnmpc;
-using Shape = QpShape<ATT_NX, ATT_NU, ATT_NY, ATT_NH>;
-using Prob = QpProb<ATT_NX, ATT_NU, ATT_NY, ATT_NH>;
 
 extern "C" void emul_linearize(int model, int nyN, int B, int N, const double* mcv, double* xbar, const double* ubar,
                                const double* yref, const double* yrefN, const double* qd, const double* pose,
@@ -19,25 +17,35 @@ extern "C" void emul_linearize(int model, int nyN, int B, int N, const double* m
     mc.g = mcv[0]; mc.gamma = mcv[1]; mc.roll = mcv[2]; mc.pitch = mcv[3]; mc.wz = mcv[4]; mc.mass = mcv[5];
     mc.cam_off[0] = mcv[6]; mc.cam_off[1] = mcv[7]; mc.cam_off[2] = mcv[8];
     mc.ax = mcv[9]; mc.ay = mcv[10]; mc.az = mcv[11]; mc.tau_roll = mcv[12]; mc.tau_pitch = mcv[13];
+    if (model == MODEL_PROPS) {          // mcv continues: wp_max, Gf / m [12], J^-1 Gt [12], inertia [3]
+        mc.wp_max = mcv[14];
+        for (int i = 0; i < 12; ++i) { mc.Gf_m[i] = mcv[15 + i]; mc.JGt[i] = mcv[27 + i]; }
+        for (int i = 0; i < 3; ++i) mc.inertia[i] = mcv[39 + i];
+    }
     LinIn in{xbar, ubar, yref, yrefN, qd, pose, flag, dt, nyN, x0};
     LinOut out{AB, bdyn, J, yres, C, hval, qpts, nullptr};
+    const int nw = model == MODEL_PROPS ? ModelDims<MODEL_PROPS>::NW : ATT_NW;
     for (int b = 0; b < B; ++b)
         for (int k = 0; k <= N; ++k)
-            for (int d = 0; d < ATT_NW; ++d) {
+            for (int d = 0; d < nw; ++d) {
                 if (model == MODEL_ATT) linearize_dir<MODEL_ATT>(mc, N, in, out, b, k, d);
                 else if (model == MODEL_ATT_TAU) linearize_dir<MODEL_ATT_TAU>(mc, N, in, out, b, k, d);
+                else if (model == MODEL_PROPS) linearize_dir<MODEL_PROPS>(mc, N, in, out, b, k, d);
                 else linearize_dir<MODEL_ACC>(mc, N, in, out, b, k, d);
             }
 }
 
-extern "C" void emul_qp(int B, int N, int k0, int max_iter, int nyN, double sdf_cost_w, double lm, double tol, double tol_res,
+template <int NX, int NU, int NY, int NH>
+static void emul_qp_t(int B, int N, int k0, int max_iter, int nyN, double sdf_cost_w, double lm, double tol, double tol_res,
                         double max_df, const double* flag, const double* AB, const double* bdyn, const double* J,
                         const double* yres, double* C, double* hval, const double* W, const double* WN,
                         const double* dt, const double* lbu, const double* ubu, const double* lh, const double* uh,
                         const double* zs, const double* Zs, const float* sdf_d, const float* sdf_g,
                         const double* pose, const double* x0, double* xbar, double* ubar, double* u0,
                         double* lam_hard, double* lam_soft, int* status, int* iters) {
-    constexpr int NX = ATT_NX, NU = ATT_NU, NW = ATT_NW, NY = ATT_NY, NH = ATT_NH;
+    constexpr int NW = NX + NU;
+    using Shape = QpShape<NX, NU, NY, NH>;
+    using Prob = QpProb<NX, NU, NY, NH>;
     std::vector<double> work(Shape::work_doubles(N));
     std::vector<double> sm(Shape::smem_doubles(N));
     Lanes L{0};
@@ -73,4 +81,19 @@ extern "C" void emul_qp(int B, int N, int k0, int max_iter, int nyN, double sdf_
         P.iters = iters + b;
         qp_solve_instance<NX, NU, NY, NH>(L, P, sm.data());
     }
+}
+
+#define EMUL_QP_ARGS B, N, k0, max_iter, nyN, sdf_cost_w, lm, tol, tol_res, max_df, flag, AB, bdyn, J, yres, C, hval, W, WN, dt, lbu, ubu, lh, uh, \
+                     zs, Zs, sdf_d, sdf_g, pose, x0, xbar, ubar, u0, lam_hard, lam_soft, status, iters
+#define EMUL_QP_PARAMS int B, int N, int k0, int max_iter, int nyN, double sdf_cost_w, double lm, double tol, double tol_res,                   \
+                       double max_df, const double* flag, const double* AB, const double* bdyn, const double* J, const double* yres, double* C, \
+                       double* hval, const double* W, const double* WN, const double* dt, const double* lbu, const double* ubu,                  \
+                       const double* lh, const double* uh, const double* zs, const double* Zs, const float* sdf_d, const float* sdf_g,          \
+                       const double* pose, const double* x0, double* xbar, double* ubar, double* u0, double* lam_hard, double* lam_soft,        \
+                       int* status, int* iters
+extern "C" void emul_qp(EMUL_QP_PARAMS) { emul_qp_t<ATT_NX, ATT_NU, ATT_NY, ATT_NH>(EMUL_QP_ARGS); }
+// model 'props': 13 states + one pad entry (model_att.cuh, ModelDims<MODEL_PROPS>)
+extern "C" void emul_qp_props(EMUL_QP_PARAMS) {
+    using D = ModelDims<MODEL_PROPS>;
+    emul_qp_t<D::NX, D::NU, D::NY, D::NH>(EMUL_QP_ARGS);
 }

@@ -33,21 +33,29 @@ def _emul_step(lib, net, cfg, prob, xe, ue):
     mcv = np.array([cfg['g'], cfg['gamma'], cfg['roll'], cfg['pitch'], cfg['wz'], cfg['mass'],
                     *(cfg['B_R_C'].T @ cfg['B_p_C'] + np.array([cfg['fov_off'], 0, 0])),
                     cfg['ax'], cfg['ay'], cfg['az'], cfg['tau_roll'], cfg['tau_pitch']])
+    props = cfg['model'] == 'props'
+    nx, ny = (14, 16) if props else (10, 11)          # device state of 'props': 13 + one pad entry (model_att.cuh)
+    nw = nx + 4
+    if props:
+        mcv = np.concatenate([mcv, [cfg['wp_max']], (cfg['Gf'] / cfg['mass']).ravel(),
+                              (cfg['Gt'] / cfg['inertia'][:, None]).ravel(), cfg['inertia']])
     lh, uh = rti.h_bounds(cfg, net['max_df'])
     zs, Zs = rti.slack_weights(cfg)
-    AB = np.zeros((B, N, 10, 14)); bd = np.zeros((B, N, 10)); J = np.zeros((B, N + 1, 11, 14)); yr = np.zeros((B, N + 1, 11))
-    C = np.zeros((B, N + 1, 3, 14)); hv = np.zeros((B, N + 1, 3)); qp = np.zeros((B, N + 1, 3), np.float32)
+    AB = np.zeros((B, N, nx, nw)); bd = np.zeros((B, N, nx)); J = np.zeros((B, N + 1, ny, nw)); yr = np.zeros((B, N + 1, ny))
+    C = np.zeros((B, N + 1, 3, nw)); hv = np.zeros((B, N + 1, 3)); qp = np.zeros((B, N + 1, 3), np.float32)
     c = np.ascontiguousarray
     yref, yrefN, qd, flag, W, WN, x0 = (c(prob[k]) for k in ('yref', 'yrefN', 'qd', 'flag', 'W', 'WN', 'x0'))
+    if props:
+        x0 = c(np.pad(x0, ((0, 0), (0, 1))))
     lib.emul_linearize(mid, nyN, B, N, _P(mcv), _P(xe), _P(ue), _P(yref), _P(yrefN), _P(qd), _P(pose), _P(flag), _P(cfg['dt']),
                        _P(AB), _P(bd), _P(J), _P(yr), _P(C), _P(hv), _P(qp), _P(x0))
-    lin = dict(AB=AB.copy(), b=bd.copy(), J=J.copy(), hv=hv.copy(), C=C.copy(), qp=qp.copy())
+    lin = dict(AB=AB.copy(), b=bd.copy(), J=J.copy(), hv=hv.copy(), C=C.copy(), qp=qp.copy(), yr=yr.copy())
     d, g = SDF.value_and_grad(net, qp.reshape(-1, 3), np.repeat(prob['latent'], N + 1, 0), dtype=np.float32)
     d, g = c(d.astype(np.float32)), c(g.astype(np.float32))
     u0 = np.zeros((B, 4)); lamh = np.zeros((B, N, 8)); lams = np.zeros((B, N + 1, 6))
     st = np.zeros(B, np.int32); its = np.zeros(B, np.int32)
     D = ctypes.c_double
-    lib.emul_qp(B, N, 1, 100, nyN, D(cfg.get('sdf_cost_w', 0.0)), D(cfg['lm']), D(1e-8), D(1e-7), D(net['max_df']), _P(flag), _P(AB), _P(bd), _P(J), _P(yr), _P(C),
+    (lib.emul_qp_props if props else lib.emul_qp)(B, N, 1, 100, nyN, D(cfg.get('sdf_cost_w', 0.0)), D(cfg['lm']), D(1e-8), D(1e-7), D(net['max_df']), _P(flag), _P(AB), _P(bd), _P(J), _P(yr), _P(C),
                 _P(hv), _P(W), _P(WN), _P(cfg['dt']), _P(cfg['lbu']), _P(cfg['ubu']), _P(lh), _P(uh), _P(zs), _P(Zs), _P(d), _P(g),
                 _P(pose), _P(x0), _P(xe), _P(ue), _P(u0), _P(lamh), _P(lams), _P(st), _P(its))
     return u0, st, its, lamh, lams, lin
@@ -76,6 +84,34 @@ def test_linearize_and_qp_cores_match_oracle(emul, model):
         assert np.abs(u0 - out['u0']).max() <= 1e-5
         assert np.abs(xe - xo).max() <= 1e-4 and np.abs(ue - uo).max() <= 1e-4
         assert np.abs(lamh[:, :, :4] - out['lam_lbu']).max() < 1e-2 and np.abs(lams[:, 1:, :3] - out['lam_lh']).max() < 1e-2
+        xb, ub = xo, uo
+
+
+def test_props_cores_match_oracle(emul):
+    """Model 'props' (quad_props.py): 13 states + one pad entry on the device, nu 4, ny 16 / 12 - linearisation by dual numbers and
+    the scalar Riccati IPM instantiated for that shape against the numpy oracle over three RTI steps."""
+    from oracle import rti
+    from sdf_nmpc_b200 import synth
+    net = synth.make_sdf_net(seed=0, **synth.ARCH_B, calibrated=True)
+    cfg = rti.default_cfg('props')
+    B = 8
+    prob, w = make_problem(B, cfg, model='props')
+    xb, ub = rti.init_traj(prob['x0'], cfg)
+    xe = np.ascontiguousarray(np.pad(xb, ((0, 0), (0, 0), (0, 1))))
+    ue = np.ascontiguousarray(ub.copy())
+    for step in range(3):
+        xo, uo, out = rti.rti_step(net, xb, ub, prob, cfg)
+        u0, st, its, lamh, lams, lin = _emul_step(emul, net, cfg, prob, xe, ue)
+        if step == 0:
+            L = out['lin']
+            assert np.abs(lin['AB'][:, :, :13, 4:17] - L['A']).max() < 1e-11 and np.abs(lin['AB'][:, :, :13, :4] - L['B']).max() < 1e-11
+            assert np.abs(lin['b'][:, :, :13] - L['b']).max() < 1e-11
+            # the pad state: identity dynamics, no coupling, zero defect
+            assert np.abs(lin['AB'][:, :, 13, :17]).max() == 0 and np.all(lin['AB'][:, :, 13, 17] == 1) and np.abs(lin['AB'][:, :, :13, 17]).max() == 0
+            assert np.abs(lin['hv'][:, 1:, :2] - L['hbar'][:, 1:, :2]).max() < 1e-12
+        assert np.all(st == 0) and its.max() <= 40
+        assert np.abs(u0 - out['u0']).max() <= 1e-5
+        assert np.abs(xe[:, :, :13] - xo).max() <= 1e-4 and np.abs(ue - uo).max() <= 1e-4 and np.abs(xe[:, :, 13]).max() == 0
         xb, ub = xo, uo
 
 
