@@ -86,12 +86,20 @@ typedef struct {
     double lh[3], uh[3];     /* [hfov, vfov, sdf] bounds                                    */
     double zl[3], Zl[3];     /* slack L1 / L2 weights in h order (ocp.py:85-92)             */
     double dt[SDFNMPC_MAX_N];/* stage lengths (ocp.py:21-27)                                */
-    int32_t model;           /* mpc.model (gen_model.py:15-20): 0 att, 1 att_tau, 2 acc; yrefN/WN are [B][4] (7 for acc) */
+    int32_t model;           /* mpc.model (gen_model.py:15-20): 0 att, 1 att_tau, 2 acc, 3 props; yrefN/WN are [B][4] (7 for acc, 12 for props) */
     int32_t reserved;
     double ax, ay, az;       /* robot.limits.ax/ay/az (model acc)                           */
     double tau_roll, tau_pitch; /* attitude lag of att_tau (0 -> 0.12 s, quad_rollpitchyawrate_tau.py:19-20) */
     double sdf_cost_w;       /* flags.sdf_cost: weight of the stage cost row (1 - 0.5 sdf)^4 (gen_model.py:65-66: 20); 0 = off */
+    /* model props (quad_props.py:18-52): rotor-speed scale limits.wp, allocation matrices with cf folded in as Gf / mass and
+     * J^-1 Gt (row-major [3][4]), diagonal inertia, hover input of Ocp.init */
+    double wp_max, Gf_m[12], JGt[12], inertia[3], u_hover_props;
 } sdfnmpc_solver_desc;
+
+/* Stage dimensions by model: att / att_tau / acc  nx 10, ny 11;  props  nx 14 (the reference's 13 states [p, q, v, w] + ONE PAD
+ * entry that callers keep at 0: the QP's staging copies move 16-byte units), ny 16.  nu = 4 and nh = 3 for all.  Wherever a
+ * comment below says [10] / [11] read nx / ny of the handle's model. */
+int sdfnmpc_solver_dims(sdfnmpc_solver_t h, int32_t* nx, int32_t* ny, int32_t* nyN);
 
 int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver_desc* desc, sdfnmpc_sdf_t sdf);
 int sdfnmpc_solver_destroy(sdfnmpc_solver_t h);
@@ -130,6 +138,9 @@ int sdfnmpc_plant_step(sdfnmpc_solver_t h, int32_t B, double* x_dev, const doubl
 int sdfnmpc_cmd_trpyr(sdfnmpc_solver_t h, int32_t B, const double* u_dev, double* cmd_dev, void* stream);
 /* u_to_acc + clip (controller.py:101-103): cmd [B][4] = [W_R_B^T W_a, wz] from x0 [B][10] and u [B][4]; all models. */
 int sdfnmpc_cmd_acc(sdfnmpc_solver_t h, int32_t B, const double* x0_dev, const double* u_dev, double* cmd_dev, void* stream);
+/* u_to_props + clip (controller.py:27-29,111-113; quad_props.py:52): cmd [B][4] = rotor speeds u * limits.wp clipped to
+ * [0, limits.wp]; model props only (SDFNMPC_E_INVALID otherwise). */
+int sdfnmpc_cmd_props(sdfnmpc_solver_t h, int32_t B, const double* u_dev, double* cmd_dev, void* stream);
 
 /* ------------------------------------------------------------------ collision labels ----- */
 /* ColChecker.check_image_points (sdf_nmpc/utils/collision_checker.py:23-125): ground-truth collision label of each point

@@ -29,7 +29,9 @@ class SolverDesc(C.Structure):
                 ('lbu', C.c_double * 4), ('ubu', C.c_double * 4), ('lh', C.c_double * 3), ('uh', C.c_double * 3),
                 ('zl', C.c_double * 3), ('Zl', C.c_double * 3), ('dt', C.c_double * MAX_N),
                 ('model', C.c_int32), ('reserved', C.c_int32), ('ax', C.c_double), ('ay', C.c_double), ('az', C.c_double),
-                ('tau_roll', C.c_double), ('tau_pitch', C.c_double), ('sdf_cost_w', C.c_double)]
+                ('tau_roll', C.c_double), ('tau_pitch', C.c_double), ('sdf_cost_w', C.c_double),
+                ('wp_max', C.c_double), ('Gf_m', C.c_double * 12), ('JGt', C.c_double * 12), ('inertia', C.c_double * 3),
+                ('u_hover_props', C.c_double)]
 
 
 class EncoderDesc(C.Structure):
@@ -55,7 +57,7 @@ CASADI_COMPANIONS = ('', '_alloc_mem', '_init_mem', '_free_mem', '_checkout', '_
 EXPORTS = (['sdfnmpc_version', 'sdfnmpc_launch_count', 'sdfnmpc_sdf_create', 'sdfnmpc_sdf_destroy',
             'sdfnmpc_sdf_set_latents', 'sdfnmpc_sdf_eval', 'sdfnmpc_sdf_eval_host', 'sdfnmpc_solver_create',
             'sdfnmpc_solver_destroy', 'sdfnmpc_solver_init_traj', 'sdfnmpc_solver_shift', 'sdfnmpc_solver_rti_step',
-            'sdfnmpc_solver_state', 'sdfnmpc_solver_diag', 'sdfnmpc_solver_qp_residual', 'sdfnmpc_solver_timing_begin', 'sdfnmpc_solver_timing_end', 'sdfnmpc_plant_step', 'sdfnmpc_cmd_trpyr', 'sdfnmpc_cmd_acc', 'sdfnmpc_colcheck', 'sdfnmpc_fail_count_update',
+            'sdfnmpc_solver_state', 'sdfnmpc_solver_diag', 'sdfnmpc_solver_qp_residual', 'sdfnmpc_solver_timing_begin', 'sdfnmpc_solver_timing_end', 'sdfnmpc_plant_step', 'sdfnmpc_cmd_trpyr', 'sdfnmpc_cmd_acc', 'sdfnmpc_cmd_props', 'sdfnmpc_solver_dims', 'sdfnmpc_colcheck', 'sdfnmpc_fail_count_update',
             'sdfnmpc_encoder_create', 'sdfnmpc_encoder_destroy', 'sdfnmpc_encoder_encode',
             'sdfnmpc_encoder_encode_host', 'sdfnmpc_l4c_bind', 'sdfnmpc_l4c_load_blob']
            + [f + s for f in ('sdf_l4c', 'jac_sdf_l4c') for s in CASADI_COMPANIONS])
@@ -101,6 +103,8 @@ def load():
     lib.sdfnmpc_plant_step.argtypes = [vp, i32, dp, dp, C.c_double, vp]
     lib.sdfnmpc_cmd_trpyr.argtypes = [vp, i32, dp, dp, vp]
     lib.sdfnmpc_cmd_acc.argtypes = [vp, i32, dp, dp, dp, vp]
+    lib.sdfnmpc_cmd_props.argtypes = [vp, i32, dp, dp, vp]
+    lib.sdfnmpc_solver_dims.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     lib.sdfnmpc_fail_count_update.argtypes = [ip, vp, i32, vp]
     lib.sdfnmpc_colcheck.argtypes = [fp, i32, i32, i32, fp, ip, i64] + [C.c_float] * 4 + [i32, i32, i32, vp, vp]
     lib.sdfnmpc_encoder_create.argtypes = [C.POINTER(vp), C.POINTER(EncoderDesc), C.POINTER(EncoderWeights)]

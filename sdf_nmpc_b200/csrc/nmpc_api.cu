@@ -20,6 +20,11 @@ using Shape = QpShape<NX, NU, NY, NH>;        // A/B builds: the scalar statemen
 #else
 using Shape = QpMmaShape;                     // product: tensor-core sweeps (qp_mma.cuh)
 #endif
+// model 'props' (13 states + one pad entry, 16 outputs): the scalar solver instantiated for its shape
+using PD = ModelDims<MODEL_PROPS>;
+using PropsProb = QpProb<PD::NX, PD::NU, PD::NY, PD::NH>;
+using PropsShape = QpShape<PD::NX, PD::NU, PD::NY, PD::NH>;
+static_assert(PD::NU == NU && PD::NH == NH, "inputs and constraint rows are common to all models");
 #ifndef QP_WARPS_PER_CTA
 #define QP_WARPS_PER_CTA 1
 #endif
@@ -43,6 +48,7 @@ struct sdfnmpc_solver {
     SolverConst sc;
     sdfnmpc_sdf_t sdf = nullptr;
     int cap = 0;
+    int nx = NX, nw = NW, ny = NY;            // stage dimensions of the handle's model (ModelDims)
     double* dt = nullptr;                     // [N] device
     double *xbar = nullptr, *ubar = nullptr;  // warm start
     double *ABt = nullptr;                    // [B][N][16][12] [A B | b] in the tensor-core operand layout
@@ -64,10 +70,11 @@ struct sdfnmpc_solver {
 template <int MODEL>
 __global__ void __launch_bounds__(128, LIN_MIN_BLOCKS) nmpc_linearize_kernel(ModelConst mc, int N, int B, LinIn in, LinOut out) {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)B * (N + 1) * NW;
+    constexpr int NW_ = ModelDims<MODEL>::NW;
+    const long long total = (long long)B * (N + 1) * NW_;
     if (gid >= total) return;
-    const int dir = (int)(gid % NW);
-    const long long node = gid / NW;
+    const int dir = (int)(gid % NW_);
+    const long long node = gid / NW_;
     const int k = (int)(node % (N + 1));
     const int b = (int)(node / (N + 1));
     linearize_dir<MODEL>(mc, N, in, out, b, k, dir);
@@ -85,13 +92,16 @@ struct QpBatch {
     int* counter;          // [2] next instance to draw, slots that ran dry (both zero between launches)
 };
 
-template <int NFIX>
+template <int NFIX, bool PROPS = false>
 #ifdef QP_MAXNREG
 __global__ void __maxnreg__(QP_MAXNREG) nmpc_qp_kernel(
 #else
 __global__ void __launch_bounds__(QP_WARPS * 32, QP_MIN_CTAS) nmpc_qp_kernel(
 #endif
     SolverConst sc, int B, QpBatch q) {
+    constexpr int NX = PROPS ? PD::NX : ::NX, NW = PROPS ? PD::NW : ::NW, NY = PROPS ? PD::NY : ::NY;
+    using Prob = typename std::conditional<PROPS, PropsProb, ::Prob>::type;
+    using Shape = typename std::conditional<PROPS, PropsShape, ::Shape>::type;
     extern __shared__ double sm_all[];
     __shared__ SolverConst scs;
     if (threadIdx.x == 0) scs = sc;
@@ -151,25 +161,27 @@ __global__ void __launch_bounds__(QP_WARPS * 32, QP_MIN_CTAS) nmpc_qp_kernel(
 #if defined(SDFNMPC_QP_SCALAR)
     qp_solve_instance<NX, NU, NY, NH, NFIX>(L, P, sm_all + (size_t)warp * Shape::smem_doubles(N));
 #else
-    qp_solve_mma<NFIX>(L, P, sm_all + (size_t)warp * Shape::smem_doubles(N));
+    if constexpr (PROPS) qp_solve_instance<NX, NU, NY, NH, NFIX>(L, P, sm_all + (size_t)warp * Shape::smem_doubles(N));
+    else qp_solve_mma<NFIX>(L, P, sm_all + (size_t)warp * Shape::smem_doubles(N));
 #endif
     __syncwarp();
     }
 }
 
-__global__ void nmpc_init_traj_kernel(int N, int B, double u_hover, const double* __restrict__ x0,
+__global__ void nmpc_init_traj_kernel(int N, int B, int nx, double u_hover, bool hover_all, const double* __restrict__ x0,
                                       double* __restrict__ xbar, double* __restrict__ ubar) {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long nx_tot = (long long)B * (N + 1) * NX;
+    const long long nx_tot = (long long)B * (N + 1) * nx;
     if (gid < nx_tot) {
-        const int i = (int)(gid % NX);
-        const long long b = gid / ((long long)(N + 1) * NX);
-        xbar[gid] = x0[b * NX + i];
+        const int i = (int)(gid % nx);
+        const long long b = gid / ((long long)(N + 1) * nx);
+        xbar[gid] = x0[b * nx + i];
     }
-    if (gid < (long long)B * N * NU) ubar[gid] = (gid % NU) == 0 ? u_hover : 0.0;
+    // thrust models hover with the first input; the rotor-speed model with all four (quad_props.py:52)
+    if (gid < (long long)B * N * NU) ubar[gid] = (hover_all || (gid % NU) == 0) ? u_hover : 0.0;
 }
 
-__global__ void nmpc_shift_kernel(int N, int B, int s, double* __restrict__ xbar, double* __restrict__ ubar) {
+__global__ void nmpc_shift_kernel(int N, int B, int s, int NX, double* __restrict__ xbar, double* __restrict__ ubar) {
     // Ocp.shift (ocp.py:152-156): for i in k..N-1: x[i-k] = x[i], u[i-k] = u[i]   (node N untouched)
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
@@ -183,6 +195,7 @@ __global__ void nmpc_shift_kernel(int N, int B, int s, double* __restrict__ xbar
 
 template <int MODEL>
 __global__ void nmpc_plant_kernel(ModelConst mc, int B, double dt, double* __restrict__ x, const double* __restrict__ u) {
+    constexpr int NX = ModelDims<MODEL>::NX;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     double xs[NX], us[NU], xn[NX];
@@ -205,9 +218,15 @@ __global__ void nmpc_cmd_acc_kernel(ModelConst mc, int B, const double* __restri
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     double c[4];
-    u_to_acc<MODEL>(mc, x + (size_t)b * NX, u + (size_t)b * NU, c);
+    u_to_acc<MODEL>(mc, x + (size_t)b * ModelDims<MODEL>::NX, u + (size_t)b * NU, c);
     const double lim[4] = {mc.ax, mc.ay, mc.az, mc.wz};                  // controller.py:19-20
     for (int i = 0; i < 4; ++i) cmd[(size_t)b * 4 + i] = fmin(fmax(c[i], -lim[i]), lim[i]);
+}
+
+// u_to_props (quad_props.py:52) + clip to [0, limits.wp] (controller.py:27-29,111-113)
+__global__ void nmpc_cmd_props_kernel(double wp_max, int B, const double* __restrict__ u, double* __restrict__ cmd) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B * NU) cmd[i] = fmin(fmax(u[i] * wp_max, 0.0), wp_max);
 }
 
 extern "C" int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver_desc* d, sdfnmpc_sdf_t sdf) {
@@ -221,10 +240,16 @@ extern "C" int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver
     SolverConst& sc = h->sc;
     sc.mc.g = d->g; sc.mc.gamma = d->gamma; sc.mc.roll = d->roll; sc.mc.pitch = d->pitch; sc.mc.wz = d->wz; sc.mc.mass = d->mass;
     for (int i = 0; i < 3; ++i) sc.mc.cam_off[i] = d->cam_off[i];
-    if (d->model < 0 || d->model > 2) { delete h; return SDFNMPC_E_INVALID; }
+    if (d->model < 0 || d->model > 3) { delete h; return SDFNMPC_E_INVALID; }
     sc.model = d->model;
-    sc.nyN = d->model == MODEL_ACC ? 7 : 4;                                   // quad_acc.py:15 vs quad_rollpitchyawrate*.py:15
-    sc.u_hover = d->model == MODEL_ACC ? 0.0 : d->g / d->gamma;              // quad_acc.py:35, quad_rollpitchyawrate.py:44
+    const bool props = d->model == MODEL_PROPS;
+    sc.nyN = d->model == MODEL_ACC ? 7 : (props ? PROPS_NYN : 4);            // quad_acc.py:15, quad_props.py:15, quad_rollpitchyawrate*.py:15
+    sc.u_hover = d->model == MODEL_ACC ? 0.0 : (props ? d->u_hover_props : d->g / d->gamma);   // quad_acc.py:35, quad_rollpitchyawrate.py:44
+    sc.mc.wp_max = d->wp_max;
+    for (int i = 0; i < 12; ++i) { sc.mc.Gf_m[i] = d->Gf_m[i]; sc.mc.JGt[i] = d->JGt[i]; }
+    for (int i = 0; i < 3; ++i) sc.mc.inertia[i] = d->inertia[i];
+    if (props && !(d->wp_max > 0 && d->inertia[0] > 0 && d->inertia[1] > 0 && d->inertia[2] > 0)) { delete h; return SDFNMPC_E_INVALID; }
+    if (props) { h->nx = PD::NX; h->nw = PD::NW; h->ny = PD::NY; }
     sc.mc.ax = d->ax; sc.mc.ay = d->ay; sc.mc.az = d->az;
     sc.mc.tau_roll = d->tau_roll > 0 ? d->tau_roll : 0.12; sc.mc.tau_pitch = d->tau_pitch > 0 ? d->tau_pitch : 0.12;
     sc.N = d->N; sc.k0 = d->h_at_node0 ? 0 : 1; sc.qp_iter_max = d->qp_iter_max;
@@ -235,7 +260,8 @@ extern "C" int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver
     const double cmin[4] = {0.0, -d->roll, -d->pitch, -d->wz}, cmax[4] = {d->gamma, d->roll, d->pitch, d->wz};
     for (int i = 0; i < 4; ++i) { sc.cmd_min[i] = cmin[i]; sc.cmd_max[i] = cmax[i]; }
     const size_t B = (size_t)h->cap, N = (size_t)d->N, N1 = N + 1;
-    h->work_per_inst = Shape::work_doubles(d->N);
+    const size_t NX = (size_t)h->nx, NW = (size_t)h->nw, NY = (size_t)h->ny;
+    h->work_per_inst = props ? PropsShape::work_doubles(d->N) : Shape::work_doubles(d->N);
     cudaError_t e = cudaSuccess;
     auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
     alloc((void**)&h->dt, N * sizeof(double));
@@ -243,7 +269,7 @@ extern "C" int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver
     alloc((void**)&h->ubar, B * N * NU * sizeof(double));
     alloc((void**)&h->AB, B * N * NX * NW * sizeof(double));
 #if !defined(SDFNMPC_QP_SCALAR)
-    alloc((void**)&h->ABt, B * N * 192 * sizeof(double));
+    if (!props) alloc((void**)&h->ABt, B * N * 192 * sizeof(double));
 #endif
     alloc((void**)&h->bdyn, B * N * NX * sizeof(double));
     alloc((void**)&h->J, B * N1 * NY * NW * sizeof(double));
@@ -254,7 +280,7 @@ extern "C" int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver
     alloc((void**)&h->sdf_d, B * N1 * sizeof(float));
     alloc((void**)&h->sdf_g, B * N1 * 3 * sizeof(float));
     // the QP kernel runs as persistent warps: as many as fit the device at once, each owning one block of scratch
-    h->qp_smem = (size_t)QP_WARPS * Shape::smem_doubles(d->N) * sizeof(double);
+    h->qp_smem = (size_t)QP_WARPS * (props ? PropsShape::smem_doubles(d->N) : Shape::smem_doubles(d->N)) * sizeof(double);
 #if defined(QP_CARVEOUT)
     if (e == cudaSuccess) e = cudaFuncSetAttribute(nmpc_qp_kernel<20>, cudaFuncAttributePreferredSharedMemoryCarveout, QP_CARVEOUT);
 #endif
@@ -264,14 +290,19 @@ extern "C" int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver
         if (h->qp_smem < want) h->qp_smem = want;
     }
 #endif
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(nmpc_qp_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qp_smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(nmpc_qp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qp_smem);
+    if (props) {
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(nmpc_qp_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qp_smem);
+    } else {
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(nmpc_qp_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qp_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(nmpc_qp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qp_smem);
+    }
     {
         int dev = 0, sms = 0, per_sm = 0;
         if (e == cudaSuccess) e = cudaGetDevice(&dev);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (e == cudaSuccess) {
-            if (d->N == 20) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nmpc_qp_kernel<20>, QP_WARPS * 32, h->qp_smem);
+            if (props) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nmpc_qp_kernel<0, true>, QP_WARPS * 32, h->qp_smem);
+            else if (d->N == 20) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nmpc_qp_kernel<20>, QP_WARPS * 32, h->qp_smem);
             else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nmpc_qp_kernel<0>, QP_WARPS * 32, h->qp_smem);
         }
         if (e == cudaSuccess && per_sm < 1) e = cudaErrorLaunchOutOfResources;
@@ -308,9 +339,9 @@ extern "C" int sdfnmpc_solver_destroy(sdfnmpc_solver_t h) {
 extern "C" int sdfnmpc_solver_init_traj(sdfnmpc_solver_t h, const double* x0, int32_t B, void* stream) {
     if (!h || !x0 || B < 1 || B > h->cap) return SDFNMPC_E_INVALID;
     const int N = h->sc.N;
-    const long long total = (long long)B * (N + 1) * NX;
+    const long long total = (long long)B * (N + 1) * h->nx;
     nmpc_init_traj_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        N, B, h->sc.u_hover, x0, h->xbar, h->ubar);
+        N, B, h->nx, h->sc.u_hover, h->sc.model == MODEL_PROPS, x0, h->xbar, h->ubar);
     count_launch();
     SDF_CUDA_CHECK(cudaGetLastError());
     return 0;
@@ -319,7 +350,7 @@ extern "C" int sdfnmpc_solver_init_traj(sdfnmpc_solver_t h, const double* x0, in
 extern "C" int sdfnmpc_solver_shift(sdfnmpc_solver_t h, int32_t B, int32_t k, void* stream) {
     if (!h || B < 1 || B > h->cap || k < 0) return SDFNMPC_E_INVALID;
     if (k == 0) return 0;
-    nmpc_shift_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->sc.N, B, k, h->xbar, h->ubar);
+    nmpc_shift_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->sc.N, B, k, h->nx, h->xbar, h->ubar);
     count_launch();
     SDF_CUDA_CHECK(cudaGetLastError());
     return 0;
@@ -343,10 +374,11 @@ extern "C" int sdfnmpc_solver_rti_step(sdfnmpc_solver_t h, int32_t B, const doub
     if (tm) cudaEventRecord(ev[0], st);
     LinIn in{h->xbar, h->ubar, yref, yrefN, qd, pose, flag, h->dt, h->sc.nyN, x0};
     LinOut lo{h->AB, h->bdyn, h->J, h->yres, h->C, h->hval, h->qpts, h->ABt};
-    const long long total = (long long)B * (N + 1) * NW;
+    const long long total = (long long)B * (N + 1) * h->nw;
     const unsigned lin_grid = (unsigned)((total + 127) / 128);
     if (h->sc.model == MODEL_ATT) nmpc_linearize_kernel<MODEL_ATT><<<lin_grid, 128, 0, st>>>(h->sc.mc, N, B, in, lo);
     else if (h->sc.model == MODEL_ATT_TAU) nmpc_linearize_kernel<MODEL_ATT_TAU><<<lin_grid, 128, 0, st>>>(h->sc.mc, N, B, in, lo);
+    else if (h->sc.model == MODEL_PROPS) nmpc_linearize_kernel<MODEL_PROPS><<<lin_grid, 128, 0, st>>>(h->sc.mc, N, B, in, lo);
     else nmpc_linearize_kernel<MODEL_ACC><<<lin_grid, 128, 0, st>>>(h->sc.mc, N, B, in, lo);
     count_launch();
     SDF_CUDA_CHECK(cudaGetLastError());
@@ -371,7 +403,8 @@ extern "C" int sdfnmpc_solver_rti_step(sdfnmpc_solver_t h, int32_t B, const doub
     q.counter = h->qp_counter;
     const int qp_warps = B < h->qp_slots ? B : h->qp_slots;
     const unsigned qp_grid = (unsigned)((qp_warps + QP_WARPS - 1) / QP_WARPS);
-    if (N == 20) nmpc_qp_kernel<20><<<qp_grid, QP_WARPS * 32, h->qp_smem, st>>>(h->sc, B, q);
+    if (h->sc.model == MODEL_PROPS) nmpc_qp_kernel<0, true><<<qp_grid, QP_WARPS * 32, h->qp_smem, st>>>(h->sc, B, q);
+    else if (N == 20) nmpc_qp_kernel<20><<<qp_grid, QP_WARPS * 32, h->qp_smem, st>>>(h->sc, B, q);
     else nmpc_qp_kernel<0><<<qp_grid, QP_WARPS * 32, h->qp_smem, st>>>(h->sc, B, q);
     count_launch();
     SDF_CUDA_CHECK(cudaGetLastError());
@@ -460,6 +493,7 @@ extern "C" int sdfnmpc_plant_step(sdfnmpc_solver_t h, int32_t B, double* x, cons
     if (!h || !x || !u || B < 1) return SDFNMPC_E_INVALID;
     if (h->sc.model == MODEL_ATT) nmpc_plant_kernel<MODEL_ATT><<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->sc.mc, B, dt, x, u);
     else if (h->sc.model == MODEL_ATT_TAU) nmpc_plant_kernel<MODEL_ATT_TAU><<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->sc.mc, B, dt, x, u);
+    else if (h->sc.model == MODEL_PROPS) nmpc_plant_kernel<MODEL_PROPS><<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->sc.mc, B, dt, x, u);
     else nmpc_plant_kernel<MODEL_ACC><<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->sc.mc, B, dt, x, u);
     count_launch();
     SDF_CUDA_CHECK(cudaGetLastError());
@@ -472,6 +506,7 @@ extern "C" int sdfnmpc_cmd_acc(sdfnmpc_solver_t h, int32_t B, const double* x0, 
     cudaStream_t st = (cudaStream_t)stream;
     if (h->sc.model == MODEL_ATT) nmpc_cmd_acc_kernel<MODEL_ATT><<<grid, 128, 0, st>>>(h->sc.mc, B, x0, u, cmd);
     else if (h->sc.model == MODEL_ATT_TAU) nmpc_cmd_acc_kernel<MODEL_ATT_TAU><<<grid, 128, 0, st>>>(h->sc.mc, B, x0, u, cmd);
+    else if (h->sc.model == MODEL_PROPS) nmpc_cmd_acc_kernel<MODEL_PROPS><<<grid, 128, 0, st>>>(h->sc.mc, B, x0, u, cmd);
     else nmpc_cmd_acc_kernel<MODEL_ACC><<<grid, 128, 0, st>>>(h->sc.mc, B, x0, u, cmd);
     count_launch();
     SDF_CUDA_CHECK(cudaGetLastError());
@@ -479,9 +514,26 @@ extern "C" int sdfnmpc_cmd_acc(sdfnmpc_solver_t h, int32_t B, const double* x0, 
 }
 
 extern "C" int sdfnmpc_cmd_trpyr(sdfnmpc_solver_t h, int32_t B, const double* u, double* cmd, void* stream) {
-    if (!h || !u || !cmd || B < 1 || h->sc.model == MODEL_ACC) return SDFNMPC_E_INVALID;   // 'acc' has no u_to_TRPYr (quad_acc.py)
+    // 'acc' and 'props' have no u_to_TRPYr (quad_acc.py, quad_props.py)
+    if (!h || !u || !cmd || B < 1 || h->sc.model == MODEL_ACC || h->sc.model == MODEL_PROPS) return SDFNMPC_E_INVALID;
     nmpc_cmd_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->sc, B, u, cmd);
     count_launch();
     SDF_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int sdfnmpc_cmd_props(sdfnmpc_solver_t h, int32_t B, const double* u, double* cmd, void* stream) {
+    if (!h || !u || !cmd || B < 1 || h->sc.model != MODEL_PROPS) return SDFNMPC_E_INVALID;
+    nmpc_cmd_props_kernel<<<(B * NU + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->sc.mc.wp_max, B, u, cmd);
+    count_launch();
+    SDF_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int sdfnmpc_solver_dims(sdfnmpc_solver_t h, int32_t* nx, int32_t* ny, int32_t* nyN) {
+    if (!h) return SDFNMPC_E_INVALID;
+    if (nx) *nx = h->nx;
+    if (ny) *ny = h->ny;
+    if (nyN) *nyN = h->sc.nyN;
     return 0;
 }

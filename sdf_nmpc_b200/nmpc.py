@@ -19,8 +19,24 @@ from . import _lib
 from .config import Config
 from .sdf import SdfEvaluator, _ptr, _stream
 
-NX, NU, NY, NH = 10, 4, 11, 3
-MODEL_ID = {'att': 0, 'att_tau': 1, 'acc': 2}      # mpc.model values reachable in gen_model.py:15-17 ('props': not built)
+NX, NU, NY, NH = 10, 4, 11, 3                       # models att / att_tau / acc; 'props': nx 13 (+ 1 pad on the device), ny 16
+MODEL_ID = {'att': 0, 'att_tau': 1, 'acc': 2, 'props': 3}      # mpc.model values reachable in gen_model.py:15-20
+
+
+def props_allocation(motors, cf, ct):
+    """(Gf, Gt) [3, 4] of ``quad_props.py:18-27``: propeller frames ``Rz(i pi / (n/2)) Ry(beta_i) Rx((-1)^i alpha_i)``, the
+    allocation of a generically tilted multi-rotor (``utils/math.py:385-396``), both scaled by the force coefficient."""
+    def rot(axis, a):
+        c, s = np.cos(a), np.sin(a)
+        return np.array({'x': [[1, 0, 0], [0, c, -s], [0, s, c]], 'y': [[c, 0, s], [0, 1, 0], [-s, 0, c]],
+                         'z': [[c, -s, 0], [s, c, 0], [0, 0, 1]]}[axis], float)
+    px, py, pz, alpha, beta, sign = zip(*motors)
+    n = len(sign)
+    ez = [rot('z', i * (np.pi / (n / 2))) @ rot('y', beta[i]) @ rot('x', (-1) ** i * alpha[i]) @ np.array([0.0, 0.0, 1.0]) for i in range(n)]
+    pos = np.array([px, py, pz], float).T
+    Gf = np.column_stack(ez)
+    Gt = np.column_stack([np.cross(pos[i], ez[i]) + ct / cf * sign[i] * ez[i] for i in range(n)])
+    return cf * Gf, cf * Gt
 
 
 class BatchedNmpc:
@@ -33,7 +49,10 @@ class BatchedNmpc:
         if cfg.mpc.model not in MODEL_ID:
             raise NotImplementedError(f"mpc.model == '{cfg.mpc.model}' is not built (available: {sorted(MODEL_ID)})")
         self.model = cfg.mpc.model
-        self.nyN = 7 if self.model == 'acc' else 4        # quad_acc.py:15 / quad_rollpitchyawrate*.py:15
+        self.nyN = {'acc': 7, 'props': 12}.get(self.model, 4)   # quad_acc.py:15 / quad_props.py:15 / quad_rollpitchyawrate*.py:15
+        # stage dimensions: nx as the reference counts it, nxd as the device stores it ('props': 13 states + one pad entry that
+        # stays zero - the QP's staging copies move 16-byte units, see model_att.cuh)
+        self.nx, self.nxd, self.ny = (13, 14, 16) if self.model == 'props' else (NX, NX, NY)
         self.cfg = cfg
         self.B = int(batch)
         self.N = int(cfg.mpc.N)
@@ -67,6 +86,20 @@ class BatchedNmpc:
         d.cam_off = (C.c_double * 3)(*cfg.cam_offset())
         d.lbu = (C.c_double * 4)(-1 if self.model == 'acc' else 0, -1, -1, -1)   # quad_rollpitchyawrate.py:58-59, quad_acc.py:50-51
         d.model = MODEL_ID[self.model]
+        if self.model == 'props':
+            # quad_props.py:18-38,51-52,62-63 on robot.alloc / robot.inertia / limits.wp (default.yaml:78-87,108)
+            al = cfg.robot.alloc
+            Gf, Gt = props_allocation(al.motors, float(al.cf), float(al.ct))
+            inertia = np.asarray(cfg.robot.inertia, float)
+            d.lbu = (C.c_double * 4)(0, 0, 0, 0)
+            d.wp_max = float(lim.wp)
+            d.Gf_m = (C.c_double * 12)(*(Gf / cfg.robot.mass).ravel())
+            d.JGt = (C.c_double * 12)(*(Gt / inertia[:, None]).ravel())
+            d.inertia = (C.c_double * 3)(*inertia)
+            self.wh = float(np.sqrt(cfg.robot.mass * self.g / 4 / al.cf))        # hover rotor speed (quad_props.py:51)
+            # DEVIATION: quad_props.py:52 starts Ocp.init at u = wh (a rotor speed) although the inputs are normalised speeds
+            # in [0, 1]; from there the first QPs end at the iteration cap (oracle/models.py).  The hover input is wh / limits.wp.
+            d.u_hover_props = self.wh / float(lim.wp)
         d.ax, d.ay, d.az = float(lim.ax), float(lim.ay), float(lim.az)
         d.tau_roll = d.tau_pitch = 0.12                   # quad_rollpitchyawrate_tau.py:19-20 (constants in the reference)
         d.sdf_cost_w = self.sdf_cost_w
@@ -84,6 +117,9 @@ class BatchedNmpc:
         self.cmd_TRPYr_hover = np.array([cfg.robot.mass * self.g, 0, 0, 0])
         self.cmd_TRPYr_min = [0, -lim.roll, -lim.pitch, -lim.wz]
         self.cmd_TRPYr_max = [lim.gamma, lim.roll, lim.pitch, lim.wz]
+        self.cmd_props_hover = np.array([cfg.robot.mass * self.g / 4] * 4)       # controller.py:27 (as written there)
+        self.cmd_props_min = [0] * 4
+        self.cmd_props_max = [lim.get('wp', 0.0)] * 4
         f64 = dict(dtype=torch.float64, device=self.device)
         B, N = self.B, self.N
         self.u0 = torch.zeros(B, NU, **f64)
@@ -109,7 +145,7 @@ class BatchedNmpc:
         """Offsets (in doubles) of the per-step inputs inside ONE device block: a host caller fills a pinned mirror with the
         same layout and uploads it with a single copy (``Nmpc``)."""
         B, N = self.B, self.N
-        sizes = (('x0', (B, NX)), ('y', (B, N, NY)), ('W', (B, N, NY)), ('yN', (B, self.nyN)), ('WN', (B, self.nyN)),
+        sizes = (('x0', (B, self.nxd)), ('y', (B, N, self.ny)), ('W', (B, N, self.ny)), ('yN', (B, self.nyN)), ('WN', (B, self.nyN)),
                  ('qd', (B, N + 1, 4)), ('flag', (B,)), ('pose', (B, 12)))
         off, lay = 0, {}
         for name, shp in sizes:
@@ -162,14 +198,14 @@ class BatchedNmpc:
     def set_x0(self, x0):
         """controller.py:65-69: the first call initialises the trajectory (ocp.py:144-149)."""
         if x0 is not self._x0:
-            self._x0.copy_(torch.as_tensor(x0, dtype=torch.float64).reshape(self.B, -1)[:, :NX], non_blocking=True)
+            self._x0[:, :self.nx].copy_(torch.as_tensor(x0, dtype=torch.float64).reshape(self.B, -1)[:, :self.nx], non_blocking=True)
         if self.x0 is None:
             _lib.check(self.lib.sdfnmpc_solver_init_traj(self.handle, _ptr(self._x0), self.B, _stream()), 'init_traj')
         self.x0 = self._x0
 
     def set_ref_arrays(self, yref, W, yrefN, WN, qd):
-        self.y[:] = self._t(yref, (self.B, self.N, NY))
-        self.W[:] = self._t(W, (self.B, self.N, NY))
+        self.y[:] = self._t(yref, (self.B, self.N, self.ny))
+        self.W[:] = self._t(W, (self.B, self.N, self.ny))
         self.yN[:] = self._t(yrefN, (self.B, self.nyN))
         self.WN[:] = self._t(WN, (self.B, self.nyN))
         self.qd[:] = self._t(qd, (self.B, self.N + 1, 4))
@@ -178,6 +214,10 @@ class BatchedNmpc:
         """quad_rollpitchyawrate.py:62-65 / quad_rollpitchyawrate_tau.py:61-64 (same rows).  For 'acc' the rows are those
         of quad_acc.py:54-58; that function reads an undefined name in the reference (it cannot run there), so the row
         order it spells out is used with the weights of `ref` itself."""
+        if self.model == 'props':          # quad_props.py:66-69
+            yr = np.concatenate([ref.p, [0, 0, 0], ref.v, [0, 0, ref.wz], [self.wh] * 4])
+            W = np.concatenate([ref.Wp, ref.Wq, ref.Wv, ref.Ww, [ref.Wa] * 4])
+            return yr, W
         if self.model == 'acc':
             yr = np.concatenate([ref.p, [0], ref.v, [0, 0, 0], [ref.wz]])
             W = np.concatenate([ref.Wp, ref.Wq[2:], ref.Wv, [ref.Wa, ref.Wa, ref.Wa], [ref.Ww[2]]])
@@ -262,10 +302,10 @@ class BatchedNmpc:
         stream (lets a caller append its own device work and read everything back with ONE synchronisation)."""
         pin = self._pin.get('x0')
         if pin is None:
-            pin = self._pin['x0'] = torch.empty(self.B, NX, dtype=torch.float64).pin_memory()
+            pin = self._pin['x0'] = torch.zeros(self.B, self.nxd, dtype=torch.float64).pin_memory()
             self._pin['u0'] = torch.empty(self.B, NU, dtype=torch.float64).pin_memory()
             self._pin['st'] = torch.empty(self.B, dtype=torch.int32).pin_memory()
-        pin.copy_(torch.as_tensor(x0, dtype=torch.float64).reshape(self.B, -1)[:, :NX])
+        pin[:, :self.nx].copy_(torch.as_tensor(x0, dtype=torch.float64).reshape(self.B, -1)[:, :self.nx])
         self._x0.copy_(pin, non_blocking=True)
         self.set_x0(self._x0)
         self.solve()
@@ -294,16 +334,18 @@ class BatchedNmpc:
     def get_matrices(self):
         """controller.py:84-92 -> (x [B,N+1,10], u [B,N,4]) device tensors (copies)."""
         xb, ub, _, _ = self._state_ptrs()
-        return (self._view(xb, (self.B, self.N + 1, NX), torch.float64), self._view(ub, (self.B, self.N, NU), torch.float64))
+        x = self._view(xb, (self.B, self.N + 1, self.nxd), torch.float64)
+        return (x[:, :, :self.nx] if self.nxd != self.nx else x), self._view(ub, (self.B, self.N, NU), torch.float64)
 
     def set_matrices(self, x, u):
         """Overwrite the SQP iterate (x [B,N+1,10], u [B,N,4]) - the batched form of the per-node ``solver.set(k, 'x'|'u', .)``
         calls of ``ocp.py:144-149``; used to warm-start from an external trajectory."""
         xb, ub, _, _ = self._state_ptrs()
-        self._view(xb, (self.B, self.N + 1, NX), torch.float64, copy=False).copy_(self._t(x, (self.B, self.N + 1, NX)))
+        self._view(xb, (self.B, self.N + 1, self.nxd), torch.float64, copy=False)[:, :, :self.nx].copy_(self._t(x, (self.B, self.N + 1, self.nx)))
         self._view(ub, (self.B, self.N, NU), torch.float64, copy=False).copy_(self._t(u, (self.B, self.N, NU)))
         if self.x0 is None:
-            self.x0 = self._t(x, (self.B, self.N + 1, NX))[:, 0].contiguous()
+            self._x0[:, :self.nx] = self._t(x, (self.B, self.N + 1, self.nx))[:, 0]
+            self.x0 = self._x0
 
     def get_multipliers(self):
         """QP multipliers of the last step: lam_hard [B,N,8] (lbu, ubu), lam_soft [B,N+1,6] (lh, uh)."""
@@ -331,15 +373,23 @@ class BatchedNmpc:
         _lib.check(self.lib.sdfnmpc_cmd_acc(self.handle, self.B, _ptr(self.x0), _ptr(self.u0), _ptr(cmd), _stream()), 'cmd_acc')
         return cmd
 
+    def get_cmd_props(self):
+        """controller.py:111-113: rotor speeds u * limits.wp clipped to [0, limits.wp] (model 'props' only)."""
+        if self.model != 'props':
+            raise _lib.SdfNmpcError(f"get_cmd_props: model '{self.model}' has no u_to_props (quad_props.py:52)")
+        cmd = torch.empty(self.B, 4, dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.sdfnmpc_cmd_props(self.handle, self.B, _ptr(self.u0), _ptr(cmd), _stream()), 'cmd_props')
+        return cmd
+
     def get_openloop_traj(self):
         """controller.py:116-122: predicted (position, quaternion) per node, node 0 = x0."""
         x, _ = self.get_matrices()
-        x[:, 0] = self.x0
+        x[:, 0] = self.x0[:, :self.nx]
         return x[:, :, 0:3], x[:, :, 3:7]
 
     def eval(self, k):
         """controller.py:125-130: SDF value at node k of the current solution, ignoring the flag."""
-        xb = self._view(self._state_ptrs()[0], (self.B, self.N + 1, NX), torch.float64, copy=False)   # node k read in place
+        xb = self._view(self._state_ptrs()[0], (self.B, self.N + 1, self.nxd), torch.float64, copy=False)   # node k read in place
         R = self.pose[:, 3:12].reshape(-1, 3, 3)
         c0 = torch.einsum('bji,bj->bi', R, xb[:, k, 0:3] - self.pose[:, 0:3]).to(torch.float32)
         if self._latent_dirty:
@@ -397,6 +447,12 @@ class BatchedNmpc:
 
     def plant_step(self, x, u, dt):
         """x <- RK4(x, u, dt) with the controller's own model (closed-loop rollouts)."""
+        if x.shape[1] != self.nxd:             # 'props': the device state carries one pad entry
+            xd = torch.zeros(x.shape[0], self.nxd, dtype=torch.float64, device=self.device)
+            xd[:, :self.nx] = x
+            _lib.check(self.lib.sdfnmpc_plant_step(self.handle, x.shape[0], _ptr(xd), _ptr(u), float(dt), _stream()), 'plant_step')
+            x.copy_(xd[:, :self.nx])
+            return x
         _lib.check(self.lib.sdfnmpc_plant_step(self.handle, x.shape[0], _ptr(x), _ptr(u), float(dt), _stream()), 'plant_step')
         return x
 
@@ -428,6 +484,7 @@ class Nmpc:
         self._fc = torch.zeros(1, dtype=torch.int64).pin_memory()
         self.cmd_acc_hover, self.cmd_acc_min, self.cmd_acc_max = self._b.cmd_acc_hover, self._b.cmd_acc_min, self._b.cmd_acc_max
         self.cmd_TRPYr_hover, self.cmd_TRPYr_min, self.cmd_TRPYr_max = self._b.cmd_TRPYr_hover, self._b.cmd_TRPYr_min, self._b.cmd_TRPYr_max
+        self.cmd_props_hover, self.cmd_props_min, self.cmd_props_max = self._b.cmd_props_hover, self._b.cmd_props_min, self._b.cmd_props_max
         self.reset()
 
     def reset(self):
@@ -452,8 +509,8 @@ class Nmpc:
         self._b._latent_dirty = True
 
     def set_x0(self, x0):
-        self.x0 = np.asarray(x0, float)[:NX]
-        self._hv['x0'][0] = self.x0
+        self.x0 = np.asarray(x0, float)[:self._b.nx]
+        self._hv['x0'][0, :self._b.nx] = self.x0
 
     def set_ref(self, ref, k):
         y, W = self._b.formate_ref(ref)
@@ -498,6 +555,9 @@ class Nmpc:
 
     def get_cmd_acc(self):
         return self._b.get_cmd_acc()[0].cpu().numpy()
+
+    def get_cmd_props(self):
+        return self._b.get_cmd_props()[0].cpu().numpy()
 
     def get_openloop_traj(self):
         p, q = self._b.get_openloop_traj()

@@ -51,16 +51,22 @@ class RefTraj:
     wz: torch.Tensor    # [B,N+1]
     zero_Wp: bool = False
 
-    def arrays(self, model, weights):
-        """(yref [B,N,11], W [B,N,11], yrefN [B,nyN], WN [B,nyN], qd [B,N+1,4]) with the row layout of the model's
-        ``formate_ref`` (quad_rollpitchyawrate.py:62-65, quad_rollpitchyawrate_tau.py:61-64, quad_acc.py:54-58).
+    def arrays(self, model, weights, wh=None):
+        """(yref [B,N,ny], W [B,N,ny], yrefN [B,nyN], WN [B,nyN], qd [B,N+1,4]) with the row layout of the model's
+        ``formate_ref`` (quad_rollpitchyawrate.py:62-65, quad_rollpitchyawrate_tau.py:61-64, quad_acc.py:54-58,
+        quad_props.py:66-69 - ``wh``: the hover rotor speed that model uses as input reference).
         ``weights``: mapping with pos, vel, att, rates (3 each) and acc (scalar) - one of ``cfg.mpc.weights.set_const_*``."""
         B, N1, _ = self.p.shape
         dev, dt = self.p.device, self.p.dtype
         zero = torch.zeros(B, N1, 1, device=dev, dtype=dt)
         Wp = [0.0, 0.0, 0.0] if self.zero_Wp else list(weights['pos'])
         Wq, Wv, Ww, Wa = list(weights['att']), list(weights['vel']), list(weights['rates']), float(weights['acc'])
-        if model == 'acc':
+        if model == 'props':
+            hov = torch.full((B, N1, 4), float(wh), device=dev, dtype=dt)
+            y = torch.cat([self.p, zero, zero, zero, self.v, zero, zero, self.wz[..., None], hov], -1)
+            Wrow = Wp + Wq + Wv + Ww + [Wa] * 4
+            nyN = 12
+        elif model == 'acc':
             y = torch.cat([self.p, zero, self.v, zero, zero, zero, self.wz[..., None]], -1)
             Wrow = Wp + [Wq[2]] + Wv + [Wa, Wa, Wa] + [Ww[2]]
             nyN = 7
@@ -71,7 +77,7 @@ class RefTraj:
         key = (model, tuple(Wrow), str(dev), dt)
         if key not in _WROW:             # device constant, built once (no host-to-device copy per control step)
             _WROW[key] = torch.tensor(Wrow, device=dev, dtype=dt)
-        W = _WROW[key].expand(B, N1, 11)
+        W = _WROW[key].expand(B, N1, len(Wrow))
         return (y[:, :-1].contiguous(), W[:, :-1].contiguous(), y[:, -1, :nyN].contiguous(), W[:, -1, :nyN].contiguous(),
                 self.q.contiguous())
 

@@ -57,6 +57,8 @@ class Rollout:
         BRC = torch.tensor(np.asarray(cfg.sensor.B_R_C, float), device=dev)
         self.W_p_Co = torch.einsum('bij,j->bi', self.R0, BpC) + self.p0        # camera pose when the frame was taken (scene is static)
         self.W_R_Co = self.R0 @ BRC
+        if cfg.mpc.model == 'props':
+            raise NotImplementedError("rollout records hold the 10-entry state of the att / att_tau / acc models; 'props' is driven through BatchedNmpc directly")
         self.mpc.set_sdf_flag(1.0)
         self.weights = cfg.mpc.weights.set_const_on
         z64 = lambda: torch.zeros(n_env, dtype=torch.float64, device=dev)
