@@ -225,6 +225,43 @@ def test_single_instance_facade(cuda_device):
     assert np.abs(out['u0'][0] - u).max() <= U_TOL
 
 
+def test_single_instance_facade_props(cuda_device):
+    """The reference's call sequence with mpc.model = 'props' (gen_model.py:20): 13-entry states in and out, 16 / 12 output rows from
+    formate_ref (quad_props.py:66-69), get_cmd_props clipped to [0, limits.wp], and the oracle's first control."""
+    import types
+    from sdf_nmpc_b200 import synth
+    from sdf_nmpc_b200.config import Config
+    from sdf_nmpc_b200.nmpc import Nmpc
+    from oracle import rti
+    net = synth.make_sdf_net(seed=0, **synth.ARCH_B, calibrated=True)
+    cfg = Config(); cfg.mpc.model = 'props'
+    mpc = Nmpc(cfg, net)
+    x0 = np.array([0, 0, 2, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0.0, 99.0])     # a longer state vector is cut to nx like controller.py:67
+    mpc.set_sdf_flag(True)
+    mpc.set_latent(synth.latent(seed=2), x0[:3], np.eye(3))
+    won = cfg.mpc.weights.set_const_on
+    for k in range(cfg.mpc.N + 1):
+        ref = types.SimpleNamespace(p=x0[:3] + np.array([3.0, 0, 0]) * k * 0.075, q=[1.0, 0, 0, 0], v=[3.0, 0, 0], wz=0.0,
+                                    Wp=won.pos, Wq=won.att, Wv=won.vel, Ww=won.rates, Wa=won.acc)
+        mpc.set_ref(ref, k)
+    mpc.set_x0(x0)
+    assert mpc.solve() == 0
+    u = mpc.get_u()
+    x, uu = mpc.get_matrices()
+    assert u.shape == (4,) and x.shape == (21, 13) and uu.shape == (20, 4) and np.all((u >= -1e-9) & (u <= 1 + 1e-9))
+    cmd = mpc.get_cmd_props()
+    assert cmd.shape == (4,) and np.all((cmd >= 0) & (cmd <= 25.0)) and np.abs(cmd - np.clip(u * 25.0, 0, 25.0)).max() < 1e-12
+    assert mpc.get_cmd_acc().shape == (4,) and len(mpc.get_openloop_traj()) == 21
+    ocfg = rti.default_cfg('props')
+    prob = dict(x0=x0[None, :13], yref=mpc._b.y.cpu().numpy(), W=mpc._b.W.cpu().numpy(), yrefN=mpc._b.yN.cpu().numpy(),
+                WN=mpc._b.WN.cpu().numpy(), qd=mpc._b.qd.cpu().numpy(), flag=np.ones(1), latent=synth.latent(seed=2)[None],
+                W_p_Co=mpc._b.pose[:, :3].cpu().numpy(), W_R_Co=mpc._b.pose[:, 3:].cpu().numpy().reshape(1, 3, 3))
+    assert prob['yref'].shape == (1, 20, 16) and prob['yrefN'].shape == (1, 12)
+    xb, ub = rti.init_traj(prob['x0'], ocfg)
+    _, _, out = rti.rti_step(net, xb, ub, prob, ocfg)
+    assert np.abs(out['u0'][0] - u).max() <= U_TOL
+
+
 def test_full_sqp_iteration_counts_match_oracle(cuda_device):
     """Full-SQP mode (BASELINE configs[4]): iterate to convergence of the step; per-instance SQP iteration counts and
     the controls at convergence are compared with the oracle's loop.  (With the reference's lm_reg = 10 the Gauss-Newton
