@@ -54,9 +54,16 @@ struct ConvTcParams {
     const float* resid;           // [B][Cout][Hout][Wout] or null
     int act;
     float* out;                   // [B][Cout][Hout][Wout]
+    // Split-K (the single-frame latency path): the K chunks of a tile are divided over `ksplit` work items, each of which
+    // writes its raw accumulator to part[split][B][Cout][Hout][Wout]; conv_splitk_reduce_kernel adds the parts IN FIXED ORDER
+    // and applies bias / residual / activation.  ksplit = 1, part = null: the epilogue below does it directly.
+    int ksplit;
+    float* part;
     long long* trace;             // development: clock64 samples of CTA 0's issuer, [sub-chunk][4] (null = off)
 };
 
+// SPLIT = false is the batch kernel (ksplit == 1 at compile time: the split bookkeeping costs it 6 % at 64 frames otherwise)
+template <bool SPLIT>
 __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcParams P) {
     using namespace tc;
     extern __shared__ __align__(1024) unsigned char cv_smem_raw[];
@@ -88,8 +95,10 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     const int n_ptiles = (int)((P.npix + TC_TM - 1) / TC_TM);
-    const int n_items = n_ptiles * P.n_ntiles;                       // item = pixel tile * n_ntiles + n tile
+    const int KSP = SPLIT ? P.ksplit : 1;
+    const int n_items = n_ptiles * P.n_ntiles * KSP;                 // item = (pixel tile * n_ntiles + n tile) * ksplit + k split
     const int nk = P.n_kchunks;
+    const size_t out_total = (size_t)P.npix * P.Cout;
     const int hw = P.Hout * P.Wout;
     uint32_t chunk = 0;                                              // stage = chunk & 1, phase = (chunk >> 1) & 1
 
@@ -99,7 +108,9 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
         const uint32_t lane_addr = tmem_base + ((uint32_t)(lq * 32) << 16);
         uint32_t item_it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_it) {
-            const int pt = item / P.n_ntiles, nt = item - pt * P.n_ntiles;
+            const int ksp = item % KSP, tile = item / KSP;
+            const int pt = tile / P.n_ntiles, nt = tile - pt * P.n_ntiles;
+            const int kc0 = (int)((long long)ksp * nk / KSP), kc1 = (int)((long long)(ksp + 1) * nk / KSP);
             const long long pix = (long long)pt * TC_TM + row;
             const bool pvalid = pix < P.npix;
             int pb = 0, oy = 0, ox = 0, r = 0;
@@ -111,7 +122,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
             }
             const int iy0 = oy * P.stride - P.pad, ix0 = ox * P.stride - P.pad;
             const float* inb = P.in + (size_t)pb * P.Cin * P.Hin * P.Win + (long long)iy0 * P.Win + ix0;
-            for (int kc = 0; kc < nk; ++kc, ++chunk) {
+            for (int kc = kc0; kc < kc1; ++kc, ++chunk) {
                 if ((int)(chunk & 1) != g) continue;
                 const int4* kt = P.ktab + kc * TC_KC + ch * 16;
                 float v[16];
@@ -138,7 +149,13 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
             for (int c0 = c_begin; c0 < c_begin + ncol; c0 += 16) {
                 float v[16];
                 tc_ld16(acc + c0, v);
-                if (pvalid) {
+                if (SPLIT && pvalid) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const int co = nt * P.NT + c0 + e;
+                        P.part[(size_t)ksp * out_total + ((size_t)pb * P.Cout + co) * hw + r] = v[e];
+                    }
+                } else if (!SPLIT && pvalid) {
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
                         const int co = nt * P.NT + c0 + e;
@@ -157,22 +174,42 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
         const uint32_t leader = elect_one();
         const int NS = P.NT < CV_NSUB ? P.NT : CV_NSUB, nsub = P.NT / NS;       // sub-chunks per chunk
         const uint32_t sub_bytes = (uint32_t)NS * TC_KC * 4 * 2;
-        const int my_items = blockIdx.x < n_items ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-        const uint64_t n_sub_total = (uint64_t)my_items * nk * nsub;
         if (warp == CV_PROD_WARPS + 1) {
             // ============================== weight streamer ==============================
-            int pf_item = blockIdx.x, pf_kc = 0, pf_h = 0;
-            for (uint64_t pf = 0; pf < n_sub_total; ++pf) {
-                const uint32_t q = (uint32_t)(pf % CV_WSTAGES);
-                mbar_wait(wfree0 + 8 * q, (uint32_t)(((pf / CV_WSTAGES) & 1) ^ 1));      // previous user of the slot has retired
-                if (leader) {
-                    const int pnt = pf_item % P.n_ntiles;
-                    mbar_expect_tx(wfull0 + 8 * q, sub_bytes);
-                    bulk_g2s(smem_u32(wst0 + q * CV_WSTAGE_BYTES), P.wblob + (((size_t)pnt * nk + pf_kc) * nsub + pf_h) * sub_bytes, sub_bytes,
-                             wfull0 + 8 * q);
+            if constexpr (!SPLIT) {
+                // batch kernel: one flat loop over the sub-chunks of all of this CTA's items
+                const int my_items = blockIdx.x < n_items ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+                const uint64_t n_sub_total = (uint64_t)my_items * nk * nsub;
+                int pf_item = blockIdx.x, pf_kc = 0, pf_h = 0;
+                for (uint64_t pf = 0; pf < n_sub_total; ++pf) {
+                    const uint32_t q = (uint32_t)(pf % CV_WSTAGES);
+                    mbar_wait(wfree0 + 8 * q, (uint32_t)(((pf / CV_WSTAGES) & 1) ^ 1));      // previous user of the slot has retired
+                    if (leader) {
+                        const int pnt = pf_item % P.n_ntiles;
+                        mbar_expect_tx(wfull0 + 8 * q, sub_bytes);
+                        bulk_g2s(smem_u32(wst0 + q * CV_WSTAGE_BYTES), P.wblob + (((size_t)pnt * nk + pf_kc) * nsub + pf_h) * sub_bytes, sub_bytes,
+                                 wfull0 + 8 * q);
+                    }
+                    __syncwarp();
+                    if (++pf_h == nsub) { pf_h = 0; if (++pf_kc == nk) { pf_kc = 0; pf_item += gridDim.x; } }
                 }
-                __syncwarp();
-                if (++pf_h == nsub) { pf_h = 0; if (++pf_kc == nk) { pf_kc = 0; pf_item += gridDim.x; } }
+            } else {
+                uint64_t pf = 0;
+                for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                    const int ksp = item % KSP, pnt = (item / KSP) % P.n_ntiles;
+                    const int kc0 = (int)((long long)ksp * nk / KSP), kc1 = (int)((long long)(ksp + 1) * nk / KSP);
+                    for (int kc = kc0; kc < kc1; ++kc)
+                        for (int h = 0; h < nsub; ++h, ++pf) {
+                            const uint32_t q = (uint32_t)(pf % CV_WSTAGES);
+                            mbar_wait(wfree0 + 8 * q, (uint32_t)(((pf / CV_WSTAGES) & 1) ^ 1));      // previous user of the slot has retired
+                            if (leader) {
+                                mbar_expect_tx(wfull0 + 8 * q, sub_bytes);
+                                bulk_g2s(smem_u32(wst0 + q * CV_WSTAGE_BYTES), P.wblob + (((size_t)pnt * nk + kc) * nsub + h) * sub_bytes, sub_bytes,
+                                         wfull0 + 8 * q);
+                            }
+                            __syncwarp();
+                        }
+                }
             }
         } else {
             // ============================== MMA issuer ==============================
@@ -181,7 +218,9 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
             uint64_t jj = 0;                                                         // sub-chunk counter (W stage = jj % 4)
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_it) {
                 const uint32_t dcol = tmem_base + (item_it & 1) * 256u;
-                for (int kc = 0; kc < nk; ++kc, ++chunk) {
+                const int ksp = item % KSP;
+                const int kc0 = (int)((long long)ksp * nk / KSP), kc1 = (int)((long long)(ksp + 1) * nk / KSP);
+                for (int kc = kc0; kc < kc1; ++kc, ++chunk) {
                     const int s = chunk & 1;
                     const uint32_t a_hi = smem_u32(ast0) + (uint32_t)s * TC_ASTAGE_BYTES;
                     const uint64_t ad_hi = make_desc(a_hi), ad_lo = make_desc(a_hi + TC_ASTAGE_BYTES / 2);
@@ -200,14 +239,14 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
                         if (elect_one()) {
 #pragma unroll
                             for (int ks = 0; ks < TC_KC / 8; ++ks) {
-                                tc_mma_tf32(dc, ad_hi + 2 * ks, wd_hi + 2 * ks, idesc, (kc == 0 && ks == 0) ? 0u : 1u);
+                                tc_mma_tf32(dc, ad_hi + 2 * ks, wd_hi + 2 * ks, idesc, (kc == kc0 && ks == 0) ? 0u : 1u);
                                 tc_mma_tf32(dc, ad_lo + 2 * ks, wd_hi + 2 * ks, idesc, 1u);
                                 tc_mma_tf32(dc, ad_hi + 2 * ks, wd_lo + 2 * ks, idesc, 1u);
                             }
                             tc_commit(wfree0 + 8 * q);
                             if (h == nsub - 1) {
                                 tc_commit(sfree0 + 8 * s);
-                                if (kc == nk - 1) tc_commit(dfull);
+                                if (kc == kc1 - 1) tc_commit(dfull);
                             }
                         }
                         __syncwarp();
@@ -222,6 +261,21 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
     if (warp == CV_PROD_WARPS) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
+}
+
+// Second half of a split-K convolution: out = act(sum_s part[s] + bias + resid), parts added in the fixed order s = 0, 1, ...
+__global__ void conv_splitk_reduce_kernel(const float* __restrict__ part, int ksplit, long long total, int Cout, int hw,
+                                          const float* __restrict__ bias, const float* __restrict__ resid, int act,
+                                          float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    float acc = part[i];
+    for (int s = 1; s < ksplit; ++s) acc += part[(size_t)s * total + i];
+    float val = acc + __ldg(bias + (int)((i / hw) % Cout));
+    if (resid) val += __ldg(resid + i);
+    if (act == CV_ACT_RELU) val = fmaxf(val, 0.f);
+    else if (act == CV_ACT_ELU) val = val > 0.f ? val : expm1f(val);
+    out[i] = val;
 }
 
 }  // namespace sdfnmpc

@@ -327,9 +327,13 @@ struct sdfnmpc_encoder {
     int Hp, Wp;       // after max-pool
     int Hf, Wf;       // final feature map
     float *h_img = nullptr, *h_lat = nullptr;
+    float* part = nullptr;      // split-K partial accumulators of the single-frame path
+    size_t part_floats = 0;
 };
 
 static int out_dim(int in, int k, int s, int p) { return (in + 2 * p - k) / s + 1; }
+constexpr int ENC_SPLIT_MAX_B = 4;      // batches of up to this many frames take the split-K latency path (conv_ksplit)
+static int conv_ksplit(const Layer& L, int B, int sm_count);
 
 static int upload(float** dst, const std::vector<float>& v) {
     SDF_CUDA_CHECK(cudaMalloc(dst, v.size() * sizeof(float)));
@@ -437,6 +441,20 @@ extern "C" int sdfnmpc_encoder_create(sdfnmpc_encoder_t* out, const sdfnmpc_enco
     for (int i = 0; i < 3 && !rc; ++i) rc = (int)cudaMalloc(&h->buf[i], h->buf_floats * sizeof(float));
     if (!rc) rc = (int)cudaMalloc(&h->yz, (size_t)H0 * W0 * sizeof(float));
     if (!rc) {
+        // split-K scratch of the small-batch path: the largest ksplit x output of any tensor-core layer at B = ENC_SPLIT_MAX_B
+        int dev = 0, sms = 0;
+        rc = (int)cudaGetDevice(&dev);
+        if (!rc) rc = (int)cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const Layer* ls[] = {&h->c1[0], &h->c1[1], &h->c1[2], &h->c1[3], &h->c2[0], &h->c2[1], &h->c2[2], &h->c2[3], &h->sc[1], &h->sc[2], &h->sc[3]};
+        for (const Layer* l : ls)
+            if (l->wblob_tc && !rc) {
+                const int ks = conv_ksplit(*l, 1, sms);
+                const size_t nb = (size_t)std::min(d->max_batch, ENC_SPLIT_MAX_B);
+                if (ks > 1) h->part_floats = std::max(h->part_floats, (size_t)ks * nb * l->s.Cout * l->s.Hout * l->s.Wout);
+            }
+        if (!rc && h->part_floats) rc = (int)cudaMalloc(&h->part, h->part_floats * sizeof(float));
+    }
+    if (!rc) {
         // torch.tan(torch.tensor(hfov, dtype=float32)): tangent evaluated on the float32-rounded angle
         yz_table_kernel<<<(H0 * W0 + 255) / 256, 256>>>(H0, W0, tanf((float)d->hfov), tanf((float)d->vfov), h->yz);
         count_launch();
@@ -454,7 +472,7 @@ extern "C" int sdfnmpc_encoder_destroy(sdfnmpc_encoder_t h) {
     for (Layer* l : ls) { cudaFree(l->w); cudaFree(l->b); cudaFree(l->wblob_tc); cudaFree(l->ktab); }
     cudaFree(h->mean_w); cudaFree(h->mean_b); cudaFree(h->yz);
     for (float* b : h->buf) cudaFree(b);
-    cudaFree(h->h_img); cudaFree(h->h_lat);
+    cudaFree(h->h_img); cudaFree(h->h_lat); cudaFree(h->part);
     delete h;
     return 0;
 }
@@ -469,7 +487,23 @@ static bool enc_use_tc() {
     return v == 1;
 }
 
-static int launch_conv_tc(const Layer& L, int B, const float* in, const float* resid, int act, float* out, cudaStream_t st) {
+// Split-K factor of a layer.  A single frame is the reference's operating point (vae.py:31-40): its deep layers have 2-16 tiles
+// for 148 SMs and a K of up to 144 chunks, so the tile's K range is divided over the idle SMs (>= 2 chunks each).  The factor is
+// a function of the LAYER only - the one that suits a single frame - and applies to batches of up to ENC_SPLIT_MAX_B frames, so
+// that a row does not depend on which small batch it is encoded in.  Larger batches are never split (their rows must not depend
+// on how a set of frames is divided into batches either: shard invariance of the rollouts); between the two regimes a row
+// differs by the summation order only (measured 3e-5, the split being the one closer to the float64 oracle).
+static int conv_ksplit(const Layer& L, int B, int sm_count) {
+    if (B > ENC_SPLIT_MAX_B) return 1;
+    const long long n_tiles = ((long long)L.s.Hout * L.s.Wout + TC_TM - 1) / TC_TM * L.n_ntiles;      // of ONE frame
+    if (n_tiles * 2 > sm_count) return 1;
+    const long long by_sm = sm_count / n_tiles, by_k = L.n_kchunks / 2;
+    const long long k = by_sm < by_k ? by_sm : by_k;
+    return k < 2 ? 1 : (int)k;
+}
+
+static int launch_conv_tc(const Layer& L, int B, const float* in, const float* resid, int act, float* out, cudaStream_t st,
+                          float* part = nullptr, size_t part_floats = 0) {
     static int sm_count = 0;
     static bool attr_set = false;
     if (!sm_count) {
@@ -478,7 +512,8 @@ static int launch_conv_tc(const Layer& L, int B, const float* in, const float* r
         SDF_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
     if (!attr_set) {
-        SDF_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM_BYTES));
+        SDF_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM_BYTES));
+        SDF_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM_BYTES));
         attr_set = true;
     }
     ConvTcParams P;
@@ -487,7 +522,10 @@ static int launch_conv_tc(const Layer& L, int B, const float* in, const float* r
     P.npix = (long long)B * L.s.Hout * L.s.Wout;
     P.NT = L.NT; P.n_ntiles = L.n_ntiles; P.n_kchunks = L.n_kchunks;
     P.in = in; P.wblob = L.wblob_tc; P.ktab = L.ktab; P.bias = L.b; P.resid = resid; P.act = act; P.out = out;
-    const long long n_items = (P.npix + TC_TM - 1) / TC_TM * L.n_ntiles;
+    P.ksplit = part ? conv_ksplit(L, B, sm_count) : 1;
+    if ((size_t)P.ksplit * P.npix * P.Cout > part_floats) P.ksplit = 1;
+    P.part = P.ksplit > 1 ? part : nullptr;
+    const long long n_items = (P.npix + TC_TM - 1) / TC_TM * L.n_ntiles * P.ksplit;
     const int grid = (int)(n_items < sm_count ? n_items : sm_count);
     P.trace = nullptr;
     static long long* tbuf = nullptr;
@@ -499,7 +537,8 @@ static int launch_conv_tc(const Layer& L, int B, const float* in, const float* r
         cudaMemset(tbuf, 0, 512 * 5 * sizeof(long long));
         P.trace = tbuf;
     }
-    conv_tc_kernel<<<grid, CV_THREADS, CV_SMEM_BYTES, st>>>(P);
+    if (P.ksplit > 1) conv_tc_kernel<true><<<grid, CV_THREADS, CV_SMEM_BYTES, st>>>(P);
+    else conv_tc_kernel<false><<<grid, CV_THREADS, CV_SMEM_BYTES, st>>>(P);
     if (want) {
         std::vector<long long> tr(512 * 5);
         cudaMemcpy(tr.data(), tbuf, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost);
@@ -510,13 +549,19 @@ static int launch_conv_tc(const Layer& L, int B, const float* in, const float* r
     }
     count_launch();
     SDF_CUDA_CHECK(cudaGetLastError());
+    if (P.ksplit > 1) {
+        const long long total = P.npix * P.Cout;
+        conv_splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(part, P.ksplit, total, P.Cout, P.Hout * P.Wout, L.b, resid, act, out);
+        count_launch();
+        SDF_CUDA_CHECK(cudaGetLastError());
+    }
     return 0;
 }
 
 template <int KS, bool PRE>
 static int launch_conv(const Layer& L, int B, const float* in, const float* resid, int act, float* out, cudaStream_t st,
-                       const float* yz = nullptr, float dmax = 1.f, int clip = 0, int d2r = 0) {
-    if (!PRE && L.wblob_tc && enc_use_tc()) return launch_conv_tc(L, B, in, resid, act, out, st);
+                       const float* yz = nullptr, float dmax = 1.f, int clip = 0, int d2r = 0, float* part = nullptr, size_t part_floats = 0) {
+    if (!PRE && L.wblob_tc && enc_use_tc()) return launch_conv_tc(L, B, in, resid, act, out, st, part, part_floats);
     const long long npix = (long long)B * L.s.Hout * L.s.Wout;
     dim3 grid((unsigned)((npix + TPX - 1) / TPX), (L.s.Cout + TCO - 1) / TCO);
     conv_igemm_kernel<KS, PRE><<<grid, 256, 0, st>>>(L.s, B, in, L.w, L.b, resid, act, out, yz, dmax, clip, d2r);
@@ -556,15 +601,15 @@ extern "C" int sdfnmpc_encoder_encode(sdfnmpc_encoder_t h, const float* imgs, in
     float* t1 = a;         // conv1 output
     float* t2 = c;         // shortcut output / block output
     for (int i = 0; i < 4; ++i) {
-        if ((rc = launch_conv<3, false>(h->c1[i], B, x, nullptr, ENC_ACT_RELU, t1, st))) return rc;
+        if ((rc = launch_conv<3, false>(h->c1[i], B, x, nullptr, ENC_ACT_RELU, t1, st, nullptr, 1.f, 0, 0, h->part, h->part_floats))) return rc;
         const float* resid = x;
         if (h->has_sc[i]) {
-            if ((rc = launch_conv<1, false>(h->sc[i], B, x, nullptr, ENC_ACT_NONE, t2, st))) return rc;
+            if ((rc = launch_conv<1, false>(h->sc[i], B, x, nullptr, ENC_ACT_NONE, t2, st, nullptr, 1.f, 0, 0, h->part, h->part_floats))) return rc;
             resid = t2;
             // conv2 writes over the (now dead) block input
-            if ((rc = launch_conv<3, false>(h->c2[i], B, t1, resid, ENC_ACT_RELU, x, st))) return rc;
+            if ((rc = launch_conv<3, false>(h->c2[i], B, t1, resid, ENC_ACT_RELU, x, st, nullptr, 1.f, 0, 0, h->part, h->part_floats))) return rc;
         } else {
-            if ((rc = launch_conv<3, false>(h->c2[i], B, t1, resid, ENC_ACT_RELU, t2, st))) return rc;
+            if ((rc = launch_conv<3, false>(h->c2[i], B, t1, resid, ENC_ACT_RELU, t2, st, nullptr, 1.f, 0, 0, h->part, h->part_floats))) return rc;
             float* tmp = x; x = t2; t2 = tmp;
         }
     }
