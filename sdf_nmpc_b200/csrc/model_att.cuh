@@ -173,19 +173,22 @@ SDF_HD void f_model(const ModelConst& c, const T* x, const T* u, T* dx, const At
 
 template <int MODEL, class T>
 SDF_HD void rk4_step(const ModelConst& c, const T* x, const T* u, double dt, T* xn) {
-    constexpr int ATT_NX = ModelDims<MODEL>::NX;
-    T k1[ATT_NX], k2[ATT_NX], k3[ATT_NX], k4[ATT_NX], xs[ATT_NX];
+    constexpr int NX_ = ModelDims<MODEL>::NX;
+    // The weighted sum of the stage derivatives is accumulated as the stages come ((k1 + 2 k2) + 2 k3) + k4, the order of the
+    // plain formula), so only one stage derivative is live at a time: with all four kept to the end the dual-number
+    // instantiation holds 100 doubles and spills (552 B per thread, more than the L1 holds for 16 resident warps).
+    T k[NX_], xs[NX_];
     AttInputTrig<T> trig;
     const AttInputTrig<T>* it = nullptr;
     if (MODEL == MODEL_ATT) { trig = att_input_trig(c, u); it = &trig; }
-    f_model<MODEL>(c, x, u, k1, it);
-    for (int i = 0; i < ATT_NX; ++i) xs[i] = x[i] + (0.5 * dt) * k1[i];
-    f_model<MODEL>(c, xs, u, k2, it);
-    for (int i = 0; i < ATT_NX; ++i) xs[i] = x[i] + (0.5 * dt) * k2[i];
-    f_model<MODEL>(c, xs, u, k3, it);
-    for (int i = 0; i < ATT_NX; ++i) xs[i] = x[i] + dt * k3[i];
-    f_model<MODEL>(c, xs, u, k4, it);
-    for (int i = 0; i < ATT_NX; ++i) xn[i] = x[i] + (dt / 6.0) * (k1[i] + 2.0 * k2[i] + 2.0 * k3[i] + k4[i]);
+    f_model<MODEL>(c, x, u, k, it);
+    for (int i = 0; i < NX_; ++i) { xn[i] = k[i]; xs[i] = x[i] + (0.5 * dt) * k[i]; }
+    f_model<MODEL>(c, xs, u, k, it);
+    for (int i = 0; i < NX_; ++i) { xn[i] = xn[i] + 2.0 * k[i]; xs[i] = x[i] + (0.5 * dt) * k[i]; }
+    f_model<MODEL>(c, xs, u, k, it);
+    for (int i = 0; i < NX_; ++i) { xn[i] = xn[i] + 2.0 * k[i]; xs[i] = x[i] + dt * k[i]; }
+    f_model<MODEL>(c, xs, u, k, it);
+    for (int i = 0; i < NX_; ++i) xn[i] = x[i] + (dt / 6.0) * (xn[i] + k[i]);
 }
 
 // y = [p, q_e[3], v, roll, pitch, wz, W_a[2]];  q_e = q_d (x) conj(q/|q|)
