@@ -38,6 +38,15 @@ struct QpMmaShape {
     static constexpr int KF = 64;                   // K~_k as fragments: [tile][lane] = K~[q][position 8 tile + g]
     static constexpr int LF = 16;                   // LDL' of Muu_k: inverse pivots [4] | unit lower factor by columns [6]
     static constexpr int GP = 16;                   // cost gradient by position
+#ifndef QM_STATE_SMEM
+#define QM_STATE_SMEM 1
+#endif
+#if QM_STATE_SMEM && !defined(QM_KF_GLOBAL)
+#define QM_KF_GLOBAL
+#endif
+    // row state (t, lam, s, mu of every row, NROW doubles per node) in shared memory, gains K~ in the slot's L2 scratch (1), or the
+    // round-2a arrangement: gains in shared memory, row state parked in L2 between the row phases (0)
+    static constexpr bool STATE_SHARED = QM_STATE_SMEM != 0;
 #if defined(QM_KF_GLOBAL)
     static constexpr bool KF_SHARED = false;        // gains in the slot's global scratch (L2): 12.8 KB of shared memory per warp
 #else
@@ -48,12 +57,15 @@ struct QpMmaShape {
     // doubles of global scratch per warp slot
     SDF_HD static size_t work_doubles(int N) {
         const size_t n1 = (size_t)N + 1;
-        return n1 * HP + (size_t)N * LF + n1 * GP + ((n1 * NH * 3 + 1) & ~(size_t)1) + 2 * (size_t)NROW * kp(N) + (KF_SHARED ? 0 : (size_t)N * KF);
+        return n1 * HP + (size_t)N * LF + n1 * GP + ((n1 * NH * 3 + 1) & ~(size_t)1) + (STATE_SHARED ? 1 : 2) * (size_t)NROW * kp(N) +
+               (KF_SHARED ? 0 : (size_t)N * KF);
     }
     // doubles of shared memory per warp: iterate, step, elimination terms (+ a zero row), second-order products, corrector
     // feed-forward, costate ping-pong of the verification, and the gains K~_k of every stage (written by the factorising sweep,
     // read by three more sweeps per iteration: 10 KB that would otherwise cycle through L2)
-    SDF_HD static int smem_doubles(int N) { return (2 * NW + NCORR + 1 + NPROD + NU) * kp(N) + 2 * 16 + (KF_SHARED ? N * KF : 0); }
+    SDF_HD static int smem_doubles(int N) {
+        return (2 * NW + NCORR + 1 + NPROD + NU) * kp(N) + 2 * 16 + (KF_SHARED ? N * KF : 0) + (STATE_SHARED ? NROW * kp(N) : 0);
+    }
 };
 
 // Lane-strided loops in this file run a WARP-UNIFORM number of trips with the tail predicated (`QM_LANES(e, n)`): a loop whose
@@ -75,6 +87,11 @@ struct QpMmaShape {
 #ifndef QM_D_HES
 #define QM_D_HES 2
 #endif
+// row phases of the iteration as rolled loops over the rows (1) or with all rows unrolled and the state in registers (0)
+#ifndef QM_ROLLED_ROWS
+#define QM_ROLLED_ROWS 1
+#endif
+// (rolling the two sides of a row as well: 2.57 vs 2.50 ms - the trip gets too short to cover its own latencies)
 #if defined(QM_ASSERT_CONVERGED)
 #define QM_CONVERGED() { if (__activemask() != 0xffffffffu) __trap(); }
 #else
@@ -134,8 +151,8 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
     double* Lf = take((size_t)N * S::LF);
     double* gpos = take(n1 * S::GP);
     double* cpos = take((n1 * NH * 3 + 1) & ~(size_t)1);
-    double* TB = take((size_t)S::NROW * KP);
-    double* TD = take((size_t)S::NROW * KP);
+    double* TB = S::STATE_SHARED ? nullptr : take((size_t)S::NROW * KP);      // row state (shared memory when STATE_SHARED: set below)
+    double* TD = take((size_t)S::NROW * KP);                                   // row steps
 
     // ---- shared workspace ----
     double* Wsm = sm;                             // [NW][KP]   iterate w
@@ -146,6 +163,7 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
     double* pp = ffd + NU * KP;                   // [2][16]    costate ping-pong of the verification
     double* Kf;                                   // [N][2][32] gains as fragments
     if constexpr (S::KF_SHARED) Kf = pp + 2 * 16; else Kf = take((size_t)N * S::KF);
+    if constexpr (S::STATE_SHARED) TB = pp + 2 * 16 + (S::KF_SHARED ? N * S::KF : 0);
 #if defined(QM_KF_GLOBAL) && !defined(QM_KF_L1)
 #define QM_KLD(p_) __ldcg(p_)
 #define QM_KST(p_, v_) __stcg(p_, v_)
@@ -295,28 +313,35 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
     };
 #define QM_LD(p_) __ldcg(p_)
 #define QM_ST(p_, v_) __stcg(p_, v_)
-#define QM_LOAD(BASE, A, B, C4, D4, E4, F4, kk)                                                                      \
+#if QM_STATE_SMEM
+#define QM_TB_LD(p_) (*(p_))
+#define QM_TB_ST(p_, v_) (*(p_) = (v_))
+#else
+#define QM_TB_LD(p_) __ldcg(p_)
+#define QM_TB_ST(p_, v_) __stcg(p_, v_)
+#endif
+#define QM_LOAD(LD_, BASE, A, B, C4, D4, E4, F4, kk)                                                                      \
     {                                                                                                                \
         const double* q__ = BASE + (kk);                                                                             \
-        _Pragma("unroll") for (int a = 0; a < 2 * NU; ++a) { A[a] = QM_LD(q__ + a * KP); B[a] = QM_LD(q__ + (2 * NU + a) * KP); } \
+        _Pragma("unroll") for (int a = 0; a < 2 * NU; ++a) { A[a] = LD_(q__ + a * KP); B[a] = LD_(q__ + (2 * NU + a) * KP); } \
         _Pragma("unroll") for (int a = 0; a < 2 * NH; ++a) {                                                         \
-            C4[a] = QM_LD(q__ + (4 * NU + a) * KP); D4[a] = QM_LD(q__ + (4 * NU + 2 * NH + a) * KP);                   \
-            E4[a] = QM_LD(q__ + (4 * NU + 4 * NH + a) * KP); F4[a] = QM_LD(q__ + (4 * NU + 6 * NH + a) * KP);          \
+            C4[a] = LD_(q__ + (4 * NU + a) * KP); D4[a] = LD_(q__ + (4 * NU + 2 * NH + a) * KP);                   \
+            E4[a] = LD_(q__ + (4 * NU + 4 * NH + a) * KP); F4[a] = LD_(q__ + (4 * NU + 6 * NH + a) * KP);          \
         }                                                                                                            \
     }
-#define QM_STORE(BASE, A, B, C4, D4, E4, F4, kk)                                                                     \
+#define QM_STORE(ST_, BASE, A, B, C4, D4, E4, F4, kk)                                                                     \
     {                                                                                                                \
         double* q__ = BASE + (kk);                                                                                   \
-        _Pragma("unroll") for (int a = 0; a < 2 * NU; ++a) { QM_ST(q__ + a * KP, A[a]); QM_ST(q__ + (2 * NU + a) * KP, B[a]); } \
+        _Pragma("unroll") for (int a = 0; a < 2 * NU; ++a) { ST_(q__ + a * KP, A[a]); ST_(q__ + (2 * NU + a) * KP, B[a]); } \
         _Pragma("unroll") for (int a = 0; a < 2 * NH; ++a) {                                                         \
-            QM_ST(q__ + (4 * NU + a) * KP, C4[a]); QM_ST(q__ + (4 * NU + 2 * NH + a) * KP, D4[a]);                    \
-            QM_ST(q__ + (4 * NU + 4 * NH + a) * KP, E4[a]); QM_ST(q__ + (4 * NU + 6 * NH + a) * KP, F4[a]);            \
+            ST_(q__ + (4 * NU + a) * KP, C4[a]); ST_(q__ + (4 * NU + 2 * NH + a) * KP, D4[a]);                    \
+            ST_(q__ + (4 * NU + 4 * NH + a) * KP, E4[a]); ST_(q__ + (4 * NU + 6 * NH + a) * KP, F4[a]);            \
         }                                                                                                            \
     }
-#define QM_LOAD_STATE(kk) QM_LOAD(TB, tb, lb, ts, ls, ss, ms, kk)
-#define QM_STORE_STATE(kk) QM_STORE(TB, tb, lb, ts, ls, ss, ms, kk)
-#define QM_LOAD_DELTA(kk) QM_LOAD(TD, dtb, dlb, dts, dls, dss, dms, kk)
-#define QM_STORE_DELTA(kk) QM_STORE(TD, dtb, dlb, dts, dls, dss, dms, kk)
+#define QM_LOAD_STATE(kk) QM_LOAD(QM_TB_LD, TB, tb, lb, ts, ls, ss, ms, kk)
+#define QM_STORE_STATE(kk) QM_STORE(QM_TB_ST, TB, tb, lb, ts, ls, ss, ms, kk)
+#define QM_LOAD_DELTA(kk) QM_LOAD(QM_LD, TD, dtb, dlb, dts, dls, dss, dms, kk)
+#define QM_STORE_DELTA(kk) QM_STORE(QM_ST, TD, dtb, dlb, dts, dls, dss, dms, kk)
 #define QM_NODE_LOOP(kk) QM_LANES(kk, N + 1)
 
     // ---- initial point and initial residuals (w = 0 except dx_0, costates 0) ----
@@ -445,6 +470,78 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
         for (int pass = 0; pass < 2 && !stop; ++pass) {
             // =========== row elimination (lane = node): corrections of the stage Hessian / rhs ===========
             double res_rows = 0.0, cmax = 0.0, csum = 0.0;
+#if QM_ROLLED_ROWS
+            // Rolled form: one trip per input (both bounds) / per constraint row (both sides), the row state read from its parked
+            // place inside the trip.  A quarter of the unrolled form's code (which held all 40 state doubles in registers and was
+            // 2000 straight-line instructions per phase): these phases were half instruction-fetch stalls.
+            QM_NODE_LOOP(kk) {
+                const double* sb = TB + kk;
+#pragma unroll 1
+                for (int j = 0; j < NU; ++j) {
+                    double thn = 0.0, cn = 0.0;
+                    if (kk < N) {
+                        const double wu = Wsm[j * KP + kk];
+                        const double ub = P.ubar[kk * NU + j];
+#pragma unroll
+                        for (int side = 0; side < 2; ++side) {
+                            const int a = side * NU + j;
+                            const double sgn = side == 0 ? 1.0 : -1.0;
+                            const double t_ = QM_TB_LD(sb + a * KP), l_ = QM_TB_LD(sb + (2 * NU + a) * KP);
+                            const double cr = pass == 0 ? 0.0 : tau - prod[a * KP + kk];
+                            const double d_ = side == 0 ? P.lbu[j] - ub : ub - P.ubu[j];
+                            const HardEval ev = hard_eval(t_, l_, sgn * wu, d_, cr);
+                            thn += ev.Th;
+                            cn += sgn * ev.coef;
+                            if (pass == 0) {
+                                res_rows = fmax(res_rows, fabs(ev.r_p));
+                                const double c = l_ * t_;
+                                cmax = fmax(cmax, c); csum += c;
+                            }
+                        }
+                    }
+                    if (pass == 0) { corr[j * KP + kk] = thn; corr[(NU + 6 + j) * KP + kk] = cn; }
+                    else corr[(NU + 6 + j) * KP + kk] = cn - corr[(NU + 6 + j) * KP + kk];
+                }
+                double Dp[6] = {0, 0, 0, 0, 0, 0}, gp[3] = {0, 0, 0};
+                if (kk >= k0) {
+#pragma unroll 1
+                    for (int r = 0; r < NH; ++r) {
+                        const double c0 = c_pos(kk, r, 0), c1 = c_pos(kk, r, 1), c2 = c_pos(kk, r, 2);
+                        const double cw = c0 * Wsm[(HC0 + 0) * KP + kk] + c1 * Wsm[(HC0 + 1) * KP + kk] + c2 * Wsm[(HC0 + 2) * KP + kk];
+                        const double z = P.zs[r] * scale(kk), Z = P.Zs[r] * scale(kk);
+                        const double hv = P.hval[kk * NH + r];
+                        double thn = 0.0, cn = 0.0;
+#pragma unroll
+                        for (int side = 0; side < 2; ++side) {
+                            const int a = side * NH + r;
+                            const double sgn = side == 0 ? 1.0 : -1.0;
+                            const double t_ = QM_TB_LD(sb + (4 * NU + a) * KP), l_ = QM_TB_LD(sb + (4 * NU + 2 * NH + a) * KP);
+                            const double s_ = QM_TB_LD(sb + (4 * NU + 4 * NH + a) * KP), m_ = QM_TB_LD(sb + (4 * NU + 6 * NH + a) * KP);
+                            const double ct = pass == 0 ? 0.0 : tau - prod[(2 * NU + a) * KP + kk];
+                            const double cs = pass == 0 ? 0.0 : tau - prod[(2 * NU + 2 * NH + a) * KP + kk];
+                            const double d_ = side == 0 ? P.lh[r] - hv : hv - P.uh[r];
+                            const SoftEval ev = soft_eval(t_, l_, s_, m_, sgn * cw, d_, z, Z, ct, cs);
+                            thn += ev.Tht;
+                            cn += sgn * ev.coef;
+                            if (pass == 0) {
+                                res_rows = fmax(res_rows, fmax(fabs(ev.r_p), fabs(ev.r_s)));
+                                const double ca = l_ * t_, cb = m_ * s_;
+                                cmax = fmax(cmax, fmax(ca, cb)); csum += ca + cb;
+                            }
+                        }
+                        Dp[0] += thn * c0 * c0; Dp[1] += thn * c1 * c0; Dp[2] += thn * c1 * c1;
+                        Dp[3] += thn * c2 * c0; Dp[4] += thn * c2 * c1; Dp[5] += thn * c2 * c2;
+                        gp[0] += cn * c0; gp[1] += cn * c1; gp[2] += cn * c2;
+                    }
+                }
+                if (pass == 0) {
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) corr[(NU + c) * KP + kk] = Dp[c];
+                }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) corr[(2 * NU + 6 + c) * KP + kk] = pass == 0 ? gp[c] : gp[c] - corr[(2 * NU + 6 + c) * KP + kk];
+            }
+#else
             QM_NODE_LOOP(kk) {
                 QM_LOAD_STATE(kk);
                 double du[NU], gu[NU], Dp[6] = {0, 0, 0, 0, 0, 0}, gp[3] = {0, 0, 0};
@@ -511,6 +608,7 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
 #pragma unroll
                 for (int c = 0; c < 3; ++c) corr[(2 * NU + 6 + c) * KP + kk] = pass == 0 ? gp[c] : gp[c] - corr[(2 * NU + 6 + c) * KP + kk];
             }
+#endif
             if (pass == 0) {
                 // ---- convergence test on the state BEFORE this iteration's step ----
                 res_rows = L.max(res_rows);
@@ -778,6 +876,76 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
             QPT(pass * 8 + 2, it == 2)
             // =========== row steps (lane = node) ===========
             double rmax = 0.0;              // largest -dx/x over the lane's rows
+#if QM_ROLLED_ROWS
+            QM_NODE_LOOP(kk) {
+                const double* sb = TB + kk;
+                double* db = TD + kk;
+#pragma unroll 1
+                for (int j = 0; j < NU; ++j) {
+                    double dt_[2] = {0.0, 0.0}, dl_[2] = {0.0, 0.0};
+                    if (kk < N) {
+                        const double wu = Wsm[j * KP + kk], dwu = dW[j * KP + kk];
+                        const double ub = P.ubar[kk * NU + j];
+#pragma unroll
+                        for (int side = 0; side < 2; ++side) {
+                            const int a = side * NU + j;
+                            const double sgn = side == 0 ? 1.0 : -1.0;
+                            const double t_ = QM_TB_LD(sb + a * KP), l_ = QM_TB_LD(sb + (2 * NU + a) * KP);
+                            const double cr = pass == 0 ? 0.0 : tau - prod[a * KP + kk];
+                            const double d_ = side == 0 ? P.lbu[j] - ub : ub - P.ubu[j];
+                            const HardEval ev = hard_eval(t_, l_, sgn * wu, d_, cr);
+                            const double kap = cr - l_ * t_;
+                            dt_[side] = sgn * dwu - ev.r_p;
+                            dl_[side] = (kap - l_ * dt_[side]) * ev.rt;
+                            rmax = fmax(rmax, fmax(boundary_ratio(dt_[side], ev.rt), boundary_ratio(dl_[side], ev.rl)));
+                        }
+                    }
+#pragma unroll
+                    for (int side = 0; side < 2; ++side) {
+                        QM_ST(db + (side * NU + j) * KP, dt_[side]);
+                        QM_ST(db + (2 * NU + side * NU + j) * KP, dl_[side]);
+                    }
+                }
+#pragma unroll 1
+                for (int r = 0; r < NH; ++r) {
+                    double dt_[2] = {0.0, 0.0}, dl_[2] = {0.0, 0.0}, ds_[2] = {0.0, 0.0}, dm_[2] = {0.0, 0.0};
+                    if (kk >= k0) {
+                        const double c0 = c_pos(kk, r, 0), c1 = c_pos(kk, r, 1), c2 = c_pos(kk, r, 2);
+                        const double cw = c0 * Wsm[(HC0 + 0) * KP + kk] + c1 * Wsm[(HC0 + 1) * KP + kk] + c2 * Wsm[(HC0 + 2) * KP + kk];
+                        const double cd = c0 * dW[(HC0 + 0) * KP + kk] + c1 * dW[(HC0 + 1) * KP + kk] + c2 * dW[(HC0 + 2) * KP + kk];
+                        const double z = P.zs[r] * scale(kk), Z = P.Zs[r] * scale(kk);
+                        const double hv = P.hval[kk * NH + r];
+#pragma unroll
+                        for (int side = 0; side < 2; ++side) {
+                            const int a = side * NH + r;
+                            const double sgn = side == 0 ? 1.0 : -1.0;
+                            const double t_ = QM_TB_LD(sb + (4 * NU + a) * KP), l_ = QM_TB_LD(sb + (4 * NU + 2 * NH + a) * KP);
+                            const double s_ = QM_TB_LD(sb + (4 * NU + 4 * NH + a) * KP), m_ = QM_TB_LD(sb + (4 * NU + 6 * NH + a) * KP);
+                            const double ct = pass == 0 ? 0.0 : tau - prod[(2 * NU + a) * KP + kk];
+                            const double cs = pass == 0 ? 0.0 : tau - prod[(2 * NU + 2 * NH + a) * KP + kk];
+                            const double d_ = side == 0 ? P.lh[r] - hv : hv - P.uh[r];
+                            const SoftEval ev = soft_eval(t_, l_, s_, m_, sgn * cw, d_, z, Z, ct, cs);
+                            const double kap = ct - l_ * t_, nu = cs - m_ * s_;
+                            const double gd = sgn * cd;
+                            ds_[side] = (ev.rho - ev.Th * gd) * ev.rD;
+                            dt_[side] = gd + ds_[side] - ev.r_p;
+                            dl_[side] = (kap - l_ * dt_[side]) * ev.rt;
+                            dm_[side] = (nu - m_ * ds_[side]) * ev.rs;
+                            rmax = fmax(rmax, fmax(fmax(boundary_ratio(dt_[side], ev.rt), boundary_ratio(dl_[side], ev.rl)),
+                                                   fmax(boundary_ratio(ds_[side], ev.rs), boundary_ratio(dm_[side], ev.rm))));
+                        }
+                    }
+#pragma unroll
+                    for (int side = 0; side < 2; ++side) {
+                        const int a = side * NH + r;
+                        QM_ST(db + (4 * NU + a) * KP, dt_[side]);
+                        QM_ST(db + (4 * NU + 2 * NH + a) * KP, dl_[side]);
+                        QM_ST(db + (4 * NU + 4 * NH + a) * KP, ds_[side]);
+                        QM_ST(db + (4 * NU + 6 * NH + a) * KP, dm_[side]);
+                    }
+                }
+            }
+#else
             QM_NODE_LOOP(kk) {
                 QM_LOAD_STATE(kk);
 #pragma unroll
@@ -828,6 +996,7 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
                 }
                 QM_STORE_DELTA(kk);
             }
+#endif
             rmax = L.max(rmax);
             const double amax = rmax > 1e-30 ? 1.0 / rmax : 1e30;
             if (pass == 0) {
@@ -835,6 +1004,33 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
                 const double aa = fmin(1.0, amax);
                 const double so = safe ? 0.0 : 1.0;
                 double csum_aff = 0.0;
+#if QM_ROLLED_ROWS
+                QM_NODE_LOOP(kk) {
+                    const double* sb = TB + kk;
+                    const double* db = TD + kk;
+                    if (kk < N) {
+#pragma unroll
+                        for (int a = 0; a < 2 * NU; ++a) {
+                            const double t_ = QM_TB_LD(sb + a * KP), l_ = QM_TB_LD(sb + (2 * NU + a) * KP);
+                            const double dt_ = QM_LD(db + a * KP), dl_ = QM_LD(db + (2 * NU + a) * KP);
+                            csum_aff += (l_ + aa * dl_) * (t_ + aa * dt_);
+                            prod[a * KP + kk] = so * dl_ * dt_;
+                        }
+                    }
+                    if (kk >= k0) {
+#pragma unroll
+                        for (int a = 0; a < 2 * NH; ++a) {
+                            const double t_ = QM_TB_LD(sb + (4 * NU + a) * KP), l_ = QM_TB_LD(sb + (4 * NU + 2 * NH + a) * KP);
+                            const double s_ = QM_TB_LD(sb + (4 * NU + 4 * NH + a) * KP), m_ = QM_TB_LD(sb + (4 * NU + 6 * NH + a) * KP);
+                            const double dt_ = QM_LD(db + (4 * NU + a) * KP), dl_ = QM_LD(db + (4 * NU + 2 * NH + a) * KP);
+                            const double ds_ = QM_LD(db + (4 * NU + 4 * NH + a) * KP), dm_ = QM_LD(db + (4 * NU + 6 * NH + a) * KP);
+                            csum_aff += (l_ + aa * dl_) * (t_ + aa * dt_) + (m_ + aa * dm_) * (s_ + aa * ds_);
+                            prod[(2 * NU + a) * KP + kk] = so * dl_ * dt_;
+                            prod[(2 * NU + 2 * NH + a) * KP + kk] = so * dm_ * ds_;
+                        }
+                    }
+                }
+#else
                 QM_NODE_LOOP(kk) {
                     QM_LOAD_STATE(kk);
                     QM_LOAD_DELTA(kk);
@@ -854,6 +1050,7 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
                         }
                     }
                 }
+#endif
                 const double mu_aff = L.sum(csum_aff) / ncomp;
                 double sig = mu_aff / fmax(mubar, 1e-300);
                 sig = fmin(fmax(sig * sig * sig, safe ? 0.2 : 0.0), 1.0);
@@ -863,6 +1060,15 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
             } else {
                 // =========== damped step ===========
                 const double al = fmin(1.0, 0.995 * amax);
+#if QM_ROLLED_ROWS
+                QM_NODE_LOOP(kk) {
+#pragma unroll
+                    for (int e = 0; e < S::NROW; ++e) {
+                        double* q_ = TB + e * KP + kk;
+                        QM_TB_ST(q_, QM_TB_LD(q_) + al * QM_LD(TD + e * KP + kk));
+                    }
+                }
+#else
                 QM_NODE_LOOP(kk) {
                     QM_LOAD_STATE(kk);
                     QM_LOAD_DELTA(kk);
@@ -872,6 +1078,7 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
                     for (int a = 0; a < 2 * NH; ++a) { ts[a] += al * dts[a]; ls[a] += al * dls[a]; ss[a] += al * dss[a]; ms[a] += al * dms[a]; }
                     QM_STORE_STATE(kk);
                 }
+#endif
                 QM_LANES(e, NW * KP) Wsm[e] += al * dW[e];
                 phi *= (1.0 - al);
                 L.sync();
