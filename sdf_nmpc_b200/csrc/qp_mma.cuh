@@ -76,7 +76,7 @@ struct QpMmaShape {
 #define QM_LANES(v, n) for (int v##_0 = 0; v##_0 < (n); v##_0 += 32) if (const int v = v##_0 + lane; v < (n))
 // register-pipeline depths of the corrector's sweep and the roll-outs (A/B knobs; tools/qp_ab.py)
 #ifndef QM_D_BACK
-#define QM_D_BACK 2
+#define QM_D_BACK 3
 #endif
 #ifndef QM_D_ROLL
 #define QM_D_ROLL 2

@@ -154,23 +154,43 @@ class BatchedNmpc:
             off += n
         return lay, off
 
-    def reset(self):
-        """controller.py:32-42."""
-        B = self.B
-        lay, total = self._layout()
-        self._in = torch.zeros(total, dtype=torch.float64, device=self.device)
-        view = lambda k: self._in[lay[k][0]:lay[k][0] + lay[k][1]].view(lay[k][2])
+    def _bind(self, block):
+        """Point the input views at `block` (layout of ``_layout``)."""
+        lay, _ = self._layout()
+        view = lambda k: block[lay[k][0]:lay[k][0] + lay[k][1]].view(lay[k][2])
+        self._in = block
         self._x0 = view('x0')                             # static address: the RTI step may be replayed as a CUDA graph
-        self.x0 = None
         self.flag = view('flag')
         self.pose = view('pose')                          # W_p_Co(3), W_R_Co row-major(9)
         self.qd = view('qd')
-        self.latent = torch.zeros(B, max(self.L, 1), dtype=torch.float32, device=self.device)
         self.y, self.yN, self.W, self.WN = view('y'), view('yN'), view('W'), view('WN')
+
+    def reset(self):
+        """controller.py:32-42."""
+        B = self.B
+        _, total = self._layout()
+        self._blocks = [torch.zeros(total, dtype=torch.float64, device=self.device)]
+        self._bind(self._blocks[0])
+        self.x0 = None
+        self.latent = torch.zeros(B, max(self.L, 1), dtype=torch.float32, device=self.device)
         self.fail_count = torch.zeros(B, dtype=torch.int64, device=self.device)
         self._latent_dirty = True
         self._graph = None
         self.set_sdf_flag(False)
+
+    def select_inputs(self, i):
+        """Double-buffered inputs for a host caller (eager mode): while a control step runs on block ``1 - i`` the references of the
+        next step are uploaded into block ``i`` on a copy stream; the state feedback, which is all that has to wait for the
+        previous step, goes last.  The second block is created on first use as a copy of the first."""
+        if self._graph is not None:
+            raise _lib.SdfNmpcError('select_inputs: the captured control step reads the block it was captured with')
+        if len(self._blocks) == 1:
+            self._blocks.append(self._blocks[0].clone())
+        had_x0 = self.x0 is not None
+        self._bind(self._blocks[int(i)])
+        if had_x0:
+            self.x0 = self._x0
+        return self._in
 
     def set_sdf_flag(self, flag):
         """controller.py:45-47 (scalar or per-instance)."""
