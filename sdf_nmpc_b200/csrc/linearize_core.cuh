@@ -25,7 +25,7 @@ struct LinIn {           // device pointers, whole batch
 };
 
 struct LinOut {
-    double* AB;    // [B][N][NX][NW]   columns ordered [u; x]
+    double* AB;    // [B][N][NX][NW]   columns ordered [u; x]; optional (null: only ABt is written)
     double* bdyn;  // [B][N][NX]       phi(xbar_k, ubar_k) - xbar_{k+1}
     double* J;     // [B][N+1][NY][NW]
     double* yres;  // [B][N+1][NY]     y - yref (terminal rows >= NYN are zero)
@@ -102,8 +102,10 @@ SDF_HD void linearize_dir(const ModelConst& mc, int N, const LinIn& in, const Li
     if (k < N) {
         Dual xn[NX];
         rk4_step_seeded<MODEL>(mc, x, dir - NU, ud, in.dt[k], xn);
-        double* AB = out.AB + ((size_t)b * N + k) * NX * NW;
-        for (int i = 0; i < NX; ++i) AB[i * NW + dir] = xn[i].d;
+        if (out.AB) {       // null when the solver reads the operand layout `ABt` only
+            double* AB = out.AB + ((size_t)b * N + k) * NX * NW;
+            for (int i = 0; i < NX; ++i) AB[i * NW + dir] = xn[i].d;
+        }
         double* T = (out.ABt && NX == ATT_NX) ? out.ABt + ((size_t)b * N + k) * 192 : nullptr;     // 10-state models only
         if (T) {
             double* row = T + mma_wpos(dir) * 12;

@@ -267,6 +267,9 @@ extern "C" int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver
     alloc((void**)&h->dt, N * sizeof(double));
     alloc((void**)&h->xbar, B * N1 * NX * sizeof(double));
     alloc((void**)&h->ubar, B * N * NU * sizeof(double));
+#if !defined(SDFNMPC_QP_SCALAR)
+    if (props)      // the tensor-core solver reads [A B | b] in its operand layout (ABt) only
+#endif
     alloc((void**)&h->AB, B * N * NX * NW * sizeof(double));
 #if !defined(SDFNMPC_QP_SCALAR)
     if (!props) alloc((void**)&h->ABt, B * N * 192 * sizeof(double));

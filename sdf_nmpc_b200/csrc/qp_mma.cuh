@@ -73,6 +73,9 @@ struct QpMmaShape {
 // the partially unrolled scatter of [A B], 2800 entries = 87.5 trips - did NOT re-join behind it: the warp went on as two
 // halves, the compiler (which assumes they re-join) had removed the __syncwarp() that followed, and every mma.sync behind it
 // multiplied half-warp fragments only (found with __activemask() probes; -DQM_ASSERT_CONVERGED keeps them as traps).
+// read-once inputs (J, residuals, constraint rows) are loaded with the evict-first policy: the slots' scratch and operand
+// blocks (97 KB x 1184 slots) fill the 126 MB L2 by themselves, and 36 KB per instance of streaming input evicts them otherwise
+#define QM_LDS(p_) __ldcs(p_)
 #define QM_LANES(v, n) for (int v##_0 = 0; v##_0 < (n); v##_0 += 32) if (const int v = v##_0 + lane; v < (n))
 // register-pipeline depths of the corrector's sweep and the roll-outs (A/B knobs; tools/qp_ab.py)
 #ifndef QM_D_BACK
@@ -206,7 +209,7 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
             P.hval[k * NH + (NH - 1)] = P.flag * (double)P.sdf_d[k] + (1.0 - P.flag) * P.max_df;
         }
         for (int r = 0; r < NH; ++r)
-            for (int c = 0; c < 3; ++c) cpos[(k * NH + r) * 3 + c] = P.C[((size_t)k * NH + r) * NW + HC0 + c];
+            for (int c = 0; c < 3; ++c) cpos[(k * NH + r) * 3 + c] = QM_LDS(P.C + ((size_t)k * NH + r) * NW + HC0 + c);
     }
     // T_k = [A B | b; 0 1]~ by (position, slot) comes ready-made from the linearisation kernel.  Node 0 is linearised at the measured
     // state (ocp.py:161), so dx_0 = x0 - xbar_0 = 0: the iterate starts at w = 0 and the dynamics defect IS the affine column.
@@ -235,9 +238,9 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
                 const int rc = r < NY ? r : NY - 1;
                 // loads only: any arithmetic on the loaded values here would wait for them and undo the pipelining
                 o.w[s] = wrow(k, rc);
-                o.v[s][0] = Jk[rc * NW + wi0];
+                o.v[s][0] = QM_LDS(Jk + rc * NW + wi0);
                 const double* src = wi1 < NW ? Jk + rc * NW + wi1 : yk + rc;
-                o.v[s][1] = *src;
+                o.v[s][1] = QM_LDS(src);
             }
             return o;
         };
