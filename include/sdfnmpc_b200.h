@@ -151,6 +151,22 @@ int sdfnmpc_colcheck(const float* imgs_dev, int32_t B, int32_t H, int32_t W, con
                      float dmax, float hfov, float vfov, float safe_ball, int32_t outside, int32_t is_depth, int32_t is_spherical,
                      uint8_t* out_dev, void* stream);
 
+/* DfComputer.get_df (sdf_nmpc/utils/df_computer.py:56-221): ground-truth distance-field labels of points against the images.
+ * Signed (get_sdf, :198-221): sign = the point's own collision label ('extrapolate', no safe ball); distance = the smallest
+ * voxel offset |grid[g]| (grid_dist[g]) among the G voxels of the multi-resolution ball (generate_dist_grid, :31-53; built by
+ * the host, sdf_nmpc_b200/collision.py) whose label differs from the point's; sdf = clamp(sign * dist, min_df, max_df);
+ * grad [n][3] = -sign * grid[g*] / |grid[g*]|, zero where sdf saturates.  One CTA per point, nothing materialised. */
+int sdfnmpc_df_signed(const float* imgs_dev, int32_t B, int32_t H, int32_t W, const float* pts_dev, const int32_t* p2i_dev, int64_t n,
+                      const float* grid_dev, const float* grid_dist_dev, int32_t G, float dmax, float hfov, float vfov,
+                      int32_t is_depth, int32_t is_spherical, float min_df, float max_df, float* sdf_dev, float* grad_dev,
+                      void* stream);
+/* Unsigned (get_udf, :138-176 with the Warp kernel :84-136): pool x pool min-pool of the image that ignores zeros (H, W
+ * multiples of pool; pooled_dev [B][H/pool][W/pool] is caller-provided scratch), distance of each point to the 3-D position of
+ * every pooled pixel or to the virtual wall at dmax, minimum over the pixels; udf = clamp(min, 0, max_df), grad = -direction. */
+int sdfnmpc_df_unsigned(const float* imgs_dev, int32_t B, int32_t H, int32_t W, int32_t pool, float* pooled_dev, const float* pts_dev,
+                        const int32_t* p2i_dev, int64_t n, float dmax, float hfov, float vfov, int32_t is_depth,
+                        int32_t is_spherical, float max_df, float* udf_dev, float* grad_dev, void* stream);
+
 /* ------------------------------------------------------------------ depth encoder ------- */
 typedef struct sdfnmpc_encoder* sdfnmpc_encoder_t;
 
@@ -180,6 +196,36 @@ int sdfnmpc_encoder_destroy(sdfnmpc_encoder_t h);
 /* imgs [B][H][W] float32 raw sensor values -> latents [B][L] (preprocessing fused). */
 int sdfnmpc_encoder_encode(sdfnmpc_encoder_t h, const float* imgs_dev, int32_t B, float* latents_dev, void* stream);
 int sdfnmpc_encoder_encode_host(sdfnmpc_encoder_t h, const float* imgs, int32_t B, float* latents);
+
+/* ------------------------------------------------------------------ VAE decoder --------- */
+/* VaeWrapper.decode (sdf_nmpc/vae.py:42-45): latent -> reconstructed range image in [0, 1]
+ * (network/vae.py:63-90: Linear + ELU, 4 x ResBlockDeconv of network/resnet.py:59-111, ConvTranspose2d 5x5, bilinear
+ * Upsample to (height, width), Sigmoid).  The feature map after the Linear layer is the reference's fixed [512][8][15]. */
+typedef struct sdfnmpc_decoder* sdfnmpc_decoder_t;
+
+typedef struct {
+    int32_t height, width;   /* Upsample size = shape_imgs                                  */
+    int32_t size_latent;
+    int32_t max_batch;
+} sdfnmpc_decoder_desc;
+
+/* Weights: host pointers, torch layouts.  ConvTranspose2d weights [Cin][Cout][kh][kw]; block i maps C_i = 512 >> i
+ * channels to C_i / 2: ct1 (3x3, stride 2, padding 1, output_padding 1), ct2 (3x3, stride 1, padding 1), shortcut
+ * sc (1x1, stride 2, output_padding 1); BatchNorm as (weight, bias, running_mean, running_var), folded at creation. */
+typedef struct {
+    const float *lin_w, *lin_b;                     /* [512*8*15][L], [512*8*15]            */
+    const float* ct1_w[4]; const float* bn1[4][4];
+    const float* ct2_w[4]; const float* bn2[4][4];
+    const float* sc_w[4];  const float* sc_bn[4][4];
+    const float *out_w, *out_b;                     /* [32][1][5][5], [1]                   */
+    float bn_eps;
+} sdfnmpc_decoder_weights;
+
+int sdfnmpc_decoder_create(sdfnmpc_decoder_t* out, const sdfnmpc_decoder_desc* desc, const sdfnmpc_decoder_weights* w);
+int sdfnmpc_decoder_destroy(sdfnmpc_decoder_t h);
+/* latents [B][L] float32 -> imgs [B][height][width] float32 in [0, 1] (normalised by dmax, like the encoder's input). */
+int sdfnmpc_decoder_decode(sdfnmpc_decoder_t h, const float* latents_dev, int32_t B, float* imgs_dev, void* stream);
+int sdfnmpc_decoder_decode_host(sdfnmpc_decoder_t h, const float* latents, int32_t B, float* imgs);
 
 /* ------------------------------------------------------------------ CasADi external ABI - */
 /* Bind the process-global network the `sdf_l4c` symbols evaluate (L4CasADi bakes the model path

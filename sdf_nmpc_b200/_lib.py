@@ -51,15 +51,28 @@ class EncoderWeights(C.Structure):
                 ('mean_w', FP), ('mean_b', FP), ('bn_eps', C.c_float)]
 
 
+class DecoderDesc(C.Structure):
+    _fields_ = [('height', C.c_int32), ('width', C.c_int32), ('size_latent', C.c_int32), ('max_batch', C.c_int32)]
+
+
+class DecoderWeights(C.Structure):
+    _fields_ = [('lin_w', FP), ('lin_b', FP),
+                ('ct1_w', FP * 4), ('bn1', (FP * 4) * 4),
+                ('ct2_w', FP * 4), ('bn2', (FP * 4) * 4),
+                ('sc_w', FP * 4), ('sc_bn', (FP * 4) * 4),
+                ('out_w', FP), ('out_b', FP), ('bn_eps', C.c_float)]
+
+
 CASADI_COMPANIONS = ('', '_alloc_mem', '_init_mem', '_free_mem', '_checkout', '_release', '_incref', '_decref', '_n_in',
                      '_n_out', '_default_in', '_name_in', '_name_out', '_sparsity_in', '_sparsity_out', '_work')
 
 EXPORTS = (['sdfnmpc_version', 'sdfnmpc_launch_count', 'sdfnmpc_sdf_create', 'sdfnmpc_sdf_destroy',
             'sdfnmpc_sdf_set_latents', 'sdfnmpc_sdf_eval', 'sdfnmpc_sdf_eval_host', 'sdfnmpc_solver_create',
             'sdfnmpc_solver_destroy', 'sdfnmpc_solver_init_traj', 'sdfnmpc_solver_shift', 'sdfnmpc_solver_rti_step',
-            'sdfnmpc_solver_state', 'sdfnmpc_solver_diag', 'sdfnmpc_solver_qp_residual', 'sdfnmpc_solver_timing_begin', 'sdfnmpc_solver_timing_end', 'sdfnmpc_plant_step', 'sdfnmpc_cmd_trpyr', 'sdfnmpc_cmd_acc', 'sdfnmpc_cmd_props', 'sdfnmpc_solver_dims', 'sdfnmpc_colcheck', 'sdfnmpc_fail_count_update',
+            'sdfnmpc_solver_state', 'sdfnmpc_solver_diag', 'sdfnmpc_solver_qp_residual', 'sdfnmpc_solver_timing_begin', 'sdfnmpc_solver_timing_end', 'sdfnmpc_plant_step', 'sdfnmpc_cmd_trpyr', 'sdfnmpc_cmd_acc', 'sdfnmpc_cmd_props', 'sdfnmpc_solver_dims', 'sdfnmpc_colcheck', 'sdfnmpc_df_signed', 'sdfnmpc_df_unsigned', 'sdfnmpc_fail_count_update',
             'sdfnmpc_encoder_create', 'sdfnmpc_encoder_destroy', 'sdfnmpc_encoder_encode',
-            'sdfnmpc_encoder_encode_host', 'sdfnmpc_l4c_bind', 'sdfnmpc_l4c_load_blob']
+            'sdfnmpc_encoder_encode_host', 'sdfnmpc_decoder_create', 'sdfnmpc_decoder_destroy', 'sdfnmpc_decoder_decode',
+            'sdfnmpc_decoder_decode_host', 'sdfnmpc_l4c_bind', 'sdfnmpc_l4c_load_blob']
            + [f + s for f in ('sdf_l4c', 'jac_sdf_l4c') for s in CASADI_COMPANIONS])
 
 
@@ -107,10 +120,16 @@ def load():
     lib.sdfnmpc_solver_dims.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     lib.sdfnmpc_fail_count_update.argtypes = [ip, vp, i32, vp]
     lib.sdfnmpc_colcheck.argtypes = [fp, i32, i32, i32, fp, ip, i64] + [C.c_float] * 4 + [i32, i32, i32, vp, vp]
+    lib.sdfnmpc_df_signed.argtypes = [fp, i32, i32, i32, fp, ip, i64, fp, fp, i32] + [C.c_float] * 3 + [i32, i32, C.c_float, C.c_float, fp, fp, vp]
+    lib.sdfnmpc_df_unsigned.argtypes = [fp, i32, i32, i32, i32, fp, fp, ip, i64] + [C.c_float] * 3 + [i32, i32, C.c_float, fp, fp, vp]
     lib.sdfnmpc_encoder_create.argtypes = [C.POINTER(vp), C.POINTER(EncoderDesc), C.POINTER(EncoderWeights)]
     lib.sdfnmpc_encoder_destroy.argtypes = [vp]
     lib.sdfnmpc_encoder_encode.argtypes = [vp, fp, i32, fp, vp]
     lib.sdfnmpc_encoder_encode_host.argtypes = [vp, fp, i32, fp]
+    lib.sdfnmpc_decoder_create.argtypes = [C.POINTER(vp), C.POINTER(DecoderDesc), C.POINTER(DecoderWeights)]
+    lib.sdfnmpc_decoder_destroy.argtypes = [vp]
+    lib.sdfnmpc_decoder_decode.argtypes = [vp, fp, i32, fp, vp]
+    lib.sdfnmpc_decoder_decode_host.argtypes = [vp, fp, i32, fp]
     lib.sdfnmpc_l4c_bind.argtypes = [vp]
     lib.sdfnmpc_l4c_load_blob.argtypes = [C.c_char_p]
     for f in ('sdf_l4c', 'jac_sdf_l4c'):

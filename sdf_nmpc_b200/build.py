@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(LIBDIR, 'libsdfnmpc_b200.so')
-SOURCES = ['sdf_api.cu', 'nmpc_api.cu', 'encoder_api.cu']
+SOURCES = ['sdf_api.cu', 'nmpc_api.cu', 'encoder_api.cu', 'df_api.cu']
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=default', '--expt-relaxed-constexpr']
 

@@ -59,11 +59,14 @@ struct ConvTcParams {
     // and applies bias / residual / activation.  ksplit = 1, part = null: the epilogue below does it directly.
     int ksplit;
     float* part;
+    // Sub-pixel output (conv_tc_kernel<*, true>, the decoder's stride-2 transposed convolutions, encoder_api.cu "decoder"): the
+    // Cout channels are 4 parity classes x Cout / 4 real channels, class (py, px) of conv pixel (oy, ox) is output pixel
+    // (2 oy + py, 2 ox + px) of a [B][Cout / 4][2 Hout][2 Wout] tensor (bias has Cout entries, resid / out / part that layout).
     long long* trace;             // development: clock64 samples of CTA 0's issuer, [sub-chunk][4] (null = off)
 };
 
 // SPLIT = false is the batch kernel (ksplit == 1 at compile time: the split bookkeeping costs it 6 % at 64 frames otherwise)
-template <bool SPLIT>
+template <bool SPLIT, bool SHUF = false>
 __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcParams P) {
     using namespace tc;
     extern __shared__ __align__(1024) unsigned char cv_smem_raw[];
@@ -149,17 +152,26 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
             for (int c0 = c_begin; c0 < c_begin + ncol; c0 += 16) {
                 float v[16];
                 tc_ld16(acc + c0, v);
+                // output offset of channel co of this thread's pixel
+                auto out_off = [&](int co) -> size_t {
+                    if constexpr (SHUF) {
+                        const int cr = P.Cout >> 2, cls = co / cr, c = co - cls * cr;
+                        return (((size_t)pb * cr + c) * (2 * P.Hout) + 2 * oy + (cls >> 1)) * (size_t)(2 * P.Wout) + 2 * ox + (cls & 1);
+                    } else {
+                        return ((size_t)pb * P.Cout + co) * hw + r;
+                    }
+                };
                 if (SPLIT && pvalid) {
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
                         const int co = nt * P.NT + c0 + e;
-                        P.part[(size_t)ksp * out_total + ((size_t)pb * P.Cout + co) * hw + r] = v[e];
+                        P.part[(size_t)ksp * out_total + out_off(co)] = v[e];
                     }
                 } else if (!SPLIT && pvalid) {
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
                         const int co = nt * P.NT + c0 + e;
-                        const size_t o = ((size_t)pb * P.Cout + co) * hw + r;
+                        const size_t o = out_off(co);
                         float val = v[e] + __ldg(P.bias + co);
                         if (P.resid) val += __ldg(P.resid + o);
                         if (P.act == CV_ACT_RELU) val = fmaxf(val, 0.f);

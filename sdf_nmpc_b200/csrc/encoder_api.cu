@@ -23,6 +23,7 @@ enum { ENC_ACT_NONE = 0, ENC_ACT_RELU = 1, ENC_ACT_ELU = 2 };
 
 struct ConvShape {
     int Cin, Hin, Win, Cout, Hout, Wout, stride, pad;
+    int shuffle = 0;      // sub-pixel output: Cout = 4 parity classes x Cout / 4 channels of a [2 Hout][2 Wout] map (the decoder)
 };
 
 constexpr int TCO = 64, TPX = 64, TK = 16;
@@ -111,7 +112,11 @@ conv_igemm_kernel(ConvShape s, int B, const float* __restrict__ in, const float*
             const long long p = px0 + tx * 4 + j;
             if (p >= npix) continue;
             const int b = (int)(p / hw), r = (int)(p % hw);
-            const size_t o = ((size_t)b * s.Cout + co) * hw + r;
+            size_t o = ((size_t)b * s.Cout + co) * hw + r;
+            if (s.shuffle) {
+                const int cr = s.Cout >> 2, cls = co / cr, c = co - cls * cr, oy = r / s.Wout, ox = r - oy * s.Wout;
+                o = (((size_t)b * cr + c) * (2 * s.Hout) + 2 * oy + (cls >> 1)) * (size_t)(2 * s.Wout) + 2 * ox + (cls & 1);
+            }
             float v = acc[i][j] + bco;
             if (resid) v += resid[o];
             if (act == ENC_ACT_RELU) v = fmaxf(v, 0.f);
@@ -342,15 +347,18 @@ static int upload(float** dst, const std::vector<float>& v) {
 }
 
 // fold BN (weight, bias, mean, var) into conv weights [Cout][K] and a bias [Cout]
+// (a sub-pixel layer has its BatchNorm / bias entries per REAL channel: index co % (Cout / 4))
 static int make_layer(Layer& L, const float* w, const float* const bn[4], const float* conv_bias, float eps) {
     const int K = L.s.Cin * L.ks * L.ks;
     std::vector<float> W((size_t)L.s.Cout * K), Bv(L.s.Cout, 0.f);
+    const int cmod = L.s.shuffle ? L.s.Cout / 4 : L.s.Cout;
     for (int co = 0; co < L.s.Cout; ++co) {
-        float scale = 1.f, shift = conv_bias ? conv_bias[co] : 0.f;
+        const int cb = co % cmod;
+        float scale = 1.f, shift = conv_bias ? conv_bias[cb] : 0.f;
         if (bn && bn[0]) {
-            const float inv = 1.0f / sqrtf(bn[3][co] + eps);
-            scale = bn[0][co] * inv;
-            shift = bn[1][co] + (shift - bn[2][co]) * scale;
+            const float inv = 1.0f / sqrtf(bn[3][cb] + eps);
+            scale = bn[0][cb] * inv;
+            shift = bn[1][cb] + (shift - bn[2][cb]) * scale;
         }
         for (int k = 0; k < K; ++k) W[(size_t)co * K + k] = w[(size_t)co * K + k] * scale;
         Bv[co] = shift;
@@ -514,6 +522,8 @@ static int launch_conv_tc(const Layer& L, int B, const float* in, const float* r
     if (!attr_set) {
         SDF_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM_BYTES));
         SDF_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM_BYTES));
+        SDF_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM_BYTES));
+        SDF_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM_BYTES));
         attr_set = true;
     }
     ConvTcParams P;
@@ -537,7 +547,10 @@ static int launch_conv_tc(const Layer& L, int B, const float* in, const float* r
         cudaMemset(tbuf, 0, 512 * 5 * sizeof(long long));
         P.trace = tbuf;
     }
-    if (P.ksplit > 1) conv_tc_kernel<true><<<grid, CV_THREADS, CV_SMEM_BYTES, st>>>(P);
+    if (L.s.shuffle) {
+        if (P.ksplit > 1) conv_tc_kernel<true, true><<<grid, CV_THREADS, CV_SMEM_BYTES, st>>>(P);
+        else conv_tc_kernel<false, true><<<grid, CV_THREADS, CV_SMEM_BYTES, st>>>(P);
+    } else if (P.ksplit > 1) conv_tc_kernel<true><<<grid, CV_THREADS, CV_SMEM_BYTES, st>>>(P);
     else conv_tc_kernel<false><<<grid, CV_THREADS, CV_SMEM_BYTES, st>>>(P);
     if (want) {
         std::vector<long long> tr(512 * 5);
@@ -551,7 +564,8 @@ static int launch_conv_tc(const Layer& L, int B, const float* in, const float* r
     SDF_CUDA_CHECK(cudaGetLastError());
     if (P.ksplit > 1) {
         const long long total = P.npix * P.Cout;
-        conv_splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(part, P.ksplit, total, P.Cout, P.Hout * P.Wout, L.b, resid, act, out);
+        const int cr = L.s.shuffle ? P.Cout / 4 : P.Cout, ohw = L.s.shuffle ? 4 * P.Hout * P.Wout : P.Hout * P.Wout;
+        conv_splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(part, P.ksplit, total, cr, ohw, L.b, resid, act, out);
         count_launch();
         SDF_CUDA_CHECK(cudaGetLastError());
     }
@@ -619,67 +633,6 @@ extern "C" int sdfnmpc_encoder_encode(sdfnmpc_encoder_t h, const float* imgs, in
     return 0;
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// Ground-truth collision labels of points against range / depth images: the function of the Warp kernel
-// ColChecker._kernel_colcheck (sdf_nmpc/utils/collision_checker.py:23-91), one thread per point.
-// ---------------------------------------------------------------------------------------------------------------------
-__global__ void colcheck_kernel(const float* __restrict__ img, int H, int W, const float* __restrict__ pts, const int* __restrict__ p2i,
-                                long long n, long long pts_per_img, float dmax, float hfov, float vfov, float safe_ball, int outside,
-                                int is_depth, int is_spherical, unsigned char* __restrict__ out) {
-    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= n) return;
-    const float px = pts[tid * 3], py = pts[tid * 3 + 1], pz = pts[tid * 3 + 2];
-    unsigned char col = 0;
-    const float len = sqrtf(px * px + py * py + pz * pz);
-    if (len > safe_ball) {                                  // inside the safe ball around the sensor: never in collision
-        const float val = is_depth ? px : len;
-        if (val >= dmax) {
-            col = 1;                                        // past dmax is unsafe by default
-        } else {
-            float az = atan2f(py, px);
-            float el = is_spherical ? atan2f(pz, sqrtf(px * px + py * py)) : atan2f(pz, px);
-            bool inside = true;
-            if (outside == 2) {                             // extrapolate: clamp to the frustum
-                az = fminf(fmaxf(az, -hfov), hfov);
-                el = fminf(fmaxf(el, -vfov), vfov);
-            } else if (fabsf(az) >= hfov || fabsf(el) >= vfov) {
-                col = outside == 1 ? 1 : 0;
-                inside = false;
-            }
-            if (inside) {
-                const float w = (float)W, h = (float)H;
-                int u, v;
-                if (is_spherical) {
-                    u = (int)(w / 2.f * (1.f - az / hfov));
-                    v = (int)(h / 2.f * (1.f - el / vfov));
-                } else {
-                    u = (int)(w / 2.f * (1.f - tanf(az) / tanf(hfov)));
-                    v = (int)(h / 2.f * (1.f - tanf(el) / tanf(vfov)));
-                }
-                u = min(max(u, 0), W - 1);
-                v = min(max(v, 0), H - 1);
-                const long long ii = p2i ? (long long)p2i[tid] : tid / pts_per_img;
-                if (val >= img[(ii * H + v) * W + u] * dmax) col = 1;
-            }
-        }
-    }
-    out[tid] = col;
-}
-
-extern "C" int sdfnmpc_colcheck(const float* imgs, int32_t B, int32_t H, int32_t W, const float* pts, const int32_t* p2i, int64_t n,
-                                float dmax, float hfov, float vfov, float safe_ball, int32_t outside, int32_t is_depth,
-                                int32_t is_spherical, uint8_t* out, void* stream) {
-    if (n == 0) return 0;
-    if (!imgs || !pts || !out || B < 1 || H < 1 || W < 1 || n < 0 || outside < 0 || outside > 2) return SDFNMPC_E_INVALID;
-    if (int rc = ensure_device()) return rc;
-    const long long ppi = (n + B - 1) / B;
-    colcheck_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(imgs, H, W, pts, p2i, n, ppi, dmax, hfov, vfov, safe_ball,
-                                                                                  outside, is_depth, is_spherical, out);
-    count_launch();
-    SDF_CUDA_CHECK(cudaGetLastError());
-    return 0;
-}
-
 extern "C" int sdfnmpc_encoder_encode_host(sdfnmpc_encoder_t h, const float* imgs, int32_t B, float* latents) {
     if (!h || !imgs || !latents || B < 1 || B > h->desc.max_batch) return SDFNMPC_E_INVALID;
     const size_t img_floats = (size_t)h->desc.height * h->desc.width;
@@ -688,6 +641,239 @@ extern "C" int sdfnmpc_encoder_encode_host(sdfnmpc_encoder_t h, const float* img
     SDF_CUDA_CHECK(cudaMemcpyAsync(h->h_img, imgs, img_floats * B * sizeof(float), cudaMemcpyHostToDevice, 0));
     if (int rc = sdfnmpc_encoder_encode(h, h->h_img, B, h->h_lat, nullptr)) return rc;
     SDF_CUDA_CHECK(cudaMemcpyAsync(latents, h->h_lat, (size_t)h->desc.size_latent * B * sizeof(float), cudaMemcpyDeviceToHost, 0));
+    SDF_CUDA_CHECK(cudaStreamSynchronize(0));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// VAE decoder (VaeWrapper.decode, sdf_nmpc/vae.py:42-45; network/vae.py:63-90, network/resnet.py:59-111): latent ->
+// Linear + ELU -> [512, 8, 15] -> 4 x ResBlockDeconv (stride 2, output_padding 1) -> ConvTranspose2d(32, 1, 5, padding 2)
+// -> bilinear Upsample(shape_imgs) -> Sigmoid.  BatchNorm in eval mode is folded, dropout is the identity.
+//
+// Every transposed convolution runs as an ordinary convolution on the tensor-core kernel of the encoder (conv_tc.cuh):
+//   * stride 1, 3x3, padding 1: a 3x3 convolution with the kernel flipped and the channel axes exchanged;
+//   * stride 2, 3x3, padding 1, output_padding 1 (oy = 2 iy - 1 + ky): output rows of parity 0 see (ky 1, iy = a), rows of
+//     parity 1 see (ky 2, iy = a) and (ky 0, iy = a + 1) - a 2x2 convolution over the INPUT grid with 4 x Cout channels, one
+//     group per output parity class, written through the kernel's sub-pixel epilogue (ConvTcParams: "Sub-pixel output").
+//     K = 4 Cin taps for 9 useful ones per 4 outputs (1.8 x the useful products) instead of the 4 x of a convolution over the
+//     zero-stuffed input;
+//   * the 1x1 stride-2 shortcut (oy = 2 iy): the same form with a 1x1 window, class (0, 0) carries the weights, the other
+//     classes only the folded BatchNorm shift.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+// out[b][j] = ELU(w[j] . z[b] + bias[j]): a warp per output row, the batch looped inside (weights read once)
+__global__ void __launch_bounds__(256)
+dec_linear_elu_kernel(int L, int J, int B, const float* __restrict__ z, const float* __restrict__ w, const float* __restrict__ bias,
+                      float* __restrict__ out) {
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (j >= J) return;
+    const float* wr = w + (size_t)j * L;
+    for (int b = 0; b < B; ++b) {
+        float s = 0.f;
+        for (int k = lane; k < L; k += 32) s = fmaf(__ldg(wr + k), __ldg(z + (size_t)b * L + k), s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) {
+            const float v = s + bias[j];
+            out[(size_t)b * J + j] = v > 0.f ? v : expm1f(v);
+        }
+    }
+}
+
+// ConvTranspose2d(Cin, 1, 5, stride 1, padding 2) + bias as a 5x5 convolution with the flipped kernel: 16 x 16 output pixels per
+// CTA, 8 input channels of the 20 x 20 patch in shared memory at a time.
+constexpr int DO_T = 16, DO_C = 8;
+__global__ void __launch_bounds__(DO_T * DO_T)
+dec_out_conv_kernel(int Cin, int H, int W, const float* __restrict__ in, const float* __restrict__ w /*[Cin][25], flipped*/, float bias,
+                    float* __restrict__ out /*[B][H][W]*/) {
+    __shared__ float patch[DO_C][DO_T + 4][DO_T + 4 + 1];
+    __shared__ float wsm[DO_C][25];
+    const int b = blockIdx.z, y0 = blockIdx.y * DO_T, x0 = blockIdx.x * DO_T, tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const float* inb = in + (size_t)b * Cin * H * W;
+    float acc = 0.f;
+    for (int c0 = 0; c0 < Cin; c0 += DO_C) {
+        for (int i = threadIdx.x; i < DO_C * (DO_T + 4) * (DO_T + 4); i += DO_T * DO_T) {
+            const int c = i / ((DO_T + 4) * (DO_T + 4)), q = i - c * (DO_T + 4) * (DO_T + 4), r = q / (DO_T + 4), cc = q - r * (DO_T + 4);
+            const int iy = y0 + r - 2, ix = x0 + cc - 2;
+            float v = 0.f;
+            if (c0 + c < Cin && iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(inb + ((size_t)(c0 + c) * H + iy) * W + ix);
+            patch[c][r][cc] = v;
+        }
+        if (threadIdx.x < DO_C * 25) {
+            const int c = threadIdx.x / 25, t = threadIdx.x - c * 25;
+            wsm[c][t] = c0 + c < Cin ? __ldg(w + (size_t)(c0 + c) * 25 + t) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < DO_C; ++c)
+#pragma unroll
+            for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 5; ++kx) acc = fmaf(patch[c][ty + ky][tx + kx], wsm[c][ky * 5 + kx], acc);
+        __syncthreads();
+    }
+    const int y = y0 + ty, x = x0 + tx;
+    if (y < H && x < W) out[((size_t)b * H + y) * W + x] = acc + bias;
+}
+
+// torch.nn.Upsample(size, mode='bilinear') (align_corners False: source = max(0, scale (dst + 0.5) - 0.5), scale = in / out in
+// float32) + Sigmoid
+__global__ void dec_upsample_sigmoid_kernel(int Hi, int Wi, int Ho, int Wo, long long total, const float* __restrict__ in,
+                                            float* __restrict__ out) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int x = (int)(gid % Wo), y = (int)((gid / Wo) % Ho);
+    const long long b = gid / ((long long)Wo * Ho);
+    const float sh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;
+    const float fy = fmaxf(sh * ((float)y + 0.5f) - 0.5f, 0.f), fx = fmaxf(sw * ((float)x + 0.5f) - 0.5f, 0.f);
+    const int y0 = (int)fy, x0 = (int)fx, y1 = y0 + (y0 < Hi - 1 ? 1 : 0), x1 = x0 + (x0 < Wi - 1 ? 1 : 0);
+    const float ly = fy - (float)y0, lx = fx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+    const float* p = in + (size_t)b * Hi * Wi;
+    const float v = hy * (hx * p[y0 * Wi + x0] + lx * p[y0 * Wi + x1]) + ly * (hx * p[y1 * Wi + x0] + lx * p[y1 * Wi + x1]);
+    out[gid] = 1.f / (1.f + expf(-v));
+}
+
+constexpr int DEC_C0 = 512, DEC_H0 = 8, DEC_W0 = 15;     // network/vae.py:73-75 (hard-coded in the reference)
+
+}  // namespace
+
+struct sdfnmpc_decoder {
+    sdfnmpc_decoder_desc desc;
+    Layer c1[4], c2[4], sc[4];
+    float *lin_w = nullptr, *lin_b = nullptr, *out_w = nullptr;
+    float out_b = 0.f;
+    float* buf[3] = {nullptr, nullptr, nullptr};
+    float *part = nullptr, *h_lat = nullptr, *h_img = nullptr;
+    size_t part_floats = 0;
+    int Hf = 0, Wf = 0, Cf = 0;
+};
+
+// ConvTranspose2d weight [Cin][Cout][3][3], stride 2, padding 1, output_padding 1 -> 2x2 convolution [4 Cout][Cin][2][2]
+static std::vector<float> convt_s2_to_subpixel(const float* wt, int Cin, int Cout) {
+    std::vector<float> w((size_t)4 * Cout * Cin * 4, 0.f);
+    const int kmap[2][2] = {{1, -1}, {2, 0}};            // [output parity][window offset] -> kernel index (-1: no tap)
+    for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px)
+            for (int co = 0; co < Cout; ++co)
+                for (int ci = 0; ci < Cin; ++ci)
+                    for (int dy = 0; dy < 2; ++dy)
+                        for (int dx = 0; dx < 2; ++dx) {
+                            const int ky = kmap[py][dy], kx = kmap[px][dx];
+                            if (ky < 0 || kx < 0) continue;
+                            w[((((size_t)(py * 2 + px) * Cout + co) * Cin + ci) * 2 + dy) * 2 + dx] = wt[(((size_t)ci * Cout + co) * 3 + ky) * 3 + kx];
+                        }
+    return w;
+}
+
+// ConvTranspose2d weight [Cin][Cout][k][k], stride 1, padding (k - 1) / 2 -> convolution weight [Cout][Cin][k][k] (flipped)
+static std::vector<float> convt_s1_to_conv(const float* wt, int Cin, int Cout, int k) {
+    std::vector<float> w((size_t)Cout * Cin * k * k);
+    for (int co = 0; co < Cout; ++co)
+        for (int ci = 0; ci < Cin; ++ci)
+            for (int ky = 0; ky < k; ++ky)
+                for (int kx = 0; kx < k; ++kx)
+                    w[(((size_t)co * Cin + ci) * k + ky) * k + kx] = wt[(((size_t)ci * Cout + co) * k + (k - 1 - ky)) * k + (k - 1 - kx)];
+    return w;
+}
+
+extern "C" int sdfnmpc_decoder_destroy(sdfnmpc_decoder_t h) {
+    if (!h) return 0;
+    for (int i = 0; i < 4; ++i)
+        for (Layer* l : {&h->c1[i], &h->c2[i], &h->sc[i]}) { cudaFree(l->w); cudaFree(l->b); cudaFree(l->wblob_tc); cudaFree(l->ktab); }
+    cudaFree(h->lin_w); cudaFree(h->lin_b); cudaFree(h->out_w);
+    for (float* b : h->buf) cudaFree(b);
+    cudaFree(h->part); cudaFree(h->h_lat); cudaFree(h->h_img);
+    delete h;
+    return 0;
+}
+
+extern "C" int sdfnmpc_decoder_create(sdfnmpc_decoder_t* out, const sdfnmpc_decoder_desc* d, const sdfnmpc_decoder_weights* w) {
+    if (!out || !d || !w || d->height < 1 || d->width < 1 || d->max_batch < 1 || d->size_latent < 1 || !w->lin_w || !w->lin_b || !w->out_w ||
+        !w->out_b)
+        return SDFNMPC_E_INVALID;
+    if (int rc = ensure_device()) return rc;
+    auto* h = new sdfnmpc_decoder();
+    h->desc = *d;
+    int rc = 0, C = DEC_C0, Hc = DEC_H0, Wc = DEC_W0;
+    const size_t J = (size_t)DEC_C0 * DEC_H0 * DEC_W0;
+    size_t maxf = J;
+    rc = upload(&h->lin_w, std::vector<float>(w->lin_w, w->lin_w + J * d->size_latent));
+    if (!rc) rc = upload(&h->lin_b, std::vector<float>(w->lin_b, w->lin_b + J));
+    for (int i = 0; i < 4 && !rc; ++i) {
+        if (!w->ct1_w[i] || !w->ct2_w[i] || !w->sc_w[i]) { rc = SDFNMPC_E_INVALID; break; }
+        const int Co = C / 2;
+        // conv form: 2x2 window over the input grid, "output" grid = input grid, 4 Co channels, sub-pixel epilogue
+        h->c1[i].s = {C, Hc, Wc, 4 * Co, Hc, Wc, 1, 0, 1}; h->c1[i].ks = 2;
+        h->sc[i].s = {C, Hc, Wc, 4 * Co, Hc, Wc, 1, 0, 1}; h->sc[i].ks = 1;
+        h->c2[i].s = {Co, 2 * Hc, 2 * Wc, Co, 2 * Hc, 2 * Wc, 1, 1, 0}; h->c2[i].ks = 3;
+        const std::vector<float> w1 = convt_s2_to_subpixel(w->ct1_w[i], C, Co);
+        std::vector<float> wsc((size_t)4 * Co * C, 0.f);                      // class (0, 0) = rows [0, Co)
+        for (int co = 0; co < Co; ++co)
+            for (int ci = 0; ci < C; ++ci) wsc[(size_t)co * C + ci] = w->sc_w[i][(size_t)ci * Co + co];
+        const std::vector<float> w2 = convt_s1_to_conv(w->ct2_w[i], Co, Co, 3);
+        rc = make_layer(h->c1[i], w1.data(), w->bn1[i], nullptr, w->bn_eps);
+        if (!rc) rc = make_layer(h->sc[i], wsc.data(), w->sc_bn[i], nullptr, w->bn_eps);
+        if (!rc) rc = make_layer(h->c2[i], w2.data(), w->bn2[i], nullptr, w->bn_eps);
+        C = Co; Hc *= 2; Wc *= 2;
+        maxf = std::max(maxf, (size_t)C * Hc * Wc);
+    }
+    h->Cf = C; h->Hf = Hc; h->Wf = Wc;
+    if (!rc) rc = upload(&h->out_w, convt_s1_to_conv(w->out_w, C, 1, 5));
+    h->out_b = w->out_b[0];
+    maxf = std::max(maxf, (size_t)d->height * d->width);
+    for (int i = 0; i < 3 && !rc; ++i) rc = (int)cudaMalloc(&h->buf[i], maxf * (size_t)d->max_batch * sizeof(float));
+    if (!rc) {
+        int dev = 0, sms = 0;
+        rc = (int)cudaGetDevice(&dev);
+        if (!rc) rc = (int)cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const size_t nb = (size_t)std::min(d->max_batch, ENC_SPLIT_MAX_B);
+        for (int i = 0; i < 4 && !rc; ++i)
+            for (const Layer* l : {&h->c1[i], &h->c2[i], &h->sc[i]})
+                if (l->wblob_tc) {
+                    const int ks = conv_ksplit(*l, 1, sms);
+                    if (ks > 1) h->part_floats = std::max(h->part_floats, (size_t)ks * nb * l->s.Cout * l->s.Hout * l->s.Wout);
+                }
+        if (!rc && h->part_floats) rc = (int)cudaMalloc(&h->part, h->part_floats * sizeof(float));
+    }
+    if (rc) { sdfnmpc_decoder_destroy(h); return rc; }
+    *out = h;
+    return 0;
+}
+
+extern "C" int sdfnmpc_decoder_decode(sdfnmpc_decoder_t h, const float* latents, int32_t B, float* imgs, void* stream) {
+    if (!h || !latents || !imgs || B < 1 || B > h->desc.max_batch) return SDFNMPC_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int J = DEC_C0 * DEC_H0 * DEC_W0;
+    float *x = h->buf[0], *t1 = h->buf[1], *t2 = h->buf[2];
+    dec_linear_elu_kernel<<<(J + 7) / 8, 256, 0, st>>>(h->desc.size_latent, J, B, latents, h->lin_w, h->lin_b, x);
+    count_launch();
+    SDF_CUDA_CHECK(cudaGetLastError());
+    int rc = 0;
+    for (int i = 0; i < 4; ++i) {
+        if ((rc = launch_conv<2, false>(h->c1[i], B, x, nullptr, ENC_ACT_RELU, t1, st, nullptr, 1.f, 0, 0, h->part, h->part_floats))) return rc;
+        if ((rc = launch_conv<1, false>(h->sc[i], B, x, nullptr, ENC_ACT_NONE, t2, st, nullptr, 1.f, 0, 0, h->part, h->part_floats))) return rc;
+        if ((rc = launch_conv<3, false>(h->c2[i], B, t1, t2, ENC_ACT_RELU, x, st, nullptr, 1.f, 0, 0, h->part, h->part_floats))) return rc;
+    }
+    dim3 grid((h->Wf + DO_T - 1) / DO_T, (h->Hf + DO_T - 1) / DO_T, B);
+    dec_out_conv_kernel<<<grid, DO_T * DO_T, 0, st>>>(h->Cf, h->Hf, h->Wf, x, h->out_w, h->out_b, t1);
+    count_launch();
+    SDF_CUDA_CHECK(cudaGetLastError());
+    const long long total = (long long)B * h->desc.height * h->desc.width;
+    dec_upsample_sigmoid_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(h->Hf, h->Wf, h->desc.height, h->desc.width, total, t1, imgs);
+    count_launch();
+    SDF_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int sdfnmpc_decoder_decode_host(sdfnmpc_decoder_t h, const float* latents, int32_t B, float* imgs) {
+    if (!h || !latents || !imgs || B < 1 || B > h->desc.max_batch) return SDFNMPC_E_INVALID;
+    const size_t img_floats = (size_t)h->desc.height * h->desc.width;
+    if (!h->h_img) SDF_CUDA_CHECK(cudaMalloc(&h->h_img, img_floats * h->desc.max_batch * sizeof(float)));
+    if (!h->h_lat) SDF_CUDA_CHECK(cudaMalloc(&h->h_lat, (size_t)h->desc.size_latent * h->desc.max_batch * sizeof(float)));
+    SDF_CUDA_CHECK(cudaMemcpyAsync(h->h_lat, latents, (size_t)h->desc.size_latent * B * sizeof(float), cudaMemcpyHostToDevice, 0));
+    if (int rc = sdfnmpc_decoder_decode(h, h->h_lat, B, h->h_img, nullptr)) return rc;
+    SDF_CUDA_CHECK(cudaMemcpyAsync(imgs, h->h_img, img_floats * B * sizeof(float), cudaMemcpyDeviceToHost, 0));
     SDF_CUDA_CHECK(cudaStreamSynchronize(0));
     return 0;
 }

@@ -87,6 +87,39 @@ def make_encoder_net(seed=0, size_latent=128, nb_chan=1):
     return net
 
 
+def make_decoder_net(seed=0, size_latent=128):
+    """Synthetic VAE-decoder parameters (``sdf_nmpc/network/vae.py:63-90``, ``resnet.py:59-111``), torch layouts:
+    ConvTranspose2d weights [Cin, Cout, kh, kw]; BatchNorm statistics randomised as for the encoder."""
+    rng = np.random.default_rng(seed)
+
+    def convt(cin, cout, k, gain=1.0):
+        # a stride-2 transposed convolution spreads each input over k*k/4 outputs: bound chosen to keep activations O(1)
+        bound = gain * np.sqrt(6.0 / (cin * k * k / 2.0))
+        return rng.uniform(-bound, bound, size=(cin, cout, k, k)).astype(np.float32)
+
+    def bn(c):
+        return dict(weight=rng.uniform(0.5, 1.5, c).astype(np.float32), bias=rng.uniform(-0.2, 0.2, c).astype(np.float32),
+                    mean=(0.1 * rng.standard_normal(c)).astype(np.float32), var=rng.uniform(0.5, 1.5, c).astype(np.float32),
+                    eps=1e-5)
+
+    J = 512 * 8 * 15
+    bound = 1.0 / np.sqrt(size_latent)
+    net = dict(size_latent=int(size_latent), seed=int(seed),
+               lin_w=rng.uniform(-bound, bound, size=(J, size_latent)).astype(np.float32),
+               lin_b=rng.uniform(-bound, bound, size=(J,)).astype(np.float32))
+    blocks = []
+    c = 512
+    for _ in range(4):
+        co = c // 2
+        blocks.append(dict(ct1_w=convt(c, co, 3), bn1=bn(co), ct2_w=convt(co, co, 3, 0.7), bn2=bn(co), sc_w=convt(c, co, 1, 0.5),
+                           sc_bn=bn(co)))
+        c = co
+    net['blocks'] = blocks
+    net['out_w'] = convt(c, 1, 5, 0.5)
+    net['out_b'] = rng.uniform(-0.2, 0.2, size=(1,)).astype(np.float32)
+    return net
+
+
 # --------------------------------------------------------------------------------------
 # workloads (SURVEY.md 8d)
 # --------------------------------------------------------------------------------------

@@ -58,6 +58,27 @@ def encoder_from_module(encoder):
     return net
 
 
+def decoder_from_module(decoder):
+    """``Vae.decoder`` (``network/vae.py:63-90``) -> the dictionary layout of ``synth.make_decoder_net``."""
+    sd = decoder.state_dict()
+    net = dict(size_latent=int(sd['layers.resnet.0.weight'].shape[1]), lin_w=_np(sd['layers.resnet.0.weight']),
+               lin_b=_np(sd['layers.resnet.0.bias']))
+    if net['lin_w'].shape[0] != 512 * 8 * 15:
+        raise ValueError('decoder: the Linear layer must feed the [512, 8, 15] feature map of network/vae.py:73-75')
+
+    def bn(q):
+        return dict(weight=_np(sd[q + '.weight']), bias=_np(sd[q + '.bias']), mean=_np(sd[q + '.running_mean']),
+                    var=_np(sd[q + '.running_var']), eps=1e-5)
+    blocks = []
+    for i in range(4):
+        p = f'layers.resnet.{4 + i}.'
+        blocks.append(dict(ct1_w=_np(sd[p + 'layers.0.weight']), bn1=bn(p + 'layers.1'), ct2_w=_np(sd[p + 'layers.3.weight']),
+                           bn2=bn(p + 'layers.4'), sc_w=_np(sd[p + 'shortcut.0.weight']), sc_bn=bn(p + 'shortcut.1')))
+    net['blocks'] = blocks
+    net['out_w'], net['out_b'] = _np(sd['layers.resnet.8.weight']), _np(sd['layers.resnet.8.bias'])
+    return net
+
+
 def load_sdf(cfg):
     """``gen_model.py:32-34``: ``torch.jit.load(default_data_dir() / cfg.nn.sdf_weights)`` -> packed dictionary."""
     import os
@@ -84,6 +105,21 @@ def load_encoder(cfg):
         raise FileNotFoundError(f'{path}: TorchScript VAE weights not found (the reference ships them through Git LFS); '
                                 'put the file there, call sdf_nmpc_b200.set_data_dir(...) or pass enc_net=')
     return encoder_from_module(torch.jit.load(path, map_location='cpu').eval().encoder)
+
+
+def load_vae(cfg):
+    """Encoder AND decoder dictionaries of the TorchScript VAE ``cfg.nn.vae_weights`` (``vae.py:11-13``)."""
+    import os
+
+    import torch
+
+    from . import default_data_dir
+    path = os.path.join(default_data_dir(), cfg.nn.vae_weights)
+    if not os.path.isfile(path) or os.path.getsize(path) < 1024:
+        raise FileNotFoundError(f'{path}: TorchScript VAE weights not found (the reference ships them through Git LFS); '
+                                'put the file there, call sdf_nmpc_b200.set_data_dir(...) or pass enc_net= / dec_net=')
+    vae = torch.jit.load(path, map_location='cpu').eval()
+    return encoder_from_module(vae.encoder), (decoder_from_module(vae.decoder) if hasattr(vae, 'decoder') else None)
 
 
 def sdf_desc_fields(net):

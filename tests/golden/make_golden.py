@@ -129,6 +129,37 @@ def encoder_case():
     np.savez_compressed(os.path.join(HERE, 'encoder.npz'), seed=5, frame_seed0=1, **out)
 
 
+def ref_decoder(net):
+    from sdf_nmpc.network.vae import Vae
+    dec = Vae(size_latent=net['size_latent'], shape_imgs=[270, 480], dropout_rate=0.1, batchnorm=True).decoder
+    sd = dec.state_dict()
+    t = torch.from_numpy
+    sd['layers.resnet.0.weight'] = t(net['lin_w']); sd['layers.resnet.0.bias'] = t(net['lin_b'])
+    for i, blk in enumerate(net['blocks']):
+        p = f'layers.resnet.{4 + i}.'
+        sd[p + 'layers.0.weight'] = t(blk['ct1_w']); sd[p + 'layers.3.weight'] = t(blk['ct2_w']); sd[p + 'shortcut.0.weight'] = t(blk['sc_w'])
+        for q, key in ((p + 'layers.1', 'bn1'), (p + 'layers.4', 'bn2'), (p + 'shortcut.1', 'sc_bn')):
+            sd[q + '.weight'] = t(blk[key]['weight']); sd[q + '.bias'] = t(blk[key]['bias'])
+            sd[q + '.running_mean'] = t(blk[key]['mean']); sd[q + '.running_var'] = t(blk[key]['var'])
+    sd['layers.resnet.8.weight'] = t(net['out_w']); sd['layers.resnet.8.bias'] = t(net['out_b'])
+    dec.load_state_dict(sd)
+    return dec.eval()
+
+
+def decoder_case():
+    """vae.py:42-45 on two seeded latents: a sparse sample of the decoded image (every 9th row, 8th column) and its sums,
+    from the reference's Decoder in float32 and float64."""
+    net = synth.make_decoder_net(seed=7)
+    dec = ref_decoder(net)
+    z = synth.latent(seed=11, n=2).astype(np.float32)
+    with torch.no_grad():
+        img32 = dec(torch.from_numpy(z)).numpy()[:, 0]
+        img64 = dec.double()(torch.from_numpy(z).double()).numpy()[:, 0]
+    np.savez_compressed(os.path.join(HERE, 'decoder.npz'), seed=7, latent_seed=11, rows32=img32[:, ::9, ::8].copy(),
+                        rows64=img64[:, ::9, ::8].copy(), sum32=img32.astype(np.float64).sum((1, 2)), sum64=img64.sum((1, 2)))
+    print('decoder: image range', img32.min(), img32.max(), 'f32-f64', np.abs(img32 - img64).max())
+
+
 def model_att_case():
     """f_expl, y, yN, h values of model 'att' composed from the reference's numpy math helpers exactly as
     model/quad_rollpitchyawrate.py:20-55, cost_const_helpers.py:56-65 and gen_model.py:46-51 compose them."""
@@ -326,6 +357,7 @@ if __name__ == '__main__':
              act='relu', w0=1.0)
     sdf_case('small_latent_softplus', 256, seed=5, embed='ico', nb_freqs=2, layer_sizes=(64, 32, 32, 16), res='latent',
              act='softplus', w0=1.0, size_latent=32)
+    decoder_case()
     model_att_case()
     model_variants_case()
     model_props_case()

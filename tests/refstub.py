@@ -81,10 +81,48 @@ class _EncoderStub(nn.Module):
         return x
 
 
+def _convt(W, bias=None, stride=1, pad=0, out_pad=0):
+    m = nn.ConvTranspose2d(W.shape[0], W.shape[1], W.shape[2], stride, pad, out_pad, bias=bias is not None)
+    with torch.no_grad():
+        m.weight.copy_(torch.as_tensor(W))
+        if bias is not None:
+            m.bias.copy_(torch.as_tensor(bias))
+    return m
+
+
+class _ResBlockDeconvStub(nn.Module):
+    def __init__(self, blk):
+        super().__init__()
+        self.layers = nn.Sequential(_convt(blk['ct1_w'], None, 2, 1, 1), _bn(blk['bn1']), nn.ReLU(), _convt(blk['ct2_w'], None, 1, 1, 0),
+                                    _bn(blk['bn2']))
+        self.shortcut = nn.Sequential(_convt(blk['sc_w'], None, 2, 0, 1), _bn(blk['sc_bn']))
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return x
+
+
+class _DecoderStub(nn.Module):
+    """Parameter names of ``network/vae.py:63-90`` (Sequential indices 0 Linear, 4-7 ResBlockDeconv, 8 ConvTranspose2d)."""
+
+    def __init__(self, dec):
+        super().__init__()
+        lin = nn.Linear(dec['lin_w'].shape[1], dec['lin_w'].shape[0])
+        with torch.no_grad():
+            lin.weight.copy_(torch.as_tensor(dec['lin_w'])); lin.bias.copy_(torch.as_tensor(dec['lin_b']))
+        self.layers = nn.ModuleDict(dict(
+            resnet=nn.Sequential(lin, nn.ELU(), nn.Identity(), nn.Identity(), *[_ResBlockDeconvStub(b) for b in dec['blocks']],
+                                 _convt(dec['out_w'], dec['out_b'], 1, 2, 0))))
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return x
+
+
 class VaeStub(nn.Module):
-    def __init__(self, enc):
+    def __init__(self, enc, dec=None):
         super().__init__()
         self.encoder = _EncoderStub(enc)
+        if dec is not None:
+            self.decoder = _DecoderStub(dec)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return x

@@ -26,7 +26,7 @@ def data_dir(tmp_path_factory):
     net = synth.make_sdf_net(seed=0, **synth.ARCH_B, calibrated=True)
     enc = synth.make_encoder_net(seed=5)
     torch.jit.script(refstub.NeuralDFStub(net).eval()).save(str(d / cfg.nn.sdf_weights))
-    torch.jit.script(refstub.VaeStub(enc).eval()).save(str(d / cfg.nn.vae_weights))
+    torch.jit.script(refstub.VaeStub(enc, synth.make_decoder_net(seed=7)).eval()).save(str(d / cfg.nn.vae_weights))
     sdf_nmpc_b200.set_data_dir(d)
     yield d, net, enc
     sdf_nmpc_b200.set_data_dir(None)
@@ -47,6 +47,8 @@ def test_reference_call_sequence_runs_verbatim(data_dir, cuda_device):
     vae.set_img(img)
     latent = vae.encode()                      # [1, 128]
     assert latent.shape == (1, 128)
+    decoded = vae.decode()                     # vae.py:42-45: [H, W] in [0, 1]
+    assert decoded.shape == (270, 480) and 0 <= decoded.min() and decoded.max() <= 1
     x0 = np.array([0, 0, 2, 1, 0, 0, 0, 0, 0, 0], float)
     mpc.set_sdf_flag(True)
     mpc.set_latent(latent, x0[:3], np.eye(3))
