@@ -218,27 +218,30 @@ conv0_pool_kernel(int Hin, int Win, int Hc, int Wc, int Hp, int Wp, const float*
                     }
                 }
             }
+            // conv pixels outside the image are the max-pool's padding: stored as -inf, so that the pooling pass below reads its
+            // nine values unconditionally (with the bounds tests per value that pass was 42 % of the kernel's instructions)
+            const int cy = cy0 + cr, cxb = cx0 + 4 * cgp;
+            const bool rowok = cy >= 0 && cy < Hc;
+            bool ok[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) ok[p] = rowok && cxb + p >= 0 && cxb + p < Wc;
 #pragma unroll
             for (int c = 0; c < 16; ++c)
-                *reinterpret_cast<float4*>(csm + ((cgl * 16 + c) * C0_CR + cr) * C0_CC + 4 * cgp) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+                *reinterpret_cast<float4*>(csm + ((cgl * 16 + c) * C0_CR + cr) * C0_CC + 4 * cgp) =
+                    make_float4(ok[0] ? acc[0][c] : -INFINITY, ok[1] ? acc[1][c] : -INFINITY, ok[2] ? acc[2][c] : -INFINITY, ok[3] ? acc[3][c] : -INFINITY);
         }
         __syncthreads();
         for (int i = threadIdx.x; i < C0_CPR * C0_PH * C0_PW; i += C0_THREADS) {
             const int c = i / (C0_PH * C0_PW), q = i - c * (C0_PH * C0_PW), pyl = q / C0_PW, pxl = q - pyl * C0_PW;
             const int py = py0 + pyl, px = px0 + pxl;
             if (py >= Hp || px >= Wp) continue;
-            float m = -INFINITY;
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-                const int cy = cy0 + 2 * pyl + ky;
-                if (cy < 0 || cy >= Hc) continue;
-#pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    const int cx = cx0 + 2 * pxl + kx;
-                    if (cx < 0 || cx >= Wc) continue;
-                    m = fmaxf(m, csm[(c * C0_CR + 2 * pyl + ky) * C0_CC + 2 * pxl + kx]);
-                }
-            }
+            const float* cw = csm + (c * C0_CR + 2 * pyl) * C0_CC + 2 * pxl;
+            // (even offsets: the first two values of a row are one conflict-free 8-byte load)
+            const float2 r0 = *reinterpret_cast<const float2*>(cw), r1 = *reinterpret_cast<const float2*>(cw + C0_CC),
+                         r2 = *reinterpret_cast<const float2*>(cw + 2 * C0_CC);
+            float m = fmaxf(fmaxf(r0.x, r0.y), cw[2]);
+            m = fmaxf(m, fmaxf(fmaxf(r1.x, r1.y), cw[C0_CC + 2]));
+            m = fmaxf(m, fmaxf(fmaxf(r2.x, r2.y), cw[2 * C0_CC + 2]));
             const int cglob = round * C0_CPR + c;
             const float v = m + __ldg(bias + cglob);
             out[(((size_t)b * C0_CH + cglob) * Hp + py) * Wp + px] = v > 0.f ? v : expm1f(v);
