@@ -437,7 +437,7 @@ def run_ours(args, rank, local_rank, world):
         latency = latency_bench(net, cfg)
     cpu_v, cpu_info, cpu_np = (None, None, None)
     if world == 1 and not args.no_cpu:
-        cpu_v, cpu_info = cpu_port_throughput(16, 6, 'cxx', os.cpu_count() or 1)
+        cpu_v, cpu_info = cpu_port_throughput(16, 20, 'cxx', os.cpu_count() or 1)      # ~25 core-seconds of CPU work
         if not args.no_sweep:
             cpu_np = cpu_port_throughput(4, 1, 'numpy', os.cpu_count() or 1, warmup=0)
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W_, ms_per_step=ms_total / K, higher_is_better=True,
@@ -761,8 +761,20 @@ def encoder_microbench(peaks):
     from sdf_nmpc_b200.config import Config
     from sdf_nmpc_b200.vae import VaeWrapper
     out = {}
-    vae = VaeWrapper(Config(), synth.make_encoder_net(seed=5), max_batch=256)
+    vae = VaeWrapper(Config(), synth.make_encoder_net(seed=5), max_batch=256, dec_net=synth.make_decoder_net(seed=7))
     base = np.stack([synth.depth_frame(seed=1 + i) for i in range(4)])
+
+    def timed(fn, reps=5):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
     for nb in (1, 64, 256):
         vae.set_img(np.concatenate([base] * ((nb + 3) // 4))[:nb])
         for _ in range(2):
@@ -779,6 +791,8 @@ def encoder_microbench(peaks):
         tf = nb * ENC_FLOP_FRAME / ms / 1e9
         out[str(nb)] = dict(ms=ms, frames_per_s=nb / ms * 1e3, tflops=tf, frac_bf16_sustained=tf / peaks['bf16_tflops_sustained'],
                             frac_of_3xtf32_ceiling=tf / (peaks['bf16_tflops_sustained'] / 6.0))
+        if nb <= 64:      # VaeWrapper.decode of the latents just encoded (vae.py:42-45), the visualisation path
+            out[str(nb)]['decode_ms'] = timed(lambda: vae.decode(to_numpy=False))
     out['note'] = 'algorithmic FLOPs (4.34 GFLOP per frame) counted once; tensor-core layers use 3 TF32 MMAs per product'
     del vae
     out['torch_cudnn'] = encoder_torch_baseline()
