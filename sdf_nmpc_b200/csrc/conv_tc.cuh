@@ -45,7 +45,7 @@ enum { CV_ACT_NONE = 0, CV_ACT_RELU = 1, CV_ACT_ELU = 2 };
 struct ConvTcParams {
     int Cin, Hin, Win, Cout, Hout, Wout, stride, pad;
     long long npix;               // B * Hout * Wout
-    int NT;                       // output channels per N tile: 64, 128, 192 or 256 (Cout % NT == 0)
+    int NT;                       // output channels per N tile: 32, 64, 128, 192 or 256 (Cout % NT == 0)
     int n_ntiles, n_kchunks;
     const float* in;              // [B][Cin][Hin][Win]
     const unsigned char* wblob;   // [n_ntiles][n_kchunks][NT / NS sub-chunks][hi: NS x 128 B swizzled | lo], NS = min(NT, 128)
@@ -148,8 +148,9 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
             mbar_wait_backoff(dfull, item_it & 1);
             tc_fence_after();
             const uint32_t acc = lane_addr + (item_it & 1) * 256u;
-            const int ncol = P.NT >> 2, c_begin = (g * 2 + ch) * ncol;
-            for (int c0 = c_begin; c0 < c_begin + ncol; c0 += 16) {
+            // (NT = 32, the decoder's last block: two of the four take 16 columns each, the others none)
+            const int ncol = P.NT >= 64 ? P.NT >> 2 : 16, c_begin = (g * 2 + ch) * ncol;
+            for (int c0 = c_begin; c0 < c_begin + ncol && c0 < P.NT; c0 += 16) {
                 float v[16];
                 tc_ld16(acc + c0, v);
                 // output offset of channel co of this thread's pixel

@@ -157,7 +157,13 @@ __global__ void maxpool3s2_kernel(int C, int Hin, int Win, int Hout, int Wout, l
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int C0_PH = 8, C0_PW = 16, C0_CR = 2 * C0_PH + 1, C0_CC = 36, C0_IR = 2 * C0_CR + 5, C0_IC = 2 * C0_CC + 5;
 constexpr int C0_THREADS = 320, C0_CH = 64, C0_CPR = 32;     // channels per round
-constexpr int C0_PATCH_FLOATS = (C0_IR * C0_IC + 3) / 4 * 4;      // keeps the float4 regions behind it 16-byte aligned
+// Patch layout in shared memory: column c of a row sits at (c % 8) * C0_S + c / 8 ("de-interleaved by 8"), rows C0_RS apart.
+// A thread reads the 13 columns 8 cgp + i of its 4 conv pixels, so lanes with consecutive cgp read consecutive words; with the
+// plain layout their stride was 8 words (3.2 wavefronts per load, simulated), with this one and C0_RS = 85 it is 1.9 - the
+// rest comes from the ~4 patch rows a warp spans.
+constexpr int C0_S = 10, C0_RS = 85;
+static_assert(C0_S * 8 <= C0_RS && (C0_IC + 7) / 8 <= C0_S, "de-interleaved patch row");
+constexpr int C0_PATCH_FLOATS = (C0_IR * C0_RS + 3) / 4 * 4;      // keeps the float4 regions behind it 16-byte aligned
 constexpr int C0_SMEM_FLOATS = C0_PATCH_FLOATS + 49 * C0_CH + C0_CPR * C0_CR * C0_CC;
 
 __global__ void __launch_bounds__(C0_THREADS, 2)
@@ -180,7 +186,7 @@ conv0_pool_kernel(int Hin, int Win, int Hc, int Wc, int Hp, int Wp, const float*
             if (clip_dist) v = fminf(fmaxf(v / dmax, 0.f), 1.f);
             if (depth2range) v = fminf(fmaxf(v * __ldg(yz + iy * Win + ix), 0.f), 1.f);
         }
-        patch[i] = v;
+        patch[r * C0_RS + (c & 7) * C0_S + (c >> 3)] = v;
     }
     for (int i = threadIdx.x; i < 49 * C0_CH; i += C0_THREADS) {
         const int tap = i / C0_CH, c = i - tap * C0_CH;
@@ -202,9 +208,9 @@ conv0_pool_kernel(int Hin, int Win, int Hc, int Wc, int Hp, int Wp, const float*
 #pragma unroll 1
             for (int ky = 0; ky < 7; ++ky) {
                 float seg[13];
-                const float* pr = patch + (2 * cr + ky) * C0_IC + 8 * cgp;
+                const float* pr = patch + (2 * cr + ky) * C0_RS + cgp;
 #pragma unroll
-                for (int i = 0; i < 13; ++i) seg[i] = pr[i];
+                for (int i = 0; i < 13; ++i) seg[i] = pr[(i & 7) * C0_S + (i >> 3)];
 #pragma unroll
                 for (int kx = 0; kx < 7; ++kx) {
                     const float4* wp = reinterpret_cast<const float4*>(wsm + (ky * 7 + kx) * C0_CH + cbase);
@@ -373,7 +379,7 @@ static int make_layer(Layer& L, const float* w, const float* const bn[4], const 
     const int NT = L.s.Cout <= 256 ? L.s.Cout : 256;
     // (conv0 - Cin = 1, K = 49: two chunks per tile - was measured on this kernel too: 2.0 ms vs 1.14 ms at B = 64; a
     // tile that short is all pipeline fill / epilogue, so it stays on the CUDA cores)
-    if (L.s.Cin < 8 || NT % 64 || L.s.Cout % NT) return 0;
+    if (L.s.Cin < 8 || (NT % 64 && NT != 32) || L.s.Cout % NT) return 0;
     const int nk = (K + TC_KC - 1) / TC_KC;
     L.NT = NT; L.n_ntiles = L.s.Cout / NT; L.n_kchunks = nk;
     // sub-chunks of NS = min(NT, 128) output channels: [n tile][k chunk][sub][hi | lo], each one bulk copy (conv_tc.cuh)
