@@ -200,4 +200,102 @@ class BatchedRefGen:
             st = self._const(x0[:, :3], yaw2quat(yaw_r), torch.zeros_like(x0[:, :3]))
             m = turn[:, None, None]
             tr = RefTraj(torch.where(m, st.p, tr.p), torch.where(m, st.q, tr.q), torch.where(m, st.v, tr.v), tr.wz)
+            tr.turned = turn            # [B] instances that took the stop-and-turn branch
         return tr
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Single-instance facade with the reference's own classes and call sequence (``sdf_nmpc/utils/reference.py:6-53``,
+# ``sdf_nmpc/ref_gen.py:7-128``): ``refgen.x0 = x; traj = refgen.gen_ref_joystick(vw); mpc.set_ref(traj[k], k)``.
+# ------------------------------------------------------------------------------------------------------------------
+class Ref:
+    """One node's reference: ``p, q, v, wz`` and - set by the caller, as in the reference, or through ``use_weights`` - the
+    weights ``Wp, Wq, Wv, Ww, Wa`` that ``Nmpc.set_ref`` reads.  ``W_on`` / ``W_off`` keep the reference's naming
+    (``utils/reference.py:15-28``: ``W_on`` holds ``set_const_off`` and vice versa)."""
+
+    def __init__(self, cfg):
+        self.cfg = cfg
+        self.p, self.q, self.v, self.wz = [0., 0., 0.], [1., 0., 0., 0.], [0., 0., 0.], 0.
+        w = cfg.mpc.weights
+
+        def pack(s):
+            from .config import AttrDict
+            return AttrDict({'Wp': s.pos, 'Wq': s.att, 'Wv': s.vel, 'Ww': s.rates, 'Wa': s.acc})
+        self.W_on, self.W_off = pack(w.set_const_off), pack(w.set_const_on)
+
+    def use_weights(self, constraints_on=True):
+        """Convenience (not in the reference, whose callers assign the five attributes themselves): take the weight set
+        ``mpc.weights.set_const_on`` / ``set_const_off`` of the configuration."""
+        s = self.cfg.mpc.weights.set_const_on if constraints_on else self.cfg.mpc.weights.set_const_off
+        self.Wp, self.Wq, self.Wv, self.Ww, self.Wa = list(s.pos), list(s.att), list(s.vel), list(s.rates), s.acc
+        return self
+
+    def hover_at_state(self, x):
+        """utils/reference.py:40-44."""
+        import numpy as np
+        x = torch.as_tensor(np.asarray(x, float))
+        self.p = x[:3].numpy().copy()
+        self.q = yaw2quat(quat2yaw(x[3:7])).numpy()
+        self.v, self.wz = [0., 0., 0.], 0.
+
+
+class Waypoint:
+    """utils/reference.py:47-53."""
+
+    def __init__(self, p, q=(1, 0, 0, 0)):
+        import numpy as np
+        self.p, self.q = np.array(p, dtype=float), np.array(q, dtype=float)
+
+    def __str__(self):
+        return f'{self.p}, yaw {float(quat2yaw(torch.as_tensor(self.q))):.4f}'
+
+
+class RefGen:
+    """``sdf_nmpc.ref_gen.RefGen`` (``ref_gen.py:7-128``): set ``x0``, then ``from_x0()``, ``gen_ref_list_wps(wps)`` or
+    ``gen_ref_joystick(vwref)`` return a list of ``Ref`` (copies of ``self.ref``, so weights assigned to it carry over).
+    The arithmetic is ``BatchedRefGen``'s with a batch of one on the CPU (pinned to the reference's outputs,
+    ``tests/golden/refgen.npz``); like there, ``from_x0`` and the stop-and-turn branch return N entries, the others N + 1."""
+
+    def __init__(self, cfg):
+        self.cfg = cfg
+        self.x0 = None
+        self.ref = Ref(cfg)
+        self._b = BatchedRefGen(cfg)
+
+    def _reset(self):
+        self.ref = Ref(self.cfg)
+
+    def _list(self, tr, n):
+        import copy
+        out = []
+        for k in range(n):
+            r = copy.copy(self.ref)
+            r.p, r.q, r.v, r.wz = tr.p[0, k].numpy().copy(), tr.q[0, k].numpy().copy(), tr.v[0, k].numpy().copy(), float(tr.wz[0, k])
+            if getattr(tr, 'zero_Wp', False):
+                r.Wp = [0, 0, 0]
+            out.append(r)
+        return out
+
+    def _x0(self):
+        import numpy as np
+        self._b.set_x0(torch.as_tensor(np.asarray(self.x0, float)[None, :]))
+
+    def from_x0(self):
+        self._x0()
+        return self._list(self._b.from_x0(), self.cfg.mpc.N)
+
+    def gen_ref_joystick(self, vwref):
+        import numpy as np
+        self._x0()
+        return self._list(self._b.gen_ref_joystick(np.asarray(vwref, float)[None, :4]), self.cfg.mpc.N + 1)
+
+    def gen_ref_list_wps(self, wps):
+        import numpy as np
+        self._reset()
+        self._x0()
+        tr = self._b.gen_ref_list_wps(np.stack([w.p for w in wps])[None], np.stack([w.q for w in wps])[None])
+        n = self.cfg.mpc.N + 1
+        turned = getattr(tr, 'turned', None)
+        if turned is not None and bool(turned[0]):
+            n = self.cfg.mpc.N              # the stop-and-turn branch (ref_gen.py:35-50) returns N entries
+        return self._list(tr, n)
