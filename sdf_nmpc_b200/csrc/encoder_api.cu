@@ -548,7 +548,7 @@ static int launch_conv_tc(const Layer& L, int B, const float* in, const float* r
     const int grid = (int)(n_items < sm_count ? n_items : sm_count);
     P.trace = nullptr;
     static long long* tbuf = nullptr;
-    const char* tp = getenv("SDFNMPC_CV_TRACE");          // development: "<Cin>x<Cout>:<file>" traces that layer's issuer
+    static const char* const tp = getenv("SDFNMPC_CV_TRACE");   // development: "<Cin>x<Cout>:<file>" traces that layer's issuer (read once)
     int tci = 0, tco = 0; char tfile[256] = {0};
     const bool want = tp && sscanf(tp, "%dx%d:%255s", &tci, &tco, tfile) == 3 && tci == L.s.Cin && tco == L.s.Cout && L.ks == 3;
     if (want) {

@@ -90,3 +90,27 @@ def test_decoder_tensor_core_and_cuda_core_paths_agree(cuda_device):
     img_ffma = np.load(out)
     assert relmax(img_tc, img_ffma) <= IMG_TOL, relmax(img_tc, img_ffma)
     assert not np.array_equal(img_tc, img_ffma)
+
+
+@pytest.mark.parametrize('shape', [(96, 160), (125, 333)])
+def test_other_image_shapes_encode_and_decode(shape, cuda_device):
+    """sensor.shape_imgs other than the default 270 x 480 (odd sizes exercise the partial tiles of the fused first layer, the
+    adaptive pooling bins and the bilinear up-sampling): latents and reconstructions against the float64 oracles."""
+    from oracle import decoder as OD, encoder as OE
+    from sdf_nmpc_b200 import synth
+    from sdf_nmpc_b200.config import Config
+    from sdf_nmpc_b200.vae import VaeWrapper
+    H, W = shape
+    cfg = Config()
+    cfg.sensor.shape_imgs = [1, H, W]
+    enc, dec = synth.make_encoder_net(seed=13), synth.make_decoder_net(seed=14)
+    frames = np.stack([synth.depth_frame(seed=70 + i, H=H, W=W) for i in range(3)])
+    vae = VaeWrapper(cfg, enc, max_batch=3, device=cuda_device, dec_net=dec)
+    vae.set_img(frames)
+    lat = vae.encode()
+    pre = OE.preprocess(frames, hfov=cfg.sensor.hfov, vfov=cfg.sensor.vfov)
+    lat_ref = OE.encode(enc, pre)
+    assert relmax(lat, lat_ref) <= 1e-4, relmax(lat, lat_ref)
+    img = vae.decode()
+    ref = OD.decode(dec, lat_ref, (H, W))
+    assert img.shape == (3, H, W) and relmax(img, ref) <= 2 * IMG_TOL, relmax(img, ref)
