@@ -49,7 +49,13 @@ struct ConvTcParams {
     int n_ntiles, n_kchunks;
     const float* in;              // [B][Cin][Hin][Win]
     const unsigned char* wblob;   // [n_ntiles][n_kchunks][NT / NS sub-chunks][hi: NS x 128 B swizzled | lo], NS = min(NT, 128)
-    const int4* ktab;             // [n_kchunks * 32]: {(ci*Hin + ky)*Win + kx, ky, kx, k < K}
+    const int4* ktab;             // [n_kchunks * 32]: {(ci*Hin + ky)*Win + kx, ky, kx, source: 0 none (k >= K), 1 `in`, 2 `in2`}
+    // Second source (the ResBlock shortcut fused into the block's last convolution, resnet.py:40-54): k entries with source 2
+    // read in2[b][ci][s2 * oy][s2 * ox] (offset ci * H2 * W2, always inside the image), i.e. the 1x1 stride-s2 convolution of
+    // the block input accumulates into the same tile; its folded-BatchNorm shift is part of `bias`.
+    const float* in2;             // [B][C2][H2][W2] or null
+    int C2, H2, W2, s2;
+    int kc2;                      // first chunk of the second source (= n_kchunks without one; Cin k^2 must be a multiple of 32)
     const float* bias;            // [Cout] (folded BatchNorm shift)
     const float* resid;           // [B][Cout][Hout][Wout] or null
     int act;
@@ -129,12 +135,23 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
                 if ((int)(chunk & 1) != g) continue;
                 const int4* kt = P.ktab + kc * TC_KC + ch * 16;
                 float v[16];
+                if (kc < P.kc2) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int4 t = __ldg(kt + i);                    // same entry for the whole warp: one broadcast load
-                    const int iy = iy0 + t.y, ix = ix0 + t.z;
-                    const bool ok = pvalid && t.w && iy >= 0 && iy < P.Hin && ix >= 0 && ix < P.Win;
-                    v[i] = ok ? __ldg(inb + t.x) : 0.f;
+                    for (int i = 0; i < 16; ++i) {
+                        const int4 t = __ldg(kt + i);                    // same entry for the whole warp: one broadcast load
+                        const int iy = iy0 + t.y, ix = ix0 + t.z;
+                        const bool ok = pvalid && t.w && iy >= 0 && iy < P.Hin && ix >= 0 && ix < P.Win;
+                        v[i] = ok ? __ldg(inb + t.x) : 0.f;
+                    }
+                } else {
+                    // chunks of the second source (a whole chunk is one or the other: kc2 * 32 = Cin k^2): the loop above stays
+                    // as it was - a per-element source select cost it the 16 loads in flight (18 % of the layer time, measured)
+                    const float* inb2 = P.in2 + (size_t)pb * P.C2 * P.H2 * P.W2 + (long long)(oy * P.s2) * P.W2 + ox * P.s2;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int4 t = __ldg(kt + i);
+                        v[i] = (pvalid && t.w) ? __ldg(inb2 + t.x) : 0.f;
+                    }
                 }
                 float vhi[16], vlo[16];
                 split_a16(v, vhi, vlo);

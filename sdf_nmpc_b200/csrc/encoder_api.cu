@@ -318,6 +318,9 @@ struct Layer {
     unsigned char* wblob_tc = nullptr;
     int4* ktab = nullptr;
     int NT = 0, n_ntiles = 0, n_kchunks = 0;
+    // tensor-core form only: the block's 1x1 stride-s2 shortcut appended to K (ConvTcParams::in2), bias = both folded shifts
+    float* b_fused = nullptr;
+    int C2 = 0, H2 = 0, W2 = 0, s2 = 0;
 };
 
 inline float tf32_rna_host(float x) {
@@ -357,7 +360,11 @@ static int upload(float** dst, const std::vector<float>& v) {
 
 // fold BN (weight, bias, mean, var) into conv weights [Cout][K] and a bias [Cout]
 // (a sub-pixel layer has its BatchNorm / bias entries per REAL channel: index co % (Cout / 4))
-static int make_layer(Layer& L, const float* w, const float* const bn[4], const float* conv_bias, float eps) {
+// `sc` (optional): the shortcut layer of the same block, already made (folded weights sc->w [Cout][C2], shift sc->b); its K
+// entries are appended to this layer's tensor-core operands.
+static int make_layer(Layer& L, const float* w, const float* const bn[4], const float* conv_bias, float eps, const Layer* sc = nullptr,
+                      const std::vector<float>* sc_w = nullptr, const std::vector<float>* sc_b = nullptr,
+                      std::vector<float>* W_out = nullptr, std::vector<float>* B_out = nullptr) {
     const int K = L.s.Cin * L.ks * L.ks;
     std::vector<float> W((size_t)L.s.Cout * K), Bv(L.s.Cout, 0.f);
     const int cmod = L.s.shuffle ? L.s.Cout / 4 : L.s.Cout;
@@ -374,13 +381,24 @@ static int make_layer(Layer& L, const float* w, const float* const bn[4], const 
     }
     if (int rc = upload(&L.w, W)) return rc;
     if (int rc = upload(&L.b, Bv)) return rc;
+    if (W_out) *W_out = W;
+    if (B_out) *B_out = Bv;
     // ---- tensor-core operands (layers with Cout a multiple of 64; conv0 with its fused preprocessing stays on the
     // CUDA-core kernel) ----
     const int NT = L.s.Cout <= 256 ? L.s.Cout : 256;
     // (conv0 - Cin = 1, K = 49: two chunks per tile - was measured on this kernel too: 2.0 ms vs 1.14 ms at B = 64; a
     // tile that short is all pipeline fill / epilogue, so it stays on the CUDA cores)
     if (L.s.Cin < 8 || (NT % 64 && NT != 32) || L.s.Cout % NT) return 0;
-    const int nk = (K + TC_KC - 1) / TC_KC;
+    if (sc && K % TC_KC) sc = nullptr;                           // a chunk must belong to one source
+    const int K2 = sc ? sc->s.Cin : 0, KT = K + K2;              // second source: one k entry per shortcut input channel
+    if (sc) {
+        L.C2 = sc->s.Cin; L.H2 = sc->s.Hin; L.W2 = sc->s.Win; L.s2 = sc->s.stride;
+        std::vector<float> bf(L.s.Cout);
+        for (int co = 0; co < L.s.Cout; ++co) bf[co] = Bv[co] + (*sc_b)[co];
+        if (int rc = upload(&L.b_fused, bf)) return rc;
+    }
+    auto wat = [&](int co, int kk) { return kk < K ? W[(size_t)co * K + kk] : (kk < KT ? (*sc_w)[(size_t)co * K2 + (kk - K)] : 0.f); };
+    const int nk = (KT + TC_KC - 1) / TC_KC;
     L.NT = NT; L.n_ntiles = L.s.Cout / NT; L.n_kchunks = nk;
     // sub-chunks of NS = min(NT, 128) output channels: [n tile][k chunk][sub][hi | lo], each one bulk copy (conv_tc.cuh)
     const int NS = NT < CV_NSUB ? NT : CV_NSUB, nsub = NT / NS;
@@ -392,7 +410,7 @@ static int make_layer(Layer& L, const float* w, const float* const bn[4], const 
                 for (int n = 0; n < NS; ++n)
                     for (int k = 0; k < TC_KC; ++k) {
                         const int kk = kc * TC_KC + k;
-                        const float v = kk < K ? W[(size_t)(nt * NT + hs * NS + n) * K + kk] : 0.f;
+                        const float v = wat(nt * NT + hs * NS + n, kk);
                         const float hi = tf32_rna_host(v), lo = tf32_rna_host(v - hi);
                         // 128-byte-swizzled K-major: 8-row atoms of 1024 B, row = 32 floats, 16-byte unit index XOR row-in-atom
                         const size_t idx = (size_t)(n >> 3) * 256 + (size_t)(n & 7) * 32 + (size_t)(((k >> 2) ^ (n & 7)) * 4) + (k & 3);
@@ -409,6 +427,8 @@ static int make_layer(Layer& L, const float* w, const float* const bn[4], const 
         if (k < K) {
             const int ci = k / (L.ks * L.ks), rem = k % (L.ks * L.ks), ky = rem / L.ks, kx = rem % L.ks;
             t = make_int4((ci * L.s.Hin + ky) * L.s.Win + kx, ky, kx, 1);
+        } else if (k < KT) {
+            t = make_int4((k - K) * L.H2 * L.W2, 0, 0, 2);
         }
         kt[k] = t;
     }
@@ -437,13 +457,15 @@ extern "C" int sdfnmpc_encoder_create(sdfnmpc_encoder_t* out, const sdfnmpc_enco
         h->c1[i].s = {C, Hc, Wc, Co, Ho, Wo, st, 1}; h->c1[i].ks = 3;
         h->c2[i].s = {Co, Ho, Wo, Co, Ho, Wo, 1, 1}; h->c2[i].ks = 3;
         rc = make_layer(h->c1[i], w->conv1_w[i], w->bn1[i], nullptr, w->bn_eps);
-        if (!rc) rc = make_layer(h->c2[i], w->conv2_w[i], w->bn2[i], nullptr, w->bn_eps);
         h->has_sc[i] = st != 1;
+        std::vector<float> scW, scB;
         if (h->has_sc[i]) {
             if (!w->sc_w[i]) { rc = SDFNMPC_E_INVALID; break; }
             h->sc[i].s = {C, Hc, Wc, Co, out_dim(Hc, 1, st, 0), out_dim(Wc, 1, st, 0), st, 0}; h->sc[i].ks = 1;
-            if (!rc) rc = make_layer(h->sc[i], w->sc_w[i], w->sc_bn[i], nullptr, w->bn_eps);
+            if (!rc) rc = make_layer(h->sc[i], w->sc_w[i], w->sc_bn[i], nullptr, w->bn_eps, nullptr, nullptr, nullptr, &scW, &scB);
         }
+        // the block's last convolution carries the shortcut as extra K entries on the tensor-core path (conv_tc.cuh: in2)
+        if (!rc) rc = make_layer(h->c2[i], w->conv2_w[i], w->bn2[i], nullptr, w->bn_eps, h->has_sc[i] ? &h->sc[i] : nullptr, &scW, &scB);
         maxf = std::max(maxf, (size_t)Co * Ho * Wo);
         C = Co; Hc = Ho; Wc = Wo;
     }
@@ -486,7 +508,7 @@ extern "C" int sdfnmpc_encoder_destroy(sdfnmpc_encoder_t h) {
     if (!h) return 0;
     Layer* ls[] = {&h->conv0, &h->c1[0], &h->c1[1], &h->c1[2], &h->c1[3], &h->c2[0], &h->c2[1], &h->c2[2], &h->c2[3],
                    &h->sc[0], &h->sc[1], &h->sc[2], &h->sc[3]};
-    for (Layer* l : ls) { cudaFree(l->w); cudaFree(l->b); cudaFree(l->wblob_tc); cudaFree(l->ktab); }
+    for (Layer* l : ls) { cudaFree(l->w); cudaFree(l->b); cudaFree(l->wblob_tc); cudaFree(l->ktab); cudaFree(l->b_fused); }
     cudaFree(h->mean_w); cudaFree(h->mean_b); cudaFree(h->yz);
     for (float* b : h->buf) cudaFree(b);
     cudaFree(h->h_img); cudaFree(h->h_lat); cudaFree(h->part);
@@ -520,7 +542,7 @@ static int conv_ksplit(const Layer& L, int B, int sm_count) {
 }
 
 static int launch_conv_tc(const Layer& L, int B, const float* in, const float* resid, int act, float* out, cudaStream_t st,
-                          float* part = nullptr, size_t part_floats = 0) {
+                          float* part = nullptr, size_t part_floats = 0, const float* in2 = nullptr) {
     static int sm_count = 0;
     static bool attr_set = false;
     if (!sm_count) {
@@ -541,6 +563,12 @@ static int launch_conv_tc(const Layer& L, int B, const float* in, const float* r
     P.npix = (long long)B * L.s.Hout * L.s.Wout;
     P.NT = L.NT; P.n_ntiles = L.n_ntiles; P.n_kchunks = L.n_kchunks;
     P.in = in; P.wblob = L.wblob_tc; P.ktab = L.ktab; P.bias = L.b; P.resid = resid; P.act = act; P.out = out;
+    P.in2 = nullptr; P.C2 = P.H2 = P.W2 = P.s2 = 0; P.kc2 = L.n_kchunks;
+    if (L.b_fused) {                 // fused shortcut: the caller passes the block input instead of a residual tensor
+        if (!in2 || resid) return SDFNMPC_E_INVALID;
+        P.in2 = in2; P.C2 = L.C2; P.H2 = L.H2; P.W2 = L.W2; P.s2 = L.s2; P.bias = L.b_fused;
+        P.kc2 = L.s.Cin * L.ks * L.ks / TC_KC;
+    }
     P.ksplit = part ? conv_ksplit(L, B, sm_count) : 1;
     if ((size_t)P.ksplit * P.npix * P.Cout > part_floats) P.ksplit = 1;
     P.part = P.ksplit > 1 ? part : nullptr;
@@ -574,7 +602,7 @@ static int launch_conv_tc(const Layer& L, int B, const float* in, const float* r
     if (P.ksplit > 1) {
         const long long total = P.npix * P.Cout;
         const int cr = L.s.shuffle ? P.Cout / 4 : P.Cout, ohw = L.s.shuffle ? 4 * P.Hout * P.Wout : P.Hout * P.Wout;
-        conv_splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(part, P.ksplit, total, cr, ohw, L.b, resid, act, out);
+        conv_splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(part, P.ksplit, total, cr, ohw, P.bias, resid, act, out);
         count_launch();
         SDF_CUDA_CHECK(cudaGetLastError());
     }
@@ -626,7 +654,12 @@ extern "C" int sdfnmpc_encoder_encode(sdfnmpc_encoder_t h, const float* imgs, in
     for (int i = 0; i < 4; ++i) {
         if ((rc = launch_conv<3, false>(h->c1[i], B, x, nullptr, ENC_ACT_RELU, t1, st, nullptr, 1.f, 0, 0, h->part, h->part_floats))) return rc;
         const float* resid = x;
-        if (h->has_sc[i]) {
+        if (h->has_sc[i] && h->c2[i].b_fused && enc_use_tc()) {
+            // tensor-core path: the 1x1 stride-2 shortcut of the block input rides in conv2's K range (no shortcut launch, no
+            // residual tensor); the block input is an operand, so the result goes to the third buffer
+            if ((rc = launch_conv_tc(h->c2[i], B, t1, nullptr, ENC_ACT_RELU, t2, st, h->part, h->part_floats, x))) return rc;
+            float* tmp = x; x = t2; t2 = tmp;
+        } else if (h->has_sc[i]) {
             if ((rc = launch_conv<1, false>(h->sc[i], B, x, nullptr, ENC_ACT_NONE, t2, st, nullptr, 1.f, 0, 0, h->part, h->part_floats))) return rc;
             resid = t2;
             // conv2 writes over the (now dead) block input
