@@ -49,7 +49,8 @@ struct ConvTcParams {
     int n_ntiles, n_kchunks;
     const float* in;              // [B][Cin][Hin][Win]
     const unsigned char* wblob;   // [n_ntiles][n_kchunks][NT / NS sub-chunks][hi: NS x 128 B swizzled | lo], NS = min(NT, 128)
-    const int4* ktab;             // [n_kchunks * 32]: {(ci*Hin + ky)*Win + kx, ky, kx, source: 0 none (k >= K), 1 `in`, 2 `in2`}
+    const int* ktab;              // [n_kchunks * 32] packed im2col entries: bits 0-23 element offset (ci*Hin + ky)*Win + kx, 24-26 ky,
+                                  // 27-29 kx, 30-31 source (0 none: k >= K, 1 `in`, 2 `in2`); four entries per 16-byte broadcast load
     // Second source (the ResBlock shortcut fused into the block's last convolution, resnet.py:40-54): k entries with source 2
     // read in2[b][ci][s2 * oy][s2 * ox] (offset ci * H2 * W2, always inside the image), i.e. the 1x1 stride-s2 convolution of
     // the block input accumulates into the same tile; its folded-BatchNorm shift is part of `bias`.
@@ -133,25 +134,28 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
             const float* inb = P.in + (size_t)pb * P.Cin * P.Hin * P.Win + (long long)iy0 * P.Win + ix0;
             for (int kc = kc0; kc < kc1; ++kc, ++chunk) {
                 if ((int)(chunk & 1) != g) continue;
-                const int4* kt = P.ktab + kc * TC_KC + ch * 16;
+                const int4* kt = reinterpret_cast<const int4*>(P.ktab + kc * TC_KC + ch * 16);
+                int tk[16];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {                            // same entries for the whole warp: broadcast loads
+                    const int4 a = __ldg(kt + q);
+                    tk[4 * q] = a.x; tk[4 * q + 1] = a.y; tk[4 * q + 2] = a.z; tk[4 * q + 3] = a.w;
+                }
                 float v[16];
                 if (kc < P.kc2) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const int4 t = __ldg(kt + i);                    // same entry for the whole warp: one broadcast load
-                        const int iy = iy0 + t.y, ix = ix0 + t.z;
-                        const bool ok = pvalid && t.w && iy >= 0 && iy < P.Hin && ix >= 0 && ix < P.Win;
-                        v[i] = ok ? __ldg(inb + t.x) : 0.f;
+                        const int t = tk[i];
+                        const int iy = iy0 + ((t >> 24) & 7), ix = ix0 + ((t >> 27) & 7);
+                        const bool ok = pvalid && (t >> 30) && iy >= 0 && iy < P.Hin && ix >= 0 && ix < P.Win;
+                        v[i] = ok ? __ldg(inb + (t & 0xFFFFFF)) : 0.f;
                     }
                 } else {
                     // chunks of the second source (a whole chunk is one or the other: kc2 * 32 = Cin k^2): the loop above stays
                     // as it was - a per-element source select cost it the 16 loads in flight (18 % of the layer time, measured)
                     const float* inb2 = P.in2 + (size_t)pb * P.C2 * P.H2 * P.W2 + (long long)(oy * P.s2) * P.W2 + ox * P.s2;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int4 t = __ldg(kt + i);
-                        v[i] = (pvalid && t.w) ? __ldg(inb2 + t.x) : 0.f;
-                    }
+                    for (int i = 0; i < 16; ++i) v[i] = (pvalid && (tk[i] >> 30)) ? __ldg(inb2 + (tk[i] & 0xFFFFFF)) : 0.f;
                 }
                 float vhi[16], vlo[16];
                 split_a16(v, vhi, vlo);

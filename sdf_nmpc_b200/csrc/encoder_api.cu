@@ -316,7 +316,7 @@ struct Layer {
     float *w = nullptr, *b = nullptr;
     // tensor-core form (conv_tc.cuh): weight chunks [n tile][k chunk][hi | lo] in the swizzled UMMA layout + im2col table
     unsigned char* wblob_tc = nullptr;
-    int4* ktab = nullptr;
+    int* ktab = nullptr;             // packed im2col entries (ConvTcParams::ktab)
     int NT = 0, n_ntiles = 0, n_kchunks = 0;
     // tensor-core form only: the block's 1x1 stride-s2 shortcut appended to K (ConvTcParams::in2), bias = both folded shifts
     float* b_fused = nullptr;
@@ -421,19 +421,22 @@ static int make_layer(Layer& L, const float* w, const float* const bn[4], const 
     float* dblob = nullptr;
     if (int rc = upload(&dblob, blob)) return rc;
     L.wblob_tc = reinterpret_cast<unsigned char*>(dblob);
-    std::vector<int4> kt((size_t)nk * TC_KC);
+    // packed im2col table: 24 bits of element offset (a layer whose input does not fit stays on the CUDA-core kernel)
+    if ((size_t)L.s.Cin * L.s.Hin * L.s.Win >= (1u << 24) || (size_t)K2 * L.H2 * L.W2 >= (1u << 24) || L.ks > 7) {
+        cudaFree(dblob); L.wblob_tc = nullptr; cudaFree(L.b_fused); L.b_fused = nullptr;
+        return 0;
+    }
+    std::vector<int> kt((size_t)nk * TC_KC, 0);
     for (int k = 0; k < nk * TC_KC; ++k) {
-        int4 t = make_int4(0, 0, 0, 0);
         if (k < K) {
             const int ci = k / (L.ks * L.ks), rem = k % (L.ks * L.ks), ky = rem / L.ks, kx = rem % L.ks;
-            t = make_int4((ci * L.s.Hin + ky) * L.s.Win + kx, ky, kx, 1);
+            kt[k] = ((ci * L.s.Hin + ky) * L.s.Win + kx) | (ky << 24) | (kx << 27) | (1 << 30);
         } else if (k < KT) {
-            t = make_int4((k - K) * L.H2 * L.W2, 0, 0, 2);
+            kt[k] = ((k - K) * L.H2 * L.W2) | (int)(2u << 30);
         }
-        kt[k] = t;
     }
-    SDF_CUDA_CHECK(cudaMalloc(&L.ktab, kt.size() * sizeof(int4)));
-    SDF_CUDA_CHECK(cudaMemcpy(L.ktab, kt.data(), kt.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    SDF_CUDA_CHECK(cudaMalloc(&L.ktab, kt.size() * sizeof(int)));
+    SDF_CUDA_CHECK(cudaMemcpy(L.ktab, kt.data(), kt.size() * sizeof(int), cudaMemcpyHostToDevice));
     return 0;
 }
 
