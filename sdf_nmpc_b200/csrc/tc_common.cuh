@@ -152,9 +152,28 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
 
 // The tf32 hi / lo split is done by split_a16 BEFORE the producer waits for its stage to be free, so that only the
 // eight 16-byte stores remain between "stage free" and "stage full".
+// TC_SPLIT_MODE: 0 = hi and lo rounded to nearest (two cvt.rna.tf32 per element: 16 % of the SDF kernel's instructions, on a
+// throttled pipe - the top line of the r2g source-level profile); 1 = hi by truncation (one LOP3; x - hi stays exact), lo
+// rounded; 2 (default) = hi by truncation, lo left as the fp32 difference - the tensor core ignores the low 13 mantissa bits
+// of a tf32 operand, so no cvt is needed at all.  Representation error |x - hi - lo_tf32| <= 2^-20 |x| instead of 2^-22.
+// Measured (profiles/r2m_split_ab.txt; modes 0 / 1 / 2): SDF 256.6 / 262.7 / 265.9 Mpts/s with value error 1.62 / 1.66 /
+// 1.76e-6 and gradient error 6.0 / 6.6 / 6.9e-6 against the float64 oracle (tolerances 1e-5 / 1e-4); encoder 32.1 / 32.6 /
+// 32.8 k frames/s with latent error 1.5 / 1.7 / 2.0e-6 (tolerance 1e-4).  Weights are pre-split on the host with rounding.
+#ifndef TC_SPLIT_MODE
+#define TC_SPLIT_MODE 2
+#endif
+__device__ __forceinline__ void split1(float x, float& hi, float& lo) {
+#if TC_SPLIT_MODE == 0
+    hi = tf32_rna(x); lo = tf32_rna(x - hi);
+#elif TC_SPLIT_MODE == 1
+    hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); lo = tf32_rna(x - hi);
+#else
+    hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); lo = x - hi;
+#endif
+}
 __device__ __forceinline__ void split_a16(const float* v, float* hi, float* lo) {
 #pragma unroll
-    for (int e = 0; e < 16; ++e) { hi[e] = tf32_rna(v[e]); lo[e] = tf32_rna(v[e] - hi[e]); }
+    for (int e = 0; e < 16; ++e) split1(v[e], hi[e], lo[e]);
 }
 __device__ __forceinline__ void store_a16(unsigned char* a_stage, int row, int ch, const float* hi, const float* lo) {
     unsigned char* base = a_stage + (row >> 3) * 1024 + (row & 7) * 128;
@@ -170,7 +189,7 @@ __device__ __forceinline__ void store_a16(unsigned char* a_stage, int row, int c
 // 8-feature variants (thread <-> row, quarter `cg` of the 32-feature chunk): two 16-byte units of hi and of lo
 __device__ __forceinline__ void split_a8(const float* v, float* hi, float* lo) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { hi[e] = tf32_rna(v[e]); lo[e] = tf32_rna(v[e] - hi[e]); }
+    for (int e = 0; e < 8; ++e) split1(v[e], hi[e], lo[e]);
 }
 __device__ __forceinline__ void store_a8(unsigned char* a_stage, int row, int cg, const float* hi, const float* lo) {
     unsigned char* base = a_stage + (row >> 3) * 1024 + (row & 7) * 128;
