@@ -260,7 +260,11 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
                     const uint64_t ad_hi = make_desc(a_hi), ad_lo = make_desc(a_hi + TC_ASTAGE_BYTES / 2);
                     for (int h = 0; h < nsub; ++h, ++jj) {
                         const uint32_t q = (uint32_t)(jj % CV_WSTAGES);
+#if defined(SDFNMPC_TRACE_BUILD)
                         const bool tr = P.trace && blockIdx.x == 0 && jj < 512 && leader;
+#else
+                        constexpr bool tr = false;
+#endif
                         if (tr) P.trace[jj * 4 + 0] = clock64();
                         mbar_wait(wfull0 + 8 * q, (uint32_t)((jj / CV_WSTAGES) & 1));
                         if (tr) P.trace[jj * 4 + 1] = clock64();

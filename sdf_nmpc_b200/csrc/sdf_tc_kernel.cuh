@@ -239,7 +239,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
             const float* b3 = P.b3f + (size_t)inst * net.H3;
             const uint32_t dpar = tile_it & 1;                  // every dfull[q] completes exactly once per tile
             float d_acc = 0.f;
+            // clock64 trace of CTA 0's second tile: compiled in only with -DSDFNMPC_TRACE_BUILD (the three tests per chunk
+            // were 4 % of the kernel's instructions in the r2g source-level profile)
+#if defined(SDFNMPC_TRACE_BUILD)
             const bool tr = P.trace && blockIdx.x == 0 && tile == (int)gridDim.x && tid == 0;
+#else
+            constexpr bool tr = false;
+#endif
             for (int oi = 0; oi < n_ops; ++oi, ++chunk) {
                 if (oi < pre_done) continue;                       // already built during the previous tile's epilogue
                 const SdfTcOp op = ops_s[oi];
@@ -399,7 +405,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
         // descriptors live in uniform registers; one elected lane executes the MMA / commit instructions.
         const uint32_t leader = elect_one();
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+#if defined(SDFNMPC_TRACE_BUILD)
             const bool tr = P.trace && blockIdx.x == 0 && tile == (int)gridDim.x;
+#else
+            constexpr bool tr = false;
+#endif
             for (int oi = 0; oi < n_ops; ++oi, ++chunk) {
                 const SdfTcOp& op = P.opsv[oi];
                 const uint32_t s = chunk & 1;
