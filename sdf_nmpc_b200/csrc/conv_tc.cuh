@@ -49,8 +49,12 @@ struct ConvTcParams {
     int n_ntiles, n_kchunks;
     const float* in;              // [B][Cin][Hin][Win]
     const unsigned char* wblob;   // [n_ntiles][n_kchunks][NT / NS sub-chunks][hi: NS x 128 B swizzled | lo], NS = min(NT, 128)
-    const int* ktab;              // [n_kchunks * 32] packed im2col entries: bits 0-23 element offset (ci*Hin + ky)*Win + kx, 24-26 ky,
-                                  // 27-29 kx, 30-31 source (0 none: k >= K, 1 `in`, 2 `in2`); four entries per 16-byte broadcast load
+    const int* ktab;              // [n_kchunks * 32] packed im2col entries: bits 0-23 element offset (ci*Hin + ky)*Win + kx, bits 24-28
+                                  // the tap ky * ks + kx (second source: 0; k >= K: 31, never valid); four entries per 16-byte
+                                  // broadcast load.  Whether a tap falls inside the image does not depend on the channel, so a
+                                  // thread forms one validity bit per tap when it starts a tile and the gather tests that bit
+                                  // (the four compares per element had been half of the kernel's instructions, r2n profile)
+    int ks;                       // kernel size (ks * ks <= 30)
     // Second source (the ResBlock shortcut fused into the block's last convolution, resnet.py:40-54): k entries with source 2
     // read in2[b][ci][s2 * oy][s2 * ox] (offset ci * H2 * W2, always inside the image), i.e. the 1x1 stride-s2 convolution of
     // the block input accumulates into the same tile; its folded-BatchNorm shift is part of `bias`.
@@ -132,6 +136,11 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
             }
             const int iy0 = oy * P.stride - P.pad, ix0 = ox * P.stride - P.pad;
             const float* inb = P.in + (size_t)pb * P.Cin * P.Hin * P.Win + (long long)iy0 * P.Win + ix0;
+            uint32_t vmask = 0;                                          // bit tap: the tap's input pixel exists
+            if (pvalid)
+                for (int ky = 0, tp = 0; ky < P.ks; ++ky)
+                    for (int kx = 0; kx < P.ks; ++kx, ++tp)
+                        if (iy0 + ky >= 0 && iy0 + ky < P.Hin && ix0 + kx >= 0 && ix0 + kx < P.Win) vmask |= 1u << tp;
             for (int kc = kc0; kc < kc1; ++kc, ++chunk) {
                 if ((int)(chunk & 1) != g) continue;
                 const int4* kt = reinterpret_cast<const int4*>(P.ktab + kc * TC_KC + ch * 16);
@@ -146,16 +155,14 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const int t = tk[i];
-                        const int iy = iy0 + ((t >> 24) & 7), ix = ix0 + ((t >> 27) & 7);
-                        const bool ok = pvalid && (t >> 30) && iy >= 0 && iy < P.Hin && ix >= 0 && ix < P.Win;
-                        v[i] = ok ? __ldg(inb + (t & 0xFFFFFF)) : 0.f;
+                        v[i] = ((vmask >> ((t >> 24) & 31)) & 1u) ? __ldg(inb + (t & 0xFFFFFF)) : 0.f;
                     }
                 } else {
                     // chunks of the second source (a whole chunk is one or the other: kc2 * 32 = Cin k^2): the loop above stays
                     // as it was - a per-element source select cost it the 16 loads in flight (18 % of the layer time, measured)
                     const float* inb2 = P.in2 + (size_t)pb * P.C2 * P.H2 * P.W2 + (long long)(oy * P.s2) * P.W2 + ox * P.s2;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = (pvalid && (tk[i] >> 30)) ? __ldg(inb2 + (tk[i] & 0xFFFFFF)) : 0.f;
+                    for (int i = 0; i < 16; ++i) v[i] = (pvalid && ((tk[i] >> 24) & 31) == 0) ? __ldg(inb2 + (tk[i] & 0xFFFFFF)) : 0.f;
                 }
                 float vhi[16], vlo[16];
                 split_a16(v, vhi, vlo);

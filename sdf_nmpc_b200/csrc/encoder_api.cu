@@ -439,17 +439,17 @@ static int make_layer(Layer& L, const float* w, const float* const bn[4], const 
     if (int rc = upload(&dblob, blob)) return rc;
     L.wblob_tc = reinterpret_cast<unsigned char*>(dblob);
     // packed im2col table: 24 bits of element offset (a layer whose input does not fit stays on the CUDA-core kernel)
-    if ((size_t)L.s.Cin * L.s.Hin * L.s.Win >= (1u << 24) || (size_t)K2 * L.H2 * L.W2 >= (1u << 24) || L.ks > 7) {
+    if ((size_t)L.s.Cin * L.s.Hin * L.s.Win >= (1u << 24) || (size_t)K2 * L.H2 * L.W2 >= (1u << 24) || L.ks * L.ks > 30) {
         cudaFree(dblob); L.wblob_tc = nullptr; cudaFree(L.b_fused); L.b_fused = nullptr;
         return 0;
     }
-    std::vector<int> kt((size_t)nk * TC_KC, 0);
+    std::vector<int> kt((size_t)nk * TC_KC, 31 << 24);            // tap 31: never valid (k >= K)
     for (int k = 0; k < nk * TC_KC; ++k) {
         if (k < K) {
             const int ci = k / (L.ks * L.ks), rem = k % (L.ks * L.ks), ky = rem / L.ks, kx = rem % L.ks;
-            kt[k] = ((ci * L.s.Hin + ky) * L.s.Win + kx) | (ky << 24) | (kx << 27) | (1 << 30);
+            kt[k] = ((ci * L.s.Hin + ky) * L.s.Win + kx) | (rem << 24);
         } else if (k < KT) {
-            kt[k] = ((k - K) * L.H2 * L.W2) | (int)(2u << 30);
+            kt[k] = (k - K) * L.H2 * L.W2;                        // second source: tap 0
         }
     }
     SDF_CUDA_CHECK(cudaMalloc(&L.ktab, kt.size() * sizeof(int)));
@@ -579,7 +579,7 @@ static int launch_conv_tc(const Layer& L, int B, const float* in, const float* r
     }
     ConvTcParams P;
     P.Cin = L.s.Cin; P.Hin = L.s.Hin; P.Win = L.s.Win; P.Cout = L.s.Cout; P.Hout = L.s.Hout; P.Wout = L.s.Wout;
-    P.stride = L.s.stride; P.pad = L.s.pad;
+    P.stride = L.s.stride; P.pad = L.s.pad; P.ks = L.ks;
     P.npix = (long long)B * L.s.Hout * L.s.Wout;
     P.NT = L.NT; P.n_ntiles = L.n_ntiles; P.n_kchunks = L.n_kchunks;
     P.in = in; P.wblob = L.wblob_tc; P.ktab = L.ktab; P.bias = L.b; P.resid = resid; P.act = act; P.out = out;
