@@ -33,6 +33,7 @@ struct sdfnmpc_sdf {
     float* tc_scratch = nullptr;
     size_t tc_scratch_per_cta = 0;
     int tc_sc_off[4] = {0, 0, 0, 0};
+    int tc_sc_off_emb = 0;
     int tc_min_points = 1;           // below this the CUDA-core kernel is used.  A mostly padded 128-point tile still takes 82 us
                                      // against 225 us of the CUDA-core kernel for the 21 query points of one instance (measured)
     // scratch for the host-convenience entry points

@@ -95,12 +95,14 @@ int build_tc(sdfnmpc_sdf* h, const float* W1, const float* W2, const float* W3, 
     };
     const int c1 = n.Ep / 32, cH1 = n.H1 / 32, cH2 = n.H2 / 32, cH3 = n.H3 / 32, cH4 = n.H4 / 32;
     // forward
-    for (int j = 0; j < c1; ++j) add(TC_PROD_EMBED, 0, 32 * j, 0, 0, oW1[j], n.H1, 0, j == 0, j == c1 - 1);
+    // (layer field of an embedding chunk: 1 = first evaluation of the tile - values and cosines go to the cache -, 3 = the skip
+    // connection's second use - read back)
+    for (int j = 0; j < c1; ++j) add(TC_PROD_EMBED, 0, 32 * j, 1, 0, oW1[j], n.H1, 0, j == 0, j == c1 - 1);
     for (int j = 0; j < cH1; ++j) add(TC_PROD_ACT, 0 + 32 * j, 32 * j, 1, j == 0, oW2[j], n.H2, 256, j == 0, j == cH1 - 1);
     // layer 3 input [h2; e]: the skip-connection (embedding) chunks go FIRST - they do not read TMEM, so the producers build
     // them while the last MMAs of layer 2 drain, instead of idling at the layer boundary
     if (n.res_state)
-        for (int j = 0; j < c1; ++j) add(TC_PROD_EMBED, 0, 32 * j, 0, 0, oW3e[j], n.H3, 0, j == 0, 0);
+        for (int j = 0; j < c1; ++j) add(TC_PROD_EMBED, 0, 32 * j, 3, 0, oW3e[j], n.H3, 0, j == 0, 0);
     for (int j = 0; j < cH2; ++j) add(TC_PROD_ACT, 256 + 32 * j, 32 * j, 2, j == 0, oW3h[j], n.H3, 0, (!n.res_state) && j == 0, j == cH2 - 1);
     for (int j = 0; j < cH3; ++j) add(TC_PROD_ACT, 0 + 32 * j, 32 * j, 3, j == 0, oW4[j], n.H4, 128, j == 0, j == cH3 - 1);
     // reverse
@@ -144,7 +146,8 @@ int build_tc(sdfnmpc_sdf* h, const float* W1, const float* W2, const float* W3, 
     h->tc_sc_off[1] = h->tc_sc_off[0] + n.H1 * TC_TM;
     h->tc_sc_off[2] = h->tc_sc_off[1] + n.H2 * TC_TM;
     h->tc_sc_off[3] = h->tc_sc_off[2] + n.H3 * TC_TM;
-    h->tc_scratch_per_cta = (size_t)h->tc_sc_off[3] + (size_t)n.Ep * TC_TM;
+    h->tc_sc_off_emb = h->tc_sc_off[3] + n.Ep * TC_TM;                      // embedding cache: [tile parity][value | cos][Ep][128]
+    h->tc_scratch_per_cta = (size_t)h->tc_sc_off_emb + (size_t)4 * n.Ep * TC_TM;
     SDF_CUDA_CHECK(cudaMalloc(&h->tc_scratch, h->tc_scratch_per_cta * sizeof(float) * h->sm_count));
     SDF_CUDA_CHECK(cudaFuncSetAttribute(sdf_eval_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     const char* env = getenv("SDFNMPC_SDF_IMPL");
@@ -294,6 +297,7 @@ extern "C" int sdfnmpc_sdf_eval(sdfnmpc_sdf_t h, const float* pts, const int32_t
         memcpy(P.opsv, h->tc_ops_host, (size_t)h->tc_n_ops * sizeof(SdfTcOp));
         P.scratch = h->tc_scratch; P.scratch_floats_per_cta = h->tc_scratch_per_cta;
         P.sc_off_c1 = h->tc_sc_off[0]; P.sc_off_c2 = h->tc_sc_off[1]; P.sc_off_c3 = h->tc_sc_off[2]; P.sc_off_ge3 = h->tc_sc_off[3];
+        P.sc_off_emb = h->tc_sc_off_emb;
         P.b1f = h->b1f; P.b3f = h->b3f; P.pts = pts; P.pt2inst = pt2inst; P.pts_per_inst = pts_per_inst; P.n = (int)n;
         P.sdf_out = sdf; P.grad_out = grad; P.n_acc = h->tc_n_acc;
         P.trace = nullptr;

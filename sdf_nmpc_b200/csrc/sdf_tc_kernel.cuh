@@ -69,6 +69,7 @@ struct SdfTcParams {
     float* scratch;                 // per CTA: c1 | c2 | c3 | ge3, each [(feat/4)][128][4]
     size_t scratch_floats_per_cta;
     int sc_off_c1, sc_off_c2, sc_off_c3, sc_off_ge3;    // float offsets inside the CTA's scratch
+    int sc_off_emb;                 // embedding cache [tile parity][value | cos][Ep / 4][128][4]
     const float* b1f;
     const float* b3f;
     const float* pts;
@@ -219,7 +220,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
             fence_async_smem();
             mbar_arrive(afull0 + 8 * s);
         };
-        auto embed8 = [&](int f8, float px, float py, float pz, float* v) {
+        // The embedding of a point is needed three times per tile - input of layer 1, skip connection into layer 3, and its
+        // cosines in the chain rule of the epilogue.  fast_sincos is ~30 instructions per feature with the argument and the
+        // select, which made the three evaluations 39 % of the producers' instructions; now the first one parks values and
+        // cosines in the CTA's L2 scratch (by tile parity: the next tile's leading chunks are built before this tile's epilogue)
+        // and the other two read them back.  -DTC_NO_EMB_CACHE restores the recomputation.
+        auto emb_slot = [&](uint32_t par, int what, int f8) {
+            return reinterpret_cast<float4*>(scr + P.sc_off_emb + (size_t)(par * 2 + what) * net.Ep * TC_TM + ((size_t)(f8 >> 2) * TC_TM + row) * 4);
+        };
+        auto embed8 = [&](int f8, float px, float py, float pz, float* v, int layer, uint32_t par) {
+#if !defined(TC_NO_EMB_CACHE)
+            if (layer == 3) {
+                const float4* src = emb_slot(par, 0, f8);
+                const float4 a = src[0], b = src[TC_TM];
+                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+                return;
+            }
+#endif
+            float cv[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int j = f8 + i;
@@ -228,7 +246,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
                 float sn, cs;
                 fast_sincos(arg, sn, cs);
                 v[i] = j < 3 ? (j == 0 ? px : (j == 1 ? py : pz)) : (j < net.E ? sn : 0.f);
+                cv[i] = cs;
             }
+#if !defined(TC_NO_EMB_CACHE)
+            float4* dv = emb_slot(par, 0, f8);
+            float4* dc = emb_slot(par, 1, f8);
+            dv[0] = make_float4(v[0], v[1], v[2], v[3]); dv[TC_TM] = make_float4(v[4], v[5], v[6], v[7]);
+            dc[0] = make_float4(cv[0], cv[1], cv[2], cv[3]); dc[TC_TM] = make_float4(cv[4], cv[5], cv[6], cv[7]);
+#endif
         };
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
             const int gi = tile * TC_TM + row;
@@ -265,7 +290,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
                 }
                 float v[8];
                 if (op.prod == TC_PROD_EMBED) {
-                    embed8(f8, sx, sy, sz, v);
+                    embed8(f8, sx, sy, sz, v, op.layer, tile_it & 1);
                 } else {
                     if (op.prod == TC_PROD_ACT) {
                         const float* bias = (op.layer == 1 ? b1 : (op.layer == 2 ? net.b2 : b3)) + f8;
@@ -316,7 +341,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
                 nx = __ldg(P.pts + (size_t)nic * 3); ny = __ldg(P.pts + (size_t)nic * 3 + 1); nz = __ldg(P.pts + (size_t)nic * 3 + 2);
                 for (int q = 0; q < n_pre; ++q) {
                     float v[8];
-                    embed8(ops_s[q].feat0 + cg * 8, nx, ny, nz, v);
+                    embed8(ops_s[q].feat0 + cg * 8, nx, ny, nz, v, 1, (tile_it + 1) & 1);
                     publish(chunk + q, v);
                 }
                 pre_done = n_pre;
@@ -337,13 +362,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
                         v[q * 4] += c.x; v[q * 4 + 1] += c.y; v[q * 4 + 2] += c.z; v[q * 4 + 3] += c.w;
                     }
                 }
+#if !defined(TC_NO_EMB_CACHE)
+                float cv[8];
+                {
+                    const float4* src = emb_slot(tile_it & 1, 1, f8);
+                    const float4 a = src[0], b = src[TC_TM];
+                    cv[0] = a.x; cv[1] = a.y; cv[2] = a.z; cv[3] = a.w; cv[4] = b.x; cv[5] = b.y; cv[6] = b.z; cv[7] = b.w;
+                }
+#endif
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int j = f8 + i;
                     const float4 t = etab[j];
+#if !defined(TC_NO_EMB_CACHE)
+                    const float cs = cv[i];
+#else
                     const float arg = fmaf(sz, t.z, fmaf(sy, t.y, sx * t.x)) + t.w;
                     float sn, cs;
                     fast_sincos(arg, sn, cs);
+#endif
                     const float w = (j >= 3 && j < net.E) ? v[i] * cs : 0.f;        // d/darg sin(arg) = cos(arg)
                     gx = fmaf(w, t.x, gx); gy = fmaf(w, t.y, gy); gz = fmaf(w, t.z, gz);
                     if (j == 0) gx += v[i];
@@ -355,7 +392,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sdf_eval_tc_kernel(const SdfTcP
             if (has_next) {
                 for (int q = n_pre; q < n_pre2; ++q) {
                     float v[8];
-                    embed8(ops_s[q].feat0 + cg * 8, nx, ny, nz, v);
+                    embed8(ops_s[q].feat0 + cg * 8, nx, ny, nz, v, 1, (tile_it + 1) & 1);
                     publish(chunk + q, v);
                 }
                 pre_done = n_pre2;
