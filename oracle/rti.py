@@ -58,6 +58,64 @@ def slack_weights(cfg):
             np.array([cfg['slack_fov'][1], cfg['slack_fov'][1], cfg['slack_df'][1]]))
 
 
+def poly3(v, deg, coeffs):
+    """3-variate polynomial of ``utils/math.py:294-321`` (terms ordered by total degree, then a, then b; c = td - a - b):
+    value [B] and gradient [B,3]."""
+    val = np.zeros(v.shape[0]); grad = np.zeros((v.shape[0], 3))
+    i = 0
+    for td in range(deg + 1):
+        for a in range(td + 1):
+            for b in range(td + 1 - a):
+                c = td - a - b
+                val += coeffs[i] * v[:, 0] ** a * v[:, 1] ** b * v[:, 2] ** c
+                if a: grad[:, 0] += coeffs[i] * a * v[:, 0] ** (a - 1) * v[:, 1] ** b * v[:, 2] ** c
+                if b: grad[:, 1] += coeffs[i] * b * v[:, 0] ** a * v[:, 1] ** (b - 1) * v[:, 2] ** c
+                if c: grad[:, 2] += coeffs[i] * c * v[:, 0] ** a * v[:, 1] ** b * v[:, 2] ** (c - 1)
+                i += 1
+    assert i == len(coeffs)
+    return val, grad
+
+
+def term_rows(net, xN, prob, cfg):
+    """Terminal rows of ``flags.recursive_feasibility`` / ``flags.stability`` (``gen_model.py:73-118``; 'att' state layout
+    [p, q, v]) at the terminal node: values h [B,m], gradients wrt x [B,m,nx], bounds, soft mask and slack weights.  Row order:
+    rec_feas = sdf_flag(p) - flag * poly(v) in [size.xy, max_df] (soft with ``weights.slack_brake``, hard when that is None);
+    hfov / vfov (hard) at the braking end point p + flag * poly(v) v / sqrt(v.v + 1e-4) (``gen_model.py:105-111``);
+    with stability the velocity box |v_i| <= limits.v_i (hard, ``cost_const_helpers.py:93-102``)."""
+    t = cfg['term']
+    B, nx = xN.shape
+    flag = prob['flag']
+    v = xN[:, 7:10]
+    pv, gpv = poly3(v, t['degree'], t['coeffs'])
+    hh, Jp = eval_h(net, xN, prob, cfg)                  # sdf_flag value and d/dp (row 2)
+    rows_h, rows_C, lo, hi, soft, z, Z = [], [], [], [], [], [], []
+    C = np.zeros((B, nx)); C[:, 0:3] = Jp[:, 2]; C[:, 7:10] = -flag[:, None] * gpv
+    rows_h.append(hh[:, 2] - flag * pv); rows_C.append(C)
+    lo.append(cfg['size_xy']); hi.append(net['max_df'])
+    sb = t.get('slack_brake')
+    soft.append(sb is not None); z.append(sb[0] if sb else 0.0); Z.append(sb[1] if sb else 0.0)
+    # braking end point and its derivative
+    n = np.sqrt((v * v).sum(1) + 1e-4)
+    dirv = v / n[:, None]
+    d = flag * pv
+    xE = xN.copy(); xE[:, 0:3] = xN[:, 0:3] + d[:, None] * dirv
+    dE_dv = d[:, None, None] * (np.eye(3)[None] / n[:, None, None] - np.einsum('bi,bj->bij', v, v) / (n ** 3)[:, None, None]) \
+        + np.einsum('bi,bj->bij', dirv, flag[:, None] * gpv)
+    hf, JE = M.h_fov(xE, prob['W_p_Co'], prob['W_R_Co'], flag, cfg)        # d/dp_E [B,2,3]
+    hl, vl = cfg['hfov'] * cfg['fov_ratio'], cfg['vfov'] * cfg['fov_ratio']
+    for r, lim in ((0, hl), (1, vl)):
+        if r == 1 and not t.get('vfov', True):
+            continue
+        C = np.zeros((B, nx)); C[:, 0:3] = JE[:, r]; C[:, 7:10] = np.einsum('bp,bpv->bv', JE[:, r], dE_dv)
+        rows_h.append(hf[:, r]); rows_C.append(C); lo.append(-lim); hi.append(lim); soft.append(False); z.append(0.0); Z.append(0.0)
+    if t.get('stability', False):
+        for i in range(3):
+            C = np.zeros((B, nx)); C[:, 7 + i] = 1.0
+            rows_h.append(v[:, i].copy()); rows_C.append(C); lo.append(-t['vlim'][i]); hi.append(t['vlim'][i])
+            soft.append(False); z.append(0.0); Z.append(0.0)
+    return (np.stack(rows_h, 1), np.stack(rows_C, 1), np.array(lo), np.array(hi), np.array(soft, bool), np.array(z), np.array(Z))
+
+
 def init_traj(x0, cfg):
     """ocp.py:144-149: x_k = x0, u_k = u_hover."""
     B, N = x0.shape[0], cfg['N']
@@ -104,13 +162,24 @@ def linearize(net, xb, ub, prob, cfg):
             g[:, k, 4:7] += dt[k] * cfg['sdf_cost_w'] * rr[:, None] * Jr
     yN, JN = mdl.y_fun(xb[:, N], np.zeros((B, 4)), prob['qd'][:, N], cfg)
     yN, JN = yN[:, :nyN], JN[:, :nyN, 4:]
+    term = cfg.get('term')
+    if term and term.get('stability', False):
+        # quad_rollpitchyawrate.py:52-55: yN = flag * [p, q_e3]; gen_model.py:139-147: extra terminal output flag * v.v
+        f = prob['flag']
+        v = xb[:, N, 7:10]
+        Jv = np.zeros((B, 1, nx)); Jv[:, 0, 7:10] = 2.0 * f[:, None] * v
+        yN = np.concatenate([f[:, None] * yN, (f * (v * v).sum(1))[:, None]], 1)
+        JN = np.concatenate([f[:, None, None] * JN, Jv], 1)
     HN = np.einsum('byi,by,byj->bij', JN, prob['WN'], JN) + cfg['lm'] * np.eye(nx)[None]
     gN = np.einsum('byi,by->bi', JN, prob['WN'] * (yN - prob['yrefN']))
     k0 = 0 if cfg['h_at_node0'] else 1
     for k in range(k0, N + 1):
         hbar[:, k], Jp = eval_h(net, xb[:, k], prob, cfg)
         C[:, k, :, 0:3] = Jp
-    return dict(A=A, B=Bm, b=b, H=H, g=g, HN=HN, gN=gN, C=C, hbar=hbar, k0=k0)
+    out = dict(A=A, B=Bm, b=b, H=H, g=g, HN=HN, gN=gN, C=C, hbar=hbar, k0=k0)
+    if term:
+        out['term'] = term_rows(net, xb[:, N], prob, cfg)
+    return out
 
 
 def condense(lin, xb, ub, prob, cfg, max_df):
@@ -149,17 +218,27 @@ def condense(lin, xb, ub, prob, cfg, max_df):
     hb = lin['hbar'][:, k0:].reshape(B, nk * 3)
     # rows the mission flags switch off (gen_model.py:41,67-70) are REMOVED here: cfg['h_off'] = bool[3] in h order
     keep = np.tile(~np.asarray(cfg.get('h_off', [False] * 3), bool), nk)
+    if cfg.get('term'):
+        keep[-1] = False        # gen_model.py:69-70: no terminal sdf row next to the recursive-feasibility row
     CG, Cg, hb = CG[:, keep], Cg[:, keep], hb[:, keep]
     nh = int(keep.sum())
     rows_G += [CG, -CG]
     rows_d += [np.tile(lh, nk)[keep][None] - hb - Cg, -(np.tile(uh, nk)[keep][None] - hb - Cg)]
-    G = np.concatenate(rows_G, 1); d = np.concatenate(rows_d, 1)
     soft = np.concatenate([np.zeros(2 * nv, bool), np.ones(2 * nh, bool)])
     # slack penalties of stage rows (nodes k0..N-1) are scaled by Ts_k, terminal rows by 1
     sc = np.concatenate([np.repeat(cfg['dt'][k0:N], 3), np.ones(3)])
     zz = np.concatenate([np.zeros(2 * nv), (np.tile(zl, nk) * sc)[keep], (np.tile(zl, nk) * sc)[keep]])
     ZZ = np.concatenate([np.zeros(2 * nv), (np.tile(Zl, nk) * sc)[keep], (np.tile(Zl, nk) * sc)[keep]])
-    return dict(P=P, q=q, G=G, d=d, soft=soft, z=zz, Z=ZZ, Gam=Gam, gam=gam, nk=nk, keep=keep)
+    nt = 0
+    if cfg.get('term'):         # rows of term_rows: full-width gradients at node N, appended as [lower; upper]
+        hT, CT, loT, hiT, sfT, zT, ZT = lin['term']
+        nt = hT.shape[1]
+        TG = np.einsum('brx,bxn->brn', CT, Gam[:, N]); Tg = np.einsum('brx,bx->br', CT, gam[:, N])
+        rows_G += [TG, -TG]
+        rows_d += [loT[None] - hT - Tg, -(hiT[None] - hT - Tg)]
+        soft = np.concatenate([soft, sfT, sfT]); zz = np.concatenate([zz, zT, zT]); ZZ = np.concatenate([ZZ, ZT, ZT])
+    G = np.concatenate(rows_G, 1); d = np.concatenate(rows_d, 1)
+    return dict(P=P, q=q, G=G, d=d, soft=soft, z=zz, Z=ZZ, Gam=Gam, gam=gam, nk=nk, keep=keep, nt=nt)
 
 
 def rti_step(net, xb, ub, prob, cfg):
@@ -187,9 +266,14 @@ def rti_step(net, xb, ub, prob, cfg):
 
     out = dict(u0=un[:, 0].copy(), status=sol['status'], qp_iters=sol['iters'],
                lam_lbu=lam[:, :nv].reshape(B, N, 4), lam_ubu=lam[:, nv:2 * nv].reshape(B, N, 4),
-               lam_lh=full(lam[:, 2 * nv:2 * nv + nh]), lam_uh=full(lam[:, 2 * nv + nh:]),
-               slack_l=full(sol['s'][:, 2 * nv:2 * nv + nh]), slack_u=full(sol['s'][:, 2 * nv + nh:]),
+               lam_lh=full(lam[:, 2 * nv:2 * nv + nh]), lam_uh=full(lam[:, 2 * nv + nh:2 * nv + 2 * nh]),
+               slack_l=full(sol['s'][:, 2 * nv:2 * nv + nh]), slack_u=full(sol['s'][:, 2 * nv + nh:2 * nv + 2 * nh]),
                du=U.reshape(B, N, 4), dx=dx, lin=lin, qp=cq)
+    nt = cq['nt']
+    if nt:
+        o = 2 * nv + 2 * nh
+        out.update(lam_term_l=lam[:, o:o + nt], lam_term_u=lam[:, o + nt:o + 2 * nt],
+                   slack_term_l=sol['s'][:, o:o + nt], slack_term_u=sol['s'][:, o + nt:o + 2 * nt])
     return xn, un, out
 
 

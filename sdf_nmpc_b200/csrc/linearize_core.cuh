@@ -22,6 +22,11 @@ struct LinIn {           // device pointers, whole batch
     int nyN;             // terminal outputs: 4 (att, att_tau) or 7 (acc)
     const double* x0;    // [B][NX] measured state: node 0 is linearised THERE (ocp.py:161 `solver.set(0, 'x', x0)` precedes
                          // the RTI step, so dx_0 = 0); null = linearise node 0 at xbar_0 (the QP then carries dx_0 = x0 - xbar_0)
+    // Lifted terminal rows (term_lift.cuh): the OCP ends at node n_real < N, nodes n_real+1..N are auxiliary (their dynamics and
+    // rows are written by term_lift_instance after the SDF evaluation).  The caller's arrays yref / qd keep the OCP's horizon
+    // ([B][n_real][NY], [B][n_real+1][4]); xbar / ubar and every output are laid out for N.  -1: n_real = N.
+    int n_real = -1;
+    int stab = 0;        // flags.stability: terminal outputs flag * [p, q_e3] and flag * v.v (quad_rollpitchyawrate.py:52-55, gen_model.py:139-147)
 };
 
 struct LinOut {
@@ -67,6 +72,17 @@ template <int MODEL>
 SDF_HD void linearize_dir(const ModelConst& mc, int N, const LinIn& in, const LinOut& out, int b, int k, int dir) {
     using D_ = ModelDims<MODEL>;
     constexpr int NX = D_::NX, NU = D_::NU, NW = D_::NW, NY = D_::NY, NH = D_::NH;
+    const int NR = in.n_real >= 0 ? in.n_real : N;
+    const size_t node = (size_t)b * (N + 1) + k;
+    if (k > NR) {        // auxiliary node: no cost; a harmless SDF query point
+        double* J = out.J + node * NY * NW;
+        for (int r = 0; r < NY; ++r) J[r * NW + dir] = 0.0;
+        if (dir == 0) {
+            for (int r = 0; r < NY; ++r) out.yres[node * NY + r] = 0.0;
+            for (int c = 0; c < 3; ++c) out.qpts[node * 3 + c] = 0.f;
+        }
+        return;
+    }
     double* xb = in.xbar + ((size_t)b * (N + 1) + k) * NX;
     const double* x = (k == 0 && in.x0) ? in.x0 + (size_t)b * NX : xb;
     // only the threads of node 0 read x0 and none of them reads xbar_0, so the direction-0 thread may store it
@@ -77,10 +93,10 @@ SDF_HD void linearize_dir(const ModelConst& mc, int N, const LinIn& in, const Li
     // outputs; cold, those loads were 25 % of the kernel's stall samples (the other lanes of the warp wait for them).  Ask for
     // the lines now.
     if (dir == 0) {
-        const double* r_ = k < N ? in.yref + ((size_t)b * N + k) * NY : in.yrefN + (size_t)b * in.nyN;
+        const double* r_ = k < NR ? in.yref + ((size_t)b * NR + k) * NY : in.yrefN + (size_t)b * in.nyN;
         asm volatile("prefetch.global.L1 [%0];" ::"l"(r_));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(r_ + (k < N ? NY : in.nyN) - 1));
-        if (k < N) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(r_ + (k < NR ? NY : in.nyN) - 1));
+        if (k < NR) {
             asm volatile("prefetch.global.L1 [%0];" ::"l"(xb + NX));
             asm volatile("prefetch.global.L1 [%0];" ::"l"(xb + 2 * NX - 1));
         }
@@ -92,14 +108,13 @@ SDF_HD void linearize_dir(const ModelConst& mc, int N, const LinIn& in, const Li
     auto seed_x = [&](Dual* xd_) {
         for (int i = 0; i < NX; ++i) xd_[i] = Dual(x[i], (dir - NU) == i ? 1.0 : 0.0);
     };
-    if (k < N) {
+    if (k < NR) {
         const double* u = in.ubar + ((size_t)b * N + k) * NU;
         for (int j = 0; j < NU; ++j) ud[j] = Dual(u[j], dir == j ? 1.0 : 0.0);
     } else {
         for (int j = 0; j < NU; ++j) ud[j] = Dual(0.0, 0.0);
     }
-    const size_t node = (size_t)b * (N + 1) + k;
-    if (k < N) {
+    if (k < NR) {
         Dual xn[NX];
         rk4_step_seeded<MODEL>(mc, x, dir - NU, ud, in.dt[k], xn);
         if (out.AB) {       // null when the solver reads the operand layout `ABt` only
@@ -128,13 +143,18 @@ SDF_HD void linearize_dir(const ModelConst& mc, int N, const LinIn& in, const Li
     seed_x(xd);
     {
         Dual y[NY];
-        y_model<MODEL>(mc, xd, ud, in.qd + node * 4, y);
+        y_model<MODEL>(mc, xd, ud, in.qd + ((size_t)b * (NR + 1) + k) * 4, y);
+        if (k == NR && in.stab) {
+            const double f = in.flag[b];
+            for (int r = 0; r < 4; ++r) y[r] = f * y[r];
+            y[4] = f * (xd[7] * xd[7] + xd[8] * xd[8] + xd[9] * xd[9]);
+        }
         double* J = out.J + node * NY * NW;
         for (int r = 0; r < NY; ++r) J[r * NW + dir] = y[r].d;
         if (dir == 0) {
             double* yr = out.yres + node * NY;
-            if (k < N) {
-                const double* ref = in.yref + ((size_t)b * N + k) * NY;
+            if (k < NR) {
+                const double* ref = in.yref + ((size_t)b * NR + k) * NY;
                 for (int r = 0; r < NY; ++r) yr[r] = y[r].v - ref[r];
             } else {
                 const double* ref = in.yrefN + (size_t)b * in.nyN;

@@ -76,6 +76,11 @@ struct QpShape {
 template <int NX, int NU, int NY, int NH>
 struct QpProb {            // all pointers are offset to ONE instance
     int N, k0, max_iter, nyN;
+    // Lifted terminal rows (flags.recursive_feasibility / stability, term_lift.cuh): nodes n_real+1..N are auxiliary nodes behind the
+    // OCP's terminal node n_real (no cost, no regularisation of their state, rows with per-node bounds); n_real == N: plain OCP.
+    // Scalar solver only (qp_mma.cuh ignores these fields).
+    int n_real;
+    const double *nlh, *nuh, *nzs, *nZs;   // [N+1][NH] per-node bounds / slack weights of the h rows, or null (lh / uh / zs / Zs apply)
     double lm, tol, tol_res, max_df, flag;
     double sdf_cost_w;     // weight of the optional stage cost row (1 - 0.5 sdf)^4 (flags.sdf_cost, gen_model.py:65-66); 0 = off
     const double* AB;      // [N][NX][NW]
@@ -240,6 +245,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
     constexpr TriTable<NW> tri{};
     const int N = NFIX > 0 ? NFIX : P.N;          // NFIX: horizon known at compile time (all strides become immediates)
     const int k0 = P.k0, KP = S::kp(N);
+    const int NR = P.n_real;                      // terminal node of the OCP (== N unless terminal rows are lifted)
     const int NL = Lanes::count();
     const int lane = L.lane;
     const int ncomp = N * 2 * NU + 2 * (N + 1 - k0) * 2 * NH;
@@ -279,12 +285,14 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
     pipe.init(L, reinterpret_cast<unsigned long long*>(stg + 2 * S::STAGE_DOUBLES));
 
     auto scale = [&](int k) { return k < N ? P.dt[k] : 1.0; };
-    auto wrow = [&](int k, int r) { return k < N ? P.W[k * NY + r] : (r < P.nyN ? P.WN[r] : 0.0); };
+    auto wrow = [&](int k, int r) { return k < NR ? P.W[k * NY + r] : ((k == NR && r < P.nyN) ? P.WN[r] : 0.0); };
+    auto zrow = [&](int k, int r) { return (P.nzs ? P.nzs[k * NH + r] : P.zs[r]) * scale(k); };
+    auto Zrow = [&](int k, int r) { return (P.nZs ? P.nZs[k * NH + r] : P.Zs[r]) * scale(k); };
 
     // ---- prologue: sdf row of C / h, Gauss-Newton Hessian and gradient ----------------------
     const bool sdf_cost = P.sdf_cost_w > 0.0;          // the cost row also needs the SDF at node 0
     for (int k = lane; k <= N; k += NL) {
-        if (k >= (sdf_cost ? 0 : k0)) {
+        if (k >= (sdf_cost ? 0 : k0) && k <= NR) {
             const double* R = P.pose + 3;
             double gx = P.sdf_g[k * 3 + 0], gy = P.sdf_g[k * 3 + 1], gz = P.sdf_g[k * 3 + 2];
             double* Cr = P.C + ((size_t)k * NH + (NH - 1)) * NW;
@@ -346,8 +354,8 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                 const int j = TRI_PACK ? (int)((ijp >> (8 * m + 4)) & 15u) : (int)tri.j[t];
                 double s = 0.0;
                 for (int r = 0; r < NY; ++r) s += Jk[r * NW + i] * wk[r] * Jk[r * NW + j];
-                if (i == j) s += P.lm;
-                if (sdf_cost && k < N && i >= HC0 && i < HC0 + 3 && j >= HC0 && j < HC0 + 3) {
+                if (i == j && (k <= NR || i < NU)) s += P.lm;      // auxiliary nodes: inputs only
+                if (sdf_cost && k < NR && i >= HC0 && i < HC0 + 3 && j >= HC0 && j < HC0 + 3) {
                     double r, Jr[3];
                     cost_r(k, r, Jr);
                     s += P.sdf_cost_w * Jr[i - HC0] * Jr[j - HC0];
@@ -359,7 +367,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
             for (int i = lane; i < NW; i += NL) {
                 double s = 0.0;
                 for (int r = 0; r < NY; ++r) s += Jk[r * NW + i] * wk[r] * wk[NY + r];
-                if (sdf_cost && k < N && i >= HC0 && i < HC0 + 3) {
+                if (sdf_cost && k < NR && i >= HC0 && i < HC0 + 3) {
                     double r, Jr[3];
                     cost_r(k, r, Jr);
                     s += P.sdf_cost_w * r * Jr[i - HC0];
@@ -386,7 +394,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
     auto soft_d = [&](int kk, int a) {
         const int r = a < NH ? a : a - NH;
         const double hv = P.hval[kk * NH + r];
-        return a < NH ? P.lh[r] - hv : hv - P.uh[r];
+        return a < NH ? (P.nlh ? P.nlh[kk * NH + r] : P.lh[r]) - hv : hv - (P.nuh ? P.nuh[kk * NH + r] : P.uh[r]);
     };
     auto c_pos = [&](int kk, int r, int c) { return cpos[(kk * NH + r) * 3 + c]; };
 
@@ -502,7 +510,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
             const int r = a < NH ? a : a - NH;
             double t = 1.0, l = 1.0, m = 1.0, s0 = SDFNMPC_QP_S0;
             if (kk >= k0) {
-                const double z = P.zs[r] * scale(kk), Z = P.Zs[r] * scale(kk);
+                const double z = zrow(kk, r), Z = Zrow(kk, r);
                 double cw = 0.0;
                 for (int c = 0; c < 3; ++c) cw += c_pos(kk, r, c) * Wsm[(HC0 + c) * KP + kk];
                 const double gw = a < NH ? cw : -cw;
@@ -616,7 +624,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                     for (int r = 0; r < NH; ++r) {
                         const double c0 = c_pos(kk, r, 0), c1 = c_pos(kk, r, 1), c2 = c_pos(kk, r, 2);
                         const double cw = c0 * Wsm[(HC0 + 0) * KP + kk] + c1 * Wsm[(HC0 + 1) * KP + kk] + c2 * Wsm[(HC0 + 2) * KP + kk];
-                        const double z = P.zs[r] * scale(kk), Z = P.Zs[r] * scale(kk);
+                        const double z = zrow(kk, r), Z = Zrow(kk, r);
                         double thn = 0.0, cn = 0.0;
 #pragma unroll
                         for (int side = 0; side < 2; ++side) {
@@ -950,7 +958,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
                         const double c0 = c_pos(kk, r, 0), c1 = c_pos(kk, r, 1), c2 = c_pos(kk, r, 2);
                         const double cw = c0 * Wsm[(HC0 + 0) * KP + kk] + c1 * Wsm[(HC0 + 1) * KP + kk] + c2 * Wsm[(HC0 + 2) * KP + kk];
                         const double cd = c0 * dW[(HC0 + 0) * KP + kk] + c1 * dW[(HC0 + 1) * KP + kk] + c2 * dW[(HC0 + 2) * KP + kk];
-                        const double z = P.zs[r] * scale(kk), Z = P.Zs[r] * scale(kk);
+                        const double z = zrow(kk, r), Z = Zrow(kk, r);
 #pragma unroll
                         for (int side = 0; side < 2; ++side) {
                             const int a = side * NH + r;

@@ -124,6 +124,20 @@ def make_decoder_net(seed=0, size_latent=128):
 # workloads
 # --------------------------------------------------------------------------------------
 
+def braking_coeffs(degree=4):
+    """Synthetic coefficients of the 3-variate braking-distance polynomial (``utils/math.py:294-321`` term order: total degree,
+    then a, then b; c = td - a - b).  The reference's file ``mpc.braking_dist.coeff_file`` is fitted by ``scripts/find_amax.py`` into
+    the user's cache directory and is not shipped; this stand-in has the same shape: a small offset plus anisotropic quadratic
+    growth with the speed and two higher-order terms."""
+    vals = {(0, 0, 0): 0.02, (2, 0, 0): 0.10, (0, 2, 0): 0.11, (0, 0, 2): 0.14, (0, 0, 3): 0.01, (2, 2, 0): 0.004}
+    co = []
+    for td in range(degree + 1):
+        for a in range(td + 1):
+            for b in range(td + 1 - a):
+                co.append(vals.get((a, b, td - a - b), 0.0))
+    return np.array(co)
+
+
 def sdf_query_points(n, seed=3):
     """Config 2: points uniform in the frustum box [0,5]x[-2.5,2.5]x[-1.5,1.5], float32 [n,3]."""
     rng = np.random.default_rng(seed)
