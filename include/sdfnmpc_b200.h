@@ -94,12 +94,26 @@ typedef struct {
     /* model props (quad_props.py:18-52): rotor-speed scale limits.wp, allocation matrices with cf folded in as Gf / mass and
      * J^-1 Gt (row-major [3][4]), diagonal inertia, hover input of Ocp.init */
     double wp_max, Gf_m[12], JGt[12], inertia[3], u_hover_props;
+    /* flags.recursive_feasibility / flags.stability (gen_model.py:73-149; model att only).  term_lift: 0 off, 1 recursive
+     * feasibility (terminal sdf row replaced by rec_feas = sdf_flag(p) - flag * poly(v) in brake_bounds, soft with slack_brake
+     * or hard when slack_brake[0] < 0; hard FoV rows at the braking end point, fov_term = (hfov, vfov) limits, vfov <= 0: no
+     * vfov row), 2 also stability (hard velocity box +- vlim, terminal outputs flag * [p, q_e3] and flag * v.v: yrefN / WN
+     * are then [B][5]).  brake_coeffs: 3-variate polynomial of degree brake_degree <= 5 in the term order of
+     * utils/math.py:306-312.  The rows are carried by term_lift auxiliary nodes behind node N (csrc/term_lift.cuh), so
+     * N + term_lift <= 31 and the state arrays of sdfnmpc_solver_state / _diag have N + term_lift (+ 1) nodes per instance
+     * (sdfnmpc_solver_horizon).  Hard rows use an exact L1 penalty of weight z_hard (0 -> 1e4), which must exceed their
+     * multipliers. */
+    int32_t term_lift, brake_degree;
+    double brake_coeffs[56];
+    double brake_bounds[2], slack_brake[2], fov_term[2], vlim[3], z_hard;
 } sdfnmpc_solver_desc;
 
 /* Stage dimensions by model: att / att_tau / acc  nx 10, ny 11;  props  nx 14 (the reference's 13 states [p, q, v, w] + ONE PAD
  * entry that callers keep at 0: the QP's staging copies move 16-byte units), ny 16.  nu = 4 and nh = 3 for all.  Wherever a
  * comment below says [10] / [11] read nx / ny of the handle's model. */
 int sdfnmpc_solver_dims(sdfnmpc_solver_t h, int32_t* nx, int32_t* ny, int32_t* nyN);
+/* N of the OCP (stride of yref / W / qd) and the node stride N_alloc = N + term_lift of the handle's own arrays. */
+int sdfnmpc_solver_horizon(sdfnmpc_solver_t h, int32_t* N, int32_t* N_alloc);
 
 int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver_desc* desc, sdfnmpc_sdf_t sdf);
 int sdfnmpc_solver_destroy(sdfnmpc_solver_t h);

@@ -31,7 +31,10 @@ class SolverDesc(C.Structure):
                 ('model', C.c_int32), ('reserved', C.c_int32), ('ax', C.c_double), ('ay', C.c_double), ('az', C.c_double),
                 ('tau_roll', C.c_double), ('tau_pitch', C.c_double), ('sdf_cost_w', C.c_double),
                 ('wp_max', C.c_double), ('Gf_m', C.c_double * 12), ('JGt', C.c_double * 12), ('inertia', C.c_double * 3),
-                ('u_hover_props', C.c_double)]
+                ('u_hover_props', C.c_double),
+                ('term_lift', C.c_int32), ('brake_degree', C.c_int32), ('brake_coeffs', C.c_double * 56),
+                ('brake_bounds', C.c_double * 2), ('slack_brake', C.c_double * 2), ('fov_term', C.c_double * 2),
+                ('vlim', C.c_double * 3), ('z_hard', C.c_double)]
 
 
 class EncoderDesc(C.Structure):
@@ -69,7 +72,7 @@ CASADI_COMPANIONS = ('', '_alloc_mem', '_init_mem', '_free_mem', '_checkout', '_
 EXPORTS = (['sdfnmpc_version', 'sdfnmpc_launch_count', 'sdfnmpc_sdf_create', 'sdfnmpc_sdf_destroy',
             'sdfnmpc_sdf_set_latents', 'sdfnmpc_sdf_eval', 'sdfnmpc_sdf_eval_host', 'sdfnmpc_solver_create',
             'sdfnmpc_solver_destroy', 'sdfnmpc_solver_init_traj', 'sdfnmpc_solver_shift', 'sdfnmpc_solver_rti_step',
-            'sdfnmpc_solver_state', 'sdfnmpc_solver_diag', 'sdfnmpc_solver_qp_residual', 'sdfnmpc_solver_timing_begin', 'sdfnmpc_solver_timing_end', 'sdfnmpc_plant_step', 'sdfnmpc_cmd_trpyr', 'sdfnmpc_cmd_acc', 'sdfnmpc_cmd_props', 'sdfnmpc_solver_dims', 'sdfnmpc_colcheck', 'sdfnmpc_df_signed', 'sdfnmpc_df_unsigned', 'sdfnmpc_fail_count_update',
+            'sdfnmpc_solver_state', 'sdfnmpc_solver_diag', 'sdfnmpc_solver_qp_residual', 'sdfnmpc_solver_timing_begin', 'sdfnmpc_solver_timing_end', 'sdfnmpc_plant_step', 'sdfnmpc_cmd_trpyr', 'sdfnmpc_cmd_acc', 'sdfnmpc_cmd_props', 'sdfnmpc_solver_dims', 'sdfnmpc_solver_horizon', 'sdfnmpc_colcheck', 'sdfnmpc_df_signed', 'sdfnmpc_df_unsigned', 'sdfnmpc_fail_count_update',
             'sdfnmpc_encoder_create', 'sdfnmpc_encoder_destroy', 'sdfnmpc_encoder_encode',
             'sdfnmpc_encoder_encode_host', 'sdfnmpc_decoder_create', 'sdfnmpc_decoder_destroy', 'sdfnmpc_decoder_decode',
             'sdfnmpc_decoder_decode_host', 'sdfnmpc_l4c_bind', 'sdfnmpc_l4c_load_blob']
@@ -118,6 +121,7 @@ def load():
     lib.sdfnmpc_cmd_acc.argtypes = [vp, i32, dp, dp, dp, vp]
     lib.sdfnmpc_cmd_props.argtypes = [vp, i32, dp, dp, vp]
     lib.sdfnmpc_solver_dims.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    lib.sdfnmpc_solver_horizon.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
     lib.sdfnmpc_fail_count_update.argtypes = [ip, vp, i32, vp]
     lib.sdfnmpc_colcheck.argtypes = [fp, i32, i32, i32, fp, ip, i64] + [C.c_float] * 4 + [i32, i32, i32, vp, vp]
     lib.sdfnmpc_df_signed.argtypes = [fp, i32, i32, i32, fp, ip, i64, fp, fp, i32] + [C.c_float] * 3 + [i32, i32, C.c_float, C.c_float, fp, fp, vp]

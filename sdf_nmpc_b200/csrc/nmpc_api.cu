@@ -9,6 +9,7 @@
 #include "linearize_core.cuh"
 #include "qp_core.cuh"
 #include "qp_mma.cuh"
+#include "term_lift.cuh"
 
 using namespace sdfnmpc;
 
@@ -20,6 +21,7 @@ using Shape = QpShape<NX, NU, NY, NH>;        // A/B builds: the scalar statemen
 #else
 using Shape = QpMmaShape;                     // product: tensor-core sweeps (qp_mma.cuh)
 #endif
+using ScalarShape = QpShape<NX, NU, NY, NH>;  // lifted terminal rows (term_lift.cuh) run on the scalar solver
 // model 'props' (13 states + one pad entry, 16 outputs): the scalar solver instantiated for its shape
 using PD = ModelDims<MODEL_PROPS>;
 using PropsProb = QpProb<PD::NX, PD::NU, PD::NY, PD::NH>;
@@ -37,6 +39,7 @@ constexpr int QP_WARPS = QP_WARPS_PER_CTA;     // instances per CTA
 struct SolverConst {
     ModelConst mc;
     int N, k0, qp_iter_max, model, nyN;
+    int n_real, stab;     // OCP horizon (N = n_real + auxiliary nodes of term_lift.cuh), flags.stability
     double lm, tol, tol_res, u_hover, sdf_cost_w;
     double lbu[NU], ubu[NU], lh[NH], uh[NH], zs[NH], Zs[NH];
     double cmd_min[4], cmd_max[4];
@@ -52,6 +55,8 @@ struct sdfnmpc_solver {
     double* dt = nullptr;                     // [N] device
     double *xbar = nullptr, *ubar = nullptr;  // warm start
     double *ABt = nullptr;                    // [B][N][16][12] [A B | b] in the tensor-core operand layout
+    TermConst tc{};                           // flags.recursive_feasibility / stability (term_lift.cuh); n_lift 0 = off
+    double* node_rows = nullptr;              // [4][N+1][NH] per-node lh, uh, zs, Zs of the lifted formulation
     double *AB = nullptr, *bdyn = nullptr, *J = nullptr, *yres = nullptr, *C = nullptr, *hval = nullptr;
     float *qpts = nullptr, *sdf_d = nullptr, *sdf_g = nullptr;
     double *work = nullptr, *lam_hard = nullptr, *lam_soft = nullptr, *qp_res = nullptr;
@@ -89,10 +94,12 @@ struct QpBatch {
     long long* trace;
     size_t work_per_inst;
     double max_df;
+    int n_real;            // OCP horizon = stride of W (== N unless terminal rows are lifted)
+    const double *nlh, *nuh, *nzs, *nZs;   // per-node rows of the lifted formulation or null
     int* counter;          // [2] next instance to draw, slots that ran dry (both zero between launches)
 };
 
-template <int NFIX, bool PROPS = false>
+template <int NFIX, bool PROPS = false, bool LIFT = false>
 #ifdef QP_MAXNREG
 __global__ void __maxnreg__(QP_MAXNREG) nmpc_qp_kernel(
 #else
@@ -101,7 +108,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32, QP_MIN_CTAS) nmpc_qp_kernel(
     SolverConst sc, int B, QpBatch q) {
     constexpr int NX = PROPS ? PD::NX : ::NX, NW = PROPS ? PD::NW : ::NW, NY = PROPS ? PD::NY : ::NY;
     using Prob = typename std::conditional<PROPS, PropsProb, ::Prob>::type;
-    using Shape = typename std::conditional<PROPS, PropsShape, ::Shape>::type;
+    using Shape = typename std::conditional<PROPS, PropsShape, typename std::conditional<LIFT, ScalarShape, ::Shape>::type>::type;
     extern __shared__ double sm_all[];
     __shared__ SolverConst scs;
     if (threadIdx.x == 0) scs = sc;
@@ -125,6 +132,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32, QP_MIN_CTAS) nmpc_qp_kernel(
     }
     Prob P;
     P.N = N; P.k0 = scs.k0; P.max_iter = scs.qp_iter_max; P.nyN = scs.nyN;
+    P.n_real = q.n_real; P.nlh = q.nlh; P.nuh = q.nuh; P.nzs = q.nzs; P.nZs = q.nZs;
     P.lm = scs.lm; P.tol = scs.tol; P.tol_res = scs.tol_res; P.max_df = q.max_df; P.flag = q.flag[b];
     P.sdf_cost_w = scs.sdf_cost_w;
     P.AB = q.AB + (size_t)b * N * NX * NW;
@@ -134,7 +142,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32, QP_MIN_CTAS) nmpc_qp_kernel(
     P.yres = q.yres + (size_t)b * (N + 1) * NY;
     P.C = q.C + (size_t)b * (N + 1) * NH * NW;
     P.hval = q.hval + (size_t)b * (N + 1) * NH;
-    P.W = q.W + (size_t)b * N * NY;
+    P.W = q.W + (size_t)b * q.n_real * NY;
     P.WN = q.WN + (size_t)b * scs.nyN;
     P.dt = q.dt;
     P.lbu = scs.lbu; P.ubu = scs.ubu; P.lh = scs.lh; P.uh = scs.uh; P.zs = scs.zs; P.Zs = scs.Zs;
@@ -161,7 +169,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32, QP_MIN_CTAS) nmpc_qp_kernel(
 #if defined(SDFNMPC_QP_SCALAR)
     qp_solve_instance<NX, NU, NY, NH, NFIX>(L, P, sm_all + (size_t)warp * Shape::smem_doubles(N));
 #else
-    if constexpr (PROPS) qp_solve_instance<NX, NU, NY, NH, NFIX>(L, P, sm_all + (size_t)warp * Shape::smem_doubles(N));
+    if constexpr (PROPS || LIFT) qp_solve_instance<NX, NU, NY, NH, NFIX>(L, P, sm_all + (size_t)warp * Shape::smem_doubles(N));
     else qp_solve_mma<NFIX>(L, P, sm_all + (size_t)warp * Shape::smem_doubles(N));
 #endif
     __syncwarp();
@@ -181,13 +189,14 @@ __global__ void nmpc_init_traj_kernel(int N, int B, int nx, double u_hover, bool
     if (gid < (long long)B * N * NU) ubar[gid] = (hover_all || (gid % NU) == 0) ? u_hover : 0.0;
 }
 
-__global__ void nmpc_shift_kernel(int N, int B, int s, int NX, double* __restrict__ xbar, double* __restrict__ ubar) {
-    // Ocp.shift (ocp.py:152-156): for i in k..N-1: x[i-k] = x[i], u[i-k] = u[i]   (node N untouched)
+__global__ void nmpc_shift_kernel(int N, int NR, int B, int s, int NX, double* __restrict__ xbar, double* __restrict__ ubar) {
+    // Ocp.shift (ocp.py:152-156): for i in k..N-1: x[i-k] = x[i], u[i-k] = u[i]   (node N untouched); NR = the OCP's horizon,
+    // N = node stride of the arrays
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     double* x = xbar + (size_t)b * (N + 1) * NX;
     double* u = ubar + (size_t)b * N * NU;
-    for (int i = s; i < N; ++i) {
+    for (int i = s; i < NR; ++i) {
         for (int j = 0; j < NX; ++j) x[(i - s) * NX + j] = x[i * NX + j];
         for (int j = 0; j < NU; ++j) u[(i - s) * NU + j] = u[i * NU + j];
     }
@@ -229,9 +238,24 @@ __global__ void nmpc_cmd_props_kernel(double wp_max, int B, const double* __rest
     if (i < B * NU) cmd[i] = fmin(fmax(u[i] * wp_max, 0.0), wp_max);
 }
 
+// auxiliary stages / nodes of the lifted terminal rows: one thread per instance (ten dual-number evaluations of two FoV rows)
+__global__ void nmpc_term_lift_kernel(ModelConst mc, TermConst tc, int N, int NR, int B, const double* __restrict__ pose,
+                                      const double* __restrict__ flag, double max_df, const float* __restrict__ sdf_d,
+                                      const float* __restrict__ sdf_g, double* __restrict__ xbar, double* __restrict__ AB,
+                                      double* __restrict__ bdyn, double* __restrict__ C, double* __restrict__ hval) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    term_lift_instance(mc, tc, N, NR, pose + (size_t)b * 12, flag[b], max_df, sdf_d[(size_t)b * (N + 1) + NR],
+                       sdf_g + ((size_t)b * (N + 1) + NR) * 3, xbar + (size_t)b * (N + 1) * NX, AB + (size_t)b * N * NX * NW,
+                       bdyn + (size_t)b * N * NX, C + (size_t)b * (N + 1) * NH * NW, hval + (size_t)b * (N + 1) * NH);
+}
+
 extern "C" int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver_desc* d, sdfnmpc_sdf_t sdf) {
     // the QP kernel maps node k to lane k of the instance's warp: N + 1 <= 32
     if (!out || !d || !sdf || d->N < 1 || d->N > 31 || d->N > SDFNMPC_MAX_N || d->max_batch < 1) return SDFNMPC_E_INVALID;
+    const int lift = d->term_lift;
+    if (lift < 0 || lift > 2 || d->N + lift > 31) return SDFNMPC_E_INVALID;
+    if (lift && (d->model != MODEL_ATT || d->brake_degree < 0 || d->brake_degree > 5 || !(d->fov_term[0] > 0))) return SDFNMPC_E_INVALID;
     if (int rc = ensure_device()) return rc;
     auto* h = new sdfnmpc_solver();
     h->desc = *d;
@@ -243,7 +267,7 @@ extern "C" int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver
     if (d->model < 0 || d->model > 3) { delete h; return SDFNMPC_E_INVALID; }
     sc.model = d->model;
     const bool props = d->model == MODEL_PROPS;
-    sc.nyN = d->model == MODEL_ACC ? 7 : (props ? PROPS_NYN : 4);            // quad_acc.py:15, quad_props.py:15, quad_rollpitchyawrate*.py:15
+    sc.nyN = d->model == MODEL_ACC ? 7 : (props ? PROPS_NYN : (lift == 2 ? 5 : 4));   // stability: + flag * v.v (gen_model.py:139-147)            // quad_acc.py:15, quad_props.py:15, quad_rollpitchyawrate*.py:15
     sc.u_hover = d->model == MODEL_ACC ? 0.0 : (props ? d->u_hover_props : d->g / d->gamma);   // quad_acc.py:35, quad_rollpitchyawrate.py:44
     sc.mc.wp_max = d->wp_max;
     for (int i = 0; i < 12; ++i) { sc.mc.Gf_m[i] = d->Gf_m[i]; sc.mc.JGt[i] = d->JGt[i]; }
@@ -252,27 +276,30 @@ extern "C" int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver
     if (props) { h->nx = PD::NX; h->nw = PD::NW; h->ny = PD::NY; }
     sc.mc.ax = d->ax; sc.mc.ay = d->ay; sc.mc.az = d->az;
     sc.mc.tau_roll = d->tau_roll > 0 ? d->tau_roll : 0.12; sc.mc.tau_pitch = d->tau_pitch > 0 ? d->tau_pitch : 0.12;
-    sc.N = d->N; sc.k0 = d->h_at_node0 ? 0 : 1; sc.qp_iter_max = d->qp_iter_max;
+    sc.N = d->N + lift; sc.n_real = d->N; sc.stab = lift == 2;
+    sc.k0 = d->h_at_node0 ? 0 : 1; sc.qp_iter_max = d->qp_iter_max;
+    h->tc.n_lift = lift; h->tc.degree = d->brake_degree;
+    for (int i = 0; i < TERM_MAX_COEFFS; ++i) h->tc.coeffs[i] = lift ? d->brake_coeffs[i] : 0.0;
     sc.lm = d->lm; sc.tol = d->qp_tol; sc.tol_res = d->qp_tol_res; sc.sdf_cost_w = d->sdf_cost_w > 0 ? d->sdf_cost_w : 0.0;
     for (int i = 0; i < NU; ++i) { sc.lbu[i] = d->lbu[i]; sc.ubu[i] = d->ubu[i]; }
     for (int i = 0; i < NH; ++i) { sc.lh[i] = d->lh[i]; sc.uh[i] = d->uh[i]; sc.zs[i] = d->zl[i]; sc.Zs[i] = d->Zl[i]; }
     // controller.py:21-23: thrust command clipped at limits.gamma (not gamma*mass) - kept for parity
     const double cmin[4] = {0.0, -d->roll, -d->pitch, -d->wz}, cmax[4] = {d->gamma, d->roll, d->pitch, d->wz};
     for (int i = 0; i < 4; ++i) { sc.cmd_min[i] = cmin[i]; sc.cmd_max[i] = cmax[i]; }
-    const size_t B = (size_t)h->cap, N = (size_t)d->N, N1 = N + 1;
+    const size_t B = (size_t)h->cap, N = (size_t)sc.N, N1 = N + 1;
     const size_t NX = (size_t)h->nx, NW = (size_t)h->nw, NY = (size_t)h->ny;
-    h->work_per_inst = props ? PropsShape::work_doubles(d->N) : Shape::work_doubles(d->N);
+    h->work_per_inst = props ? PropsShape::work_doubles(sc.N) : (lift ? ScalarShape::work_doubles(sc.N) : Shape::work_doubles(sc.N));
     cudaError_t e = cudaSuccess;
     auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
     alloc((void**)&h->dt, N * sizeof(double));
     alloc((void**)&h->xbar, B * N1 * NX * sizeof(double));
     alloc((void**)&h->ubar, B * N * NU * sizeof(double));
 #if !defined(SDFNMPC_QP_SCALAR)
-    if (props)      // the tensor-core solver reads [A B | b] in its operand layout (ABt) only
+    if (props || lift)      // the tensor-core solver reads [A B | b] in its operand layout (ABt) only
 #endif
     alloc((void**)&h->AB, B * N * NX * NW * sizeof(double));
 #if !defined(SDFNMPC_QP_SCALAR)
-    if (!props) alloc((void**)&h->ABt, B * N * 192 * sizeof(double));
+    if (!props && !lift) alloc((void**)&h->ABt, B * N * 192 * sizeof(double));
 #endif
     alloc((void**)&h->bdyn, B * N * NX * sizeof(double));
     alloc((void**)&h->J, B * N1 * NY * NW * sizeof(double));
@@ -283,7 +310,7 @@ extern "C" int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver
     alloc((void**)&h->sdf_d, B * N1 * sizeof(float));
     alloc((void**)&h->sdf_g, B * N1 * 3 * sizeof(float));
     // the QP kernel runs as persistent warps: as many as fit the device at once, each owning one block of scratch
-    h->qp_smem = (size_t)QP_WARPS * (props ? PropsShape::smem_doubles(d->N) : Shape::smem_doubles(d->N)) * sizeof(double);
+    h->qp_smem = (size_t)QP_WARPS * (props ? PropsShape::smem_doubles(sc.N) : (lift ? ScalarShape::smem_doubles(sc.N) : Shape::smem_doubles(sc.N))) * sizeof(double);
 #if defined(QP_CARVEOUT)
     if (e == cudaSuccess) e = cudaFuncSetAttribute(nmpc_qp_kernel<20>, cudaFuncAttributePreferredSharedMemoryCarveout, QP_CARVEOUT);
 #endif
@@ -295,6 +322,8 @@ extern "C" int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver
 #endif
     if (props) {
         if (e == cudaSuccess) e = cudaFuncSetAttribute(nmpc_qp_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qp_smem);
+    } else if (lift) {
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(nmpc_qp_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qp_smem);
     } else {
         if (e == cudaSuccess) e = cudaFuncSetAttribute(nmpc_qp_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qp_smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(nmpc_qp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qp_smem);
@@ -305,6 +334,7 @@ extern "C" int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (e == cudaSuccess) {
             if (props) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nmpc_qp_kernel<0, true>, QP_WARPS * 32, h->qp_smem);
+            else if (lift) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nmpc_qp_kernel<0, false, true>, QP_WARPS * 32, h->qp_smem);
             else if (d->N == 20) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nmpc_qp_kernel<20>, QP_WARPS * 32, h->qp_smem);
             else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nmpc_qp_kernel<0>, QP_WARPS * 32, h->qp_smem);
         }
@@ -321,7 +351,31 @@ extern "C" int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver
     alloc((void**)&h->lam_hard, B * N * 2 * NU * sizeof(double));
     alloc((void**)&h->lam_soft, B * N1 * 2 * NH * sizeof(double));
     alloc((void**)&h->qp_res, 2 * B * sizeof(double));
-    if (e == cudaSuccess) e = cudaMemcpy(h->dt, d->dt, N * sizeof(double), cudaMemcpyHostToDevice);
+    {
+        std::vector<double> dth(N, 1.0);           // auxiliary stages: scale 1 like the terminal node
+        for (int k = 0; k < d->N; ++k) dth[k] = d->dt[k];
+        if (e == cudaSuccess) e = cudaMemcpy(h->dt, dth.data(), N * sizeof(double), cudaMemcpyHostToDevice);
+    }
+    if (lift) {
+        // per-node bounds / slack weights: OCP nodes keep the stage values; node N loses its sdf row (gen_model.py:69-70);
+        // node N + 1 = [hfov_E, vfov_E, rec_feas], node N + 2 = velocity box.  Hard rows: exact L1 penalty z_hard.
+        const double zh = d->z_hard > 0 ? d->z_hard : 1e4, off = 50.0;     // |h| never reaches `off` (angles, metres of clearance)
+        std::vector<double> rows(4 * N1 * NH);
+        double *nlh = rows.data(), *nuh = nlh + N1 * NH, *nzs = nuh + N1 * NH, *nZs = nzs + N1 * NH;
+        for (size_t k = 0; k < N1; ++k)
+            for (int r = 0; r < NH; ++r) { nlh[k * NH + r] = d->lh[r]; nuh[k * NH + r] = d->uh[r]; nzs[k * NH + r] = d->zl[r]; nZs[k * NH + r] = d->Zl[r]; }
+        const size_t kN = (size_t)d->N;
+        nlh[kN * NH + 2] = -off; nuh[kN * NH + 2] = off;
+        const bool vf = d->fov_term[1] > 0, soft = d->slack_brake[0] >= 0;
+        const double l1[3] = {-d->fov_term[0], vf ? -d->fov_term[1] : -off, d->brake_bounds[0]};
+        const double u1[3] = {d->fov_term[0], vf ? d->fov_term[1] : off, d->brake_bounds[1]};
+        const double z1[3] = {zh, zh, soft ? d->slack_brake[0] : zh}, Z1[3] = {0.0, 0.0, soft ? d->slack_brake[1] : 0.0};
+        for (int r = 0; r < NH; ++r) { nlh[(kN + 1) * NH + r] = l1[r]; nuh[(kN + 1) * NH + r] = u1[r]; nzs[(kN + 1) * NH + r] = z1[r]; nZs[(kN + 1) * NH + r] = Z1[r]; }
+        if (lift == 2)
+            for (int r = 0; r < NH; ++r) { nlh[(kN + 2) * NH + r] = -d->vlim[r]; nuh[(kN + 2) * NH + r] = d->vlim[r]; nzs[(kN + 2) * NH + r] = zh; nZs[(kN + 2) * NH + r] = 0.0; }
+        alloc((void**)&h->node_rows, rows.size() * sizeof(double));
+        if (e == cudaSuccess) e = cudaMemcpy(h->node_rows, rows.data(), rows.size() * sizeof(double), cudaMemcpyHostToDevice);
+    }
     if (e == cudaSuccess) e = cudaMemset(h->xbar, 0, B * N1 * NX * sizeof(double));
     if (e == cudaSuccess) e = cudaMemset(h->ubar, 0, B * N * NU * sizeof(double));
     if (e != cudaSuccess) { sdfnmpc_solver_destroy(h); return (int)e; }
@@ -332,7 +386,7 @@ extern "C" int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver
 extern "C" int sdfnmpc_solver_destroy(sdfnmpc_solver_t h) {
     if (!h) return 0;
     void* ptrs[] = {h->dt, h->xbar, h->ubar, h->ABt, h->AB, h->bdyn, h->J, h->yres, h->C, h->hval, h->qpts, h->sdf_d, h->sdf_g,
-                    h->work, h->lam_hard, h->lam_soft, h->qp_res, h->qp_counter};
+                    h->work, h->lam_hard, h->lam_soft, h->qp_res, h->qp_counter, h->node_rows};
     for (void* p : ptrs) cudaFree(p);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     delete h;
@@ -353,7 +407,7 @@ extern "C" int sdfnmpc_solver_init_traj(sdfnmpc_solver_t h, const double* x0, in
 extern "C" int sdfnmpc_solver_shift(sdfnmpc_solver_t h, int32_t B, int32_t k, void* stream) {
     if (!h || B < 1 || B > h->cap || k < 0) return SDFNMPC_E_INVALID;
     if (k == 0) return 0;
-    nmpc_shift_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->sc.N, B, k, h->nx, h->xbar, h->ubar);
+    nmpc_shift_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->sc.N, h->sc.n_real, B, k, h->nx, h->xbar, h->ubar);
     count_launch();
     SDF_CUDA_CHECK(cudaGetLastError());
     return 0;
@@ -376,6 +430,7 @@ extern "C" int sdfnmpc_solver_rti_step(sdfnmpc_solver_t h, int32_t B, const doub
     cudaEvent_t* ev = tm ? &h->ev[(size_t)h->ev_steps * 4] : nullptr;
     if (tm) cudaEventRecord(ev[0], st);
     LinIn in{h->xbar, h->ubar, yref, yrefN, qd, pose, flag, h->dt, h->sc.nyN, x0};
+    in.n_real = h->sc.n_real; in.stab = h->sc.stab;
     LinOut lo{h->AB, h->bdyn, h->J, h->yres, h->C, h->hval, h->qpts, h->ABt};
     const long long total = (long long)B * (N + 1) * h->nw;
     const unsigned lin_grid = (unsigned)((total + 127) / 128);
@@ -387,6 +442,13 @@ extern "C" int sdfnmpc_solver_rti_step(sdfnmpc_solver_t h, int32_t B, const doub
     SDF_CUDA_CHECK(cudaGetLastError());
     if (tm) cudaEventRecord(ev[1], st);
     if (int rc = sdfnmpc_sdf_eval(h->sdf, h->qpts, nullptr, N + 1, (int64_t)B * (N + 1), h->sdf_d, h->sdf_g, stream)) return rc;
+    const int lift = h->tc.n_lift;
+    if (lift) {
+        nmpc_term_lift_kernel<<<(B + 127) / 128, 128, 0, st>>>(h->sc.mc, h->tc, N, h->sc.n_real, B, pose, flag, (double)h->sdf->net.max_df,
+                                                             h->sdf_d, h->sdf_g, h->xbar, h->AB, h->bdyn, h->C, h->hval);
+        count_launch();
+        SDF_CUDA_CHECK(cudaGetLastError());
+    }
     if (tm) cudaEventRecord(ev[2], st);
     QpBatch q;
     q.AB = h->AB; q.ABt = h->ABt; q.bdyn = h->bdyn; q.J = h->J; q.yres = h->yres; q.W = W; q.WN = WN; q.dt = h->dt; q.pose = pose;
@@ -394,6 +456,10 @@ extern "C" int sdfnmpc_solver_rti_step(sdfnmpc_solver_t h, int32_t B, const doub
     q.u0 = u0; q.lam_hard = h->lam_hard; q.lam_soft = h->lam_soft; q.sdf_d = h->sdf_d; q.sdf_g = h->sdf_g;
     q.status = status; q.iters = qp_iters; q.work_per_inst = h->work_per_inst; q.max_df = (double)h->sdf->net.max_df;
     q.res_out = h->qp_res;
+    q.n_real = h->sc.n_real;
+    const size_t nrow = (size_t)(N + 1) * NH;
+    q.nlh = h->node_rows; q.nuh = lift ? h->node_rows + nrow : nullptr; q.nzs = lift ? h->node_rows + 2 * nrow : nullptr;
+    q.nZs = lift ? h->node_rows + 3 * nrow : nullptr;
     q.trace = nullptr;
 #if defined(SDFNMPC_QP_TRACE)
     static long long* qtrace = nullptr;          // development: per-phase cycles of instance 0, IPM iteration 2
@@ -407,6 +473,7 @@ extern "C" int sdfnmpc_solver_rti_step(sdfnmpc_solver_t h, int32_t B, const doub
     const int qp_warps = B < h->qp_slots ? B : h->qp_slots;
     const unsigned qp_grid = (unsigned)((qp_warps + QP_WARPS - 1) / QP_WARPS);
     if (h->sc.model == MODEL_PROPS) nmpc_qp_kernel<0, true><<<qp_grid, QP_WARPS * 32, h->qp_smem, st>>>(h->sc, B, q);
+    else if (lift) nmpc_qp_kernel<0, false, true><<<qp_grid, QP_WARPS * 32, h->qp_smem, st>>>(h->sc, B, q);
     else if (N == 20) nmpc_qp_kernel<20><<<qp_grid, QP_WARPS * 32, h->qp_smem, st>>>(h->sc, B, q);
     else nmpc_qp_kernel<0><<<qp_grid, QP_WARPS * 32, h->qp_smem, st>>>(h->sc, B, q);
     count_launch();
@@ -530,6 +597,13 @@ extern "C" int sdfnmpc_cmd_props(sdfnmpc_solver_t h, int32_t B, const double* u,
     nmpc_cmd_props_kernel<<<(B * NU + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->sc.mc.wp_max, B, u, cmd);
     count_launch();
     SDF_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int sdfnmpc_solver_horizon(sdfnmpc_solver_t h, int32_t* N, int32_t* N_alloc) {
+    if (!h) return SDFNMPC_E_INVALID;
+    if (N) *N = h->sc.n_real;
+    if (N_alloc) *N_alloc = h->sc.N;
     return 0;
 }
 

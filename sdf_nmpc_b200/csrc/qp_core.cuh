@@ -68,7 +68,7 @@ struct QpShape {
     SDF_HD static int smem_doubles(int N) {
         return NX * NX + NX * (NW + 1) + NW * NW + NW + NU * NX + NU + 2 * NX       // Riccati workspace
                + 2 * NW * kp(N)                                                   // W (iterate), dW (step)
-               + (NCORR + NPROD) * kp(N) + 8
+               + (NCORR + NPROD) * kp(N) + (((NCORR + NPROD) * kp(N)) & 1) + 8     // stage slots and the next lane group stay 16-byte aligned (odd N)
                + 2 * STAGE_DOUBLES + 2;                                           // double-buffered per-stage data, 2 mbarriers
     }
 };
@@ -280,7 +280,7 @@ SDF_HD void qp_solve_instance(const Lanes& L, const QpProb<NX, NU, NY, NH>& P, d
     double* dW = Wsm + NW * KP;          // [NW][KP]   step
     double* corr = dW + NW * KP;         // [NCORR][KP] du(NU) Dp(6) gu(NU) gp(3) per node
     double* prod = corr + NCORR * KP;    // [NPROD][KP] affine second-order products
-    double* stg = prod + NPROD * KP + ((NPROD * KP) & 1);   // 2 x STAGE_DOUBLES (16-byte aligned)
+    double* stg = prod + NPROD * KP + (((NCORR + NPROD) * KP) & 1);   // 2 x STAGE_DOUBLES (16-byte aligned: everything before `corr` is even)
     StagePipe pipe;
     pipe.init(L, reinterpret_cast<unsigned long long*>(stg + 2 * S::STAGE_DOUBLES));
 

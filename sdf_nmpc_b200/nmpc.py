@@ -23,6 +23,53 @@ NX, NU, NY, NH = 10, 4, 11, 3                       # models att / att_tau / acc
 MODEL_ID = {'att': 0, 'att_tau': 1, 'acc': 2, 'props': 3}      # mpc.model values reachable in gen_model.py:15-20
 
 
+def braking_coeffs(cfg):
+    """Coefficients of the braking-distance polynomial (``gen_model.py:76-78``): ``mpc.braking_dist.coeffs`` if the YAML carries
+    them inline, else the ``.npy`` file ``mpc.braking_dist.coeff_file`` in the cache directory (``$SDFNMPC_CACHE_DIR`` or
+    ``~/.cache/sdf_nmpc``, where the reference's ``scripts/find_amax.py`` writes it)."""
+    import os
+    bd = cfg.mpc.braking_dist
+    deg = int(bd.degree)
+    if bd.get('coeffs') is not None:
+        co = np.asarray(bd.coeffs, float).ravel()
+    else:
+        root = os.environ.get('SDFNMPC_CACHE_DIR', os.path.join(os.path.expanduser('~'), '.cache', 'sdf_nmpc'))
+        path = os.path.join(root, bd.coeff_file)
+        if not os.path.exists(path):
+            raise FileNotFoundError(f'flags.recursive_feasibility needs the braking-distance coefficients {path} '
+                                    '(scripts/find_amax.py of the reference) or mpc.braking_dist.coeffs in the YAML')
+        co = np.load(path).astype(float).ravel()
+    n = (deg + 1) * (deg + 2) * (deg + 3) // 6
+    if deg > 5 or co.size != n:
+        raise ValueError(f'braking_dist: degree {deg} needs {n} coefficients (degree <= 5), got {co.size}')
+    return deg, co
+
+
+def stability_p_term(cfg, g=9.81):
+    """Terminal weight ``p_term`` of ``gen_model.py:121-147`` (upper bound of the stage cost over the braking manoeuvre).
+    ``r_tilde`` (``utils/stability.py:6-75``) is the largest ratio input cost / (dt^2 |T R e3 - g e3|^2 ) over the input box - the
+    reference solves its sympy expression with SLSQP from a random start; here a dense grid plus the same ratio in closed form.
+    NOTE the reference computes ``p_term`` into ``model.extra_WN`` but ``controller.set_ref`` fills ``WN`` with ``W[:nyN]``
+    (``controller.py:140-142``), so the weight that reaches acados for the fifth terminal output is ``Wv[0]``; ``set_ref`` here
+    does the same, and callers of ``set_ref_arrays`` choose the weight themselves."""
+    # gen_model.py:129-134 reads cfg.mpc.weights.vel / .att / .rates / .acc, which predate the weight SETS of default.yaml:36-48
+    # (the flag cannot be switched on with the shipped YAML); the set used while constraints are on stands in for them
+    w = cfg.mpc.weights if 'vel' in cfg.mpc.weights else cfg.mpc.weights.set_const_on
+    lim, m = cfg.robot.limits, cfg.mpc
+    dt = m.T / m.N
+    max_vel_error = (2 * cfg.ref.vref) ** 2 * max(w.vel)
+    max_att = np.array([lim.roll, lim.pitch, lim.wz])
+    max_att_error = float(max_att @ np.diag(list(w.att[:2]) + list(w.rates[2:])) @ max_att)
+    max_thrust_error = max(w.acc * (lim.gamma - g) ** 2, w.acc * g ** 2)
+    sc_max = max_vel_error + max_att_error + max_thrust_error
+    T, ph, th = np.meshgrid(np.linspace(0, lim.gamma, 81), np.linspace(-lim.roll, lim.roll, 41), np.linspace(-lim.pitch, lim.pitch, 41), indexing='ij')
+    Ut = np.stack([T * np.sin(th) * np.cos(ph), -T * np.sin(ph), T * np.cos(th) * np.cos(ph) - g], -1) * dt
+    num = w.acc * (T - g) ** 2 + w.att[0] * ph ** 2 + w.att[1] * th ** 2
+    den = (Ut ** 2).sum(-1)
+    r_tilde = float(np.max(np.where(den > 1e-9, num / np.maximum(den, 1e-9), 0.0)))
+    return max(r_tilde + max_vel_error, sc_max / m.stability.a_b_min ** 2 / dt ** 2)
+
+
 def props_allocation(motors, cf, ct):
     """(Gf, Gt) [3, 4] of ``quad_props.py:18-27``: propeller frames ``Rz(i pi / (n/2)) Ry(beta_i) Rx((-1)^i alpha_i)``, the
     allocation of a generically tilted multi-rotor (``utils/math.py:385-396``), both scaled by the force coefficient."""
@@ -50,6 +97,16 @@ class BatchedNmpc:
             raise NotImplementedError(f"mpc.model == '{cfg.mpc.model}' is not built (available: {sorted(MODEL_ID)})")
         self.model = cfg.mpc.model
         self.nyN = {'acc': 7, 'props': 12}.get(self.model, 4)   # quad_acc.py:15 / quad_props.py:15 / quad_rollpitchyawrate*.py:15
+        fl = cfg.get('flags', {})
+        # flags.recursive_feasibility / stability (gen_model.py:73-149): terminal rows lifted onto auxiliary nodes behind node N
+        # (csrc/term_lift.cuh).  `stability` only acts inside the recursive-feasibility branch, as in the reference.
+        self.lift = 0
+        if fl.get('enable_sdf', True) and fl.get('recursive_feasibility', False):
+            if self.model != 'att':
+                raise NotImplementedError("recursive feasibility and stability are implemented only for mpc.model == 'att' (gen_model.py:74)")
+            self.lift = 2 if fl.get('stability', False) else 1
+            if self.lift == 2:
+                self.nyN = 5                                    # + flag * v.v (gen_model.py:139-147)
         # stage dimensions: nx as the reference counts it, nxd as the device stores it ('props': 13 states + one pad entry that
         # stays zero - the QP's staging copies move 16-byte units, see model_att.cuh)
         self.nx, self.nxd, self.ny = (13, 14, 16) if self.model == 'props' else (NX, NX, NY)
@@ -67,12 +124,6 @@ class BatchedNmpc:
         lh, uh = cfg.h_bounds(self.sdf.max_df)
         # mission flags (gen_model.py:26-70): a row the reference would not add is kept with bounds that can never be
         # active, which leaves the optimum unchanged (slack 0, multiplier 0)
-        fl = cfg.get('flags', {})
-        for name in ('recursive_feasibility', 'stability'):
-            if fl.get(name, False):
-                # gen_model.py:69-142 changes the OCP for these (terminal SDF row dropped, braking-distance row, terminal FoV at the
-                # braking point, terminal velocity box, p_term cost): solving the plain OCP instead would be silently wrong
-                raise NotImplementedError(f"flags.{name} is not built: the terminal ingredients of gen_model.py:73-149 are missing")
         off = [not fl.get('enable_sdf', True) or not (cfg.sensor.hfov < 3.14),
                not fl.get('enable_sdf', True) or not fl.get('vfov_constraint', True),
                not fl.get('enable_sdf', True) or not fl.get('sdf_constraint', True)]
@@ -108,6 +159,20 @@ class BatchedNmpc:
         d.zl, d.Zl = (C.c_double * 3)(*zl), (C.c_double * 3)(*Zl)
         for k in range(self.N):
             d.dt[k] = float(self.dt[k])
+        if self.lift:
+            deg, co = braking_coeffs(cfg)
+            d.term_lift, d.brake_degree = self.lift, deg
+            d.brake_coeffs = (C.c_double * 56)(*co)
+            d.brake_bounds = (C.c_double * 2)(float(cfg.robot.size.xy), float(self.sdf.max_df))      # gen_model.py:116
+            sb = cfg.mpc.weights.get('slack_brake')
+            sb = None if isinstance(sb, str) else sb                # default.yaml:51 spells `None`, which YAML reads as a string
+            d.slack_brake = (C.c_double * 2)(*(sb if sb else (-1.0, 0.0)))                           # None: hard row
+            hl, vl = cfg.sensor.hfov * cfg.mpc.fov_ratio, cfg.sensor.vfov * cfg.mpc.fov_ratio
+            d.fov_term = (C.c_double * 2)(hl, vl if fl.get('vfov_constraint', True) else -1.0)
+            d.vlim = (C.c_double * 3)(float(lim.vx), float(lim.vy), float(lim.vz))
+            d.z_hard = float(cfg.b200.get('z_hard', 1e4))
+            self.p_term = stability_p_term(cfg, self.g) if self.lift == 2 else None
+        self.NI = self.N + self.lift                      # node stride of the library's own arrays (sdfnmpc_solver_horizon)
         self.handle = C.c_void_p()
         _lib.check(self.lib.sdfnmpc_solver_create(C.byref(self.handle), C.byref(d), self.sdf.handle), 'sdfnmpc_solver_create')
         # command clipping (controller.py:18-26)
@@ -354,29 +419,30 @@ class BatchedNmpc:
     def get_matrices(self):
         """controller.py:84-92 -> (x [B,N+1,10], u [B,N,4]) device tensors (copies)."""
         xb, ub, _, _ = self._state_ptrs()
-        x = self._view(xb, (self.B, self.N + 1, self.nxd), torch.float64)
-        return (x[:, :, :self.nx] if self.nxd != self.nx else x), self._view(ub, (self.B, self.N, NU), torch.float64)
+        x = self._view(xb, (self.B, self.NI + 1, self.nxd), torch.float64)[:, :self.N + 1]
+        return (x[:, :, :self.nx] if self.nxd != self.nx else x), self._view(ub, (self.B, self.NI, NU), torch.float64)[:, :self.N]
 
     def set_matrices(self, x, u):
         """Overwrite the SQP iterate (x [B,N+1,10], u [B,N,4]) - the batched form of the per-node ``solver.set(k, 'x'|'u', .)``
         calls of ``ocp.py:144-149``; used to warm-start from an external trajectory."""
         xb, ub, _, _ = self._state_ptrs()
-        self._view(xb, (self.B, self.N + 1, self.nxd), torch.float64, copy=False)[:, :, :self.nx].copy_(self._t(x, (self.B, self.N + 1, self.nx)))
-        self._view(ub, (self.B, self.N, NU), torch.float64, copy=False).copy_(self._t(u, (self.B, self.N, NU)))
+        self._view(xb, (self.B, self.NI + 1, self.nxd), torch.float64, copy=False)[:, :self.N + 1, :self.nx].copy_(self._t(x, (self.B, self.N + 1, self.nx)))
+        self._view(ub, (self.B, self.NI, NU), torch.float64, copy=False)[:, :self.N].copy_(self._t(u, (self.B, self.N, NU)))
         if self.x0 is None:
             self._x0[:, :self.nx] = self._t(x, (self.B, self.N + 1, self.nx))[:, 0]
             self.x0 = self._x0
 
     def get_multipliers(self):
-        """QP multipliers of the last step: lam_hard [B,N,8] (lbu, ubu), lam_soft [B,N+1,6] (lh, uh)."""
+        """QP multipliers of the last step: lam_hard [B,N,8] (lbu, ubu), lam_soft [B,N+1,6] (lh, uh).  With lifted terminal rows
+        (flags.recursive_feasibility) lam_soft has N + 1 + lift nodes: node N + 1 = [hfov_E, vfov_E, rec_feas], node N + 2 = velocity box."""
         _, _, lh, ls = self._state_ptrs()
-        return (self._view(lh, (self.B, self.N, 2 * NU), torch.float64), self._view(ls, (self.B, self.N + 1, 2 * NH), torch.float64))
+        return (self._view(lh, (self.B, self.NI, 2 * NU), torch.float64)[:, :self.N], self._view(ls, (self.B, self.NI + 1, 2 * NH), torch.float64))
 
     def get_diag(self):
         ptrs = [C.c_void_p() for _ in range(3)]
         _lib.check(self.lib.sdfnmpc_solver_diag(self.handle, *[C.byref(p) for p in ptrs]), 'solver_diag')
-        return (self._view(ptrs[0], (self.B, self.N + 1, NH), torch.float64), self._view(ptrs[1], (self.B, self.N + 1), torch.float32),
-                self._view(ptrs[2], (self.B, self.N + 1, 3), torch.float32))
+        return (self._view(ptrs[0], (self.B, self.NI + 1, NH), torch.float64), self._view(ptrs[1], (self.B, self.NI + 1), torch.float32)[:, :self.N + 1],
+                self._view(ptrs[2], (self.B, self.NI + 1, 3), torch.float32)[:, :self.N + 1])
 
     def get_u(self):
         return self.u0
@@ -409,7 +475,7 @@ class BatchedNmpc:
 
     def eval(self, k):
         """controller.py:125-130: SDF value at node k of the current solution, ignoring the flag."""
-        xb = self._view(self._state_ptrs()[0], (self.B, self.N + 1, self.nxd), torch.float64, copy=False)   # node k read in place
+        xb = self._view(self._state_ptrs()[0], (self.B, self.NI + 1, self.nxd), torch.float64, copy=False)   # node k read in place
         R = self.pose[:, 3:12].reshape(-1, 3, 3)
         c0 = torch.einsum('bji,bj->bi', R, xb[:, k, 0:3] - self.pose[:, 0:3]).to(torch.float32)
         if self._latent_dirty:

@@ -422,7 +422,7 @@ def test_full_size_properties(cuda_device):
         xg = one.plant_step(xg.clone(), one.get_u(), ocfg['dt'][0])
 
 
-@pytest.mark.parametrize('variant', ['N12', 'nonuniform_dt', 'shift1', 'h_at_node0'])
+@pytest.mark.parametrize('variant', ['N12', 'N15', 'N15_props', 'nonuniform_dt', 'shift1', 'h_at_node0'])
 def test_config_variants_match_oracle(variant, cuda_device):
     """Configuration options of the reference OCP other than the defaults: a different horizon (generic-N kernel path),
     the non-uniform time grid of ocp.py:21-27 and the iterate shift of ocp.py:152-156, each against the oracle."""
@@ -435,9 +435,11 @@ def test_config_variants_match_oracle(variant, cuda_device):
     net = synth.make_sdf_net(seed=0, **synth.ARCH_B, calibrated=True)
     cfg = Config()
     ocfg = rti.default_cfg()
-    if variant == 'N12':
-        cfg.mpc.N = 12
-        ocfg['N'] = 12
+    if variant == 'N15_props':         # odd horizon on the scalar solver (its per-warp workspace must stay 16-byte aligned)
+        cfg.mpc.model = 'props'
+        ocfg = rti.default_cfg('props')
+    if variant.startswith('N1'):
+        cfg.mpc.N = ocfg['N'] = int(variant[1:3])
     elif variant == 'nonuniform_dt':
         cfg.mpc.uniform_dt = False
     elif variant == 'shift1':
@@ -449,7 +451,7 @@ def test_config_variants_match_oracle(variant, cuda_device):
     assert len(ocfg['dt']) == cfg.mpc.N and abs(ocfg['dt'].sum() - cfg.mpc.T) < 1e-12
     if variant == 'nonuniform_dt':
         assert ocfg['dt'][0] == pytest.approx(0.01) and ocfg['dt'].max() > 0.07
-    prob, w = make_problem(B, ocfg)
+    prob, w = make_problem(B, ocfg, model=cfg.mpc.model)
     mpc = BatchedNmpc(cfg, net, B, cuda_device)
     mpc.set_sdf_flag(1.0)
     mpc.set_latent(w['latent'], w['W_p_Bo'], w['W_R_Bo'])
@@ -510,3 +512,76 @@ def test_mission_flags_match_oracle(variant, cuda_device):
     _, lam_s = mpc.get_multipliers()
     if variant == 'no_vfov':
         assert float(lam_s[:, :, [1, 4]].abs().max()) < 1e-6
+
+
+@pytest.mark.parametrize('stability,slack_brake', [(False, (100.0, 10.0)), (True, (100.0, 10.0)), (True, None)])
+def test_terminal_ingredients_match_oracle(stability, slack_brake, cuda_device):
+    """flags.recursive_feasibility / flags.stability (gen_model.py:73-149) through the C ABI: the terminal sdf row is replaced by
+    rec_feas, the FoV rows sit at the braking end point, stability adds the velocity box and the output flag * v.v.  The device
+    lifts those rows onto auxiliary nodes (csrc/term_lift.cuh) with an exact L1 penalty for the hard ones; the oracle states
+    them as full-width terminal rows, hard where the reference's are.  QP / RTI semantics unpinned (acados not installable)."""
+    from oracle import rti
+    from sdf_nmpc_b200 import synth
+    from sdf_nmpc_b200.config import Config
+    from sdf_nmpc_b200.nmpc import BatchedNmpc
+    B = 12
+    net = synth.make_sdf_net(seed=0, **synth.ARCH_B, calibrated=True)
+    ocfg = rti.default_cfg('att')
+    prob, w = make_problem(B, ocfg)
+    vlim = [1.5, 1.5, 1.0]
+    ocfg['term'] = dict(degree=4, coeffs=synth.braking_coeffs(4), slack_brake=slack_brake, stability=stability, vlim=vlim, vfov=True)
+    yrefN, WN = w['yrefN'], w['WN']
+    if stability:
+        WN = np.concatenate([WN, np.full((B, 1), 3.0)], 1)
+        yrefN = np.concatenate([yrefN, np.full((B, 1), 0.3)], 1)
+        prob = dict(prob, WN=WN, yrefN=yrefN)
+    cfg = Config()
+    cfg.flags.recursive_feasibility = True
+    cfg.flags.stability = stability
+    cfg.mpc.braking_dist = dict(degree=4, coeffs=[float(c) for c in synth.braking_coeffs(4)])
+    cfg.mpc.weights.slack_brake = list(slack_brake) if slack_brake else None
+    cfg.robot.limits.vx, cfg.robot.limits.vy, cfg.robot.limits.vz = vlim
+    mpc = BatchedNmpc(cfg, net, B, cuda_device)
+    N = mpc.N
+    assert mpc.NI == N + (2 if stability else 1) and mpc.nyN == (5 if stability else 4)
+    mpc.set_sdf_flag(1.0)
+    mpc.set_latent(w['latent'], w['W_p_Bo'], w['W_R_Bo'])
+    mpc.set_ref_arrays(w['yref'], w['W'], yrefN, WN, w['qd'])
+    xb, ub = rti.init_traj(prob['x0'], ocfg)
+    active = 0.0
+    for step in range(3):
+        mpc.set_x0(prob['x0'])
+        assert int(mpc.solve().max().item()) == 0
+        xb, ub, out = rti.rti_step(net, xb, ub, prob, ocfg)
+        assert np.all(out['status'] == 0) and int(mpc.status.abs().sum().item()) == 0
+        assert np.abs(mpc.get_u().cpu().numpy() - out['u0']).max() <= U_TOL, (step, np.abs(mpc.get_u().cpu().numpy() - out['u0']).max())
+        x, u = mpc.get_matrices()
+        assert x.shape == (B, N + 1, 10) and u.shape == (B, N, 4)
+        assert np.abs(x.cpu().numpy() - xb).max() <= 2e-4 and np.abs(u.cpu().numpy() - ub).max() <= 5e-4
+        # multipliers of the lifted rows: node N + 1 = [hfov_E, vfov_E, rec_feas]; the oracle orders them [rec_feas, hfov_E, vfov_E]
+        _, lam_s = mpc.get_multipliers()
+        lam_s = lam_s.cpu().numpy()
+        assert lam_s.shape == (B, mpc.NI + 1, 6)
+        assert np.abs(lam_s[:, N + 1, [2, 0, 1]] - out['lam_term_l'][:, :3]).max() < 1e-2
+        assert np.abs(lam_s[:, N + 1, [5, 3, 4]] - out['lam_term_u'][:, :3]).max() < 1e-2
+        active = max(active, out['lam_term_l'].max(), out['lam_term_u'].max())
+    assert active > 1.0          # the terminal rows do bind in this sample
+    # the flags change the problem: the plain OCP gives other controls
+    ocfg0 = rti.default_cfg('att')
+    prob0 = dict(prob, WN=w['WN'], yrefN=w['yrefN'])
+    xb0, ub0 = rti.init_traj(prob['x0'], ocfg0)
+    for step in range(3):
+        xb0, ub0, out0 = rti.rti_step(net, xb0, ub0, prob0, ocfg0)
+    assert np.abs(out0['u0'] - out['u0']).max() > 1e-4
+
+
+def test_terminal_ingredients_reject_other_models(cuda_device):
+    """gen_model.py:74 builds the braking rows from the 'att' state layout only; other models must refuse the flag loudly."""
+    from sdf_nmpc_b200 import synth
+    from sdf_nmpc_b200.config import Config
+    from sdf_nmpc_b200.nmpc import BatchedNmpc
+    cfg = Config()
+    cfg.mpc.model = 'acc'
+    cfg.flags.recursive_feasibility = True
+    with pytest.raises(NotImplementedError):
+        BatchedNmpc(cfg, synth.make_sdf_net(seed=0, **synth.ARCH_B, calibrated=True), 2, cuda_device)
