@@ -93,11 +93,24 @@ def test_encoder_from_archive_matches_packed_weights(data_dir, cuda_device):
     assert np.array_equal(a.encode(), b.encode())
 
 
-def test_unbuilt_flags_are_refused(cuda_device):
+def test_terminal_flags_follow_the_reference(cuda_device):
+    """gen_model.py:73-149: `stability` only acts inside the recursive-feasibility branch (alone it leaves the plain OCP), the branch
+    is stated for the 'att' layout only (gen_model.py:74 asserts), and it needs the braking-distance coefficients."""
     from sdf_nmpc_b200 import synth
     from sdf_nmpc_b200.config import Config
     from sdf_nmpc_b200.nmpc import BatchedNmpc
+    net = synth.make_sdf_net(seed=0, **synth.ARCH_B)
     cfg = Config()
     cfg.flags['stability'] = True
+    mpc = BatchedNmpc(cfg, net, 2, cuda_device)
+    assert mpc.lift == 0 and mpc.nyN == 4 and mpc.NI == mpc.N
+    cfg.flags['recursive_feasibility'] = True
+    cfg.mpc.braking_dist = dict(degree=4, coeff_file='does/not/exist.npy')
+    with pytest.raises(FileNotFoundError):
+        BatchedNmpc(cfg, net, 2, cuda_device)
+    cfg.mpc.braking_dist = dict(degree=4, coeffs=[0.0] * 34)       # degree 4 has 35 terms
+    with pytest.raises(ValueError):
+        BatchedNmpc(cfg, net, 2, cuda_device)
+    cfg.mpc.model = 'att_tau'
     with pytest.raises(NotImplementedError):
-        BatchedNmpc(cfg, synth.make_sdf_net(seed=0, **synth.ARCH_B), 2, cuda_device)
+        BatchedNmpc(cfg, net, 2, cuda_device)
