@@ -432,9 +432,10 @@ def run_ours(args, rank, local_rank, world):
     if world == 1 and not args.no_sweep:
         sweep = sdf_microbench(net, peaks)
         enc_sweep = encoder_microbench(peaks)
-    latency = {}
+    latency, term_var = {}, None
     if world == 1 and not args.no_sweep:
         latency = latency_bench(net, cfg)
+        term_var = terminal_variant_bench(net, w, dev, B, torch.from_numpy(w['x0']).to(dev))
     cpu_v, cpu_info, cpu_np = (None, None, None)
     if world == 1 and not args.no_cpu:
         cpu_v, cpu_info = cpu_port_throughput(16, 20, 'cxx', os.cpu_count() or 1)      # ~25 core-seconds of CPU work
@@ -486,6 +487,8 @@ def run_ours(args, rank, local_rank, world):
         line['encoder_microbench'] = enc_sweep
     if latency:
         line['latency'] = latency
+    if term_var:
+        line.setdefault('extra', {})['terminal_ingredients'] = term_var
     if cpu_v is not None:
         line['cpu_baseline'] = dict(value=cpu_v, unit=UNIT, cores=cpu_info['workers'], kind='port',
                                     sample=f"{cpu_info['workers']} processes x {cpu_info['per_worker']} instances x {cpu_info['steps']} closed-loop "
@@ -570,6 +573,50 @@ class _Ref:
     def __init__(self, p, q, v, wz, wts):
         self.p, self.q, self.v, self.wz = p, q, v, wz
         self.Wp, self.Wv, self.Wq, self.Ww, self.Wa = wts['pos'], wts['vel'], wts['att'], wts['rates'], wts['acc']
+
+
+def terminal_variant_bench(net, w, dev, B, x0, steps=10):
+    """The same closed-loop step with flags.recursive_feasibility + flags.stability on (gen_model.py:73-149): terminal rows lifted onto
+    two auxiliary nodes (csrc/term_lift.cuh), 22-node OCP on the scalar Riccati kernel.  Synthetic braking-distance polynomial."""
+    import numpy as np
+    import torch
+    from sdf_nmpc_b200 import synth
+    from sdf_nmpc_b200.config import Config
+    from sdf_nmpc_b200.nmpc import BatchedNmpc
+    cfg = Config()
+    cfg.flags.recursive_feasibility = True
+    cfg.flags.stability = True
+    cfg.mpc.braking_dist = dict(degree=4, coeffs=[float(c) for c in synth.braking_coeffs(4)])
+    cfg.mpc.weights.slack_brake = [100.0, 10.0]
+    mpc = BatchedNmpc(cfg, net, B, dev)
+    mpc.set_sdf_flag(1.0)
+    mpc.set_latent(w['latent'], w['W_p_Bo'], w['W_R_Bo'])
+    yrefN = np.concatenate([w['yrefN'], np.zeros((B, 1))], 1)
+    WN = np.concatenate([w['WN'], np.full((B, 1), float(cfg.mpc.weights.set_const_on.vel[0]))], 1)     # controller.py:140-142: WN = W[:nyN]
+    mpc.set_ref_arrays(w['yref'], w['W'], yrefN, WN, w['qd'])
+    x = x0.clone()
+    dt = float(mpc.dt[0])
+
+    def step():
+        mpc.set_x0(x)
+        mpc.solve()
+        mpc.plant_step(x, mpc.u0, dt)
+
+    for _ in range(3):
+        step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    out = dict(value=B / (ms * 1e-3), unit=UNIT, ms_per_step=ms, steps=steps, status_ok=int((mpc.status == 0).sum().item()), instances=B,
+               workload='configs[2] instances with flags.recursive_feasibility + stability (22-node lifted OCP, scalar Riccati kernel)')
+    del mpc
+    torch.cuda.empty_cache()
+    return out
 
 
 def latency_bench(net, cfg, steps=200):
