@@ -612,8 +612,14 @@ def terminal_variant_bench(net, w, dev, B, x0, steps=10):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
+    mpc.timing_begin(3)            # per-kernel split of three more steps (the term-lift kernel is inside the sdf segment)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    kms, ksteps = mpc.timing_end()
     out = dict(value=B / (ms * 1e-3), unit=UNIT, ms_per_step=ms, steps=steps, status_ok=int((mpc.status == 0).sum().item()), instances=B,
-               workload='configs[2] instances with flags.recursive_feasibility + stability (22-node lifted OCP, scalar Riccati kernel)')
+               qp_iters_mean=float(mpc.qp_iters.double().mean().item()), kernels_ms={k: v / max(ksteps, 1) for k, v in kms.items()},
+               workload='configs[2] instances with flags.recursive_feasibility + stability (22-node lifted OCP on the tensor-pipe QP kernel)')
     del mpc
     torch.cuda.empty_cache()
     return out

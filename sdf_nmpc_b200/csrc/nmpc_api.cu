@@ -21,7 +21,15 @@ using Shape = QpShape<NX, NU, NY, NH>;        // A/B builds: the scalar statemen
 #else
 using Shape = QpMmaShape;                     // product: tensor-core sweeps (qp_mma.cuh)
 #endif
-using ScalarShape = QpShape<NX, NU, NY, NH>;  // lifted terminal rows (term_lift.cuh) run on the scalar solver
+using ScalarShape = QpShape<NX, NU, NY, NH>;
+// lifted terminal rows (term_lift.cuh): tensor-core solver with per-node rows (qp_solve_mma<0, true>); -DSDFNMPC_LIFT_SCALAR
+// puts them on the scalar solver (the statement the host emulation checks against the oracle) for A/B runs
+#if defined(SDFNMPC_LIFT_SCALAR) || defined(SDFNMPC_QP_SCALAR)
+constexpr bool LIFT_SCALAR = true;
+#else
+constexpr bool LIFT_SCALAR = false;
+#endif
+using LiftShape = std::conditional<LIFT_SCALAR, ScalarShape, Shape>::type;
 // model 'props' (13 states + one pad entry, 16 outputs): the scalar solver instantiated for its shape
 using PD = ModelDims<MODEL_PROPS>;
 using PropsProb = QpProb<PD::NX, PD::NU, PD::NY, PD::NH>;
@@ -108,7 +116,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32, QP_MIN_CTAS) nmpc_qp_kernel(
     SolverConst sc, int B, QpBatch q) {
     constexpr int NX = PROPS ? PD::NX : ::NX, NW = PROPS ? PD::NW : ::NW, NY = PROPS ? PD::NY : ::NY;
     using Prob = typename std::conditional<PROPS, PropsProb, ::Prob>::type;
-    using Shape = typename std::conditional<PROPS, PropsShape, typename std::conditional<LIFT, ScalarShape, ::Shape>::type>::type;
+    using Shape = typename std::conditional<PROPS, PropsShape, typename std::conditional<LIFT && LIFT_SCALAR, ScalarShape, ::Shape>::type>::type;
     extern __shared__ double sm_all[];
     __shared__ SolverConst scs;
     if (threadIdx.x == 0) scs = sc;
@@ -169,8 +177,8 @@ __global__ void __launch_bounds__(QP_WARPS * 32, QP_MIN_CTAS) nmpc_qp_kernel(
 #if defined(SDFNMPC_QP_SCALAR)
     qp_solve_instance<NX, NU, NY, NH, NFIX>(L, P, sm_all + (size_t)warp * Shape::smem_doubles(N));
 #else
-    if constexpr (PROPS || LIFT) qp_solve_instance<NX, NU, NY, NH, NFIX>(L, P, sm_all + (size_t)warp * Shape::smem_doubles(N));
-    else qp_solve_mma<NFIX>(L, P, sm_all + (size_t)warp * Shape::smem_doubles(N));
+    if constexpr (PROPS || (LIFT && LIFT_SCALAR)) qp_solve_instance<NX, NU, NY, NH, NFIX>(L, P, sm_all + (size_t)warp * Shape::smem_doubles(N));
+    else qp_solve_mma<NFIX, LIFT>(L, P, sm_all + (size_t)warp * Shape::smem_doubles(N));
 #endif
     __syncwarp();
     }
@@ -242,12 +250,13 @@ __global__ void nmpc_cmd_props_kernel(double wp_max, int B, const double* __rest
 __global__ void nmpc_term_lift_kernel(ModelConst mc, TermConst tc, int N, int NR, int B, const double* __restrict__ pose,
                                       const double* __restrict__ flag, double max_df, const float* __restrict__ sdf_d,
                                       const float* __restrict__ sdf_g, double* __restrict__ xbar, double* __restrict__ AB,
-                                      double* __restrict__ bdyn, double* __restrict__ C, double* __restrict__ hval) {
+                                      double* __restrict__ bdyn, double* __restrict__ C, double* __restrict__ hval, double* __restrict__ ABt) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     term_lift_instance(mc, tc, N, NR, pose + (size_t)b * 12, flag[b], max_df, sdf_d[(size_t)b * (N + 1) + NR],
                        sdf_g + ((size_t)b * (N + 1) + NR) * 3, xbar + (size_t)b * (N + 1) * NX, AB + (size_t)b * N * NX * NW,
-                       bdyn + (size_t)b * N * NX, C + (size_t)b * (N + 1) * NH * NW, hval + (size_t)b * (N + 1) * NH);
+                       bdyn + (size_t)b * N * NX, C + (size_t)b * (N + 1) * NH * NW, hval + (size_t)b * (N + 1) * NH,
+                       ABt ? ABt + (size_t)b * N * 192 : nullptr);
 }
 
 extern "C" int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver_desc* d, sdfnmpc_sdf_t sdf) {
@@ -288,7 +297,7 @@ extern "C" int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver
     for (int i = 0; i < 4; ++i) { sc.cmd_min[i] = cmin[i]; sc.cmd_max[i] = cmax[i]; }
     const size_t B = (size_t)h->cap, N = (size_t)sc.N, N1 = N + 1;
     const size_t NX = (size_t)h->nx, NW = (size_t)h->nw, NY = (size_t)h->ny;
-    h->work_per_inst = props ? PropsShape::work_doubles(sc.N) : (lift ? ScalarShape::work_doubles(sc.N) : Shape::work_doubles(sc.N));
+    h->work_per_inst = props ? PropsShape::work_doubles(sc.N) : (lift ? LiftShape::work_doubles(sc.N) : Shape::work_doubles(sc.N));
     cudaError_t e = cudaSuccess;
     auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
     alloc((void**)&h->dt, N * sizeof(double));
@@ -299,7 +308,7 @@ extern "C" int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver
 #endif
     alloc((void**)&h->AB, B * N * NX * NW * sizeof(double));
 #if !defined(SDFNMPC_QP_SCALAR)
-    if (!props && !lift) alloc((void**)&h->ABt, B * N * 192 * sizeof(double));
+    if (!props && !(lift && LIFT_SCALAR)) alloc((void**)&h->ABt, B * N * 192 * sizeof(double));
 #endif
     alloc((void**)&h->bdyn, B * N * NX * sizeof(double));
     alloc((void**)&h->J, B * N1 * NY * NW * sizeof(double));
@@ -310,7 +319,7 @@ extern "C" int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver
     alloc((void**)&h->sdf_d, B * N1 * sizeof(float));
     alloc((void**)&h->sdf_g, B * N1 * 3 * sizeof(float));
     // the QP kernel runs as persistent warps: as many as fit the device at once, each owning one block of scratch
-    h->qp_smem = (size_t)QP_WARPS * (props ? PropsShape::smem_doubles(sc.N) : (lift ? ScalarShape::smem_doubles(sc.N) : Shape::smem_doubles(sc.N))) * sizeof(double);
+    h->qp_smem = (size_t)QP_WARPS * (props ? PropsShape::smem_doubles(sc.N) : (lift ? LiftShape::smem_doubles(sc.N) : Shape::smem_doubles(sc.N))) * sizeof(double);
 #if defined(QP_CARVEOUT)
     if (e == cudaSuccess) e = cudaFuncSetAttribute(nmpc_qp_kernel<20>, cudaFuncAttributePreferredSharedMemoryCarveout, QP_CARVEOUT);
 #endif
@@ -431,7 +440,9 @@ extern "C" int sdfnmpc_solver_rti_step(sdfnmpc_solver_t h, int32_t B, const doub
     if (tm) cudaEventRecord(ev[0], st);
     LinIn in{h->xbar, h->ubar, yref, yrefN, qd, pose, flag, h->dt, h->sc.nyN, x0};
     in.n_real = h->sc.n_real; in.stab = h->sc.stab;
-    LinOut lo{h->AB, h->bdyn, h->J, h->yres, h->C, h->hval, h->qpts, h->ABt};
+    // lifted rows on the tensor-core solver: the stages of the OCP go straight to the operand layout, `AB` only holds the
+    // auxiliary stages term_lift writes (and re-lays into ABt)
+    LinOut lo{(h->tc.n_lift && h->ABt) ? nullptr : h->AB, h->bdyn, h->J, h->yres, h->C, h->hval, h->qpts, h->ABt};
     const long long total = (long long)B * (N + 1) * h->nw;
     const unsigned lin_grid = (unsigned)((total + 127) / 128);
     if (h->sc.model == MODEL_ATT) nmpc_linearize_kernel<MODEL_ATT><<<lin_grid, 128, 0, st>>>(h->sc.mc, N, B, in, lo);
@@ -445,7 +456,7 @@ extern "C" int sdfnmpc_solver_rti_step(sdfnmpc_solver_t h, int32_t B, const doub
     const int lift = h->tc.n_lift;
     if (lift) {
         nmpc_term_lift_kernel<<<(B + 127) / 128, 128, 0, st>>>(h->sc.mc, h->tc, N, h->sc.n_real, B, pose, flag, (double)h->sdf->net.max_df,
-                                                             h->sdf_d, h->sdf_g, h->xbar, h->AB, h->bdyn, h->C, h->hval);
+                                                             h->sdf_d, h->sdf_g, h->xbar, h->AB, h->bdyn, h->C, h->hval, h->ABt);
         count_launch();
         SDF_CUDA_CHECK(cudaGetLastError());
     }

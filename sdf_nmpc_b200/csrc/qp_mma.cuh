@@ -133,7 +133,9 @@ __device__ __forceinline__ void pipelined_stages(int n, Ld&& ld, St&& stage) {
 
 }  // namespace qpdetail
 
-template <int NFIX = 0>
+// LIFT: terminal rows lifted onto auxiliary nodes behind node P.n_real (term_lift.cuh): per-node bounds / slack weights P.nlh ...
+// P.nZs, cost rows and state regularisation end at node n_real.  false compiles to the plain OCP with no trace of it.
+template <int NFIX = 0, bool LIFT = false>
 __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, double* sm) {
     using namespace qpdetail;
     using S = QpMmaShape;
@@ -141,6 +143,7 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
     constexpr int HC0 = NU;                       // position block of the constraint rows = first three states
     const int N = NFIX > 0 ? NFIX : P.N;
     const int k0 = P.k0, KP = S::kp(N);
+    const int NR = LIFT ? P.n_real : N;          // terminal node of the OCP
     const int lane = L.lane, g_ = lane >> 2, q_ = lane & 3;
     const int ncomp = N * 2 * NU + 2 * (N + 1 - k0) * 2 * NH;
     constexpr unsigned FULL = 0xffffffffu;
@@ -176,7 +179,11 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
 #endif
 
     auto scale = [&](int k) { return k < N ? P.dt[k] : 1.0; };
-    auto wrow = [&](int k, int r) { return k < N ? P.W[k * NY + r] : (r < P.nyN ? P.WN[r] : 0.0); };
+    auto wrow = [&](int k, int r) { return k < NR ? P.W[k * NY + r] : ((k == NR && r < P.nyN) ? P.WN[r] : 0.0); };
+    auto lh_ = [&](int kk, int r) { return LIFT ? P.nlh[kk * NH + r] : P.lh[r]; };
+    auto uh_ = [&](int kk, int r) { return LIFT ? P.nuh[kk * NH + r] : P.uh[r]; };
+    auto zs_ = [&](int kk, int r) { return LIFT ? P.nzs[kk * NH + r] : P.zs[r]; };
+    auto Zs_ = [&](int kk, int r) { return LIFT ? P.nZs[kk * NH + r] : P.Zs[r]; };
     auto c_pos = [&](int kk, int r, int c) { return cpos[(kk * NH + r) * 3 + c]; };
     // position -> index into w = [u; x] (14 = affine, 15 = pad)
     auto widx = [](int pos) { return pos < 8 ? NU + pos : ((pos & 1) ? (pos - 9) >> 1 : (pos == 8 ? NU + 8 : (pos == 10 ? NU + 9 : (pos == 12 ? 14 : 15)))); };
@@ -201,7 +208,7 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
     // =====================================================================================================
     const bool sdf_cost = P.sdf_cost_w > 0.0;     // the cost row also needs the SDF at node 0
     QM_LANES(k, N + 1) {
-        if (k >= (sdf_cost ? 0 : k0)) {
+        if (k >= (sdf_cost ? 0 : k0) && k <= NR) {
             const double* R = P.pose + 3;
             const double gx = P.sdf_g[k * 3 + 0], gy = P.sdf_g[k * 3 + 1], gz = P.sdf_g[k * 3 + 2];
             double* Cr = P.C + ((size_t)k * NH + (NH - 1)) * NW;
@@ -251,7 +258,7 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
             Acc2 H[2][2];
             const double lmk = P.lm * scale(k);
             double cr = 0.0, cJ[3] = {0.0, 0.0, 0.0}, wk = 0.0;
-            if (sdf_cost && k < N) {       // optional cost row r = (1 - 0.5 d)^4, position block only (gen_model.py:65-66)
+            if (sdf_cost && k < NR) {       // optional cost row r = (1 - 0.5 d)^4, position block only (gen_model.py:65-66)
                 const double qq = 1.0 - 0.5 * P.hval[k * NH + (NH - 1)];
                 const double* Cr = P.C + ((size_t)k * NH + (NH - 1)) * NW;
                 cr = qq * qq * qq * qq;
@@ -261,7 +268,8 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 const int row = 8 * (e >> 2) + g_, col = 8 * ((e >> 1) & 1) + 2 * q_ + (e & 1);
-                double v = (row == col && row != 12 && row != 14) ? lmk : 0.0;
+                // auxiliary nodes (LIFT): inputs only (positions 9, 11, 13, 15), their state is not regularised
+                double v = (row == col && row != 12 && row != 14 && (!LIFT || k <= NR || (row >= 9 && (row & 1)))) ? lmk : 0.0;
                 if (sdf_cost) {
                     const double jr = row == 0 ? cJ[0] : (row == 1 ? cJ[1] : cJ[2]), jc = col == 0 ? cJ[0] : (col == 1 ? cJ[1] : cJ[2]);
                     if (row < 3 && col < 3) v += wk * jr * jc;
@@ -312,7 +320,7 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
     auto soft_d = [&](int kk, int a) {
         const int r = a < NH ? a : a - NH;
         const double hv = P.hval[kk * NH + r];
-        return a < NH ? P.lh[r] - hv : hv - P.uh[r];
+        return a < NH ? lh_(kk, r) - hv : hv - uh_(kk, r);
     };
 #define QM_LD(p_) __ldcg(p_)
 #define QM_ST(p_, v_) __stcg(p_, v_)
@@ -364,7 +372,7 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
             const int r = a < NH ? a : a - NH;
             double t = 1.0, l = 1.0, m = 1.0, s0 = SDFNMPC_QP_S0;
             if (kk >= k0) {
-                const double z = P.zs[r] * scale(kk), Z = P.Zs[r] * scale(kk);
+                const double z = zs_(kk, r) * scale(kk), Z = Zs_(kk, r) * scale(kk);
                 double cw = 0.0;
                 for (int c = 0; c < 3; ++c) cw += c_pos(kk, r, c) * Wsm[(HC0 + c) * KP + kk];
                 const double gw = a < NH ? cw : -cw;
@@ -511,7 +519,7 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
                     for (int r = 0; r < NH; ++r) {
                         const double c0 = c_pos(kk, r, 0), c1 = c_pos(kk, r, 1), c2 = c_pos(kk, r, 2);
                         const double cw = c0 * Wsm[(HC0 + 0) * KP + kk] + c1 * Wsm[(HC0 + 1) * KP + kk] + c2 * Wsm[(HC0 + 2) * KP + kk];
-                        const double z = P.zs[r] * scale(kk), Z = P.Zs[r] * scale(kk);
+                        const double z = zs_(kk, r) * scale(kk), Z = Zs_(kk, r) * scale(kk);
                         const double hv = P.hval[kk * NH + r];
                         double thn = 0.0, cn = 0.0;
 #pragma unroll
@@ -522,7 +530,7 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
                             const double s_ = QM_TB_LD(sb + (4 * NU + 4 * NH + a) * KP), m_ = QM_TB_LD(sb + (4 * NU + 6 * NH + a) * KP);
                             const double ct = pass == 0 ? 0.0 : tau - prod[(2 * NU + a) * KP + kk];
                             const double cs = pass == 0 ? 0.0 : tau - prod[(2 * NU + 2 * NH + a) * KP + kk];
-                            const double d_ = side == 0 ? P.lh[r] - hv : hv - P.uh[r];
+                            const double d_ = side == 0 ? lh_(kk, r) - hv : hv - uh_(kk, r);
                             const SoftEval ev = soft_eval(t_, l_, s_, m_, sgn * cw, d_, z, Z, ct, cs);
                             thn += ev.Tht;
                             cn += sgn * ev.coef;
@@ -575,7 +583,7 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
                     for (int r = 0; r < NH; ++r) {
                         const double c0 = c_pos(kk, r, 0), c1 = c_pos(kk, r, 1), c2 = c_pos(kk, r, 2);
                         const double cw = c0 * Wsm[(HC0 + 0) * KP + kk] + c1 * Wsm[(HC0 + 1) * KP + kk] + c2 * Wsm[(HC0 + 2) * KP + kk];
-                        const double z = P.zs[r] * scale(kk), Z = P.Zs[r] * scale(kk);
+                        const double z = zs_(kk, r) * scale(kk), Z = Zs_(kk, r) * scale(kk);
                         double thn = 0.0, cn = 0.0;
 #pragma unroll
                         for (int side = 0; side < 2; ++side) {
@@ -916,7 +924,7 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
                         const double c0 = c_pos(kk, r, 0), c1 = c_pos(kk, r, 1), c2 = c_pos(kk, r, 2);
                         const double cw = c0 * Wsm[(HC0 + 0) * KP + kk] + c1 * Wsm[(HC0 + 1) * KP + kk] + c2 * Wsm[(HC0 + 2) * KP + kk];
                         const double cd = c0 * dW[(HC0 + 0) * KP + kk] + c1 * dW[(HC0 + 1) * KP + kk] + c2 * dW[(HC0 + 2) * KP + kk];
-                        const double z = P.zs[r] * scale(kk), Z = P.Zs[r] * scale(kk);
+                        const double z = zs_(kk, r) * scale(kk), Z = Zs_(kk, r) * scale(kk);
                         const double hv = P.hval[kk * NH + r];
 #pragma unroll
                         for (int side = 0; side < 2; ++side) {
@@ -926,7 +934,7 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
                             const double s_ = QM_TB_LD(sb + (4 * NU + 4 * NH + a) * KP), m_ = QM_TB_LD(sb + (4 * NU + 6 * NH + a) * KP);
                             const double ct = pass == 0 ? 0.0 : tau - prod[(2 * NU + a) * KP + kk];
                             const double cs = pass == 0 ? 0.0 : tau - prod[(2 * NU + 2 * NH + a) * KP + kk];
-                            const double d_ = side == 0 ? P.lh[r] - hv : hv - P.uh[r];
+                            const double d_ = side == 0 ? lh_(kk, r) - hv : hv - uh_(kk, r);
                             const SoftEval ev = soft_eval(t_, l_, s_, m_, sgn * cw, d_, z, Z, ct, cs);
                             const double kap = ct - l_ * t_, nu = cs - m_ * s_;
                             const double gd = sgn * cd;
@@ -978,7 +986,7 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
                         const double c0 = c_pos(kk, r, 0), c1 = c_pos(kk, r, 1), c2 = c_pos(kk, r, 2);
                         const double cw = c0 * Wsm[(HC0 + 0) * KP + kk] + c1 * Wsm[(HC0 + 1) * KP + kk] + c2 * Wsm[(HC0 + 2) * KP + kk];
                         const double cd = c0 * dW[(HC0 + 0) * KP + kk] + c1 * dW[(HC0 + 1) * KP + kk] + c2 * dW[(HC0 + 2) * KP + kk];
-                        const double z = P.zs[r] * scale(kk), Z = P.Zs[r] * scale(kk);
+                        const double z = zs_(kk, r) * scale(kk), Z = Zs_(kk, r) * scale(kk);
 #pragma unroll
                         for (int side = 0; side < 2; ++side) {
                             const int a = side * NH + r;

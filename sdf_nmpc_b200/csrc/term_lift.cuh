@@ -15,6 +15,7 @@
 // into  lh <= h + grad h . dx_N <= uh.  Hard rows use the exact L1 penalty (slack weight `z_hard` far above any multiplier).
 #pragma once
 #include "model_att.cuh"
+#include "linearize_core.cuh"   // mma_wpos
 
 namespace sdfnmpc {
 
@@ -43,7 +44,8 @@ SDF_HD T term_poly3(const TermConst& tc, const T* v) {
 // Pointers are offset to the instance; AB is [N][NX][NW] with columns [u; x].  sdf_d / sdf_g: network value and gradient (camera
 // frame) at node n_real.
 SDF_HD void term_lift_instance(const ModelConst& mc, const TermConst& tc, int N, int NR, const double* pose, double flag, double max_df,
-                               float sdf_d, const float* sdf_g, double* xbar, double* AB, double* bdyn, double* C, double* hval) {
+                               float sdf_d, const float* sdf_g, double* xbar, double* AB, double* bdyn, double* C, double* hval,
+                               double* ABt = nullptr) {
     constexpr int NX = ATT_NX, NU = ATT_NU, NW = ATT_NW, NH = ATT_NH;
     const double* x = xbar + (size_t)NR * NX;
     double* A1 = AB + (size_t)NR * NX * NW;
@@ -96,6 +98,20 @@ SDF_HD void term_lift_instance(const ModelConst& mc, const TermConst& tc, int N,
         x2[3] = 1.0; x2[4] = 0.0; x2[5] = 0.0; x2[6] = 0.0;
         x2[7] = 0.0; x2[8] = 0.0; x2[9] = 0.0;
         unit_rows(NR + 2, vv);
+    }
+    // the same stages in the operand layout of the tensor-core sweeps (LinOut::ABt: [16 positions][12 slots], affine position 12
+    // = zero defect and the 1 that carries the affine entry, pad position 14 zero)
+    if (ABt) {
+        for (int k = NR; k < N && k < NR + tc.n_lift; ++k) {
+            const double* A = AB + (size_t)k * NX * NW;
+            double* T = ABt + (size_t)k * 192;
+            for (int dir = 0; dir < NW; ++dir) {
+                double* row = T + mma_wpos(dir) * 12;
+                for (int i = 0; i < NX; ++i) row[i] = A[i * NW + dir];
+                row[10] = 0.0; row[11] = 0.0;
+            }
+            for (int i = 0; i < 12; ++i) { T[12 * 12 + i] = i == 10 ? 1.0 : 0.0; T[14 * 12 + i] = 0.0; }
+        }
     }
 }
 
