@@ -246,7 +246,8 @@ __global__ void nmpc_cmd_props_kernel(double wp_max, int B, const double* __rest
     if (i < B * NU) cmd[i] = fmin(fmax(u[i] * wp_max, 0.0), wp_max);
 }
 
-// auxiliary stages / nodes of the lifted terminal rows: one thread per instance (ten dual-number evaluations of two FoV rows)
+// auxiliary stages / nodes of the lifted terminal rows: one thread per instance (ten dual-number evaluations of two FoV rows),
+// launched as one-warp CTAs so that 4096 instances spread over 128 SMs instead of 32
 __global__ void nmpc_term_lift_kernel(ModelConst mc, TermConst tc, int N, int NR, int B, const double* __restrict__ pose,
                                       const double* __restrict__ flag, double max_df, const float* __restrict__ sdf_d,
                                       const float* __restrict__ sdf_g, double* __restrict__ xbar, double* __restrict__ AB,
@@ -463,7 +464,7 @@ extern "C" int sdfnmpc_solver_rti_step(sdfnmpc_solver_t h, int32_t B, const doub
     if (int rc = sdfnmpc_sdf_eval(h->sdf, h->qpts, nullptr, N + 1, (int64_t)B * (N + 1), h->sdf_d, h->sdf_g, stream)) return rc;
     const int lift = h->tc.n_lift;
     if (lift) {
-        nmpc_term_lift_kernel<<<(B + 127) / 128, 128, 0, st>>>(h->sc.mc, h->tc, N, h->sc.n_real, B, pose, flag, (double)h->sdf->net.max_df,
+        nmpc_term_lift_kernel<<<(B + 31) / 32, 32, 0, st>>>(h->sc.mc, h->tc, N, h->sc.n_real, B, pose, flag, (double)h->sdf->net.max_df,
                                                              h->sdf_d, h->sdf_g, h->xbar, h->AB, h->bdyn, h->C, h->hval, h->ABt);
         count_launch();
         SDF_CUDA_CHECK(cudaGetLastError());
