@@ -114,3 +114,49 @@ def test_terminal_flags_follow_the_reference(cuda_device):
     cfg.mpc.model = 'att_tau'
     with pytest.raises(NotImplementedError):
         BatchedNmpc(cfg, net, 2, cuda_device)
+
+
+def test_single_instance_facade_with_terminal_flags(cuda_device):
+    """The reference's call sequence with flags.recursive_feasibility + stability on: ``set_ref`` fills the five terminal outputs /
+    weights with ``y[:nyN]`` / ``W[:nyN]`` (controller.py:140-142), the CUDA-graph replay includes the term-lift kernel, and the
+    facade gives the controls of the batched solver fed with the same arrays."""
+    import torch
+    from sdf_nmpc_b200 import synth
+    from sdf_nmpc_b200.config import Config
+    from sdf_nmpc_b200.nmpc import BatchedNmpc, Nmpc
+    net = synth.make_sdf_net(seed=0, **synth.ARCH_B, calibrated=True)
+    cfg = Config()
+    cfg.flags.recursive_feasibility = True
+    cfg.flags.stability = True
+    cfg.mpc.braking_dist = dict(degree=4, coeffs=[float(c) for c in synth.braking_coeffs(4)])
+    cfg.mpc.weights.slack_brake = [100.0, 10.0]
+    mpc = Nmpc(cfg, sdf_net=net, device=cuda_device)
+    ref = BatchedNmpc(cfg, net, 1, cuda_device)
+    assert mpc._b.nyN == 5 and mpc._b.NI == mpc.N + 2
+    latent = synth.latent(seed=2)[None]
+    x0 = np.array([0, 0, 2, 1, 0, 0, 0, 1.5, 0.2, 0], float)
+    vref, dt = np.array([3.0, 0.5, 0.0]), 0.075
+    for m in (mpc, ref):
+        m.set_sdf_flag(True)
+    mpc.set_latent(latent, x0[:3], np.eye(3))
+    ref.set_latent(latent, x0[None, :3], np.eye(3)[None])
+    N = mpc.N
+    yref = np.zeros((1, N, 11)); W = np.zeros((1, N, 11)); qd = np.zeros((1, N + 1, 4)); qd[..., 0] = 1
+    for k in range(N):
+        yref[0, k, 0:3] = x0[:3] + vref * k * dt; yref[0, k, 4:7] = vref
+        W[0, k] = [0, 0, 5, 10, 3, 3, 3, 50, 50, 3, 0.05]
+    # terminal: y[:5] = [p, q_e3, v_x] and W[:5] = [Wp, Wq_e3, Wv_x] - what controller.py:140-142 hands to acados
+    yN = np.concatenate([x0[:3] + vref * N * dt, [0.0, vref[0]]])[None]
+    WN = np.array([[0, 0, 5, 10.0, 3.0]])
+    ref.set_ref_arrays(yref, W, yN, WN, qd)
+    for step in range(3):                      # eager, graph capture, graph replay
+        mpc.set_x0(x0)
+        for k in range(N + 1):
+            mpc.set_ref(Ref(x0[:3] + vref * k * dt, np.array([1.0, 0, 0, 0]), vref, 0.0), k)
+        assert mpc.solve() == 0
+        ref.set_x0(x0[None])
+        assert int(ref.solve().max().item()) == 0
+        assert np.abs(mpc.get_u() - ref.get_u().cpu().numpy()[0]).max() <= 1e-9, step
+    x, u = mpc.get_matrices()
+    assert x.shape == (N + 1, 10) and u.shape == (N, 4)
+    assert len(mpc.get_openloop_traj()) == N + 1
