@@ -37,6 +37,10 @@ extern "C" {
 const char* sdfnmpc_version(void);
 /* number of kernels this library has launched since load (all handles) */
 uint64_t sdfnmpc_launch_count(void);
+/* sizeof of the descriptor structs below as this build sees them, for bindings that restate them (ctypes, cgo, JNI): 0 sdf_desc,
+ * 1 solver_desc, 2 encoder_desc, 3 encoder_weights, 4 decoder_desc, 5 decoder_weights; anything else -1.  A binding whose own
+ * layout differs must refuse to call the create functions. */
+int32_t sdfnmpc_sizeof(int32_t which);
 
 /* ------------------------------------------------------------------ neural SDF ---------- */
 typedef struct sdfnmpc_sdf* sdfnmpc_sdf_t;

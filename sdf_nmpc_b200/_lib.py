@@ -69,7 +69,7 @@ class DecoderWeights(C.Structure):
 CASADI_COMPANIONS = ('', '_alloc_mem', '_init_mem', '_free_mem', '_checkout', '_release', '_incref', '_decref', '_n_in',
                      '_n_out', '_default_in', '_name_in', '_name_out', '_sparsity_in', '_sparsity_out', '_work')
 
-EXPORTS = (['sdfnmpc_version', 'sdfnmpc_launch_count', 'sdfnmpc_sdf_create', 'sdfnmpc_sdf_destroy',
+EXPORTS = (['sdfnmpc_version', 'sdfnmpc_launch_count', 'sdfnmpc_sizeof', 'sdfnmpc_sdf_create', 'sdfnmpc_sdf_destroy',
             'sdfnmpc_sdf_set_latents', 'sdfnmpc_sdf_eval', 'sdfnmpc_sdf_eval_host', 'sdfnmpc_solver_create',
             'sdfnmpc_solver_destroy', 'sdfnmpc_solver_init_traj', 'sdfnmpc_solver_shift', 'sdfnmpc_solver_rti_step',
             'sdfnmpc_solver_state', 'sdfnmpc_solver_diag', 'sdfnmpc_solver_qp_residual', 'sdfnmpc_solver_timing_begin', 'sdfnmpc_solver_timing_end', 'sdfnmpc_plant_step', 'sdfnmpc_cmd_trpyr', 'sdfnmpc_cmd_acc', 'sdfnmpc_cmd_props', 'sdfnmpc_solver_dims', 'sdfnmpc_solver_horizon', 'sdfnmpc_colcheck', 'sdfnmpc_df_signed', 'sdfnmpc_df_unsigned', 'sdfnmpc_fail_count_update',
@@ -101,6 +101,12 @@ def load():
     vp, i32, i64, dp, fp, ip = C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p
     lib.sdfnmpc_version.restype = C.c_char_p
     lib.sdfnmpc_launch_count.restype = C.c_uint64
+    lib.sdfnmpc_sizeof.argtypes, lib.sdfnmpc_sizeof.restype = [C.c_int32], C.c_int32
+    # the ctypes restatements of the descriptor structs must have the library's layout: refuse loudly otherwise
+    for which, cls in enumerate((SdfDesc, SolverDesc, EncoderDesc, EncoderWeights, DecoderDesc, DecoderWeights)):
+        if lib.sdfnmpc_sizeof(which) != C.sizeof(cls):
+            raise SdfNmpcError(f'{cls.__name__}: ctypes layout is {C.sizeof(cls)} bytes, {LIB_PATH} has {lib.sdfnmpc_sizeof(which)} '
+                               '(stale build? run `python -m sdf_nmpc_b200.build --force`)')
     lib.sdfnmpc_sdf_create.argtypes = [C.POINTER(vp), C.POINTER(SdfDesc)] + [fp] * 11
     lib.sdfnmpc_sdf_destroy.argtypes = [vp]
     lib.sdfnmpc_sdf_set_latents.argtypes = [vp, fp, i32, vp]

@@ -26,6 +26,17 @@ using namespace sdfnmpc;
 
 extern "C" const char* sdfnmpc_version(void) { return "sdfnmpc_b200 0.1 (sm_100a)"; }
 extern "C" uint64_t sdfnmpc_launch_count(void) { return g_launches.load(); }
+extern "C" int32_t sdfnmpc_sizeof(int32_t which) {
+    switch (which) {
+        case 0: return (int32_t)sizeof(sdfnmpc_sdf_desc);
+        case 1: return (int32_t)sizeof(sdfnmpc_solver_desc);
+        case 2: return (int32_t)sizeof(sdfnmpc_encoder_desc);
+        case 3: return (int32_t)sizeof(sdfnmpc_encoder_weights);
+        case 4: return (int32_t)sizeof(sdfnmpc_decoder_desc);
+        case 5: return (int32_t)sizeof(sdfnmpc_decoder_weights);
+        default: return -1;
+    }
+}
 
 static inline int pad8(int v) { return (v + 31) / 32 * 32; }   // every feature dimension is padded to the 32-wide tensor-core chunk
 

@@ -34,6 +34,29 @@ def test_library_exports_every_declared_symbol():
     assert lib.sdf_l4c_name_in(0) == b'i0' and lib.jac_sdf_l4c_name_in(1) == b'out_o0'
 
 
+def test_descriptor_layouts_agree_between_header_library_and_ctypes(tmp_path):
+    """The header compiles as plain C (gcc, no CUDA headers) and its descriptor structs have the size the library reports
+    (``sdfnmpc_sizeof``) and the size of the ctypes restatements in ``_lib.py`` - a binding with another layout would hand the
+    create functions garbage."""
+    import ctypes as C
+    import subprocess
+    from sdf_nmpc_b200 import _lib, build
+    build.build()
+    lib = _lib.load()
+    names = ['sdfnmpc_sdf_desc', 'sdfnmpc_solver_desc', 'sdfnmpc_encoder_desc', 'sdfnmpc_encoder_weights', 'sdfnmpc_decoder_desc',
+             'sdfnmpc_decoder_weights']
+    src = tmp_path / 'sizes.c'
+    src.write_text('#include <stdio.h>\n#include "sdfnmpc_b200.h"\nint main(void) { printf("' + ' '.join(['%zu'] * len(names)) + '\\n", '
+                   + ', '.join(f'sizeof({n})' for n in names) + '); return 0; }\n')
+    exe = tmp_path / 'sizes'
+    subprocess.run(['gcc', '-std=c99', '-Wall', '-Werror', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)], check=True)
+    c_sizes = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    py = (_lib.SdfDesc, _lib.SolverDesc, _lib.EncoderDesc, _lib.EncoderWeights, _lib.DecoderDesc, _lib.DecoderWeights)
+    for which, (n, cls) in enumerate(zip(names, py)):
+        assert c_sizes[which] == lib.sdfnmpc_sizeof(which) == C.sizeof(cls), (n, c_sizes[which], lib.sdfnmpc_sizeof(which), C.sizeof(cls))
+    assert lib.sdfnmpc_sizeof(6) == -1
+
+
 def test_sass_is_sm100a_only():
     import subprocess
     from sdf_nmpc_b200 import _lib
