@@ -514,8 +514,9 @@ def test_mission_flags_match_oracle(variant, cuda_device):
         assert float(lam_s[:, :, [1, 4]].abs().max()) < 1e-6
 
 
-@pytest.mark.parametrize('stability,slack_brake', [(False, (100.0, 10.0)), (True, (100.0, 10.0)), (True, None)])
-def test_terminal_ingredients_match_oracle(stability, slack_brake, cuda_device):
+@pytest.mark.parametrize('stability,slack_brake,flag', [(False, (100.0, 10.0), 1.0), (True, (100.0, 10.0), 1.0), (True, None, 1.0),
+                                                       (True, (100.0, 10.0), 0.0)])
+def test_terminal_ingredients_match_oracle(stability, slack_brake, flag, cuda_device):
     """flags.recursive_feasibility / flags.stability (gen_model.py:73-149) through the C ABI: the terminal sdf row is replaced by
     rec_feas, the FoV rows sit at the braking end point, stability adds the velocity box and the output flag * v.v.  The device
     lifts those rows onto auxiliary nodes (csrc/term_lift.cuh) with an exact L1 penalty for the hard ones; the oracle states
@@ -527,7 +528,7 @@ def test_terminal_ingredients_match_oracle(stability, slack_brake, cuda_device):
     B = 12
     net = synth.make_sdf_net(seed=0, **synth.ARCH_B, calibrated=True)
     ocfg = rti.default_cfg('att')
-    prob, w = make_problem(B, ocfg)
+    prob, w = make_problem(B, ocfg, flag=flag)
     vlim = [1.5, 1.5, 1.0]
     ocfg['term'] = dict(degree=4, coeffs=synth.braking_coeffs(4), slack_brake=slack_brake, stability=stability, vlim=vlim, vfov=True)
     yrefN, WN = w['yrefN'], w['WN']
@@ -544,7 +545,7 @@ def test_terminal_ingredients_match_oracle(stability, slack_brake, cuda_device):
     mpc = BatchedNmpc(cfg, net, B, cuda_device)
     N = mpc.N
     assert mpc.NI == N + (2 if stability else 1) and mpc.nyN == (5 if stability else 4)
-    mpc.set_sdf_flag(1.0)
+    mpc.set_sdf_flag(flag)
     mpc.set_latent(w['latent'], w['W_p_Bo'], w['W_R_Bo'])
     mpc.set_ref_arrays(w['yref'], w['W'], yrefN, WN, w['qd'])
     xb, ub = rti.init_traj(prob['x0'], ocfg)
@@ -562,10 +563,15 @@ def test_terminal_ingredients_match_oracle(stability, slack_brake, cuda_device):
         _, lam_s = mpc.get_multipliers()
         lam_s = lam_s.cpu().numpy()
         assert lam_s.shape == (B, mpc.NI + 1, 6)
-        assert np.abs(lam_s[:, N + 1, [2, 0, 1]] - out['lam_term_l'][:, :3]).max() < 1e-2
-        assert np.abs(lam_s[:, N + 1, [5, 3, 4]] - out['lam_term_u'][:, :3]).max() < 1e-2
+        # flag off: rec_feas is the constant max_df sitting ON its upper bound with a zero gradient - its multiplier is not determined
+        # by the QP (any value up to the slack weight is optimal; each interior point returns its own centre), so only the FoV rows count
+        rows_d, rows_o = ([2, 0, 1], [0, 1, 2]) if flag else ([0, 1], [1, 2])
+        assert np.abs(lam_s[:, N + 1, rows_d] - out['lam_term_l'][:, rows_o]).max() < 1e-2
+        assert np.abs(lam_s[:, N + 1, [r + 3 for r in rows_d]] - out['lam_term_u'][:, rows_o]).max() < 1e-2
         active = max(active, out['lam_term_l'].max(), out['lam_term_u'].max())
-    assert active > 1.0          # the terminal rows do bind in this sample
+    # the terminal rows do bind in this sample; with the flag off (gen_model.py:58-61, 85, 139-147) they are gated out: rec_feas = max_df,
+    # FoV angles 0, terminal outputs 0 - only the velocity box is left
+    assert active > 1.0 if flag else True
     # the flags change the problem: the plain OCP gives other controls
     ocfg0 = rti.default_cfg('att')
     prob0 = dict(prob, WN=w['WN'], yrefN=w['yrefN'])
