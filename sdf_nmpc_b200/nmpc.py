@@ -175,6 +175,7 @@ class BatchedNmpc:
         self.NI = self.N + self.lift                      # node stride of the library's own arrays (sdfnmpc_solver_horizon)
         self.handle = C.c_void_p()
         _lib.check(self.lib.sdfnmpc_solver_create(C.byref(self.handle), C.byref(d), self.sdf.handle), 'sdfnmpc_solver_create')
+        self._desc = d                                    # the descriptor this handle was built from (diagnostics, tests)
         # command clipping (controller.py:18-26)
         self.cmd_acc_hover = np.array([0, 0, 0, 0])
         self.cmd_acc_min = [-lim.ax, -lim.ay, -lim.az, -lim.wz]
