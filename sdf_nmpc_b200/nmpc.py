@@ -45,6 +45,23 @@ def braking_coeffs(cfg):
     return deg, co
 
 
+def r_tilde_ratio(T, phi, theta, r1, r2, r3, dt, g=9.81):
+    """The expression ``utils/stability.py:6-42`` derives with sympy (smallest ``r_tilde`` with ``U~' (r_tilde I) U~ >= U' R U``, ``U = [T - g,
+    phi, theta]``, ``U~ = dt (T R e3 - g e3)`` at zero yaw): input cost over the squared velocity change of one step.  Pinned to the
+    reference's own symbolic result in ``tests/golden/stability.npz``."""
+    num = r1 * (T - g) ** 2 + r2 * phi ** 2 + r3 * theta ** 2
+    den = dt ** 2 * (T ** 2 - 2.0 * T * g * np.cos(phi) * np.cos(theta) + g ** 2)
+    return num, den
+
+
+def stability_r_tilde(w, lim, dt, g=9.81):
+    """``get_r_tilde_max`` (``utils/stability.py:45-75``): the largest ``r_tilde_ratio`` over the input box ``[0, gamma] x [-roll, roll] x
+    [-pitch, pitch]`` - a dense grid here, SLSQP from a random start in the reference."""
+    T, ph, th = np.meshgrid(np.linspace(0, lim.gamma, 161), np.linspace(-lim.roll, lim.roll, 41), np.linspace(-lim.pitch, lim.pitch, 41), indexing='ij')
+    num, den = r_tilde_ratio(T, ph, th, w.acc, w.att[0], w.att[1], dt, g)
+    return float(np.max(np.where(den > 1e-9, num / np.maximum(den, 1e-9), 0.0)))
+
+
 def stability_p_term(cfg, g=9.81):
     """Terminal weight ``p_term`` of ``gen_model.py:121-147`` (upper bound of the stage cost over the braking manoeuvre).
     ``r_tilde`` (``utils/stability.py:6-75``) is the largest ratio input cost / (dt^2 |T R e3 - g e3|^2 ) over the input box - the
@@ -62,11 +79,7 @@ def stability_p_term(cfg, g=9.81):
     max_att_error = float(max_att @ np.diag(list(w.att[:2]) + list(w.rates[2:])) @ max_att)
     max_thrust_error = max(w.acc * (lim.gamma - g) ** 2, w.acc * g ** 2)
     sc_max = max_vel_error + max_att_error + max_thrust_error
-    T, ph, th = np.meshgrid(np.linspace(0, lim.gamma, 81), np.linspace(-lim.roll, lim.roll, 41), np.linspace(-lim.pitch, lim.pitch, 41), indexing='ij')
-    Ut = np.stack([T * np.sin(th) * np.cos(ph), -T * np.sin(ph), T * np.cos(th) * np.cos(ph) - g], -1) * dt
-    num = w.acc * (T - g) ** 2 + w.att[0] * ph ** 2 + w.att[1] * th ** 2
-    den = (Ut ** 2).sum(-1)
-    r_tilde = float(np.max(np.where(den > 1e-9, num / np.maximum(den, 1e-9), 0.0)))
+    r_tilde = stability_r_tilde(w, lim, dt, g)
     return max(r_tilde + max_vel_error, sc_max / m.stability.a_b_min ** 2 / dt ** 2)
 
 

@@ -347,6 +347,25 @@ def refgen_case():
     print('refgen: cases', len(out))
 
 
+def stability_case():
+    """``utils/stability.py:6-42``: the reference's symbolic r_tilde expression evaluated at seeded points of the input box."""
+    import importlib.util
+    import sympy
+    spec = importlib.util.spec_from_file_location('ref_stability', '/root/reference/sdf_nmpc/utils/stability.py')
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    expr = mod.symbolic_r_tilde()
+    f = sympy.lambdify(sympy.symbols('T phi theta g m dt r_1 r_2 r_3'), expr, 'numpy')
+    rng = np.random.default_rng(21)
+    n = 64
+    T, phi, theta = rng.uniform(0.0, 20.0, n), rng.uniform(-0.7, 0.7, n), rng.uniform(-0.7, 0.7, n)
+    r = rng.uniform(0.01, 60.0, (3, n))
+    dt = rng.uniform(0.01, 0.1, n)
+    val = np.array([float(f(T[i], phi[i], theta[i], 9.81, 1.0, dt[i], r[0, i], r[1, i], r[2, i])) for i in range(n)])
+    np.savez_compressed(os.path.join(HERE, 'stability.npz'), T=T, phi=phi, theta=theta, r=r, dt=dt, r_tilde=val, expr=str(expr))
+    print('stability: r_tilde range', val.min(), val.max())
+
+
 if __name__ == '__main__':
     torch.manual_seed(0)
     torch.set_num_threads(4)
@@ -362,4 +381,5 @@ if __name__ == '__main__':
     model_variants_case()
     model_props_case()
     refgen_case()
+    stability_case()
     encoder_case()
