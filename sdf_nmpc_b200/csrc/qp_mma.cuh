@@ -380,7 +380,8 @@ __device__ void qp_solve_mma(const Lanes& L, const QpProb<10, 4, 11, 3>& P, doub
                 l = fmax(0.5 * (z + Z * s0), 1e-3);
                 m = l;
                 // lifted rows (exact-penalty weight z_hard): row multiplier capped, the rest to the slack's multiplier (qp_core.cuh)
-                if ((LIFT || SDFNMPC_QP_LCAP_ALL) && l > SDFNMPC_QP_LCAP) { l = SDFNMPC_QP_LCAP; m = z + Z * s0 - l; }
+                constexpr double lcap = LIFT ? SDFNMPC_QP_LCAP_LIFT : SDFNMPC_QP_LCAP;
+                if ((LIFT || SDFNMPC_QP_LCAP_ALL) && l > lcap) { l = lcap; m = z + Z * s0 - l; }
             }
             ts[a] = t; ss[a] = s0; ls[a] = l; ms[a] = m;
         }
