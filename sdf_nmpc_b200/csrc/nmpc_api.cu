@@ -246,18 +246,20 @@ __global__ void nmpc_cmd_props_kernel(double wp_max, int B, const double* __rest
     if (i < B * NU) cmd[i] = fmin(fmax(u[i] * wp_max, 0.0), wp_max);
 }
 
-// auxiliary stages / nodes of the lifted terminal rows: one thread per instance (ten dual-number evaluations of two FoV rows),
-// launched as one-warp CTAs so that 4096 instances spread over 128 SMs instead of 32
+// auxiliary stages / nodes of the lifted terminal rows: one thread per (instance, state direction) - ten dual-number evaluations of the
+// two FoV rows and the braking polynomial per instance, side by side (one thread per instance took 0.10 ms per 4096, section 10 of
+// profiles/r2_ncu_summary.md)
 __global__ void nmpc_term_lift_kernel(ModelConst mc, TermConst tc, int N, int NR, int B, const double* __restrict__ pose,
                                       const double* __restrict__ flag, double max_df, const float* __restrict__ sdf_d,
                                       const float* __restrict__ sdf_g, double* __restrict__ xbar, double* __restrict__ AB,
                                       double* __restrict__ bdyn, double* __restrict__ C, double* __restrict__ hval, double* __restrict__ ABt) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = gid / NX, d = gid - b * NX;
     if (b >= B) return;
-    term_lift_instance(mc, tc, N, NR, pose + (size_t)b * 12, flag[b], max_df, sdf_d[(size_t)b * (N + 1) + NR],
-                       sdf_g + ((size_t)b * (N + 1) + NR) * 3, xbar + (size_t)b * (N + 1) * NX, AB + (size_t)b * N * NX * NW,
-                       bdyn + (size_t)b * N * NX, C + (size_t)b * (N + 1) * NH * NW, hval + (size_t)b * (N + 1) * NH,
-                       ABt ? ABt + (size_t)b * N * 192 : nullptr);
+    term_lift_dir(mc, tc, N, NR, pose + (size_t)b * 12, flag[b], max_df, sdf_d[(size_t)b * (N + 1) + NR],
+                  sdf_g + ((size_t)b * (N + 1) + NR) * 3, xbar + (size_t)b * (N + 1) * NX, AB + (size_t)b * N * NX * NW,
+                  bdyn + (size_t)b * N * NX, C + (size_t)b * (N + 1) * NH * NW, hval + (size_t)b * (N + 1) * NH,
+                  ABt ? ABt + (size_t)b * N * 192 : nullptr, d);
 }
 
 extern "C" int sdfnmpc_solver_create(sdfnmpc_solver_t* out, const sdfnmpc_solver_desc* d, sdfnmpc_sdf_t sdf) {
@@ -464,7 +466,7 @@ extern "C" int sdfnmpc_solver_rti_step(sdfnmpc_solver_t h, int32_t B, const doub
     if (int rc = sdfnmpc_sdf_eval(h->sdf, h->qpts, nullptr, N + 1, (int64_t)B * (N + 1), h->sdf_d, h->sdf_g, stream)) return rc;
     const int lift = h->tc.n_lift;
     if (lift) {
-        nmpc_term_lift_kernel<<<(B + 31) / 32, 32, 0, st>>>(h->sc.mc, h->tc, N, h->sc.n_real, B, pose, flag, (double)h->sdf->net.max_df,
+        nmpc_term_lift_kernel<<<(B * NX + 127) / 128, 128, 0, st>>>(h->sc.mc, h->tc, N, h->sc.n_real, B, pose, flag, (double)h->sdf->net.max_df,
                                                              h->sdf_d, h->sdf_g, h->xbar, h->AB, h->bdyn, h->C, h->hval, h->ABt);
         count_launch();
         SDF_CUDA_CHECK(cudaGetLastError());
